@@ -1,0 +1,193 @@
+/*
+ * minotert.h -- C ABI of the B200-native MinoteRT ray-tracing hot path (libminotert.so).
+ *
+ * This is the drop-in boundary: the entry points a maintainer of Tearnote/MinoteRT would bind
+ * in place of the vuk/Vulkan dispatches recorded by src/gfx/modules/{pathtracer,sky,tonemapper}.ixx.
+ * Plain pointers and sizes only; no exceptions cross the seam.  Every function returns
+ * MRT_OK (0) or a negative mrt_status; mrt_last_error() gives the sticky message.
+ *
+ * Threading: one host thread per context (the reference is single-threaded, src/main.cpp:20);
+ * distinct contexts may be driven from distinct threads.  All work is stream-ordered on the
+ * context's CUDA stream; only mrt_sync / mrt_readback / mrt_stats block.
+ *
+ * Ownership: the context owns all device memory.  Host pointers passed in are consumed before
+ * the call returns.  Device pointers from mrt_buffer are BORROWED: valid until the next call
+ * that (re)renders that buffer at a different size, or mrt_destroy.
+ *
+ * There is no CPU fallback: without a CUDA device mrt_create fails with MRT_ERR_CUDA.
+ */
+#ifndef MINOTERT_H
+#define MINOTERT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRT_ABI_VERSION 1
+#define MRT_MISS_ID 0xFFFFFFFFu /* primaryRay.comp:25 `-1u` */
+
+typedef enum {
+    MRT_OK = 0,
+    MRT_ERR_INVALID = -1, /* bad argument / call order */
+    MRT_ERR_CUDA = -2,    /* CUDA runtime error (context is poisoned) */
+    MRT_ERR_OOM = -3,
+    MRT_ERR_STATE = -4    /* required input (scene, LUTs, blue noise, G-buffer) missing */
+} mrt_status;
+
+typedef struct mrt_context mrt_context;
+
+/* ---- PODs: the binary host<->device contract of the reference ---- */
+
+/* column-major, m[col][row]  (src/stx/math.ixx:531-539) */
+typedef struct { float m[4][4]; } mrt_mat4;
+
+/* UBO of primaryRay.comp:14-21, filled at src/gfx/modules/pathtracer.ixx:94-104 */
+typedef struct {
+    mrt_mat4 view, projection, invView, invProjection, prevView;
+    uint32_t frameCounter;
+} mrt_primary_constants;
+
+/* UBO of secondaryRays.comp:25-32, filled at src/gfx/modules/pathtracer.ixx:178-188 */
+typedef struct {
+    mrt_mat4 view, projection, invView, invProjection;
+    float cameraPos[3];
+    uint32_t frameCounter;
+} mrt_secondary_constants;
+
+/* src/gpu/intersect.glsl:9-13 */
+typedef struct { float center[3]; float radius; float albedo[3]; } mrt_sphere;
+
+/* Atmosphere::Params, std140 mirror, 144 bytes (src/gfx/modules/sky.ixx:28-56) */
+typedef struct {
+    float bottomRadius, topRadius, rayleighDensityExpScale, _pad0;
+    float rayleighScattering[3]; float mieDensityExpScale;
+    float mieScattering[3]; float _pad1;
+    float mieExtinction[3]; float _pad2;
+    float mieAbsorption[3]; float miePhaseG;
+    float absorptionDensity0LayerWidth, absorptionDensity0ConstantTerm,
+          absorptionDensity0LinearTerm, absorptionDensity1ConstantTerm;
+    float absorptionDensity1LinearTerm, _pad3, _pad4, _pad5;
+    float absorptionExtinction[3]; float _pad6;
+    float groundAlbedo[3]; float _pad7;
+} mrt_atmosphere_params;
+
+/* Tonemapper::<op> selector, same order as Renderer_impl::tonemap (src/gfx/renderer.ixx:165-172) */
+typedef enum {
+    MRT_TONEMAP_LINEAR = 0, MRT_TONEMAP_REINHARD = 1, MRT_TONEMAP_HABLE = 2,
+    MRT_TONEMAP_ACES = 3, MRT_TONEMAP_UCHIMURA = 4, MRT_TONEMAP_AMD = 5
+} mrt_tonemap_mode;
+
+typedef enum {
+    MRT_BUF_VISIBILITY = 0, /* R32_UINT   4 B/px  (pathtracer.ixx:42-48)  */
+    MRT_BUF_DEPTH = 1,      /* R16F       2 B/px  (pathtracer.ixx:49-55)  */
+    MRT_BUF_NORMAL = 2,     /* RGBA16F    8 B/px  (pathtracer.ixx:56-62)  */
+    MRT_BUF_MOTION = 3,     /* RG16F      4 B/px  (pathtracer.ixx:63-69)  */
+    MRT_BUF_COLOR = 4,      /* RGBA16F    8 B/px  (pathtracer.ixx:139-145): frame average   */
+    MRT_BUF_ACCUM = 5,      /* RGBA32F   16 B/px  progressive sum, .w = samples (row n7)    */
+    MRT_BUF_LDR = 6,        /* RGBA8      4 B/px  (tonemapper.ixx:332) output framebuffer   */
+    MRT_BUF_TRANSMITTANCE = 7,   /* RGBA16F 256x64 (sky.ixx:22-23)   */
+    MRT_BUF_MULTISCATTERING = 8, /* RGBA16F 32x32  (sky.ixx:25-26)   */
+    MRT_BUF_SKY_VIEW = 9,        /* B10G11R11 192x108 (sky.ixx:187-188) */
+    MRT_BUF_HIT_T = 10,          /* R32F 4 B/px primary hit distance (triangle scenes) */
+    MRT_BUF_COUNT_
+} mrt_buffer_id;
+
+typedef enum {
+    MRT_BUILD_FULL = 0, /* Morton sort + LBVH + wide-node collapse */
+    MRT_BUILD_REFIT = 1 /* keep topology, recompute boxes after mrt_scene_update_positions */
+} mrt_build_mode;
+
+/* mrt_secondary_rays flags */
+#define MRT_SECONDARY_ACCUMULATE 1u /* add to MRT_BUF_ACCUM instead of restarting it */
+#define MRT_SECONDARY_SORT_RAYS 2u  /* sort each bounce's ray queue by (origin cell, octant) */
+
+typedef struct {
+    uint64_t primary_rays;   /* rays traced by the last mrt_primary_rays */
+    uint64_t secondary_rays; /* rays traced by the last mrt_secondary_rays */
+    float ms_primary;        /* device time of the last call of each kind (CUDA events) */
+    float ms_secondary;
+    float ms_trace;          /* traversal kernels only, inside the last mrt_secondary_rays */
+    float ms_tonemap;
+    float ms_build;
+    float ms_sky;
+    uint32_t kernel_launches; /* kernels launched by this context since mrt_stats_reset */
+    uint32_t stack_overflows; /* traversal stack overflow events (must be 0) */
+    uint32_t num_triangles;
+    uint32_t num_wide_nodes;
+    uint64_t bvh_bytes;       /* wide nodes + reordered triangles resident in HBM */
+    uint64_t node_visits;     /* wide nodes fetched / triangles tested by the last counted trace */
+    uint64_t tri_tests;       /*   (only when mrt_set_option("count_visits", 1))            */
+} mrt_stats;
+
+/* ---- lifetime ---- */
+int mrt_abi_version(void);
+/* device: CUDA ordinal.  Replaces Vulkan::Provider + lazy pipeline creation
+ * (src/sys/vulkan.ixx:106-115, pathtracer.ixx:30-39). */
+int mrt_create(int device, mrt_context** out);
+void mrt_destroy(mrt_context* ctx);
+/* Sticky message of the last failure on this context (ctx may be NULL: last mrt_create error). */
+const char* mrt_last_error(const mrt_context* ctx);
+/* name: "count_visits" (0/1), "sort_rays" (0/1), "persistent" (0/1), "stack_sm" ... */
+int mrt_set_option(mrt_context* ctx, const char* name, int64_t value);
+
+/* ---- inputs ---- */
+/* RGBA8 blue-noise texture (Renderer_impl ctor, src/gfx/renderer.ixx:101-110) */
+int mrt_upload_blue_noise(mrt_context* ctx, const uint8_t* rgba8, uint32_t w, uint32_t h);
+/* The scene of src/gpu/scene.glsl:4-11 as data (n <= 16).  Selects the sphere path. */
+int mrt_scene_set_spheres(mrt_context* ctx, const mrt_sphere* spheres, uint32_t n);
+/* Indexed triangle mesh, primitive id = triangle index in upload order; albedo: 3 floats per
+ * triangle.  Selects the triangle path (north_star rows n1-n7).  Call mrt_scene_build next. */
+int mrt_scene_upload_mesh(mrt_context* ctx, const float* positions, uint32_t nverts,
+                          const uint32_t* indices, uint32_t ntris, const float* albedo);
+/* New vertex positions for the uploaded topology (animated scenes); then build FULL or REFIT. */
+int mrt_scene_update_positions(mrt_context* ctx, const float* positions, uint32_t nverts);
+int mrt_scene_build(mrt_context* ctx, int build_mode);
+
+/* ---- sky (src/gfx/modules/sky.ixx) ---- */
+/* Atmosphere(allocator, params): transmittance + multi-scattering LUTs (sky.ixx:91-176) */
+int mrt_atmosphere(mrt_context* ctx, const mrt_atmosphere_params* params);
+/* Sky::createView(atmo, probePos) with the push constants of sky.ixx:239-250 */
+int mrt_sky_view(mrt_context* ctx, const float probePos[3], const float sunDirection[3],
+                 const float sunIlluminance[3]);
+
+/* ---- partition (multi-GPU tile mode; default rank 0 of 1) ----
+ * Image rows are grouped into slabs of slab_rows rows; slab j belongs to rank j % nranks.
+ * A context renders only its own slabs, stored compactly (slab-major) in its buffers. */
+int mrt_set_partition(mrt_context* ctx, uint32_t rank, uint32_t nranks, uint32_t slab_rows);
+/* rows of the full image owned by this context, in local storage order */
+int mrt_partition_rows(const mrt_context* ctx, uint32_t full_h, uint32_t* rows_out,
+                       uint32_t* nrows_out);
+
+/* ---- per-frame render calls, in the order of Renderer_impl::draw (renderer.ixx:56-62) ---- */
+/* Pathtracer::primaryRays(size, camera, prevCamera) -> GBuffer (pathtracer.ixx:29-116) */
+int mrt_primary_rays(mrt_context* ctx, uint32_t w, uint32_t h, const mrt_primary_constants* c);
+/* Pathtracer::secondaryRays(gbuffer, camera, atmo, skyView, blueNoise) (pathtracer.ixx:118-195).
+ * The reference hard-codes spp = 8, bounces = 8 (secondaryRays.comp:128-129). */
+int mrt_secondary_rays(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp,
+                       uint32_t bounces, uint32_t flags);
+/* Tonemapper::{linear,reinhard,hable,aces,uchimura,amd}(input, exposure, params)
+ * (tonemapper.ixx:57-373).  source: MRT_BUF_COLOR (reference path) or MRT_BUF_ACCUM
+ * (progressive average).  params: the push constants after `exposure`. */
+int mrt_tonemap(mrt_context* ctx, int mode, float exposure, const float* params, uint32_t nparams,
+                int source);
+
+/* ---- outputs ---- */
+int mrt_buffer(mrt_context* ctx, int buffer_id, void** device_ptr, size_t* bytes);
+int mrt_readback(mrt_context* ctx, int buffer_id, void* host, size_t bytes);
+int mrt_sync(mrt_context* ctx);
+int mrt_stats_get(mrt_context* ctx, mrt_stats* out);
+int mrt_stats_reset(mrt_context* ctx);
+/* raw CUDA stream (cudaStream_t) of the context, for callers that enqueue collectives */
+int mrt_stream(mrt_context* ctx, void** stream_out);
+
+/* ---- closest-hit query (tests / tools): traces n rays through the built scene ---- */
+int mrt_trace_rays(mrt_context* ctx, const float* origins, const float* directions, uint32_t n,
+                   uint32_t* prim_ids, float* t, int brute_force);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINOTERT_H */

@@ -1,0 +1,259 @@
+"""ctypes binding of libminotert.so -- the C ABI declared in include/minotert.h.
+
+This is a thin binding, not an implementation: every render call lands in the CUDA library.
+There is no CPU fallback; if the library is missing or no CUDA device exists the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libminotert.so")
+
+MISS_ID = 0xFFFFFFFF
+(BUF_VISIBILITY, BUF_DEPTH, BUF_NORMAL, BUF_MOTION, BUF_COLOR, BUF_ACCUM, BUF_LDR, BUF_TRANSMITTANCE,
+ BUF_MULTISCATTERING, BUF_SKY_VIEW, BUF_HIT_T) = range(11)
+BUILD_FULL, BUILD_REFIT = 0, 1
+SECONDARY_ACCUMULATE, SECONDARY_SORT_RAYS = 1, 2
+TONEMAP = {"linear": 0, "reinhard": 1, "hable": 2, "aces": 3, "uchimura": 4, "amd": 5}
+
+
+class Mat4(C.Structure):
+    _fields_ = [("m", (C.c_float * 4) * 4)]
+
+
+class PrimaryConstants(C.Structure):
+    _fields_ = [("view", Mat4), ("projection", Mat4), ("invView", Mat4), ("invProjection", Mat4),
+                ("prevView", Mat4), ("frameCounter", C.c_uint32)]
+
+
+class SecondaryConstants(C.Structure):
+    _fields_ = [("view", Mat4), ("projection", Mat4), ("invView", Mat4), ("invProjection", Mat4),
+                ("cameraPos", C.c_float * 3), ("frameCounter", C.c_uint32)]
+
+
+class Sphere(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("radius", C.c_float), ("albedo", C.c_float * 3)]
+
+
+class AtmosphereParams(C.Structure):
+    _fields_ = [("raw", C.c_float * 36)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("primary_rays", C.c_uint64), ("secondary_rays", C.c_uint64), ("ms_primary", C.c_float),
+                ("ms_secondary", C.c_float), ("ms_trace", C.c_float), ("ms_tonemap", C.c_float),
+                ("ms_build", C.c_float), ("ms_sky", C.c_float), ("kernel_launches", C.c_uint32),
+                ("stack_overflows", C.c_uint32), ("num_triangles", C.c_uint32), ("num_wide_nodes", C.c_uint32),
+                ("bvh_bytes", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64)]
+
+
+EXPORTS = [
+    "mrt_abi_version", "mrt_create", "mrt_destroy", "mrt_last_error", "mrt_set_option", "mrt_upload_blue_noise",
+    "mrt_scene_set_spheres", "mrt_scene_upload_mesh", "mrt_scene_update_positions", "mrt_scene_build",
+    "mrt_atmosphere", "mrt_sky_view", "mrt_set_partition", "mrt_partition_rows", "mrt_primary_rays",
+    "mrt_secondary_rays", "mrt_tonemap", "mrt_buffer", "mrt_readback", "mrt_sync", "mrt_stats_get",
+    "mrt_stats_reset", "mrt_stream", "mrt_trace_rays",
+]
+
+
+class MinoteError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libminotert.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MinoteError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C minotert_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, f32p = C.c_void_p, C.c_uint32, C.POINTER(C.c_float)
+    L.mrt_abi_version.restype = C.c_int
+    L.mrt_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.mrt_destroy.argtypes = [vp]
+    L.mrt_destroy.restype = None
+    L.mrt_last_error.argtypes = [vp]
+    L.mrt_last_error.restype = C.c_char_p
+    L.mrt_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.mrt_upload_blue_noise.argtypes = [vp, vp, u32, u32]
+    L.mrt_scene_set_spheres.argtypes = [vp, vp, u32]
+    L.mrt_scene_upload_mesh.argtypes = [vp, vp, u32, vp, u32, vp]
+    L.mrt_scene_update_positions.argtypes = [vp, vp, u32]
+    L.mrt_scene_build.argtypes = [vp, C.c_int]
+    L.mrt_atmosphere.argtypes = [vp, vp]
+    L.mrt_sky_view.argtypes = [vp, f32p, f32p, f32p]
+    L.mrt_set_partition.argtypes = [vp, u32, u32, u32]
+    L.mrt_partition_rows.argtypes = [vp, u32, vp, C.POINTER(u32)]
+    L.mrt_primary_rays.argtypes = [vp, u32, u32, vp]
+    L.mrt_secondary_rays.argtypes = [vp, vp, u32, u32, u32]
+    L.mrt_tonemap.argtypes = [vp, C.c_int, C.c_float, f32p, u32, C.c_int]
+    L.mrt_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mrt_readback.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.mrt_sync.argtypes = [vp]
+    L.mrt_stats_get.argtypes = [vp, C.POINTER(Stats)]
+    L.mrt_stats_reset.argtypes = [vp]
+    L.mrt_stream.argtypes = [vp, C.POINTER(vp)]
+    L.mrt_trace_rays.argtypes = [vp, vp, vp, u32, vp, vp, C.c_int]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("mrt_destroy", "mrt_last_error"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class Context:
+    """One mrt_context: device memory, stream and scene state on one GPU."""
+
+    _DTYPES = {BUF_VISIBILITY: (np.uint32, 1), BUF_DEPTH: (np.uint16, 1), BUF_NORMAL: (np.uint16, 4),
+               BUF_MOTION: (np.uint16, 2), BUF_COLOR: (np.uint16, 4), BUF_ACCUM: (np.float32, 4),
+               BUF_LDR: (np.uint8, 4), BUF_HIT_T: (np.float32, 1)}
+
+    def __init__(self, device=0):
+        self.L = load()
+        self.h = C.c_void_p()
+        s = self.L.mrt_create(device, C.byref(self.h))
+        if s != 0:
+            raise MinoteError(f"mrt_create({device}) failed ({s}): {self.L.mrt_last_error(None).decode()}")
+        self.device = device
+        self.size = (0, 0)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mrt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, s):
+        if s != 0:
+            raise MinoteError(f"minotert error {s}: {self.L.mrt_last_error(self.h).decode()}")
+
+    # ---- inputs
+    def set_option(self, name, value):
+        self._ck(self.L.mrt_set_option(self.h, name.encode(), int(value)))
+
+    def upload_blue_noise(self, rgba8):
+        a = np.ascontiguousarray(rgba8, np.uint8)
+        self._ck(self.L.mrt_upload_blue_noise(self.h, _ptr(a), a.shape[1], a.shape[0]))
+
+    def set_spheres(self, spheres):
+        arr = (Sphere * max(1, len(spheres)))()
+        for i, (c, r, al) in enumerate(spheres):
+            arr[i].center[:] = c
+            arr[i].radius = r
+            arr[i].albedo[:] = al
+        self._ck(self.L.mrt_scene_set_spheres(self.h, C.cast(arr, C.c_void_p), len(spheres)))
+
+    def upload_mesh(self, positions, indices, albedo):
+        p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        i = np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
+        a = np.ascontiguousarray(albedo, np.float32).reshape(-1, 3)
+        assert a.shape[0] == i.shape[0]
+        self._ck(self.L.mrt_scene_upload_mesh(self.h, _ptr(p), p.shape[0], _ptr(i), i.shape[0], _ptr(a)))
+
+    def update_positions(self, positions):
+        p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        self._ck(self.L.mrt_scene_update_positions(self.h, _ptr(p), p.shape[0]))
+
+    def build(self, mode=BUILD_FULL):
+        self._ck(self.L.mrt_scene_build(self.h, mode))
+
+    def atmosphere(self, params):
+        self._ck(self.L.mrt_atmosphere(self.h, C.cast(C.byref(params), C.c_void_p)))
+
+    def sky_view(self, probe_pos, sun_dir, sun_ill):
+        self._ck(self.L.mrt_sky_view(self.h, _f3(probe_pos), _f3(sun_dir), _f3(sun_ill)))
+
+    def set_partition(self, rank, nranks, slab_rows=8):
+        self._ck(self.L.mrt_set_partition(self.h, rank, nranks, slab_rows))
+
+    def partition_rows(self, full_h):
+        n = C.c_uint32()
+        self._ck(self.L.mrt_partition_rows(self.h, full_h, None, C.byref(n)))
+        rows = np.zeros(n.value, np.uint32)
+        self._ck(self.L.mrt_partition_rows(self.h, full_h, _ptr(rows), C.byref(n)))
+        return rows
+
+    # ---- render calls
+    def primary_rays(self, w, h, pc):
+        self._ck(self.L.mrt_primary_rays(self.h, w, h, C.cast(C.byref(pc), C.c_void_p)))
+        self.size = (w, h)
+
+    def secondary_rays(self, sc, spp=8, bounces=8, flags=0):
+        self._ck(self.L.mrt_secondary_rays(self.h, C.cast(C.byref(sc), C.c_void_p), spp, bounces, flags))
+
+    def tonemap(self, mode="amd", exposure=1.0, params=(16.0, 2.0, 1.0, 0.18, 0.18), source=BUF_COLOR):
+        par = (C.c_float * 8)(*params)
+        m = TONEMAP[mode] if isinstance(mode, str) else int(mode)
+        self._ck(self.L.mrt_tonemap(self.h, m, exposure, par, len(params), source))
+
+    # ---- outputs
+    def sync(self):
+        self._ck(self.L.mrt_sync(self.h))
+
+    def buffer(self, buf):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.L.mrt_buffer(self.h, buf, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def readback(self, buf, out=None):
+        _, nbytes = self.buffer(buf)
+        if buf in self._DTYPES:
+            dt, ch = self._DTYPES[buf]
+            n = nbytes // (np.dtype(dt).itemsize * ch)
+            w = self.size[0]
+            shape = (n // w, w, ch) if ch > 1 else (n // w, w)
+        elif buf == BUF_SKY_VIEW:
+            dt, shape = np.uint32, (108, 192)
+        elif buf == BUF_TRANSMITTANCE:
+            dt, shape = np.uint16, (64, 256, 4)
+        else:
+            dt, shape = np.uint16, (32, 32, 4)
+        if out is None:
+            out = np.empty(shape, dt)
+        self._ck(self.L.mrt_readback(self.h, buf, _ptr(out), nbytes))
+        return out
+
+    def readback_into(self, buf, host_ptr, nbytes):
+        self._ck(self.L.mrt_readback(self.h, buf, host_ptr, nbytes))
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.L.mrt_stats_get(self.h, C.byref(s)))
+        return s
+
+    def stats_reset(self):
+        self._ck(self.L.mrt_stats_reset(self.h))
+
+    def stream(self):
+        p = C.c_void_p()
+        self._ck(self.L.mrt_stream(self.h, C.byref(p)))
+        return p.value
+
+    def trace_rays(self, origins, directions, brute_force=False):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+        ids = np.empty(o.shape[0], np.uint32)
+        t = np.empty(o.shape[0], np.float32)
+        self._ck(self.L.mrt_trace_rays(self.h, _ptr(o), _ptr(d), o.shape[0], _ptr(ids), _ptr(t), int(brute_force)))
+        return ids, t

@@ -1,0 +1,382 @@
+// api.cu -- the extern "C" entry points declared in include/minotert.h.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "context.cuh"
+
+static char g_create_error[512] = "";
+
+int mrt_fail(mrt_context* ctx, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    char* dst = ctx ? ctx->err : g_create_error;
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    if (ctx && code == MRT_ERR_CUDA) ctx->poisoned = true;
+    return code;
+}
+
+int mrt_check_cuda(mrt_context* ctx, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return MRT_OK;
+    return mrt_fail(ctx, e == cudaErrorMemoryAllocation ? MRT_ERR_OOM : MRT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define MRT_ENTER(ctx)                                                                        \
+    do {                                                                                      \
+        if (!(ctx)) return MRT_ERR_INVALID;                                                   \
+        if ((ctx)->poisoned) return MRT_ERR_CUDA;                                             \
+        cudaError_t _e = cudaSetDevice((ctx)->device);                                        \
+        if (_e != cudaSuccess) return mrt_check_cuda((ctx), _e, "cudaSetDevice");             \
+    } while (0)
+
+namespace {
+
+__global__ void k_accum_to_color16(const float4* __restrict__ accum, uint2* __restrict__ color16, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = accum[i];
+    float3 c = a.w > 0.0f ? f3(a.x / a.w, a.y / a.w, a.z / a.w) : f3s(0.0f);
+    uint2 pk;
+    pk.x = (uint32_t)f32_to_f16_bits(c.x) | ((uint32_t)f32_to_f16_bits(c.y) << 16);
+    pk.y = (uint32_t)f32_to_f16_bits(c.z) | (0x3C00u << 16);
+    color16[i] = pk;
+}
+
+int buffer_info(mrt_context* ctx, int id, void** p, size_t* bytes) {
+    const size_t n = ctx->npix;
+    switch (id) {
+    case MRT_BUF_VISIBILITY: if (!ctx->have_gbuffer) break; *p = ctx->visibility.p; *bytes = n * 4; return MRT_OK;
+    case MRT_BUF_DEPTH: if (!ctx->have_gbuffer) break; *p = ctx->depth.p; *bytes = n * 2; return MRT_OK;
+    case MRT_BUF_NORMAL: if (!ctx->have_gbuffer) break; *p = ctx->normal.p; *bytes = n * 8; return MRT_OK;
+    case MRT_BUF_MOTION: if (!ctx->have_gbuffer) break; *p = ctx->motion.p; *bytes = n * 4; return MRT_OK;
+    case MRT_BUF_COLOR:
+        if (!ctx->have_accum) break;
+        if (!ctx->have_color) {  // triangle path: resolve the accumulator into the reference's RGBA16F image
+            k_accum_to_color16<<<div_up(n, 256), 256, 0, ctx->stream>>>(ctx->accum.p, reinterpret_cast<uint2*>(ctx->color16.p), n);
+            MRT_LAUNCHED(ctx);
+            ctx->have_color = true;
+        }
+        *p = ctx->color16.p; *bytes = n * 8; return MRT_OK;
+    case MRT_BUF_ACCUM: if (!ctx->have_accum) break; *p = ctx->accum.p; *bytes = n * 16; return MRT_OK;
+    case MRT_BUF_LDR: if (!ctx->have_ldr) break; *p = ctx->ldr.p; *bytes = n * 4; return MRT_OK;
+    case MRT_BUF_TRANSMITTANCE: if (!ctx->have_atmo) break; *p = ctx->trans16.p; *bytes = (size_t)MRT_TRANS_W * MRT_TRANS_H * 8; return MRT_OK;
+    case MRT_BUF_MULTISCATTERING: if (!ctx->have_atmo) break; *p = ctx->multi16.p; *bytes = (size_t)MRT_MULTI_W * MRT_MULTI_H * 8; return MRT_OK;
+    case MRT_BUF_SKY_VIEW: if (!ctx->have_view) break; *p = ctx->view_packed.p; *bytes = (size_t)MRT_VIEW_W * MRT_VIEW_H * 4; return MRT_OK;
+    case MRT_BUF_HIT_T: if (!ctx->have_gbuffer || ctx->scene_kind != 2) break; *p = ctx->hit_t.p; *bytes = n * 4; return MRT_OK;
+    default: return mrt_fail(ctx, MRT_ERR_INVALID, "unknown buffer id %d", id);
+    }
+    return mrt_fail(ctx, MRT_ERR_STATE, "buffer %d has not been rendered yet", id);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mrt_abi_version(void) { return MRT_ABI_VERSION; }
+
+int mrt_create(int device, mrt_context** out) {
+    if (!out) return MRT_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return mrt_fail(nullptr, MRT_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return mrt_fail(nullptr, MRT_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return mrt_fail(nullptr, MRT_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    mrt_context* ctx = new mrt_context();
+    ctx->device = device;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        mrt_fail(nullptr, MRT_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        delete ctx;
+        return MRT_ERR_CUDA;
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return MRT_OK;
+}
+
+void mrt_destroy(mrt_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->bn) cudaFree(ctx->bn);
+    dev_free(ctx->pos); dev_free(ctx->idx); dev_free(ctx->albedo);
+    dev_free(ctx->prim_lo); dev_free(ctx->prim_hi); dev_free(ctx->keys); dev_free(ctx->keys_alt);
+    dev_free(ctx->order); dev_free(ctx->order_alt); dev_free(ctx->hist); dev_free(ctx->scan_tmp);
+    dev_free(ctx->bin_left); dev_free(ctx->bin_right); dev_free(ctx->bin_parent); dev_free(ctx->bin_first);
+    dev_free(ctx->bin_last); dev_free(ctx->bin_lo); dev_free(ctx->bin_hi); dev_free(ctx->bin_flag);
+    dev_free(ctx->scene_bounds); dev_free(ctx->work_a); dev_free(ctx->work_b); dev_free(ctx->slot_node);
+    dev_free(ctx->node_nchild); dev_free(ctx->node_ntri); dev_free(ctx->node_child_base); dev_free(ctx->node_tri_base);
+    dev_free(ctx->nodes); dev_free(ctx->tris); dev_free(ctx->counters);
+    dev_free(ctx->trans16); dev_free(ctx->multi16); dev_free(ctx->view_packed);
+    dev_free(ctx->trans_f); dev_free(ctx->multi_f); dev_free(ctx->view_f);
+    dev_free(ctx->visibility); dev_free(ctx->depth); dev_free(ctx->normal); dev_free(ctx->motion); dev_free(ctx->color16);
+    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->ldr);
+    dev_free(ctx->hit0_pos); dev_free(ctx->hit0_n); dev_free(ctx->path_state);
+    for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); }
+    dev_free(ctx->hits); dev_free(ctx->queue_counts); dev_free(ctx->sort_keys); dev_free(ctx->sort_keys_alt);
+    dev_free(ctx->sort_vals); dev_free(ctx->sort_vals_alt); dev_free(ctx->visit_counters);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* mrt_last_error(const mrt_context* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
+    MRT_ENTER(ctx);
+    if (!name) return mrt_fail(ctx, MRT_ERR_INVALID, "option name is NULL");
+    if (!strcmp(name, "count_visits")) ctx->opt_count_visits = value != 0;
+    else if (!strcmp(name, "sort_rays")) ctx->opt_sort_rays = value != 0;
+    else if (!strcmp(name, "persistent")) ctx->opt_persistent = value != 0;
+    else return mrt_fail(ctx, MRT_ERR_INVALID, "unknown option '%s'", name);
+    return MRT_OK;
+}
+
+int mrt_upload_blue_noise(mrt_context* ctx, const uint8_t* rgba8, uint32_t w, uint32_t h) {
+    MRT_ENTER(ctx);
+    if (!rgba8 || w == 0 || h == 0) return mrt_fail(ctx, MRT_ERR_INVALID, "blue noise: empty texture");
+    if (ctx->bn) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->bn); ctx->bn = nullptr; }
+    MRT_CUDA(ctx, cudaMalloc((void**)&ctx->bn, (size_t)w * h * 4));
+    MRT_CUDA(ctx, cudaMemcpyAsync(ctx->bn, rgba8, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->bnW = w;
+    ctx->bnH = h;
+    return MRT_OK;
+}
+
+int mrt_scene_set_spheres(mrt_context* ctx, const mrt_sphere* spheres, uint32_t n) {
+    MRT_ENTER(ctx);
+    if (n > MRT_MAX_SPHERES) return mrt_fail(ctx, MRT_ERR_INVALID, "at most %d spheres", MRT_MAX_SPHERES);
+    if (n && !spheres) return mrt_fail(ctx, MRT_ERR_INVALID, "spheres is NULL");
+    memset(&ctx->spheres, 0, sizeof ctx->spheres);
+    for (uint32_t i = 0; i < n; i++) ctx->spheres.s[i] = spheres[i];
+    ctx->spheres.n = n;
+    ctx->scene_kind = 1;
+    ctx->have_gbuffer = false;
+    return MRT_OK;
+}
+
+int mrt_scene_upload_mesh(mrt_context* ctx, const float* positions, uint32_t nverts, const uint32_t* indices, uint32_t ntris,
+                          const float* albedo) {
+    MRT_ENTER(ctx);
+    if (ntris && (!positions || !indices || !albedo || nverts == 0))
+        return mrt_fail(ctx, MRT_ERR_INVALID, "mesh: NULL array with ntris = %u", ntris);
+    for (size_t i = 0; i < 3 * (size_t)ntris; i++)
+        if (indices[i] >= nverts) return mrt_fail(ctx, MRT_ERR_INVALID, "mesh: index %u out of range at %zu", indices[i], i);
+    MRT_TRY(dev_reserve(ctx, ctx->pos, 3 * (size_t)nverts));
+    MRT_TRY(dev_reserve(ctx, ctx->idx, 3 * (size_t)ntris));
+    MRT_TRY(dev_reserve(ctx, ctx->albedo, ntris));
+    if (ntris) {
+        MRT_CUDA(ctx, cudaMemcpyAsync(ctx->pos.p, positions, sizeof(float) * 3 * (size_t)nverts, cudaMemcpyHostToDevice, ctx->stream));
+        MRT_CUDA(ctx, cudaMemcpyAsync(ctx->idx.p, indices, sizeof(uint32_t) * 3 * (size_t)ntris, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<float4> al(ntris);
+        for (uint32_t i = 0; i < ntris; i++) al[i] = make_float4(albedo[3 * (size_t)i], albedo[3 * (size_t)i + 1], albedo[3 * (size_t)i + 2], 0.0f);
+        MRT_CUDA(ctx, cudaMemcpyAsync(ctx->albedo.p, al.data(), sizeof(float4) * (size_t)ntris, cudaMemcpyHostToDevice, ctx->stream));
+        MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->nverts = nverts;
+    ctx->ntris = ntris;
+    ctx->scene_kind = 2;
+    ctx->bvh_valid = false;
+    ctx->have_gbuffer = false;
+    return MRT_OK;
+}
+
+int mrt_scene_update_positions(mrt_context* ctx, const float* positions, uint32_t nverts) {
+    MRT_ENTER(ctx);
+    if (ctx->scene_kind != 2) return mrt_fail(ctx, MRT_ERR_STATE, "no mesh uploaded");
+    if (nverts != ctx->nverts || !positions) return mrt_fail(ctx, MRT_ERR_INVALID, "vertex count mismatch (%u vs %u)", nverts, ctx->nverts);
+    MRT_CUDA(ctx, cudaMemcpyAsync(ctx->pos.p, positions, sizeof(float) * 3 * (size_t)nverts, cudaMemcpyHostToDevice, ctx->stream));
+    MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MRT_OK;
+}
+
+int mrt_scene_build(mrt_context* ctx, int build_mode) {
+    MRT_ENTER(ctx);
+    if (ctx->scene_kind != 2) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_scene_build: no mesh uploaded");
+    if (build_mode == MRT_BUILD_REFIT) return bvh_refit(ctx);
+    if (build_mode != MRT_BUILD_FULL) return mrt_fail(ctx, MRT_ERR_INVALID, "unknown build mode %d", build_mode);
+    return bvh_build_full(ctx);
+}
+
+int mrt_atmosphere(mrt_context* ctx, const mrt_atmosphere_params* params) {
+    MRT_ENTER(ctx);
+    if (!params) return mrt_fail(ctx, MRT_ERR_INVALID, "atmosphere params is NULL");
+    ctx->atmo = *params;
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    MRT_TRY(sky_gen_atmosphere(ctx));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->have_atmo = true;
+    ctx->have_view = false;
+    return MRT_OK;
+}
+
+int mrt_sky_view(mrt_context* ctx, const float probePos[3], const float sunDirection[3], const float sunIlluminance[3]) {
+    MRT_ENTER(ctx);
+    if (!ctx->have_atmo) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_sky_view before mrt_atmosphere");
+    if (!probePos || !sunDirection || !sunIlluminance) return mrt_fail(ctx, MRT_ERR_INVALID, "sky view: NULL argument");
+    MRT_TRY(sky_gen_view(ctx, probePos, sunDirection, sunIlluminance));
+    ctx->have_view = true;
+    return MRT_OK;
+}
+
+int mrt_set_partition(mrt_context* ctx, uint32_t rank, uint32_t nranks, uint32_t slab_rows) {
+    MRT_ENTER(ctx);
+    if (nranks == 0 || rank >= nranks || slab_rows == 0) return mrt_fail(ctx, MRT_ERR_INVALID, "bad partition %u/%u slab %u", rank, nranks, slab_rows);
+    ctx->part = Partition{rank, nranks, slab_rows};
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = false;
+    return MRT_OK;
+}
+
+int mrt_partition_rows(const mrt_context* ctx, uint32_t full_h, uint32_t* rows_out, uint32_t* nrows_out) {
+    if (!ctx || !nrows_out) return MRT_ERR_INVALID;
+    uint32_t n = partition_local_rows(ctx->part, full_h);
+    *nrows_out = n;
+    if (rows_out)
+        for (uint32_t lr = 0; lr < n; lr++) rows_out[lr] = partition_local_to_y(ctx->part, lr);
+    return MRT_OK;
+}
+
+int mrt_primary_rays(mrt_context* ctx, uint32_t w, uint32_t h, const mrt_primary_constants* c) {
+    MRT_ENTER(ctx);
+    if (!c || w == 0 || h == 0) return mrt_fail(ctx, MRT_ERR_INVALID, "primary rays: bad size %ux%u or NULL constants", w, h);
+    if (ctx->scene_kind == 0) return mrt_fail(ctx, MRT_ERR_STATE, "primary rays: no scene");
+    if (ctx->scene_kind == 2 && !ctx->bvh_valid) return mrt_fail(ctx, MRT_ERR_STATE, "primary rays: mesh uploaded but not built");
+    uint32_t rows = partition_local_rows(ctx->part, h);
+    if (w != ctx->W || h != ctx->H || rows != ctx->local_rows) ctx->have_accum = ctx->have_color = ctx->have_ldr = false;
+    ctx->W = w; ctx->H = h; ctx->local_rows = rows;
+    ctx->npix = (size_t)w * rows;
+    ctx->pc = *c;
+    size_t n = ctx->npix;
+    MRT_TRY(dev_reserve(ctx, ctx->visibility, n));
+    MRT_TRY(dev_reserve(ctx, ctx->depth, n));
+    MRT_TRY(dev_reserve(ctx, ctx->normal, 4 * n));
+    MRT_TRY(dev_reserve(ctx, ctx->motion, 2 * n));
+    MRT_TRY(dev_reserve(ctx, ctx->color16, 4 * n));
+    MRT_TRY(dev_reserve(ctx, ctx->accum, n));
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    int s = n == 0 ? MRT_OK : (ctx->scene_kind == 1 ? spheres_primary(ctx) : mesh_primary(ctx));
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    if (s == MRT_OK) ctx->have_gbuffer = true;
+    return s;
+}
+
+int mrt_secondary_rays(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags) {
+    MRT_ENTER(ctx);
+    if (!c || spp == 0) return mrt_fail(ctx, MRT_ERR_INVALID, "secondary rays: NULL constants or spp = 0");
+    if (!ctx->have_gbuffer) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays before primary rays");
+    if (!ctx->have_atmo || !ctx->have_view) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: sky LUTs missing (mrt_atmosphere, mrt_sky_view)");
+    if (!ctx->bn) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: blue noise texture missing");
+    cudaEventRecord(ctx->ev[4], ctx->stream);
+    int s = MRT_OK;
+    if (ctx->npix) s = ctx->scene_kind == 1 ? spheres_secondary(ctx, c, spp, bounces, flags) : mesh_secondary(ctx, c, spp, bounces, flags);
+    cudaEventRecord(ctx->ev[5], ctx->stream);
+    if (s == MRT_OK) {
+        ctx->have_accum = true;
+        ctx->have_color = ctx->scene_kind == 1;
+        ctx->stats.secondary_rays = ~0ull;  // resolved lazily in mrt_stats_get
+    }
+    return s;
+}
+
+int mrt_tonemap(mrt_context* ctx, int mode, float exposure, const float* params, uint32_t nparams, int source) {
+    MRT_ENTER(ctx);
+    if (mode < MRT_TONEMAP_LINEAR || mode > MRT_TONEMAP_AMD) return mrt_fail(ctx, MRT_ERR_INVALID, "unknown tonemap mode %d", mode);
+    static const uint32_t need[6] = {0, 1, 0, 0, 6, 5};
+    if (nparams < need[mode] || (need[mode] && !params)) return mrt_fail(ctx, MRT_ERR_INVALID, "tonemap mode %d needs %u params", mode, need[mode]);
+    if (source != MRT_BUF_COLOR && source != MRT_BUF_ACCUM) return mrt_fail(ctx, MRT_ERR_INVALID, "tonemap source must be COLOR or ACCUM");
+    if (!ctx->have_accum) return mrt_fail(ctx, MRT_ERR_STATE, "tonemap before secondary rays");
+    if (source == MRT_BUF_COLOR && !ctx->have_color) {
+        void* p; size_t b;
+        MRT_TRY(buffer_info(ctx, MRT_BUF_COLOR, &p, &b));
+    }
+    cudaEventRecord(ctx->ev[6], ctx->stream);
+    int s = tonemap_run(ctx, mode, exposure, params, nparams, source);
+    cudaEventRecord(ctx->ev[7], ctx->stream);
+    return s;
+}
+
+int mrt_buffer(mrt_context* ctx, int buffer_id, void** device_ptr, size_t* bytes) {
+    MRT_ENTER(ctx);
+    if (!device_ptr || !bytes) return mrt_fail(ctx, MRT_ERR_INVALID, "mrt_buffer: NULL out pointer");
+    return buffer_info(ctx, buffer_id, device_ptr, bytes);
+}
+
+int mrt_readback(mrt_context* ctx, int buffer_id, void* host, size_t bytes) {
+    MRT_ENTER(ctx);
+    void* p = nullptr;
+    size_t have = 0;
+    MRT_TRY(buffer_info(ctx, buffer_id, &p, &have));
+    if (!host || bytes > have) return mrt_fail(ctx, MRT_ERR_INVALID, "readback of %zu bytes from a %zu-byte buffer", bytes, have);
+    MRT_CUDA(ctx, cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MRT_OK;
+}
+
+int mrt_sync(mrt_context* ctx) {
+    MRT_ENTER(ctx);
+    MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MRT_OK;
+}
+
+int mrt_stream(mrt_context* ctx, void** stream_out) {
+    MRT_ENTER(ctx);
+    if (!stream_out) return MRT_ERR_INVALID;
+    *stream_out = (void*)ctx->stream;
+    return MRT_OK;
+}
+
+int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
+    MRT_ENTER(ctx);
+    if (!out) return MRT_ERR_INVALID;
+    MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms;
+    if (ctx->have_gbuffer && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.ms_primary = ms;
+    if (ctx->have_accum && cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->stats.ms_secondary = ms;
+    if (ctx->have_ldr && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->stats.ms_tonemap = ms;
+    cudaGetLastError();
+    if (ctx->have_accum && ctx->stats.secondary_rays == ~0ull) {
+        if (ctx->scene_kind == 1) {
+            unsigned long long v = 0;
+            MRT_CUDA(ctx, cudaMemcpy(&v, ctx->visit_counters.p + 4, sizeof v, cudaMemcpyDeviceToHost));
+            ctx->stats.secondary_rays = v;
+        } else {
+            std::vector<uint32_t> counts(ctx->queue_counts.cap);
+            MRT_CUDA(ctx, cudaMemcpy(counts.data(), ctx->queue_counts.p, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost));
+            uint64_t total = 0;
+            for (uint32_t v : counts) total += v;
+            ctx->stats.secondary_rays = total;
+        }
+    }
+    if (ctx->scene_kind == 2 && ctx->visit_counters.p) {
+        unsigned long long vc[8];
+        MRT_CUDA(ctx, cudaMemcpy(vc, ctx->visit_counters.p, sizeof vc, cudaMemcpyDeviceToHost));
+        ctx->stats.node_visits = vc[0] + vc[4];
+        ctx->stats.tri_tests = vc[1] + vc[5];
+        ctx->stats.stack_overflows = (uint32_t)(vc[2] + vc[6]);
+    }
+    *out = ctx->stats;
+    return MRT_OK;
+}
+
+int mrt_stats_reset(mrt_context* ctx) {
+    MRT_ENTER(ctx);
+    ctx->stats.kernel_launches = 0;
+    return MRT_OK;
+}
+
+int mrt_trace_rays(mrt_context* ctx, const float* origins, const float* directions, uint32_t n, uint32_t* prim_ids, float* t,
+                   int brute_force) {
+    MRT_ENTER(ctx);
+    if (ctx->scene_kind != 2) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_trace_rays: no mesh uploaded");
+    if (!brute_force && !ctx->bvh_valid) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_trace_rays: BVH not built");
+    if (n && (!origins || !directions || !prim_ids || !t)) return mrt_fail(ctx, MRT_ERR_INVALID, "mrt_trace_rays: NULL array");
+    return mesh_trace_rays(ctx, origins, directions, n, prim_ids, t, brute_force);
+}
+
+}  // extern "C"

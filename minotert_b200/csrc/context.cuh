@@ -1,0 +1,185 @@
+// context.cuh -- the mrt_context: device memory, stream, scene and frame state.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/minotert.h"
+#include "sky.cuh"
+#include "vec.cuh"
+
+// ---- wide BVH (row n3): 80-byte compressed 8-wide node, five 128-bit words ----
+//  w0: origin.x, origin.y, origin.z (fp32 bits), ex | ey<<8 | ez<<16 | imask<<24
+//  w1: child_base, tri_base, meta[0..3], meta[4..7]
+//  w2: qlo_x[0..7], qlo_y[0..7]        w3: qlo_z[0..7], qhi_x[0..7]       w4: qhi_y[0..7], qhi_z[0..7]
+//  meta: 0 = empty; internal = 0x20 | (24 + slot); leaf = unary tri count << 5 | first tri offset (0..23)
+struct WideNode { uint4 w[5]; };
+static_assert(sizeof(WideNode) == 80, "wide node is 80 bytes");
+
+#define MRT_MAX_LEAF_TRIS 3
+#define MRT_MAX_SPHERES 16
+
+struct BvhDev {
+    const WideNode* nodes;  // [num_nodes]
+    const float4* tris;     // [3 * num_leaf_tris] : v0.xyz|prim id, v1.xyz|0, v2.xyz|0 in node-leaf order
+    uint32_t num_nodes;
+    uint32_t num_tris;
+};
+
+struct Partition { uint32_t rank, nranks, slab_rows; };
+
+// local row -> row of the full image (mrt_set_partition)
+MRT_HD uint32_t partition_local_to_y(const Partition& p, uint32_t lr) {
+    uint32_t slab = lr / p.slab_rows, r = lr % p.slab_rows;
+    return (slab * p.nranks + p.rank) * p.slab_rows + r;
+}
+static inline uint32_t partition_local_rows(const Partition& p, uint32_t H) {
+    uint32_t n = 0;
+    for (uint32_t y = 0; y < H; y++)
+        if ((y / p.slab_rows) % p.nranks == p.rank) n++;
+    return n;
+}
+
+struct Spheres { mrt_sphere s[MRT_MAX_SPHERES]; uint32_t n; };
+
+template <typename T>
+struct DevArray {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+};
+
+struct mrt_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    bool poisoned = false;
+
+    // options
+    int opt_count_visits = 0;
+    int opt_sort_rays = 0;
+    int opt_persistent = 1;
+
+    // inputs
+    uchar4* bn = nullptr;
+    uint32_t bnW = 0, bnH = 0;
+    int scene_kind = 0;  // 0 none, 1 spheres, 2 mesh
+    Spheres spheres{};
+
+    // mesh (upload order)
+    DevArray<float> pos;      // 3 * nverts
+    DevArray<uint32_t> idx;   // 3 * ntris
+    DevArray<float4> albedo;  // per primitive, rgb_
+    uint32_t nverts = 0, ntris = 0;
+    bool bvh_valid = false;
+
+    // LBVH build scratch + result (bvh_build.cu)
+    DevArray<float4> prim_lo, prim_hi;      // per primitive AABB
+    DevArray<uint64_t> keys, keys_alt;      // Morton keys
+    DevArray<uint32_t> order, order_alt;    // sorted primitive ids
+    DevArray<uint32_t> hist;                // radix histograms
+    DevArray<uint32_t> scan_tmp;
+    DevArray<int32_t> bin_left, bin_right, bin_parent;  // binary nodes: [0,N-1) internal, [N-1,2N-1) leaves
+    DevArray<uint32_t> bin_first, bin_last;              // sorted range covered by each internal node
+    DevArray<float4> bin_lo, bin_hi;                      // boxes of all 2N-1 binary nodes
+    DevArray<uint32_t> bin_flag;
+    DevArray<uint32_t> scene_bounds;                      // 6 ordered-int floats
+    DevArray<uint2> work_a, work_b;                       // collapse work items (binary node, wide node)
+    DevArray<int32_t> slot_node;                          // [num_nodes][8] binary node behind each slot
+    DevArray<uint32_t> node_nchild, node_ntri, node_child_base, node_tri_base;
+    DevArray<WideNode> nodes;
+    DevArray<float4> tris;
+    DevArray<uint32_t> counters;                          // misc device counters
+    uint32_t num_nodes = 0, num_leaf_tris = 0;
+
+    // sky
+    mrt_atmosphere_params atmo{};
+    bool have_atmo = false, have_view = false;
+    DevArray<uint16_t> trans16, multi16;
+    DevArray<uint32_t> view_packed;
+    DevArray<float4> trans_f, multi_f, view_f;
+
+    // frame
+    Partition part{0, 1, 8};
+    uint32_t W = 0, H = 0, local_rows = 0;
+    size_t npix = 0;  // local pixels
+    bool have_gbuffer = false, have_color = false, have_accum = false, have_ldr = false;
+    mrt_primary_constants pc{};
+    DevArray<uint32_t> visibility;
+    DevArray<uint16_t> depth, normal, motion, color16;
+    DevArray<float> hit_t;
+    DevArray<float4> accum;
+    DevArray<uchar4> ldr;
+    // wavefront state (triangle path)
+    DevArray<float4> hit0_pos, hit0_n;   // primary hit position|prim id, normal|valid
+    DevArray<float4> path_state;         // throughput rgb | rng state
+    DevArray<float4> ray_o[2], ray_d[2]; // queues: origin|pixel, direction|tmax
+    DevArray<float4> hits;               // t | tri slot | u | v
+    DevArray<uint32_t> queue_counts;     // one counter per wave
+    DevArray<uint64_t> sort_keys, sort_keys_alt;
+    DevArray<uint32_t> sort_vals, sort_vals_alt;
+    DevArray<unsigned long long> visit_counters;  // node visits, tri tests, stack overflows
+
+    // stats
+    mrt_stats stats{};
+    cudaEvent_t ev[8] = {nullptr};
+};
+
+// ---- error plumbing ----
+int mrt_fail(mrt_context* ctx, int code, const char* fmt, ...);
+int mrt_check_cuda(mrt_context* ctx, cudaError_t e, const char* what);
+#define MRT_CUDA(ctx, call)                                            \
+    do {                                                               \
+        int _s = mrt_check_cuda((ctx), (call), #call);                 \
+        if (_s != MRT_OK) return _s;                                   \
+    } while (0)
+#define MRT_TRY(call)                    \
+    do {                                 \
+        int _s = (call);                 \
+        if (_s != MRT_OK) return _s;     \
+    } while (0)
+
+template <typename T>
+static inline int dev_reserve(mrt_context* ctx, DevArray<T>& a, size_t n) {
+    if (n <= a.cap && a.p) return MRT_OK;
+    if (a.p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(a.p);
+        a.p = nullptr;
+        a.cap = 0;
+    }
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)&a.p, n * sizeof(T));
+    if (e != cudaSuccess) {
+        a.p = nullptr;
+        return mrt_fail(ctx, e == cudaErrorMemoryAllocation ? MRT_ERR_OOM : MRT_ERR_CUDA, "cudaMalloc(%zu bytes): %s",
+                        n * sizeof(T), cudaGetErrorString(e));
+    }
+    a.cap = n;
+    return MRT_OK;
+}
+template <typename T>
+static inline void dev_free(DevArray<T>& a) {
+    if (a.p) cudaFree(a.p);
+    a.p = nullptr;
+    a.cap = 0;
+}
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+#define MRT_LAUNCHED(ctx) ((ctx)->stats.kernel_launches++)
+
+// ---- stage entry points implemented across the .cu files ----
+int sky_gen_atmosphere(mrt_context* ctx);
+int sky_gen_view(mrt_context* ctx, const float probe[3], const float sunDir[3], const float sunIll[3]);
+int spheres_primary(mrt_context* ctx);
+int spheres_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags);
+int tonemap_run(mrt_context* ctx, int mode, float exposure, const float* params, uint32_t nparams, int source);
+int bvh_build_full(mrt_context* ctx);
+int bvh_refit(mrt_context* ctx);
+int mesh_primary(mrt_context* ctx);
+int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags);
+int mesh_trace_rays(mrt_context* ctx, const float* o, const float* d, uint32_t n, uint32_t* ids, float* t, int brute);
+// device-wide primitives (sort.cu)
+int scan_exclusive_u32(mrt_context* ctx, const uint32_t* in, uint32_t* out, size_t n);
+int radix_sort_pairs_u64(mrt_context* ctx, uint64_t* keys, uint64_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, size_t n,
+                         int begin_bit, int end_bit, bool* result_in_alt);

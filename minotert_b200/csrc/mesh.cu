@@ -1,0 +1,344 @@
+// mesh.cu -- the triangle-scene path: primary pass (ray-gen + traversal + G-buffer) and the
+// wavefront path tracer (north_star rows n3-n7):
+//     per sample:  shade(primary hits) -> [ trace(queue) -> shade(queue) ] x bounces
+// shade = material + blue-noise-rotated PCG sampling + sky on miss + accumulation; it emits the next
+// bounce's rays into a compacted queue with one warp-aggregated atomic per warp (row n5).
+// Per-pixel semantics are those of secondaryRays.comp:64-135 with the primary hit carried in fp32:
+// the PCG state threads through all samples of a pixel, so samples run sequentially and the
+// wavefront is over pixels.  Every pixel owns at most one live path => accumulation needs no atomics
+// and the image is independent of queue order (deterministic).
+#include "shading.cuh"
+#include "trace.cuh"
+
+namespace {
+
+struct MeshFrame {
+    RayGen gen;
+    Mat4 PV, PVprev;
+    Partition part;
+    uint32_t local_rows;
+};
+
+MRT_D void flush_counters(const TraceCounters& c, unsigned long long* counters, bool count_visits) {
+    if (c.overflow) atomicAdd(&counters[2], (unsigned long long)c.overflow);
+    if (count_visits) {
+        unsigned n = c.nodes, t = c.tris;
+        for (int off = 16; off > 0; off >>= 1) {
+            n += __shfl_down_sync(0xFFFFFFFFu, n, off);
+            t += __shfl_down_sync(0xFFFFFFFFu, t, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&counters[0], (unsigned long long)n);
+            atomicAdd(&counters[1], (unsigned long long)t);
+        }
+    }
+}
+
+// Primary pass: primaryRay.comp:38-76 with the 5-sphere loop replaced by BVH traversal.
+// 8x4-pixel tiles per warp keep primary rays of a warp spatially coherent.
+__global__ void __launch_bounds__(TRACE_BLOCK)
+k_mesh_primary(MeshFrame F, BvhDev bvh, uint32_t* __restrict__ vis, uint16_t* __restrict__ depth, uint16_t* __restrict__ normal,
+               uint16_t* __restrict__ motion, float* __restrict__ hit_t, float4* __restrict__ hit0_pos,
+               float4* __restrict__ hit0_n, unsigned long long* counters, int count_visits) {
+    __shared__ uint2 sm_stack[TRACE_SM_STACK][TRACE_BLOCK];
+    // block = 4 warps stacked vertically: 8 wide x 16 tall; warp = 8x4 tile
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x = blockIdx.x * 8 + (lane & 7);
+    const uint32_t lr = blockIdx.y * 16 + warp * 4 + (lane >> 3);
+    TraceCounters cnt{0, 0, 0};
+    if (x < F.gen.W && lr < F.local_rows) {
+        const uint32_t y = partition_local_to_y(F.part, lr);
+        float3 o, d;
+        ray_gen(F.gen, x, y, o, d);
+        TraceHit h = bvh_trace(bvh, o, d, &sm_stack[0][threadIdx.x], cnt);
+        const size_t p = (size_t)lr * F.gen.W + x;
+        float dep = 0.0f;
+        float2 mo = make_float2(0.0f, 0.0f);
+        float3 n = d, pos = f3s(0.0f);
+        if (h.prim != MRT_MISS_ID) {
+            pos = o + d * h.t;
+            n = tri_facing_normal(bvh, h.tri, d, nullptr);
+            project_hit(F.PV, F.PVprev, pos, F.gen.W, F.gen.H, dep, mo);
+        }
+        store_gbuffer(vis, depth, normal, motion, p, h.prim, dep, n, mo);
+        hit_t[p] = h.prim != MRT_MISS_ID ? h.t : 0.0f;
+        hit0_pos[p] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(h.prim));
+        hit0_n[p] = make_float4(n.x, n.y, n.z, 0.0f);
+    }
+    flush_counters(cnt, counters, count_visits != 0);
+}
+
+// Trace one wave: queue entry k -> hit record k.
+__global__ void __launch_bounds__(TRACE_BLOCK)
+k_trace(BvhDev bvh, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const uint32_t* __restrict__ count_ptr,
+        float4* __restrict__ hits, unsigned long long* counters, int count_visits) {
+    __shared__ uint2 sm_stack[TRACE_SM_STACK][TRACE_BLOCK];
+    const uint32_t count = *count_ptr;
+    const uint32_t k = blockIdx.x * TRACE_BLOCK + threadIdx.x;
+    if (blockIdx.x * TRACE_BLOCK >= count) return;
+    TraceCounters cnt{0, 0, 0};
+    if (k < count) {
+        float4 o4 = __ldg(&ray_o[k]), d4 = __ldg(&ray_d[k]);
+        TraceHit h = bvh_trace(bvh, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), &sm_stack[0][threadIdx.x], cnt);
+        hits[k] = make_float4(h.t, __uint_as_float(h.tri), h.u, h.v);
+    }
+    flush_counters(cnt, counters, count_visits != 0);
+}
+
+struct ShadeParams {
+    float3 cameraPos;
+    uint32_t seed;       // (frameCounter << 1) | 1, secondaryRays.comp:124
+    uint32_t W;
+    uint32_t spp;
+    uint32_t bnW, bnH;
+    uint32_t vertex;     // path vertex being shaded: 0 = primary hit
+    uint32_t bounces;
+    int first_sample;    // sample 0 of this frame: seed the PCG state, start/continue the accumulator
+    int accumulate;
+    Partition part;
+};
+
+// Shade one path vertex per thread.  FIRST: vertex 0, one thread per pixel, inputs from the primary
+// pass.  Otherwise: one thread per traced ray of the previous wave.
+template <bool FIRST>
+__global__ void __launch_bounds__(256)
+k_shade(ShadeParams P, BvhDev bvh, mrt_atmosphere_params A, SkyLuts luts, const uchar4* __restrict__ bn,
+        const float4* __restrict__ albedo, const float4* __restrict__ hit0_pos, const float4* __restrict__ hit0_n,
+        const float4* __restrict__ in_o, const float4* __restrict__ in_d, const float4* __restrict__ hits,
+        const uint32_t* __restrict__ in_count_ptr, uint32_t npix, float4* __restrict__ path_state, float4* __restrict__ accum,
+        float4* __restrict__ out_o, float4* __restrict__ out_d, uint32_t* __restrict__ out_count) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t count = FIRST ? npix : *in_count_ptr;
+    bool emit = false;
+    float3 ro = f3s(0.0f), rd = f3s(0.0f);
+    uint32_t pixel = 0;
+    if (k < count) {
+        float3 pos, n, thr;
+        uint32_t prim, rng;
+        if (FIRST) {
+            pixel = k;
+            float4 hp = hit0_pos[k], hn = hit0_n[k];
+            pos = f3(hp.x, hp.y, hp.z);
+            n = f3(hn.x, hn.y, hn.z);
+            prim = __float_as_uint(hp.w);
+            thr = f3s(1.0f);
+            rng = P.first_sample ? P.seed : __float_as_uint(path_state[k].w);
+            if (P.first_sample) {
+                float4 a = P.accumulate ? accum[k] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                a.w += (float)P.spp;
+                accum[k] = a;
+            }
+        } else {
+            float4 o4 = in_o[k], d4 = in_d[k], h = hits[k];
+            pixel = __float_as_uint(o4.w);
+            float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
+            uint32_t tri = __float_as_uint(h.y);
+            float4 st = path_state[pixel];
+            thr = f3(st.x, st.y, st.z);
+            rng = __float_as_uint(st.w);
+            if (tri != MRT_MISS_ID) {
+                pos = o + d * h.x;
+                n = tri_facing_normal(bvh, tri, d, &prim);
+            } else {
+                prim = MRT_MISS_ID;
+                pos = f3s(0.0f);
+                n = d;  // secondaryRays.comp:88
+            }
+        }
+        if (prim == MRT_MISS_ID) {
+            // secondaryRays.comp:96: the path ends in the sky
+            float3 c = thr * sky_color(A, luts, P.cameraPos, n);
+            float4 a = accum[pixel];
+            accum[pixel] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w);
+            if (FIRST) path_state[pixel] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
+        } else {
+            float4 al = __ldg(&albedo[prim]);
+            thr = thr * f3(al.x, al.y, al.z);  // secondaryRays.comp:94
+            if (P.vertex < P.bounces) {
+                uint32_t lr = pixel / P.W, x = pixel - lr * P.W;
+                float2 rot = blue_noise_rotation(bn, P.bnW, P.bnH, x, partition_local_to_y(P.part, lr));
+                lambert_bounce(pos, n, rng, rot.x, rot.y, ro, rd);
+                emit = true;
+            }
+            path_state[pixel] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
+        }
+    }
+    // compaction: one atomic per warp, lanes take consecutive queue slots
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, emit);
+    if (ballot) {
+        const unsigned lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == (unsigned)(__ffs(ballot) - 1)) base = atomicAdd(out_count, (uint32_t)__popc(ballot));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ballot) - 1);
+        if (emit) {
+            uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
+            out_o[slot] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(pixel));
+            out_d[slot] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+        }
+    }
+}
+
+// brute-force closest hit over the uploaded mesh (validation of the BVH path; mrt_trace_rays)
+__global__ void __launch_bounds__(128) k_trace_brute(const float* __restrict__ pos, const uint32_t* __restrict__ idx, uint32_t ntris,
+                                                     const float* __restrict__ ro, const float* __restrict__ rdir, uint32_t n,
+                                                     uint32_t* __restrict__ ids, float* __restrict__ ts) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float3 o = f3(ro[3 * k], ro[3 * k + 1], ro[3 * k + 2]), d = f3(rdir[3 * k], rdir[3 * k + 1], rdir[3 * k + 2]);
+    RayShear rs = make_shear(d);
+    TraceHit h;
+    h.t = 0.0f; h.tri = h.prim = MRT_MISS_ID; h.u = h.v = 0.0f;
+    for (uint32_t i = 0; i < ntris; i++) {
+        uint32_t i0 = idx[3 * (size_t)i], i1 = idx[3 * (size_t)i + 1], i2 = idx[3 * (size_t)i + 2];
+        float t, u, v;
+        if (tri_test(o, rs, f3(pos[3 * (size_t)i0], pos[3 * (size_t)i0 + 1], pos[3 * (size_t)i0 + 2]),
+                     f3(pos[3 * (size_t)i1], pos[3 * (size_t)i1 + 1], pos[3 * (size_t)i1 + 2]),
+                     f3(pos[3 * (size_t)i2], pos[3 * (size_t)i2 + 1], pos[3 * (size_t)i2 + 2]), t, u, v))
+            hit_consider(h, t, u, v, i, i);
+    }
+    ids[k] = h.prim;
+    ts[k] = h.prim != MRT_MISS_ID ? h.t : 0.0f;
+}
+
+__global__ void __launch_bounds__(TRACE_BLOCK) k_trace_query(BvhDev bvh, const float* __restrict__ ro, const float* __restrict__ rdir,
+                                                             uint32_t n, uint32_t* __restrict__ ids, float* __restrict__ ts,
+                                                             unsigned long long* counters) {
+    __shared__ uint2 sm_stack[TRACE_SM_STACK][TRACE_BLOCK];
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    TraceCounters cnt{0, 0, 0};
+    if (k < n) {
+        float3 o = f3(ro[3 * k], ro[3 * k + 1], ro[3 * k + 2]), d = f3(rdir[3 * k], rdir[3 * k + 1], rdir[3 * k + 2]);
+        TraceHit h = bvh_trace(bvh, o, d, &sm_stack[0][threadIdx.x], cnt);
+        ids[k] = h.prim;
+        ts[k] = h.prim != MRT_MISS_ID ? h.t : 0.0f;
+    }
+    flush_counters(cnt, counters, true);
+}
+
+BvhDev make_bvh(mrt_context* ctx) {
+    BvhDev b;
+    b.nodes = ctx->nodes.p;
+    b.tris = ctx->tris.p;
+    b.num_nodes = ctx->num_nodes;
+    b.num_tris = ctx->num_leaf_tris;
+    return b;
+}
+
+}  // namespace
+
+int mesh_primary(mrt_context* ctx) {
+    MeshFrame F;
+    memcpy(&F.gen.invView, &ctx->pc.invView, sizeof(Mat4));
+    memcpy(&F.gen.invProj, &ctx->pc.invProjection, sizeof(Mat4));
+    F.gen.W = ctx->W;
+    F.gen.H = ctx->H;
+    Mat4 P, V, Vp;
+    memcpy(&P, &ctx->pc.projection, sizeof(Mat4));
+    memcpy(&V, &ctx->pc.view, sizeof(Mat4));
+    memcpy(&Vp, &ctx->pc.prevView, sizeof(Mat4));
+    F.PV = mat_mul(P, V);
+    F.PVprev = mat_mul(P, Vp);
+    F.part = ctx->part;
+    F.local_rows = ctx->local_rows;
+    MRT_TRY(dev_reserve(ctx, ctx->hit_t, ctx->npix));
+    MRT_TRY(dev_reserve(ctx, ctx->hit0_pos, ctx->npix));
+    MRT_TRY(dev_reserve(ctx, ctx->hit0_n, ctx->npix));
+    MRT_TRY(dev_reserve(ctx, ctx->visit_counters, 8));
+    MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    dim3 grid(div_up(ctx->W, 8), div_up(ctx->local_rows, 16));
+    k_mesh_primary<<<grid, TRACE_BLOCK, 0, ctx->stream>>>(F, make_bvh(ctx), ctx->visibility.p, ctx->depth.p, ctx->normal.p,
+                                                          ctx->motion.p, ctx->hit_t.p, ctx->hit0_pos.p, ctx->hit0_n.p,
+                                                          ctx->visit_counters.p, ctx->opt_count_visits);
+    MRT_LAUNCHED(ctx);
+    ctx->stats.primary_rays = ctx->npix;
+    return mrt_check_cuda(ctx, cudaGetLastError(), "mesh_primary");
+}
+
+int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags) {
+    const uint32_t npix = (uint32_t)ctx->npix;
+    const uint32_t waves = spp * bounces;
+    MRT_TRY(dev_reserve(ctx, ctx->path_state, npix));
+    for (int q = 0; q < 2; q++) {
+        MRT_TRY(dev_reserve(ctx, ctx->ray_o[q], npix));
+        MRT_TRY(dev_reserve(ctx, ctx->ray_d[q], npix));
+    }
+    MRT_TRY(dev_reserve(ctx, ctx->hits, npix));
+    MRT_TRY(dev_reserve(ctx, ctx->queue_counts, (size_t)waves + 1));
+    MRT_TRY(dev_reserve(ctx, ctx->visit_counters, 8));
+    MRT_CUDA(ctx, cudaMemsetAsync(ctx->queue_counts.p, 0, sizeof(uint32_t) * ((size_t)waves + 1), ctx->stream));
+    MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
+
+    ShadeParams P;
+    P.cameraPos = f3(c->cameraPos[0], c->cameraPos[1], c->cameraPos[2]);
+    P.seed = (c->frameCounter << 1u) | 1u;
+    P.W = ctx->W;
+    P.spp = spp;
+    P.bnW = ctx->bnW;
+    P.bnH = ctx->bnH;
+    P.bounces = bounces;
+    P.accumulate = ((flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum) ? 1 : 0;
+    P.part = ctx->part;
+    SkyLuts luts{ctx->trans_f.p, nullptr, ctx->view_f.p};
+    BvhDev bvh = make_bvh(ctx);
+    const unsigned shade_grid = div_up(npix, 256), trace_grid = div_up(npix, TRACE_BLOCK);
+
+    uint32_t wave = 0;
+    for (uint32_t s = 0; s < spp; s++) {
+        P.first_sample = s == 0;
+        P.vertex = 0;
+        int q = 0;
+        uint32_t* out_count = ctx->queue_counts.p + wave;
+        k_shade<true><<<shade_grid, 256, 0, ctx->stream>>>(P, bvh, ctx->atmo, luts, ctx->bn, ctx->albedo.p, ctx->hit0_pos.p,
+                                                           ctx->hit0_n.p, nullptr, nullptr, nullptr, nullptr, npix,
+                                                           ctx->path_state.p, ctx->accum.p, ctx->ray_o[q].p, ctx->ray_d[q].p,
+                                                           out_count);
+        MRT_LAUNCHED(ctx);
+        for (uint32_t b = 1; b <= bounces; b++) {
+            const uint32_t* in_count = ctx->queue_counts.p + wave;
+            k_trace<<<trace_grid, TRACE_BLOCK, 0, ctx->stream>>>(bvh, ctx->ray_o[q].p, ctx->ray_d[q].p, in_count, ctx->hits.p,
+                                                                 ctx->visit_counters.p + 4, ctx->opt_count_visits);
+            MRT_LAUNCHED(ctx);
+            wave++;
+            P.vertex = b;
+            // the last vertex emits nothing; its counter slot stays 0
+            out_count = ctx->queue_counts.p + (wave < waves ? wave : waves);
+            k_shade<false><<<shade_grid, 256, 0, ctx->stream>>>(P, bvh, ctx->atmo, luts, ctx->bn, ctx->albedo.p, nullptr, nullptr,
+                                                                ctx->ray_o[q].p, ctx->ray_d[q].p, ctx->hits.p, in_count, npix,
+                                                                ctx->path_state.p, ctx->accum.p, ctx->ray_o[q ^ 1].p,
+                                                                ctx->ray_d[q ^ 1].p, out_count);
+            MRT_LAUNCHED(ctx);
+            q ^= 1;
+        }
+    }
+    return mrt_check_cuda(ctx, cudaGetLastError(), "mesh_secondary");
+}
+
+int mesh_trace_rays(mrt_context* ctx, const float* o, const float* d, uint32_t n, uint32_t* ids, float* t, int brute) {
+    if (n == 0) return MRT_OK;
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
+    uint32_t* d_ids = nullptr;
+    MRT_CUDA(ctx, cudaMalloc(&d_o, sizeof(float) * 3 * (size_t)n));
+    MRT_CUDA(ctx, cudaMalloc(&d_d, sizeof(float) * 3 * (size_t)n));
+    MRT_CUDA(ctx, cudaMalloc(&d_t, sizeof(float) * (size_t)n));
+    MRT_CUDA(ctx, cudaMalloc(&d_ids, sizeof(uint32_t) * (size_t)n));
+    MRT_CUDA(ctx, cudaMemcpyAsync(d_o, o, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    MRT_CUDA(ctx, cudaMemcpyAsync(d_d, d, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    MRT_TRY(dev_reserve(ctx, ctx->visit_counters, 8));
+    MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    if (brute)
+        k_trace_brute<<<div_up(n, 128), 128, 0, ctx->stream>>>(ctx->pos.p, ctx->idx.p, ctx->ntris, d_o, d_d, n, d_ids, d_t);
+    else
+        k_trace_query<<<div_up(n, TRACE_BLOCK), TRACE_BLOCK, 0, ctx->stream>>>(make_bvh(ctx), d_o, d_d, n, d_ids, d_t,
+                                                                              ctx->visit_counters.p);
+    MRT_LAUNCHED(ctx);
+    MRT_CUDA(ctx, cudaMemcpyAsync(ids, d_ids, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    MRT_CUDA(ctx, cudaMemcpyAsync(t, d_t, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long vc[3] = {0, 0, 0};
+    cudaMemcpy(vc, ctx->visit_counters.p, sizeof vc, cudaMemcpyDeviceToHost);
+    ctx->stats.node_visits = vc[0];
+    ctx->stats.tri_tests = vc[1];
+    ctx->stats.stack_overflows += (uint32_t)vc[2];
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_ids);
+    return MRT_OK;
+}

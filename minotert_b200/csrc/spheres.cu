@@ -1,0 +1,159 @@
+// spheres.cu -- the reference's own scene (src/gpu/scene.glsl) through the reference's two-pass
+// structure, "faithful" mode: primaryRay.comp -> fp16 G-buffer -> secondaryRays.comp -> RGBA16F.
+// This path is ALU/SFU-bound (5 analytic spheres in kernel parameters, no scene memory traffic):
+// one thread per pixel, 8x8 sample/bounce loop kept in registers exactly as the reference does.
+#include "shading.cuh"
+
+namespace {
+
+// primaryRay.comp:23-76
+__global__ void __launch_bounds__(256)
+k_spheres_primary(RayGen g, Mat4 PV, Mat4 PVprev, Spheres sp, Partition part, uint32_t local_rows, uint32_t* vis,
+                  uint16_t* depth, uint16_t* normal, uint16_t* motion) {
+    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, lr = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= g.W || lr >= local_rows) return;
+    uint32_t y = partition_local_to_y(part, lr);
+    float3 o, d;
+    ray_gen(g, x, y, o, d);
+    uint32_t id = MRT_MISS_ID;
+    float best = 0.0f;
+    for (uint32_t i = 0; i < sp.n; i++) {
+        float t = ray_sphere(o, d, sp.s[i]);
+        if (t >= 0.0f && (id == MRT_MISS_ID || t < best)) { best = t; id = i; }
+    }
+    // miss: depth 0 (infinitely far, inverted-Z), motion 0, normal = ray direction (:69-70)
+    float dep = 0.0f;
+    float2 mo = make_float2(0.0f, 0.0f);
+    float3 n = d;
+    if (id != MRT_MISS_ID) {
+        float3 pos = o + d * best;
+        n = normalize3(pos - f3(sp.s[id].center[0], sp.s[id].center[1], sp.s[id].center[2]));
+        project_hit(PV, PVprev, pos, g.W, g.H, dep, mo);
+    }
+    store_gbuffer(vis, depth, normal, motion, (size_t)lr * g.W + x, id, dep, n, mo);
+}
+
+struct SecondaryParams {
+    Mat4 invView, invProj;
+    float3 cameraPos;
+    uint32_t frameCounter;
+    uint32_t W, H, local_rows, spp, bounces;
+    uint32_t bnW, bnH;
+};
+
+// secondaryRays.comp:64-135 with Samples/Bounces as parameters
+__global__ void __launch_bounds__(128)
+k_spheres_secondary(SecondaryParams P, Spheres sp, Partition part, mrt_atmosphere_params A, SkyLuts luts,
+                    const uchar4* __restrict__ bn, const uint32_t* __restrict__ vis, const uint16_t* __restrict__ depth,
+                    const uint16_t* __restrict__ normal, uint16_t* __restrict__ color16, float4* __restrict__ accum,
+                    int accumulate, unsigned long long* __restrict__ ray_counter) {
+    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, lr = blockIdx.y * blockDim.y + threadIdx.y;
+    unsigned long long rays = 0;
+    if (x < P.W && lr < P.local_rows) {
+        uint32_t y = partition_local_to_y(part, lr);
+        size_t p = (size_t)lr * P.W + x;
+        float pitchx = 1.0f / (float)P.W, pitchy = 1.0f / (float)P.H;
+        float u = ((float)x + 0.5f) * pitchx;
+        float v = ((float)y + 0.5f) * pitchy;
+        v = 1.0f - v;
+        // reconstruct the primary hit from the fp16 G-buffer (:114-123)
+        uint32_t pid = vis[p];
+        uint2 npk = reinterpret_cast<const uint2*>(normal)[p];
+        float3 pn = f3(f16_bits_to_f32((uint16_t)(npk.x & 0xFFFF)), f16_bits_to_f32((uint16_t)(npk.x >> 16)),
+                       f16_bits_to_f32((uint16_t)(npk.y & 0xFFFF)));
+        float dep = f16_bits_to_f32(depth[p]);
+        float4 vp = mat_vec(P.invProj, u * 2.0f - 1.0f, v * 2.0f - 1.0f, dep, 1.0f);
+        vp.x /= vp.w; vp.y /= vp.w; vp.z /= vp.w;
+        float4 wp = mat_vec(P.invView, vp.x, vp.y, vp.z, 1.0f);
+        float3 ppos = f3(wp.x, wp.y, wp.z);
+        uint32_t rng = (P.frameCounter << 1u) | 1u;
+        float2 rot = blue_noise_rotation(bn, P.bnW, P.bnH, x, y);
+
+        float3 color = f3s(0.0f);
+        for (uint32_t s = 0; s < P.spp; s++) {
+            float3 thr = f3s(1.0f);
+            uint32_t hid = pid;
+            float3 hpos = ppos, hn = pn;
+            float3 contrib = f3s(0.0f);
+            for (uint32_t i = 0; i < P.bounces + 1u; i++) {
+                if (i > 0) {
+                    float3 ro, rd;
+                    lambert_bounce(hpos, hn, rng, rot.x, rot.y, ro, rd);
+                    rays++;
+                    hid = MRT_MISS_ID;
+                    float ht = -1.0f;
+                    for (uint32_t k = 0; k < sp.n; k++) {
+                        float t = ray_sphere(ro, rd, sp.s[k]);
+                        if (t >= 0.0f && (t < ht || ht < 0.0f)) { hid = k; ht = t; }
+                    }
+                    if (hid != MRT_MISS_ID) {
+                        hpos = ro + rd * ht;
+                        hn = normalize3(hpos - f3(sp.s[hid].center[0], sp.s[hid].center[1], sp.s[hid].center[2]));
+                    } else {
+                        hn = rd;
+                    }
+                }
+                if (hid != MRT_MISS_ID) {
+                    thr = thr * f3(sp.s[hid].albedo[0], sp.s[hid].albedo[1], sp.s[hid].albedo[2]);
+                } else {
+                    contrib = thr * sky_color(A, luts, P.cameraPos, hn);
+                    break;
+                }
+            }
+            color = color + contrib;
+        }
+        // progressive sum (row n7) before the reference's own average (:133)
+        float4 a = accumulate ? accum[p] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        accum[p] = make_float4(a.x + color.x, a.y + color.y, a.z + color.z, a.w + (float)P.spp);
+        color = color / (float)P.spp;
+        uint2 pk;
+        pk.x = (uint32_t)f32_to_f16_bits(color.x) | ((uint32_t)f32_to_f16_bits(color.y) << 16);
+        pk.y = (uint32_t)f32_to_f16_bits(color.z) | (0x3C00u << 16);
+        reinterpret_cast<uint2*>(color16)[p] = pk;
+    }
+    // one atomic per warp for the ray statistics
+    for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xFFFFFFFFu, rays, off);
+    if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0 && rays) atomicAdd(ray_counter, rays);
+}
+
+}  // namespace
+
+int spheres_primary(mrt_context* ctx) {
+    RayGen g;
+    memcpy(&g.invView, &ctx->pc.invView, sizeof(Mat4));
+    memcpy(&g.invProj, &ctx->pc.invProjection, sizeof(Mat4));
+    g.W = ctx->W;
+    g.H = ctx->H;
+    Mat4 P, V, Vp;
+    memcpy(&P, &ctx->pc.projection, sizeof(Mat4));
+    memcpy(&V, &ctx->pc.view, sizeof(Mat4));
+    memcpy(&Vp, &ctx->pc.prevView, sizeof(Mat4));
+    Mat4 PV = mat_mul(P, V), PVprev = mat_mul(P, Vp);
+    dim3 b(32, 8), grid(div_up(ctx->W, 32), div_up(ctx->local_rows, 8));
+    k_spheres_primary<<<grid, b, 0, ctx->stream>>>(g, PV, PVprev, ctx->spheres, ctx->part, ctx->local_rows,
+                                                   ctx->visibility.p, ctx->depth.p, ctx->normal.p, ctx->motion.p);
+    MRT_LAUNCHED(ctx);
+    ctx->stats.primary_rays = ctx->npix;
+    return mrt_check_cuda(ctx, cudaGetLastError(), "spheres_primary");
+}
+
+int spheres_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags) {
+    SecondaryParams P;
+    memcpy(&P.invView, &c->invView, sizeof(Mat4));
+    memcpy(&P.invProj, &c->invProjection, sizeof(Mat4));
+    P.cameraPos = f3(c->cameraPos[0], c->cameraPos[1], c->cameraPos[2]);
+    P.frameCounter = c->frameCounter;
+    P.W = ctx->W; P.H = ctx->H; P.local_rows = ctx->local_rows; P.spp = spp; P.bounces = bounces;
+    P.bnW = ctx->bnW; P.bnH = ctx->bnH;
+    SkyLuts luts{ctx->trans_f.p, nullptr, ctx->view_f.p};
+    MRT_TRY(dev_reserve(ctx, ctx->visit_counters, 8));
+    MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    // 16x8 tiles: warps cover 16x2 pixel footprints, which keeps the divergent bounce loops of
+    // neighbouring pixels (same sphere, similar path length) in one warp.
+    dim3 b(16, 8), grid(div_up(ctx->W, 16), div_up(ctx->local_rows, 8));
+    k_spheres_secondary<<<grid, b, 0, ctx->stream>>>(P, ctx->spheres, ctx->part, ctx->atmo, luts, ctx->bn, ctx->visibility.p,
+                                                     ctx->depth.p, ctx->normal.p, ctx->color16.p, ctx->accum.p,
+                                                     (flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum ? 1 : 0, ctx->visit_counters.p + 4);
+    MRT_LAUNCHED(ctx);
+    return mrt_check_cuda(ctx, cudaGetLastError(), "spheres_secondary");
+}

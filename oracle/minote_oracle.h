@@ -1,0 +1,192 @@
+/*
+ * minote_oracle.h -- CPU ORACLE for the MinoteRT ray-tracing hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, the smoke test in
+ * __graft_entry__.py and bench.py's cpu_baseline / --impl reference legs may load it.
+ * The product path (minotert_b200/csrc, libminotert.so) never links or calls it.
+ *
+ * PARITY UNPINNED: the reference (Tearnote/MinoteRT) ships no tests, golden vectors or
+ * fixtures for this path, cannot be built outside Windows/MSVC and its GLSL cannot be
+ * compiled or run here (no glslc, no Vulkan ICD).  This file is a plain-C restatement of
+ * the reference's GLSL + host matrix code, each function citing the reference file:line it
+ * follows.  Every implementation-defined Vulkan behaviour is fixed explicitly:
+ *   fp32 -> fp16          : IEEE round-to-nearest-even, overflow -> inf
+ *   fp32 -> B10G11R11     : RNE to 6/6/5-bit mantissa, negatives/NaN -> 0, saturate to max finite
+ *   fp32 -> unorm8        : rint(clamp(x,0,1)*255), NaN -> 0
+ *   bilinear filtering    : fp32 lerp on texel-centre coordinates, clamp/repeat per sampler
+ *   mat4*vec4             : sum of columns scaled by components, left to right, no FMA
+ *   normalize(v)          : v / sqrt(dot(v,v)) per component
+ *   transcendentals       : glibc libm (sinf, cosf, acosf, powf, expf, sqrtf)
+ * All arithmetic is fp32 without contraction (build with -ffp-contract=off).
+ *
+ * Extensions beyond the reference (north_star rows n1-n7; semantics inherited from the
+ * sphere path): brute-force and BVH-accelerated watertight ray/triangle closest hit with
+ * the lexicographic (t, primitive id) tie rule, parametric spp/bounces, fp32 progressive
+ * accumulation.
+ */
+#ifndef MINOTE_ORACLE_H
+#define MINOTE_ORACLE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- PODs shared with the product's C ABI (layouts restated, not included) ---- */
+
+/* src/gfx/camera.ixx:8-22 */
+typedef struct {
+    uint32_t viewport[2];
+    float verticalFov;
+    float nearPlane;
+    float position[3];
+    float yaw;
+    float pitch;
+    float lookSpeed;
+    float moveSpeed;
+} orc_camera;
+
+/* column-major 4x4: m[col][row]  (src/stx/math.ixx:531-539) */
+typedef struct { float m[4][4]; } orc_mat4;
+
+/* src/gfx/modules/pathtracer.ixx:86-93  <-> src/gpu/primaryRay.comp:14-21 */
+typedef struct {
+    orc_mat4 view, projection, invView, invProjection, prevView;
+    uint32_t frameCounter;
+} orc_primary_constants;
+
+/* src/gfx/modules/pathtracer.ixx:170-177 <-> src/gpu/secondaryRays.comp:25-32 */
+typedef struct {
+    orc_mat4 view, projection, invView, invProjection;
+    float cameraPos[3];
+    uint32_t frameCounter;
+} orc_secondary_constants;
+
+/* src/gpu/intersect.glsl:9-13 */
+typedef struct { float center[3]; float radius; float albedo[3]; } orc_sphere;
+
+/* src/gfx/modules/sky.ixx:28-56 (std140 mirror, 144 bytes) */
+typedef struct {
+    float bottomRadius, topRadius, rayleighDensityExpScale, _pad0;
+    float rayleighScattering[3]; float mieDensityExpScale;
+    float mieScattering[3]; float _pad1;
+    float mieExtinction[3]; float _pad2;
+    float mieAbsorption[3]; float miePhaseG;
+    float absorptionDensity0LayerWidth, absorptionDensity0ConstantTerm,
+          absorptionDensity0LinearTerm, absorptionDensity1ConstantTerm;
+    float absorptionDensity1LinearTerm, _pad3, _pad4, _pad5;
+    float absorptionExtinction[3]; float _pad6;
+    float groundAlbedo[3]; float _pad7;
+} orc_atmosphere_params;
+
+enum { ORC_TRANS_W = 256, ORC_TRANS_H = 64, ORC_MULTI_W = 32, ORC_MULTI_H = 32,
+       ORC_VIEW_W = 192, ORC_VIEW_H = 108 };
+
+enum { ORC_TONEMAP_LINEAR = 0, ORC_TONEMAP_REINHARD = 1, ORC_TONEMAP_HABLE = 2,
+       ORC_TONEMAP_ACES = 3, ORC_TONEMAP_UCHIMURA = 4, ORC_TONEMAP_AMD = 5 };
+
+/* ---- storage formats ---- */
+uint16_t orc_f32_to_f16(float f);
+float    orc_f16_to_f32(uint16_t h);
+uint32_t orc_pack_b10g11r11(const float rgb[3]);
+void     orc_unpack_b10g11r11(uint32_t p, float rgb[3]);
+uint8_t  orc_unorm8(float f);
+
+/* ---- host matrices (a1) ---- */
+void orc_camera_direction(const orc_camera* c, float out[3]);
+void orc_camera_view(const orc_camera* c, orc_mat4* out);
+void orc_camera_projection(const orc_camera* c, orc_mat4* out);
+void orc_look(const float pos[3], const float dir[3], const float up[3], orc_mat4* out);
+void orc_perspective(float vFov, float aspect, float zNear, orc_mat4* out);
+void orc_inverse(const orc_mat4* m, orc_mat4* out);
+void orc_mat_mul(const orc_mat4* a, const orc_mat4* b, orc_mat4* out);
+void orc_primary_constants_fill(const orc_camera* cam, const orc_camera* prev, uint32_t frame,
+                                orc_primary_constants* out);
+void orc_secondary_constants_fill(const orc_camera* cam, uint32_t frame,
+                                  orc_secondary_constants* out);
+void orc_atmosphere_earth(orc_atmosphere_params* out);
+/* Camera::rotate / shift / roam (src/gfx/camera.ixx:47-63) */
+void orc_camera_rotate(orc_camera* c, float horz, float vert);
+void orc_camera_shift(orc_camera* c, const float d[3]);
+void orc_camera_roam(orc_camera* c, const float d[3]);
+
+/* ---- RNG / sampling (a7-a9) ---- */
+uint32_t orc_pcg(uint32_t* state);
+float    orc_random_float(uint32_t* state);
+void     orc_random_sphere_point(float rx, float ry, float out[3]);
+
+/* ---- primitives (a3, n4) ---- */
+float orc_ray_sphere(const float o[3], const float d[3], const orc_sphere* s);
+/* returns 1 on hit; *t,*u,*v set (u,v barycentrics of v1,v2) */
+int orc_ray_triangle(const float o[3], const float d[3], const float v0[3], const float v1[3],
+                     const float v2[3], float* t, float* u, float* v);
+void orc_ray_gen(const orc_mat4* invView, const orc_mat4* invProjection, uint32_t x, uint32_t y,
+                 uint32_t w, uint32_t h, float origin[3], float dir[3]);
+
+/* ---- sky (a11, a13) ---- */
+void orc_gen_transmittance(const orc_atmosphere_params* p, uint16_t* rgba16f /*256*64*4*/);
+void orc_gen_multiscattering(const orc_atmosphere_params* p, const uint16_t* trans,
+                             uint16_t* rgba16f /*32*32*4*/);
+void orc_gen_sky_view(const orc_atmosphere_params* p, const uint16_t* trans, const uint16_t* multi,
+                      const float probePos[3], const float sunDir[3], const float sunIlluminance[3],
+                      uint32_t* b10g11r11 /*192*108*/);
+void orc_sky_color(const orc_atmosphere_params* p, const uint16_t* trans, const uint32_t* skyView,
+                   const float cameraPos[3], const float dir[3], float out[3]);
+
+/* ---- reference sphere path, faithful mode (a2-a12) ---- */
+void orc_primary_rays_spheres(uint32_t w, uint32_t h, const orc_primary_constants* c,
+                              const orc_sphere* spheres, uint32_t nspheres,
+                              uint32_t* visibility, uint16_t* depth, uint16_t* normal /*4/px*/,
+                              uint16_t* motion /*2/px*/);
+/* color16: RGBA16F (8 B/px) as the reference stores it; color32 (optional, may be NULL):
+ * the same average before fp16 rounding.  rays_out (optional): secondary rays traced. */
+void orc_secondary_rays_spheres(uint32_t w, uint32_t h, const orc_secondary_constants* c,
+                                const orc_sphere* spheres, uint32_t nspheres,
+                                const uint32_t* visibility, const uint16_t* depth,
+                                const uint16_t* normal, const uint8_t* blueNoise, uint32_t bnW,
+                                uint32_t bnH, const orc_atmosphere_params* atmo,
+                                const uint16_t* trans, const uint32_t* skyView, uint32_t spp,
+                                uint32_t bounces, uint16_t* color16, float* color32,
+                                uint64_t* rays_out);
+
+/* ---- tonemap (a14) ---- */
+/* src: RGBA16F if src_is_f16 else RGBA32F.  params: mode-specific push constants after exposure
+ * (reinhard: hdrMax; uchimura: 6 floats; amd: 5 floats). */
+void orc_tonemap(int mode, uint32_t w, uint32_t h, const void* src, int src_is_f16, float exposure,
+                 const float* params, uint8_t* rgba8);
+void orc_tonemap_pixel(int mode, const float rgb_in[3], float exposure, const float* params,
+                       float rgb_out[3]);
+
+/* ---- triangle scenes (n1-n7) ---- */
+typedef struct orc_scene orc_scene;
+orc_scene* orc_scene_create(const float* positions, uint32_t nverts, const uint32_t* indices,
+                            uint32_t ntris, const float* albedo /*3/tri*/);
+void orc_scene_destroy(orc_scene* s);
+/* closest hit for one ray. use_bvh=0 -> brute force. returns prim id or 0xFFFFFFFF */
+uint32_t orc_scene_closest_hit(const orc_scene* s, const float o[3], const float d[3], int use_bvh,
+                               float* t, float* u, float* v);
+/* G-buffer + fp32 hit (t; 0 on miss) for every pixel in rows [y0,y1) */
+void orc_primary_rays_tris(const orc_scene* s, uint32_t w, uint32_t h,
+                           const orc_primary_constants* c, int use_bvh, uint32_t y0, uint32_t y1,
+                           uint32_t* visibility, uint16_t* depth, uint16_t* normal,
+                           uint16_t* motion, float* hit_t);
+/* native path trace: accum (RGBA32F, += sample sums, .w += spp) for rows [y0,y1).
+ * rays_out: [0] primary rays, [1] secondary rays traced. */
+void orc_render_tris(const orc_scene* s, uint32_t w, uint32_t h, const orc_primary_constants* pc,
+                     const orc_secondary_constants* sc, const uint8_t* blueNoise, uint32_t bnW,
+                     uint32_t bnH, const orc_atmosphere_params* atmo, const uint16_t* trans,
+                     const uint32_t* skyView, uint32_t spp, uint32_t bounces, int use_bvh,
+                     uint32_t y0, uint32_t y1, float* accum, uint32_t* visibility,
+                     uint64_t* rays_out);
+/* accum (RGBA32F sums, w = spp) -> RGBA32F average */
+void orc_resolve(uint32_t npixels, const float* accum, float* color32);
+
+int orc_num_threads(void);
+void orc_set_num_threads(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,261 @@
+"""GPU parity, triangle path: BVH build + traversal + wavefront shading
+through the C ABI vs the CPU oracle (brute force on small scenes, oracle BVH on larger ones)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from minotert_b200 import capi, scenes
+from test_gpu_spheres import as_capi, setup_sky, ulp16_diff
+
+pytestmark = pytest.mark.gpu
+
+
+def camera_for(oracle, view, w, h):
+    return oracle.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+
+
+def random_rays(n, lo, hi, seed):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    return o, d
+
+
+@pytest.mark.parametrize("maker", ["cornell", "small_terrain"])
+def test_bvh_equals_brute_force_random_rays(gpu_ctx, oracle, maker):
+    pos, idx, alb, view = getattr(scenes, maker)()
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    st = gpu_ctx.stats()
+    assert st.num_triangles == idx.shape[0] and st.num_wide_nodes >= 1
+    lo, hi = pos.min(0) - 0.001, pos.max(0) + 0.001
+    o, d = random_rays(20000, lo, hi, 7)
+    ids_bvh, t_bvh = gpu_ctx.trace_rays(o, d)
+    ids_bf, t_bf = gpu_ctx.trace_rays(o, d, brute_force=True)
+    assert gpu_ctx.stats().stack_overflows == 0
+    assert np.array_equal(ids_bvh, ids_bf), f"{(ids_bvh != ids_bf).sum()} of {len(o)} hit ids differ (GPU BVH vs GPU brute force)"
+    assert np.array_equal(t_bvh, t_bf)
+    # and against the CPU oracle's brute force (same fp32 test, no contraction): bit-exact
+    sc = oracle.Scene(pos, idx, alb)
+    for k in range(0, 20000, 97):
+        i, t, _, _ = sc.closest_hit(o[k], d[k], use_bvh=False)
+        assert i == ids_bvh[k]
+        if i != oracle.NONE_ID:
+            assert np.float32(t) == t_bvh[k]
+
+
+def test_axis_parallel_and_edge_rays(gpu_ctx, oracle):
+    """Rays along axes, through shared edges and vertices of a tessellated quad: watertight, lowest id wins."""
+    pos, idx, alb, _ = scenes.cornell()
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    sc = oracle.Scene(pos, idx, alb)
+    # rays aimed exactly at mesh vertices (shared by up to 6 triangles) and edge midpoints of the floor grid
+    verts = pos[:81]
+    mids = 0.5 * (pos[idx[:128, 0]] + pos[idx[:128, 1]])
+    targets = np.concatenate([verts, mids]).astype(np.float32)
+    o = np.tile(np.array([[0.0, 0.0035, 0.1005]], np.float32), (targets.shape[0], 1))
+    d = targets - o
+    axis = np.array([[0, 0, -1], [0, 1, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1]], np.float32)
+    o = np.concatenate([o, np.tile(np.array([[0.0003, 0.0041, 0.1001]], np.float32), (5, 1))])
+    d = np.concatenate([d, axis])
+    ids, t = gpu_ctx.trace_rays(o, d)
+    ids_bf, t_bf = gpu_ctx.trace_rays(o, d, brute_force=True)
+    assert np.array_equal(ids, ids_bf) and np.array_equal(t, t_bf)
+    assert (ids != capi.MISS_ID).all()
+    for k in range(len(o)):
+        i, tt, _, _ = sc.closest_hit(o[k], d[k], use_bvh=False)
+        assert i == ids[k] and np.float32(tt) == t[k]
+
+
+def test_degenerate_and_tiny_meshes(gpu_ctx, oracle):
+    # one triangle
+    pos = np.array([[0, 1, 0], [1, 1, 0], [0, 1, 1]], np.float32)
+    idx = np.array([[0, 1, 2]], np.uint32)
+    alb = np.full((1, 3), 0.5, np.float32)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    ids, t = gpu_ctx.trace_rays([[0.2, 0, 0.2], [2, 0, 2]], [[0, 1, 0], [0, 1, 0]])
+    assert ids[0] == 0 and t[0] == 1.0 and ids[1] == capi.MISS_ID
+    # duplicates (equal t => lowest id), a zero-area triangle and 2..9 triangles
+    for n in range(2, 10):
+        p = np.concatenate([pos] * n + [np.array([[5, 5, 5], [5, 5, 5], [6, 6, 6]], np.float32)])
+        i = np.arange(3 * (n + 1), dtype=np.uint32).reshape(-1, 3)
+        a = np.full((n + 1, 3), 0.5, np.float32)
+        gpu_ctx.upload_mesh(p, i, a)
+        gpu_ctx.build()
+        ids, t = gpu_ctx.trace_rays([[0.2, 0, 0.2]], [[0, 1, 0]])
+        assert ids[0] == 0 and t[0] == 1.0
+    # empty mesh: everything misses
+    gpu_ctx.upload_mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), np.zeros((0, 3), np.float32))
+    gpu_ctx.build()
+    ids, t = gpu_ctx.trace_rays([[0, 0, 0]], [[0, 1, 0]])
+    assert ids[0] == capi.MISS_ID
+    with pytest.raises(capi.MinoteError, match="out of range"):
+        gpu_ctx.upload_mesh(pos, np.array([[0, 1, 3]], np.uint32), alb)
+
+
+def test_primary_gbuffer_cornell_config1(gpu_ctx, oracle):
+    """BASELINE config 1 geometry: 512x512 primary pass, hit ids bit-exact vs brute-force oracle."""
+    pos, idx, alb, view = scenes.cornell()
+    w = h = 512
+    cam = camera_for(oracle, view, w, h)
+    pc, _ = oracle.constants(cam)
+    sc = oracle.Scene(pos, idx, alb)
+    vis, depth, normal, motion, t = sc.primary(w, h, pc, use_bvh=False)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+    g_vis = gpu_ctx.readback(capi.BUF_VISIBILITY)
+    mism = (g_vis != vis).mean()
+    assert mism == 0.0, f"{mism:.2e} of primary hit ids differ"
+    assert np.array_equal(gpu_ctx.readback(capi.BUF_HIT_T), t)
+    assert ulp16_diff(gpu_ctx.readback(capi.BUF_DEPTH), depth).max() <= 1
+    assert ulp16_diff(gpu_ctx.readback(capi.BUF_NORMAL)[..., :3], normal[..., :3]).max() <= 1
+
+
+def render_both(gpu_ctx, oracle, sky_inputs, blue_noise, scene, w, h, spp, bounces, frame=1, use_bvh=True):
+    atmo, trans, multi, view_lut = sky_inputs
+    pos, idx, alb, view = scene
+    cam = camera_for(oracle, view, w, h)
+    pc, scn = oracle.constants(cam, frame=frame)
+    # sky LUTs for this camera from the oracle and from the GPU
+    trans, multi, view_lut = oracle.sky_luts(atmo, cam.position[:])
+    osc = oracle.Scene(pos, idx, alb)
+    acc, vis, rays = osc.render(w, h, pc, scn, blue_noise, atmo, trans, view_lut, spp, bounces, use_bvh=use_bvh)
+    setup_sky(gpu_ctx, oracle, atmo, cam.position[:])
+    gpu_ctx.upload_blue_noise(blue_noise)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+    gpu_ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), spp, bounces)
+    return acc, vis, rays, pc, scn
+
+
+def test_render_cornell_config1(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """BASELINE config 1: 512x512, 1 spp, 1 bounce; oracle = brute force."""
+    w = h = 512
+    acc, vis, rays, _, _ = render_both(gpu_ctx, oracle, sky_inputs, blue_noise, scenes.cornell(), w, h, 1, 1, use_bvh=False)
+    g_vis = gpu_ctx.readback(capi.BUF_VISIBILITY)
+    assert (g_vis != vis).mean() <= 1e-3
+    gacc = gpu_ctx.readback(capi.BUF_ACCUM)
+    st = gpu_ctx.stats()
+    assert st.stack_overflows == 0
+    assert st.primary_rays == rays[0]
+    assert abs(int(st.secondary_rays) - rays[1]) <= 1e-3 * rays[1] + 2
+    p = oracle.psnr(oracle.resolve(gacc)[..., :3], oracle.resolve(acc)[..., :3], 16.0)
+    assert p >= 50.0, f"PSNR {p:.1f} dB"
+    gpu_ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+    g_ldr = gpu_ctx.readback(capi.BUF_LDR)
+    o_ldr = oracle.tonemap("amd", oracle.resolve(acc))
+    assert (np.abs(g_ldr.astype(int) - o_ldr.astype(int)).max(-1) <= 1).mean() >= 0.998
+
+
+def test_render_multi_sample_multi_bounce(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """4 spp x 3 bounces: the PCG state threads through samples exactly as secondaryRays.comp:131-132."""
+    w, h = 200, 120
+    acc, vis, rays, _, _ = render_both(gpu_ctx, oracle, sky_inputs, blue_noise, scenes.small_terrain(), w, h, 4, 3)
+    gacc = gpu_ctx.readback(capi.BUF_ACCUM)
+    assert np.all(gacc[..., 3] == 4.0)
+    st = gpu_ctx.stats()
+    assert abs(int(st.secondary_rays) - rays[1]) <= 2e-3 * rays[1] + 2
+    p = oracle.psnr(oracle.resolve(gacc)[..., :3], oracle.resolve(acc)[..., :3], 16.0)
+    assert p >= 50.0, f"PSNR {p:.1f} dB"
+    # RGBA16F colour image the reference interface returns
+    g16 = gpu_ctx.readback(capi.BUF_COLOR)
+    assert oracle.psnr(oracle.f16_to_f32(g16)[..., :3], oracle.resolve(acc)[..., :3], 16.0) >= 50.0
+
+
+def test_render_260k_config2_reduced_resolution(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """BASELINE config 2 scene (~260k tris), 1 spp, 2 bounces, at 480x270 so the oracle finishes in seconds."""
+    w, h = 480, 270
+    acc, vis, rays, _, _ = render_both(gpu_ctx, oracle, sky_inputs, blue_noise, scenes.hall_260k(), w, h, 1, 2)
+    g_vis = gpu_ctx.readback(capi.BUF_VISIBILITY)
+    mism = (g_vis != vis).mean()
+    assert mism <= 1e-3, f"primary hit-id mismatch {mism:.2e}"
+    gacc = gpu_ctx.readback(capi.BUF_ACCUM)
+    st = gpu_ctx.stats()
+    assert st.stack_overflows == 0
+    p = oracle.psnr(oracle.resolve(gacc)[..., :3], oracle.resolve(acc)[..., :3], 16.0)
+    assert p >= 50.0, f"PSNR {p:.1f} dB"
+
+
+def test_progressive_accumulation(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """Row n7: frames f = 1..3 with seeds (f<<1)|1 accumulate; equals the oracle's accumulated sum."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.cornell()
+    w, h = 128, 128
+    cam = camera_for(oracle, view, w, h)
+    trans, multi, view_lut = oracle.sky_luts(atmo, cam.position[:])
+    osc = oracle.Scene(pos, idx, alb)
+    setup_sky(gpu_ctx, oracle, atmo, cam.position[:])
+    gpu_ctx.upload_blue_noise(blue_noise)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    acc = None
+    for f in (1, 2, 3):
+        pc, scn = oracle.constants(cam, frame=f)
+        acc, _, _ = osc.render(w, h, pc, scn, blue_noise, atmo, trans, view_lut, 2, 2, accum=acc)
+        gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+        gpu_ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 2, 2, capi.SECONDARY_ACCUMULATE if f > 1 else 0)
+    gacc = gpu_ctx.readback(capi.BUF_ACCUM)
+    assert np.all(gacc[..., 3] == 6.0)
+    assert oracle.psnr(oracle.resolve(gacc)[..., :3], oracle.resolve(acc)[..., :3], 16.0) >= 50.0
+
+
+def test_tile_partition_equals_single_context(oracle, sky_inputs, blue_noise):
+    """Row 8e: rank-r-of-N contexts render disjoint row slabs; reassembled image == 1-context image, bit for bit."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h = 160, 101  # not a multiple of the slab height
+    cam = camera_for(oracle, view, w, h)
+    pc, scn = oracle.constants(cam)
+
+    def render(rank, nranks):
+        ctx = capi.Context(0)
+        try:
+            setup_sky(ctx, oracle, atmo, cam.position[:])
+            ctx.upload_blue_noise(blue_noise)
+            ctx.upload_mesh(pos, idx, alb)
+            ctx.build()
+            ctx.set_partition(rank, nranks, 8)
+            ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+            ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 2, 2)
+            ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+            return ctx.partition_rows(h), ctx.readback(capi.BUF_ACCUM), ctx.readback(capi.BUF_LDR), ctx.readback(capi.BUF_VISIBILITY)
+        finally:
+            ctx.close()
+
+    rows1, acc1, ldr1, vis1 = render(0, 1)
+    assert np.array_equal(rows1, np.arange(h))
+    for nranks in (2, 3):
+        acc = np.zeros_like(acc1)
+        ldr = np.zeros_like(ldr1)
+        vis = np.zeros_like(vis1)
+        seen = np.zeros(h, bool)
+        for r in range(nranks):
+            rows, a, l, v = render(r, nranks)
+            assert not seen[rows].any()
+            seen[rows] = True
+            acc[rows], ldr[rows], vis[rows] = a, l, v
+        assert seen.all()
+        assert np.array_equal(vis, vis1) and np.array_equal(acc, acc1) and np.array_equal(ldr, ldr1)
+
+
+def test_refit_matches_full_rebuild(gpu_ctx, oracle):
+    """BASELINE config 5 mechanics: animate vertices, REFIT; closest hits equal a fresh FULL build and brute force."""
+    pos, idx, alb, _ = scenes.small_terrain()
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    moved = scenes.animate(pos, 0.37)
+    gpu_ctx.update_positions(moved)
+    gpu_ctx.build(capi.BUILD_REFIT)
+    o, d = random_rays(8000, moved.min(0) - 0.001, moved.max(0) + 0.001, 3)
+    ids_refit, t_refit = gpu_ctx.trace_rays(o, d)
+    ids_bf, t_bf = gpu_ctx.trace_rays(o, d, brute_force=True)
+    gpu_ctx.build(capi.BUILD_FULL)
+    ids_full, t_full = gpu_ctx.trace_rays(o, d)
+    assert np.array_equal(ids_refit, ids_bf) and np.array_equal(t_refit, t_bf)
+    assert np.array_equal(ids_full, ids_bf) and np.array_equal(t_full, t_bf)

@@ -1,0 +1,151 @@
+"""GPU parity, reference sphere scene: CUDA path through the C ABI vs
+the CPU oracle on the same PODs.  Integer outputs bit-exact; fp16/fp32 outputs within stated bounds."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from minotert_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def as_capi(obj, cls):
+    out = cls()
+    C.memmove(C.byref(out), C.byref(obj), C.sizeof(cls))
+    return out
+
+
+def setup_sky(ctx, oracle, atmo, cam_pos):
+    ctx.atmosphere(as_capi(atmo, capi.AtmosphereParams))
+    ctx.sky_view(cam_pos, oracle.SUN_DIRECTION, oracle.SUN_ILLUMINANCE)
+
+
+def ulp16_diff(a, b):
+    """distance in fp16 representable steps between two uint16 bit patterns (same sign assumed)."""
+    def key(x):
+        x = x.astype(np.int32)
+        return np.where(x & 0x8000, -(x & 0x7FFF), x & 0x7FFF)
+    return np.abs(key(a) - key(b))
+
+
+def test_sky_luts_match_oracle(gpu_ctx, oracle, sky_inputs):
+    atmo, trans, multi, view = sky_inputs
+    cam = oracle.default_camera()
+    setup_sky(gpu_ctx, oracle, atmo, cam.position[:])
+    g_trans = gpu_ctx.readback(capi.BUF_TRANSMITTANCE)
+    g_multi = gpu_ctx.readback(capi.BUF_MULTISCATTERING)
+    g_view = gpu_ctx.readback(capi.BUF_SKY_VIEW)
+    # expf/sinf/cosf/powf differ by <= 2 ulp(fp32) between libdevice and glibc; after ~40 integration steps
+    # and rounding to fp16 (11-bit significand) the LUT texels may differ by at most 1 fp16 step.
+    assert ulp16_diff(g_trans[..., :3], trans[..., :3]).max() <= 1
+    assert (g_trans[..., :3] != trans[..., :3]).mean() < 0.02
+    assert ulp16_diff(g_multi[..., :3], multi[..., :3]).max() <= 2
+    # B10G11R11: compare decoded values, one 6-bit-mantissa step = 1.6 % relative
+    def dec(v):
+        out = np.zeros(v.shape + (3,), np.float32)
+        buf = (C.c_float * 3)()
+        for idx in np.ndindex(v.shape):
+            oracle.lib().orc_unpack_b10g11r11(int(v[idx]), buf)
+            out[idx] = buf[:]
+        return out
+    dv, ov = dec(g_view), dec(view)
+    assert np.all(np.abs(dv - ov) <= 0.035 * np.maximum(ov, 1e-4))
+    assert (g_view != view).mean() < 0.02
+
+
+@pytest.mark.parametrize("size", [(960, 540), (512, 512), (67, 35)])
+def test_primary_spheres(gpu_ctx, oracle, size):
+    w, h = size
+    cam = oracle.default_camera(w, h)
+    pc, _ = oracle.constants(cam)
+    sp = oracle.spheres_array()
+    vis, depth, normal, motion = oracle.primary_spheres(w, h, pc, sp)
+    gpu_ctx.set_spheres(oracle.REFERENCE_SPHERES)
+    gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+    g_vis = gpu_ctx.readback(capi.BUF_VISIBILITY)
+    assert np.array_equal(g_vis, vis), f"{(g_vis != vis).sum()} visibility ids differ"
+    g_depth = gpu_ctx.readback(capi.BUF_DEPTH)
+    g_normal = gpu_ctx.readback(capi.BUF_NORMAL)
+    g_motion = gpu_ctx.readback(capi.BUF_MOTION)
+    assert ulp16_diff(g_depth, depth).max() <= 1
+    assert ulp16_diff(g_normal[..., :3], normal[..., :3]).max() <= 1
+    assert np.array_equal(g_normal[..., 3], normal[..., 3])
+    assert np.abs(oracle.f16_to_f32(g_motion) - oracle.f16_to_f32(motion)).max() <= 1e-3
+
+
+def test_secondary_spheres_reference_config(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """The only configuration the reference itself renders: 960x540, 8 spp x 8 bounces, frame 1."""
+    atmo, trans, multi, view = sky_inputs
+    w, h = 960, 540
+    cam = oracle.default_camera(w, h)
+    pc, sc = oracle.constants(cam, frame=1)
+    sp = oracle.spheres_array()
+    vis, depth, normal, motion = oracle.primary_spheres(w, h, pc, sp)
+    c16, c32, rays = oracle.secondary_spheres(w, h, sc, sp, vis, depth, normal, blue_noise, atmo, trans, view)
+
+    setup_sky(gpu_ctx, oracle, atmo, cam.position[:])
+    gpu_ctx.upload_blue_noise(blue_noise)
+    gpu_ctx.set_spheres(oracle.REFERENCE_SPHERES)
+    gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+    gpu_ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), 8, 8)
+    g16 = gpu_ctx.readback(capi.BUF_COLOR)
+    gacc = gpu_ctx.readback(capi.BUF_ACCUM)
+    st = gpu_ctx.stats()
+    assert st.primary_rays == w * h
+    # ray counts differ only where an ulp-level difference flips a hit/miss decision
+    assert abs(int(st.secondary_rays) - rays) <= 2e-4 * rays
+    g32 = oracle.f16_to_f32(g16)
+    o32 = oracle.f16_to_f32(c16)
+    # north_star gate: PSNR >= 50 dB on linear radiance clamped to [0, hdrMax = 16], peak 16
+    p = oracle.psnr(g32[..., :3], o32[..., :3], 16.0)
+    assert p >= 50.0, f"PSNR {p:.1f} dB"
+    assert np.all(gacc[..., 3] == 8.0)
+    avg = gacc[..., :3] / 8.0
+    assert oracle.psnr(avg, c32[..., :3], 16.0) >= 50.0
+    # tonemapped framebuffer, default AMD operator: at most 1 code value on 99.9 % of pixels
+    gpu_ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_COLOR)
+    g_ldr = gpu_ctx.readback(capi.BUF_LDR)
+    o_ldr = oracle.tonemap("amd", c16)
+    diff = np.abs(g_ldr.astype(np.int32) - o_ldr.astype(np.int32)).max(axis=-1)
+    assert (diff <= 1).mean() >= 0.999
+
+
+@pytest.mark.parametrize("mode,params", [("linear", ()), ("reinhard", (8.0,)), ("hable", ()), ("aces", ()),
+                                          ("uchimura", (1.0, 1.0, 0.22, 0.4, 1.33, 0.0)),
+                                          ("amd", (16.0, 2.0, 1.0, 0.18, 0.18))])
+def test_tonemap_operators(gpu_ctx, oracle, sky_inputs, blue_noise, mode, params):
+    """Same RGBA16F input through each operator: <= 1 code value everywhere (powf/expf ulps)."""
+    atmo, trans, multi, view = sky_inputs
+    w, h = 160, 90
+    cam = oracle.default_camera(w, h)
+    pc, sc = oracle.constants(cam)
+    setup_sky(gpu_ctx, oracle, atmo, cam.position[:])
+    gpu_ctx.upload_blue_noise(blue_noise)
+    gpu_ctx.set_spheres(oracle.REFERENCE_SPHERES)
+    gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+    gpu_ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), 2, 3)
+    g16 = gpu_ctx.readback(capi.BUF_COLOR)
+    gpu_ctx.tonemap(mode, 1.3, params, capi.BUF_COLOR)
+    g_ldr = gpu_ctx.readback(capi.BUF_LDR)
+    o_ldr = oracle.tonemap(mode, g16, 1.3, params if params else (0.0,))
+    diff = np.abs(g_ldr.astype(np.int32) - o_ldr.astype(np.int32))
+    assert diff.max() <= 1, f"{mode}: max diff {diff.max()}"
+    assert (diff > 0).mean() < 0.01
+    assert np.all(g_ldr[..., 3] == 255)
+
+
+def test_call_order_errors(gpu_ctx, oracle):
+    """Error behaviour across the seam: status codes + sticky message, no exceptions from C."""
+    cam = oracle.default_camera(64, 64)
+    pc, sc = oracle.constants(cam)
+    with pytest.raises(capi.MinoteError, match="no scene"):
+        gpu_ctx.primary_rays(64, 64, as_capi(pc, capi.PrimaryConstants))
+    gpu_ctx.set_spheres(oracle.REFERENCE_SPHERES)
+    with pytest.raises(capi.MinoteError, match="before primary"):
+        gpu_ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), 1, 1)
+    gpu_ctx.primary_rays(64, 64, as_capi(pc, capi.PrimaryConstants))
+    with pytest.raises(capi.MinoteError, match="sky LUTs"):
+        gpu_ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), 1, 1)
+    with pytest.raises(capi.MinoteError):
+        gpu_ctx.readback(capi.BUF_LDR)
