@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s (primary + secondary) of the MinoteRT hot path on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                      # our arm
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                                 # CPU arm (oracle on host cores)
+
+A step is one frame of BASELINE.json configs[1]: the ~260k-triangle procedural scene at 1920x1080,
+1 spp, 2 bounces, blue-noise-rotated sampling: primaryRays -> secondaryRays -> tonemap, the reference's
+per-frame call order (src/gfx/renderer.ixx:56-62).  Rays are counted as the reference's structure
+implies: pixels x 1 primary + every secondary ray for which a traversal was issued.
+
+value : device-timed (CUDA events on the context's stream), scene/BVH/LUTs resident in HBM.
+e2e   : wall clock through the host modules' Renderer::draw(camera) (C++20 modules -> C ABI), camera PODs
+        coming from host memory and the RGBA8 framebuffer read back into pinned host memory every step.
+N > 1 : sample-set partition with a replicated BVH: rank r renders frame (step*N + r + 1), the fp32
+        accumulators are summed onto rank 0 with NCCL (reduce) and rank 0 tonemaps.  Weak scaling.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene generator, width, height, spp, bounces)
+    "hall_260k_1080p": ("hall_260k", 1920, 1080, 1, 2),      # BASELINE.json configs[1]
+    "scene_1m_1080p": ("scene_1m", 1920, 1080, 1, 1),        # north_star target: 1M tris, primary + one bounce
+    "scene_10m_4k": ("scene_10m", 3840, 2160, 4, 3),         # configs[2]
+    "cornell_512": ("cornell", 512, 512, 1, 1),              # configs[0]
+}
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_scene(name):
+    from minotert_b200 import scenes
+    return getattr(scenes, name)()
+
+
+# ----------------------------------------------------------------------------- CPU arm
+
+def oracle_sample(workload, budget_s=15.0):
+    """Times the CPU oracle (all host threads) on a bounded row strip of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    gen, w, h, spp, bounces = WORKLOADS[workload]
+    pos, idx, alb, view = make_scene(gen)
+    cam = O.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+    atmo = O.earth()
+    trans, multi, skyv = O.sky_luts(atmo, cam.position[:])
+    bn = O.load_blue_noise()
+    scene = O.Scene(pos, idx, alb)  # oracle's own binary BVH (setup, untimed)
+    cores = O.lib().orc_num_threads()
+
+    def run(rows, frame):
+        pc, sc = O.constants(cam, frame=frame)
+        t0 = time.perf_counter()
+        acc, vis, rays = scene.render(w, h, pc, sc, bn, atmo, trans, skyv, spp, bounces, rows=rows)
+        O.tonemap("amd", O.resolve(acc)[rows[0]:rows[1]])
+        return time.perf_counter() - t0, rays[0] + rays[1]
+
+    mid = h // 2
+    dt, rays = run((mid - 8, mid + 8), 1)  # calibration strip (also warms the caches)
+    nrows = int(max(16, min(h, 16 * budget_s / max(dt, 1e-6))))
+    y0 = max(0, mid - nrows // 2)
+    rows = (y0, min(h, y0 + nrows))
+    return run, rows, cores, (w, h, spp, bounces)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    steps, warmup = args.steps, args.warmup
+    run, rows, cores, (w, h, spp, bounces) = oracle_sample(wl, budget_s=max(2.0, 120.0 / max(1, steps + warmup)))
+    for i in range(warmup):
+        run(rows, i + 1)
+    t_total, rays_total = 0.0, 0
+    for i in range(steps):
+        dt, rays = run(rows, warmup + i + 1)
+        t_total += dt
+        rays_total += rays
+    value = rays_total / t_total / 1e6
+    sample = f"rows [{rows[0]},{rows[1]}) of {w}x{h} ({rows[1] - rows[0]} rows) per step, {spp} spp, {bounces} bounces"
+    line = {"impl": "reference", "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t_total / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl, "note": "CPU oracle (port of the reference's GLSL path + binary BVH); the reference's "
+                       "Vulkan renderer cannot run here (no lavapipe/glslc, MSVC-only host)"},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from minotert_b200 import capi, host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    wl = args.workload
+    gen, w, h, spp, bounces = WORKLOADS[wl]
+    if args.spp:
+        spp = args.spp
+    if args.bounces is not None:
+        bounces = args.bounces
+    pos, idx, alb, view = make_scene(gen)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from PIL import Image
+    bn = np.ascontiguousarray(np.array(Image.open(os.path.join(ROOT, "assets", "blue_noise.png")).convert("RGBA"), np.uint8))
+
+    # host modules: Cuda::Provider + Renderer::Provider, scene upload + BVH build (setup, untimed)
+    r = host.Renderer(w, h, bn, device=local)
+    r.set_mesh(pos, idx, alb)
+    r.configure(samples=spp, bounces=bounces, accumulate=False, tonemap="amd", exposure=1.0)
+    ctx = r.context()
+    cam = host.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+    r.draw(cam)  # builds the atmosphere LUTs + sky view, allocates every frame buffer
+    ctx.sync()
+    build_stats = ctx.stats()
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    npix = w * h
+    amd = (16.0, 2.0, 1.0, 0.18, 0.18)
+    accum_ptr, accum_bytes = ctx.buffer(capi.BUF_ACCUM)
+
+    class _Wrap:  # zero-copy torch view of the context's fp32 accumulator (for the NCCL reduce)
+        __cuda_array_interface__ = {"shape": (npix * 4,), "typestr": "<f4", "data": (accum_ptr, False), "version": 2}
+    accum_t = torch.as_tensor(_Wrap(), device=f"cuda:{local}") if world > 1 else None
+
+    def frame(frame_no, tonemap=True):
+        pc, sc = host.camera_constants(cam, cam, frame_no)
+        ctx.primary_rays(w, h, pc)
+        ctx.secondary_rays(sc, spp, bounces, 0)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
+        if tonemap and rank == 0:
+            ctx.tonemap("amd", 1.0, amd, capi.BUF_ACCUM)
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush_buf.zero_()
+
+    # per-ray visit counts for the algorithmic-bytes figure (untimed, counted pass)
+    ctx.set_option("count_visits", 1)
+    frame(1)
+    st = ctx.stats()
+    nodes_per_ray = st.node_visits / max(1, st.primary_rays + st.secondary_rays)
+    tris_per_ray = st.tri_tests / max(1, st.primary_rays + st.secondary_rays)
+    ctx.set_option("count_visits", 0)
+
+    for i in range(args.warmup):
+        frame(i * world + rank + 1)
+    ctx.sync()
+    ctx.stats_reset()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    rays_total, trace_ms, trace_launches, trace_rays, primary_ms = 0, 0.0, 0, 0, 0.0
+    for i in range(args.steps):
+        flush_l2()
+        ev[i][0].record(stream)
+        frame((args.warmup + i) * world + rank + 1)
+        ev[i][1].record(stream)
+        st = ctx.stats()  # syncs; outside the event-bracketed region
+        rays_total += st.primary_rays + st.secondary_rays
+        trace_ms += st.ms_trace
+        trace_launches += st.trace_launches
+        trace_rays += st.secondary_rays
+        primary_ms += st.ms_primary
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = ctx.stats().kernel_launches
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- e2e: Renderer::draw(camera) + framebuffer readback into pinned host memory, wall clock
+    fb = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
+    fb_ptr = C.c_void_p(fb.data_ptr())
+    for _ in range(2):
+        r.draw(cam)
+        r.read_framebuffer_into(fb_ptr, fb.numel())
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_rays, t0 = 0, time.perf_counter()
+    for i in range(args.steps):
+        if world > 1:
+            frame(r.frame_count() * world + rank + 1)
+            if rank == 0:
+                ctx.readback_into(capi.BUF_LDR, fb_ptr, fb.numel())
+            else:
+                ctx.sync()
+        else:
+            r.draw(cam)                                   # host: camera -> constants -> sky view -> primary -> secondary -> tonemap
+            r.read_framebuffer_into(fb_ptr, fb.numel())   # D2H, blocks until the frame is done
+        st = ctx.stats()  # the frame is already complete (readback/sync above); a few counters, device -> host
+        e2e_rays += st.primary_rays + st.secondary_rays
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    counts = torch.tensor([rays_total, e2e_rays, launches], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms = times.tolist()
+    rays_all, e2e_rays_all, launches_all = counts.tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bytes_per_ray = 32 + 16 + 80.0 * nodes_per_ray + 48.0 * tris_per_ray
+        achieved = (trace_rays * bytes_per_ray) / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "trace_traffic.json")) as f:
+                traffic = json.load(f).get(wl)
+        except Exception:
+            pass
+        line = {
+            "metric": "Mrays/s (primary+secondary)", "value": rays_all / (dev_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl, "triangles": int(idx.shape[0]), "resolution": [w, h], "spp": spp, "bounces": bounces,
+                       "sampling": "PCG + blue-noise Cranley-Patterson rotation", "tonemap": "amd",
+                       "l2": "flushed between steps (256 MiB memset)", "bvh_bytes": int(build_stats.bvh_bytes),
+                       "wide_nodes": int(build_stats.num_wide_nodes), "bvh_build_ms": build_stats.ms_build,
+                       "parallelism": "1 GPU" if world == 1 else f"sample sets over {world} GPUs, replicated BVH, NCCL reduce of the fp32 accumulator"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_rays_all / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                    "h2d_bytes_per_step": 44 + 324 + 272 + 36, "d2h_bytes_per_step": int(fb.numel()),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "hbm", "kernel": "k_trace (secondary-ray BVH traversal)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                         "launches": trace_launches, "avg_launch_ms": trace_ms / max(1, trace_launches),
+                         "share_of_step": trace_ms / max(dev_ms if world == 1 else dev_ms, 1e-9),
+                         "note": "algorithmic bytes; the BVH of this config fits in L2, so frac > DRAM utilisation"},
+            "kernels": {"primary_ms_per_step": primary_ms / args.steps, "trace_ms_per_step": trace_ms / args.steps},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            run, rows, cores, _ = oracle_sample(wl, budget_s=15.0)
+            dt, rays = run(rows, args.warmup + 1)
+            line["cpu_baseline"] = {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                    "sample": f"rows [{rows[0]},{rows[1]}) of {w}x{h}, 1 frame, {dt:.1f} s; CPU oracle with its own binary BVH "
+                                              "(stands in for Mesa lavapipe, which is not installable offline)"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hall_260k_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0)
+    ap.add_argument("--bounces", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,8 @@ typedef struct {
     uint64_t bvh_bytes;       /* wide nodes + reordered triangles resident in HBM */
     uint64_t node_visits;     /* wide nodes fetched / triangles tested by the last counted trace */
     uint64_t tri_tests;       /*   (only when mrt_set_option("count_visits", 1))            */
+    uint32_t trace_launches;  /* traversal kernel launches inside the last mrt_secondary_rays */
+    uint32_t _reserved;
 } mrt_stats;
 
 /* ---- lifetime ---- */
@@ -160,6 +162,9 @@ int mrt_set_partition(mrt_context* ctx, uint32_t rank, uint32_t nranks, uint32_t
 /* rows of the full image owned by this context, in local storage order */
 int mrt_partition_rows(const mrt_context* ctx, uint32_t full_h, uint32_t* rows_out,
                        uint32_t* nrows_out);
+/* same mapping without a context (host-side gather/scatter logic, usable without a GPU) */
+int mrt_partition_rows_for(uint32_t rank, uint32_t nranks, uint32_t slab_rows, uint32_t full_h,
+                           uint32_t* rows_out, uint32_t* nrows_out);
 
 /* ---- per-frame render calls, in the order of Renderer_impl::draw (renderer.ixx:56-62) ---- */
 /* Pathtracer::primaryRays(size, camera, prevCamera) -> GBuffer (pathtracer.ixx:29-116) */

@@ -46,7 +46,8 @@ class Stats(C.Structure):
                 ("ms_secondary", C.c_float), ("ms_trace", C.c_float), ("ms_tonemap", C.c_float),
                 ("ms_build", C.c_float), ("ms_sky", C.c_float), ("kernel_launches", C.c_uint32),
                 ("stack_overflows", C.c_uint32), ("num_triangles", C.c_uint32), ("num_wide_nodes", C.c_uint32),
-                ("bvh_bytes", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64)]
+                ("bvh_bytes", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
+                ("trace_launches", C.c_uint32), ("_reserved", C.c_uint32)]
 
 
 EXPORTS = [
@@ -54,7 +55,7 @@ EXPORTS = [
     "mrt_scene_set_spheres", "mrt_scene_upload_mesh", "mrt_scene_update_positions", "mrt_scene_build",
     "mrt_atmosphere", "mrt_sky_view", "mrt_set_partition", "mrt_partition_rows", "mrt_primary_rays",
     "mrt_secondary_rays", "mrt_tonemap", "mrt_buffer", "mrt_readback", "mrt_sync", "mrt_stats_get",
-    "mrt_stats_reset", "mrt_stream", "mrt_trace_rays",
+    "mrt_stats_reset", "mrt_stream", "mrt_trace_rays", "mrt_partition_rows_for",
 ]
 
 
@@ -101,6 +102,7 @@ def load():
     L.mrt_stats_reset.argtypes = [vp]
     L.mrt_stream.argtypes = [vp, C.POINTER(vp)]
     L.mrt_trace_rays.argtypes = [vp, vp, vp, u32, vp, vp, C.c_int]
+    L.mrt_partition_rows_for.argtypes = [u32, u32, u32, u32, vp, C.POINTER(u32)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("mrt_destroy", "mrt_last_error"):

@@ -121,6 +121,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->hits); dev_free(ctx->queue_counts); dev_free(ctx->sort_keys); dev_free(ctx->sort_keys_alt);
     dev_free(ctx->sort_vals); dev_free(ctx->sort_vals_alt); dev_free(ctx->visit_counters);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->trace_ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -157,7 +158,7 @@ int mrt_scene_set_spheres(mrt_context* ctx, const mrt_sphere* spheres, uint32_t 
     for (uint32_t i = 0; i < n; i++) ctx->spheres.s[i] = spheres[i];
     ctx->spheres.n = n;
     ctx->scene_kind = 1;
-    ctx->have_gbuffer = false;
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = false;  // a new scene restarts accumulation
     return MRT_OK;
 }
 
@@ -183,7 +184,7 @@ int mrt_scene_upload_mesh(mrt_context* ctx, const float* positions, uint32_t nve
     ctx->ntris = ntris;
     ctx->scene_kind = 2;
     ctx->bvh_valid = false;
-    ctx->have_gbuffer = false;
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = false;  // a new scene restarts accumulation
     return MRT_OK;
 }
 
@@ -239,6 +240,17 @@ int mrt_partition_rows(const mrt_context* ctx, uint32_t full_h, uint32_t* rows_o
     *nrows_out = n;
     if (rows_out)
         for (uint32_t lr = 0; lr < n; lr++) rows_out[lr] = partition_local_to_y(ctx->part, lr);
+    return MRT_OK;
+}
+
+int mrt_partition_rows_for(uint32_t rank, uint32_t nranks, uint32_t slab_rows, uint32_t full_h, uint32_t* rows_out,
+                           uint32_t* nrows_out) {
+    if (!nrows_out || nranks == 0 || rank >= nranks || slab_rows == 0) return MRT_ERR_INVALID;
+    Partition p{rank, nranks, slab_rows};
+    uint32_t n = partition_local_rows(p, full_h);
+    *nrows_out = n;
+    if (rows_out)
+        for (uint32_t lr = 0; lr < n; lr++) rows_out[lr] = partition_local_to_y(p, lr);
     return MRT_OK;
 }
 
@@ -353,6 +365,12 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
             ctx->stats.secondary_rays = total;
         }
     }
+    ctx->stats.ms_trace = 0.0f;
+    ctx->stats.trace_launches = ctx->scene_kind == 2 ? ctx->trace_ev_used : 0;
+    if (ctx->scene_kind == 2 && ctx->have_accum)
+        for (uint32_t i = 0; i < ctx->trace_ev_used; i++)
+            if (cudaEventElapsedTime(&ms, ctx->trace_ev[2 * i], ctx->trace_ev[2 * i + 1]) == cudaSuccess) ctx->stats.ms_trace += ms;
+    cudaGetLastError();
     if (ctx->scene_kind == 2 && ctx->visit_counters.p) {
         unsigned long long vc[8];
         MRT_CUDA(ctx, cudaMemcpy(vc, ctx->visit_counters.p, sizeof vc, cudaMemcpyDeviceToHost));

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/minotert.h"
 #include "sky.cuh"
 #include "vec.cuh"
@@ -123,6 +125,8 @@ struct mrt_context {
     // stats
     mrt_stats stats{};
     cudaEvent_t ev[8] = {nullptr};
+    std::vector<cudaEvent_t> trace_ev;  // begin/end pairs around each traversal launch of the last frame
+    uint32_t trace_ev_used = 0;
 };
 
 // ---- error plumbing ----

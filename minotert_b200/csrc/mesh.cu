@@ -283,6 +283,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     const unsigned shade_grid = div_up(npix, 256), trace_grid = div_up(npix, TRACE_BLOCK);
 
     uint32_t wave = 0;
+    ctx->trace_ev_used = 0;
     for (uint32_t s = 0; s < spp; s++) {
         P.first_sample = s == 0;
         P.vertex = 0;
@@ -295,9 +296,17 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         MRT_LAUNCHED(ctx);
         for (uint32_t b = 1; b <= bounces; b++) {
             const uint32_t* in_count = ctx->queue_counts.p + wave;
+            while (ctx->trace_ev.size() < 2 * (size_t)(ctx->trace_ev_used + 1)) {
+                cudaEvent_t e;
+                MRT_CUDA(ctx, cudaEventCreate(&e));
+                ctx->trace_ev.push_back(e);
+            }
+            cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used], ctx->stream);
             k_trace<<<trace_grid, TRACE_BLOCK, 0, ctx->stream>>>(bvh, ctx->ray_o[q].p, ctx->ray_d[q].p, in_count, ctx->hits.p,
                                                                  ctx->visit_counters.p + 4, ctx->opt_count_visits);
             MRT_LAUNCHED(ctx);
+            cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used + 1], ctx->stream);
+            ctx->trace_ev_used++;
             wave++;
             P.vertex = b;
             // the last vertex emits nothing; its counter slot stays 0

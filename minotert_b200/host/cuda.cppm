@@ -1,0 +1,75 @@
+// minote.cuda -- the device service of the B200 build.  It takes the place of the reference's
+// Vulkan service (src/sys/vulkan.ixx:44-49,106-115): owns one mrt_context (CUDA device + stream +
+// all device memory) and is reached by the gfx modules through the same Service<T> locator pattern
+// (src/util/service.ixx:13-55).  Status codes from the C ABI become std::runtime_error here, which
+// preserves the reference's exception behaviour (stx/except.ixx, caught in App::run).
+module;
+#include <cstdint>
+
+#include "../../include/minotert.h"
+export module minote.cuda;
+
+export class Cuda_impl {
+public:
+    explicit Cuda_impl(int device = 0);  // throws std::runtime_error when no CUDA device exists (no fallback)
+    ~Cuda_impl() { mrt_destroy(ctx); }
+    Cuda_impl(Cuda_impl const&) = delete;
+    auto operator=(Cuda_impl const&) -> Cuda_impl& = delete;
+
+    // throw on any non-OK status, carrying the context's sticky message
+    void check(int status) const {
+        if (status != MRT_OK) fail(status);
+    }
+    [[noreturn]] void raise(char const* message) const;  // std::logic_error, defined in cuda_impl.cpp
+    [[nodiscard]] auto frameCount() const -> std::uint32_t { return frames; }
+    void nextFrame() { frames += 1; }  // vuk::Context::next_frame(): 1 on the first frame (renderer.ixx:41,52)
+
+    mrt_context* ctx = nullptr;
+
+private:
+    [[noreturn]] void fail(int status) const;  // defined in cuda_impl.cpp (keeps <string> out of importers)
+    std::uint32_t frames = 0;
+};
+
+// Service locator in the style of src/util/service.ixx:13-55: a Provider owns the instance for a scope,
+// consumers inherit from the service class and reach the instance through Cuda::serv.
+// (Written per service instead of as a class template: g++ 13's -fmodules-ts miscompiles the
+// exception clean-up of a variadic constructor of a nested class of an exported template.)
+export class Cuda {
+public:
+    class Provider {
+    public:
+        explicit Provider(int device = 0) : inst(new Cuda_impl(device)), prev(serv) { serv = inst; }
+        ~Provider() {
+            serv = prev;
+            delete inst;
+        }
+        Provider(Provider const&) = delete;
+        auto operator=(Provider const&) -> Provider& = delete;
+
+    private:
+        Cuda_impl* inst;
+        Cuda_impl* prev;
+    };
+    static inline Cuda_impl* serv = nullptr;
+};
+
+// A rendered device image: borrowed pointer into the context, valid until that buffer is re-rendered
+// at another size (what a vuk::Future resolves to after execution).
+export struct DeviceImage {
+    int id = -1;  // mrt_buffer_id
+    [[nodiscard]] auto valid() const -> bool { return id >= 0; }
+    [[nodiscard]] auto data() const -> void* {
+        void* p = nullptr;
+        std::size_t n = 0;
+        Cuda::serv->check(mrt_buffer(Cuda::serv->ctx, id, &p, &n));
+        return p;
+    }
+    [[nodiscard]] auto bytes() const -> std::size_t {
+        void* p = nullptr;
+        std::size_t n = 0;
+        Cuda::serv->check(mrt_buffer(Cuda::serv->ctx, id, &p, &n));
+        return n;
+    }
+    void readback(void* host, std::size_t n) const { Cuda::serv->check(mrt_readback(Cuda::serv->ctx, id, host, n)); }
+};

@@ -1,0 +1,117 @@
+// minote.renderer -- frame orchestration, Renderer_impl::draw(camera) (src/gfx/renderer.ixx:39-68):
+// sky LUTs -> primaryRays -> secondaryRays -> [denoise: out of scope] -> tonemap, same order and
+// defaults (AMD tonemapper, exposure 1, renderer.ixx:183-184).  Presentation (swapchain blit) is
+// replaced by an RGBA8 framebuffer the caller reads back.
+module;
+#include <cstdint>
+
+#include "../../include/minotert.h"
+export module minote.renderer;
+import minote.math;
+import minote.camera;
+import minote.cuda;
+import minote.modules.sky;
+import minote.modules.pathtracer;
+import minote.modules.tonemapper;
+
+export enum class TonemapMode : int { Linear = 0, Reinhard = 1, Hable = 2, ACES = 3, Uchimura = 4, AMD = 5 };
+
+export class Renderer_impl : Cuda {
+public:
+    // blue noise: decoded RGBA8 pixels of assets/blue_noise.png (renderer.ixx:101-110)
+    Renderer_impl(uvec2 outputSize, std::uint8_t const* blueNoiseRgba8, uvec2 blueNoiseSize) : outputSize(outputSize) {
+        Cuda::serv->check(mrt_upload_blue_noise(Cuda::serv->ctx, blueNoiseRgba8, blueNoiseSize.x(), blueNoiseSize.y()));
+        blueNoise.id = 0;
+    }
+    ~Renderer_impl() { delete atmosphere; }
+    Renderer_impl(Renderer_impl const&) = delete;
+    auto operator=(Renderer_impl const&) -> Renderer_impl& = delete;
+
+    // scene selection (the reference compiles its scene into the shader, src/gpu/scene.glsl)
+    void setSpheres(mrt_sphere const* spheres, u32 n) { Cuda::serv->check(mrt_scene_set_spheres(Cuda::serv->ctx, spheres, n)); }
+    void setMesh(float const* positions, u32 nverts, std::uint32_t const* indices, u32 ntris, float const* albedo) {
+        Cuda::serv->check(mrt_scene_upload_mesh(Cuda::serv->ctx, positions, nverts, indices, ntris, albedo));
+        Cuda::serv->check(mrt_scene_build(Cuda::serv->ctx, MRT_BUILD_FULL));
+    }
+    void updateMesh(float const* positions, u32 nverts, bool refit) {
+        Cuda::serv->check(mrt_scene_update_positions(Cuda::serv->ctx, positions, nverts));
+        Cuda::serv->check(mrt_scene_build(Cuda::serv->ctx, refit ? MRT_BUILD_REFIT : MRT_BUILD_FULL));
+    }
+
+    void draw(Camera const& camera) {
+        // Begin the frame
+        Cuda::serv->nextFrame();
+        // Initial temporal resource values
+        if (Cuda::serv->frameCount() == 1) prevCamera = camera;
+
+        // transmittance / multi-scattering depend only on the (constant) parameters: the reference
+        // rebuilds them every frame (renderer.ixx:56), here once per parameter set
+        if (!atmosphere) atmosphere = new Atmosphere(Atmosphere::Params::earth());
+        auto sky = Sky();
+        auto skyView = sky.createView(*atmosphere, camera.position);
+        auto gbuffer = pathtracer.primaryRays(outputSize, camera, prevCamera);
+        auto pathtraced = pathtracer.secondaryRays(gbuffer, camera, *atmosphere, skyView, blueNoise);
+        framebuffer = tonemap(pathtraced);
+
+        // Temporal preservation
+        prevCamera = camera;
+    }
+
+    // host copy of the output framebuffer (RGBA8); blocks until the frame is done
+    void readFramebuffer(void* host, std::size_t bytes) const { framebuffer.readback(host, bytes); }
+    [[nodiscard]] auto stats() const -> mrt_stats {
+        mrt_stats s;
+        Cuda::serv->check(mrt_stats_get(Cuda::serv->ctx, &s));
+        return s;
+    }
+
+    uvec2 outputSize;
+    Pathtracer pathtracer;
+    Tonemapper tonemapper;
+    // ImGui statics of Renderer_impl::tonemap (renderer.ixx:183-187)
+    float exposure = 1.0f;
+    TonemapMode tonemapMode = TonemapMode::AMD;
+    float reinhardMax = 8.0f;
+    UchimuraParams uchimuraParams = UchimuraParams::make_default();
+    AMDParams amdParams = AMDParams::make_default();
+    DeviceImage framebuffer;
+
+private:
+    auto tonemap(DeviceImage color) -> DeviceImage {
+        switch (tonemapMode) {
+        case TonemapMode::Linear: return tonemapper.linear(color, exposure);
+        case TonemapMode::Reinhard: return tonemapper.reinhard(color, exposure, reinhardMax);
+        case TonemapMode::Hable: return tonemapper.hable(color, exposure);
+        case TonemapMode::ACES: return tonemapper.aces(color, exposure);
+        case TonemapMode::Uchimura: return tonemapper.uchimura(color, exposure, uchimuraParams);
+        case TonemapMode::AMD: return tonemapper.amd(color, exposure, amdParams);
+        default: Cuda::serv->raise("Unknown tonemap mode");
+        }
+    }
+
+    Camera prevCamera{};
+    DeviceImage blueNoise;
+    Atmosphere* atmosphere = nullptr;
+};
+
+export class Renderer {
+public:
+    class Provider {
+    public:
+        Provider(uvec2 outputSize, std::uint8_t const* blueNoiseRgba8, uvec2 blueNoiseSize)
+            : inst(new Renderer_impl(outputSize, blueNoiseRgba8, blueNoiseSize)), prev(serv) {
+            serv = inst;
+        }
+        ~Provider() {
+            serv = prev;
+            delete inst;
+        }
+        Provider(Provider const&) = delete;
+        auto operator=(Provider const&) -> Provider& = delete;
+
+    private:
+        Renderer_impl* inst;
+        Renderer_impl* prev;
+    };
+    static inline Renderer_impl* serv = nullptr;
+};
