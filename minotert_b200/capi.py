@@ -9,7 +9,10 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libminotert.so")
+# MINOTERT_LIB_DIR: directory holding an alternative build of libminotert.so / libminote_host.so
+# (kernel-tuning variants built with different -D flags); default is the in-tree build.
+LIB_DIR = os.environ.get("MINOTERT_LIB_DIR", _HERE)
+LIB_PATH = os.path.join(LIB_DIR, "libminotert.so")
 
 MISS_ID = 0xFFFFFFFF
 (BUF_VISIBILITY, BUF_DEPTH, BUF_NORMAL, BUF_MOTION, BUF_COLOR, BUF_ACCUM, BUF_LDR, BUF_TRANSMITTANCE,

@@ -134,6 +134,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "count_visits")) ctx->opt_count_visits = value != 0;
     else if (!strcmp(name, "sort_rays")) ctx->opt_sort_rays = value != 0;
     else if (!strcmp(name, "persistent")) ctx->opt_persistent = value != 0;
+    else if (!strcmp(name, "persistent_primary")) ctx->opt_persistent_primary = value != 0;
     else return mrt_fail(ctx, MRT_ERR_INVALID, "unknown option '%s'", name);
     return MRT_OK;
 }
@@ -358,7 +359,7 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
             MRT_CUDA(ctx, cudaMemcpy(&v, ctx->visit_counters.p + 4, sizeof v, cudaMemcpyDeviceToHost));
             ctx->stats.secondary_rays = v;
         } else {
-            std::vector<uint32_t> counts(ctx->queue_counts.cap);
+            std::vector<uint32_t> counts(ctx->num_queue_counts);
             MRT_CUDA(ctx, cudaMemcpy(counts.data(), ctx->queue_counts.p, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost));
             uint64_t total = 0;
             for (uint32_t v : counts) total += v;

@@ -290,18 +290,24 @@ __global__ void __launch_bounds__(128) k_collapse_emit(BinTree T, uint32_t level
     }
 }
 
-MRT_D uint32_t ceil_pow2_exponent(float ext) {
-    // biased exponent e such that 2^(e-127) * 255 >= ext
-    float s = ext / 255.0f;
+// Quantisation grid of a wide node, per axis: 255 steps of size 2^e starting two steps below the node
+// box, sized so that 250 steps span the box.  Every child plane then lies strictly inside the grid with
+// room to spare, which lets the traversal fold the integer->float decode into its FMA (trace.cuh) at the
+// price of a plane error of at most 1/512 step; planes are rounded outward with 1/128 step of slack.
+MRT_D uint32_t grid_exponent(float ext) {
+    // biased exponent e such that 2^(e-127) * 250 >= ext
+    float s = ext / 250.0f;
     uint32_t b = __float_as_uint(s);
     uint32_t e = (b >> 23) & 0xFFu;
     if (b & 0x7FFFFFu) e += 1;
-    // guard against rounding in the division above
-    while (e < 254u && __uint_as_float(e << 23) * 255.0f < ext) e++;
+    while (e < 254u && __uint_as_float(e << 23) * 250.0f < ext) e++;  // guard against rounding in the division
     return e > 254u ? 254u : e;
 }
 
 // One thread per wide node: quantise, pack, and copy the node's triangles in leaf order.
+// Leaf triangles: slot s owns bits 3s..3s+2 of leafmask24 (one bit per triangle present); the triangle
+// behind bit b is tris[tri_base + popc(leafmask24 & ((1 << b) - 1))].  Empty slots get the inverted
+// box lo = 255, hi = 0 and can never be hit.
 __global__ void __launch_bounds__(128)
 k_emit_nodes(BinTree T, uint32_t num_nodes, const int32_t* __restrict__ slot_node, const uint32_t* __restrict__ node_child_base,
              const uint32_t* __restrict__ node_tri_base, const uint32_t* __restrict__ order, const float* __restrict__ pos,
@@ -317,41 +323,39 @@ k_emit_nodes(BinTree T, uint32_t num_nodes, const int32_t* __restrict__ slot_nod
         nlo = f3(fminf(nlo.x, lo.x), fminf(nlo.y, lo.y), fminf(nlo.z, lo.z));
         nhi = f3(fmaxf(nhi.x, hi.x), fmaxf(nhi.y, hi.y), fmaxf(nhi.z, hi.z));
     }
-    uint32_t ex = ceil_pow2_exponent(nhi.x - nlo.x), ey = ceil_pow2_exponent(nhi.y - nlo.y),
-             ez = ceil_pow2_exponent(nhi.z - nlo.z);
-    float3 scale = f3(__uint_as_float(ex << 23), __uint_as_float(ey << 23), __uint_as_float(ez << 23));
+    uint32_t ex = grid_exponent(nhi.x - nlo.x), ey = grid_exponent(nhi.y - nlo.y), ez = grid_exponent(nhi.z - nlo.z);
+    float sc[3] = {__uint_as_float(ex << 23), __uint_as_float(ey << 23), __uint_as_float(ez << 23)};
+    float org[3] = {nlo.x - 2.0f * sc[0], nlo.y - 2.0f * sc[1], nlo.z - 2.0f * sc[2]};
     uint32_t qlo[3][2] = {{0, 0}, {0, 0}, {0, 0}}, qhi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    uint32_t meta[2] = {0, 0};
-    uint32_t imask = 0;
+    uint32_t imask = 0, leafmask = 0;
     uint32_t tri_base = node_tri_base[w];
     uint32_t tri_off = 0;
     for (int s = 0; s < 8; s++) {
         int c = sl[s];
-        if (c < 0) continue;
+        if (c < 0) {
+            for (int a = 0; a < 3; a++) qlo[a][s >> 2] |= 255u << (8 * (s & 3));
+            continue;
+        }
         float4 lo4 = T.lo[c], hi4 = T.hi[c];
         float clo[3] = {lo4.x, lo4.y, lo4.z}, chi[3] = {hi4.x, hi4.y, hi4.z};
-        float org[3] = {nlo.x, nlo.y, nlo.z}, sc[3] = {scale.x, scale.y, scale.z};
         for (int a = 0; a < 3; a++) {
-            float ql = 0.0f, qh = 0.0f;
+            float ql = 0.0f, qh = 255.0f;
             if (sc[a] > 0.0f) {
-                ql = floorf((clo[a] - org[a]) / sc[a]);
-                qh = ceilf((chi[a] - org[a]) / sc[a]);
+                const float slack = sc[a] * 0.0078125f;
+                ql = fminf(fmaxf(floorf((clo[a] - org[a]) / sc[a] - 0.01f), 0.0f), 255.0f);
+                qh = fminf(fmaxf(ceilf((chi[a] - org[a]) / sc[a] + 0.01f), 0.0f), 255.0f);
+                // outward rounding under the decode arithmetic (origin + q * scale)
+                while (ql > 0.0f && org[a] + ql * sc[a] > clo[a] - slack) ql -= 1.0f;
+                while (qh < 255.0f && org[a] + qh * sc[a] < chi[a] + slack) qh += 1.0f;
             }
-            ql = fminf(fmaxf(ql, 0.0f), 255.0f);
-            qh = fminf(fmaxf(qh, 0.0f), 255.0f);
-            // conservative under the decode arithmetic: origin + q * scale
-            while (ql > 0.0f && org[a] + ql * sc[a] > clo[a]) ql -= 1.0f;
-            while (qh < 255.0f && org[a] + qh * sc[a] < chi[a]) qh += 1.0f;
             qlo[a][s >> 2] |= (uint32_t)ql << (8 * (s & 3));
             qhi[a][s >> 2] |= (uint32_t)qh << (8 * (s & 3));
         }
         uint32_t cnt = bin_count(T, c);
-        uint32_t m;
         if (cnt > MRT_MAX_LEAF_TRIS) {
-            m = 0x20u | (24u + (uint32_t)s);
             imask |= 1u << s;
         } else {
-            m = (((1u << cnt) - 1u) << 5) | tri_off;
+            leafmask |= ((1u << cnt) - 1u) << (3 * s);
             uint32_t f0 = bin_first(T, c);
             for (uint32_t t = 0; t < cnt; t++) {
                 uint32_t prim = order[f0 + t];
@@ -363,12 +367,11 @@ k_emit_nodes(BinTree T, uint32_t num_nodes, const int32_t* __restrict__ slot_nod
             }
             tri_off += cnt;
         }
-        meta[s >> 2] |= m << (8 * (s & 3));
     }
     WideNode N;
-    N.w[0] = make_uint4(__float_as_uint(nlo.x), __float_as_uint(nlo.y), __float_as_uint(nlo.z),
+    N.w[0] = make_uint4(__float_as_uint(org[0]), __float_as_uint(org[1]), __float_as_uint(org[2]),
                         ex | (ey << 8) | (ez << 16) | (imask << 24));
-    N.w[1] = make_uint4(node_child_base[w], tri_base, meta[0], meta[1]);
+    N.w[1] = make_uint4(node_child_base[w], tri_base, leafmask, 0u);
     N.w[2] = make_uint4(qlo[0][0], qlo[0][1], qlo[1][0], qlo[1][1]);
     N.w[3] = make_uint4(qlo[2][0], qlo[2][1], qhi[0][0], qhi[0][1]);
     N.w[4] = make_uint4(qhi[1][0], qhi[1][1], qhi[2][0], qhi[2][1]);

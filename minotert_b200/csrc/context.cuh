@@ -12,10 +12,12 @@
 #include "vec.cuh"
 
 // ---- wide BVH (row n3): 80-byte compressed 8-wide node, five 128-bit words ----
-//  w0: origin.x, origin.y, origin.z (fp32 bits), ex | ey<<8 | ez<<16 | imask<<24
-//  w1: child_base, tri_base, meta[0..3], meta[4..7]
+//  w0: grid origin x, y, z (fp32 bits), ex | ey<<8 | ez<<16 | imask<<24   (grid step on axis a = 2^(e_a-127))
+//  w1: child_base, tri_base, leafmask24, 0
 //  w2: qlo_x[0..7], qlo_y[0..7]        w3: qlo_z[0..7], qhi_x[0..7]       w4: qhi_y[0..7], qhi_z[0..7]
-//  meta: 0 = empty; internal = 0x20 | (24 + slot); leaf = unary tri count << 5 | first tri offset (0..23)
+//  child plane = origin + q * step.  imask bit s: slot s is an inner node, the k-th set bit of imask is node
+//  child_base + k.  leafmask24 bits 3s..3s+2: triangles of leaf slot s, the k-th set bit of leafmask24 is
+//  triangle tri_base + k.  Empty slot: qlo = 255, qhi = 0.
 struct WideNode { uint4 w[5]; };
 static_assert(sizeof(WideNode) == 80, "wide node is 80 bytes");
 
@@ -27,6 +29,7 @@ struct BvhDev {
     const float4* tris;     // [3 * num_leaf_tris] : v0.xyz|prim id, v1.xyz|0, v2.xyz|0 in node-leaf order
     uint32_t num_nodes;
     uint32_t num_tris;
+    uint32_t prmt_k;        // 0x47000000: exponent bytes of the float 2^15 + q built by PRMT in the node step
 };
 
 struct Partition { uint32_t rank, nranks, slab_rows; };
@@ -61,6 +64,7 @@ struct mrt_context {
     int opt_count_visits = 0;
     int opt_sort_rays = 0;
     int opt_persistent = 1;
+    int opt_persistent_primary = 0;  // run primary rays through the persistent state machine too (A/B switch)
 
     // inputs
     uchar4* bn = nullptr;
@@ -117,7 +121,8 @@ struct mrt_context {
     DevArray<float4> path_state;         // throughput rgb | rng state
     DevArray<float4> ray_o[2], ray_d[2]; // queues: origin|pixel, direction|tmax
     DevArray<float4> hits;               // t | tri slot | u | v
-    DevArray<uint32_t> queue_counts;     // one counter per wave
+    DevArray<uint32_t> queue_counts;     // one counter per wave, then one work counter per trace launch
+    uint32_t num_queue_counts = 0;
     DevArray<uint64_t> sort_keys, sort_keys_alt;
     DevArray<uint32_t> sort_vals, sort_vals_alt;
     DevArray<unsigned long long> visit_counters;  // node visits, tri tests, stack overflows

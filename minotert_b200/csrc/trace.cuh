@@ -1,30 +1,69 @@
 // trace.cuh -- closest-hit traversal of the compressed 8-wide BVH (north_star rows n3, n4).
 //
-// Node fetch: five 128-bit read-only loads (ld.global.nc.v4) per 80-byte node.  Child boxes are
-// decoded with one PRMT + FADD per byte (0x4B000000 | q is the float 2^23 + q) and tested with one
-// FMA per slab plane against the pre-scaled inverse direction.  Hits are gathered into a 32-bit
-// mask: inner children land in bits 24..31 at position (slot ^ inverse ray octant), so the highest
-// set bit is the child that lies first along the ray; leaf triangles land in bits 0..23.
-// The traversal stack holds (child_base, hit bits | imask) groups: the first TRACE_SM_STACK entries
+// Execution model for incoherent rays (bounce waves): persistent warps.  Every lane owns one ray; the
+// warp runs a warp-synchronous state machine whose step is chosen by ballot:
+//     refill  : lanes whose ray finished take the next ray of the warp's chunk (one global atomic per
+//               TRACE_CHUNK rays), once enough lanes are idle -- bounce rays finish at very different
+//               times, refilling keeps the warp populated;
+//     node    : lanes with a pending node fetch it (five 128-bit ld.global.nc) and test its 8 children;
+//     triangle: lanes with pending leaf triangles test ONE triangle; triangle steps are postponed until
+//               TRACE_TRI_MIN lanes have one (or no lane has node work), so they run batched.
+// Coherent rays (the primary pass) use the plain per-lane loop trace_coherent().
+// History (profiles/): v0 "one node then its triangles per lane" ran bounce rays at 7.8 of 32 active
+// lanes; the state machine reached ~19; v2 (this file) halves the instructions of a node step.
+//
+// Node step, ~260 SASS instructions for 8 children:
+//   * decode + slab plane in ONE FMA: PRMT builds the float 2^15 + q from the quantised byte
+//     (0x47000000 | q << 8), and t = fma(2^15 + q, step/d, (origin - o)/d - 2^15 * step/d).  The constant
+//     term carries an error of at most step/512, which the builder's outward rounding (1/128 step of
+//     slack, bvh_build.cu) covers; near planes use 1/d * (1 - 2^-21), far planes 1/d * (1 + 2^-21), so
+//     fp32 rounding can never cull a box the exact ray touches;
+//   * hit mask by sign funnel: SHF.L.W shifts the sign bit of (tmax - tmin) of each child into an 8-bit
+//     miss mask, no predicates or branches;
+//   * inner hits are permuted by three delta swaps into "slot ^ inverse ray octant" order so that the
+//     highest set bit is the child that lies first along the ray; leaf hits are expanded to the node's
+//     fixed 3-bits-per-slot triangle mask.
+// The stack holds (child_base, ordered inner hits << 24 | imask) groups: the first TRACE_SM_STACK entries
 // per lane live in shared memory (column layout, conflict-free), deeper ones spill to local memory.
 //
-// Ray/triangle: Woop-Benthin-Wald watertight test, fp32, no contraction (file built with
-// -fmad=false; the only FMAs are the explicit fmaf() of the slab test), double fallback on zero
-// edge functions, no culling, accept t >= 0.  Closest hit = lexicographic min of (t, primitive id),
-// the tie rule of primaryRay.comp:28.
+// Ray/triangle: Woop-Benthin-Wald watertight test, fp32, no contraction (file built with -fmad=false;
+// the only FMAs are the explicit fmaf() of the slab test), double fallback on zero edge functions, no
+// culling, accept t >= 0.  Closest hit = lexicographic min of (t, primitive id), the tie rule of
+// primaryRay.comp:28.  The axis permutation uses predicated selects (no divergent branches).
 #pragma once
 #include "context.cuh"
 
 #define TRACE_BLOCK 128
-#define TRACE_SM_STACK 12
-#define TRACE_LOCAL_STACK 36
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 6   // resident CTAs per SM the register budget is capped for (80 regs/thread)
+#endif
+#define TRACE_SM_STACK 10
+#define TRACE_LOCAL_STACK 38
+#ifndef TRACE_CHUNK
+#define TRACE_CHUNK 32       // rays a warp takes per global atomic
+#endif
+#ifndef TRACE_REFILL_MIN
+#define TRACE_REFILL_MIN 8   // idle lanes that trigger a refill
+#endif
+#ifndef TRACE_TRI_MIN
+#define TRACE_TRI_MIN 8      // lanes with a pending triangle that trigger a triangle step
+#endif
 
 struct TraceHit {
     float t;
     uint32_t tri;   // index into BvhDev::tris / 3, or MRT_MISS_ID
-    float u, v;
     uint32_t prim;  // upload-order primitive id, or MRT_MISS_ID
 };
+
+// component k (0,1,2) of (x,y,z) with predicated selects
+MRT_D float sel3(float x, float y, float z, int k) {
+    float r;
+    asm("{\n\t.reg .pred p0, p1;\n\tsetp.eq.s32 p0, %4, 0;\n\tsetp.eq.s32 p1, %4, 1;\n\t"
+        "selp.f32 %0, %2, %3, p1;\n\tselp.f32 %0, %1, %0, p0;\n\t}"
+        : "=f"(r)
+        : "f"(x), "f"(y), "f"(z), "r"(k));
+    return r;
+}
 
 struct RayShear { int kx, ky, kz; float Sx, Sy, Sz; };
 
@@ -34,20 +73,21 @@ MRT_D RayShear make_shear(float3 d) {
     r.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
     r.kx = r.kz == 2 ? 0 : r.kz + 1;
     r.ky = r.kx == 2 ? 0 : r.kx + 1;
-    float dz = comp3(d, r.kz);
+    float dz = sel3(d.x, d.y, d.z, r.kz);
     if (dz < 0.0f) { int t = r.kx; r.kx = r.ky; r.ky = t; }
-    r.Sx = comp3(d, r.kx) / dz;
-    r.Sy = comp3(d, r.ky) / dz;
+    r.Sx = sel3(d.x, d.y, d.z, r.kx) / dz;
+    r.Sy = sel3(d.x, d.y, d.z, r.ky) / dz;
     r.Sz = 1.0f / dz;
     return r;
 }
 
-MRT_D bool tri_test(float3 o, const RayShear& rs, float3 p0, float3 p1, float3 p2, float& t, float& u, float& v) {
+// returns true and t on a hit (t >= 0); barycentrics are not needed by the flat-shaded path
+MRT_D bool tri_test(float3 o, const RayShear& rs, float3 p0, float3 p1, float3 p2, float& t) {
     float3 A = p0 - o, B = p1 - o, C = p2 - o;
-    float Akz = comp3(A, rs.kz), Bkz = comp3(B, rs.kz), Ckz = comp3(C, rs.kz);
-    float Ax = comp3(A, rs.kx) - rs.Sx * Akz, Ay = comp3(A, rs.ky) - rs.Sy * Akz;
-    float Bx = comp3(B, rs.kx) - rs.Sx * Bkz, By = comp3(B, rs.ky) - rs.Sy * Bkz;
-    float Cx = comp3(C, rs.kx) - rs.Sx * Ckz, Cy = comp3(C, rs.ky) - rs.Sy * Ckz;
+    float Akz = sel3(A.x, A.y, A.z, rs.kz), Bkz = sel3(B.x, B.y, B.z, rs.kz), Ckz = sel3(C.x, C.y, C.z, rs.kz);
+    float Ax = sel3(A.x, A.y, A.z, rs.kx) - rs.Sx * Akz, Ay = sel3(A.x, A.y, A.z, rs.ky) - rs.Sy * Akz;
+    float Bx = sel3(B.x, B.y, B.z, rs.kx) - rs.Sx * Bkz, By = sel3(B.x, B.y, B.z, rs.ky) - rs.Sy * Bkz;
+    float Cx = sel3(C.x, C.y, C.z, rs.kx) - rs.Sx * Ckz, Cy = sel3(C.x, C.y, C.z, rs.ky) - rs.Sy * Ckz;
     float U = Cx * By - Cy * Bx;
     float V = Ax * Cy - Ay * Cx;
     float W = Bx * Ay - By * Ax;
@@ -64,134 +104,226 @@ MRT_D bool tri_test(float3 o, const RayShear& rs, float3 p0, float3 p1, float3 p
     float tt = T / det;
     if (!(tt >= 0.0f)) return false;
     t = tt;
-    u = V / det;
-    v = W / det;
     return true;
 }
 
-MRT_D void hit_consider(TraceHit& h, float t, float u, float v, uint32_t tri, uint32_t prim) {
+MRT_D void hit_consider(TraceHit& h, float t, uint32_t tri, uint32_t prim) {
     if (h.prim == MRT_MISS_ID || t < h.t || (t == h.t && prim < h.prim)) {
-        h.t = t; h.u = u; h.v = v; h.tri = tri; h.prim = prim;
+        h.t = t; h.tri = tri; h.prim = prim;
     }
-}
-
-MRT_D float q_to_float(unsigned w, unsigned sel) {
-    // byte `sel` of w -> float, via the 2^23 + q bit pattern
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | sel)) - 8388608.0f;
-}
-
-// stack: per-lane column in shared memory (stride TRACE_BLOCK) + local spill
-struct TraceStack {
-    uint2* sm;  // &shared[0][lane column]
-    uint2 spill[TRACE_LOCAL_STACK];
-    int sp;
-};
-
-MRT_D void stack_push(TraceStack& S, uint2 e, unsigned& overflow) {
-    if (S.sp < TRACE_SM_STACK) S.sm[S.sp * TRACE_BLOCK] = e;
-    else if (S.sp < TRACE_SM_STACK + TRACE_LOCAL_STACK) S.spill[S.sp - TRACE_SM_STACK] = e;
-    else { overflow++; return; }
-    S.sp++;
-}
-MRT_D uint2 stack_pop(TraceStack& S) {
-    S.sp--;
-    return S.sp < TRACE_SM_STACK ? S.sm[S.sp * TRACE_BLOCK] : S.spill[S.sp - TRACE_SM_STACK];
 }
 
 struct TraceCounters { unsigned nodes, tris, overflow; };
 
-// sm_column: this lane's column of a __shared__ uint2[TRACE_SM_STACK][TRACE_BLOCK] array
-MRT_D TraceHit bvh_trace(const BvhDev& bvh, float3 o, float3 d, uint2* sm_column, TraceCounters& cnt) {
+// Per-lane traversal state.
+struct LaneState {
+    float3 o;
+    float3 idn, idf;   // 1/d * (1 - 2^-21) for near planes, 1/d * (1 + 2^-21) for far planes
+    RayShear rs;
+    unsigned oct_inv;  // 7 - octant; bit a clear <=> direction negative on axis a
+    uint2 ng;          // pending node group: child_base, ordered inner hits << 24 | imask
+    uint2 tg;          // pending triangle group: tri_base, hit triangle bits
+    unsigned tgmask;   // leafmask24 of the node tg came from
+    int sp;
     TraceHit hit;
-    hit.t = 3.0e38f; hit.tri = MRT_MISS_ID; hit.u = hit.v = 0.0f; hit.prim = MRT_MISS_ID;
-    if (bvh.num_nodes == 0) return hit;
+    float tlimit;      // hit.t * (1 + 2^-21)
+};
 
+#define TRACE_KNEAR 0.99999952f
+#define TRACE_KFAR 1.00000048f
+
+MRT_D void lane_begin(LaneState& L, float3 o, float3 d) {
     const float tiny = 1e-20f;
     float3 dd = f3(fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x), fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y),
                    fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-    const float3 idir = f3(1.0f / dd.x, 1.0f / dd.y, 1.0f / dd.z);
-    const bool negx = idir.x < 0.0f, negy = idir.y < 0.0f, negz = idir.z < 0.0f;
-    const unsigned oct_inv = 7u - ((negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u));
-    const RayShear rs = make_shear(d);
+    float3 idir = f3(1.0f / dd.x, 1.0f / dd.y, 1.0f / dd.z);
+    L.o = o;
+    L.idn = idir * TRACE_KNEAR;
+    L.idf = idir * TRACE_KFAR;
+    L.oct_inv = 7u - ((idir.x < 0.0f ? 1u : 0u) | (idir.y < 0.0f ? 2u : 0u) | (idir.z < 0.0f ? 4u : 0u));
+    L.rs = make_shear(d);
+    L.ng = make_uint2(0u, 0x80000000u);  // root "group": node 0, one pending inner hit
+    L.tg = make_uint2(0u, 0u);
+    L.tgmask = 0u;
+    L.sp = 0;
+    L.hit.t = 3.0e38f; L.hit.tri = MRT_MISS_ID; L.hit.prim = MRT_MISS_ID;
+    L.tlimit = 3.0e38f;
+}
 
-    TraceStack S;
-    S.sm = sm_column;
-    S.sp = 0;
-    uint2 ng = make_uint2(0u, 0x80000000u);  // root "group": node 0, one pending inner hit
-    uint2 tg = make_uint2(0u, 0u);
+// float 2^15 + (byte `sel` of w).  K = 0x47000000 is passed in a register so that the selector can be the
+// immediate operand of PRMT (otherwise ptxas keeps four selectors in uniform registers and copies them).
+MRT_D float q_plane(unsigned w, unsigned K, unsigned sel) { return __uint_as_float(__byte_perm(w, K, 0x7404u | (sel << 4))); }
+
+// conditional delta swap: exchanges the bit groups selected by m (pairs at distance sh)
+MRT_D unsigned delta_swap(unsigned x, unsigned m, int sh) {
+    unsigned t = ((x >> sh) ^ x) & m;
+    return x ^ (t | (t << sh));
+}
+
+// One node step: take the nearest pending child of L.ng, fetch it, test its 8 children.
+MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, uint2* sm, uint2* spill, TraceCounters& cnt) {
+    const unsigned bit = 31u - __clz(L.ng.y);
+    L.ng.y &= ~(1u << bit);
+    if (L.ng.y & 0xFF000000u) {  // siblings remain: keep the group for later
+        if (L.sp < TRACE_SM_STACK) sm[L.sp * TRACE_BLOCK] = L.ng;
+        else if (L.sp < TRACE_SM_STACK + TRACE_LOCAL_STACK) spill[L.sp - TRACE_SM_STACK] = L.ng;
+        else cnt.overflow++;
+        L.sp = min(L.sp + 1, TRACE_SM_STACK + TRACE_LOCAL_STACK);
+    }
+    const unsigned slot = (bit - 24u) ^ L.oct_inv;
+    const unsigned rel = __popc(L.ng.y & ~(0xFFFFFFFFu << slot));
+    const uint4* np = reinterpret_cast<const uint4*>(bvh.nodes + (L.ng.x + rel));
+    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    cnt.nodes++;
+
+    // per-axis slope and offset of  t(q) = (origin + q * step - o) / d  evaluated at the float 2^15 + q
+    const float stx = __uint_as_float((n0.w & 0xFFu) << 23), sty = __uint_as_float((n0.w & 0xFF00u) << 15),
+                stz = __uint_as_float((n0.w & 0xFF0000u) << 7);
+    const float dx = __uint_as_float(n0.x) - L.o.x, dy = __uint_as_float(n0.y) - L.o.y, dz = __uint_as_float(n0.z) - L.o.z;
+    const float snx = stx * L.idn.x, sny = sty * L.idn.y, snz = stz * L.idn.z;
+    const float sfx = stx * L.idf.x, sfy = sty * L.idf.y, sfz = stz * L.idf.z;
+    const float bnx = fmaf(-32768.0f, snx, dx * L.idn.x), bny = fmaf(-32768.0f, sny, dy * L.idn.y),
+                bnz = fmaf(-32768.0f, snz, dz * L.idn.z);
+    const float bfx = fmaf(-32768.0f, sfx, dx * L.idf.x), bfy = fmaf(-32768.0f, sfy, dy * L.idf.y),
+                bfz = fmaf(-32768.0f, sfz, dz * L.idf.z);
+    // near / far quantised planes per axis, chosen by the ray octant
+    const bool px = L.oct_inv & 1u, py = L.oct_inv & 2u, pz = L.oct_inv & 4u;  // direction positive on the axis
+    const unsigned nx0 = px ? n2.x : n3.z, nx1 = px ? n2.y : n3.w, fx0 = px ? n3.z : n2.x, fx1 = px ? n3.w : n2.y;
+    const unsigned ny0 = py ? n2.z : n4.x, ny1 = py ? n2.w : n4.y, fy0 = py ? n4.x : n2.z, fy1 = py ? n4.y : n2.w;
+    const unsigned nz0 = pz ? n3.x : n4.z, nz1 = pz ? n3.y : n4.w, fz0 = pz ? n4.z : n3.x, fz1 = pz ? n4.w : n3.y;
+    const float tlimit = L.tlimit;
+
+    const unsigned K = bvh.prmt_k;  // 0x47000000 from the kernel parameters (a constant-bank operand of PRMT)
+    unsigned miss = 0u;  // after the loop: bit j set <=> child j missed
+#pragma unroll
+    for (int j = 7; j >= 0; j--) {
+        const unsigned wnx = j < 4 ? nx0 : nx1, wny = j < 4 ? ny0 : ny1, wnz = j < 4 ? nz0 : nz1;
+        const unsigned wfx = j < 4 ? fx0 : fx1, wfy = j < 4 ? fy0 : fy1, wfz = j < 4 ? fz0 : fz1;
+        const float t0x = fmaf(q_plane(wnx, K, j & 3), snx, bnx), t1x = fmaf(q_plane(wfx, K, j & 3), sfx, bfx);
+        const float t0y = fmaf(q_plane(wny, K, j & 3), sny, bny), t1y = fmaf(q_plane(wfy, K, j & 3), sfy, bfy);
+        const float t0z = fmaf(q_plane(wnz, K, j & 3), snz, bnz), t1z = fmaf(q_plane(wfz, K, j & 3), sfz, bfz);
+        const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+        const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tlimit));
+        miss = __funnelshift_l(__float_as_uint(tmax - tmin), miss, 1);  // (miss << 1) | sign(tmax - tmin)
+    }
+    const unsigned imask = n0.w >> 24;
+    const unsigned hit8 = ~miss & 0xFFu;
+    // inner hits -> bit (slot ^ oct_inv)
+    unsigned inner = hit8 & imask;
+    inner = delta_swap(inner, (L.oct_inv & 1u) ? 0x55u : 0u, 1);
+    inner = delta_swap(inner, (L.oct_inv & 2u) ? 0x33u : 0u, 2);
+    inner = delta_swap(inner, (L.oct_inv & 4u) ? 0x0Fu : 0u, 4);
+    // leaf hits -> 3 bits per slot, masked by the triangles that exist
+    unsigned leaf = hit8 & ~imask;
+    leaf = (leaf ^ (leaf << 8)) & 0x00F00Fu;
+    leaf = (leaf ^ (leaf << 4)) & 0x0C30C3u;
+    leaf = (leaf ^ (leaf << 2)) & 0x249249u;
+    L.ng = make_uint2(n1.x, (inner << 24) | imask);
+    L.tg = make_uint2(n1.y, (leaf * 7u) & n1.z);
+    L.tgmask = n1.z;
+}
+
+MRT_D void lane_tri_step(LaneState& L, const BvhDev& bvh, TraceCounters& cnt) {
+    const unsigned bit = __ffs(L.tg.y) - 1;
+    L.tg.y &= L.tg.y - 1;
+    const uint32_t tri = L.tg.x + __popc(L.tgmask & ((1u << bit) - 1u));
+    const float4* tp = bvh.tris + 3 * (size_t)tri;
+    const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+    cnt.tris++;
+    float t;
+    if (tri_test(L.o, L.rs, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), t)) {
+        hit_consider(L.hit, t, tri, __float_as_uint(v0.w));
+        L.tlimit = L.hit.t * TRACE_KFAR;
+    }
+}
+
+// Persistent warp loop.  Job supplies the rays and consumes the hits:
+//   uint32_t Job::count() const;                          rays in this wave
+//   bool     Job::load(uint32_t i, float3& o, float3& d); false => ray i does not exist (padding)
+//   void     Job::store(uint32_t i, const TraceHit& h);
+// work_counter: global counter of handed-out rays (zeroed before the launch).
+template <class Job>
+MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter, uint2* sm, TraceCounters& cnt) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t total = job.count();
+    uint2 spill[TRACE_LOCAL_STACK];
+    LaneState L;
+    L.ng = L.tg = make_uint2(0u, 0u);
+    L.sp = 0;
+    bool have_ray = false;
+    uint32_t ray_index = 0;
+    uint32_t pool_next = 0, pool_end = 0;  // warp-uniform chunk of ray indices
+    bool exhausted = false;
 
     for (;;) {
-        if (ng.y & 0xFF000000u) {
-            const unsigned bit = 31u - __clz(ng.y);
-            ng.y &= ~(1u << bit);
-            if (ng.y & 0xFF000000u) stack_push(S, ng, cnt.overflow);
-            const unsigned slot = (bit - 24u) ^ oct_inv;
-            const unsigned rel = __popc(ng.y & ~(0xFFFFFFFFu << slot));
-            const uint4* np = reinterpret_cast<const uint4*>(bvh.nodes + (ng.x + rel));
-            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-            cnt.nodes++;
-
-            const float adx = __uint_as_float((n0.w & 0xFFu) << 23) * idir.x;
-            const float ady = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idir.y;
-            const float adz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idir.z;
-            const float ox = (__uint_as_float(n0.x) - o.x) * idir.x;
-            const float oy = (__uint_as_float(n0.y) - o.y) * idir.y;
-            const float oz = (__uint_as_float(n0.z) - o.z) * idir.z;
-            // near / far quantised planes per axis, chosen by the ray octant
-            const uint2 qlx = make_uint2(n2.x, n2.y), qly = make_uint2(n2.z, n2.w), qlz = make_uint2(n3.x, n3.y);
-            const uint2 qhx = make_uint2(n3.z, n3.w), qhy = make_uint2(n4.x, n4.y), qhz = make_uint2(n4.z, n4.w);
-            const uint2 nx = negx ? qhx : qlx, fx = negx ? qlx : qhx;
-            const uint2 ny = negy ? qhy : qly, fy = negy ? qly : qhy;
-            const uint2 nz = negz ? qhz : qlz, fz = negz ? qlz : qhz;
-            const float tlimit = hit.t;
-
-            unsigned hitmask = 0u;
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const unsigned meta4 = half ? n1.w : n1.z;
-                const unsigned wnx = half ? nx.y : nx.x, wny = half ? ny.y : ny.x, wnz = half ? nz.y : nz.x;
-                const unsigned wfx = half ? fx.y : fx.x, wfy = half ? fy.y : fy.x, wfz = half ? fz.y : fz.x;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float t0x = fmaf(q_to_float(wnx, j), adx, ox), t1x = fmaf(q_to_float(wfx, j), adx, ox);
-                    const float t0y = fmaf(q_to_float(wny, j), ady, oy), t1y = fmaf(q_to_float(wfy, j), ady, oy);
-                    const float t0z = fmaf(q_to_float(wnz, j), adz, oz), t1z = fmaf(q_to_float(wfz, j), adz, oz);
-                    // padded so fp32 rounding can never cull a box the exact ray touches
-                    const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f)) * 0.9999995f;
-                    const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tlimit)) * 1.0000005f;
-                    if (tmin <= tmax) {
-                        const unsigned m = (meta4 >> (8 * j)) & 0xFFu;
-                        const unsigned inner = ((m & 0x18u) == 0x18u) ? 7u : 0u;
-                        const unsigned bit_index = (m ^ (oct_inv & inner)) & 31u;
-                        hitmask |= (m >> 5) << bit_index;
+        // ---- refill idle lanes from the warp's chunk
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have_ray);
+        if (idle && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= TRACE_REFILL_MIN)) {
+            if (pool_next >= pool_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work_counter, (uint32_t)TRACE_CHUNK);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                pool_next = base;
+                pool_end = min(base + (uint32_t)TRACE_CHUNK, total);
+                if (base >= total) { exhausted = true; pool_next = pool_end = 0; }
+            }
+            if (!exhausted) {
+                const uint32_t mine = pool_next + __popc(idle & lt_mask);
+                if (!have_ray && mine < pool_end) {
+                    float3 o, d;
+                    ray_index = mine;
+                    if (job.load(mine, o, d)) {
+                        lane_begin(L, o, d);
+                        if (bvh.num_nodes == 0) L.ng.y = 0u;  // empty scene: finishes as a miss below
+                        have_ray = true;
                     }
                 }
+                pool_next = min(pool_next + (uint32_t)__popc(idle), pool_end);
             }
-            ng = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
-            tg = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
-        } else {
-            tg = ng;
-            ng = make_uint2(0u, 0u);
         }
+        if (exhausted && __ballot_sync(0xFFFFFFFFu, have_ray) == 0u) break;
 
-        while (tg.y) {
-            const unsigned bit = __ffs(tg.y) - 1;
-            tg.y &= tg.y - 1;
-            const uint32_t tri = tg.x + bit;
-            const float4* tp = bvh.tris + 3 * (size_t)tri;
-            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-            cnt.tris++;
-            float t, u, v;
-            if (tri_test(o, rs, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), t, u, v))
-                hit_consider(hit, t, u, v, tri, __float_as_uint(v0.w));
+        // ---- lanes with a ray but no pending work: pop, or finish the ray
+        if (have_ray && !(L.ng.y & 0xFF000000u) && L.tg.y == 0u) {
+            if (L.sp == 0) {
+                job.store(ray_index, L.hit);
+                have_ray = false;
+            } else {
+                L.sp--;
+                L.ng = L.sp < TRACE_SM_STACK ? sm[L.sp * TRACE_BLOCK] : spill[L.sp - TRACE_SM_STACK];
+            }
         }
-
-        if (!(ng.y & 0xFF000000u)) {
-            if (S.sp == 0) break;
-            ng = stack_pop(S);
+        const bool want_tri = have_ray && L.tg.y != 0u;
+        const bool want_node = have_ray && !want_tri && (L.ng.y & 0xFF000000u);
+        const unsigned tmask = __ballot_sync(0xFFFFFFFFu, want_tri);
+        const unsigned nmask = __ballot_sync(0xFFFFFFFFu, want_node);
+        if (tmask && (nmask == 0u || __popc(tmask) >= TRACE_TRI_MIN)) {
+            if (want_tri) lane_tri_step(L, bvh, cnt);
+        } else if (nmask) {
+            if (want_node) lane_node_step(L, bvh, sm, spill, cnt);
         }
     }
-    return hit;
+}
+
+// Per-lane loop for COHERENT rays (the primary pass): one node, then its triangles, per iteration.
+// Rays of an 8x4 pixel tile walk the same nodes and reach leaves together, so the warp stays
+// converged without the state machine, and testing triangles at once tightens t early.
+MRT_D TraceHit trace_coherent(const BvhDev& bvh, float3 o, float3 d, uint2* sm, TraceCounters& cnt) {
+    uint2 spill[TRACE_LOCAL_STACK];
+    LaneState L;
+    lane_begin(L, o, d);
+    if (bvh.num_nodes == 0) return L.hit;
+    for (;;) {
+        if (L.ng.y & 0xFF000000u) lane_node_step(L, bvh, sm, spill, cnt);
+        while (L.tg.y) lane_tri_step(L, bvh, cnt);
+        if (!(L.ng.y & 0xFF000000u)) {
+            if (L.sp == 0) break;
+            L.sp--;
+            L.ng = L.sp < TRACE_SM_STACK ? sm[L.sp * TRACE_BLOCK] : spill[L.sp - TRACE_SM_STACK];
+        }
+    }
+    return L.hit;
 }
 
 // geometric normal of a hit triangle, flipped to face the incoming ray (two-sided surfaces)

@@ -9,8 +9,7 @@ import numpy as np
 
 from . import capi
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libminote_host.so")
+LIB_PATH = os.path.join(capi.LIB_DIR, "libminote_host.so")
 
 
 class Camera(C.Structure):
