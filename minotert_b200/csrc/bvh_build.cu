@@ -341,9 +341,9 @@ k_emit_nodes(BinTree T, uint32_t num_nodes, const int32_t* __restrict__ slot_nod
         for (int a = 0; a < 3; a++) {
             float ql = 0.0f, qh = 255.0f;
             if (sc[a] > 0.0f) {
-                const float slack = sc[a] * 0.0078125f;
-                ql = fminf(fmaxf(floorf((clo[a] - org[a]) / sc[a] - 0.01f), 0.0f), 255.0f);
-                qh = fminf(fmaxf(ceilf((chi[a] - org[a]) / sc[a] + 0.01f), 0.0f), 255.0f);
+                const float slack = sc[a] * 0.015625f;  // 1/64 step; the traversal's decode error is <= 1/256 step
+                ql = fminf(fmaxf(floorf((clo[a] - org[a]) / sc[a] - 0.02f), 0.0f), 255.0f);
+                qh = fminf(fmaxf(ceilf((chi[a] - org[a]) / sc[a] + 0.02f), 0.0f), 255.0f);
                 // outward rounding under the decode arithmetic (origin + q * scale)
                 while (ql > 0.0f && org[a] + ql * sc[a] > clo[a] - slack) ql -= 1.0f;
                 while (qh < 255.0f && org[a] + qh * sc[a] < chi[a] + slack) qh += 1.0f;

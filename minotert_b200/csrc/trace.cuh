@@ -48,6 +48,9 @@
 #ifndef TRACE_TRI_MIN
 #define TRACE_TRI_MIN 8      // lanes with a pending triangle that trigger a triangle step
 #endif
+#ifndef TRACE_DP4A_NEAR
+#define TRACE_DP4A_NEAR 1    // decode near planes with IDP.4A (FMA-heavy pipe), far planes with PRMT (ALU pipe)
+#endif
 
 struct TraceHit {
     float t;
@@ -153,6 +156,10 @@ MRT_D void lane_begin(LaneState& L, float3 o, float3 d) {
 // float 2^15 + (byte `sel` of w).  K = 0x47000000 is passed in a register so that the selector can be the
 // immediate operand of PRMT (otherwise ptxas keeps four selectors in uniform registers and copies them).
 MRT_D float q_plane(unsigned w, unsigned K, unsigned sel) { return __uint_as_float(__byte_perm(w, K, 0x7404u | (sel << 4))); }
+// float 2^15 + (byte `sel` of w) / 2 through the integer dot-product unit (FMA-heavy pipe instead of the
+// ALU pipe PRMT runs on): 0x47000000 + 128 * byte.  The node step decodes near planes this way and far
+// planes with PRMT so that neither pipe carries all 48 decodes (ncu: ALU pipe 65 % busy, FMA 22 %).
+MRT_D float q_plane_half(unsigned w, unsigned K, unsigned sel) { return __uint_as_float(__dp4a(w, 128u << (8 * sel), K)); }
 
 // conditional delta swap: exchanges the bit groups selected by m (pairs at distance sh)
 MRT_D unsigned delta_swap(unsigned x, unsigned m, int sh) {
@@ -182,8 +189,15 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, uint2* sm, uint2* spi
     const float dx = __uint_as_float(n0.x) - L.o.x, dy = __uint_as_float(n0.y) - L.o.y, dz = __uint_as_float(n0.z) - L.o.z;
     const float snx = stx * L.idn.x, sny = sty * L.idn.y, snz = stz * L.idn.z;
     const float sfx = stx * L.idf.x, sfy = sty * L.idf.y, sfz = stz * L.idf.z;
+#if TRACE_DP4A_NEAR
+    // near planes are decoded as 2^15 + q/2: slope 2 * step/d, offset -2^16 * step/d (error <= step/256)
+    const float bnx = fmaf(-65536.0f, snx, dx * L.idn.x), bny = fmaf(-65536.0f, sny, dy * L.idn.y),
+                bnz = fmaf(-65536.0f, snz, dz * L.idn.z);
+    const float snx2 = snx * 2.0f, sny2 = sny * 2.0f, snz2 = snz * 2.0f;
+#else
     const float bnx = fmaf(-32768.0f, snx, dx * L.idn.x), bny = fmaf(-32768.0f, sny, dy * L.idn.y),
                 bnz = fmaf(-32768.0f, snz, dz * L.idn.z);
+#endif
     const float bfx = fmaf(-32768.0f, sfx, dx * L.idf.x), bfy = fmaf(-32768.0f, sfy, dy * L.idf.y),
                 bfz = fmaf(-32768.0f, sfz, dz * L.idf.z);
     // near / far quantised planes per axis, chosen by the ray octant
@@ -199,9 +213,15 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, uint2* sm, uint2* spi
     for (int j = 7; j >= 0; j--) {
         const unsigned wnx = j < 4 ? nx0 : nx1, wny = j < 4 ? ny0 : ny1, wnz = j < 4 ? nz0 : nz1;
         const unsigned wfx = j < 4 ? fx0 : fx1, wfy = j < 4 ? fy0 : fy1, wfz = j < 4 ? fz0 : fz1;
-        const float t0x = fmaf(q_plane(wnx, K, j & 3), snx, bnx), t1x = fmaf(q_plane(wfx, K, j & 3), sfx, bfx);
-        const float t0y = fmaf(q_plane(wny, K, j & 3), sny, bny), t1y = fmaf(q_plane(wfy, K, j & 3), sfy, bfy);
-        const float t0z = fmaf(q_plane(wnz, K, j & 3), snz, bnz), t1z = fmaf(q_plane(wfz, K, j & 3), sfz, bfz);
+#if TRACE_DP4A_NEAR
+        const float t0x = fmaf(q_plane_half(wnx, K, j & 3), snx2, bnx), t0y = fmaf(q_plane_half(wny, K, j & 3), sny2, bny),
+                    t0z = fmaf(q_plane_half(wnz, K, j & 3), snz2, bnz);
+#else
+        const float t0x = fmaf(q_plane(wnx, K, j & 3), snx, bnx), t0y = fmaf(q_plane(wny, K, j & 3), sny, bny),
+                    t0z = fmaf(q_plane(wnz, K, j & 3), snz, bnz);
+#endif
+        const float t1x = fmaf(q_plane(wfx, K, j & 3), sfx, bfx), t1y = fmaf(q_plane(wfy, K, j & 3), sfy, bfy),
+                    t1z = fmaf(q_plane(wfz, K, j & 3), sfz, bfz);
         const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
         const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tlimit));
         miss = __funnelshift_l(__float_as_uint(tmax - tmin), miss, 1);  // (miss << 1) | sign(tmax - tmin)
