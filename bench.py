@@ -49,35 +49,49 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled through NVML every ~2 ms by a background thread DURING the timed
+    region (nvidia-smi -lms is too coarse for a region of a few tens of milliseconds; same counters)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.max_sm = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            names = {"hw_slowdown": getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        r = int(get_reasons(h))
+                        for k, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(k)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._thread = None
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML, 2 ms period, timed region only"}
 
 
 def make_scene(name):
@@ -172,6 +186,8 @@ def run_ours(args):
 
     # host modules: Cuda::Provider + Renderer::Provider, scene upload + BVH build (setup, untimed)
     r = host.Renderer(w, h, bn, device=local)
+    r.context().set_option("builder", 1 if args.builder == "ploc" else 0)
+    r.context().set_option("ploc_radius", args.ploc_radius)
     r.set_mesh(pos, idx, alb)
     r.configure(samples=spp, bounces=bounces, accumulate=False, tonemap="amd", exposure=1.0)
     ctx = r.context()
@@ -290,7 +306,7 @@ def run_ours(args):
             "config": {"workload": wl, "triangles": int(idx.shape[0]), "resolution": [w, h], "spp": spp, "bounces": bounces,
                        "sampling": "PCG + blue-noise Cranley-Patterson rotation", "tonemap": "amd",
                        "l2": "flushed between steps (256 MiB memset)", "bvh_bytes": int(build_stats.bvh_bytes),
-                       "wide_nodes": int(build_stats.num_wide_nodes), "bvh_build_ms": build_stats.ms_build,
+                       "wide_nodes": int(build_stats.num_wide_nodes), "bvh_build_ms": build_stats.ms_build, "builder": args.builder,
                        "parallelism": "1 GPU" if world == 1 else f"sample sets over {world} GPUs, replicated BVH, NCCL reduce of the fp32 accumulator"},
             "clocks": clocks,
             "e2e": {"value": e2e_rays_all / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
@@ -329,6 +345,8 @@ def main():
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--bounces", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ploc-radius", type=int, default=10)
+    ap.add_argument("--builder", default="ploc", choices=["ploc", "lbvh"], help="binary hierarchy under the 8-wide BVH")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

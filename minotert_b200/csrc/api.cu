@@ -107,8 +107,10 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->pos); dev_free(ctx->idx); dev_free(ctx->albedo);
     dev_free(ctx->prim_lo); dev_free(ctx->prim_hi); dev_free(ctx->keys); dev_free(ctx->keys_alt);
     dev_free(ctx->order); dev_free(ctx->order_alt); dev_free(ctx->hist); dev_free(ctx->scan_tmp);
-    dev_free(ctx->bin_left); dev_free(ctx->bin_right); dev_free(ctx->bin_parent); dev_free(ctx->bin_first);
-    dev_free(ctx->bin_last); dev_free(ctx->bin_lo); dev_free(ctx->bin_hi); dev_free(ctx->bin_flag);
+    dev_free(ctx->bin_left); dev_free(ctx->bin_right); dev_free(ctx->bin_parent); dev_free(ctx->bin_count);
+    for (int k = 0; k < 2; k++) { dev_free(ctx->ploc_c[k]); dev_free(ctx->ploc_flag[k]); dev_free(ctx->ploc_scan[k]); }
+    dev_free(ctx->ploc_nn);
+    dev_free(ctx->bin_lo); dev_free(ctx->bin_hi); dev_free(ctx->bin_flag);
     dev_free(ctx->scene_bounds); dev_free(ctx->work_a); dev_free(ctx->work_b); dev_free(ctx->slot_node);
     dev_free(ctx->node_nchild); dev_free(ctx->node_ntri); dev_free(ctx->node_child_base); dev_free(ctx->node_tri_base);
     dev_free(ctx->nodes); dev_free(ctx->tris); dev_free(ctx->counters);
@@ -135,6 +137,8 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "sort_rays")) ctx->opt_sort_rays = value != 0;
     else if (!strcmp(name, "persistent")) ctx->opt_persistent = value != 0;
     else if (!strcmp(name, "persistent_primary")) ctx->opt_persistent_primary = value != 0;
+    else if (!strcmp(name, "builder")) { ctx->opt_builder = value != 0; ctx->bvh_valid = false; }
+    else if (!strcmp(name, "ploc_radius")) { ctx->opt_ploc_radius = (int)(value < 1 ? 1 : (value > 32 ? 32 : value)); ctx->bvh_valid = false; }
     else return mrt_fail(ctx, MRT_ERR_INVALID, "unknown option '%s'", name);
     return MRT_OK;
 }

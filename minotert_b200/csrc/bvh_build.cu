@@ -111,7 +111,7 @@ MRT_D int lbvh_delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
 
 __global__ void __launch_bounds__(256) k_karras(const uint64_t* __restrict__ keys, int n, int32_t* __restrict__ left,
                                                 int32_t* __restrict__ right, int32_t* __restrict__ parent,
-                                                uint32_t* __restrict__ first, uint32_t* __restrict__ last) {
+                                                uint32_t* __restrict__ count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -136,8 +136,7 @@ __global__ void __launch_bounds__(256) k_karras(const uint64_t* __restrict__ key
     right[i] = R;
     parent[L] = i;
     parent[R] = i;
-    first[i] = (uint32_t)lo;
-    last[i] = (uint32_t)hi;
+    count[i] = (uint32_t)(hi - lo + 1);
     if (i == 0) parent[0] = -1;
 }
 
@@ -171,19 +170,137 @@ __global__ void __launch_bounds__(256) k_bin_boxes(const float4* __restrict__ pr
     }
 }
 
+// ---- PLOC: parallel locally-ordered clustering (Meister & Bittner 2018) over the Morton order ----
+// Each round, every cluster finds the neighbour within +-radius positions whose merged box has the
+// smallest surface area; mutual nearest neighbours merge into a new internal node.  Node ids and the
+// compacted cluster list come from exclusive scans, so the tree is deterministic.  Compared with the
+// Karras hierarchy (splits dictated by Morton bits) this approaches SAH quality.
+MRT_D float merged_area(float4 alo, float4 ahi, float4 blo, float4 bhi) {
+    float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x);
+    float dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y);
+    float dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void __launch_bounds__(256) k_ploc_init(uint32_t n, uint32_t* __restrict__ clusters, int32_t* __restrict__ parent) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    clusters[i] = n - 1 + i;  // leaf of sorted position i
+    parent[n - 1 + i] = -1;
+}
+
+__global__ void __launch_bounds__(256) k_ploc_nearest(const uint32_t* __restrict__ clusters, uint32_t m, int radius,
+                                                      const float4* __restrict__ lo, const float4* __restrict__ hi,
+                                                      uint32_t* __restrict__ nn) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint32_t ci = clusters[i];
+    float4 ilo = lo[ci], ihi = hi[ci];
+    int j0 = max((int)i - radius, 0), j1 = min((int)i + radius, (int)m - 1);
+    // Ties are the rule on regular meshes (rows of identical quads).  Breaking them by "lowest position"
+    // makes every cluster point down the row and only one pair per row is mutual per round (slow rounds,
+    // caterpillar trees).  The tie-break below is symmetric in (i, j): nearer position first, then pairs
+    // whose lower position is even -- in a uniform row that pairs (0,1), (2,3), ... in a single round.
+    float best = 3.0e38f;
+    uint32_t bj = i, bkey = 0xFFFFFFFFu;
+    for (int j = j0; j <= j1; j++) {
+        if (j == (int)i) continue;
+        uint32_t cj = clusters[j];
+        float a = merged_area(ilo, ihi, lo[cj], hi[cj]);
+        uint32_t dist = (uint32_t)abs(j - (int)i);
+        uint32_t lowpos = (uint32_t)min(j, (int)i);
+        // (distance, parity of the lower position, lower position): a total order on the pairs around i that
+        // both partners evaluate identically, so the globally best pair is always mutual (progress)
+        uint32_t key = (dist << 26) | ((lowpos & 1u) << 25) | (lowpos & 0x1FFFFFFu);
+        if (a < best || (a == best && key < bkey)) { best = a; bj = (uint32_t)j; bkey = key; }
+    }
+    nn[i] = bj;
+}
+
+// flags: create[i] = 1 if i is the left partner of a mutual pair; keep[i] = 0 if i is the right partner
+__global__ void __launch_bounds__(256) k_ploc_flags(const uint32_t* __restrict__ nn, uint32_t m, uint32_t* __restrict__ create,
+                                                    uint32_t* __restrict__ keep) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint32_t j = nn[i];
+    bool mutual = j != i && nn[j] == i;
+    create[i] = (mutual && i < j) ? 1u : 0u;
+    keep[i] = (mutual && i > j) ? 0u : 1u;
+}
+
+__global__ void __launch_bounds__(256)
+k_ploc_merge(const uint32_t* __restrict__ clusters, const uint32_t* __restrict__ nn, uint32_t m, const uint32_t* __restrict__ create,
+             const uint32_t* __restrict__ keep, const uint32_t* __restrict__ create_scan, const uint32_t* __restrict__ keep_scan,
+             uint32_t next_node, int nprims, int32_t* __restrict__ left, int32_t* __restrict__ right, int32_t* __restrict__ parent,
+             uint32_t* __restrict__ count, float4* __restrict__ lo, float4* __restrict__ hi, uint32_t* __restrict__ clusters_out,
+             uint32_t* __restrict__ totals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (i == m - 1) {
+        totals[0] = keep_scan[i] + keep[i];      // clusters after this round
+        totals[1] = create_scan[i] + create[i];  // nodes created
+    }
+    if (!keep[i]) return;
+    uint32_t c = clusters[i];
+    if (create[i]) {
+        uint32_t j = nn[i], cj = clusters[j];
+        uint32_t id = next_node + create_scan[i];
+        float4 alo = lo[c], ahi = hi[c], blo = lo[cj], bhi = hi[cj];
+        left[id] = (int32_t)c;
+        right[id] = (int32_t)cj;
+        parent[c] = (int32_t)id;
+        parent[cj] = (int32_t)id;
+        parent[id] = -1;
+        uint32_t na = (int)c >= nprims - 1 ? 1u : count[c], nb = (int)cj >= nprims - 1 ? 1u : count[cj];
+        count[id] = na + nb;
+        lo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+        hi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+        c = id;
+    }
+    clusters_out[keep_scan[i]] = c;
+}
+
+__global__ void __launch_bounds__(256) k_leaf_boxes(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
+                                                    const uint32_t* __restrict__ order, uint32_t n, float4* __restrict__ bin_lo,
+                                                    float4* __restrict__ bin_hi) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t prim = order[k];
+    bin_lo[n - 1 + k] = prim_lo[prim];
+    bin_hi[n - 1 + k] = prim_hi[prim];
+}
+
 // ---- collapse to 8-wide ----
+// Binary tree over the Morton-sorted primitives, produced by either builder (Karras LBVH or PLOC):
+// internal nodes [0, n-1), leaf of sorted position k = node n-1+k.
 struct BinTree {
     const int32_t* left;
     const int32_t* right;
-    const uint32_t* first;
-    const uint32_t* last;
+    const uint32_t* count;  // primitives below each internal node
     const float4* lo;
     const float4* hi;
-    int n;  // primitives
+    int n;     // primitives
+    int root;  // 0 for the LBVH, n-2 for PLOC (last node created); n-1 when n == 1
 };
 MRT_D bool bin_is_leaf(const BinTree& T, int b) { return b >= T.n - 1; }
-MRT_D uint32_t bin_count(const BinTree& T, int b) { return bin_is_leaf(T, b) ? 1u : (T.last[b] - T.first[b] + 1u); }
-MRT_D uint32_t bin_first(const BinTree& T, int b) { return bin_is_leaf(T, b) ? (uint32_t)(b - (T.n - 1)) : T.first[b]; }
+MRT_D uint32_t bin_count(const BinTree& T, int b) { return bin_is_leaf(T, b) ? 1u : T.count[b]; }
+// sorted positions of the (at most MRT_MAX_LEAF_TRIS = 3) primitives below b, left to right
+MRT_D uint32_t bin_gather(const BinTree& T, int b, uint32_t out[3]) {
+    uint32_t n = 0;
+    int stack[3];
+    int sp = 0;
+    stack[sp++] = b;
+    while (sp) {
+        int c = stack[--sp];
+        if (bin_is_leaf(T, c)) {
+            if (n < 3) out[n++] = (uint32_t)(c - (T.n - 1));
+        } else {
+            stack[sp++] = T.right[c];
+            stack[sp++] = T.left[c];
+        }
+    }
+    return n;
+}
 MRT_D float bin_area(const BinTree& T, int b) {
     float4 lo = T.lo[b], hi = T.hi[b];
     float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
@@ -356,9 +473,10 @@ k_emit_nodes(BinTree T, uint32_t num_nodes, const int32_t* __restrict__ slot_nod
             imask |= 1u << s;
         } else {
             leafmask |= ((1u << cnt) - 1u) << (3 * s);
-            uint32_t f0 = bin_first(T, c);
+            uint32_t where[3];
+            bin_gather(T, c, where);
             for (uint32_t t = 0; t < cnt; t++) {
-                uint32_t prim = order[f0 + t];
+                uint32_t prim = order[where[t]];
                 uint32_t i0 = idx[3 * (size_t)prim], i1 = idx[3 * (size_t)prim + 1], i2 = idx[3 * (size_t)prim + 2];
                 size_t o = 3 * (size_t)(tri_base + tri_off + t);
                 tris[o + 0] = make_float4(pos[3 * (size_t)i0], pos[3 * (size_t)i0 + 1], pos[3 * (size_t)i0 + 2], __uint_as_float(prim));
@@ -384,7 +502,7 @@ __global__ void k_last_total(const uint32_t* __restrict__ off, const uint32_t* _
 
 BinTree make_tree(mrt_context* ctx) {
     BinTree T;
-    T.left = ctx->bin_left.p; T.right = ctx->bin_right.p; T.first = ctx->bin_first.p; T.last = ctx->bin_last.p;
+    T.left = ctx->bin_left.p; T.right = ctx->bin_right.p; T.count = ctx->bin_count.p; T.root = ctx->bin_root;
     T.lo = ctx->bin_lo.p; T.hi = ctx->bin_hi.p; T.n = (int)ctx->ntris;
     return T;
 }
@@ -407,6 +525,48 @@ int climb_boxes(mrt_context* ctx) {
                                                          ctx->bin_flag.p);
     MRT_LAUNCHED(ctx);
     return mrt_check_cuda(ctx, cudaGetLastError(), "bin_boxes");
+}
+
+int build_ploc(mrt_context* ctx) {
+    const uint32_t n = ctx->ntris;
+    for (int k = 0; k < 2; k++) {
+        MRT_TRY(dev_reserve(ctx, ctx->ploc_c[k], n));
+        MRT_TRY(dev_reserve(ctx, ctx->ploc_flag[k], n));
+        MRT_TRY(dev_reserve(ctx, ctx->ploc_scan[k], n));
+    }
+    MRT_TRY(dev_reserve(ctx, ctx->ploc_nn, n));
+    k_leaf_boxes<<<div_up(n, 256), 256, 0, ctx->stream>>>(ctx->prim_lo.p, ctx->prim_hi.p, ctx->order.p, n, ctx->bin_lo.p,
+                                                          ctx->bin_hi.p);
+    MRT_LAUNCHED(ctx);
+    k_ploc_init<<<div_up(n, 256), 256, 0, ctx->stream>>>(n, ctx->ploc_c[0].p, ctx->bin_parent.p);
+    MRT_LAUNCHED(ctx);
+    uint32_t m = n, next_node = 0;
+    int cur = 0;
+    while (m > 1) {
+        const unsigned g = div_up(m, 256);
+        k_ploc_nearest<<<g, 256, 0, ctx->stream>>>(ctx->ploc_c[cur].p, m, ctx->opt_ploc_radius, ctx->bin_lo.p, ctx->bin_hi.p,
+                                                   ctx->ploc_nn.p);
+        MRT_LAUNCHED(ctx);
+        k_ploc_flags<<<g, 256, 0, ctx->stream>>>(ctx->ploc_nn.p, m, ctx->ploc_flag[0].p, ctx->ploc_flag[1].p);
+        MRT_LAUNCHED(ctx);
+        MRT_TRY(scan_exclusive_u32(ctx, ctx->ploc_flag[0].p, ctx->ploc_scan[0].p, m));
+        MRT_TRY(scan_exclusive_u32(ctx, ctx->ploc_flag[1].p, ctx->ploc_scan[1].p, m));
+        k_ploc_merge<<<g, 256, 0, ctx->stream>>>(ctx->ploc_c[cur].p, ctx->ploc_nn.p, m, ctx->ploc_flag[0].p, ctx->ploc_flag[1].p,
+                                                 ctx->ploc_scan[0].p, ctx->ploc_scan[1].p, next_node, (int)n, ctx->bin_left.p,
+                                                 ctx->bin_right.p, ctx->bin_parent.p, ctx->bin_count.p, ctx->bin_lo.p,
+                                                 ctx->bin_hi.p, ctx->ploc_c[cur ^ 1].p, ctx->counters.p);
+        MRT_LAUNCHED(ctx);
+        uint32_t totals[2] = {0, 0};
+        MRT_CUDA(ctx, cudaMemcpyAsync(totals, ctx->counters.p, sizeof totals, cudaMemcpyDeviceToHost, ctx->stream));
+        MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (totals[1] == 0 || totals[0] >= m) return mrt_fail(ctx, MRT_ERR_INVALID, "PLOC made no progress at %u clusters", m);
+        next_node += totals[1];
+        m = totals[0];
+        cur ^= 1;
+    }
+    if (next_node != n - 1) return mrt_fail(ctx, MRT_ERR_INVALID, "PLOC produced %u internal nodes for %u primitives", next_node, n);
+    ctx->bin_root = (int)n - 2;
+    return MRT_OK;
 }
 
 int emit_nodes(mrt_context* ctx) {
@@ -439,8 +599,7 @@ int bvh_build_full(mrt_context* ctx) {
     MRT_TRY(dev_reserve(ctx, ctx->bin_left, n));
     MRT_TRY(dev_reserve(ctx, ctx->bin_right, n));
     MRT_TRY(dev_reserve(ctx, ctx->bin_parent, 2 * (size_t)n));
-    MRT_TRY(dev_reserve(ctx, ctx->bin_first, n));
-    MRT_TRY(dev_reserve(ctx, ctx->bin_last, n));
+    MRT_TRY(dev_reserve(ctx, ctx->bin_count, n));
     MRT_TRY(dev_reserve(ctx, ctx->bin_lo, 2 * (size_t)n));
     MRT_TRY(dev_reserve(ctx, ctx->bin_hi, 2 * (size_t)n));
     MRT_TRY(dev_reserve(ctx, ctx->bin_flag, n));
@@ -466,16 +625,21 @@ int bvh_build_full(mrt_context* ctx) {
         std::swap(ctx->order, ctx->order_alt);
     }
     // 4-5: hierarchy + boxes
-    if (n > 1) {
-        k_karras<<<div_up(n - 1, 256), 256, 0, ctx->stream>>>(ctx->keys.p, (int)n, ctx->bin_left.p, ctx->bin_right.p,
-                                                              ctx->bin_parent.p, ctx->bin_first.p, ctx->bin_last.p);
-        MRT_LAUNCHED(ctx);
+    ctx->bin_root = 0;
+    if (n > 1 && ctx->opt_builder == 1) {
+        MRT_TRY(build_ploc(ctx));  // boxes are produced by the merges
+    } else {
+        if (n > 1) {
+            k_karras<<<div_up(n - 1, 256), 256, 0, ctx->stream>>>(ctx->keys.p, (int)n, ctx->bin_left.p, ctx->bin_right.p,
+                                                                  ctx->bin_parent.p, ctx->bin_count.p);
+            MRT_LAUNCHED(ctx);
+        }
+        MRT_TRY(climb_boxes(ctx));
     }
-    MRT_TRY(climb_boxes(ctx));
 
     // 6: collapse, one level per iteration
     BinTree T = make_tree(ctx);
-    uint2 root = make_uint2(n > 1 ? 0u : 0u /* single leaf = binary node n-1 = 0 */, 0u);
+    uint2 root = make_uint2((uint32_t)ctx->bin_root /* n == 1: the single leaf is binary node n-1 = 0 */, 0u);
     MRT_CUDA(ctx, cudaMemcpyAsync(ctx->work_a.p, &root, sizeof root, cudaMemcpyHostToDevice, ctx->stream));
     uint32_t level_start = 0, level_count = 1;
     DevArray<uint2>* cur = &ctx->work_a;

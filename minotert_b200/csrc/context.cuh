@@ -65,6 +65,8 @@ struct mrt_context {
     int opt_sort_rays = 0;
     int opt_persistent = 1;
     int opt_persistent_primary = 0;  // run primary rays through the persistent state machine too (A/B switch)
+    int opt_builder = 1;             // 0: Karras LBVH hierarchy, 1: PLOC (locally-ordered clustering) hierarchy
+    int opt_ploc_radius = 10;
 
     // inputs
     uchar4* bn = nullptr;
@@ -86,7 +88,9 @@ struct mrt_context {
     DevArray<uint32_t> hist;                // radix histograms
     DevArray<uint32_t> scan_tmp;
     DevArray<int32_t> bin_left, bin_right, bin_parent;  // binary nodes: [0,N-1) internal, [N-1,2N-1) leaves
-    DevArray<uint32_t> bin_first, bin_last;              // sorted range covered by each internal node
+    DevArray<uint32_t> bin_count;                        // primitives below each internal node
+    int bin_root = 0;                                    // root of the binary tree (0: LBVH, n-2: PLOC)
+    DevArray<uint32_t> ploc_c[2], ploc_nn, ploc_flag[2], ploc_scan[2];  // PLOC cluster lists and scratch
     DevArray<float4> bin_lo, bin_hi;                      // boxes of all 2N-1 binary nodes
     DevArray<uint32_t> bin_flag;
     DevArray<uint32_t> scene_bounds;                      // 6 ordered-int floats

@@ -161,14 +161,45 @@ MRT_D float q_plane(unsigned w, unsigned K, unsigned sel) { return __uint_as_flo
 // planes with PRMT so that neither pipe carries all 48 decodes (ncu: ALU pipe 65 % busy, FMA 22 %).
 MRT_D float q_plane_half(unsigned w, unsigned K, unsigned sel) { return __uint_as_float(__dp4a(w, 128u << (8 * sel), K)); }
 
-// conditional delta swap: exchanges the bit groups selected by m (pairs at distance sh)
-MRT_D unsigned delta_swap(unsigned x, unsigned m, int sh) {
-    unsigned t = ((x >> sh) ^ x) & m;
-    return x ^ (t | (t << sh));
+// Per-CTA shared memory of the traversal kernels: the lanes' stack columns and two bit-shuffle tables.
+struct TraceShared {
+    uint2 stack[TRACE_SM_STACK][TRACE_BLOCK];
+    uint32_t expand3[256];        // bit j -> bits 3j..3j+2
+    unsigned char perm[8][256];   // perm[c][x]: bit (s ^ c) = bit s of x
+};
+
+// The tables are compile-time constants in global memory; each CTA copies them (3 KB) into shared memory.
+struct TraceTables {
+    uint32_t expand3[256];
+    unsigned char perm[8][256];
+    constexpr TraceTables() : expand3(), perm() {
+        for (unsigned x = 0; x < 256u; x++) {
+            unsigned e = 0;
+            for (unsigned j = 0; j < 8; j++)
+                if (x & (1u << j)) e |= 7u << (3 * j);
+            expand3[x] = e;
+            for (unsigned c = 0; c < 8; c++) {
+                unsigned p = 0;
+                for (unsigned j = 0; j < 8; j++)
+                    if (x & (1u << j)) p |= 1u << (j ^ c);
+                perm[c][x] = (unsigned char)p;
+            }
+        }
+    }
+};
+static __device__ const TraceTables g_trace_tables = TraceTables();
+
+MRT_D void trace_shared_init(TraceShared& S) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_trace_tables);
+    uint32_t* dst = S.expand3;  // expand3[256] and perm[8][256] are contiguous in both structs
+    static_assert(sizeof(TraceTables) == 3072, "table layout");
+    for (unsigned i = threadIdx.x; i < sizeof(TraceTables) / 4; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
 }
 
 // One node step: take the nearest pending child of L.ng, fetch it, test its 8 children.
-MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, uint2* sm, uint2* spill, TraceCounters& cnt) {
+MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2* spill, TraceCounters& cnt) {
+    uint2* const sm = &S.stack[0][threadIdx.x];
     const unsigned bit = 31u - __clz(L.ng.y);
     L.ng.y &= ~(1u << bit);
     if (L.ng.y & 0xFF000000u) {  // siblings remain: keep the group for later
@@ -222,24 +253,21 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, uint2* sm, uint2* spi
 #endif
         const float t1x = fmaf(q_plane(wfx, K, j & 3), sfx, bfx), t1y = fmaf(q_plane(wfy, K, j & 3), sfy, bfy),
                     t1z = fmaf(q_plane(wfz, K, j & 3), sfz, bfz);
-        const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
-        const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tlimit));
-        miss = __funnelshift_l(__float_as_uint(tmax - tmin), miss, 1);  // (miss << 1) | sign(tmax - tmin)
+        // hit <=> tmin <= tmax && tmin <= tlimit && tmax >= 0: OR the three sign bits (one LOP3) instead of
+        // clamping with two more FMNMX -- the subtractions run on the under-used FMA pipe
+        const float tmin = fmaxf(fmaxf(t0x, t0y), t0z);
+        const float tmax = fminf(fminf(t1x, t1y), t1z);
+        const unsigned neg = __float_as_uint(tmax - tmin) | __float_as_uint(tlimit - tmin) | __float_as_uint(tmax);
+        miss = __funnelshift_l(neg, miss, 1);  // (miss << 1) | any sign set
     }
     const unsigned imask = n0.w >> 24;
     const unsigned hit8 = ~miss & 0xFFu;
-    // inner hits -> bit (slot ^ oct_inv)
-    unsigned inner = hit8 & imask;
-    inner = delta_swap(inner, (L.oct_inv & 1u) ? 0x55u : 0u, 1);
-    inner = delta_swap(inner, (L.oct_inv & 2u) ? 0x33u : 0u, 2);
-    inner = delta_swap(inner, (L.oct_inv & 4u) ? 0x0Fu : 0u, 4);
-    // leaf hits -> 3 bits per slot, masked by the triangles that exist
-    unsigned leaf = hit8 & ~imask;
-    leaf = (leaf ^ (leaf << 8)) & 0x00F00Fu;
-    leaf = (leaf ^ (leaf << 4)) & 0x0C30C3u;
-    leaf = (leaf ^ (leaf << 2)) & 0x249249u;
+    // inner hits -> bit (slot ^ oct_inv); leaf hits -> 3 bits per slot, masked by the triangles that exist.
+    // Both are 256-entry shared-memory tables (the LSU is idle here, the ALU pipe is the bottleneck).
+    const unsigned inner = S.perm[L.oct_inv][hit8 & imask];
+    const unsigned leaf = S.expand3[hit8 & ~imask];
     L.ng = make_uint2(n1.x, (inner << 24) | imask);
-    L.tg = make_uint2(n1.y, (leaf * 7u) & n1.z);
+    L.tg = make_uint2(n1.y, leaf & n1.z);
     L.tgmask = n1.z;
 }
 
@@ -263,7 +291,8 @@ MRT_D void lane_tri_step(LaneState& L, const BvhDev& bvh, TraceCounters& cnt) {
 //   void     Job::store(uint32_t i, const TraceHit& h);
 // work_counter: global counter of handed-out rays (zeroed before the launch).
 template <class Job>
-MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter, uint2* sm, TraceCounters& cnt) {
+MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter, TraceShared& S, TraceCounters& cnt) {
+    uint2* const sm = &S.stack[0][threadIdx.x];
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t total = job.count();
@@ -321,7 +350,7 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
         if (tmask && (nmask == 0u || __popc(tmask) >= TRACE_TRI_MIN)) {
             if (want_tri) lane_tri_step(L, bvh, cnt);
         } else if (nmask) {
-            if (want_node) lane_node_step(L, bvh, sm, spill, cnt);
+            if (want_node) lane_node_step(L, bvh, S, spill, cnt);
         }
     }
 }
@@ -329,13 +358,14 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
 // Per-lane loop for COHERENT rays (the primary pass): one node, then its triangles, per iteration.
 // Rays of an 8x4 pixel tile walk the same nodes and reach leaves together, so the warp stays
 // converged without the state machine, and testing triangles at once tightens t early.
-MRT_D TraceHit trace_coherent(const BvhDev& bvh, float3 o, float3 d, uint2* sm, TraceCounters& cnt) {
+MRT_D TraceHit trace_coherent(const BvhDev& bvh, float3 o, float3 d, TraceShared& S, TraceCounters& cnt) {
+    uint2* const sm = &S.stack[0][threadIdx.x];
     uint2 spill[TRACE_LOCAL_STACK];
     LaneState L;
     lane_begin(L, o, d);
     if (bvh.num_nodes == 0) return L.hit;
     for (;;) {
-        if (L.ng.y & 0xFF000000u) lane_node_step(L, bvh, sm, spill, cnt);
+        if (L.ng.y & 0xFF000000u) lane_node_step(L, bvh, S, spill, cnt);
         while (L.tg.y) lane_tri_step(L, bvh, cnt);
         if (!(L.ng.y & 0xFF000000u)) {
             if (L.sp == 0) break;
