@@ -33,10 +33,23 @@ def partition_rows(rank, nranks, slab_rows, full_h):
     return rows
 
 
+_ROW_CACHE = {}
+
+
+def _rows_on_device(world, slab_rows, full_h, device):
+    """(counts, one int64 row-index tensor per rank on `device`), cached: the mapping is static per partition."""
+    key = (world, slab_rows, full_h, str(device))
+    if key not in _ROW_CACHE:
+        rows = [partition_rows(r, world, slab_rows, full_h) for r in range(world)]
+        _ROW_CACHE[key] = ([len(x) for x in rows],
+                           [torch.from_numpy(x.astype(np.int64)).to(device) for x in rows])
+    return _ROW_CACHE[key]
+
+
 def gather_tiles(local, full_h, slab_rows, dst=0, group=None):
     """local: [local_rows, W, C] tensor of this rank's slabs.  Returns the [full_h, W, C] image on dst, None elsewhere."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    counts = [len(partition_rows(r, world, slab_rows, full_h)) for r in range(world)]
+    counts, row_idx = _rows_on_device(world, slab_rows, full_h, local.device)
     assert local.shape[0] == counts[rank], f"rank {rank}: {local.shape[0]} local rows, expected {counts[rank]}"
     pad = max(counts)
     buf = local
@@ -49,8 +62,7 @@ def gather_tiles(local, full_h, slab_rows, dst=0, group=None):
         dist.gather(buf, parts, dst=dst, group=group)
         full = torch.empty((full_h,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         for r in range(world):
-            rows = torch.from_numpy(partition_rows(r, world, slab_rows, full_h).astype(np.int64)).to(local.device)
-            full[rows] = parts[r][: counts[r]]
+            full[row_idx[r]] = parts[r][: counts[r]]
         return full
     dist.gather(buf, None, dst=dst, group=group)
     return None

@@ -23,9 +23,11 @@ def random_rays(n, lo, hi, seed):
     return o, d
 
 
+@pytest.mark.parametrize("builder", [0, 1], ids=["lbvh", "ploc"])
 @pytest.mark.parametrize("maker", ["cornell", "small_terrain"])
-def test_bvh_equals_brute_force_random_rays(gpu_ctx, oracle, maker):
+def test_bvh_equals_brute_force_random_rays(gpu_ctx, oracle, maker, builder):
     pos, idx, alb, view = getattr(scenes, maker)()
+    gpu_ctx.set_option("builder", builder)
     gpu_ctx.upload_mesh(pos, idx, alb)
     gpu_ctx.build()
     st = gpu_ctx.stats()
