@@ -122,6 +122,7 @@ typedef struct {
     uint64_t tri_tests;       /*   (only when mrt_set_option("count_visits", 1))            */
     uint32_t trace_launches;  /* traversal kernel launches inside the last mrt_secondary_rays */
     uint32_t _reserved;
+    uint64_t total_rays;      /* primary + secondary rays traced since mrt_stats_reset (device-side running sum) */
 } mrt_stats;
 
 /* ---- lifetime ---- */
@@ -182,6 +183,13 @@ int mrt_tonemap(mrt_context* ctx, int mode, float exposure, const float* params,
 /* ---- outputs ---- */
 int mrt_buffer(mrt_context* ctx, int buffer_id, void** device_ptr, size_t* bytes);
 int mrt_readback(mrt_context* ctx, int buffer_id, void* host, size_t bytes);
+/* Pipelined framebuffer readback (MRT_BUF_LDR only): the device->host copy of the frame just tonemapped runs
+ * on a second stream while the caller issues the next frame, which tonemaps into the other half of the
+ * double-buffered framebuffer -- the counterpart of the reference's frames in flight (renderer.ixx:36).
+ * host must stay valid (ideally pinned) until mrt_readback_wait returns. */
+int mrt_readback_async(mrt_context* ctx, int buffer_id, void* host, size_t bytes);
+/* blocks until at most frames_in_flight (0 or 1) async readbacks are still outstanding */
+int mrt_readback_wait(mrt_context* ctx, int frames_in_flight);
 int mrt_sync(mrt_context* ctx);
 int mrt_stats_get(mrt_context* ctx, mrt_stats* out);
 int mrt_stats_reset(mrt_context* ctx);

@@ -50,7 +50,7 @@ class Stats(C.Structure):
                 ("ms_build", C.c_float), ("ms_sky", C.c_float), ("kernel_launches", C.c_uint32),
                 ("stack_overflows", C.c_uint32), ("num_triangles", C.c_uint32), ("num_wide_nodes", C.c_uint32),
                 ("bvh_bytes", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
-                ("trace_launches", C.c_uint32), ("_reserved", C.c_uint32)]
+                ("trace_launches", C.c_uint32), ("_reserved", C.c_uint32), ("total_rays", C.c_uint64)]
 
 
 EXPORTS = [
@@ -58,7 +58,8 @@ EXPORTS = [
     "mrt_scene_set_spheres", "mrt_scene_upload_mesh", "mrt_scene_update_positions", "mrt_scene_build",
     "mrt_atmosphere", "mrt_sky_view", "mrt_set_partition", "mrt_partition_rows", "mrt_primary_rays",
     "mrt_secondary_rays", "mrt_tonemap", "mrt_buffer", "mrt_readback", "mrt_sync", "mrt_stats_get",
-    "mrt_stats_reset", "mrt_stream", "mrt_trace_rays", "mrt_partition_rows_for",
+    "mrt_stats_reset", "mrt_stream", "mrt_trace_rays", "mrt_partition_rows_for", "mrt_readback_async",
+    "mrt_readback_wait",
 ]
 
 
@@ -101,6 +102,8 @@ def load():
     L.mrt_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mrt_readback.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.mrt_sync.argtypes = [vp]
+    L.mrt_readback_async.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.mrt_readback_wait.argtypes = [vp, C.c_int]
     L.mrt_stats_get.argtypes = [vp, C.POINTER(Stats)]
     L.mrt_stats_reset.argtypes = [vp]
     L.mrt_stream.argtypes = [vp, C.POINTER(vp)]
@@ -241,6 +244,12 @@ class Context:
 
     def readback_into(self, buf, host_ptr, nbytes):
         self._ck(self.L.mrt_readback(self.h, buf, host_ptr, nbytes))
+
+    def readback_async(self, buf, host_ptr, nbytes):
+        self._ck(self.L.mrt_readback_async(self.h, buf, host_ptr, nbytes))
+
+    def readback_wait(self, frames_in_flight=0):
+        self._ck(self.L.mrt_readback_wait(self.h, frames_in_flight))
 
     def stats(self):
         s = Stats()

@@ -59,7 +59,7 @@ int buffer_info(mrt_context* ctx, int id, void** p, size_t* bytes) {
         }
         *p = ctx->color16.p; *bytes = n * 8; return MRT_OK;
     case MRT_BUF_ACCUM: if (!ctx->have_accum) break; *p = ctx->accum.p; *bytes = n * 16; return MRT_OK;
-    case MRT_BUF_LDR: if (!ctx->have_ldr) break; *p = ctx->ldr.p; *bytes = n * 4; return MRT_OK;
+    case MRT_BUF_LDR: if (!ctx->have_ldr) break; *p = ctx->ldr_buf[ctx->ldr_cur].p; *bytes = n * 4; return MRT_OK;
     case MRT_BUF_TRANSMITTANCE: if (!ctx->have_atmo) break; *p = ctx->trans16.p; *bytes = (size_t)MRT_TRANS_W * MRT_TRANS_H * 8; return MRT_OK;
     case MRT_BUF_MULTISCATTERING: if (!ctx->have_atmo) break; *p = ctx->multi16.p; *bytes = (size_t)MRT_MULTI_W * MRT_MULTI_H * 8; return MRT_OK;
     case MRT_BUF_SKY_VIEW: if (!ctx->have_view) break; *p = ctx->view_packed.p; *bytes = (size_t)MRT_VIEW_W * MRT_VIEW_H * 4; return MRT_OK;
@@ -95,6 +95,9 @@ int mrt_create(int device, mrt_context** out) {
         return MRT_ERR_CUDA;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ldr_ready, cudaEventDisableTiming);
+    for (auto& ev : ctx->copy_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     *out = ctx;
     return MRT_OK;
 }
@@ -117,13 +120,16 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->trans16); dev_free(ctx->multi16); dev_free(ctx->view_packed);
     dev_free(ctx->trans_f); dev_free(ctx->multi_f); dev_free(ctx->view_f);
     dev_free(ctx->visibility); dev_free(ctx->depth); dev_free(ctx->normal); dev_free(ctx->motion); dev_free(ctx->color16);
-    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->ldr);
+    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
     dev_free(ctx->hit0_pos); dev_free(ctx->hit0_n); dev_free(ctx->path_state);
     for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); }
     dev_free(ctx->hits); dev_free(ctx->queue_counts); dev_free(ctx->sort_keys); dev_free(ctx->sort_keys_alt);
-    dev_free(ctx->sort_vals); dev_free(ctx->sort_vals_alt); dev_free(ctx->visit_counters);
+    dev_free(ctx->sort_vals); dev_free(ctx->sort_vals_alt); dev_free(ctx->visit_counters); dev_free(ctx->total_rays);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->trace_ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ldr_ready) cudaEventDestroy(ctx->ldr_ready);
+    for (auto& ev : ctx->copy_done) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -335,6 +341,38 @@ int mrt_readback(mrt_context* ctx, int buffer_id, void* host, size_t bytes) {
     return MRT_OK;
 }
 
+// Asynchronous framebuffer readback: the copy runs on a second stream as soon as the tonemap that produced
+// the current LDR buffer is done, so the host can already issue the next frame (which tonemaps into the
+// other LDR buffer).  mrt_readback_wait blocks until every outstanding async readback has landed.
+int mrt_readback_async(mrt_context* ctx, int buffer_id, void* host, size_t bytes) {
+    MRT_ENTER(ctx);
+    if (buffer_id != MRT_BUF_LDR) return mrt_fail(ctx, MRT_ERR_INVALID, "async readback is only available for MRT_BUF_LDR");
+    void* p = nullptr;
+    size_t have = 0;
+    MRT_TRY(buffer_info(ctx, buffer_id, &p, &have));
+    if (!host || bytes > have) return mrt_fail(ctx, MRT_ERR_INVALID, "readback of %zu bytes from a %zu-byte buffer", bytes, have);
+    MRT_CUDA(ctx, cudaEventRecord(ctx->ldr_ready, ctx->stream));
+    MRT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ldr_ready, 0));
+    MRT_CUDA(ctx, cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    MRT_CUDA(ctx, cudaEventRecord(ctx->copy_done[ctx->ldr_cur], ctx->copy_stream));
+    ctx->copy_pending[ctx->ldr_cur] = true;
+    return MRT_OK;
+}
+
+int mrt_readback_wait(mrt_context* ctx, int frames_in_flight) {
+    MRT_ENTER(ctx);
+    const int newest = ctx->ldr_cur, older = ctx->ldr_cur ^ 1;
+    if (ctx->copy_pending[older]) {
+        MRT_CUDA(ctx, cudaEventSynchronize(ctx->copy_done[older]));
+        ctx->copy_pending[older] = false;
+    }
+    if (frames_in_flight <= 0 && ctx->copy_pending[newest]) {
+        MRT_CUDA(ctx, cudaEventSynchronize(ctx->copy_done[newest]));
+        ctx->copy_pending[newest] = false;
+    }
+    return MRT_OK;
+}
+
 int mrt_sync(mrt_context* ctx) {
     MRT_ENTER(ctx);
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -383,6 +421,11 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
         ctx->stats.tri_tests = vc[1] + vc[5];
         ctx->stats.stack_overflows = (uint32_t)(vc[2] + vc[6]);
     }
+    if (ctx->total_rays.p) {
+        unsigned long long t = 0;
+        MRT_CUDA(ctx, cudaMemcpy(&t, ctx->total_rays.p, sizeof t, cudaMemcpyDeviceToHost));
+        ctx->stats.total_rays = t;
+    }
     *out = ctx->stats;
     return MRT_OK;
 }
@@ -390,6 +433,8 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
 int mrt_stats_reset(mrt_context* ctx) {
     MRT_ENTER(ctx);
     ctx->stats.kernel_launches = 0;
+    MRT_TRY(dev_reserve(ctx, ctx->total_rays, 1));
+    MRT_CUDA(ctx, cudaMemsetAsync(ctx->total_rays.p, 0, sizeof(unsigned long long), ctx->stream));
     return MRT_OK;
 }
 

@@ -119,7 +119,11 @@ struct mrt_context {
     DevArray<uint16_t> depth, normal, motion, color16;
     DevArray<float> hit_t;
     DevArray<float4> accum;
-    DevArray<uchar4> ldr;
+    DevArray<uchar4> ldr_buf[2];         // double-buffered output framebuffer: an async readback of frame f
+    int ldr_cur = 0;                     // overlaps the rendering of frame f+1 (the reference keeps 3 frames in flight)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ldr_ready = nullptr, copy_done[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
     // wavefront state (triangle path)
     DevArray<float4> hit0_pos, hit0_n;   // primary hit position|prim id, normal|valid
     DevArray<float4> path_state;         // throughput rgb | rng state
@@ -130,6 +134,7 @@ struct mrt_context {
     DevArray<uint64_t> sort_keys, sort_keys_alt;
     DevArray<uint32_t> sort_vals, sort_vals_alt;
     DevArray<unsigned long long> visit_counters;  // node visits, tri tests, stack overflows
+    DevArray<unsigned long long> total_rays;      // running sum of traced rays since mrt_stats_reset
 
     // stats
     mrt_stats stats{};

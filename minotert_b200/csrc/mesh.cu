@@ -266,6 +266,14 @@ __global__ void __launch_bounds__(128) k_trace_brute(const float* __restrict__ p
     ts[k] = h.prim != MRT_MISS_ID ? h.t : 0.0f;
 }
 
+// running ray total (mrt_stats.total_rays): primary pixels + every queue size of this frame
+__global__ void k_sum_rays(const uint32_t* __restrict__ counts, uint32_t n, unsigned long long extra, unsigned long long* total) {
+    unsigned long long s = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += 32) s += counts[i];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, off);
+    if (threadIdx.x == 0) *total += s + extra;
+}
+
 BvhDev make_bvh(mrt_context* ctx) {
     BvhDev b;
     b.nodes = ctx->nodes.p;
@@ -397,6 +405,10 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
             MRT_LAUNCHED(ctx);
             q ^= 1;
         }
+    }
+    if (ctx->total_rays.p) {
+        k_sum_rays<<<1, 32, 0, ctx->stream>>>(ctx->queue_counts.p, waves + 1, (unsigned long long)npix, ctx->total_rays.p);
+        MRT_LAUNCHED(ctx);
     }
     return mrt_check_cuda(ctx, cudaGetLastError(), "mesh_secondary");
 }

@@ -141,7 +141,13 @@ int tonemap_run(mrt_context* ctx, int mode, float exposure, const float* params,
     T.mode = mode;
     T.exposure = exposure;
     for (uint32_t i = 0; i < nparams && i < 6; i++) T.p[i] = params[i];
-    MRT_TRY(dev_reserve(ctx, ctx->ldr, ctx->npix));
+    ctx->ldr_cur ^= 1;
+    DevArray<uchar4>& ldr = ctx->ldr_buf[ctx->ldr_cur];
+    if (ctx->copy_pending[ctx->ldr_cur]) {  // an async readback may still be draining this buffer
+        MRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done[ctx->ldr_cur], 0));
+        ctx->copy_pending[ctx->ldr_cur] = false;
+    }
+    MRT_TRY(dev_reserve(ctx, ldr, ctx->npix));
     size_t n = ctx->npix;
     // grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM
     int sms = 148;
@@ -150,10 +156,10 @@ int tonemap_run(mrt_context* ctx, int mode, float exposure, const float* params,
     if ((size_t)grid * 256 > n) grid = div_up(n, 256);
     if (grid == 0) grid = 1;
     if (source == MRT_BUF_ACCUM)
-        k_tonemap<true><<<grid, 256, 0, ctx->stream>>>(T, ctx->accum.p, nullptr, ctx->ldr.p, n);
+        k_tonemap<true><<<grid, 256, 0, ctx->stream>>>(T, ctx->accum.p, nullptr, ldr.p, n);
     else
         k_tonemap<false><<<grid, 256, 0, ctx->stream>>>(T, nullptr, reinterpret_cast<const uint2*>(ctx->color16.p),
-                                                        ctx->ldr.p, n);
+                                                        ldr.p, n);
     MRT_LAUNCHED(ctx);
     ctx->have_ldr = true;
     return mrt_check_cuda(ctx, cudaGetLastError(), "tonemap");

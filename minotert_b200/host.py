@@ -60,6 +60,8 @@ def load():
     L.minote_app_draw.argtypes = [vp, cam]
     L.minote_app_read_framebuffer.argtypes = [vp, vp, C.c_size_t]
     L.minote_app_stats.argtypes = [vp, C.POINTER(capi.Stats)]
+    L.minote_app_read_framebuffer_async.argtypes = [vp, vp, C.c_size_t]
+    L.minote_app_wait_framebuffer.argtypes = [vp, C.c_int]
     L.minote_app_frame_count.argtypes = [vp]
     L.minote_app_frame_count.restype = u32
     _lib = L
@@ -164,6 +166,12 @@ class Renderer:
 
     def read_framebuffer_into(self, host_ptr, nbytes):
         self._ck(self.L.minote_app_read_framebuffer(self.h, host_ptr, nbytes))
+
+    def read_framebuffer_async(self, host_ptr, nbytes):
+        self._ck(self.L.minote_app_read_framebuffer_async(self.h, host_ptr, nbytes))
+
+    def wait_framebuffer(self, frames_in_flight=0):
+        self._ck(self.L.minote_app_wait_framebuffer(self.h, frames_in_flight))
 
     def stats(self):
         s = capi.Stats()

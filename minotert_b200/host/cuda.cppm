@@ -72,4 +72,5 @@ export struct DeviceImage {
         return n;
     }
     void readback(void* host, std::size_t n) const { Cuda::serv->check(mrt_readback(Cuda::serv->ctx, id, host, n)); }
+    void readbackAsync(void* host, std::size_t n) const { Cuda::serv->check(mrt_readback_async(Cuda::serv->ctx, id, host, n)); }
 };

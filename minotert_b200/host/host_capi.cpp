@@ -139,6 +139,12 @@ int minote_app_draw(void* a, Camera const* cam) {
 int minote_app_read_framebuffer(void* a, void* host, std::size_t bytes) {
     return guarded(static_cast<App*>(a), [&] { Renderer::serv->readFramebuffer(host, bytes); });
 }
+int minote_app_read_framebuffer_async(void* a, void* host, std::size_t bytes) {
+    return guarded(static_cast<App*>(a), [&] { Renderer::serv->readFramebufferAsync(host, bytes); });
+}
+int minote_app_wait_framebuffer(void* a, int frames_in_flight) {
+    return guarded(static_cast<App*>(a), [&] { Renderer::serv->waitFramebuffer(frames_in_flight); });
+}
 int minote_app_stats(void* a, mrt_stats* out) {
     return guarded(static_cast<App*>(a), [&] { *out = Renderer::serv->stats(); });
 }

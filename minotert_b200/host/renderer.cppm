@@ -59,6 +59,9 @@ public:
 
     // host copy of the output framebuffer (RGBA8); blocks until the frame is done
     void readFramebuffer(void* host, std::size_t bytes) const { framebuffer.readback(host, bytes); }
+    // frames in flight (renderer.ixx:36): start copying this frame out while the next draw() is issued
+    void readFramebufferAsync(void* host, std::size_t bytes) const { framebuffer.readbackAsync(host, bytes); }
+    void waitFramebuffer(int framesInFlight = 0) const { Cuda::serv->check(mrt_readback_wait(Cuda::serv->ctx, framesInFlight)); }
     [[nodiscard]] auto stats() const -> mrt_stats {
         mrt_stats s;
         Cuda::serv->check(mrt_stats_get(Cuda::serv->ctx, &s));
