@@ -188,6 +188,8 @@ def run_ours(args):
     r = host.Renderer(w, h, bn, device=local)
     r.context().set_option("builder", 1 if args.builder == "ploc" else 0)
     r.context().set_option("ploc_radius", args.ploc_radius)
+    r.context().set_option("sort_rays", 1 if args.sort_rays else 0)
+    r.context().set_option("trace_timing", 0 if args.no_trace_timing else 1)
     r.set_mesh(pos, idx, alb)
     r.configure(samples=spp, bounces=bounces, accumulate=False, tonemap="amd", exposure=1.0)
     ctx = r.context()
@@ -238,21 +240,19 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    rays_total, trace_ms, trace_launches, trace_rays, primary_ms = 0, 0.0, 0, 0, 0.0
     for i in range(args.steps):
-        flush_l2()
+        flush_l2()                                   # outside the event pair of the step
         ev[i][0].record(stream)
-        frame((args.warmup + i) * world + rank + 1)
+        frame((args.warmup + i) * world + rank + 1)  # no host sync inside the loop: frames are issued back to back
         ev[i][1].record(stream)
-        st = ctx.stats()  # syncs; outside the event-bracketed region
-        rays_total += st.primary_rays + st.secondary_rays
-        trace_ms += st.ms_trace
-        trace_launches += st.trace_launches
-        trace_rays += st.secondary_rays
-        primary_ms += st.ms_primary
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    st = ctx.stats()  # running totals since stats_reset: rays (device-side sum), traversal launches and their event times
+    rays_total = int(st.total_rays)
+    trace_ms, trace_launches = st.ms_trace, st.trace_launches
+    trace_rays = rays_total - npix * args.steps
+    primary_ms = st.ms_primary * args.steps          # last frame's primary pass (identical work every frame)
     launches = ctx.stats().kernel_launches
     clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -315,7 +315,7 @@ def run_ours(args):
             "config": {"workload": wl, "triangles": int(idx.shape[0]), "resolution": [w, h], "spp": spp, "bounces": bounces,
                        "sampling": "PCG + blue-noise Cranley-Patterson rotation", "tonemap": "amd",
                        "l2": "flushed between steps (256 MiB memset)", "bvh_bytes": int(build_stats.bvh_bytes),
-                       "wide_nodes": int(build_stats.num_wide_nodes), "bvh_build_ms": build_stats.ms_build, "builder": args.builder,
+                       "wide_nodes": int(build_stats.num_wide_nodes), "bvh_build_ms": build_stats.ms_build, "builder": args.builder, "sort_rays": bool(args.sort_rays),
                        "stack_overflows": int(ctx.stats().stack_overflows),
                        "parallelism": "1 GPU" if world == 1 else f"sample sets over {world} GPUs, replicated BVH, NCCL reduce of the fp32 accumulator"},
             "clocks": clocks,
@@ -362,6 +362,8 @@ def main():
     ap.add_argument("--bounces", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ploc-radius", type=int, default=6)
+    ap.add_argument("--no-trace-timing", action="store_true", help="A/B: drop the per-launch CUDA events (roofline fields become 0)")
+    ap.add_argument("--sort-rays", action="store_true", help="bin each bounce's ray queue by direction octant before tracing")
     ap.add_argument("--builder", default="ploc", choices=["ploc", "lbvh"], help="binary hierarchy under the 8-wide BVH")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

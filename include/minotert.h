@@ -109,7 +109,7 @@ typedef struct {
     uint64_t secondary_rays; /* rays traced by the last mrt_secondary_rays */
     float ms_primary;        /* device time of the last call of each kind (CUDA events) */
     float ms_secondary;
-    float ms_trace;          /* traversal kernels only, inside the last mrt_secondary_rays */
+    float ms_trace;          /* bounce-wave traversal launches since mrt_stats_reset: summed device time */
     float ms_tonemap;
     float ms_build;
     float ms_sky;
@@ -120,7 +120,7 @@ typedef struct {
     uint64_t bvh_bytes;       /* wide nodes + reordered triangles resident in HBM */
     uint64_t node_visits;     /* wide nodes fetched / triangles tested by the last counted trace */
     uint64_t tri_tests;       /*   (only when mrt_set_option("count_visits", 1))            */
-    uint32_t trace_launches;  /* traversal kernel launches inside the last mrt_secondary_rays */
+    uint32_t trace_launches;  /* ... and their number (CUDA event pairs, at most 4096 per reset) */
     uint32_t _reserved;
     uint64_t total_rays;      /* primary + secondary rays traced since mrt_stats_reset (device-side running sum) */
 } mrt_stats;

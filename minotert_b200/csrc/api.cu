@@ -143,6 +143,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "sort_rays")) ctx->opt_sort_rays = value != 0;
     else if (!strcmp(name, "persistent")) ctx->opt_persistent = value != 0;
     else if (!strcmp(name, "persistent_primary")) ctx->opt_persistent_primary = value != 0;
+    else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "builder")) { ctx->opt_builder = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "ploc_radius")) { ctx->opt_ploc_radius = (int)(value < 1 ? 1 : (value > 32 ? 32 : value)); ctx->bvh_valid = false; }
     else return mrt_fail(ctx, MRT_ERR_INVALID, "unknown option '%s'", name);
@@ -433,6 +434,7 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
 int mrt_stats_reset(mrt_context* ctx) {
     MRT_ENTER(ctx);
     ctx->stats.kernel_launches = 0;
+    ctx->trace_ev_used = 0;
     MRT_TRY(dev_reserve(ctx, ctx->total_rays, 1));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->total_rays.p, 0, sizeof(unsigned long long), ctx->stream));
     return MRT_OK;

@@ -109,17 +109,99 @@ struct QueueJob {
     const float4* ray_d;
     const uint32_t* count_ptr;
     float4* hits;
+    const uint32_t* order;  // optional: ray k of the sorted order is queue entry order[k] (row n5 sort stage)
     MRT_D uint32_t count() const { return *count_ptr; }
     MRT_D bool load(uint32_t i, float3& o, float3& d) const {
-        float4 o4 = __ldg(&ray_o[i]), d4 = __ldg(&ray_d[i]);
+        const uint32_t k = order ? __ldg(&order[i]) : i;
+        float4 o4 = __ldg(&ray_o[k]), d4 = __ldg(&ray_d[k]);
         o = f3(o4.x, o4.y, o4.z);
         d = f3(d4.x, d4.y, d4.z);
         return true;
     }
     MRT_D void store(uint32_t i, const TraceHit& h) const {
-        hits[i] = make_float4(h.t, __uint_as_float(h.tri), 0.0f, 0.0f);
+        const uint32_t k = order ? __ldg(&order[i]) : i;  // hit records stay in queue order for the shade kernel
+        hits[k] = make_float4(h.t, __uint_as_float(h.tri), 0.0f, 0.0f);
     }
 };
+
+// ---- ray sort between bounces (row n5, optional): stable counting sort of the queue by direction octant ----
+// Compaction already leaves the queue in pixel order (neighbouring origins); binning by octant on top of that
+// gives every warp rays that share the near/far plane selection and the child visiting order.  One histogram
+// pass, one scan over 8 x tiles counters, one scatter that writes only the 4-byte permutation: the 32-byte ray
+// records are not moved, the trace kernel gathers them through the permutation.
+constexpr int OB_THREADS = 256, OB_ITEMS = 8, OB_TILE = OB_THREADS * OB_ITEMS, OB_WARPS = OB_THREADS / 32;
+
+MRT_D unsigned ray_octant(float4 d) { return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u); }
+
+__global__ void __launch_bounds__(OB_THREADS) k_oct_hist(const float4* __restrict__ ray_d, const uint32_t* __restrict__ count_ptr,
+                                                         uint32_t* __restrict__ hist, uint32_t tiles) {
+    __shared__ uint32_t h[8];
+    if (threadIdx.x < 8) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t count = *count_ptr;
+    const uint32_t base = blockIdx.x * OB_TILE;
+    if (base < count) {
+#pragma unroll
+        for (int j = 0; j < OB_ITEMS; j++) {
+            uint32_t i = base + j * OB_THREADS + threadIdx.x;
+            bool valid = i < count;
+            unsigned oct = valid ? ray_octant(__ldg(&ray_d[i])) : 8u + (threadIdx.x & 31);
+            unsigned peers = __match_any_sync(0xFFFFFFFFu, oct);
+            if (valid && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[oct], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) hist[threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(OB_THREADS) k_oct_scatter(const float4* __restrict__ ray_d, const uint32_t* __restrict__ count_ptr,
+                                                            const uint32_t* __restrict__ offsets, uint32_t tiles,
+                                                            uint32_t* __restrict__ order) {
+    __shared__ uint32_t wc[OB_WARPS][8];
+    __shared__ uint32_t gbase[8];
+    const uint32_t count = *count_ptr;
+    const uint32_t tile_base = blockIdx.x * OB_TILE;
+    if (tile_base >= count) return;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < OB_WARPS * 8) (&wc[0][0])[threadIdx.x] = 0;
+    if (threadIdx.x < 8) gbase[threadIdx.x] = offsets[threadIdx.x * tiles + blockIdx.x];
+    __syncthreads();
+    unsigned oct[OB_ITEMS];
+    uint32_t loc[OB_ITEMS];
+    const uint32_t wbase = tile_base + warp * (32 * OB_ITEMS);
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < OB_ITEMS; j++) {
+        uint32_t i = wbase + j * 32 + lane;
+        bool valid = i < count;
+        oct[j] = valid ? ray_octant(__ldg(&ray_d[i])) : 8u + lane;
+        unsigned peers = __match_any_sync(0xFFFFFFFFu, oct[j]);
+        unsigned leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (valid && lane == leader) {
+            base = wc[warp][oct[j]];
+            wc[warp][oct[j]] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        loc[j] = base + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {  // exclusive prefix over the tile's warps, per octant
+        uint32_t run = 0;
+        for (int w = 0; w < OB_WARPS; w++) {
+            uint32_t c = wc[w][threadIdx.x];
+            wc[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < OB_ITEMS; j++) {
+        uint32_t i = wbase + j * 32 + lane;
+        if (i < count) order[gbase[oct[j]] + wc[warp][oct[j]] + loc[j]] = i;
+    }
+}
 
 // ---- closest-hit query for mrt_trace_rays ----
 struct QueryJob {
@@ -369,7 +451,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     const unsigned shade_grid = div_up(npix, 256), tgrid = trace_grid(ctx, npix);
 
     uint32_t wave = 0;
-    ctx->trace_ev_used = 0;
+    constexpr uint32_t kMaxTimedLaunches = 4096;  // event pairs kept since mrt_stats_reset
     for (uint32_t s = 0; s < spp; s++) {
         P.first_sample = s == 0;
         P.vertex = 0;
@@ -382,18 +464,33 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         MRT_LAUNCHED(ctx);
         for (uint32_t b = 1; b <= bounces; b++) {
             const uint32_t* in_count = ctx->queue_counts.p + wave;
-            while (ctx->trace_ev.size() < 2 * (size_t)(ctx->trace_ev_used + 1)) {
+            const bool timed = ctx->opt_trace_timing && ctx->trace_ev_used < kMaxTimedLaunches;
+            while (timed && ctx->trace_ev.size() < 2 * (size_t)(ctx->trace_ev_used + 1)) {
                 cudaEvent_t e;
                 MRT_CUDA(ctx, cudaEventCreate(&e));
                 ctx->trace_ev.push_back(e);
             }
-            cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used], ctx->stream);
-            QueueJob J{ctx->ray_o[q].p, ctx->ray_d[q].p, in_count, ctx->hits.p};
+            if (timed) cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used], ctx->stream);
+            const bool sort = ctx->opt_sort_rays || (flags & MRT_SECONDARY_SORT_RAYS);
+            if (sort) {
+                const uint32_t tiles = div_up(npix, OB_TILE);
+                MRT_TRY(dev_reserve(ctx, ctx->sort_vals, npix));
+                MRT_TRY(dev_reserve(ctx, ctx->sort_vals_alt, 8 * (size_t)tiles));
+                k_oct_hist<<<tiles, OB_THREADS, 0, ctx->stream>>>(ctx->ray_d[q].p, in_count, ctx->sort_vals_alt.p, tiles);
+                MRT_LAUNCHED(ctx);
+                MRT_TRY(scan_exclusive_u32(ctx, ctx->sort_vals_alt.p, ctx->sort_vals_alt.p, 8 * (size_t)tiles));
+                k_oct_scatter<<<tiles, OB_THREADS, 0, ctx->stream>>>(ctx->ray_d[q].p, in_count, ctx->sort_vals_alt.p, tiles,
+                                                                    ctx->sort_vals.p);
+                MRT_LAUNCHED(ctx);
+            }
+            QueueJob J{ctx->ray_o[q].p, ctx->ray_d[q].p, in_count, ctx->hits.p, sort ? ctx->sort_vals.p : nullptr};
             k_trace<QueueJob><<<tgrid, TRACE_BLOCK, 0, ctx->stream>>>(J, bvh, ctx->queue_counts.p + waves + 1 + wave,
                                                                       ctx->visit_counters.p + 4, ctx->opt_count_visits);
             MRT_LAUNCHED(ctx);
-            cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used + 1], ctx->stream);
-            ctx->trace_ev_used++;
+            if (timed) {
+                cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used + 1], ctx->stream);
+                ctx->trace_ev_used++;
+            }
             wave++;
             P.vertex = b;
             // the last vertex emits nothing; its counter slot stays 0

@@ -37,8 +37,12 @@
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 6   // resident CTAs per SM the register budget is capped for (80 regs/thread)
 #endif
-#define TRACE_SM_STACK 10
-#define TRACE_LOCAL_STACK 38
+#ifndef TRACE_SM_STACK
+#define TRACE_SM_STACK 10    // stack entries per lane kept in shared memory
+#endif
+#ifndef TRACE_LOCAL_STACK
+#define TRACE_LOCAL_STACK 38 // deeper entries spill to local memory
+#endif
 #ifndef TRACE_CHUNK
 #define TRACE_CHUNK 32       // rays a warp takes per global atomic
 #endif
@@ -47,6 +51,12 @@
 #endif
 #ifndef TRACE_TRI_MIN
 #define TRACE_TRI_MIN 8      // lanes with a pending triangle that trigger a triangle step
+#endif
+#ifndef TRACE_TRI_PER_STEP
+#define TRACE_TRI_PER_STEP 2 // triangles a lane may test in one triangle step (1: lanes with leftovers idle; 3+: long steps)
+#endif
+#ifndef TRACE_PREFETCH
+#define TRACE_PREFETCH 0     // prefetch the next child node to L1 at the end of a node step (A/B measured)
 #endif
 #ifndef TRACE_DP4A_NEAR
 #define TRACE_DP4A_NEAR 1    // decode near planes with IDP.4A (FMA-heavy pipe), far planes with PRMT (ALU pipe)
@@ -269,6 +279,18 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2
     L.ng = make_uint2(n1.x, (inner << 24) | imask);
     L.tg = make_uint2(n1.y, leaf & n1.z);
     L.tgmask = n1.z;
+#if TRACE_PREFETCH
+    // The child this lane visits next is already known: pull its 80 bytes towards L1 while the warp does its
+    // triangle step / loop bookkeeping (ncu: long_scoreboard is the top stall of the bounce waves).
+    if (inner) {
+        const unsigned nbit = 31u - __clz(inner << 24);
+        const unsigned nslot = (nbit - 24u) ^ L.oct_inv;
+        const unsigned nrel = __popc(imask & ~(0xFFFFFFFFu << nslot));
+        const char* p = reinterpret_cast<const char*>(bvh.nodes + (n1.x + nrel));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 64));
+    }
+#endif
 }
 
 MRT_D void lane_tri_step(LaneState& L, const BvhDev& bvh, TraceCounters& cnt) {
@@ -348,7 +370,13 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
         const unsigned tmask = __ballot_sync(0xFFFFFFFFu, want_tri);
         const unsigned nmask = __ballot_sync(0xFFFFFFFFu, want_node);
         if (tmask && (nmask == 0u || __popc(tmask) >= TRACE_TRI_MIN)) {
-            if (want_tri) lane_tri_step(L, bvh, cnt);
+            if (want_tri) {
+                lane_tri_step(L, bvh, cnt);
+#if TRACE_TRI_PER_STEP > 1
+#pragma unroll 1
+                for (int k = 1; k < TRACE_TRI_PER_STEP && L.tg.y; k++) lane_tri_step(L, bvh, cnt);
+#endif
+            }
         } else if (nmask) {
             if (want_node) lane_node_step(L, bvh, S, spill, cnt);
         }

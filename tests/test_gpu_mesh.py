@@ -184,6 +184,62 @@ def test_render_260k_config2_reduced_resolution(gpu_ctx, oracle, sky_inputs, blu
     assert p >= 50.0, f"PSNR {p:.1f} dB"
 
 
+def test_ray_sort_does_not_change_the_image(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """Row n5: binning the bounce queues by direction octant reorders work only; every pixel owns its path, so the
+    accumulator must be bit-identical with and without the sort stage."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h = 192, 128
+    cam = camera_for(oracle, view, w, h)
+    pc, scn = oracle.constants(cam, frame=5)
+    setup_sky(gpu_ctx, oracle, atmo, cam.position[:])
+    gpu_ctx.upload_blue_noise(blue_noise)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    out = []
+    for sort in (0, 1):
+        gpu_ctx.set_option("sort_rays", sort)
+        gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+        gpu_ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 3, 3)
+        out.append((gpu_ctx.readback(capi.BUF_ACCUM).copy(), int(gpu_ctx.stats().secondary_rays)))
+    assert out[0][1] == out[1][1] and out[0][1] > 0
+    assert np.array_equal(out[0][0], out[1][0])
+    # the flag on the call does the same as the option
+    gpu_ctx.set_option("sort_rays", 0)
+    gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+    gpu_ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 3, 3, capi.SECONDARY_SORT_RAYS)
+    assert np.array_equal(gpu_ctx.readback(capi.BUF_ACCUM), out[0][0])
+
+
+def test_async_readback_matches_blocking(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """Pipelined framebuffer readback (double-buffered LDR): frame f's async copy equals its blocking readback even
+    when frame f+1 has been issued in between."""
+    import torch
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.cornell()
+    w, h = 160, 96
+    cam = camera_for(oracle, view, w, h)
+    setup_sky(gpu_ctx, oracle, atmo, cam.position[:])
+    gpu_ctx.upload_blue_noise(blue_noise)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    bufs = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    blocking = []
+    for f in (1, 2, 3):
+        pc, scn = oracle.constants(cam, frame=f)
+        gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+        gpu_ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 1, 2)
+        gpu_ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+        gpu_ctx.readback_async(capi.BUF_LDR, C.c_void_p(bufs[f & 1].data_ptr()), bufs[f & 1].numel())
+        gpu_ctx.readback_wait(1)
+        if f > 1:  # frame f-1 has landed while frame f may still be copying
+            assert np.array_equal(bufs[(f - 1) & 1].numpy(), blocking[-1])
+        blocking.append(gpu_ctx.readback(capi.BUF_LDR).copy())
+    gpu_ctx.readback_wait(0)
+    assert np.array_equal(bufs[3 & 1].numpy(), blocking[-1])
+    assert not np.array_equal(blocking[0], blocking[1])
+
+
 def test_progressive_accumulation(gpu_ctx, oracle, sky_inputs, blue_noise):
     """Row n7: frames f = 1..3 with seeds (f<<1)|1 accumulate; equals the oracle's accumulated sum."""
     atmo = sky_inputs[0]
