@@ -148,8 +148,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t_total / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl, "note": "CPU oracle (port of the reference's GLSL path + binary BVH); the reference's "
-                       "Vulkan renderer cannot run here (no lavapipe/glslc, MSVC-only host)"},
+            "config": {"workload": wl, "resolution": [w, h], "spp": spp, "bounces": bounces,
+                       "sampling": "PCG + blue-noise Cranley-Patterson rotation", "tonemap": "amd",
+                       "note": "CPU oracle (port of the reference's GLSL path + binary BVH) on all host threads; the reference's "
+                               "Vulkan renderer cannot run here (no lavapipe/glslc, MSVC-only host)"},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
