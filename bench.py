@@ -319,6 +319,7 @@ def run_ours(args):
                        "l2": "flushed between steps (256 MiB memset)", "bvh_bytes": int(build_stats.bvh_bytes),
                        "wide_nodes": int(build_stats.num_wide_nodes), "bvh_build_ms": build_stats.ms_build, "builder": args.builder, "sort_rays": bool(args.sort_rays),
                        "stack_overflows": int(ctx.stats().stack_overflows),
+                       "sah_node_cost": build_stats.sah_node_cost, "sah_tri_cost": build_stats.sah_tri_cost,
                        "parallelism": "1 GPU" if world == 1 else f"sample sets over {world} GPUs, replicated BVH, NCCL reduce of the fp32 accumulator"},
             "clocks": clocks,
             "e2e": {"value": e2e_rays_all / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",

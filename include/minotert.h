@@ -123,6 +123,8 @@ typedef struct {
     uint32_t trace_launches;  /* ... and their number (CUDA event pairs, at most 4096 per reset) */
     uint32_t _reserved;
     uint64_t total_rays;      /* primary + secondary rays traced since mrt_stats_reset (device-side running sum) */
+    float sah_node_cost;      /* surface-area heuristic of the wide BVH: expected node steps ... */
+    float sah_tri_cost;       /* ... and triangle tests of a random ray that hits the root box */
 } mrt_stats;
 
 /* ---- lifetime ---- */

@@ -50,7 +50,7 @@ class Stats(C.Structure):
                 ("ms_build", C.c_float), ("ms_sky", C.c_float), ("kernel_launches", C.c_uint32),
                 ("stack_overflows", C.c_uint32), ("num_triangles", C.c_uint32), ("num_wide_nodes", C.c_uint32),
                 ("bvh_bytes", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
-                ("trace_launches", C.c_uint32), ("_reserved", C.c_uint32), ("total_rays", C.c_uint64)]
+                ("trace_launches", C.c_uint32), ("_reserved", C.c_uint32), ("total_rays", C.c_uint64), ("sah_node_cost", C.c_float), ("sah_tri_cost", C.c_float)]
 
 
 EXPORTS = [

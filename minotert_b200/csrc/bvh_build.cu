@@ -496,6 +496,44 @@ k_emit_nodes(BinTree T, uint32_t num_nodes, const int32_t* __restrict__ slot_nod
     nodes[w] = N;
 }
 
+// SAH cost of the wide tree (quality metric reported in mrt_stats.sah_cost): sum over wide nodes of
+// area(node) / area(root) * 1 (one node step) + sum over leaf slots of area(slot box) / area(root) * ntris.
+__global__ void __launch_bounds__(256) k_sah_cost(const WideNode* __restrict__ nodes, uint32_t num_nodes, float* __restrict__ out) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    float node_cost = 0.0f, tri_cost = 0.0f;
+    if (w < num_nodes) {
+        const uint4 n0 = nodes[w].w[0], n1 = nodes[w].w[1], n2 = nodes[w].w[2], n3 = nodes[w].w[3], n4 = nodes[w].w[4];
+        float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
+              sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
+        unsigned imask = n0.w >> 24, leafmask = n1.z;
+        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+        for (int s = 0; s < 8; s++) {
+            unsigned sh = 8 * (s & 3);
+            float qlx = (float)(((s < 4 ? n2.x : n2.y) >> sh) & 0xFF), qly = (float)(((s < 4 ? n2.z : n2.w) >> sh) & 0xFF);
+            float qlz = (float)(((s < 4 ? n3.x : n3.y) >> sh) & 0xFF), qhx = (float)(((s < 4 ? n3.z : n3.w) >> sh) & 0xFF);
+            float qhy = (float)(((s < 4 ? n4.x : n4.y) >> sh) & 0xFF), qhz = (float)(((s < 4 ? n4.z : n4.w) >> sh) & 0xFF);
+            if (qlx > qhx) continue;  // empty slot
+            float dx = (qhx - qlx) * sx, dy = (qhy - qly) * sy, dz = (qhz - qlz) * sz;
+            float area = dx * dy + dy * dz + dz * dx;
+            lo[0] = fminf(lo[0], qlx * sx); hi[0] = fmaxf(hi[0], qhx * sx);
+            lo[1] = fminf(lo[1], qly * sy); hi[1] = fmaxf(hi[1], qhy * sy);
+            lo[2] = fminf(lo[2], qlz * sz); hi[2] = fmaxf(hi[2], qhz * sz);
+            if (!(imask & (1u << s))) tri_cost += area * (float)__popc((leafmask >> (3 * s)) & 7u);
+        }
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        node_cost = dx * dy + dy * dz + dz * dx;
+        if (w == 0) out[2] = node_cost;  // root area
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        node_cost += __shfl_down_sync(0xFFFFFFFFu, node_cost, off);
+        tri_cost += __shfl_down_sync(0xFFFFFFFFu, tri_cost, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], node_cost);
+        atomicAdd(&out[1], tri_cost);
+    }
+}
+
 __global__ void k_last_total(const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt, uint32_t last, uint32_t* out) {
     out[0] = off[last] + cnt[last];
 }
@@ -682,6 +720,17 @@ int bvh_build_full(mrt_context* ctx) {
     ctx->stats.num_triangles = n;
     ctx->stats.num_wide_nodes = ctx->num_nodes;
     ctx->stats.bvh_bytes = (uint64_t)ctx->num_nodes * sizeof(WideNode) + (uint64_t)n * 48u;
+    {
+        float* sah = reinterpret_cast<float*>(ctx->counters.p + 12);
+        float h[3] = {0, 0, 0};
+        cudaMemsetAsync(sah, 0, 3 * sizeof(float), ctx->stream);
+        k_sah_cost<<<div_up(ctx->num_nodes, 256), 256, 0, ctx->stream>>>(ctx->nodes.p, ctx->num_nodes, sah);
+        MRT_LAUNCHED(ctx);
+        MRT_CUDA(ctx, cudaMemcpyAsync(h, sah, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats.sah_node_cost = h[2] > 0.0f ? h[0] / h[2] : 0.0f;
+        ctx->stats.sah_tri_cost = h[2] > 0.0f ? h[1] / h[2] : 0.0f;
+    }
     ctx->bvh_valid = true;
     return MRT_OK;
 }

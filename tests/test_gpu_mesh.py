@@ -317,3 +317,63 @@ def test_refit_matches_full_rebuild(gpu_ctx, oracle):
     ids_full, t_full = gpu_ctx.trace_rays(o, d)
     assert np.array_equal(ids_refit, ids_bf) and np.array_equal(t_refit, t_bf)
     assert np.array_equal(ids_full, ids_bf) and np.array_equal(t_full, t_bf)
+
+
+def test_config2_full_size_properties(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """BASELINE config 2 at FULL size (260 864 triangles, 1920x1080, 1 spp, 2 bounces), checked through
+    size-independent properties: (a) primary visibility ids equal GPU brute force and the oracle's brute force on
+    sampled pixels; (b) the image is independent of the hierarchy builder (LBVH vs PLOC: both are exact
+    closest-hit structures) and of the ray-sort stage; (c) rendering the same frame twice is bit-identical;
+    (d) accumulating two frames equals the sum of the two frames rendered separately."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.hall_260k()
+    w, h = 1920, 1080
+    cam = camera_for(oracle, view, w, h)
+    setup_sky(gpu_ctx, oracle, atmo, cam.position[:])
+    gpu_ctx.upload_blue_noise(blue_noise)
+
+    def render(frame, flags=0):
+        pc, scn = oracle.constants(cam, frame=frame)
+        gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+        gpu_ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 1, 2, flags)
+        return gpu_ctx.readback(capi.BUF_ACCUM).copy()
+
+    images = {}
+    for builder in (0, 1):
+        gpu_ctx.set_option("builder", builder)
+        gpu_ctx.upload_mesh(pos, idx, alb)
+        gpu_ctx.build()
+        images[builder] = render(1)
+        assert gpu_ctx.stats().stack_overflows == 0
+    assert np.array_equal(images[0], images[1]), "image depends on the BVH builder"
+    vis = gpu_ctx.readback(capi.BUF_VISIBILITY)
+    t = gpu_ctx.readback(capi.BUF_HIT_T)
+    # (a) sampled pixels against brute force
+    rng = np.random.default_rng(2)
+    xs, ys = rng.integers(0, w, 3000), rng.integers(0, h, 3000)
+    pc, _ = oracle.constants(cam, frame=1)
+    o = np.zeros((3000, 3), np.float32)
+    d = np.zeros((3000, 3), np.float32)
+    oo, dd = (C.c_float * 3)(), (C.c_float * 3)()
+    for k in range(3000):
+        oracle.lib().orc_ray_gen(C.byref(pc.invView), C.byref(pc.invProjection), int(xs[k]), int(ys[k]), w, h, oo, dd)
+        o[k], d[k] = oo[:], dd[:]
+    ids_bf, t_bf = gpu_ctx.trace_rays(o, d, brute_force=True)
+    assert np.array_equal(vis[ys, xs], ids_bf), "primary visibility differs from brute force at full size"
+    assert np.array_equal(t[ys, xs], t_bf)
+    osc = oracle.Scene(pos, idx, alb)
+    for k in range(0, 3000, 150):
+        i, tt, _, _ = osc.closest_hit(o[k], d[k], use_bvh=False)
+        assert i == ids_bf[k] and (i == oracle.NONE_ID or np.float32(tt) == t_bf[k])
+    # (b) sort stage, (c) determinism
+    assert np.array_equal(render(1, capi.SECONDARY_SORT_RAYS), images[1])
+    assert np.array_equal(render(1), images[1])
+    # (d) linearity of the accumulator
+    f2 = render(2)
+    render(1)
+    pc, scn = oracle.constants(cam, frame=2)
+    gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+    gpu_ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 1, 2, capi.SECONDARY_ACCUMULATE)
+    both = gpu_ctx.readback(capi.BUF_ACCUM)
+    assert np.array_equal(both, images[1] + f2)
+    assert np.all(both[..., 3] == 2.0)
