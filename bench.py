@@ -198,6 +198,7 @@ def run_ours(args):
     cam = host.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
     r.draw(cam)  # builds the atmosphere LUTs + sky view, allocates every frame buffer
     ctx.sync()
+    ctx.build()  # second, warm build: ms_build without the first-launch module loading
     build_stats = ctx.stats()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")

@@ -3,26 +3,28 @@
 // Execution model for incoherent rays (bounce waves): persistent warps.  Every lane owns one ray; the
 // warp runs a warp-synchronous state machine whose step is chosen by ballot:
 //     refill  : lanes whose ray finished take the next ray of the warp's chunk (one global atomic per
-//               TRACE_CHUNK rays), once enough lanes are idle -- bounce rays finish at very different
-//               times, refilling keeps the warp populated;
+//               TRACE_CHUNK rays) once TRACE_REFILL_MIN lanes are idle -- bounce rays finish at very
+//               different times, refilling keeps the warp populated;
 //     node    : lanes with a pending node fetch it (five 128-bit ld.global.nc) and test its 8 children;
-//     triangle: lanes with pending leaf triangles test ONE triangle; triangle steps are postponed until
-//               TRACE_TRI_MIN lanes have one (or no lane has node work), so they run batched.
+//     triangle: lanes with pending leaf triangles test up to TRACE_TRI_PER_STEP of them; triangle steps wait
+//               until TRACE_TRI_MIN lanes have one (or no lane has node work), so they run batched.  A lane may
+//               hold ONE postponed triangle group and keep taking node steps meanwhile (TRACE_POSTPONE).
 // Coherent rays (the primary pass) use the plain per-lane loop trace_coherent().
-// History (profiles/): v0 "one node then its triangles per lane" ran bounce rays at 7.8 of 32 active
-// lanes; the state machine reached ~19; v2 (this file) halves the instructions of a node step.
+// History (profiles/r1_results.md): v0 "one node then its triangles per lane" ran bounce rays at 7.8 of 32
+// active lanes; the state machine reached ~19; the node encoding below halved the instructions of a node step.
 //
-// Node step, ~260 SASS instructions for 8 children:
-//   * decode + slab plane in ONE FMA: PRMT builds the float 2^15 + q from the quantised byte
-//     (0x47000000 | q << 8), and t = fma(2^15 + q, step/d, (origin - o)/d - 2^15 * step/d).  The constant
-//     term carries an error of at most step/512, which the builder's outward rounding (1/128 step of
-//     slack, bvh_build.cu) covers; near planes use 1/d * (1 - 2^-21), far planes 1/d * (1 + 2^-21), so
-//     fp32 rounding can never cull a box the exact ray touches;
-//   * hit mask by sign funnel: SHF.L.W shifts the sign bit of (tmax - tmin) of each child into an 8-bit
-//     miss mask, no predicates or branches;
-//   * inner hits are permuted by three delta swaps into "slot ^ inverse ray octant" order so that the
-//     highest set bit is the child that lies first along the ray; leaf hits are expanded to the node's
-//     fixed 3-bits-per-slot triangle mask.
+// Node step, ~215 SASS instructions, 18 per child:
+//   * decode + slab plane in ONE FMA: far planes -- PRMT builds the float 2^15 + q from the quantised byte
+//     (0x47000000 | q << 8); near planes -- IDP.4A builds 2^15 + q/2 (0x47000000 + 128 q) so that the 48
+//     decodes split between the ALU pipe and the FMA-heavy pipe; t = fma(decoded, step/d, (origin - o)/d -
+//     2^15 * step/d).  The constant term carries an error of at most step/256, which the builder's outward
+//     rounding (slack in bvh_build.cu k_emit_nodes) covers; near planes use 1/d * (1 - 2^-21), far planes
+//     1/d * (1 + 2^-21), so fp32 rounding can never cull a box the exact ray touches;
+//   * hit <=> tmin <= tmax && tmin <= tlimit && tmax >= 0: the three sign bits are ORed (one LOP3) and
+//     funnel-shifted (SHF.L.W) into an 8-bit miss mask -- no predicates, no branches;
+//   * inner hits are permuted into "slot ^ inverse ray octant" order by a 2 KB shared-memory table so that
+//     the highest set bit is the child that lies first along the ray; leaf hits are expanded to the node's
+//     fixed 3-bits-per-slot triangle mask by a second table (the LSU is idle here, the ALU pipe is not).
 // The stack holds (child_base, ordered inner hits << 24 | imask) groups: the first TRACE_SM_STACK entries
 // per lane live in shared memory (column layout, conflict-free), deeper ones spill to local memory.
 //
@@ -50,13 +52,16 @@
 #define TRACE_REFILL_MIN 8   // idle lanes that trigger a refill
 #endif
 #ifndef TRACE_TRI_MIN
-#define TRACE_TRI_MIN 8      // lanes with a pending triangle that trigger a triangle step
+#define TRACE_TRI_MIN 12     // lanes with pending triangles that trigger a triangle step
 #endif
 #ifndef TRACE_TRI_PER_STEP
 #define TRACE_TRI_PER_STEP 2 // triangles a lane may test in one triangle step (1: lanes with leftovers idle; 3+: long steps)
 #endif
 #ifndef TRACE_PREFETCH
 #define TRACE_PREFETCH 0     // prefetch the next child node to L1 at the end of a node step (A/B measured)
+#endif
+#ifndef TRACE_POSTPONE
+#define TRACE_POSTPONE 1     // 1: a lane of the persistent loop may hold one postponed triangle group and keep taking node steps
 #endif
 #ifndef TRACE_DP4A_NEAR
 #define TRACE_DP4A_NEAR 1    // decode near planes with IDP.4A (FMA-heavy pipe), far planes with PRMT (ALU pipe)
@@ -137,6 +142,8 @@ struct LaneState {
     uint2 ng;          // pending node group: child_base, ordered inner hits << 24 | imask
     uint2 tg;          // pending triangle group: tri_base, hit triangle bits
     unsigned tgmask;   // leafmask24 of the node tg came from
+    uint2 tg2;         // postponed (older) triangle group (persistent loop with TRACE_POSTPONE only)
+    unsigned tg2mask;
     int sp;
     TraceHit hit;
     float tlimit;      // hit.t * (1 + 2^-21)
@@ -158,6 +165,8 @@ MRT_D void lane_begin(LaneState& L, float3 o, float3 d) {
     L.ng = make_uint2(0u, 0x80000000u);  // root "group": node 0, one pending inner hit
     L.tg = make_uint2(0u, 0u);
     L.tgmask = 0u;
+    L.tg2 = make_uint2(0u, 0u);
+    L.tg2mask = 0u;
     L.sp = 0;
     L.hit.t = 3.0e38f; L.hit.tri = MRT_MISS_ID; L.hit.prim = MRT_MISS_ID;
     L.tlimit = 3.0e38f;
@@ -208,8 +217,11 @@ MRT_D void trace_shared_init(TraceShared& S) {
 }
 
 // One node step: take the nearest pending child of L.ng, fetch it, test its 8 children.
+// POSTPONE: the lane may arrive with untested triangles in L.tg; they move to the (free) postponed slot.
+template <bool POSTPONE>
 MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2* spill, TraceCounters& cnt) {
     uint2* const sm = &S.stack[0][threadIdx.x];
+    if (POSTPONE && L.tg.y) { L.tg2 = L.tg; L.tg2mask = L.tgmask; }
     const unsigned bit = 31u - __clz(L.ng.y);
     L.ng.y &= ~(1u << bit);
     if (L.ng.y & 0xFF000000u) {  // siblings remain: keep the group for later
@@ -293,10 +305,22 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2
 #endif
 }
 
+// One triangle of the lane's pending group (POSTPONE: of the older group first).
+template <bool POSTPONE>
 MRT_D void lane_tri_step(LaneState& L, const BvhDev& bvh, TraceCounters& cnt) {
-    const unsigned bit = __ffs(L.tg.y) - 1;
-    L.tg.y &= L.tg.y - 1;
-    const uint32_t tri = L.tg.x + __popc(L.tgmask & ((1u << bit) - 1u));
+    uint32_t tri;
+    if (POSTPONE) {
+        const bool old = L.tg2.y != 0u;
+        const unsigned bits = old ? L.tg2.y : L.tg.y;
+        const unsigned bit = __ffs(bits) - 1;
+        tri = (old ? L.tg2.x : L.tg.x) + __popc((old ? L.tg2mask : L.tgmask) & ((1u << bit) - 1u));
+        if (old) L.tg2.y = bits & (bits - 1);
+        else L.tg.y = bits & (bits - 1);
+    } else {
+        const unsigned bit = __ffs(L.tg.y) - 1;
+        L.tg.y &= L.tg.y - 1;
+        tri = L.tg.x + __popc(L.tgmask & ((1u << bit) - 1u));
+    }
     const float4* tp = bvh.tris + 3 * (size_t)tri;
     const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
     cnt.tris++;
@@ -320,7 +344,7 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
     const uint32_t total = job.count();
     uint2 spill[TRACE_LOCAL_STACK];
     LaneState L;
-    L.ng = L.tg = make_uint2(0u, 0u);
+    L.ng = L.tg = L.tg2 = make_uint2(0u, 0u);
     L.sp = 0;
     bool have_ray = false;
     uint32_t ray_index = 0;
@@ -356,6 +380,22 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
         if (exhausted && __ballot_sync(0xFFFFFFFFu, have_ray) == 0u) break;
 
         // ---- lanes with a ray but no pending work: pop, or finish the ray
+#if TRACE_POSTPONE
+        // a lane with a free postponed slot keeps walking nodes (pops included); it finishes only with no work left
+        if (have_ray && !(L.ng.y & 0xFF000000u) && !(L.tg.y && L.tg2.y)) {
+            if (L.sp == 0) {
+                if (!(L.tg.y | L.tg2.y)) {
+                    job.store(ray_index, L.hit);
+                    have_ray = false;
+                }
+            } else {
+                L.sp--;
+                L.ng = L.sp < TRACE_SM_STACK ? sm[L.sp * TRACE_BLOCK] : spill[L.sp - TRACE_SM_STACK];
+            }
+        }
+        const bool want_tri = have_ray && (L.tg.y | L.tg2.y) != 0u;
+        const bool want_node = have_ray && !(L.tg.y && L.tg2.y) && (L.ng.y & 0xFF000000u);
+#else
         if (have_ray && !(L.ng.y & 0xFF000000u) && L.tg.y == 0u) {
             if (L.sp == 0) {
                 job.store(ray_index, L.hit);
@@ -367,18 +407,20 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
         }
         const bool want_tri = have_ray && L.tg.y != 0u;
         const bool want_node = have_ray && !want_tri && (L.ng.y & 0xFF000000u);
+#endif
         const unsigned tmask = __ballot_sync(0xFFFFFFFFu, want_tri);
         const unsigned nmask = __ballot_sync(0xFFFFFFFFu, want_node);
         if (tmask && (nmask == 0u || __popc(tmask) >= TRACE_TRI_MIN)) {
             if (want_tri) {
-                lane_tri_step(L, bvh, cnt);
+                constexpr bool PP = TRACE_POSTPONE != 0;
+                lane_tri_step<PP>(L, bvh, cnt);
 #if TRACE_TRI_PER_STEP > 1
 #pragma unroll 1
-                for (int k = 1; k < TRACE_TRI_PER_STEP && L.tg.y; k++) lane_tri_step(L, bvh, cnt);
+                for (int k = 1; k < TRACE_TRI_PER_STEP && (L.tg.y | (PP ? L.tg2.y : 0u)); k++) lane_tri_step<PP>(L, bvh, cnt);
 #endif
             }
         } else if (nmask) {
-            if (want_node) lane_node_step(L, bvh, S, spill, cnt);
+            if (want_node) lane_node_step<TRACE_POSTPONE != 0>(L, bvh, S, spill, cnt);
         }
     }
 }
@@ -393,8 +435,8 @@ MRT_D TraceHit trace_coherent(const BvhDev& bvh, float3 o, float3 d, TraceShared
     lane_begin(L, o, d);
     if (bvh.num_nodes == 0) return L.hit;
     for (;;) {
-        if (L.ng.y & 0xFF000000u) lane_node_step(L, bvh, S, spill, cnt);
-        while (L.tg.y) lane_tri_step(L, bvh, cnt);
+        if (L.ng.y & 0xFF000000u) lane_node_step<false>(L, bvh, S, spill, cnt);
+        while (L.tg.y) lane_tri_step<false>(L, bvh, cnt);
         if (!(L.ng.y & 0xFF000000u)) {
             if (L.sp == 0) break;
             L.sp--;
