@@ -135,7 +135,16 @@ int mrt_create(int device, mrt_context** out);
 void mrt_destroy(mrt_context* ctx);
 /* Sticky message of the last failure on this context (ctx may be NULL: last mrt_create error). */
 const char* mrt_last_error(const mrt_context* ctx);
-/* name: "count_visits" (0/1), "sort_rays" (0/1), "persistent" (0/1), "stack_sm" ... */
+/* Tuning / instrumentation switches (unknown names fail with MRT_ERR_INVALID):
+ *   "count_visits" 0/1        count node visits and triangle tests (mrt_stats.node_visits / tri_tests)
+ *   "trace_timing" 0/1        CUDA event pair around every bounce-wave traversal launch (default 1)
+ *   "sort_rays" 0/1           octant sort of every bounce wave (default 0; measured slower)
+ *   "persistent" 0/1          persistent-warp state machine for bounce waves (default 1)
+ *   "persistent_primary" 0/1  ... and for primary rays (default 0: coherent per-lane loop)
+ *   "trace_ctas_per_sm" n     cap the persistent traversal grid at n CTAs per SM (0 = as many as fit), for
+ *                             contexts that share a GPU
+ *   "builder" 0/1             hierarchy builder: 0 Karras LBVH, 1 PLOC (default); invalidates the BVH
+ *   "ploc_radius" 1..32       PLOC search radius (default 6); invalidates the BVH */
 int mrt_set_option(mrt_context* ctx, const char* name, int64_t value);
 
 /* ---- inputs ---- */

@@ -66,6 +66,7 @@ struct mrt_context {
     int opt_persistent = 1;
     int opt_persistent_primary = 0;  // run primary rays through the persistent state machine too (A/B switch)
     int opt_trace_timing = 1;        // CUDA event pair around every bounce-wave traversal launch (mrt_stats.ms_trace)
+    int opt_trace_ctas_per_sm = 0;   // 0: as many as fit; n: persistent traversal grids use n CTAs per SM (co-running contexts)
     int opt_builder = 1;             // 0: Karras LBVH hierarchy, 1: PLOC (locally-ordered clustering) hierarchy
     int opt_ploc_radius = 6;         // +-positions searched for the nearest cluster (measured best of 2..32 on config 2)
 

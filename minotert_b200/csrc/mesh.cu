@@ -376,7 +376,7 @@ unsigned trace_grid(mrt_context* ctx, size_t max_rays) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<QueueJob>, TRACE_BLOCK, 0);
         if (occ <= 0) occ = 4;
     }
-    size_t want = (size_t)sms * occ;
+    size_t want = (size_t)sms * (ctx->opt_trace_ctas_per_sm > 0 && ctx->opt_trace_ctas_per_sm < occ ? ctx->opt_trace_ctas_per_sm : occ);
     size_t need = (max_rays + 31) / 32 / (TRACE_BLOCK / 32) + 1;  // no more CTAs than there are warps of work
     return (unsigned)(need < want ? need : want);
 }
