@@ -8,9 +8,11 @@ namespace {
 
 struct TonemapParams { int mode; float exposure; float p[6]; float amd_b, amd_c; };
 
-// x^e for x >= 0 through the accurate exp2f/log2f (a few ulp; the general powf costs ~3x the instructions and
-// made this kernel SFU/ALU-bound at 88 us per 1080p frame).  0^e = 0 for e > 0, 1^e = 1.
-MRT_D float pw(float x, float e) { return exp2f(e * log2f(x)); }
+// x^e for x >= 0 as ex2(e * lg2(x)) on the SFU -- what GLSL pow() compiles to on the reference's GPU path
+// (Vulkan precision: inherited from exp2/log2).  The general powf costs ~15x the instructions and made this
+// kernel ALU-bound at 88 us per 1080p frame; the 8-bit result differs from the libm oracle by at most one
+// code value (tests/test_gpu_spheres.py::test_tonemap_operators).  0^e = 0 for e > 0, 1^e = 1.
+MRT_D float pw(float x, float e) { return __powf(x, e); }
 
 MRT_D float srgb1(float c) { return c < 0.0031308f ? 12.92f * c : 1.055f * pw(c, 1.0f / 2.4f) - 0.055f; }
 MRT_D float mixf(float x, float y, float a) { return x * (1.0f - a) + y * a; }
