@@ -192,6 +192,9 @@ def run_ours(args):
     r.context().set_option("ploc_radius", args.ploc_radius)
     r.context().set_option("sort_rays", 1 if args.sort_rays else 0)
     r.context().set_option("trace_timing", 0 if args.no_trace_timing else 1)
+    for kv in args.opt:  # A/B experiments: any mrt_set_option switch
+        name, value = kv.split("=")
+        r.context().set_option(name, int(value))
     r.set_mesh(pos, idx, alb)
     r.configure(samples=spp, bounces=bounces, accumulate=False, tonemap="amd", exposure=1.0)
     ctx = r.context()
@@ -368,6 +371,7 @@ def main():
     ap.add_argument("--ploc-radius", type=int, default=6)
     ap.add_argument("--no-trace-timing", action="store_true", help="A/B: drop the per-launch CUDA events (roofline fields become 0)")
     ap.add_argument("--sort-rays", action="store_true", help="bin each bounce's ray queue by direction octant before tracing")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="extra mrt_set_option switches (A/B experiments)")
     ap.add_argument("--builder", default="ploc", choices=["ploc", "lbvh"], help="binary hierarchy under the 8-wide BVH")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
