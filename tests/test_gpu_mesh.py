@@ -377,3 +377,89 @@ def test_config2_full_size_properties(gpu_ctx, oracle, sky_inputs, blue_noise):
     both = gpu_ctx.readback(capi.BUF_ACCUM)
     assert np.array_equal(both, images[1] + f2)
     assert np.all(both[..., 3] == 2.0)
+
+
+@pytest.mark.parametrize("builder", [0, 1], ids=["lbvh", "ploc"])
+def test_mixed_scale_soup_far_from_origin(gpu_ctx, oracle, builder):
+    """Conservativeness of the quantised boxes under stress: 20 000 triangles whose sizes span six decades,
+    centred 10 000 units from the origin (few mantissa bits left for the node grids), rays from inside and
+    outside the cloud.  BVH result == GPU brute force (ids and t bit-exact), sampled rays == oracle brute force."""
+    rng = np.random.default_rng(11 + builder)
+    n = 20000
+    centre = np.array([1.0e4, -2.0e4, 5.0e3], np.float32)
+    c = centre + rng.uniform(-50, 50, (n, 3)).astype(np.float32)
+    size = (10.0 ** rng.uniform(-4, 2, (n, 1))).astype(np.float32)
+    pos = (c[:, None, :] + size[:, None, :] * rng.normal(size=(n, 3, 3)).astype(np.float32)).reshape(-1, 3).astype(np.float32)
+    idx = np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)
+    alb = np.full((n, 3), 0.5, np.float32)
+    gpu_ctx.set_option("builder", builder)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    m = 30000
+    o = (centre + rng.uniform(-80, 80, (m, 3))).astype(np.float32)
+    d = rng.normal(size=(m, 3)).astype(np.float32)
+    d[: m // 10, 0] = 0.0          # axis-parallel components
+    d[m // 10: m // 5, 1:] = 0.0   # axis-aligned rays
+    d[m // 5] = (1.0, 0.0, 0.0)
+    ids, t = gpu_ctx.trace_rays(o, d)
+    ids_bf, t_bf = gpu_ctx.trace_rays(o, d, brute_force=True)
+    assert gpu_ctx.stats().stack_overflows == 0
+    assert np.array_equal(ids, ids_bf)
+    assert np.array_equal(t, t_bf)
+    assert (ids != capi.MISS_ID).mean() > 0.3
+    osc = oracle.Scene(pos, idx, alb)
+    for k in range(0, m, 500):
+        i, tt, _, _ = osc.closest_hit(o[k], d[k], use_bvh=False)
+        assert i == ids[k] and (i == oracle.NONE_ID or np.float32(tt) == t[k])
+    gpu_ctx.set_option("builder", 1)
+
+
+def _icosphere(level):
+    g = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [(-1, g, 0), (1, g, 0), (-1, -g, 0), (1, -g, 0), (0, -1, g), (0, 1, g), (0, -1, -g), (0, 1, -g),
+         (g, 0, -1), (g, 0, 1), (-g, 0, -1), (-g, 0, 1)]
+    v = [np.array(p, np.float64) / np.linalg.norm(p) for p in v]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+         (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    for _ in range(level):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                p = v[a] + v[b]
+                v.append(p / np.linalg.norm(p))
+                cache[key] = len(v) - 1
+            return cache[key]
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return np.array(v, np.float32), np.array(f, np.uint32)
+
+
+def test_watertight_closed_mesh(gpu_ctx, oracle):
+    """A closed icosphere (20 480 triangles, shared vertices) seen from inside: rays aimed exactly at every vertex and
+    every edge midpoint, plus random ones, must all hit something -- no ray leaks through a shared edge or vertex --
+    and agree with brute force."""
+    pos, idx = _icosphere(5)
+    pos = (pos * np.float32(3.0) + np.array([0.3, -0.2, 0.1], np.float32)).astype(np.float32)
+    alb = np.full((idx.shape[0], 3), 0.5, np.float32)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    e = np.concatenate([idx[:, [0, 1]], idx[:, [1, 2]], idx[:, [2, 0]]])
+    mids = (0.5 * (pos[e[:, 0]].astype(np.float64) + pos[e[:, 1]].astype(np.float64))).astype(np.float32)
+    rng = np.random.default_rng(5)
+    for origin in ([0.3, -0.2, 0.1], [1.1, 0.4, -0.9], [0.0, 0.0, 0.0]):
+        org = np.array(origin, np.float32)
+        targets = np.concatenate([pos, mids, org + rng.normal(size=(20000, 3)).astype(np.float32)])
+        d = (targets - org).astype(np.float32)
+        o = np.tile(org, (d.shape[0], 1))
+        ids, t = gpu_ctx.trace_rays(o, d)
+        assert (ids != capi.MISS_ID).all(), f"{(ids == capi.MISS_ID).sum()} rays leaked out of a closed mesh"
+        ids_bf, t_bf = gpu_ctx.trace_rays(o, d, brute_force=True)
+        assert np.array_equal(ids, ids_bf) and np.array_equal(t, t_bf)
+    osc = oracle.Scene(pos, idx, alb)
+    for k in range(0, pos.shape[0], 97):   # vertex rays: up to six triangles tie, the lowest primitive id wins
+        i, tt, _, _ = osc.closest_hit(o[k], d[k], use_bvh=False)
+        assert i == ids[k] and np.float32(tt) == t[k]
