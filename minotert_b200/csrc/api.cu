@@ -62,7 +62,13 @@ int buffer_info(mrt_context* ctx, int id, void** p, size_t* bytes) {
     case MRT_BUF_LDR: if (!ctx->have_ldr) break; *p = ctx->ldr_buf[ctx->ldr_cur].p; *bytes = n * 4; return MRT_OK;
     case MRT_BUF_TRANSMITTANCE: if (!ctx->have_atmo) break; *p = ctx->trans16.p; *bytes = (size_t)MRT_TRANS_W * MRT_TRANS_H * 8; return MRT_OK;
     case MRT_BUF_MULTISCATTERING: if (!ctx->have_atmo) break; *p = ctx->multi16.p; *bytes = (size_t)MRT_MULTI_W * MRT_MULTI_H * 8; return MRT_OK;
-    case MRT_BUF_SKY_VIEW: if (!ctx->have_view) break; *p = ctx->view_packed.p; *bytes = (size_t)MRT_VIEW_W * MRT_VIEW_H * 4; return MRT_OK;
+    case MRT_BUF_SKY_VIEW:
+        if (!ctx->have_view) break;
+        if (ctx->sky_pending) {  // still being generated on the side stream: order the main stream after it
+            cudaStreamWaitEvent(ctx->stream, ctx->sky_ready, 0);
+            ctx->sky_pending = false;
+        }
+        *p = ctx->view_packed.p; *bytes = (size_t)MRT_VIEW_W * MRT_VIEW_H * 4; return MRT_OK;
     case MRT_BUF_HIT_T: if (!ctx->have_gbuffer || ctx->scene_kind != 2) break; *p = ctx->hit_t.p; *bytes = n * 4; return MRT_OK;
     default: return mrt_fail(ctx, MRT_ERR_INVALID, "unknown buffer id %d", id);
     }
@@ -96,6 +102,9 @@ int mrt_create(int device, mrt_context** out) {
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->sky_ready, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ldr_ready, cudaEventDisableTiming);
     for (auto& ev : ctx->copy_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     *out = ctx;
@@ -128,6 +137,9 @@ void mrt_destroy(mrt_context* ctx) {
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->trace_ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+    if (ctx->sky_ready) cudaEventDestroy(ctx->sky_ready);
     if (ctx->ldr_ready) cudaEventDestroy(ctx->ldr_ready);
     for (auto& ev : ctx->copy_done) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
@@ -218,9 +230,18 @@ int mrt_scene_build(mrt_context* ctx, int build_mode) {
     return bvh_build_full(ctx);
 }
 
+// the main stream waits for a sky view still being generated on the side stream
+static void sky_join(mrt_context* ctx) {
+    if (ctx->sky_pending) {
+        cudaStreamWaitEvent(ctx->stream, ctx->sky_ready, 0);
+        ctx->sky_pending = false;
+    }
+}
+
 int mrt_atmosphere(mrt_context* ctx, const mrt_atmosphere_params* params) {
     MRT_ENTER(ctx);
     if (!params) return mrt_fail(ctx, MRT_ERR_INVALID, "atmosphere params is NULL");
+    sky_join(ctx);
     ctx->atmo = *params;
     cudaEventRecord(ctx->ev[0], ctx->stream);
     MRT_TRY(sky_gen_atmosphere(ctx));
@@ -234,7 +255,13 @@ int mrt_sky_view(mrt_context* ctx, const float probePos[3], const float sunDirec
     MRT_ENTER(ctx);
     if (!ctx->have_atmo) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_sky_view before mrt_atmosphere");
     if (!probePos || !sunDirection || !sunIlluminance) return mrt_fail(ctx, MRT_ERR_INVALID, "sky view: NULL argument");
+    // side stream: ordered after everything issued so far (atmosphere LUTs, the previous view's readers), then
+    // free to overlap whatever the caller issues next on the main stream until a reader joins
+    MRT_CUDA(ctx, cudaEventRecord(ctx->aux_fork, ctx->stream));
+    MRT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
     MRT_TRY(sky_gen_view(ctx, probePos, sunDirection, sunIlluminance));
+    MRT_CUDA(ctx, cudaEventRecord(ctx->sky_ready, ctx->aux_stream));
+    ctx->sky_pending = true;
     ctx->have_view = true;
     return MRT_OK;
 }
@@ -297,6 +324,7 @@ int mrt_secondary_rays(mrt_context* ctx, const mrt_secondary_constants* c, uint3
     if (!ctx->have_gbuffer) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays before primary rays");
     if (!ctx->have_atmo || !ctx->have_view) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: sky LUTs missing (mrt_atmosphere, mrt_sky_view)");
     if (!ctx->bn) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: blue noise texture missing");
+    sky_join(ctx);
     cudaEventRecord(ctx->ev[4], ctx->stream);
     int s = MRT_OK;
     if (ctx->npix) s = ctx->scene_kind == 1 ? spheres_secondary(ctx, c, spp, bounces, flags) : mesh_secondary(ctx, c, spp, bounces, flags);
@@ -377,6 +405,7 @@ int mrt_readback_wait(mrt_context* ctx, int frames_in_flight) {
 
 int mrt_sync(mrt_context* ctx) {
     MRT_ENTER(ctx);
+    sky_join(ctx);
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MRT_OK;
 }
@@ -393,6 +422,7 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
     if (!out) return MRT_ERR_INVALID;
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms;
+    if (ctx->have_atmo && cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->stats.ms_sky = ms;
     if (ctx->have_gbuffer && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.ms_primary = ms;
     if (ctx->have_accum && cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->stats.ms_secondary = ms;
     if (ctx->have_ldr && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->stats.ms_tonemap = ms;

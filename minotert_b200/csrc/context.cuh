@@ -141,6 +141,11 @@ struct mrt_context {
     // stats
     mrt_stats stats{};
     cudaEvent_t ev[8] = {nullptr};
+    // The sky view of a frame is generated on a side stream so that it overlaps the primary pass
+    // (Renderer::draw order: sky -> primary -> secondary); consumers join through sky_join().
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_fork = nullptr, sky_ready = nullptr;
+    bool sky_pending = false;
     std::vector<cudaEvent_t> trace_ev;  // begin/end pairs around each traversal launch of the last frame
     uint32_t trace_ev_used = 0;
 };

@@ -224,8 +224,11 @@ struct QueryJob {
 
 template <class Job>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
-k_trace(Job job, BvhDev bvh, uint32_t* work_counter, unsigned long long* counters, int count_visits) {
+k_trace(Job job, BvhDev bvh, uint32_t* work_counter, unsigned long long* counters, int count_visits,
+        unsigned long long* total_rays = nullptr, unsigned long long extra_rays = 0) {
     __shared__ TraceShared S;
+    // running ray total (mrt_stats.total_rays): this wave's rays (+ the frame's primary rays with its first wave)
+    if (total_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total_rays, (unsigned long long)job.count() + extra_rays);
     trace_shared_init(S);
     TraceCounters cnt{0, 0, 0};
     trace_persistent(bvh, job, work_counter, S, cnt);
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(128) k_trace_brute(const float* __restrict__ p
     ts[k] = h.prim != MRT_MISS_ID ? h.t : 0.0f;
 }
 
-// running ray total (mrt_stats.total_rays): primary pixels + every queue size of this frame
+// running ray total for frames without bounce waves (otherwise k_trace adds its wave): primary pixels only
 __global__ void k_sum_rays(const uint32_t* __restrict__ counts, uint32_t n, unsigned long long extra, unsigned long long* total) {
     unsigned long long s = 0;
     for (uint32_t i = threadIdx.x; i < n; i += 32) s += counts[i];
@@ -485,7 +488,8 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
             }
             QueueJob J{ctx->ray_o[q].p, ctx->ray_d[q].p, in_count, ctx->hits.p, sort ? ctx->sort_vals.p : nullptr};
             k_trace<QueueJob><<<tgrid, TRACE_BLOCK, 0, ctx->stream>>>(J, bvh, ctx->queue_counts.p + waves + 1 + wave,
-                                                                      ctx->visit_counters.p + 4, ctx->opt_count_visits);
+                                                                      ctx->visit_counters.p + 4, ctx->opt_count_visits,
+                                                                      ctx->total_rays.p, wave == 0 ? (unsigned long long)npix : 0ull);
             MRT_LAUNCHED(ctx);
             if (timed) {
                 cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used + 1], ctx->stream);
@@ -503,8 +507,8 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
             q ^= 1;
         }
     }
-    if (ctx->total_rays.p) {
-        k_sum_rays<<<1, 32, 0, ctx->stream>>>(ctx->queue_counts.p, waves + 1, (unsigned long long)npix, ctx->total_rays.p);
+    if (ctx->total_rays.p && waves == 0) {
+        k_sum_rays<<<1, 32, 0, ctx->stream>>>(ctx->queue_counts.p, 0, (unsigned long long)npix, ctx->total_rays.p);
         MRT_LAUNCHED(ctx);
     }
     return mrt_check_cuda(ctx, cudaGetLastError(), "mesh_secondary");

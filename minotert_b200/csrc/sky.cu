@@ -307,7 +307,7 @@ int sky_gen_view(mrt_context* ctx, const float probe[3], const float sunDir[3], 
     MRT_TRY(dev_reserve(ctx, ctx->view_f, (size_t)MRT_VIEW_W * MRT_VIEW_H));
     SkyLuts luts{ctx->trans_f.p, ctx->multi_f.p, nullptr};
     dim3 b(8, 8), g(div_up(MRT_VIEW_W, 8), div_up(MRT_VIEW_H, 8));
-    k_gen_view<<<g, b, 0, ctx->stream>>>(ctx->atmo, luts, f3(probe[0], probe[1], probe[2]),
+    k_gen_view<<<g, b, 0, ctx->aux_stream>>>(ctx->atmo, luts, f3(probe[0], probe[1], probe[2]),
                                          f3(sunDir[0], sunDir[1], sunDir[2]), f3(sunIll[0], sunIll[1], sunIll[2]),
                                          ctx->view_packed.p, ctx->view_f.p);
     MRT_LAUNCHED(ctx);
