@@ -88,7 +88,10 @@ struct PrimaryJob {
 
 // Primary rays are coherent: one thread per pixel, 8x4-pixel tile per warp, per-lane traversal loop
 // (trace_coherent).  Measured 2x faster than running them through the persistent state machine.
-__global__ void __launch_bounds__(TRACE_BLOCK)
+#ifndef PRIMARY_MIN_BLOCKS
+#define PRIMARY_MIN_BLOCKS 6  // register cap 85 (ptxas picks 80 instead of 72): measured best of 1, 4, 5, 6, 8, 9
+#endif
+__global__ void __launch_bounds__(TRACE_BLOCK, PRIMARY_MIN_BLOCKS)
 k_mesh_primary(PrimaryJob J, unsigned long long* counters, int count_visits) {
     __shared__ TraceShared S;
     trace_shared_init(S);
