@@ -21,7 +21,9 @@
 struct WideNode { uint4 w[5]; };
 static_assert(sizeof(WideNode) == 80, "wide node is 80 bytes");
 
-#define MRT_MAX_LEAF_TRIS 3
+#ifndef MRT_MAX_LEAF_TRIS
+#define MRT_MAX_LEAF_TRIS 2  // triangles per leaf slot (the node format allows 3): 2 measured best of 1, 2, 3
+#endif
 #define MRT_MAX_SPHERES 16
 
 struct BvhDev {
