@@ -140,6 +140,7 @@ const char* mrt_last_error(const mrt_context* ctx);
  *   "trace_timing" 0/1        CUDA event pair around every bounce-wave traversal launch (default 1)
  *   "sort_rays" 0/1           octant sort of every bounce wave (default 0; measured slower)
  *   "persistent" 0/1          persistent-warp state machine for bounce waves (default 1)
+ *   "fused_shade" 0/1         shade stage of a bounce wave inside its traversal launch (default 0; measured +-2 %)
  *   "persistent_primary" 0/1  ... and for primary rays (default 0: coherent per-lane loop)
  *   "trace_ctas_per_sm" n     cap the persistent traversal grid at n CTAs per SM (0 = as many as fit), for
  *                             contexts that share a GPU

@@ -156,6 +156,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "persistent")) ctx->opt_persistent = value != 0;
     else if (!strcmp(name, "persistent_primary")) ctx->opt_persistent_primary = value != 0;
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
+    else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;
     else if (!strcmp(name, "trace_ctas_per_sm")) ctx->opt_trace_ctas_per_sm = (int)(value > 32 ? 32 : value);
     else if (!strcmp(name, "builder")) { ctx->opt_builder = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "ploc_radius")) { ctx->opt_ploc_radius = (int)(value < 1 ? 1 : (value > 32 ? 32 : value)); ctx->bvh_valid = false; }

@@ -68,6 +68,7 @@ struct mrt_context {
     int opt_persistent = 1;
     int opt_persistent_primary = 0;  // run primary rays through the persistent state machine too (A/B switch)
     int opt_trace_timing = 1;        // CUDA event pair around every bounce-wave traversal launch (mrt_stats.ms_trace)
+    int opt_fused_shade = 0;         // shade stage of a bounce wave inside the traversal kernel (mesh.cu k_trace_shade); A/B: +1.5 % at 1080p 1 spp, -2 % at 4K 8 spp
     int opt_trace_ctas_per_sm = 0;   // 0: as many as fit; n: persistent traversal grids use n CTAs per SM (co-running contexts)
     int opt_builder = 1;             // 0: Karras LBVH hierarchy, 1: PLOC (locally-ordered clustering) hierarchy
     int opt_ploc_radius = 6;         // +-positions searched for the nearest cluster (measured best of 2..32 on config 2)
@@ -132,7 +133,8 @@ struct mrt_context {
     DevArray<float4> hit0_pos, hit0_n;   // primary hit position|prim id, normal|valid
     DevArray<float4> path_state;         // throughput rgb | rng state
     DevArray<float4> ray_o[2], ray_d[2]; // queues: origin|pixel, direction|tmax
-    DevArray<float4> hits;               // t | tri slot | u | v
+    DevArray<unsigned long long> hits;   // t bits | tri slot << 32 (MRT_HIT_PENDING_TRI: not traced yet)
+    bool hits_dirty = true;              // records are not all "pending": reset before the next fused wave
     DevArray<uint32_t> queue_counts;     // one counter per wave, then one work counter per trace launch
     uint32_t num_queue_counts = 0;
     DevArray<uint64_t> sort_keys, sort_keys_alt;

@@ -4,6 +4,12 @@
 // trace = persistent-warp traversal (trace.cuh).  shade = material + blue-noise-rotated PCG sampling +
 // sky on miss + accumulation; it emits the next bounce's rays into a compacted queue with one
 // warp-aggregated atomic per warp (row n5).
+// Option "fused_shade": the shade stage of a bounce wave runs inside the traversal kernel (k_trace_shade): a
+// persistent warp that has traced its last ray and found the queue empty turns into a shading worker for the
+// wave, so that shading fills the SMs which the kernel's drain phase (the longest rays finishing, ~25 % of the
+// launch) leaves idle.  The 8-byte hit record itself is the ready flag (sentinel until the ray is traced).
+// Measured: warps only become free late in the drain, so the overlap is small (+1.5 % at 1080p 1 spp, -2 % at
+// 4K 8 spp where a full-GPU shade kernel is more efficient) -- off by default.
 // Per-pixel semantics are those of secondaryRays.comp:64-135 with the primary hit carried in fp32:
 // the PCG state threads through all samples of a pixel, so samples run sequentially and the
 // wavefront is over pixels.  Every pixel owns at most one live path => accumulation needs no atomics
@@ -111,7 +117,7 @@ struct QueueJob {
     const float4* ray_o;
     const float4* ray_d;
     const uint32_t* count_ptr;
-    float4* hits;
+    unsigned long long* hits;  // t bits | tri << 32; MRT_HIT_PENDING until the ray has been traced
     const uint32_t* order;  // optional: ray k of the sorted order is queue entry order[k] (row n5 sort stage)
     MRT_D uint32_t count() const { return *count_ptr; }
     MRT_D bool load(uint32_t i, float3& o, float3& d) const {
@@ -123,7 +129,9 @@ struct QueueJob {
     }
     MRT_D void store(uint32_t i, const TraceHit& h) const {
         const uint32_t k = order ? __ldg(&order[i]) : i;  // hit records stay in queue order for the shade kernel
-        hits[k] = make_float4(h.t, __uint_as_float(h.tri), 0.0f, 0.0f);
+        // one 64-bit relaxed store: the record doubles as the "ray k is done" flag of the fused shade stage
+        const unsigned long long rec = (unsigned long long)__float_as_uint(h.t) | ((unsigned long long)h.tri << 32);
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(hits + k), "l"(rec) : "memory");
     }
 };
 
@@ -251,18 +259,38 @@ struct ShadeParams {
     Partition part;
 };
 
-// Shade one path vertex per thread.  FIRST: vertex 0, one thread per pixel, inputs from the primary
-// pass.  Otherwise: one thread per traced ray of the previous wave.
-template <bool FIRST>
-__global__ void __launch_bounds__(256)
-k_shade(ShadeParams P, BvhDev bvh, mrt_atmosphere_params A, SkyLuts luts, const uchar4* __restrict__ bn,
-        const float4* __restrict__ albedo, const float4* __restrict__ hit0_pos, const float4* __restrict__ hit0_n,
-        const float4* __restrict__ in_o, const float4* __restrict__ in_d, const float4* __restrict__ hits,
-        const uint32_t* __restrict__ in_count_ptr, uint32_t npix, float4* __restrict__ path_state, float4* __restrict__ accum,
-        float4* __restrict__ out_o, float4* __restrict__ out_d, uint32_t* __restrict__ out_count) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t count = FIRST ? npix : *in_count_ptr;
-    if (blockIdx.x * blockDim.x >= count) return;
+// Everything the shade stage reads and writes (passed by value to the kernels).
+struct ShadeArgs {
+    ShadeParams P;
+    BvhDev bvh;
+    mrt_atmosphere_params A;
+    SkyLuts luts;
+    const uchar4* bn;
+    const float4* albedo;
+    const float4* hit0_pos;       // FIRST: primary hits
+    const float4* hit0_n;
+    const float4* in_o;           // otherwise: the traced queue ...
+    const float4* in_d;
+    unsigned long long* hits;     // ... and its hit records
+    uint32_t npix;
+    float4* path_state;
+    float4* accum;
+    float4* out_o;                // next bounce's queue
+    float4* out_d;
+    uint32_t* out_count;
+    unsigned long long* overflow; // error counter (mrt_stats.stack_overflows) for a fused worker that gave up waiting
+};
+
+// hit record of a ray that has not been traced yet (byte pattern of cudaMemset(0xFE)): tri index 0xFEFEFEFE
+#define MRT_HIT_PENDING_TRI 0xFEFEFEFEu
+
+// Shade path vertex k.  Must be called by all 32 lanes of a warp (k >= count: lane idles through the
+// compaction).  FIRST: vertex 0, k = pixel, inputs from the primary pass.  Otherwise k = queue entry of the
+// traced wave.  FUSED: called from the traversal kernel while other warps still trace -- the lane waits for
+// its hit record and hands the sentinel back for the next wave.
+template <bool FIRST, bool FUSED>
+MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
+    const ShadeParams& P = a.P;
     bool emit = false;
     float3 ro = f3s(0.0f), rd = f3s(0.0f);
     uint32_t pixel = 0;
@@ -271,28 +299,45 @@ k_shade(ShadeParams P, BvhDev bvh, mrt_atmosphere_params A, SkyLuts luts, const 
         uint32_t prim, rng;
         if (FIRST) {
             pixel = k;
-            float4 hp = hit0_pos[k], hn = hit0_n[k];
+            float4 hp = __ldg(&a.hit0_pos[k]), hn = __ldg(&a.hit0_n[k]);
             pos = f3(hp.x, hp.y, hp.z);
             n = f3(hn.x, hn.y, hn.z);
             prim = __float_as_uint(hp.w);
             thr = f3s(1.0f);
-            rng = P.first_sample ? P.seed : __float_as_uint(path_state[k].w);
+            rng = P.first_sample ? P.seed : __float_as_uint(a.path_state[k].w);
             if (P.first_sample) {
-                float4 a = P.accumulate ? accum[k] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                a.w += (float)P.spp;
-                accum[k] = a;
+                float4 acc = P.accumulate ? a.accum[k] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                acc.w += (float)P.spp;
+                a.accum[k] = acc;
             }
         } else {
-            float4 o4 = in_o[k], d4 = in_d[k], h = hits[k];
+            unsigned long long rec;
+            if (FUSED) {
+                unsigned spins = 0;
+                for (;;) {
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(rec) : "l"(a.hits + k) : "memory");
+                    if ((uint32_t)(rec >> 32) != MRT_HIT_PENDING_TRI) break;
+                    if (++spins > (1u << 22)) {  // ~1 s: never expected; counted instead of hanging the GPU
+                        atomicAdd(a.overflow, 1ull);
+                        rec = (unsigned long long)MRT_MISS_ID << 32;
+                        break;
+                    }
+                    __nanosleep(200);
+                }
+                a.hits[k] = ((unsigned long long)MRT_HIT_PENDING_TRI << 32) | MRT_HIT_PENDING_TRI;
+            } else {
+                rec = a.hits[k];
+            }
+            float4 o4 = __ldg(&a.in_o[k]), d4 = __ldg(&a.in_d[k]);
             pixel = __float_as_uint(o4.w);
             float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
-            uint32_t tri = __float_as_uint(h.y);
-            float4 st = path_state[pixel];
+            const uint32_t tri = (uint32_t)(rec >> 32);
+            float4 st = a.path_state[pixel];
             thr = f3(st.x, st.y, st.z);
             rng = __float_as_uint(st.w);
             if (tri != MRT_MISS_ID) {
-                pos = o + d * h.x;
-                n = tri_facing_normal(bvh, tri, d, &prim);
+                pos = o + d * __uint_as_float((uint32_t)rec);
+                n = tri_facing_normal(a.bvh, tri, d, &prim);
             } else {
                 prim = MRT_MISS_ID;
                 pos = f3s(0.0f);
@@ -301,20 +346,20 @@ k_shade(ShadeParams P, BvhDev bvh, mrt_atmosphere_params A, SkyLuts luts, const 
         }
         if (prim == MRT_MISS_ID) {
             // secondaryRays.comp:96: the path ends in the sky
-            float3 c = thr * sky_color(A, luts, P.cameraPos, n);
-            float4 a = accum[pixel];
-            accum[pixel] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w);
-            if (FIRST) path_state[pixel] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
+            float3 c = thr * sky_color(a.A, a.luts, P.cameraPos, n);
+            float4 acc = a.accum[pixel];
+            a.accum[pixel] = make_float4(acc.x + c.x, acc.y + c.y, acc.z + c.z, acc.w);
+            if (FIRST) a.path_state[pixel] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
         } else {
-            float4 al = __ldg(&albedo[prim]);
+            float4 al = __ldg(&a.albedo[prim]);
             thr = thr * f3(al.x, al.y, al.z);  // secondaryRays.comp:94
             if (P.vertex < P.bounces) {
                 uint32_t lr = pixel / P.W, x = pixel - lr * P.W;
-                float2 rot = blue_noise_rotation(bn, P.bnW, P.bnH, x, partition_local_to_y(P.part, lr));
+                float2 rot = blue_noise_rotation(a.bn, P.bnW, P.bnH, x, partition_local_to_y(P.part, lr));
                 lambert_bounce(pos, n, rng, rot.x, rot.y, ro, rd);
                 emit = true;
             }
-            path_state[pixel] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
+            a.path_state[pixel] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
         }
     }
     // compaction: one atomic per warp, lanes take consecutive queue slots
@@ -322,13 +367,46 @@ k_shade(ShadeParams P, BvhDev bvh, mrt_atmosphere_params A, SkyLuts luts, const 
     if (ballot) {
         const unsigned lane = threadIdx.x & 31;
         uint32_t base = 0;
-        if (lane == (unsigned)(__ffs(ballot) - 1)) base = atomicAdd(out_count, (uint32_t)__popc(ballot));
+        if (lane == (unsigned)(__ffs(ballot) - 1)) base = atomicAdd(a.out_count, (uint32_t)__popc(ballot));
         base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ballot) - 1);
         if (emit) {
             uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
-            out_o[slot] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(pixel));
-            out_d[slot] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+            a.out_o[slot] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(pixel));
+            a.out_d[slot] = make_float4(rd.x, rd.y, rd.z, 0.0f);
         }
+    }
+}
+
+// Shade stage as its own kernel: one thread per path vertex.
+template <bool FIRST>
+__global__ void __launch_bounds__(256) k_shade(ShadeArgs a, const uint32_t* __restrict__ in_count_ptr) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t count = FIRST ? a.npix : *in_count_ptr;
+    if (blockIdx.x * blockDim.x >= count) return;
+    shade_vertex<FIRST, false>(k, count, a);
+}
+
+// One bounce wave, traversal + shading in one persistent launch.  A warp leaves trace_persistent() when the
+// queue is exhausted and its own rays are done; it then takes 32-entry chunks of the wave (shade_counter)
+// and shades them, waiting per lane for hit records that slower warps are still producing.  All CTAs of
+// the grid are resident (trace_grid) and waiting warps hold no rays, so the producers always progress.
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
+k_trace_shade(QueueJob job, BvhDev bvh, uint32_t* work_counter, unsigned long long* counters, int count_visits,
+              unsigned long long* total_rays, unsigned long long extra_rays, ShadeArgs sa, uint32_t* shade_counter) {
+    __shared__ TraceShared S;
+    if (total_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total_rays, (unsigned long long)job.count() + extra_rays);
+    trace_shared_init(S);
+    TraceCounters cnt{0, 0, 0};
+    trace_persistent(bvh, job, work_counter, S, cnt);
+    flush_counters(cnt, counters, count_visits != 0);
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t count = job.count();
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(shade_counter, 32u);
+        c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        if (c >= count) break;
+        shade_vertex<false, true>(c + lane, count, sa);
     }
 }
 
@@ -429,20 +507,27 @@ int mesh_primary(mrt_context* ctx) {
 int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags) {
     const uint32_t npix = (uint32_t)ctx->npix;
     const uint32_t waves = spp * bounces;
+    const bool fused = ctx->opt_fused_shade != 0;
     MRT_TRY(dev_reserve(ctx, ctx->path_state, npix));
     for (int q = 0; q < 2; q++) {
         MRT_TRY(dev_reserve(ctx, ctx->ray_o[q], npix));
         MRT_TRY(dev_reserve(ctx, ctx->ray_d[q], npix));
     }
+    if (npix > ctx->hits.cap || !ctx->hits.p) ctx->hits_dirty = true;
     MRT_TRY(dev_reserve(ctx, ctx->hits, npix));
-    // [0, waves]: queue sizes; [waves+1, 2*waves+1]: work counters of the persistent trace launches
-    MRT_TRY(dev_reserve(ctx, ctx->queue_counts, 2 * (size_t)waves + 2));
+    if (fused && ctx->hits_dirty) {  // every record "pending" (MRT_HIT_PENDING_TRI); the fused workers keep it that way
+        MRT_CUDA(ctx, cudaMemsetAsync(ctx->hits.p, 0xFE, sizeof(unsigned long long) * ctx->hits.cap, ctx->stream));
+        ctx->hits_dirty = false;
+    }
+    // [0, waves]: queue sizes; then per wave: work counter of the persistent launch, chunk counter of its shade stage
+    MRT_TRY(dev_reserve(ctx, ctx->queue_counts, 3 * (size_t)waves + 3));
     MRT_TRY(dev_reserve(ctx, ctx->visit_counters, 8));
-    MRT_CUDA(ctx, cudaMemsetAsync(ctx->queue_counts.p, 0, sizeof(uint32_t) * (2 * (size_t)waves + 2), ctx->stream));
+    MRT_CUDA(ctx, cudaMemsetAsync(ctx->queue_counts.p, 0, sizeof(uint32_t) * (3 * (size_t)waves + 3), ctx->stream));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
     ctx->num_queue_counts = waves + 1;
 
-    ShadeParams P;
+    ShadeArgs sa;
+    ShadeParams& P = sa.P;
     P.cameraPos = f3(c->cameraPos[0], c->cameraPos[1], c->cameraPos[2]);
     P.seed = (c->frameCounter << 1u) | 1u;
     P.W = ctx->W;
@@ -452,9 +537,21 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     P.bounces = bounces;
     P.accumulate = ((flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum) ? 1 : 0;
     P.part = ctx->part;
-    SkyLuts luts{ctx->trans_f.p, nullptr, ctx->view_f.p};
-    BvhDev bvh = make_bvh(ctx);
+    sa.bvh = make_bvh(ctx);
+    sa.A = ctx->atmo;
+    sa.luts = SkyLuts{ctx->trans_f.p, nullptr, ctx->view_f.p};
+    sa.bn = ctx->bn;
+    sa.albedo = ctx->albedo.p;
+    sa.hit0_pos = ctx->hit0_pos.p;
+    sa.hit0_n = ctx->hit0_n.p;
+    sa.hits = ctx->hits.p;
+    sa.npix = npix;
+    sa.path_state = ctx->path_state.p;
+    sa.accum = ctx->accum.p;
+    sa.overflow = ctx->visit_counters.p + 4 + 2;
     const unsigned shade_grid = div_up(npix, 256), tgrid = trace_grid(ctx, npix);
+    uint32_t* const work_counters = ctx->queue_counts.p + waves + 1;
+    uint32_t* const shade_counters = ctx->queue_counts.p + 2 * (size_t)waves + 2;
 
     uint32_t wave = 0;
     constexpr uint32_t kMaxTimedLaunches = 4096;  // event pairs kept since mrt_stats_reset
@@ -462,11 +559,11 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         P.first_sample = s == 0;
         P.vertex = 0;
         int q = 0;
-        uint32_t* out_count = ctx->queue_counts.p + wave;
-        k_shade<true><<<shade_grid, 256, 0, ctx->stream>>>(P, bvh, ctx->atmo, luts, ctx->bn, ctx->albedo.p, ctx->hit0_pos.p,
-                                                           ctx->hit0_n.p, nullptr, nullptr, nullptr, nullptr, npix,
-                                                           ctx->path_state.p, ctx->accum.p, ctx->ray_o[q].p, ctx->ray_d[q].p,
-                                                           out_count);
+        sa.in_o = sa.in_d = nullptr;
+        sa.out_o = ctx->ray_o[q].p;
+        sa.out_d = ctx->ray_d[q].p;
+        sa.out_count = ctx->queue_counts.p + wave;
+        k_shade<true><<<shade_grid, 256, 0, ctx->stream>>>(sa, nullptr);
         MRT_LAUNCHED(ctx);
         for (uint32_t b = 1; b <= bounces; b++) {
             const uint32_t* in_count = ctx->queue_counts.p + wave;
@@ -490,23 +587,34 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
                 MRT_LAUNCHED(ctx);
             }
             QueueJob J{ctx->ray_o[q].p, ctx->ray_d[q].p, in_count, ctx->hits.p, sort ? ctx->sort_vals.p : nullptr};
-            k_trace<QueueJob><<<tgrid, TRACE_BLOCK, 0, ctx->stream>>>(J, bvh, ctx->queue_counts.p + waves + 1 + wave,
-                                                                      ctx->visit_counters.p + 4, ctx->opt_count_visits,
-                                                                      ctx->total_rays.p, wave == 0 ? (unsigned long long)npix : 0ull);
-            MRT_LAUNCHED(ctx);
+            const unsigned long long extra = wave == 0 ? (unsigned long long)npix : 0ull;
+            // the shade stage of this wave: vertex b of the paths; the last vertex emits nothing (its counter slot stays 0)
+            P.vertex = b;
+            sa.in_o = ctx->ray_o[q].p;
+            sa.in_d = ctx->ray_d[q].p;
+            sa.out_o = ctx->ray_o[q ^ 1].p;
+            sa.out_d = ctx->ray_d[q ^ 1].p;
+            sa.out_count = ctx->queue_counts.p + (wave + 1 < waves ? wave + 1 : waves);
+            if (fused) {
+                k_trace_shade<<<tgrid, TRACE_BLOCK, 0, ctx->stream>>>(J, sa.bvh, work_counters + wave, ctx->visit_counters.p + 4,
+                                                                     ctx->opt_count_visits, ctx->total_rays.p, extra, sa,
+                                                                     shade_counters + wave);
+                MRT_LAUNCHED(ctx);
+            } else {
+                k_trace<QueueJob><<<tgrid, TRACE_BLOCK, 0, ctx->stream>>>(J, sa.bvh, work_counters + wave, ctx->visit_counters.p + 4,
+                                                                          ctx->opt_count_visits, ctx->total_rays.p, extra);
+                MRT_LAUNCHED(ctx);
+                ctx->hits_dirty = true;
+            }
             if (timed) {
                 cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used + 1], ctx->stream);
                 ctx->trace_ev_used++;
             }
+            if (!fused) {
+                k_shade<false><<<shade_grid, 256, 0, ctx->stream>>>(sa, in_count);
+                MRT_LAUNCHED(ctx);
+            }
             wave++;
-            P.vertex = b;
-            // the last vertex emits nothing; its counter slot stays 0
-            out_count = ctx->queue_counts.p + (wave < waves ? wave : waves);
-            k_shade<false><<<shade_grid, 256, 0, ctx->stream>>>(P, bvh, ctx->atmo, luts, ctx->bn, ctx->albedo.p, nullptr, nullptr,
-                                                                ctx->ray_o[q].p, ctx->ray_d[q].p, ctx->hits.p, in_count, npix,
-                                                                ctx->path_state.p, ctx->accum.p, ctx->ray_o[q ^ 1].p,
-                                                                ctx->ray_d[q ^ 1].p, out_count);
-            MRT_LAUNCHED(ctx);
             q ^= 1;
         }
     }

@@ -211,6 +211,35 @@ def test_ray_sort_does_not_change_the_image(gpu_ctx, oracle, sky_inputs, blue_no
     assert np.array_equal(gpu_ctx.readback(capi.BUF_ACCUM), out[0][0])
 
 
+def test_fused_shade_does_not_change_the_image(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """Option fused_shade (shade stage inside the traversal launch, hit record = ready flag): the accumulator is
+    bit-identical to the two-kernel path, with and without the sort stage, also when toggled between frames and when
+    the image size (and with it the hit-record buffer) changes."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    gpu_ctx.upload_blue_noise(blue_noise)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    try:
+        for (w, h) in ((192, 128), (333, 211), (64, 48)):
+            cam = camera_for(oracle, view, w, h)
+            pc, scn = oracle.constants(cam, frame=3)
+            setup_sky(gpu_ctx, oracle, atmo, cam.position[:])
+            out = {}
+            for fused, flags in ((0, 0), (1, 0), (0, 0), (1, capi.SECONDARY_SORT_RAYS), (1, 0)):
+                gpu_ctx.set_option("fused_shade", fused)
+                gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+                gpu_ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 3, 3, flags)
+                acc = gpu_ctx.readback(capi.BUF_ACCUM).copy()
+                st = gpu_ctx.stats()
+                assert st.stack_overflows == 0
+                out.setdefault("ref", (acc, int(st.secondary_rays)))
+                assert int(st.secondary_rays) == out["ref"][1]
+                assert np.array_equal(acc, out["ref"][0]), f"fused={fused} flags={flags} {w}x{h}"
+    finally:
+        gpu_ctx.set_option("fused_shade", 0)
+
+
 def test_async_readback_matches_blocking(gpu_ctx, oracle, sky_inputs, blue_noise):
     """Pipelined framebuffer readback (double-buffered LDR): frame f's async copy equals its blocking readback even
     when frame f+1 has been issued in between."""
