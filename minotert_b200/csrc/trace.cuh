@@ -60,6 +60,9 @@
 #ifndef TRACE_PREFETCH
 #define TRACE_PREFETCH 0     // prefetch the next child node to L1 at the end of a node step (A/B measured)
 #endif
+#ifndef TRACE_DRAIN_TRI
+#define TRACE_DRAIN_TRI 3    // drain phase: a triangle step runs once 1/n of the working lanes want one (measured 2..32: flat)
+#endif
 #ifndef TRACE_POSTPONE
 #define TRACE_POSTPONE 1     // 1: a lane of the persistent loop may hold one postponed triangle group and keep taking node steps
 #endif
@@ -410,7 +413,10 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
 #endif
         const unsigned tmask = __ballot_sync(0xFFFFFFFFu, want_tri);
         const unsigned nmask = __ballot_sync(0xFFFFFFFFu, want_node);
-        if (tmask && (nmask == 0u || __popc(tmask) >= TRACE_TRI_MIN)) {
+        // drain phase (queue empty, the warp thins out): the fixed batch size would make the triangle lanes wait
+        // for every node lane, so a triangle step runs once a third of the lanes still working want one
+        const int tri_min = exhausted ? min(TRACE_TRI_MIN, max(1, (__popc(tmask | nmask) + TRACE_DRAIN_TRI - 1) / TRACE_DRAIN_TRI)) : TRACE_TRI_MIN;
+        if (tmask && (nmask == 0u || __popc(tmask) >= tri_min)) {
             if (want_tri) {
                 constexpr bool PP = TRACE_POSTPONE != 0;
                 lane_tri_step<PP>(L, bvh, cnt);
