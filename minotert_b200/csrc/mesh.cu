@@ -377,12 +377,42 @@ MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
     }
 }
 
+#ifndef SHADE_REGROUP
+#define SHADE_REGROUP 1  // bounce waves: order the CTA's 256 vertices hits-first so that warps do not run both branches
+#endif
+
 // Shade stage as its own kernel: one thread per path vertex.
 template <bool FIRST>
 __global__ void __launch_bounds__(256) k_shade(ShadeArgs a, const uint32_t* __restrict__ in_count_ptr) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t count = FIRST ? a.npix : *in_count_ptr;
     if (blockIdx.x * blockDim.x >= count) return;
+#if SHADE_REGROUP
+    if (!FIRST) {
+        // A hit runs the bounce (triangle fetch, sincos), a miss the sky evaluation; mixed warps execute both, one
+        // after the other (ncu: 17 of 32 lanes active).  Stable partition of the CTA's window: hits, then misses.
+        __shared__ uint32_t perm[256];
+        __shared__ uint32_t warp_hits[8];
+        const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const bool valid = k < count;
+        const bool is_hit = valid && (uint32_t)(a.hits[k] >> 32) != MRT_MISS_ID;
+        const unsigned hb = __ballot_sync(0xFFFFFFFFu, is_hit);
+        if (lane == 0) warp_hits[wid] = __popc(hb);
+        __syncthreads();
+        uint32_t hits_before = 0, hits_total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const uint32_t h = warp_hits[w];
+            hits_before += w < (int)wid ? h : 0u;
+            hits_total += h;
+        }
+        const uint32_t hit_rank = hits_before + __popc(hb & ((1u << lane) - 1u));
+        const uint32_t miss_rank = (wid * 32u - hits_before) + __popc(~hb & ((1u << lane) - 1u));
+        perm[is_hit ? hit_rank : hits_total + miss_rank] = k;  // invalid lanes count as misses and stay last
+        __syncthreads();
+        k = perm[threadIdx.x];
+    }
+#endif
     shade_vertex<FIRST, false>(k, count, a);
 }
 
