@@ -92,6 +92,7 @@ typedef enum {
     MRT_BUF_MULTISCATTERING = 8, /* RGBA16F 32x32  (sky.ixx:25-26)   */
     MRT_BUF_SKY_VIEW = 9,        /* B10G11R11 192x108 (sky.ixx:187-188) */
     MRT_BUF_HIT_T = 10,          /* R32F 4 B/px primary hit distance (triangle scenes) */
+    MRT_BUF_DENOISED = 11,       /* RGBA8 4 B/px (denoiser.ixx:56) output of mrt_denoise_bilateral */
     MRT_BUF_COUNT_
 } mrt_buffer_id;
 
@@ -125,6 +126,8 @@ typedef struct {
     uint64_t total_rays;      /* primary + secondary rays traced since mrt_stats_reset (device-side running sum) */
     float sah_node_cost;      /* surface-area heuristic of the wide BVH: expected node steps ... */
     float sah_tri_cost;       /* ... and triangle tests of a random ray that hits the root box */
+    float ms_denoise;         /* device time of the last mrt_denoise_bilateral */
+    uint32_t _reserved2;
 } mrt_stats;
 
 /* ---- lifetime ---- */
@@ -186,9 +189,18 @@ int mrt_primary_rays(mrt_context* ctx, uint32_t w, uint32_t h, const mrt_primary
  * The reference hard-codes spp = 8, bounces = 8 (secondaryRays.comp:128-129). */
 int mrt_secondary_rays(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp,
                        uint32_t bounces, uint32_t flags);
+/* Denoiser::bilateral(color, depth, normal, camera, params) (src/gfx/modules/denoiser.ixx:36-97,
+ * src/gpu/denoise/bilateral.comp): filters MRT_BUF_COLOR guided by MRT_BUF_DEPTH / MRT_BUF_NORMAL into
+ * MRT_BUF_DENOISED (RGBA8 unorm, i.e. clamped to [0,1] before the tonemapper, denoiser.ixx:56).
+ * sigma, kSigma, threshold: BilateralParams (defaults 5, 2, 0.12, denoiser.ixx:27-33); nearPlane and
+ * frameCounter: the other push constants (denoiser.ixx:85-91).  round(kSigma*sigma) <= 32.
+ * Needs the whole image in one context (fails with MRT_ERR_STATE under mrt_set_partition with nranks > 1). */
+int mrt_denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float threshold, float nearPlane,
+                          uint32_t frameCounter);
 /* Tonemapper::{linear,reinhard,hable,aces,uchimura,amd}(input, exposure, params)
- * (tonemapper.ixx:57-373).  source: MRT_BUF_COLOR (reference path) or MRT_BUF_ACCUM
- * (progressive average).  params: the push constants after `exposure`. */
+ * (tonemapper.ixx:57-373).  source: MRT_BUF_COLOR (reference path), MRT_BUF_ACCUM
+ * (progressive average) or MRT_BUF_DENOISED (the denoiser's RGBA8 image, as Renderer_impl::draw
+ * chains them, renderer.ixx:61-62).  params: the push constants after `exposure`. */
 int mrt_tonemap(mrt_context* ctx, int mode, float exposure, const float* params, uint32_t nparams,
                 int source);
 

@@ -69,6 +69,7 @@ int buffer_info(mrt_context* ctx, int id, void** p, size_t* bytes) {
             ctx->sky_pending = false;
         }
         *p = ctx->view_packed.p; *bytes = (size_t)MRT_VIEW_W * MRT_VIEW_H * 4; return MRT_OK;
+    case MRT_BUF_DENOISED: if (!ctx->have_denoised) break; *p = ctx->denoised.p; *bytes = n * 4; return MRT_OK;
     case MRT_BUF_HIT_T: if (!ctx->have_gbuffer || ctx->scene_kind != 2) break; *p = ctx->hit_t.p; *bytes = n * 4; return MRT_OK;
     default: return mrt_fail(ctx, MRT_ERR_INVALID, "unknown buffer id %d", id);
     }
@@ -100,7 +101,7 @@ int mrt_create(int device, mrt_context** out) {
         delete ctx;
         return MRT_ERR_CUDA;
     }
-    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);  // pairs: sky, primary, secondary, tonemap, denoise
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
@@ -129,6 +130,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->trans16); dev_free(ctx->multi16); dev_free(ctx->view_packed);
     dev_free(ctx->trans_f); dev_free(ctx->multi_f); dev_free(ctx->view_f);
     dev_free(ctx->visibility); dev_free(ctx->depth); dev_free(ctx->normal); dev_free(ctx->motion); dev_free(ctx->color16);
+    dev_free(ctx->denoised); dev_free(ctx->dn_taps);
     dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
     dev_free(ctx->hit0_pos); dev_free(ctx->hit0_n); dev_free(ctx->path_state);
     for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); }
@@ -184,7 +186,7 @@ int mrt_scene_set_spheres(mrt_context* ctx, const mrt_sphere* spheres, uint32_t 
     for (uint32_t i = 0; i < n; i++) ctx->spheres.s[i] = spheres[i];
     ctx->spheres.n = n;
     ctx->scene_kind = 1;
-    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = false;  // a new scene restarts accumulation
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;  // a new scene restarts accumulation
     return MRT_OK;
 }
 
@@ -210,7 +212,7 @@ int mrt_scene_upload_mesh(mrt_context* ctx, const float* positions, uint32_t nve
     ctx->ntris = ntris;
     ctx->scene_kind = 2;
     ctx->bvh_valid = false;
-    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = false;  // a new scene restarts accumulation
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;  // a new scene restarts accumulation
     return MRT_OK;
 }
 
@@ -271,7 +273,7 @@ int mrt_set_partition(mrt_context* ctx, uint32_t rank, uint32_t nranks, uint32_t
     MRT_ENTER(ctx);
     if (nranks == 0 || rank >= nranks || slab_rows == 0) return mrt_fail(ctx, MRT_ERR_INVALID, "bad partition %u/%u slab %u", rank, nranks, slab_rows);
     ctx->part = Partition{rank, nranks, slab_rows};
-    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = false;
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;
     return MRT_OK;
 }
 
@@ -301,7 +303,7 @@ int mrt_primary_rays(mrt_context* ctx, uint32_t w, uint32_t h, const mrt_primary
     if (ctx->scene_kind == 0) return mrt_fail(ctx, MRT_ERR_STATE, "primary rays: no scene");
     if (ctx->scene_kind == 2 && !ctx->bvh_valid) return mrt_fail(ctx, MRT_ERR_STATE, "primary rays: mesh uploaded but not built");
     uint32_t rows = partition_local_rows(ctx->part, h);
-    if (w != ctx->W || h != ctx->H || rows != ctx->local_rows) ctx->have_accum = ctx->have_color = ctx->have_ldr = false;
+    if (w != ctx->W || h != ctx->H || rows != ctx->local_rows) ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;
     ctx->W = w; ctx->H = h; ctx->local_rows = rows;
     ctx->npix = (size_t)w * rows;
     ctx->pc = *c;
@@ -333,8 +335,24 @@ int mrt_secondary_rays(mrt_context* ctx, const mrt_secondary_constants* c, uint3
     if (s == MRT_OK) {
         ctx->have_accum = true;
         ctx->have_color = ctx->scene_kind == 1;
+        ctx->have_denoised = false;
         ctx->stats.secondary_rays = ~0ull;  // resolved lazily in mrt_stats_get
     }
+    return s;
+}
+
+int mrt_denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float threshold, float nearPlane, uint32_t frameCounter) {
+    MRT_ENTER(ctx);
+    if (!ctx->have_gbuffer || !ctx->have_accum) return mrt_fail(ctx, MRT_ERR_STATE, "denoise before primary + secondary rays");
+    if (ctx->part.nranks > 1) return mrt_fail(ctx, MRT_ERR_STATE, "denoise needs the whole image in one context (partition %u of %u)", ctx->part.rank, ctx->part.nranks);
+    if (!ctx->have_color) {  // triangle path: resolve the accumulator into the RGBA16F image the filter reads
+        void* p; size_t b;
+        MRT_TRY(buffer_info(ctx, MRT_BUF_COLOR, &p, &b));
+    }
+    cudaEventRecord(ctx->ev[8], ctx->stream);
+    int s = denoise_bilateral(ctx, sigma, kSigma, threshold, nearPlane, frameCounter);
+    cudaEventRecord(ctx->ev[9], ctx->stream);
+    if (s == MRT_OK) ctx->have_denoised = true;
     return s;
 }
 
@@ -343,8 +361,10 @@ int mrt_tonemap(mrt_context* ctx, int mode, float exposure, const float* params,
     if (mode < MRT_TONEMAP_LINEAR || mode > MRT_TONEMAP_AMD) return mrt_fail(ctx, MRT_ERR_INVALID, "unknown tonemap mode %d", mode);
     static const uint32_t need[6] = {0, 1, 0, 0, 6, 5};
     if (nparams < need[mode] || (need[mode] && !params)) return mrt_fail(ctx, MRT_ERR_INVALID, "tonemap mode %d needs %u params", mode, need[mode]);
-    if (source != MRT_BUF_COLOR && source != MRT_BUF_ACCUM) return mrt_fail(ctx, MRT_ERR_INVALID, "tonemap source must be COLOR or ACCUM");
+    if (source != MRT_BUF_COLOR && source != MRT_BUF_ACCUM && source != MRT_BUF_DENOISED)
+        return mrt_fail(ctx, MRT_ERR_INVALID, "tonemap source must be COLOR, ACCUM or DENOISED");
     if (!ctx->have_accum) return mrt_fail(ctx, MRT_ERR_STATE, "tonemap before secondary rays");
+    if (source == MRT_BUF_DENOISED && !ctx->have_denoised) return mrt_fail(ctx, MRT_ERR_STATE, "tonemap of the denoised image before mrt_denoise_bilateral");
     if (source == MRT_BUF_COLOR && !ctx->have_color) {
         void* p; size_t b;
         MRT_TRY(buffer_info(ctx, MRT_BUF_COLOR, &p, &b));
@@ -427,6 +447,7 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
     if (ctx->have_gbuffer && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.ms_primary = ms;
     if (ctx->have_accum && cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->stats.ms_secondary = ms;
     if (ctx->have_ldr && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->stats.ms_tonemap = ms;
+    if (ctx->have_denoised && cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]) == cudaSuccess) ctx->stats.ms_denoise = ms;
     cudaGetLastError();
     if (ctx->have_accum && ctx->stats.secondary_rays == ~0ull) {
         if (ctx->scene_kind == 1) {

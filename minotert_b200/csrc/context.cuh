@@ -124,6 +124,13 @@ struct mrt_context {
     DevArray<uint16_t> depth, normal, motion, color16;
     DevArray<float> hit_t;
     DevArray<float4> accum;
+    // bilateral denoiser (denoise.cu): RGBA8 output, tap list cached per (sigma, kSigma, image size)
+    DevArray<uchar4> denoised;
+    DevArray<float4> dn_taps;
+    int dn_ntaps = 0;
+    float dn_key_sigma = 0.0f, dn_key_ksigma = 0.0f;
+    uint32_t dn_key_w = 0, dn_key_h = 0;
+    bool have_denoised = false;
     DevArray<uchar4> ldr_buf[2];         // double-buffered output framebuffer: an async readback of frame f
     int ldr_cur = 0;                     // overlaps the rendering of frame f+1 (the reference keeps 3 frames in flight)
     cudaStream_t copy_stream = nullptr;
@@ -144,7 +151,7 @@ struct mrt_context {
 
     // stats
     mrt_stats stats{};
-    cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t ev[10] = {nullptr};
     // The sky view of a frame is generated on a side stream so that it overlaps the primary pass
     // (Renderer::draw order: sky -> primary -> secondary); consumers join through sky_join().
     cudaStream_t aux_stream = nullptr;
@@ -202,6 +209,7 @@ int sky_gen_atmosphere(mrt_context* ctx);
 int sky_gen_view(mrt_context* ctx, const float probe[3], const float sunDir[3], const float sunIll[3]);
 int spheres_primary(mrt_context* ctx);
 int spheres_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags);
+int denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float threshold, float nearPlane, uint32_t frameCounter);
 int tonemap_run(mrt_context* ctx, int mode, float exposure, const float* params, uint32_t nparams, int source);
 int bvh_build_full(mrt_context* ctx);
 int bvh_refit(mrt_context* ctx);

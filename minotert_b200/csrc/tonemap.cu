@@ -116,16 +116,20 @@ MRT_D uchar4 encode_ldr(float3 mapped) {
                        (unsigned char)unorm8(srgb1(mapped.z)), 255);
 }
 
-// SRC_ACCUM: read the fp32 accumulator and divide by its sample count (row n7);
-// otherwise read the reference's RGBA16F colour image (row a12).
-template <bool SRC_ACCUM>
+// SRC 1: read the fp32 accumulator and divide by its sample count (row n7); SRC 2: the denoiser's RGBA8 unorm
+// image (denoiser.ixx:56, texel = k/255); SRC 0: the reference's RGBA16F colour image (row a12).
+template <int SRC>
 __global__ void __launch_bounds__(256) k_tonemap(TonemapParams T, const float4* __restrict__ accum,
-                                                 const uint2* __restrict__ color16, uchar4* __restrict__ ldr, size_t n) {
+                                                 const uint2* __restrict__ color16, const uchar4* __restrict__ rgba8,
+                                                 uchar4* __restrict__ ldr, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float3 src;
-        if (SRC_ACCUM) {
+        if (SRC == 1) {
             float4 a = __ldcs(&accum[i]);
             src = a.w > 0.0f ? f3(a.x / a.w, a.y / a.w, a.z / a.w) : f3s(0.0f);
+        } else if (SRC == 2) {
+            uchar4 c = __ldcs(&rgba8[i]);
+            src = f3((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f);
         } else {
             uint2 pk = __ldcs(&color16[i]);
             src = f3(f16_bits_to_f32((uint16_t)(pk.x & 0xFFFF)), f16_bits_to_f32((uint16_t)(pk.x >> 16)),
@@ -162,10 +166,12 @@ int tonemap_run(mrt_context* ctx, int mode, float exposure, const float* params,
     if ((size_t)grid * 256 > n) grid = div_up(n, 256);
     if (grid == 0) grid = 1;
     if (source == MRT_BUF_ACCUM)
-        k_tonemap<true><<<grid, 256, 0, ctx->stream>>>(T, ctx->accum.p, nullptr, ldr.p, n);
+        k_tonemap<1><<<grid, 256, 0, ctx->stream>>>(T, ctx->accum.p, nullptr, nullptr, ldr.p, n);
+    else if (source == MRT_BUF_DENOISED)
+        k_tonemap<2><<<grid, 256, 0, ctx->stream>>>(T, nullptr, nullptr, ctx->denoised.p, ldr.p, n);
     else
-        k_tonemap<false><<<grid, 256, 0, ctx->stream>>>(T, nullptr, reinterpret_cast<const uint2*>(ctx->color16.p),
-                                                        ldr.p, n);
+        k_tonemap<0><<<grid, 256, 0, ctx->stream>>>(T, nullptr, reinterpret_cast<const uint2*>(ctx->color16.p), nullptr,
+                                                    ldr.p, n);
     MRT_LAUNCHED(ctx);
     ctx->have_ldr = true;
     return mrt_check_cuda(ctx, cudaGetLastError(), "tonemap");

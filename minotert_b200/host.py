@@ -56,6 +56,7 @@ def load():
     L.minote_app_set_mesh.argtypes = [vp, vp, u32, vp, u32, vp]
     L.minote_app_update_mesh.argtypes = [vp, vp, u32, C.c_int]
     L.minote_app_configure.argtypes = [vp, u32, u32, C.c_int, C.c_int, C.c_float]
+    L.minote_app_set_denoise.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float]
     L.minote_app_resize.argtypes = [vp, u32, u32]
     L.minote_app_draw.argtypes = [vp, cam]
     L.minote_app_read_framebuffer.argtypes = [vp, vp, C.c_size_t]
@@ -151,8 +152,13 @@ class Renderer:
         p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
         self._ck(self.L.minote_app_update_mesh(self.h, p.ctypes.data_as(C.c_void_p), p.shape[0], int(refit)))
 
-    def configure(self, samples=8, bounces=8, accumulate=False, tonemap="amd", exposure=1.0):
+    def configure(self, samples=8, bounces=8, accumulate=False, tonemap="amd", exposure=1.0, denoise="none",
+                  bilateral=capi.BILATERAL_DEFAULT):
+        """Renderer settings (the reference's ImGui statics).  NOTE: the C++ Renderer defaults to the reference's
+        bilateral denoiser (renderer.ixx:140); this method sets the mode explicitly and its own default is "none",
+        so that the ray-throughput measurements and the path-trace parity tests see the path tracer's image."""
         self._ck(self.L.minote_app_configure(self.h, samples, bounces, int(accumulate), capi.TONEMAP[tonemap], exposure))
+        self._ck(self.L.minote_app_set_denoise(self.h, capi.DENOISE[denoise], *[float(x) for x in bilateral]))
 
     def draw(self, camera):
         self._ck(self.L.minote_app_draw(self.h, C.byref(camera)))

@@ -13,6 +13,7 @@ import minote.cuda;
 import minote.modules.sky;
 import minote.modules.pathtracer;
 import minote.modules.tonemapper;
+import minote.modules.denoiser;
 import minote.renderer;
 import minote.freecam;
 
@@ -127,6 +128,14 @@ int minote_app_configure(void* a, std::uint32_t samples, std::uint32_t bounces, 
         r.pathtracer.accumulate = accumulate != 0;
         r.tonemapMode = static_cast<TonemapMode>(tonemap_mode);
         r.exposure = exposure;
+    });
+}
+// Renderer_impl::denoise controls (renderer.ixx:140-152): mode 0 None, 1 Bilateral
+int minote_app_set_denoise(void* a, int mode, float sigma, float kSigma, float threshold) {
+    return guarded(static_cast<App*>(a), [&] {
+        auto& r = *Renderer::serv;
+        r.denoiseMode = static_cast<DenoiseMode>(mode);
+        r.bilateralParams = BilateralParams{sigma, kSigma, threshold};
     });
 }
 int minote_app_resize(void* a, std::uint32_t w, std::uint32_t h) {

@@ -1,6 +1,6 @@
 // minote.renderer -- frame orchestration, Renderer_impl::draw(camera) (src/gfx/renderer.ixx:39-68):
-// sky LUTs -> primaryRays -> secondaryRays -> [denoise: out of scope] -> tonemap, same order and
-// defaults (AMD tonemapper, exposure 1, renderer.ixx:183-184).  Presentation (swapchain blit) is
+// sky LUTs -> primaryRays -> secondaryRays -> denoise -> tonemap, same order and defaults (bilateral
+// denoiser renderer.ixx:140-141, AMD tonemapper, exposure 1, renderer.ixx:183-184).  Presentation (swapchain blit) is
 // replaced by an RGBA8 framebuffer the caller reads back.
 module;
 #include <cstdint>
@@ -13,7 +13,9 @@ import minote.cuda;
 import minote.modules.sky;
 import minote.modules.pathtracer;
 import minote.modules.tonemapper;
+import minote.modules.denoiser;
 
+export enum class DenoiseMode : int { None = 0, Bilateral = 1 };  // renderer.ixx:129-132
 export enum class TonemapMode : int { Linear = 0, Reinhard = 1, Hable = 2, ACES = 3, Uchimura = 4, AMD = 5 };
 
 export class Renderer_impl : Cuda {
@@ -51,7 +53,8 @@ public:
         auto skyView = sky.createView(*atmosphere, camera.position);
         auto gbuffer = pathtracer.primaryRays(outputSize, camera, prevCamera);
         auto pathtraced = pathtracer.secondaryRays(gbuffer, camera, *atmosphere, skyView, blueNoise);
-        framebuffer = tonemap(pathtraced);
+        auto filtered = denoise(pathtraced, gbuffer.depth, gbuffer.normal, camera);
+        framebuffer = tonemap(filtered);
 
         // Temporal preservation
         prevCamera = camera;
@@ -71,6 +74,10 @@ public:
     uvec2 outputSize;
     Pathtracer pathtracer;
     Tonemapper tonemapper;
+    Denoiser denoiser;
+    // ImGui statics of Renderer_impl::denoise (renderer.ixx:140-141)
+    DenoiseMode denoiseMode = DenoiseMode::Bilateral;
+    BilateralParams bilateralParams = BilateralParams::make_default();
     // ImGui statics of Renderer_impl::tonemap (renderer.ixx:183-187)
     float exposure = 1.0f;
     TonemapMode tonemapMode = TonemapMode::AMD;
@@ -80,6 +87,15 @@ public:
     DeviceImage framebuffer;
 
 private:
+    // renderer.ixx:127-161
+    auto denoise(DeviceImage color, DeviceImage depth, DeviceImage normal, Camera const& camera) -> DeviceImage {
+        switch (denoiseMode) {
+        case DenoiseMode::None: return color;
+        case DenoiseMode::Bilateral: return denoiser.bilateral(color, depth, normal, camera, bilateralParams);
+        default: Cuda::serv->raise("Unknown denoise mode");
+        }
+    }
+
     auto tonemap(DeviceImage color) -> DeviceImage {
         switch (tonemapMode) {
         case TonemapMode::Linear: return tonemapper.linear(color, exposure);

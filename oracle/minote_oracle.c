@@ -1087,6 +1087,111 @@ void orc_secondary_rays_spheres(uint32_t w, uint32_t h, const orc_secondary_cons
     sky_ctx_free(&S);
 }
 
+/* =============================== bilateral denoiser =============================== */
+
+typedef struct { int w, h, ch; const float* px; } texn;
+
+/* texture(tex, uv) with the LinearClamp sampler (src/gfx/modules/denoiser.ixx:72-74,
+ * src/gfx/samplers.ixx:14-19), ch channels.  Filtering rule fixed for THIS stage: the fractional
+ * texel position is held with 8 fractional bits (VkPhysicalDeviceLimits::subTexelPrecisionBits,
+ * 8 on every desktop implementation), weights are k/256, and a texel whose weight is zero is not
+ * read.  The shader's taps are built to land on texel centres in x (d.x is integral) and the
+ * colour image holds +inf on the sun disc (fp16 overflow of 1.2e5 nits): with unquantised fp32
+ * weights the 1e-4-texel rounding residue of uv + d/size would decide, tap by tap, between inf,
+ * NaN (0 * inf) and a finite value, which no GPU does.  (The sky LUT lookups keep the plain fp32
+ * lerp of tex_bilinear: they are smooth and finite, so weight precision is immaterial there.) */
+static void texn_bilinear(const texn* t, float u, float v, float* out) {
+    float x = u * (float)t->w - 0.5f, y = v * (float)t->h - 0.5f;
+    float fx0 = floorf(x), fy0 = floorf(y);
+    float fx = rintf((x - fx0) * 256.0f) * (1.0f / 256.0f), fy = rintf((y - fy0) * 256.0f) * (1.0f / 256.0f);
+    int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    x0 = x0 < 0 ? 0 : (x0 > t->w - 1 ? t->w - 1 : x0);
+    x1 = x1 < 0 ? 0 : (x1 > t->w - 1 ? t->w - 1 : x1);
+    y0 = y0 < 0 ? 0 : (y0 > t->h - 1 ? t->h - 1 : y0);
+    y1 = y1 < 0 ? 0 : (y1 > t->h - 1 ? t->h - 1 : y1);
+    const float* p00 = &t->px[(size_t)t->ch * ((size_t)y0 * t->w + x0)];
+    const float* p10 = &t->px[(size_t)t->ch * ((size_t)y0 * t->w + x1)];
+    const float* p01 = &t->px[(size_t)t->ch * ((size_t)y1 * t->w + x0)];
+    const float* p11 = &t->px[(size_t)t->ch * ((size_t)y1 * t->w + x1)];
+    float gx = 1.0f - fx, gy = 1.0f - fy;
+    for (int c = 0; c < t->ch; c++) {
+        float top = fx == 0.0f ? p00[c] : (gx == 0.0f ? p10[c] : p00[c] * gx + p10[c] * fx);
+        float bot = fx == 0.0f ? p01[c] : (gx == 0.0f ? p11[c] : p01[c] * gx + p11[c] * fx);
+        out[c] = fy == 0.0f ? top : (gy == 0.0f ? bot : top * gy + bot * fy);
+    }
+}
+
+/* smartDeNoise + main of src/gpu/denoise/bilateral.comp:23-76, push constants of
+ * src/gfx/modules/denoiser.ixx:78-91 (defaults sigma 5, kSigma 2, threshold 0.12, :27-33).
+ * Inputs are the reference's images: colour RGBA16F, depth R16F, normal RGBA16F; output RGBA8 unorm
+ * (denoiser.ixx:56), i.e. the HDR colour is clamped to [0,1] BEFORE the tonemapper sees it.
+ * Fixed here where GLSL leaves it open: round() = roundf (half away from zero); clamp(NaN,0,1) = 0
+ * (inf - inf arises where both taps are sky: depth 0 in inverted Z). */
+void orc_denoise_bilateral(uint32_t w, uint32_t h, const uint16_t* color16, const uint16_t* depth16,
+                           const uint16_t* normal16, float sigma, float kSigma, float threshold,
+                           float nearPlane, uint32_t frameCounter, uint8_t* rgba8) {
+    size_t n = (size_t)w * h;
+    float* col = (float*)malloc(sizeof(float) * 4 * n);
+    float* dep = (float*)malloc(sizeof(float) * n);
+    float* nor = (float*)malloc(sizeof(float) * 3 * n);
+    for (size_t i = 0; i < n; i++) {
+        for (int c = 0; c < 4; c++) col[4 * i + c] = orc_f16_to_f32(color16[4 * i + c]);
+        dep[i] = orc_f16_to_f32(depth16[i]);
+        for (int c = 0; c < 3; c++) nor[3 * i + c] = orc_f16_to_f32(normal16[4 * i + c]);
+    }
+    const texn tc = {(int)w, (int)h, 4, col}, tz = {(int)w, (int)h, 1, dep}, tn = {(int)w, (int)h, 3, nor};
+    const float INV_SQRT_OF_2PI = 0.39894228040143267793994605993439f;
+    const float INV_PI = 0.31830988618379067153776752674503f;
+    const float radius = roundf(kSigma * sigma);
+    const float radQ = radius * radius;
+    const float invSigmaQx2 = .5f / (sigma * sigma);
+    const float invSigmaQx2PI = INV_PI * invSigmaQx2;
+    const float invThresholdSqx2 = .5f / (threshold * threshold);
+    const float invThresholdSqrt2PI = INV_SQRT_OF_2PI / threshold;
+    const float sizeX = (float)w, sizeY = (float)h;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long long gy = 0; gy < (long long)h; gy++)
+        for (uint32_t gx = 0; gx < w; gx++) {
+            float uvx = ((float)gx + 0.5f) / sizeX, uvy = ((float)gy + 0.5f) / sizeY;
+            float filtered[4], centrPx[4], centrZ, centrN[3];
+            texn_bilinear(&tc, uvx, uvy, centrPx);
+            texn_bilinear(&tz, uvx, uvy, &centrZ);
+            if (centrZ < 0.0f) {
+                memcpy(filtered, centrPx, sizeof filtered);
+            } else {
+                texn_bilinear(&tn, uvx, uvy, centrN);
+                float zBuff = 0.0f, aBuff[4] = {0, 0, 0, 0};
+                for (float dx = -radius; dx <= radius; dx++) {
+                    float pt = sqrtf(radQ - dx * dx);
+                    for (float dy = -pt; dy <= pt; dy++) {
+                        float blurFactor = expf(-(dx * dx + dy * dy) * invSigmaQx2) * invSigmaQx2PI;
+                        float u = uvx + dx / sizeX, v = uvy + dy / sizeY;
+                        float walkPx[4], walkZ, walkN[3];
+                        texn_bilinear(&tc, u, v, walkPx);
+                        texn_bilinear(&tz, u, v, &walkZ);
+                        texn_bilinear(&tn, u, v, walkN);
+                        float dZ = nearPlane / walkZ - nearPlane / centrZ;
+                        dZ *= 100.0f;
+                        float dN = walkN[0] * centrN[0] + walkN[1] * centrN[1] + walkN[2] * centrN[2];
+                        float deltaFactor = expf(clampf(dN - dZ * dZ, 0.0f, 1.0f) * invThresholdSqx2) *
+                                            invThresholdSqrt2PI * blurFactor;
+                        zBuff += deltaFactor;
+                        for (int c = 0; c < 4; c++) aBuff[c] += deltaFactor * walkPx[c];
+                    }
+                }
+                for (int c = 0; c < 4; c++) filtered[c] = aBuff[c] / zBuff;
+            }
+            uint32_t seed = gx * 709u + (uint32_t)gy * 1153u + frameCounter * 1361u;
+            float noise = orc_random_float(&seed) * 0.005f;
+            size_t i = (size_t)gy * w + gx;
+            rgba8[4 * i] = orc_unorm8(filtered[0] + noise);
+            rgba8[4 * i + 1] = orc_unorm8(filtered[1] + noise);
+            rgba8[4 * i + 2] = orc_unorm8(filtered[2] + noise);
+            rgba8[4 * i + 3] = orc_unorm8(filtered[3]);
+        }
+    free(col); free(dep); free(nor);
+}
+
 /* =============================== tonemap (a14) =============================== */
 
 /* src/gpu/util.glsl:13-18 */
@@ -1215,7 +1320,10 @@ void orc_tonemap(int mode, uint32_t w, uint32_t h, const void* src, int src_is_f
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < (long long)n; i++) {
         float in[3], out[3];
-        if (src_is_f16) {
+        if (src_is_f16 == 2) { /* the denoiser's RGBA8 unorm image (denoiser.ixx:56): texel = k/255 */
+            const uint8_t* s = (const uint8_t*)src + 4 * i;
+            in[0] = (float)s[0] / 255.0f; in[1] = (float)s[1] / 255.0f; in[2] = (float)s[2] / 255.0f;
+        } else if (src_is_f16) {
             const uint16_t* s = (const uint16_t*)src + 4 * i;
             in[0] = orc_f16_to_f32(s[0]); in[1] = orc_f16_to_f32(s[1]); in[2] = orc_f16_to_f32(s[2]);
         } else {

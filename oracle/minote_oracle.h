@@ -14,6 +14,8 @@
  *   fp32 -> B10G11R11     : RNE to 6/6/5-bit mantissa, negatives/NaN -> 0, saturate to max finite
  *   fp32 -> unorm8        : rint(clamp(x,0,1)*255), NaN -> 0
  *   bilinear filtering    : fp32 lerp on texel-centre coordinates, clamp/repeat per sampler
+ *                           (denoiser only: weights held to 8 fractional bits, zero-weight texels
+ *                           not read -- see texn_bilinear in minote_oracle.c for why)
  *   mat4*vec4             : sum of columns scaled by components, left to right, no FMA
  *   normalize(v)          : v / sqrt(dot(v,v)) per component
  *   transcendentals       : glibc libm (sinf, cosf, acosf, powf, expf, sqrtf)
@@ -151,8 +153,14 @@ void orc_secondary_rays_spheres(uint32_t w, uint32_t h, const orc_secondary_cons
                                 uint32_t bounces, uint16_t* color16, float* color32,
                                 uint64_t* rays_out);
 
+/* ---- bilateral denoiser (src/gpu/denoise/bilateral.comp, denoiser.ixx:36-97) ---- */
+void orc_denoise_bilateral(uint32_t w, uint32_t h, const uint16_t* color16 /*RGBA16F*/,
+                           const uint16_t* depth16 /*R16F*/, const uint16_t* normal16 /*RGBA16F*/,
+                           float sigma, float kSigma, float threshold, float nearPlane,
+                           uint32_t frameCounter, uint8_t* rgba8);
+
 /* ---- tonemap (a14) ---- */
-/* src: RGBA16F if src_is_f16 else RGBA32F.  params: mode-specific push constants after exposure
+/* src: RGBA32F if src_is_f16 == 0, RGBA16F if 1, RGBA8 unorm (denoiser output) if 2.  params: mode-specific push constants after exposure
  * (reinhard: hdrMax; uchimura: 6 floats; amd: 5 floats). */
 void orc_tonemap(int mode, uint32_t w, uint32_t h, const void* src, int src_is_f16, float exposure,
                  const float* params, uint8_t* rgba8);

@@ -130,6 +130,7 @@ def lib():
         "orc_sky_color": (None, [C.POINTER(AtmosphereParams), u16p, u32p, f32p, f32p, f32p]),
         "orc_primary_rays_spheres": (None, [C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.POINTER(Sphere), C.c_uint32, u32p, u16p, u16p, u16p]),
         "orc_secondary_rays_spheres": (None, [C.c_uint32, C.c_uint32, C.POINTER(SecondaryConstants), C.POINTER(Sphere), C.c_uint32, u32p, u16p, u16p, u8p, C.c_uint32, C.c_uint32, C.POINTER(AtmosphereParams), u16p, u32p, C.c_uint32, C.c_uint32, u16p, f32p, u64p]),
+        "orc_denoise_bilateral": (None, [C.c_uint32, C.c_uint32, u16p, u16p, u16p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32, u8p]),
         "orc_tonemap": (None, [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, f32p, u8p]),
         "orc_tonemap_pixel": (None, [C.c_int, f32p, C.c_float, f32p, f32p]),
         "orc_scene_create": (C.c_void_p, [f32p, C.c_uint32, u32p, C.c_uint32, f32p]),
@@ -253,7 +254,21 @@ def tonemap(mode, src, exposure=1.0, params=AMD_DEFAULT):
     src = np.ascontiguousarray(src)
     par = (C.c_float * 8)(*params)
     lib().orc_tonemap(TONEMAP[mode] if isinstance(mode, str) else mode, w, h, src.ctypes.data_as(C.c_void_p),
-                      1 if src.dtype == np.uint16 else 0, exposure, par, _p(out, C.c_uint8))
+                      {np.dtype(np.uint16): 1, np.dtype(np.uint8): 2}.get(src.dtype, 0), exposure, par,
+                      _p(out, C.c_uint8))
+    return out
+
+
+BILATERAL_DEFAULT = (5.0, 2.0, 0.12)  # sigma, kSigma, threshold: src/gfx/modules/denoiser.ixx:27-33
+
+
+def denoise_bilateral(color16, depth16, normal16, params=BILATERAL_DEFAULT, near=0.001, frame=1):
+    """Denoiser::bilateral (denoiser.ixx:36-97): RGBA16F colour + R16F depth + RGBA16F normal -> RGBA8."""
+    h, w = depth16.shape[:2]
+    out = np.zeros((h, w, 4), np.uint8)
+    c, d, n = (np.ascontiguousarray(a, np.uint16) for a in (color16, depth16, normal16))
+    lib().orc_denoise_bilateral(w, h, _p(c, C.c_uint16), _p(d, C.c_uint16), _p(n, C.c_uint16), params[0], params[1],
+                                params[2], near, frame, _p(out, C.c_uint8))
     return out
 
 
