@@ -294,6 +294,16 @@ def run_ours(args):
     clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
 
+    # ---- the stage after the path tracer in Renderer::draw: bilateral denoiser (reference defaults), timed on its own
+    # (not part of a "step": the metric counts rays; BASELINE's configs do not name the denoiser)
+    den_ms = None
+    if world == 1:
+        dm = []
+        for i in range(8):
+            ctx.denoise_bilateral(capi.BILATERAL_DEFAULT, cam.nearPlane, i + 1)
+            dm.append(ctx.stats().ms_denoise)
+        den_ms = float(np.median(dm[3:]))
+
     # ---- e2e: Renderer::draw(camera) + framebuffer readback into pinned host memory, wall clock.
     # One frame in flight, like the reference's swapchain (renderer.ixx:36): the D2H copy of frame i overlaps
     # the rendering of frame i+1 (double-buffered framebuffer), every frame's result still reaches the host.
@@ -350,7 +360,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl, "triangles": int(idx.shape[0]), "resolution": [w, h], "spp": spp, "bounces": bounces,
-                       "sampling": "PCG + blue-noise Cranley-Patterson rotation", "tonemap": "amd",
+                       "sampling": "PCG + blue-noise Cranley-Patterson rotation", "tonemap": "amd", "denoise": "none (timed separately: kernels.denoise_bilateral_ms)",
                        "l2": "flushed between steps (256 MiB memset)", "bvh_bytes": int(build_stats.bvh_bytes),
                        "wide_nodes": int(build_stats.num_wide_nodes), "bvh_build_ms": build_stats.ms_build, "builder": args.builder, "sort_rays": bool(args.sort_rays),
                        "stack_overflows": int(ctx.stats().stack_overflows),
@@ -368,7 +378,8 @@ def run_ours(args):
                          "share_of_step": trace_ms / max(dev_ms if world == 1 else dev_ms, 1e-9),
                          "note": ("algorithmic bytes; the BVH of this config fits in L2, so frac > DRAM utilisation" if build_stats.bvh_bytes < (100 << 20)
                                   else "algorithmic bytes; the BVH exceeds L2 (HBM-resident)")},
-            "kernels": {"primary_ms_per_step": primary_ms / args.steps, "trace_ms_per_step": trace_ms / args.steps},
+            "kernels": {"primary_ms_per_step": primary_ms / args.steps, "trace_ms_per_step": trace_ms / args.steps,
+                        "denoise_bilateral_ms": den_ms},
         }
         if not args.no_cpu_baseline and world == 1:
             run, rows, cores, _ = oracle_sample(wl, budget_s=15.0)

@@ -29,7 +29,13 @@
 
 namespace {
 
-constexpr int DN_BX = 32, DN_BY = 8;
+#ifndef DN_ROWS
+#define DN_ROWS 8     // CTA = 32 x DN_ROWS pixels
+#endif
+#ifndef DN_UNROLL
+#define DN_UNROLL 2   // taps per loop trip
+#endif
+constexpr int DN_BX = 32, DN_BY = DN_ROWS, DN_UNROLL_N = DN_UNROLL;
 
 struct DenoiseArgs {
     uint32_t W, H;
@@ -81,7 +87,7 @@ __global__ void __launch_bounds__(DN_BX* DN_BY)
         const float centreDist = __fdividef(A.nearPlane, centre.z);
         float zBuff = 0.0f;
         float3 aBuff = f3s(0.0f);
-#pragma unroll 2
+#pragma unroll DN_UNROLL_N
         for (int i = 0; i < A.ntaps; i++) {
             const float4 tp = __ldg(&taps[i]);  // d.x/size.x, d.y/size.y, blurFactor, d.y integral?
             const float x = (uvx + tp.x) * A.sizeX - 0.5f;
