@@ -93,6 +93,8 @@ typedef enum {
     MRT_BUF_SKY_VIEW = 9,        /* B10G11R11 192x108 (sky.ixx:187-188) */
     MRT_BUF_HIT_T = 10,          /* R32F 4 B/px primary hit distance (triangle scenes) */
     MRT_BUF_DENOISED = 11,       /* RGBA8 4 B/px (denoiser.ixx:56) output of mrt_denoise_bilateral */
+    MRT_BUF_BVH_NODES = 12,      /* the built wide BVH, for tests and tools: 80-byte nodes ... */
+    MRT_BUF_BVH_TRIS = 13,       /* ... and its triangles in leaf order, 3 x float4 each (v0.w = primitive id) */
     MRT_BUF_COUNT_
 } mrt_buffer_id;
 
@@ -147,6 +149,8 @@ const char* mrt_last_error(const mrt_context* ctx);
  *   "persistent_primary" 0/1  ... and for primary rays (default 0: coherent per-lane loop)
  *   "trace_ctas_per_sm" n     cap the persistent traversal grid at n CTAs per SM (0 = as many as fit), for
  *                             contexts that share a GPU
+ *   "build_device_loop" 0/1   PLOC rounds and collapse levels looped inside two cooperative kernels (default 1) or
+ *                             driven from the host with a readback per round (0); same tree either way; invalidates the BVH
  *   "builder" 0/1             hierarchy builder: 0 Karras LBVH, 1 PLOC (default); invalidates the BVH
  *   "ploc_radius" 1..32       PLOC search radius (default 6); invalidates the BVH */
 int mrt_set_option(mrt_context* ctx, const char* name, int64_t value);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libminotert.so")
 
 MISS_ID = 0xFFFFFFFF
 (BUF_VISIBILITY, BUF_DEPTH, BUF_NORMAL, BUF_MOTION, BUF_COLOR, BUF_ACCUM, BUF_LDR, BUF_TRANSMITTANCE,
- BUF_MULTISCATTERING, BUF_SKY_VIEW, BUF_HIT_T, BUF_DENOISED) = range(12)
+ BUF_MULTISCATTERING, BUF_SKY_VIEW, BUF_HIT_T, BUF_DENOISED, BUF_BVH_NODES, BUF_BVH_TRIS) = range(14)
 BUILD_FULL, BUILD_REFIT = 0, 1
 SECONDARY_ACCUMULATE, SECONDARY_SORT_RAYS = 1, 2
 TONEMAP = {"linear": 0, "reinhard": 1, "hable": 2, "aces": 3, "uchimura": 4, "amd": 5}
@@ -238,6 +238,8 @@ class Context:
             n = nbytes // (np.dtype(dt).itemsize * ch)
             w = self.size[0]
             shape = (n // w, w, ch) if ch > 1 else (n // w, w)
+        elif buf in (BUF_BVH_NODES, BUF_BVH_TRIS):
+            dt, shape = np.uint32, (nbytes // 4,)
         elif buf == BUF_SKY_VIEW:
             dt, shape = np.uint32, (108, 192)
         elif buf == BUF_TRANSMITTANCE:

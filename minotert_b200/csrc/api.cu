@@ -69,6 +69,8 @@ int buffer_info(mrt_context* ctx, int id, void** p, size_t* bytes) {
             ctx->sky_pending = false;
         }
         *p = ctx->view_packed.p; *bytes = (size_t)MRT_VIEW_W * MRT_VIEW_H * 4; return MRT_OK;
+    case MRT_BUF_BVH_NODES: if (ctx->scene_kind != 2 || !ctx->bvh_valid) break; *p = ctx->nodes.p; *bytes = (size_t)ctx->num_nodes * sizeof(WideNode); return MRT_OK;
+    case MRT_BUF_BVH_TRIS: if (ctx->scene_kind != 2 || !ctx->bvh_valid) break; *p = ctx->tris.p; *bytes = (size_t)ctx->num_leaf_tris * 48; return MRT_OK;
     case MRT_BUF_DENOISED: if (!ctx->have_denoised) break; *p = ctx->denoised.p; *bytes = n * 4; return MRT_OK;
     case MRT_BUF_HIT_T: if (!ctx->have_gbuffer || ctx->scene_kind != 2) break; *p = ctx->hit_t.p; *bytes = n * 4; return MRT_OK;
     default: return mrt_fail(ctx, MRT_ERR_INVALID, "unknown buffer id %d", id);
@@ -126,7 +128,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->bin_lo); dev_free(ctx->bin_hi); dev_free(ctx->bin_flag);
     dev_free(ctx->scene_bounds); dev_free(ctx->work_a); dev_free(ctx->work_b); dev_free(ctx->slot_node);
     dev_free(ctx->node_nchild); dev_free(ctx->node_ntri); dev_free(ctx->node_child_base); dev_free(ctx->node_tri_base);
-    dev_free(ctx->nodes); dev_free(ctx->tris); dev_free(ctx->counters);
+    dev_free(ctx->nodes); dev_free(ctx->tris); dev_free(ctx->counters); dev_free(ctx->loop_sums);
     dev_free(ctx->trans16); dev_free(ctx->multi16); dev_free(ctx->view_packed);
     dev_free(ctx->trans_f); dev_free(ctx->multi_f); dev_free(ctx->view_f);
     dev_free(ctx->visibility); dev_free(ctx->depth); dev_free(ctx->normal); dev_free(ctx->motion); dev_free(ctx->color16);
@@ -160,6 +162,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;
     else if (!strcmp(name, "trace_ctas_per_sm")) ctx->opt_trace_ctas_per_sm = (int)(value > 32 ? 32 : value);
+    else if (!strcmp(name, "build_device_loop")) { ctx->opt_build_device_loop = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "builder")) { ctx->opt_builder = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "ploc_radius")) { ctx->opt_ploc_radius = (int)(value < 1 ? 1 : (value > 32 ? 32 : value)); ctx->bvh_valid = false; }
     else return mrt_fail(ctx, MRT_ERR_INVALID, "unknown option '%s'", name);

@@ -11,9 +11,13 @@
 //      write 80-byte nodes and the triangles in node-leaf order          (k_emit_nodes)
 // Refit (animated scenes) reruns 1, 5 and 7 on the kept topology.
 // Every pass streams its arrays once: the build is HBM-bound (DESIGN.md lists bytes per triangle).
+#include <cooperative_groups.h>
+
 #include <utility>
 
 #include "context.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -189,11 +193,8 @@ __global__ void __launch_bounds__(256) k_ploc_init(uint32_t n, uint32_t* __restr
     parent[n - 1 + i] = -1;
 }
 
-__global__ void __launch_bounds__(256) k_ploc_nearest(const uint32_t* __restrict__ clusters, uint32_t m, int radius,
-                                                      const float4* __restrict__ lo, const float4* __restrict__ hi,
-                                                      uint32_t* __restrict__ nn) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+// nearest cluster of position i within +-radius positions (plain loads: the device-side loop mutates these arrays)
+MRT_D uint32_t ploc_nearest_one(const uint32_t* clusters, uint32_t m, int radius, const float4* lo, const float4* hi, uint32_t i) {
     uint32_t ci = clusters[i];
     float4 ilo = lo[ci], ihi = hi[ci];
     int j0 = max((int)i - radius, 0), j1 = min((int)i + radius, (int)m - 1);
@@ -214,7 +215,15 @@ __global__ void __launch_bounds__(256) k_ploc_nearest(const uint32_t* __restrict
         uint32_t key = (dist << 26) | ((lowpos & 1u) << 25) | (lowpos & 0x1FFFFFFu);
         if (a < best || (a == best && key < bkey)) { best = a; bj = (uint32_t)j; bkey = key; }
     }
-    nn[i] = bj;
+    return bj;
+}
+
+__global__ void __launch_bounds__(256) k_ploc_nearest(const uint32_t* __restrict__ clusters, uint32_t m, int radius,
+                                                      const float4* __restrict__ lo, const float4* __restrict__ hi,
+                                                      uint32_t* __restrict__ nn) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    nn[i] = ploc_nearest_one(clusters, m, radius, lo, hi, i);
 }
 
 // flags: create[i] = 1 if i is the left partner of a mutual pair; keep[i] = 0 if i is the right partner
@@ -270,6 +279,227 @@ __global__ void __launch_bounds__(256) k_leaf_boxes(const float4* __restrict__ p
     bin_hi[n - 1 + k] = prim_hi[prim];
 }
 
+// ---- PLOC with the round loop on the device ----
+// The host-driven loop above costs ~10 launches and one readback per round (40 rounds at 1 M triangles: 443
+// launches, 3.5 ms, of which the arithmetic is a few per cent).  k_ploc_loop runs every round inside ONE
+// cooperative launch: phases are separated by grid-wide barriers, the two stream compactions of a round
+// (surviving clusters, created nodes) are chunked scans -- each CTA owns a contiguous range of positions, publishes
+// its counts, and after the barrier sums the counts of the CTAs before it -- and once few clusters are left a
+// single CTA finishes the remaining rounds with CTA barriers only.  Node ids, child order and boxes are produced
+// by the same rules as the host-driven loop, so both build the same tree bit for bit (tested).
+#ifndef PLOC_CTAS_PER_SM
+#define PLOC_CTAS_PER_SM 8      // grid of the cooperative loops: more CTAs = more lanes per phase, slower grid barrier
+#endif
+#ifndef COLLAPSE_CTAS_PER_SM
+#define COLLAPSE_CTAS_PER_SM 8
+#endif
+#define PLOC_MAX_RADIUS 32      // mrt_set_option("ploc_radius") range
+#ifndef PLOC_TAIL
+#define PLOC_TAIL 256u  // clusters at which CTA 0 takes over (one position per thread)
+#endif
+
+struct PlocLoop {
+    uint32_t n;
+    int radius;
+    uint32_t* clusters[2];
+    uint32_t* nn;
+    int32_t *left, *right, *parent;
+    uint32_t* count;
+    float4 *lo, *hi;
+    uint2* block_sums;  // [gridDim.x]: (kept clusters, created nodes) of each CTA's range
+    uint32_t* result;   // [0] internal nodes created, [1] status (0 ok, 1 no progress), [2] rounds
+};
+
+// exclusive scan of one 32-bit value per thread over a 256-thread CTA (packed counters: two 16-bit fields)
+MRT_D uint32_t cta_scan_256(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t ws[8];
+    __shared__ uint32_t tot;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+        if (lane >= (unsigned)off) inc += t;
+    }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < 8 ? ws[lane] : 0u, winc = w;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, off);
+            if (lane >= (unsigned)off) winc += t;
+        }
+        if (lane < 8) ws[lane] = winc - w;
+        if (lane == 7) tot = winc;
+    }
+    __syncthreads();
+    const uint32_t r = ws[warp] + inc - v;
+    *total = tot;
+    __syncthreads();
+    return r;
+}
+// sum of (a, b) over the CTA, returned to every thread
+MRT_D uint2 cta_sum2_256(uint32_t a, uint32_t b) {
+    __shared__ uint2 ws[8];
+    __shared__ uint2 tot;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_down_sync(0xFFFFFFFFu, a, off);
+        b += __shfl_down_sync(0xFFFFFFFFu, b, off);
+    }
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = make_uint2(a, b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint2 t = make_uint2(0u, 0u);
+        for (int w = 0; w < 8; w++) { t.x += ws[w].x; t.y += ws[w].y; }
+        tot = t;
+    }
+    __syncthreads();
+    const uint2 r = tot;
+    __syncthreads();
+    return r;
+}
+
+// One PLOC round over positions [0, m).  nb CTAs take part (b = this CTA's index); SYNC is the barrier between
+// phases: the grid barrier, or __syncthreads when a single CTA runs the tail.  Returns (clusters kept, nodes created).
+template <class Sync>
+MRT_D uint2 ploc_round(const PlocLoop& A, uint32_t m, int cur, uint32_t next_node, uint32_t b, uint32_t nb, Sync sync) {
+    const uint32_t* C = A.clusters[cur];
+    uint32_t* Cout = A.clusters[cur ^ 1];
+    // phase 1: nearest neighbour of every position.  A CTA takes 256 consecutive positions at a time and stages
+    // the boxes of that window (+- radius) in shared memory: one gather per position instead of one per pair.
+    {
+        __shared__ float4 wlo[256 + 2 * PLOC_MAX_RADIUS], whi[256 + 2 * PLOC_MAX_RADIUS];
+        const int radius = A.radius;
+        for (uint32_t t0 = b * 256u; t0 < m; t0 += nb * 256u) {
+            const int w0 = (int)t0 - radius;                       // window = positions [w0, w0 + 256 + 2 radius)
+            for (int q = threadIdx.x; q < 256 + 2 * radius; q += 256) {
+                const int pos = w0 + q;
+                if (pos >= 0 && pos < (int)m) {
+                    const uint32_t c = C[pos];
+                    wlo[q] = A.lo[c];
+                    whi[q] = A.hi[c];
+                }
+            }
+            __syncthreads();
+            const uint32_t i = t0 + threadIdx.x;
+            if (i < m) {
+                const int qi = (int)threadIdx.x + radius;
+                const float4 ilo = wlo[qi], ihi = whi[qi];
+                const int j0 = max((int)i - radius, 0), j1 = min((int)i + radius, (int)m - 1);
+                float best = 3.0e38f;
+                uint32_t bj = i, bkey = 0xFFFFFFFFu;
+                for (int j = j0; j <= j1; j++) {  // same pair order and tie-break as ploc_nearest_one
+                    if (j == (int)i) continue;
+                    const float a = merged_area(ilo, ihi, wlo[j - w0], whi[j - w0]);
+                    const uint32_t dist = (uint32_t)abs(j - (int)i);
+                    const uint32_t lowpos = (uint32_t)min(j, (int)i);
+                    const uint32_t key = (dist << 26) | ((lowpos & 1u) << 25) | (lowpos & 0x1FFFFFFu);
+                    if (a < best || (a == best && key < bkey)) { best = a; bj = (uint32_t)j; bkey = key; }
+                }
+                A.nn[i] = bj;
+            }
+            __syncthreads();
+        }
+    }
+    sync();
+    // phase 2: counts of this CTA's range
+    const uint32_t chunk = (m + nb - 1) / nb;
+    const uint32_t r0 = min(m, b * chunk), r1 = min(m, r0 + chunk);
+    uint32_t keepc = 0, createc = 0;
+    for (uint32_t i = r0 + threadIdx.x; i < r1; i += 256u) {
+        const uint32_t j = A.nn[i];
+        const bool mutual = j != i && A.nn[j] == i;
+        keepc += (mutual && i > j) ? 0u : 1u;
+        createc += (mutual && i < j) ? 1u : 0u;
+    }
+    const uint2 mine = cta_sum2_256(keepc, createc);
+    if (threadIdx.x == 0) A.block_sums[b] = mine;
+    sync();
+    // phase 3: offsets of the range, then compaction + merges tile by tile
+    uint32_t kb = 0, cb = 0, kt = 0, ct = 0;
+    for (uint32_t q = threadIdx.x; q < nb; q += 256u) {
+        const uint2 sq = A.block_sums[q];
+        kt += sq.x; ct += sq.y;
+        if (q < b) { kb += sq.x; cb += sq.y; }
+    }
+    const uint2 before = cta_sum2_256(kb, cb), total = cta_sum2_256(kt, ct);
+    uint32_t keep_base = before.x, create_base = before.y;
+    const int nprims = (int)A.n;
+    for (uint32_t base = r0; base < r1; base += 256u) {
+        const uint32_t i = base + threadIdx.x;
+        const bool valid = i < r1;
+        uint32_t j = 0;
+        bool keep = false, create = false;
+        if (valid) {
+            j = A.nn[i];
+            const bool mutual = j != i && A.nn[j] == i;
+            keep = !(mutual && i > j);
+            create = mutual && i < j;
+        }
+        uint32_t tile_total;
+        const uint32_t ex = cta_scan_256((keep ? 1u : 0u) | (create ? 0x10000u : 0u), &tile_total);
+        if (keep) {
+            uint32_t c = C[i];
+            if (create) {
+                const uint32_t cj = C[j];
+                const uint32_t id = next_node + create_base + (ex >> 16);
+                const float4 alo = A.lo[c], ahi = A.hi[c], blo = A.lo[cj], bhi = A.hi[cj];
+                A.left[id] = (int32_t)c;
+                A.right[id] = (int32_t)cj;
+                A.parent[c] = (int32_t)id;
+                A.parent[cj] = (int32_t)id;
+                A.parent[id] = -1;
+                const uint32_t na = (int)c >= nprims - 1 ? 1u : A.count[c], nbb = (int)cj >= nprims - 1 ? 1u : A.count[cj];
+                A.count[id] = na + nbb;
+                A.lo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+                A.hi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+                c = id;
+            }
+            Cout[keep_base + (ex & 0xFFFFu)] = c;
+        }
+        keep_base += tile_total & 0xFFFFu;
+        create_base += tile_total >> 16;
+    }
+    sync();
+    return total;
+}
+
+__global__ void __launch_bounds__(256, 4) k_ploc_loop(PlocLoop A) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t nb = gridDim.x, b = blockIdx.x;
+    for (uint32_t i = b * 256u + threadIdx.x; i < A.n; i += nb * 256u) {  // k_ploc_init
+        A.clusters[0][i] = A.n - 1 + i;
+        A.parent[A.n - 1 + i] = -1;
+    }
+    grid.sync();
+    uint32_t m = A.n, next_node = 0, rounds = 0, status = 0;
+    int cur = 0;
+    while (m > PLOC_TAIL) {
+        const uint2 t = ploc_round(A, m, cur, next_node, b, nb, [&] { grid.sync(); });
+        rounds++;
+        if (t.y == 0 || t.x >= m) { status = 1; break; }  // every CTA sees the same totals
+        next_node += t.y;
+        m = t.x;
+        cur ^= 1;
+    }
+    if (b != 0) return;
+    while (status == 0 && m > 1) {
+        const uint2 t = ploc_round(A, m, cur, next_node, 0u, 1u, [] { __syncthreads(); });
+        rounds++;
+        if (t.y == 0 || t.x >= m) { status = 1; break; }
+        next_node += t.y;
+        m = t.x;
+        cur ^= 1;
+    }
+    if (threadIdx.x == 0) {
+        A.result[0] = next_node;
+        A.result[1] = status;
+        A.result[2] = rounds;
+    }
+}
+
 // ---- collapse to 8-wide ----
 // Binary tree over the Morton-sorted primitives, produced by either builder (Karras LBVH or PLOC):
 // internal nodes [0, n-1), leaf of sorted position k = node n-1+k.
@@ -307,14 +537,8 @@ MRT_D float bin_area(const BinTree& T, int b) {
     return dx * dy + dy * dz + dz * dx;
 }
 
-// One thread per wide node of the current level: choose its <= 8 slots.
-__global__ void __launch_bounds__(128) k_collapse_expand(BinTree T, const uint2* __restrict__ items, uint32_t count,
-                                                         int32_t* __restrict__ slot_node, uint32_t* __restrict__ node_nchild,
-                                                         uint32_t* __restrict__ node_ntri) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
-    int b = (int)items[k].x;
-    uint32_t w = items[k].y;
+// Choose the <= 8 slots of wide node w, which stands for binary node b.
+MRT_D void collapse_expand_one(const BinTree& T, int b, uint32_t w, int32_t* slot_node, uint32_t* node_nchild, uint32_t* node_ntri) {
     int slots[8];
     int ns;
     if (bin_is_leaf(T, b)) {
@@ -386,6 +610,125 @@ __global__ void __launch_bounds__(128) k_collapse_expand(BinTree T, const uint2*
     node_ntri[w] = ntri;
 }
 
+// The same choice made by EIGHT lanes per wide node (lane s of the group = slot s during the expansion, child s
+// during the slot assignment): the single-thread version above walks ~500 (child, slot) pairs and keeps its arrays
+// in local memory, 15-25 us of dependent work per thread and per level whatever the level's size.  Every pick
+// reproduces the serial scan order -- largest area / cost first, ties to the lowest slot, then the lowest child --
+// so both versions build the same node bit for bit (tested through build_device_loop 0 vs 1).
+// All 32 lanes of the warp call this together; groups without a node pass active = false.
+MRT_D void collapse_expand_group(const BinTree& T, bool active, int b, uint32_t w, int32_t* slot_node, uint32_t* node_nchild,
+                                 uint32_t* node_ntri) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int s = threadIdx.x & 7;
+    int slot = -1;      // binary node in slot s
+    int ns = 1;
+    if (bin_is_leaf(T, b)) {
+        if (s == 0) slot = b;
+    } else {
+        if (s == 0) slot = T.left[b];
+        if (s == 1) slot = T.right[b];
+        ns = 2;
+    }
+    // cached per lane: can this slot be opened, is it "big", its area
+    bool inner = false, big = false;
+    float area = 0.0f;
+    auto refresh = [&]() {
+        inner = slot >= 0 && !bin_is_leaf(T, slot);
+        big = inner && T.count[slot] > MRT_MAX_LEAF_TRIS;
+        area = inner ? bin_area(T, slot) : 0.0f;
+    };
+    refresh();
+    // phase 0: open the largest subtree that is too big to be a leaf; phase 1: spend spare slots on small leaves
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+        for (int it = 0; it < 6; it++) {
+            const bool eligible = inner && (phase == 0 ? big : !big);
+            float key = eligible ? area : -1.0f;
+            int who = s;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const float ok = __shfl_xor_sync(FULL, key, d, 8);
+                const int ow = __shfl_xor_sync(FULL, who, d, 8);
+                if (ok > key || (ok == key && ow < who)) { key = ok; who = ow; }
+            }
+            const bool open = key >= 0.0f && ns < 8;
+            if (!__any_sync(FULL, open)) break;  // no group of this warp can open a slot in this phase any more
+            // the chosen slot takes its left child, slot ns its right child
+            const int chosen = __shfl_sync(FULL, slot, who, 8);
+            if (open) {
+                if (s == who) { slot = T.left[chosen]; refresh(); }
+                else if (s == ns) { slot = T.right[chosen]; refresh(); }
+                ns++;
+            }
+        }
+    }
+    // octant-aware slot assignment: slot q lies towards (q&1 ? +x : -x, q&2 ? +y : -y, q&4 ? +z : -z) of the
+    // node centre, so that traversal priority (slot ^ ray octant) approximates front-to-back.  Lane s = child s.
+    const float4 nlo = T.lo[b], nhi = T.hi[b];
+    const float3 nc = f3(nlo.x + nhi.x, nlo.y + nhi.y, nlo.z + nhi.z);
+    float3 off = f3s(0.0f);
+    if (slot >= 0) {
+        const float4 lo = T.lo[slot], hi = T.hi[slot];
+        off = f3(lo.x + hi.x, lo.y + hi.y, lo.z + hi.z) - nc;
+    }
+    unsigned slot_done = 0;
+    bool child_done = slot < 0;
+    int my_slot = -1;
+#pragma unroll 1
+    for (int it = 0; it < 8; it++) {
+        float bestC = -3.0e38f;
+        int bs = -1;
+        if (!child_done) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (slot_done & (1u << q)) continue;
+                const float cost = ((q & 1) ? off.x : -off.x) + ((q & 2) ? off.y : -off.y) + ((q & 4) ? off.z : -off.z);
+                if (cost > bestC) { bestC = cost; bs = q; }
+            }
+        }
+        // first maximum in (child, slot) scan order: highest cost, then lowest child
+        float key = bs >= 0 ? bestC : -3.4e38f;
+        int who = bs >= 0 ? s : 8;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            const float ok = __shfl_xor_sync(FULL, key, d, 8);
+            const int ow = __shfl_xor_sync(FULL, who, d, 8);
+            if (ok > key || (ok == key && ow < who)) { key = ok; who = ow; }
+        }
+        if (!__any_sync(FULL, who < 8)) break;  // every child of every group is placed
+        const int win_slot = __shfl_sync(FULL, bs, who & 7, 8);
+        if (who < 8) {
+            if (s == who) { my_slot = win_slot; child_done = true; }
+            slot_done |= 1u << win_slot;
+        }
+    }
+    const uint32_t cnt = slot >= 0 ? bin_count(T, slot) : 0u;
+    const bool is_child = slot >= 0 && cnt > MRT_MAX_LEAF_TRIS;
+    uint32_t nchild = is_child ? 1u : 0u, ntri = (slot >= 0 && !is_child) ? cnt : 0u;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        nchild += __shfl_xor_sync(FULL, nchild, d, 8);
+        ntri += __shfl_xor_sync(FULL, ntri, d, 8);
+    }
+    if (!active) return;
+    if (slot >= 0 && my_slot >= 0) slot_node[(size_t)w * 8 + my_slot] = slot;
+    if (!(slot_done & (1u << s))) slot_node[(size_t)w * 8 + s] = -1;
+    if (s == 0) {
+        node_nchild[w] = nchild;
+        node_ntri[w] = ntri;
+    }
+}
+
+// One thread per wide node of the current level.
+__global__ void __launch_bounds__(128) k_collapse_expand(BinTree T, const uint2* __restrict__ items, uint32_t count,
+                                                         int32_t* __restrict__ slot_node, uint32_t* __restrict__ node_nchild,
+                                                         uint32_t* __restrict__ node_ntri) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    collapse_expand_one(T, (int)items[k].x, items[k].y, slot_node, node_nchild, node_ntri);
+}
+
 // child_off: exclusive scan of node_nchild over this level (indexed like node_nchild)
 __global__ void __launch_bounds__(128) k_collapse_emit(BinTree T, uint32_t level_start, uint32_t count, uint32_t next_start,
                                                        const int32_t* __restrict__ slot_node,
@@ -404,6 +747,105 @@ __global__ void __launch_bounds__(128) k_collapse_emit(BinTree T, uint32_t level
             next_items[base - next_start + rel] = make_uint2((uint32_t)c, base + rel);
             rel++;
         }
+    }
+}
+
+// ---- collapse with the level loop on the device ----
+// Same idea as k_ploc_loop: the host-driven loop launches 6 kernels and reads one counter back per level of the
+// wide tree; here all levels run inside one cooperative launch.  Per level: expand (one thread per node), grid
+// barrier, chunked scan of the child counts fused with the emission of the next level's work items, grid barrier.
+// After the last level the per-node triangle counts are scanned into node_tri_base the same way.
+struct CollapseLoop {
+    BinTree T;
+    uint2* items[2];          // work items (binary node, wide node) of the current / next level
+    int32_t* slot_node;
+    uint32_t *node_nchild, *node_ntri, *node_child_base, *node_tri_base;
+    uint32_t* block_sums;     // [gridDim.x]
+    uint32_t* result;         // [0] wide nodes, [1] status (0 ok, 1 node budget exceeded), [2] levels
+    uint32_t n;               // primitives = node budget
+};
+
+
+// exclusive scan of in[first .. first+count) across the grid; calls emit(index, exclusive prefix) for every element
+// and returns the total.  Two grid barriers (counts published, then consumed); block_sums is reused by the caller.
+template <class Emit>
+MRT_D uint32_t grid_scan_256(cg::grid_group& grid, const uint32_t* in, uint32_t first, uint32_t count, uint32_t* block_sums, Emit emit) {
+    const uint32_t nb = gridDim.x, b = blockIdx.x;
+    const uint32_t chunk = (count + nb - 1) / nb;
+    const uint32_t r0 = min(count, b * chunk), r1 = min(count, r0 + chunk);
+    uint32_t local = 0;
+    for (uint32_t k = r0 + threadIdx.x; k < r1; k += 256u) local += in[first + k];
+    const uint32_t mine = cta_sum2_256(local, 0u).x;
+    if (threadIdx.x == 0) block_sums[b] = mine;
+    grid.sync();
+    uint32_t before = 0, all = 0;
+    for (uint32_t q = threadIdx.x; q < nb; q += 256u) {
+        const uint32_t sq = block_sums[q];
+        all += sq;
+        if (q < b) before += sq;
+    }
+    const uint2 sums = cta_sum2_256(before, all);
+    uint32_t base = sums.x;
+    const uint32_t total = sums.y;
+    for (uint32_t t0 = r0; t0 < r1; t0 += 256u) {
+        const uint32_t k = t0 + threadIdx.x;
+        const uint32_t v = k < r1 ? in[first + k] : 0u;
+        uint32_t tile_total;
+        const uint32_t ex = cta_scan_256(v, &tile_total);
+        if (k < r1) emit(first + k, base + ex);
+        base += tile_total;
+    }
+    grid.sync();
+    return total;
+}
+
+__global__ void __launch_bounds__(256) k_collapse_loop(CollapseLoop A) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t gtid = blockIdx.x * 256u + threadIdx.x, gsize = gridDim.x * 256u;
+    uint32_t level_start = 0, level_count = 1, levels = 0, status = 0;
+    int cur = 0;
+    if (gtid == 0) A.items[0][0] = make_uint2((uint32_t)A.T.root, 0u);
+    grid.sync();
+    while (level_count > 0) {
+        if ((size_t)level_start + level_count > A.n) { status = 1; break; }
+        const uint2* items = A.items[cur];
+        uint2* next_items = A.items[cur ^ 1];
+        for (uint32_t k0 = (gtid >> 5) * 4u; k0 < level_count; k0 += (gsize >> 5) * 4u) {  // a warp takes 4 nodes, 8 lanes each
+            const uint32_t k = k0 + ((threadIdx.x & 31) >> 3);
+            const bool active = k < level_count;
+            const uint2 item = active ? items[k] : make_uint2((uint32_t)A.T.root, 0u);
+            collapse_expand_group(A.T, active, (int)item.x, item.y, A.slot_node, A.node_nchild, A.node_ntri);
+        }
+        grid.sync();
+        const uint32_t next_start = level_start + level_count;
+        // k_collapse_emit fused into the scan of the child counts
+        const uint32_t next_count = grid_scan_256(grid, A.node_nchild, level_start, level_count, A.block_sums,
+            [&](uint32_t w, uint32_t child_off) {
+                const uint32_t base = next_start + child_off;
+                A.node_child_base[w] = base;
+                uint32_t rel = 0;
+                for (int s = 0; s < 8; s++) {
+                    const int c = A.slot_node[(size_t)w * 8 + s];
+                    if (c < 0) continue;
+                    if (bin_count(A.T, c) > MRT_MAX_LEAF_TRIS) {
+                        next_items[base - next_start + rel] = make_uint2((uint32_t)c, base + rel);
+                        rel++;
+                    }
+                }
+            });
+        if ((size_t)next_start + next_count > A.n) { status = 1; break; }
+        level_start = next_start;
+        level_count = next_count;
+        cur ^= 1;
+        levels++;
+    }
+    uint32_t num_nodes = level_start;
+    if (status == 0)
+        grid_scan_256(grid, A.node_ntri, 0u, num_nodes, A.block_sums, [&](uint32_t w, uint32_t off) { A.node_tri_base[w] = off; });
+    if (gtid == 0) {
+        A.result[0] = num_nodes;
+        A.result[1] = status;
+        A.result[2] = levels;
     }
 }
 
@@ -576,9 +1018,33 @@ int build_ploc(mrt_context* ctx) {
     k_leaf_boxes<<<div_up(n, 256), 256, 0, ctx->stream>>>(ctx->prim_lo.p, ctx->prim_hi.p, ctx->order.p, n, ctx->bin_lo.p,
                                                           ctx->bin_hi.p);
     MRT_LAUNCHED(ctx);
+    uint32_t next_node = 0;
+    if (ctx->opt_build_device_loop) {
+        // every round inside one cooperative launch (k_ploc_loop); k_ploc_init is folded into it
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        MRT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ploc_loop, 256, 0));
+        if (per_sm < 1) return mrt_fail(ctx, MRT_ERR_CUDA, "k_ploc_loop does not fit on an SM");
+        unsigned grid = (unsigned)sms * (unsigned)min(per_sm, PLOC_CTAS_PER_SM);
+        grid = max(1u, min(grid, div_up(n, 256)));
+        MRT_TRY(dev_reserve(ctx, ctx->loop_sums, grid));
+        PlocLoop A;
+        A.n = n; A.radius = ctx->opt_ploc_radius;
+        A.clusters[0] = ctx->ploc_c[0].p; A.clusters[1] = ctx->ploc_c[1].p; A.nn = ctx->ploc_nn.p;
+        A.left = ctx->bin_left.p; A.right = ctx->bin_right.p; A.parent = ctx->bin_parent.p; A.count = ctx->bin_count.p;
+        A.lo = ctx->bin_lo.p; A.hi = ctx->bin_hi.p; A.block_sums = ctx->loop_sums.p; A.result = ctx->counters.p;
+        void* args[] = {&A};
+        MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_ploc_loop, dim3(grid), dim3(256), args, 0, ctx->stream));
+        MRT_LAUNCHED(ctx);
+        uint32_t res[3] = {0, 0, 0};
+        MRT_CUDA(ctx, cudaMemcpyAsync(res, ctx->counters.p, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
+        MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (res[1] != 0) return mrt_fail(ctx, MRT_ERR_INVALID, "PLOC made no progress (round %u)", res[2]);
+        next_node = res[0];
+    } else {
     k_ploc_init<<<div_up(n, 256), 256, 0, ctx->stream>>>(n, ctx->ploc_c[0].p, ctx->bin_parent.p);
     MRT_LAUNCHED(ctx);
-    uint32_t m = n, next_node = 0;
+    uint32_t m = n;
     int cur = 0;
     while (m > 1) {
         const unsigned g = div_up(m, 256);
@@ -601,6 +1067,7 @@ int build_ploc(mrt_context* ctx) {
         next_node += totals[1];
         m = totals[0];
         cur ^= 1;
+    }
     }
     if (next_node != n - 1) return mrt_fail(ctx, MRT_ERR_INVALID, "PLOC produced %u internal nodes for %u primitives", next_node, n);
     ctx->bin_root = (int)n - 2;
@@ -675,8 +1142,32 @@ int bvh_build_full(mrt_context* ctx) {
         MRT_TRY(climb_boxes(ctx));
     }
 
-    // 6: collapse, one level per iteration
+    // 6: collapse into 8-wide nodes, level by level; 7a: triangle ranges
     BinTree T = make_tree(ctx);
+    if (ctx->opt_build_device_loop) {
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        MRT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse_loop, 256, 0));
+        if (per_sm < 1) return mrt_fail(ctx, MRT_ERR_CUDA, "k_collapse_loop does not fit on an SM");
+        unsigned grid = (unsigned)sms * (unsigned)min(per_sm, COLLAPSE_CTAS_PER_SM);
+        grid = max(1u, min(grid, div_up(n, 32)));  // 8 lanes per wide node
+        MRT_TRY(dev_reserve(ctx, ctx->loop_sums, grid));
+        CollapseLoop A;
+        A.T = T;
+        A.items[0] = ctx->work_a.p; A.items[1] = ctx->work_b.p;
+        A.slot_node = ctx->slot_node.p; A.node_nchild = ctx->node_nchild.p; A.node_ntri = ctx->node_ntri.p;
+        A.node_child_base = ctx->node_child_base.p; A.node_tri_base = ctx->node_tri_base.p;
+        A.block_sums = reinterpret_cast<uint32_t*>(ctx->loop_sums.p); A.result = ctx->counters.p; A.n = n;
+        void* args[] = {&A};
+        MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_collapse_loop, dim3(grid), dim3(256), args, 0, ctx->stream));
+        MRT_LAUNCHED(ctx);
+        uint32_t res[3] = {0, 0, 0};
+        MRT_CUDA(ctx, cudaMemcpyAsync(res, ctx->counters.p, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
+        MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (res[1] != 0) return mrt_fail(ctx, MRT_ERR_INVALID, "wide BVH node budget exceeded");
+        ctx->num_nodes = res[0];
+        ctx->num_leaf_tris = n;
+    } else {
     uint2 root = make_uint2((uint32_t)ctx->bin_root /* n == 1: the single leaf is binary node n-1 = 0 */, 0u);
     MRT_CUDA(ctx, cudaMemcpyAsync(ctx->work_a.p, &root, sizeof root, cudaMemcpyHostToDevice, ctx->stream));
     uint32_t level_start = 0, level_count = 1;
@@ -708,9 +1199,10 @@ int bvh_build_full(mrt_context* ctx) {
     }
     ctx->num_nodes = level_start;
     ctx->num_leaf_tris = n;
-
-    // 7: triangle ranges + final nodes
     MRT_TRY(scan_exclusive_u32(ctx, ctx->node_ntri.p, ctx->node_tri_base.p, ctx->num_nodes));
+    }
+
+    // 7b: final nodes
     MRT_TRY(dev_reserve(ctx, ctx->nodes, ctx->num_nodes));
     MRT_TRY(dev_reserve(ctx, ctx->tris, 3 * (size_t)n));
     MRT_TRY(emit_nodes(ctx));

@@ -17,6 +17,15 @@
 #include "shading.cuh"
 #include "trace.cuh"
 
+// The two halves of the visit counters (primary / trace_rays: [0..3], bounce waves: [4..7]) are reset by their own
+// passes, and mrt_stats adds them up: a fresh allocation must start at zero or the half that has not run yet
+// reports garbage (seen as 4 phantom stack overflows in a context that had only called mrt_trace_rays).
+static int reserve_visit_counters(mrt_context* ctx) {
+    if (ctx->visit_counters.p) return MRT_OK;
+    MRT_TRY(dev_reserve(ctx, ctx->visit_counters, 8));
+    return mrt_check_cuda(ctx, cudaMemsetAsync(ctx->visit_counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream), "visit counters");
+}
+
 namespace {
 
 struct MeshFrame {
@@ -514,7 +523,7 @@ int mesh_primary(mrt_context* ctx) {
     MRT_TRY(dev_reserve(ctx, ctx->hit_t, ctx->npix));
     MRT_TRY(dev_reserve(ctx, ctx->hit0_pos, ctx->npix));
     MRT_TRY(dev_reserve(ctx, ctx->hit0_n, ctx->npix));
-    MRT_TRY(dev_reserve(ctx, ctx->visit_counters, 8));
+    MRT_TRY(reserve_visit_counters(ctx));
     MRT_TRY(dev_reserve(ctx, ctx->counters, 16));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p + 8, 0, sizeof(uint32_t), ctx->stream));
@@ -551,7 +560,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     }
     // [0, waves]: queue sizes; then per wave: work counter of the persistent launch, chunk counter of its shade stage
     MRT_TRY(dev_reserve(ctx, ctx->queue_counts, 3 * (size_t)waves + 3));
-    MRT_TRY(dev_reserve(ctx, ctx->visit_counters, 8));
+    MRT_TRY(reserve_visit_counters(ctx));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->queue_counts.p, 0, sizeof(uint32_t) * (3 * (size_t)waves + 3), ctx->stream));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
     ctx->num_queue_counts = waves + 1;
@@ -665,7 +674,7 @@ int mesh_trace_rays(mrt_context* ctx, const float* o, const float* d, uint32_t n
     MRT_CUDA(ctx, cudaMalloc(&d_ids, sizeof(uint32_t) * (size_t)n));
     MRT_CUDA(ctx, cudaMemcpyAsync(d_o, o, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     MRT_CUDA(ctx, cudaMemcpyAsync(d_d, d, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    MRT_TRY(dev_reserve(ctx, ctx->visit_counters, 8));
+    MRT_TRY(reserve_visit_counters(ctx));
     MRT_TRY(dev_reserve(ctx, ctx->counters, 16));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p + 8, 0, sizeof(uint32_t), ctx->stream));

@@ -492,3 +492,38 @@ def test_watertight_closed_mesh(gpu_ctx, oracle):
     for k in range(0, pos.shape[0], 97):   # vertex rays: up to six triangles tie, the lowest primitive id wins
         i, tt, _, _ = osc.closest_hit(o[k], d[k], use_bvh=False)
         assert i == ids[k] and np.float32(tt) == t[k]
+
+
+@pytest.mark.parametrize("builder", [0, 1], ids=["lbvh", "ploc"])
+@pytest.mark.parametrize("maker", ["cornell", "small_terrain", "hall_260k", "tiny", "soup"])
+def test_device_side_build_loops_give_the_same_tree(gpu_ctx, maker, builder):
+    """PLOC rounds and collapse levels looped inside cooperative kernels (default) vs driven from the host with
+    a readback per round: node ids come from the same scans, so nodes and leaf triangles are bit-identical.
+    hall_260k runs the grid-wide rounds (> 2048 clusters), the small scenes only the single-CTA tail."""
+    if maker == "tiny":
+        pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.5], [2, 0, 1], [2, 2, 1]], np.float32)
+        idx = np.array([[0, 1, 2], [1, 3, 2], [3, 4, 5]], np.uint32)
+        alb = np.full((3, 3), 0.5, np.float32)
+    elif maker == "soup":  # sizes over six decades, far from the origin: ties and near-degenerate boxes
+        rng = np.random.default_rng(12)
+        n = 20000
+        c = np.array([1.0e4, -2.0e4, 5.0e3], np.float32) + rng.uniform(-50, 50, (n, 3)).astype(np.float32)
+        size = (10.0 ** rng.uniform(-4, 2, (n, 1))).astype(np.float32)
+        pos = (c[:, None, :] + size[:, None, :] * rng.normal(size=(n, 3, 3)).astype(np.float32)).reshape(-1, 3).astype(np.float32)
+        idx = np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)
+        alb = np.full((n, 3), 0.5, np.float32)
+    else:
+        pos, idx, alb, _ = getattr(scenes, maker)()
+    gpu_ctx.set_option("builder", builder)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    trees = []
+    for device_loop in (0, 1, 1):
+        gpu_ctx.set_option("build_device_loop", device_loop)
+        gpu_ctx.build()
+        st = gpu_ctx.stats()
+        trees.append((gpu_ctx.readback(capi.BUF_BVH_NODES).copy(), gpu_ctx.readback(capi.BUF_BVH_TRIS).copy(), st.num_wide_nodes))
+    for nodes, tris, nn in trees[1:]:
+        assert nn == trees[0][2]
+        assert np.array_equal(nodes, trees[0][0])
+        assert np.array_equal(tris, trees[0][1])
+    assert trees[0][0].size == trees[0][2] * 20 and trees[0][1].size == idx.shape[0] * 12

@@ -1,0 +1,8 @@
+set +e
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_mesh.py -q -m gpu -x > gpurun_out/pytest_mesh.log 2>&1; echo "mesh tests rc=$?"
+tail -15 gpurun_out/pytest_mesh.log
+timeout 200 python tools/bench_build.py > gpurun_out/build.jsonl 2> gpurun_out/build.err; echo "build bench rc=$?"
+grep -v refit gpurun_out/build.jsonl | cut -c1-200; tail -3 gpurun_out/build.err
+for v in b2 b8 t1k t64; do echo $v; MINOTERT_LIB_DIR=$PWD/variants/$v timeout 100 python tools/bench_build.py --scenes scene_1m 2>/dev/null | grep '"device_loop": true' | cut -c1-170; done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/build_launches.csv python tools/bench_build.py --scenes scene_1m --repeat 1 > gpurun_out/ncu_build.log 2>&1
