@@ -287,15 +287,9 @@ __global__ void __launch_bounds__(256) k_leaf_boxes(const float4* __restrict__ p
 // its counts, and after the barrier sums the counts of the CTAs before it -- and once few clusters are left a
 // single CTA finishes the remaining rounds with CTA barriers only.  Node ids, child order and boxes are produced
 // by the same rules as the host-driven loop, so both build the same tree bit for bit (tested).
-#ifndef PLOC_CTAS_PER_SM
-#define PLOC_CTAS_PER_SM 8      // grid of the cooperative loops: more CTAs = more lanes per phase, slower grid barrier
-#endif
-#ifndef COLLAPSE_CTAS_PER_SM
-#define COLLAPSE_CTAS_PER_SM 8
-#endif
 #define PLOC_MAX_RADIUS 32      // mrt_set_option("ploc_radius") range
 #ifndef PLOC_TAIL
-#define PLOC_TAIL 256u  // clusters at which CTA 0 takes over (one position per thread)
+#define PLOC_TAIL LOOP_THREADS  // clusters at which CTA 0 takes over (one position per thread)
 #endif
 
 struct PlocLoop {
@@ -310,9 +304,26 @@ struct PlocLoop {
     uint32_t* result;   // [0] internal nodes created, [1] status (0 ok, 1 no progress), [2] rounds
 };
 
-// exclusive scan of one 32-bit value per thread over a 256-thread CTA (packed counters: two 16-bit fields)
-MRT_D uint32_t cta_scan_256(uint32_t v, uint32_t* total) {
-    __shared__ uint32_t ws[8];
+// CTA-wide helpers of the cooperative loops (LOOP_THREADS threads, one CTA per SM: the grid barrier costs one
+// atomic per CTA, so few fat CTAs synchronise faster than many thin ones -- 1184 CTAs of 256: ~6 us per barrier).
+#ifndef LOOP_THREADS
+#define LOOP_THREADS 1024
+#endif
+constexpr unsigned LOOP_WARPS = LOOP_THREADS / 32;
+
+// -DBUILD_PROFILE: thread 0 of CTA 0 prints the time between phase boundaries of the cooperative loops
+#ifdef BUILD_PROFILE
+MRT_D unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PROF_DECL unsigned long long prof_t = gtimer();
+#define PROF(label, a, b) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long n_ = gtimer(); printf("%s %u %u: %llu ns\n", label, (unsigned)(a), (unsigned)(b), n_ - prof_t); prof_t = n_; } } while (0)
+#else
+#define PROF_DECL
+#define PROF(label, a, b) do {} while (0)
+#endif
+
+// exclusive scan of one 32-bit value per thread (packed counters: two 16-bit fields); *total = CTA sum
+MRT_D uint32_t cta_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t ws[LOOP_WARPS];
     __shared__ uint32_t tot;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t inc = v;
@@ -324,14 +335,14 @@ MRT_D uint32_t cta_scan_256(uint32_t v, uint32_t* total) {
     if (lane == 31) ws[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = lane < 8 ? ws[lane] : 0u, winc = w;
+        uint32_t w = lane < LOOP_WARPS ? ws[lane] : 0u, winc = w;
 #pragma unroll
-        for (int off = 1; off < 8; off <<= 1) {
+        for (int off = 1; off < 32; off <<= 1) {
             uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, off);
             if (lane >= (unsigned)off) winc += t;
         }
-        if (lane < 8) ws[lane] = winc - w;
-        if (lane == 7) tot = winc;
+        if (lane < LOOP_WARPS) ws[lane] = winc - w;
+        if (lane == 31) tot = winc;
     }
     __syncthreads();
     const uint32_t r = ws[warp] + inc - v;
@@ -340,8 +351,8 @@ MRT_D uint32_t cta_scan_256(uint32_t v, uint32_t* total) {
     return r;
 }
 // sum of (a, b) over the CTA, returned to every thread
-MRT_D uint2 cta_sum2_256(uint32_t a, uint32_t b) {
-    __shared__ uint2 ws[8];
+MRT_D uint2 cta_sum2(uint32_t a, uint32_t b) {
+    __shared__ uint2 ws[LOOP_WARPS];
     __shared__ uint2 tot;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -350,10 +361,14 @@ MRT_D uint2 cta_sum2_256(uint32_t a, uint32_t b) {
     }
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = make_uint2(a, b);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint2 t = make_uint2(0u, 0u);
-        for (int w = 0; w < 8; w++) { t.x += ws[w].x; t.y += ws[w].y; }
-        tot = t;
+    if (threadIdx.x < 32) {
+        uint2 t = threadIdx.x < LOOP_WARPS ? ws[threadIdx.x] : make_uint2(0u, 0u);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            t.x += __shfl_down_sync(0xFFFFFFFFu, t.x, off);
+            t.y += __shfl_down_sync(0xFFFFFFFFu, t.y, off);
+        }
+        if (threadIdx.x == 0) tot = t;
     }
     __syncthreads();
     const uint2 r = tot;
@@ -364,17 +379,17 @@ MRT_D uint2 cta_sum2_256(uint32_t a, uint32_t b) {
 // One PLOC round over positions [0, m).  nb CTAs take part (b = this CTA's index); SYNC is the barrier between
 // phases: the grid barrier, or __syncthreads when a single CTA runs the tail.  Returns (clusters kept, nodes created).
 template <class Sync>
-MRT_D uint2 ploc_round(const PlocLoop& A, uint32_t m, int cur, uint32_t next_node, uint32_t b, uint32_t nb, Sync sync) {
+MRT_D uint2 ploc_round(const PlocLoop& A, uint32_t m, int cur, uint32_t next_node, uint32_t b, uint32_t nb, float4* wlo, float4* whi,
+                        Sync sync) {
     const uint32_t* C = A.clusters[cur];
     uint32_t* Cout = A.clusters[cur ^ 1];
-    // phase 1: nearest neighbour of every position.  A CTA takes 256 consecutive positions at a time and stages
+    // phase 1: nearest neighbour of every position.  A CTA takes LOOP_THREADS consecutive positions at a time and stages
     // the boxes of that window (+- radius) in shared memory: one gather per position instead of one per pair.
     {
-        __shared__ float4 wlo[256 + 2 * PLOC_MAX_RADIUS], whi[256 + 2 * PLOC_MAX_RADIUS];
         const int radius = A.radius;
-        for (uint32_t t0 = b * 256u; t0 < m; t0 += nb * 256u) {
-            const int w0 = (int)t0 - radius;                       // window = positions [w0, w0 + 256 + 2 radius)
-            for (int q = threadIdx.x; q < 256 + 2 * radius; q += 256) {
+        for (uint32_t t0 = b * LOOP_THREADS; t0 < m; t0 += nb * LOOP_THREADS) {
+            const int w0 = (int)t0 - radius;                       // window = positions [w0, w0 + LOOP_THREADS + 2 radius)
+            for (int q = threadIdx.x; q < LOOP_THREADS + 2 * radius; q += LOOP_THREADS) {
                 const int pos = w0 + q;
                 if (pos >= 0 && pos < (int)m) {
                     const uint32_t c = C[pos];
@@ -408,26 +423,26 @@ MRT_D uint2 ploc_round(const PlocLoop& A, uint32_t m, int cur, uint32_t next_nod
     const uint32_t chunk = (m + nb - 1) / nb;
     const uint32_t r0 = min(m, b * chunk), r1 = min(m, r0 + chunk);
     uint32_t keepc = 0, createc = 0;
-    for (uint32_t i = r0 + threadIdx.x; i < r1; i += 256u) {
+    for (uint32_t i = r0 + threadIdx.x; i < r1; i += LOOP_THREADS) {
         const uint32_t j = A.nn[i];
         const bool mutual = j != i && A.nn[j] == i;
         keepc += (mutual && i > j) ? 0u : 1u;
         createc += (mutual && i < j) ? 1u : 0u;
     }
-    const uint2 mine = cta_sum2_256(keepc, createc);
+    const uint2 mine = cta_sum2(keepc, createc);
     if (threadIdx.x == 0) A.block_sums[b] = mine;
     sync();
     // phase 3: offsets of the range, then compaction + merges tile by tile
     uint32_t kb = 0, cb = 0, kt = 0, ct = 0;
-    for (uint32_t q = threadIdx.x; q < nb; q += 256u) {
+    for (uint32_t q = threadIdx.x; q < nb; q += LOOP_THREADS) {
         const uint2 sq = A.block_sums[q];
         kt += sq.x; ct += sq.y;
         if (q < b) { kb += sq.x; cb += sq.y; }
     }
-    const uint2 before = cta_sum2_256(kb, cb), total = cta_sum2_256(kt, ct);
+    const uint2 before = cta_sum2(kb, cb), total = cta_sum2(kt, ct);
     uint32_t keep_base = before.x, create_base = before.y;
     const int nprims = (int)A.n;
-    for (uint32_t base = r0; base < r1; base += 256u) {
+    for (uint32_t base = r0; base < r1; base += LOOP_THREADS) {
         const uint32_t i = base + threadIdx.x;
         const bool valid = i < r1;
         uint32_t j = 0;
@@ -439,7 +454,7 @@ MRT_D uint2 ploc_round(const PlocLoop& A, uint32_t m, int cur, uint32_t next_nod
             create = mutual && i < j;
         }
         uint32_t tile_total;
-        const uint32_t ex = cta_scan_256((keep ? 1u : 0u) | (create ? 0x10000u : 0u), &tile_total);
+        const uint32_t ex = cta_scan((keep ? 1u : 0u) | (create ? 0x10000u : 0u), &tile_total);
         if (keep) {
             uint32_t c = C[i];
             if (create) {
@@ -466,18 +481,21 @@ MRT_D uint2 ploc_round(const PlocLoop& A, uint32_t m, int cur, uint32_t next_nod
     return total;
 }
 
-__global__ void __launch_bounds__(256, 4) k_ploc_loop(PlocLoop A) {
+__global__ void __launch_bounds__(LOOP_THREADS, 1) k_ploc_loop(PlocLoop A) {
+    __shared__ float4 wlo[LOOP_THREADS + 2 * PLOC_MAX_RADIUS], whi[LOOP_THREADS + 2 * PLOC_MAX_RADIUS];
     cg::grid_group grid = cg::this_grid();
     const uint32_t nb = gridDim.x, b = blockIdx.x;
-    for (uint32_t i = b * 256u + threadIdx.x; i < A.n; i += nb * 256u) {  // k_ploc_init
+    for (uint32_t i = b * LOOP_THREADS + threadIdx.x; i < A.n; i += nb * LOOP_THREADS) {  // k_ploc_init
         A.clusters[0][i] = A.n - 1 + i;
         A.parent[A.n - 1 + i] = -1;
     }
     grid.sync();
     uint32_t m = A.n, next_node = 0, rounds = 0, status = 0;
     int cur = 0;
-    while (m > PLOC_TAIL) {
-        const uint2 t = ploc_round(A, m, cur, next_node, b, nb, [&] { grid.sync(); });
+    PROF_DECL
+    while (m > (uint32_t)PLOC_TAIL) {
+        PROF("ploc grid round/m", rounds, m);
+        const uint2 t = ploc_round(A, m, cur, next_node, b, nb, wlo, whi, [&] { grid.sync(); });
         rounds++;
         if (t.y == 0 || t.x >= m) { status = 1; break; }  // every CTA sees the same totals
         next_node += t.y;
@@ -485,14 +503,16 @@ __global__ void __launch_bounds__(256, 4) k_ploc_loop(PlocLoop A) {
         cur ^= 1;
     }
     if (b != 0) return;
+    PROF("ploc grid done round/m", rounds, m);
     while (status == 0 && m > 1) {
-        const uint2 t = ploc_round(A, m, cur, next_node, 0u, 1u, [] { __syncthreads(); });
+        const uint2 t = ploc_round(A, m, cur, next_node, 0u, 1u, wlo, whi, [] { __syncthreads(); });
         rounds++;
         if (t.y == 0 || t.x >= m) { status = 1; break; }
         next_node += t.y;
         m = t.x;
         cur ^= 1;
     }
+    PROF("ploc tail done round/m", rounds, m);
     if (threadIdx.x == 0) {
         A.result[0] = next_node;
         A.result[1] = status;
@@ -769,29 +789,29 @@ struct CollapseLoop {
 // exclusive scan of in[first .. first+count) across the grid; calls emit(index, exclusive prefix) for every element
 // and returns the total.  Two grid barriers (counts published, then consumed); block_sums is reused by the caller.
 template <class Emit>
-MRT_D uint32_t grid_scan_256(cg::grid_group& grid, const uint32_t* in, uint32_t first, uint32_t count, uint32_t* block_sums, Emit emit) {
+MRT_D uint32_t grid_scan(cg::grid_group& grid, const uint32_t* in, uint32_t first, uint32_t count, uint32_t* block_sums, Emit emit) {
     const uint32_t nb = gridDim.x, b = blockIdx.x;
     const uint32_t chunk = (count + nb - 1) / nb;
     const uint32_t r0 = min(count, b * chunk), r1 = min(count, r0 + chunk);
     uint32_t local = 0;
-    for (uint32_t k = r0 + threadIdx.x; k < r1; k += 256u) local += in[first + k];
-    const uint32_t mine = cta_sum2_256(local, 0u).x;
+    for (uint32_t k = r0 + threadIdx.x; k < r1; k += LOOP_THREADS) local += in[first + k];
+    const uint32_t mine = cta_sum2(local, 0u).x;
     if (threadIdx.x == 0) block_sums[b] = mine;
     grid.sync();
     uint32_t before = 0, all = 0;
-    for (uint32_t q = threadIdx.x; q < nb; q += 256u) {
+    for (uint32_t q = threadIdx.x; q < nb; q += LOOP_THREADS) {
         const uint32_t sq = block_sums[q];
         all += sq;
         if (q < b) before += sq;
     }
-    const uint2 sums = cta_sum2_256(before, all);
+    const uint2 sums = cta_sum2(before, all);
     uint32_t base = sums.x;
     const uint32_t total = sums.y;
-    for (uint32_t t0 = r0; t0 < r1; t0 += 256u) {
+    for (uint32_t t0 = r0; t0 < r1; t0 += LOOP_THREADS) {
         const uint32_t k = t0 + threadIdx.x;
         const uint32_t v = k < r1 ? in[first + k] : 0u;
         uint32_t tile_total;
-        const uint32_t ex = cta_scan_256(v, &tile_total);
+        const uint32_t ex = cta_scan(v, &tile_total);
         if (k < r1) emit(first + k, base + ex);
         base += tile_total;
     }
@@ -799,11 +819,12 @@ MRT_D uint32_t grid_scan_256(cg::grid_group& grid, const uint32_t* in, uint32_t 
     return total;
 }
 
-__global__ void __launch_bounds__(256) k_collapse_loop(CollapseLoop A) {
+__global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop A) {
     cg::grid_group grid = cg::this_grid();
-    const uint32_t gtid = blockIdx.x * 256u + threadIdx.x, gsize = gridDim.x * 256u;
+    const uint32_t gtid = blockIdx.x * LOOP_THREADS + threadIdx.x, gsize = gridDim.x * LOOP_THREADS;
     uint32_t level_start = 0, level_count = 1, levels = 0, status = 0;
     int cur = 0;
+    PROF_DECL
     if (gtid == 0) A.items[0][0] = make_uint2((uint32_t)A.T.root, 0u);
     grid.sync();
     while (level_count > 0) {
@@ -816,10 +837,12 @@ __global__ void __launch_bounds__(256) k_collapse_loop(CollapseLoop A) {
             const uint2 item = active ? items[k] : make_uint2((uint32_t)A.T.root, 0u);
             collapse_expand_group(A.T, active, (int)item.x, item.y, A.slot_node, A.node_nchild, A.node_ntri);
         }
+        PROF("collapse expand(cta0) level/count", levels, level_count);
         grid.sync();
+        PROF("collapse expand-wait level/count", levels, level_count);
         const uint32_t next_start = level_start + level_count;
         // k_collapse_emit fused into the scan of the child counts
-        const uint32_t next_count = grid_scan_256(grid, A.node_nchild, level_start, level_count, A.block_sums,
+        const uint32_t next_count = grid_scan(grid, A.node_nchild, level_start, level_count, A.block_sums,
             [&](uint32_t w, uint32_t child_off) {
                 const uint32_t base = next_start + child_off;
                 A.node_child_base[w] = base;
@@ -833,6 +856,7 @@ __global__ void __launch_bounds__(256) k_collapse_loop(CollapseLoop A) {
                     }
                 }
             });
+        PROF("collapse scan+emit level/next", levels, next_count);
         if ((size_t)next_start + next_count > A.n) { status = 1; break; }
         level_start = next_start;
         level_count = next_count;
@@ -841,7 +865,7 @@ __global__ void __launch_bounds__(256) k_collapse_loop(CollapseLoop A) {
     }
     uint32_t num_nodes = level_start;
     if (status == 0)
-        grid_scan_256(grid, A.node_ntri, 0u, num_nodes, A.block_sums, [&](uint32_t w, uint32_t off) { A.node_tri_base[w] = off; });
+        grid_scan(grid, A.node_ntri, 0u, num_nodes, A.block_sums, [&](uint32_t w, uint32_t off) { A.node_tri_base[w] = off; });
     if (gtid == 0) {
         A.result[0] = num_nodes;
         A.result[1] = status;
@@ -1023,10 +1047,9 @@ int build_ploc(mrt_context* ctx) {
         // every round inside one cooperative launch (k_ploc_loop); k_ploc_init is folded into it
         int sms = 148, per_sm = 1;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        MRT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ploc_loop, 256, 0));
+        MRT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ploc_loop, LOOP_THREADS, 0));
         if (per_sm < 1) return mrt_fail(ctx, MRT_ERR_CUDA, "k_ploc_loop does not fit on an SM");
-        unsigned grid = (unsigned)sms * (unsigned)min(per_sm, PLOC_CTAS_PER_SM);
-        grid = max(1u, min(grid, div_up(n, 256)));
+        unsigned grid = max(1u, min((unsigned)sms, div_up(n, LOOP_THREADS)));  // one CTA per SM
         MRT_TRY(dev_reserve(ctx, ctx->loop_sums, grid));
         PlocLoop A;
         A.n = n; A.radius = ctx->opt_ploc_radius;
@@ -1034,7 +1057,7 @@ int build_ploc(mrt_context* ctx) {
         A.left = ctx->bin_left.p; A.right = ctx->bin_right.p; A.parent = ctx->bin_parent.p; A.count = ctx->bin_count.p;
         A.lo = ctx->bin_lo.p; A.hi = ctx->bin_hi.p; A.block_sums = ctx->loop_sums.p; A.result = ctx->counters.p;
         void* args[] = {&A};
-        MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_ploc_loop, dim3(grid), dim3(256), args, 0, ctx->stream));
+        MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_ploc_loop, dim3(grid), dim3(LOOP_THREADS), args, 0, ctx->stream));
         MRT_LAUNCHED(ctx);
         uint32_t res[3] = {0, 0, 0};
         MRT_CUDA(ctx, cudaMemcpyAsync(res, ctx->counters.p, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1147,10 +1170,9 @@ int bvh_build_full(mrt_context* ctx) {
     if (ctx->opt_build_device_loop) {
         int sms = 148, per_sm = 1;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        MRT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse_loop, 256, 0));
+        MRT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse_loop, LOOP_THREADS, 0));
         if (per_sm < 1) return mrt_fail(ctx, MRT_ERR_CUDA, "k_collapse_loop does not fit on an SM");
-        unsigned grid = (unsigned)sms * (unsigned)min(per_sm, COLLAPSE_CTAS_PER_SM);
-        grid = max(1u, min(grid, div_up(n, 32)));  // 8 lanes per wide node
+        unsigned grid = max(1u, min((unsigned)sms, div_up(n, LOOP_THREADS / 8)));  // one CTA per SM, 8 lanes per wide node
         MRT_TRY(dev_reserve(ctx, ctx->loop_sums, grid));
         CollapseLoop A;
         A.T = T;
@@ -1159,7 +1181,7 @@ int bvh_build_full(mrt_context* ctx) {
         A.node_child_base = ctx->node_child_base.p; A.node_tri_base = ctx->node_tri_base.p;
         A.block_sums = reinterpret_cast<uint32_t*>(ctx->loop_sums.p); A.result = ctx->counters.p; A.n = n;
         void* args[] = {&A};
-        MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_collapse_loop, dim3(grid), dim3(256), args, 0, ctx->stream));
+        MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_collapse_loop, dim3(grid), dim3(LOOP_THREADS), args, 0, ctx->stream));
         MRT_LAUNCHED(ctx);
         uint32_t res[3] = {0, 0, 0};
         MRT_CUDA(ctx, cudaMemcpyAsync(res, ctx->counters.p, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
