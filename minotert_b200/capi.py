@@ -62,7 +62,7 @@ EXPORTS = [
     "mrt_atmosphere", "mrt_sky_view", "mrt_set_partition", "mrt_partition_rows", "mrt_primary_rays",
     "mrt_secondary_rays", "mrt_tonemap", "mrt_buffer", "mrt_readback", "mrt_sync", "mrt_stats_get",
     "mrt_stats_reset", "mrt_stream", "mrt_trace_rays", "mrt_partition_rows_for", "mrt_readback_async",
-    "mrt_readback_wait", "mrt_denoise_bilateral",
+    "mrt_readback_wait", "mrt_denoise_bilateral", "mrt_scene_share",
 ]
 
 
@@ -95,6 +95,7 @@ def load():
     L.mrt_scene_upload_mesh.argtypes = [vp, vp, u32, vp, u32, vp]
     L.mrt_scene_update_positions.argtypes = [vp, vp, u32]
     L.mrt_scene_build.argtypes = [vp, C.c_int]
+    L.mrt_scene_share.argtypes = [vp, vp]
     L.mrt_atmosphere.argtypes = [vp, vp]
     L.mrt_sky_view.argtypes = [vp, f32p, f32p, f32p]
     L.mrt_set_partition.argtypes = [vp, u32, u32, u32]
@@ -189,6 +190,10 @@ class Context:
 
     def build(self, mode=BUILD_FULL):
         self._ck(self.L.mrt_scene_build(self.h, mode))
+
+    def share_scene(self, owner):
+        """Render the mesh scene (triangles + built BVH) that `owner` holds (mrt_scene_share: frames in flight)."""
+        self._ck(self.L.mrt_scene_share(self.h, owner.h))
 
     def atmosphere(self, params):
         self._ck(self.L.mrt_atmosphere(self.h, C.cast(C.byref(params), C.c_void_p)))

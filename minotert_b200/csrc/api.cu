@@ -80,6 +80,16 @@ int buffer_info(mrt_context* ctx, int id, void** p, size_t* bytes) {
 
 }  // namespace
 
+// a context that renders another context's scene (mrt_scene_share) forgets the borrowed arrays instead of freeing them
+static void scene_unborrow(mrt_context* ctx) {
+    if (!ctx->scene_borrowed) return;
+    ctx->pos = {}; ctx->idx = {}; ctx->albedo = {}; ctx->nodes = {}; ctx->tris = {};
+    ctx->nverts = ctx->ntris = ctx->num_nodes = ctx->num_leaf_tris = 0;
+    ctx->scene_borrowed = false;
+    ctx->bvh_valid = false;
+    ctx->scene_kind = 0;
+}
+
 extern "C" {
 
 int mrt_abi_version(void) { return MRT_ABI_VERSION; }
@@ -119,6 +129,7 @@ void mrt_destroy(mrt_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->bn) cudaFree(ctx->bn);
+    scene_unborrow(ctx);
     dev_free(ctx->pos); dev_free(ctx->idx); dev_free(ctx->albedo);
     dev_free(ctx->prim_lo); dev_free(ctx->prim_hi); dev_free(ctx->keys); dev_free(ctx->keys_alt);
     dev_free(ctx->order); dev_free(ctx->order_alt); dev_free(ctx->hist); dev_free(ctx->scan_tmp);
@@ -200,6 +211,7 @@ int mrt_scene_upload_mesh(mrt_context* ctx, const float* positions, uint32_t nve
         return mrt_fail(ctx, MRT_ERR_INVALID, "mesh: NULL array with ntris = %u", ntris);
     for (size_t i = 0; i < 3 * (size_t)ntris; i++)
         if (indices[i] >= nverts) return mrt_fail(ctx, MRT_ERR_INVALID, "mesh: index %u out of range at %zu", indices[i], i);
+    if (ctx->scene_borrowed) { cudaStreamSynchronize(ctx->stream); scene_unborrow(ctx); }
     MRT_TRY(dev_reserve(ctx, ctx->pos, 3 * (size_t)nverts));
     MRT_TRY(dev_reserve(ctx, ctx->idx, 3 * (size_t)ntris));
     MRT_TRY(dev_reserve(ctx, ctx->albedo, ntris));
@@ -222,6 +234,7 @@ int mrt_scene_upload_mesh(mrt_context* ctx, const float* positions, uint32_t nve
 int mrt_scene_update_positions(mrt_context* ctx, const float* positions, uint32_t nverts) {
     MRT_ENTER(ctx);
     if (ctx->scene_kind != 2) return mrt_fail(ctx, MRT_ERR_STATE, "no mesh uploaded");
+    if (ctx->scene_borrowed) return mrt_fail(ctx, MRT_ERR_STATE, "the scene is borrowed (mrt_scene_share): update it through its owner");
     if (nverts != ctx->nverts || !positions) return mrt_fail(ctx, MRT_ERR_INVALID, "vertex count mismatch (%u vs %u)", nverts, ctx->nverts);
     MRT_CUDA(ctx, cudaMemcpyAsync(ctx->pos.p, positions, sizeof(float) * 3 * (size_t)nverts, cudaMemcpyHostToDevice, ctx->stream));
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -231,9 +244,38 @@ int mrt_scene_update_positions(mrt_context* ctx, const float* positions, uint32_
 int mrt_scene_build(mrt_context* ctx, int build_mode) {
     MRT_ENTER(ctx);
     if (ctx->scene_kind != 2) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_scene_build: no mesh uploaded");
+    if (ctx->scene_borrowed) return mrt_fail(ctx, MRT_ERR_STATE, "the scene is borrowed (mrt_scene_share): build it through its owner");
     if (build_mode == MRT_BUILD_REFIT) return bvh_refit(ctx);
     if (build_mode != MRT_BUILD_FULL) return mrt_fail(ctx, MRT_ERR_INVALID, "unknown build mode %d", build_mode);
     return bvh_build_full(ctx);
+}
+
+int mrt_scene_share(mrt_context* ctx, mrt_context* owner) {
+    MRT_ENTER(ctx);
+    if (!owner || owner == ctx) return mrt_fail(ctx, MRT_ERR_INVALID, "mrt_scene_share: owner is NULL or the context itself");
+    if (owner->device != ctx->device) return mrt_fail(ctx, MRT_ERR_INVALID, "mrt_scene_share: contexts live on devices %d and %d", ctx->device, owner->device);
+    if (owner->scene_borrowed) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_scene_share: the owner borrows its scene itself");
+    if (owner->scene_kind != 2 || !owner->bvh_valid) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_scene_share: the owner has no built mesh scene");
+    MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // frames of this context that still read the old scene
+    if (ctx->scene_borrowed) scene_unborrow(ctx);
+    else { dev_free(ctx->pos); dev_free(ctx->idx); dev_free(ctx->albedo); dev_free(ctx->nodes); dev_free(ctx->tris); }
+    ctx->pos = owner->pos; ctx->idx = owner->idx; ctx->albedo = owner->albedo; ctx->nodes = owner->nodes; ctx->tris = owner->tris;
+    ctx->nverts = owner->nverts; ctx->ntris = owner->ntris;
+    ctx->num_nodes = owner->num_nodes; ctx->num_leaf_tris = owner->num_leaf_tris;
+    ctx->stats.num_triangles = owner->stats.num_triangles; ctx->stats.num_wide_nodes = owner->stats.num_wide_nodes;
+    ctx->stats.bvh_bytes = owner->stats.bvh_bytes;
+    ctx->stats.sah_node_cost = owner->stats.sah_node_cost; ctx->stats.sah_tri_cost = owner->stats.sah_tri_cost;
+    ctx->scene_borrowed = true;
+    ctx->scene_kind = 2;
+    ctx->bvh_valid = true;
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;
+    // builds and refits already queued on the owner's stream come first
+    cudaEvent_t built;
+    MRT_CUDA(ctx, cudaEventCreateWithFlags(&built, cudaEventDisableTiming));
+    cudaEventRecord(built, owner->stream);
+    cudaStreamWaitEvent(ctx->stream, built, 0);
+    cudaEventDestroy(built);
+    return MRT_OK;
 }
 
 // the main stream waits for a sky view still being generated on the side stream

@@ -86,6 +86,7 @@ struct mrt_context {
     DevArray<float4> albedo;  // per primitive, rgb_
     uint32_t nverts = 0, ntris = 0;
     bool bvh_valid = false;
+    bool scene_borrowed = false;  // pos/idx/albedo/nodes/tris alias another context's arrays (mrt_scene_share): never freed here
 
     // LBVH build scratch + result (bvh_build.cu)
     DevArray<float4> prim_lo, prim_hi;      // per primitive AABB

@@ -47,6 +47,13 @@ def load():
         getattr(L, n).restype = None
     L.minote_app_create.argtypes = [C.c_int, u32, u32, vp, u32, u32]
     L.minote_app_create.restype = vp
+    L.minote_app_create_in_flight.argtypes = [C.c_int, C.c_int, u32, u32, vp, u32, u32]
+    L.minote_app_create_in_flight.restype = vp
+    L.minote_app_frame_context.argtypes = [vp, C.c_int]
+    L.minote_app_frame_context.restype = vp
+    L.minote_app_frames_in_flight.argtypes = [vp]
+    L.minote_app_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.minote_app_stats_reset.argtypes = [vp]
     L.minote_app_destroy.argtypes = [vp]
     L.minote_app_error.argtypes = [vp]
     L.minote_app_error.restype = C.c_char_p
@@ -110,10 +117,13 @@ def freecam_update(cam, frame_time, up=False, down=False, left=False, right=Fals
 class Renderer:
     """Cuda::Provider + Renderer::Provider and the per-frame Renderer::serv->draw(camera) call."""
 
-    def __init__(self, width, height, blue_noise_rgba8, device=0):
+    def __init__(self, width, height, blue_noise_rgba8, device=0, frames_in_flight=1):
+        """frames_in_flight: 1..3 frame contexts draw() rotates through (the reference keeps 3, renderer.ixx:36); the
+        scene lives in frame context 0 and is borrowed by the others (mrt_scene_share)."""
         self.L = load()
         bn = np.ascontiguousarray(blue_noise_rgba8, np.uint8)
-        self.h = self.L.minote_app_create(device, width, height, bn.ctypes.data_as(C.c_void_p), bn.shape[1], bn.shape[0])
+        self.h = self.L.minote_app_create_in_flight(device, frames_in_flight, width, height, bn.ctypes.data_as(C.c_void_p),
+                                                    bn.shape[1], bn.shape[0])
         if not self.h:
             raise capi.MinoteError("Renderer: " + self.L.minote_app_error(None).decode())
         self.size = (width, height)
@@ -187,11 +197,25 @@ class Renderer:
     def frame_count(self):
         return self.L.minote_app_frame_count(self.h)
 
-    def context(self):
-        """Borrowed capi-level view of the renderer's mrt_context (buffers, stream, options)."""
+    def frames_in_flight(self):
+        return self.L.minote_app_frames_in_flight(self.h)
+
+    def set_option(self, name, value):
+        """mrt_set_option on every frame context."""
+        self._ck(self.L.minote_app_set_option(self.h, name.encode(), int(value)))
+
+    def stats_reset(self):
+        self._ck(self.L.minote_app_stats_reset(self.h))
+
+    def context(self, frame=0):
+        """Borrowed capi-level view of one of the renderer's mrt_contexts (buffers, stream, options): frame context
+        `frame` (0 owns the scene; the only one with one frame in flight), or the one the last draw() recorded into
+        (frame=-1)."""
         ctx = capi.Context.__new__(capi.Context)
         ctx.L = capi.load()
-        ctx.h = C.c_void_p(self.L.minote_app_context(self.h))
+        ctx.h = C.c_void_p(self.L.minote_app_context(self.h) if frame == 0 else self.L.minote_app_frame_context(self.h, frame))
+        if not ctx.h:
+            raise capi.MinoteError(f"Renderer: no frame context {frame}")
         ctx.device = 0
         ctx.size = self.size
         ctx.close = lambda: None  # not owned

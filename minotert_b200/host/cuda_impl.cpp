@@ -6,13 +6,22 @@ module;
 #include "../../include/minotert.h"
 module minote.cuda;
 
-Cuda_impl::Cuda_impl(int device) {
-    if (int s = mrt_create(device, &ctx); s != MRT_OK)
-        throw std::runtime_error(std::string("mrt_create failed: ") + mrt_last_error(nullptr));
+Cuda_impl::Cuda_impl(int device, int framesInFlight) {
+    if (framesInFlight < 1 || framesInFlight > MaxFramesInFlight)
+        throw std::logic_error("frames in flight must be 1.." + std::to_string(MaxFramesInFlight));
+    for (int i = 0; i < framesInFlight; i++) {
+        if (int s = mrt_create(device, &frameCtx[i]); s != MRT_OK) {
+            std::string const why = mrt_last_error(nullptr);
+            for (int k = i - 1; k >= 0; k--) mrt_destroy(frameCtx[k]);
+            throw std::runtime_error("mrt_create failed: " + why);
+        }
+    }
+    inFlight = framesInFlight;
+    ctx = frameCtx[0];
 }
 
-void Cuda_impl::fail(int status) const {
-    throw std::runtime_error(std::string("minotert: ") + mrt_last_error(ctx) + " (status " + std::to_string(status) + ")");
+void Cuda_impl::fail(int status, mrt_context* on) const {
+    throw std::runtime_error(std::string("minotert: ") + mrt_last_error(on) + " (status " + std::to_string(status) + ")");
 }
 
 void Cuda_impl::raise(char const* message) const { throw std::logic_error(message); }

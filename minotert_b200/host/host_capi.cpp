@@ -88,10 +88,11 @@ void minote_freecam_update(Camera* cam, std::uint32_t keys, float cursor_dx, flo
 }
 
 // ---- renderer ----
-void* minote_app_create(int device, std::uint32_t w, std::uint32_t h, std::uint8_t const* blue_noise, std::uint32_t bn_w,
-                        std::uint32_t bn_h) {
+// frames_in_flight: 1..3 frame contexts that draw() rotates through (the reference: 3, renderer.ixx:36)
+void* minote_app_create_in_flight(int device, int frames_in_flight, std::uint32_t w, std::uint32_t h, std::uint8_t const* blue_noise,
+                                  std::uint32_t bn_w, std::uint32_t bn_h) {
     App* app = new App();
-    int s = guarded(nullptr, [&] { app->cuda = new Cuda::Provider(device); });
+    int s = guarded(nullptr, [&] { app->cuda = new Cuda::Provider(device, frames_in_flight); });
     if (s == 0) s = guarded(nullptr, [&] { app->renderer = new Renderer::Provider(uvec2{w, h}, blue_noise, uvec2{bn_w, bn_h}); });
     if (s != 0) {
         delete app->cuda;
@@ -99,6 +100,10 @@ void* minote_app_create(int device, std::uint32_t w, std::uint32_t h, std::uint8
         return nullptr;
     }
     return app;
+}
+void* minote_app_create(int device, std::uint32_t w, std::uint32_t h, std::uint8_t const* blue_noise, std::uint32_t bn_w,
+                        std::uint32_t bn_h) {
+    return minote_app_create_in_flight(device, 1, w, h, blue_noise, bn_w, bn_h);
 }
 void minote_app_destroy(void* a) {
     auto* app = static_cast<App*>(a);
@@ -108,7 +113,23 @@ void minote_app_destroy(void* a) {
     delete app;
 }
 char const* minote_app_error(void* a) { return a ? static_cast<App*>(a)->error : g_error; }
-mrt_context* minote_app_context(void* a) { (void)a; return Cuda::serv ? Cuda::serv->ctx : nullptr; }
+// frame context 0: owns the scene; with one frame in flight it is also the context of every frame
+mrt_context* minote_app_context(void* a) { (void)a; return Cuda::serv ? Cuda::serv->owner() : nullptr; }
+// the context the last draw() recorded into (index < 0) or frame context `index`
+mrt_context* minote_app_frame_context(void* a, int index) {
+    (void)a;
+    if (!Cuda::serv) return nullptr;
+    if (index < 0) return Cuda::serv->ctx;
+    return index < Cuda::serv->framesInFlight() ? Cuda::serv->frameContext(index) : nullptr;
+}
+int minote_app_frames_in_flight(void* a) { (void)a; return Cuda::serv ? Cuda::serv->framesInFlight() : 0; }
+// mrt_set_option on every frame context
+int minote_app_set_option(void* a, char const* name, std::int64_t value) {
+    return guarded(static_cast<App*>(a), [&] { Renderer::serv->setOption(name, value); });
+}
+int minote_app_stats_reset(void* a) {
+    return guarded(static_cast<App*>(a), [&] { Renderer::serv->resetStats(); });
+}
 
 int minote_app_set_spheres(void* a, mrt_sphere const* s, std::uint32_t n) {
     return guarded(static_cast<App*>(a), [&] { Renderer::serv->setSpheres(s, n); });

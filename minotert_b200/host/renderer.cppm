@@ -22,37 +22,49 @@ export class Renderer_impl : Cuda {
 public:
     // blue noise: decoded RGBA8 pixels of assets/blue_noise.png (renderer.ixx:101-110)
     Renderer_impl(uvec2 outputSize, std::uint8_t const* blueNoiseRgba8, uvec2 blueNoiseSize) : outputSize(outputSize) {
-        Cuda::serv->check(mrt_upload_blue_noise(Cuda::serv->ctx, blueNoiseRgba8, blueNoiseSize.x(), blueNoiseSize.y()));
+        forEachFrame([&](mrt_context* c) { return mrt_upload_blue_noise(c, blueNoiseRgba8, blueNoiseSize.x(), blueNoiseSize.y()); });
         blueNoise.id = 0;
     }
-    ~Renderer_impl() { delete atmosphere; }
+    ~Renderer_impl() {
+        for (auto* a : atmosphere) delete a;
+    }
     Renderer_impl(Renderer_impl const&) = delete;
     auto operator=(Renderer_impl const&) -> Renderer_impl& = delete;
 
     // scene selection (the reference compiles its scene into the shader, src/gpu/scene.glsl)
-    void setSpheres(mrt_sphere const* spheres, u32 n) { Cuda::serv->check(mrt_scene_set_spheres(Cuda::serv->ctx, spheres, n)); }
+    // and keeps one copy of it for all frames in flight: frame context 0 owns triangles + BVH, the others borrow them
+    void setSpheres(mrt_sphere const* spheres, u32 n) {
+        forEachFrame([&](mrt_context* c) { return mrt_scene_set_spheres(c, spheres, n); });
+    }
     void setMesh(float const* positions, u32 nverts, std::uint32_t const* indices, u32 ntris, float const* albedo) {
-        Cuda::serv->check(mrt_scene_upload_mesh(Cuda::serv->ctx, positions, nverts, indices, ntris, albedo));
-        Cuda::serv->check(mrt_scene_build(Cuda::serv->ctx, MRT_BUILD_FULL));
+        auto* const owner = Cuda::serv->owner();
+        waitBorrowers();
+        Cuda::serv->checkOn(owner, mrt_scene_upload_mesh(owner, positions, nverts, indices, ntris, albedo));
+        Cuda::serv->checkOn(owner, mrt_scene_build(owner, MRT_BUILD_FULL));
+        shareScene();
     }
     void updateMesh(float const* positions, u32 nverts, bool refit) {
-        Cuda::serv->check(mrt_scene_update_positions(Cuda::serv->ctx, positions, nverts));
-        Cuda::serv->check(mrt_scene_build(Cuda::serv->ctx, refit ? MRT_BUILD_REFIT : MRT_BUILD_FULL));
+        auto* const owner = Cuda::serv->owner();
+        waitBorrowers();  // frames in flight still read the nodes a refit rewrites in place
+        Cuda::serv->checkOn(owner, mrt_scene_update_positions(owner, positions, nverts));
+        Cuda::serv->checkOn(owner, mrt_scene_build(owner, refit ? MRT_BUILD_REFIT : MRT_BUILD_FULL));
+        shareScene();
     }
 
     void draw(Camera const& camera) {
-        // Begin the frame
-        Cuda::serv->nextFrame();
+        // Begin the frame: the next frame context (a progressive accumulator lives in one context, so it stays put)
+        Cuda::serv->nextFrame(!pathtracer.accumulate);
         // Initial temporal resource values
         if (Cuda::serv->frameCount() == 1) prevCamera = camera;
 
         // transmittance / multi-scattering depend only on the (constant) parameters: the reference
-        // rebuilds them every frame (renderer.ixx:56), here once per parameter set
-        if (!atmosphere) atmosphere = new Atmosphere(Atmosphere::Params::earth());
+        // rebuilds them every frame (renderer.ixx:56), here once per parameter set and frame context
+        auto*& atmo = atmosphere[Cuda::serv->frameSlot()];
+        if (!atmo) atmo = new Atmosphere(Atmosphere::Params::earth());
         auto sky = Sky();
-        auto skyView = sky.createView(*atmosphere, camera.position);
+        auto skyView = sky.createView(*atmo, camera.position);
         auto gbuffer = pathtracer.primaryRays(outputSize, camera, prevCamera);
-        auto pathtraced = pathtracer.secondaryRays(gbuffer, camera, *atmosphere, skyView, blueNoise);
+        auto pathtraced = pathtracer.secondaryRays(gbuffer, camera, *atmo, skyView, blueNoise);
         auto filtered = denoise(pathtraced, gbuffer.depth, gbuffer.normal, camera);
         framebuffer = tonemap(filtered);
 
@@ -64,11 +76,33 @@ public:
     void readFramebuffer(void* host, std::size_t bytes) const { framebuffer.readback(host, bytes); }
     // frames in flight (renderer.ixx:36): start copying this frame out while the next draw() is issued
     void readFramebufferAsync(void* host, std::size_t bytes) const { framebuffer.readbackAsync(host, bytes); }
-    void waitFramebuffer(int framesInFlight = 0) const { Cuda::serv->check(mrt_readback_wait(Cuda::serv->ctx, framesInFlight)); }
+    // returns once all but the `framesInFlight` most recent frames have landed in host memory
+    void waitFramebuffer(int framesInFlight = 0) const {
+        int const n = Cuda::serv->framesInFlight(), cur = Cuda::serv->frameSlot();
+        for (int back = 0; back < n; back++) {  // back = 0: the context of the newest frame
+            auto* const c = Cuda::serv->frameContext((cur - back + n) % n);
+            Cuda::serv->checkOn(c, mrt_readback_wait(c, back < framesInFlight ? 1 : 0));
+        }
+    }
+    // stats of the current frame context; the running totals (rays, kernel launches) summed over all frames in flight
     [[nodiscard]] auto stats() const -> mrt_stats {
         mrt_stats s;
         Cuda::serv->check(mrt_stats_get(Cuda::serv->ctx, &s));
+        for (int i = 0; i < Cuda::serv->framesInFlight(); i++) {
+            auto* const c = Cuda::serv->frameContext(i);
+            if (c == Cuda::serv->ctx) continue;
+            mrt_stats o;
+            Cuda::serv->checkOn(c, mrt_stats_get(c, &o));
+            s.total_rays += o.total_rays;
+            s.kernel_launches += o.kernel_launches;
+        }
         return s;
+    }
+    void resetStats() const {
+        forEachFrame([](mrt_context* c) { return mrt_stats_reset(c); });
+    }
+    void setOption(char const* name, std::int64_t value) const {
+        forEachFrame([&](mrt_context* c) { return mrt_set_option(c, name, value); });
     }
 
     uvec2 outputSize;
@@ -87,6 +121,21 @@ public:
     DeviceImage framebuffer;
 
 private:
+    template <typename F>
+    void forEachFrame(F&& call) const {
+        for (int i = 0; i < Cuda::serv->framesInFlight(); i++) {
+            auto* const c = Cuda::serv->frameContext(i);
+            Cuda::serv->checkOn(c, call(c));
+        }
+    }
+    void waitBorrowers() const {
+        for (int i = 1; i < Cuda::serv->framesInFlight(); i++) Cuda::serv->checkOn(Cuda::serv->frameContext(i), mrt_sync(Cuda::serv->frameContext(i)));
+    }
+    void shareScene() const {
+        for (int i = 1; i < Cuda::serv->framesInFlight(); i++)
+            Cuda::serv->checkOn(Cuda::serv->frameContext(i), mrt_scene_share(Cuda::serv->frameContext(i), Cuda::serv->owner()));
+    }
+
     // renderer.ixx:127-161
     auto denoise(DeviceImage color, DeviceImage depth, DeviceImage normal, Camera const& camera) -> DeviceImage {
         switch (denoiseMode) {
@@ -110,7 +159,7 @@ private:
 
     Camera prevCamera{};
     DeviceImage blueNoise;
-    Atmosphere* atmosphere = nullptr;
+    Atmosphere* atmosphere[Cuda_impl::MaxFramesInFlight] = {nullptr, nullptr, nullptr};  // one per frame context
 };
 
 export class Renderer {

@@ -527,3 +527,121 @@ def test_device_side_build_loops_give_the_same_tree(gpu_ctx, maker, builder):
         assert np.array_equal(nodes, trees[0][0])
         assert np.array_equal(tris, trees[0][1])
     assert trees[0][0].size == trees[0][2] * 20 and trees[0][1].size == idx.shape[0] * 12
+
+
+def test_shared_scene_renders_the_same_frames(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """mrt_scene_share (frames in flight): a context that borrows another context's triangles + BVH produces the same
+    hits and the same image bit for bit, may not build or update the borrowed scene, follows the owner's refit after
+    sharing again, and can be destroyed before or go back to a scene of its own."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h = 160, 96
+    cam = camera_for(oracle, view, w, h)
+    owner = gpu_ctx
+    owner.upload_blue_noise(blue_noise)
+    setup_sky(owner, oracle, atmo, cam.position[:])
+    owner.upload_mesh(pos, idx, alb)
+    other = capi.Context(0)
+    try:
+        with pytest.raises(capi.MinoteError):  # nothing built yet
+            other.share_scene(owner)
+        owner.build()
+        other.upload_blue_noise(blue_noise)
+        setup_sky(other, oracle, atmo, cam.position[:])
+        other.share_scene(owner)
+        so, sb = owner.stats(), other.stats()
+        assert sb.num_triangles == so.num_triangles and sb.num_wide_nodes == so.num_wide_nodes and sb.bvh_bytes == so.bvh_bytes
+
+        def render(ctx, f):
+            pc, scn = oracle.constants(cam, frame=f)
+            ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+            ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 2, 2)
+            ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+
+        # both contexts in flight at once, different frames each, then compared with the owner alone
+        for f in (1, 2):
+            render(owner, f)
+            render(other, f + 10)
+        got = (other.readback(capi.BUF_ACCUM).copy(), other.readback(capi.BUF_LDR).copy(), other.readback(capi.BUF_VISIBILITY).copy())
+        render(owner, 12)
+        want = (owner.readback(capi.BUF_ACCUM), owner.readback(capi.BUF_LDR), owner.readback(capi.BUF_VISIBILITY))
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+        o, d = random_rays(5000, pos.min(0) - 0.001, pos.max(0) + 0.001, 3)
+        ids_a, t_a = owner.trace_rays(o, d)
+        ids_b, t_b = other.trace_rays(o, d)
+        ids_bf, _ = other.trace_rays(o, d, brute_force=True)
+        assert np.array_equal(ids_a, ids_b) and np.array_equal(t_a, t_b) and np.array_equal(ids_b, ids_bf)
+        # the borrower cannot change the scene
+        for call in (lambda: other.build(), lambda: other.build(capi.BUILD_REFIT), lambda: other.update_positions(pos)):
+            with pytest.raises(capi.MinoteError):
+                call()
+        # owner animates + refits (borrower idle), shares again: the borrower sees the new geometry
+        other.sync()
+        pos2 = pos.copy()
+        pos2[:, 1] += 0.0004 * np.sin(40.0 * pos[:, 0]).astype(np.float32)
+        owner.update_positions(pos2)
+        owner.build(capi.BUILD_REFIT)
+        other.share_scene(owner)
+        render(other, 5)
+        render(owner, 5)
+        assert np.array_equal(other.readback(capi.BUF_ACCUM), owner.readback(capi.BUF_ACCUM))
+        ids_b2, t_b2 = other.trace_rays(o, d)
+        ids_bf2, t_bf2 = other.trace_rays(o, d, brute_force=True)
+        assert np.array_equal(ids_b2, ids_bf2) and np.array_equal(t_b2, t_bf2)
+        assert not np.array_equal(t_b2, t_b)
+        # a scene of its own ends the borrowing; the owner's arrays stay alive
+        cpos, cidx, calb, _ = scenes.cornell()
+        other.upload_mesh(cpos, cidx, calb)
+        other.build()
+        assert other.stats().num_triangles == cidx.shape[0]
+        ids_a2, _ = owner.trace_rays(o, d)
+        assert np.array_equal(ids_a2, ids_bf2)
+        other.share_scene(owner)  # and back: frees its own copy
+    finally:
+        other.close()  # borrower destroyed first; the owner (fixture) still works afterwards
+    ids_a3, _ = owner.trace_rays(o, d)
+    assert np.array_equal(ids_a3, ids_bf2)
+
+
+def test_renderer_frames_in_flight(oracle, blue_noise):
+    """Renderer::draw with 3 frame contexts (the reference's frames in flight, renderer.ixx:36): every frame's
+    framebuffer equals the one the single-context renderer produces for the same frame counter, also across a mesh
+    update (refit) between frames, with the async readbacks of up to 2 frames pending."""
+    import torch
+    from minotert_b200 import host
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h = 160, 96
+    cam = host.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+    pos2 = pos.copy()
+    pos2[:, 1] += 0.0004 * np.sin(40.0 * pos[:, 0]).astype(np.float32)
+    nframes = 7
+
+    def run(in_flight):
+        r = host.Renderer(w, h, blue_noise, frames_in_flight=in_flight)
+        try:
+            assert r.frames_in_flight() == in_flight
+            r.set_mesh(pos, idx, alb)
+            r.configure(samples=2, bounces=2, accumulate=False, tonemap="amd", exposure=1.0)
+            r.stats_reset()  # starts the running ray totals of every frame context
+            bufs = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(nframes)]
+            for f in range(nframes):
+                if f == 4:
+                    r.update_mesh(pos2, refit=True)
+                r.draw(cam)
+                assert r.frame_count() == f + 1
+                r.read_framebuffer_async(C.c_void_p(bufs[f].data_ptr()), bufs[f].numel())
+                r.wait_framebuffer(in_flight - 1)
+            r.wait_framebuffer(0)
+            st = r.stats()
+            return [b.numpy().copy() for b in bufs], int(st.total_rays)
+        finally:
+            r.close()
+
+    one, rays1 = run(1)
+    three, rays3 = run(3)
+    assert rays1 == rays3 and rays1 > nframes * w * h
+    for f in range(nframes):
+        assert np.array_equal(one[f], three[f]), f"frame {f + 1}"
+    assert not np.array_equal(one[0], one[1])      # different seeds
+    assert not np.array_equal(one[3], one[4])      # the refit is visible
