@@ -95,6 +95,8 @@ typedef enum {
     MRT_BUF_DENOISED = 11,       /* RGBA8 4 B/px (denoiser.ixx:56) output of mrt_denoise_bilateral */
     MRT_BUF_BVH_NODES = 12,      /* the built wide BVH, for tests and tools: 80-byte nodes ... */
     MRT_BUF_BVH_TRIS = 13,       /* ... and its triangles in leaf order, 3 x float4 each (v0.w = primitive id) */
+    MRT_BUF_TEMPORAL = 14,       /* RGBA32F 16 B/px (rgb, 1): output of mrt_temporal_accumulate = next frame's history */
+    MRT_BUF_TEMPORAL_COUNT = 15, /* R32F 4 B/px: history length of each pixel after mrt_temporal_accumulate (1 = reset) */
     MRT_BUF_COUNT_
 } mrt_buffer_id;
 
@@ -129,7 +131,7 @@ typedef struct {
     float sah_node_cost;      /* surface-area heuristic of the wide BVH: expected node steps ... */
     float sah_tri_cost;       /* ... and triangle tests of a random ray that hits the root box */
     float ms_denoise;         /* device time of the last mrt_denoise_bilateral */
-    uint32_t _reserved2;
+    float ms_temporal;        /* device time of the last mrt_temporal_accumulate */
 } mrt_stats;
 
 /* ---- lifetime ---- */
@@ -209,10 +211,21 @@ int mrt_secondary_rays(mrt_context* ctx, const mrt_secondary_constants* c, uint3
  * Needs the whole image in one context (fails with MRT_ERR_STATE under mrt_set_partition with nranks > 1). */
 int mrt_denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float threshold, float nearPlane,
                           uint32_t frameCounter);
+/* Temporal accumulation by reprojection.  No reference counterpart: it is the consumer of
+ * the motion image that src/gpu/primaryRay.comp:73-75 writes (pathtracer.ixx:63-69) and Renderer_impl::draw drops
+ * (renderer.ixx:61).  Blends the frame's average radiance (MRT_BUF_ACCUM) into the history fetched at each pixel's
+ * previous position (MRT_BUF_MOTION; history taps on another primitive are rejected through the previous frame's
+ * MRT_BUF_VISIBILITY) -> MRT_BUF_TEMPORAL (+ MRT_BUF_TEMPORAL_COUNT), which is the next call's history.
+ * maxHistory: cap of the history length (the blend weight of a new frame never falls below 1/(maxHistory+1)).
+ * The first call, a call after the image size or the scene changed, or MRT_TEMPORAL_RESET start a new history.
+ * Call after mrt_primary_rays (with prevView = the previous frame's view) + mrt_secondary_rays; whole image in
+ * one context (MRT_ERR_STATE under a partition).  Exact contract: oracle/minote_oracle.h orc_temporal_accumulate. */
+#define MRT_TEMPORAL_RESET 1u
+int mrt_temporal_accumulate(mrt_context* ctx, float maxHistory, uint32_t flags);
 /* Tonemapper::{linear,reinhard,hable,aces,uchimura,amd}(input, exposure, params)
  * (tonemapper.ixx:57-373).  source: MRT_BUF_COLOR (reference path), MRT_BUF_ACCUM
- * (progressive average) or MRT_BUF_DENOISED (the denoiser's RGBA8 image, as Renderer_impl::draw
- * chains them, renderer.ixx:61-62).  params: the push constants after `exposure`. */
+ * (progressive average), MRT_BUF_DENOISED (the denoiser's RGBA8 image, as Renderer_impl::draw
+ * chains them, renderer.ixx:61-62) or MRT_BUF_TEMPORAL.  params: the push constants after `exposure`. */
 int mrt_tonemap(mrt_context* ctx, int mode, float exposure, const float* params, uint32_t nparams,
                 int source);
 

@@ -16,9 +16,11 @@ LIB_PATH = os.path.join(LIB_DIR, "libminotert.so")
 
 MISS_ID = 0xFFFFFFFF
 (BUF_VISIBILITY, BUF_DEPTH, BUF_NORMAL, BUF_MOTION, BUF_COLOR, BUF_ACCUM, BUF_LDR, BUF_TRANSMITTANCE,
- BUF_MULTISCATTERING, BUF_SKY_VIEW, BUF_HIT_T, BUF_DENOISED, BUF_BVH_NODES, BUF_BVH_TRIS) = range(14)
+ BUF_MULTISCATTERING, BUF_SKY_VIEW, BUF_HIT_T, BUF_DENOISED, BUF_BVH_NODES, BUF_BVH_TRIS, BUF_TEMPORAL,
+ BUF_TEMPORAL_COUNT) = range(16)
 BUILD_FULL, BUILD_REFIT = 0, 1
 SECONDARY_ACCUMULATE, SECONDARY_SORT_RAYS = 1, 2
+TEMPORAL_RESET = 1
 TONEMAP = {"linear": 0, "reinhard": 1, "hable": 2, "aces": 3, "uchimura": 4, "amd": 5}
 DENOISE = {"none": 0, "bilateral": 1}   # Renderer_impl::denoise modes (src/gfx/renderer.ixx:129-132)
 BILATERAL_DEFAULT = (5.0, 2.0, 0.12)   # sigma, kSigma, threshold (src/gfx/modules/denoiser.ixx:27-33)
@@ -53,7 +55,7 @@ class Stats(C.Structure):
                 ("stack_overflows", C.c_uint32), ("num_triangles", C.c_uint32), ("num_wide_nodes", C.c_uint32),
                 ("bvh_bytes", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
                 ("trace_launches", C.c_uint32), ("_reserved", C.c_uint32), ("total_rays", C.c_uint64), ("sah_node_cost", C.c_float), ("sah_tri_cost", C.c_float),
-                ("ms_denoise", C.c_float), ("_reserved2", C.c_uint32)]
+                ("ms_denoise", C.c_float), ("ms_temporal", C.c_float)]
 
 
 EXPORTS = [
@@ -62,7 +64,7 @@ EXPORTS = [
     "mrt_atmosphere", "mrt_sky_view", "mrt_set_partition", "mrt_partition_rows", "mrt_primary_rays",
     "mrt_secondary_rays", "mrt_tonemap", "mrt_buffer", "mrt_readback", "mrt_sync", "mrt_stats_get",
     "mrt_stats_reset", "mrt_stream", "mrt_trace_rays", "mrt_partition_rows_for", "mrt_readback_async",
-    "mrt_readback_wait", "mrt_denoise_bilateral", "mrt_scene_share",
+    "mrt_readback_wait", "mrt_denoise_bilateral", "mrt_scene_share", "mrt_temporal_accumulate",
 ]
 
 
@@ -96,6 +98,7 @@ def load():
     L.mrt_scene_update_positions.argtypes = [vp, vp, u32]
     L.mrt_scene_build.argtypes = [vp, C.c_int]
     L.mrt_scene_share.argtypes = [vp, vp]
+    L.mrt_temporal_accumulate.argtypes = [vp, C.c_float, u32]
     L.mrt_atmosphere.argtypes = [vp, vp]
     L.mrt_sky_view.argtypes = [vp, f32p, f32p, f32p]
     L.mrt_set_partition.argtypes = [vp, u32, u32, u32]
@@ -135,7 +138,8 @@ class Context:
 
     _DTYPES = {BUF_VISIBILITY: (np.uint32, 1), BUF_DEPTH: (np.uint16, 1), BUF_NORMAL: (np.uint16, 4),
                BUF_MOTION: (np.uint16, 2), BUF_COLOR: (np.uint16, 4), BUF_ACCUM: (np.float32, 4),
-               BUF_LDR: (np.uint8, 4), BUF_HIT_T: (np.float32, 1), BUF_DENOISED: (np.uint8, 4)}
+               BUF_LDR: (np.uint8, 4), BUF_HIT_T: (np.float32, 1), BUF_DENOISED: (np.uint8, 4),
+               BUF_TEMPORAL: (np.float32, 4), BUF_TEMPORAL_COUNT: (np.float32, 1)}
 
     def __init__(self, device=0):
         self.L = load()
@@ -221,6 +225,10 @@ class Context:
 
     def denoise_bilateral(self, params=BILATERAL_DEFAULT, near=0.001, frame=1):
         self._ck(self.L.mrt_denoise_bilateral(self.h, params[0], params[1], params[2], near, frame))
+
+    def temporal_accumulate(self, max_history=32.0, reset=False):
+        """mrt_temporal_accumulate: blend this frame into the reprojected history (BUF_TEMPORAL, BUF_TEMPORAL_COUNT)."""
+        self._ck(self.L.mrt_temporal_accumulate(self.h, float(max_history), TEMPORAL_RESET if reset else 0))
 
     def tonemap(self, mode="amd", exposure=1.0, params=(16.0, 2.0, 1.0, 0.18, 0.18), source=BUF_COLOR):
         par = (C.c_float * 8)(*params)

@@ -72,6 +72,8 @@ int buffer_info(mrt_context* ctx, int id, void** p, size_t* bytes) {
     case MRT_BUF_BVH_NODES: if (ctx->scene_kind != 2 || !ctx->bvh_valid) break; *p = ctx->nodes.p; *bytes = (size_t)ctx->num_nodes * sizeof(WideNode); return MRT_OK;
     case MRT_BUF_BVH_TRIS: if (ctx->scene_kind != 2 || !ctx->bvh_valid) break; *p = ctx->tris.p; *bytes = (size_t)ctx->num_leaf_tris * 48; return MRT_OK;
     case MRT_BUF_DENOISED: if (!ctx->have_denoised) break; *p = ctx->denoised.p; *bytes = n * 4; return MRT_OK;
+    case MRT_BUF_TEMPORAL: if (!ctx->have_temporal) break; *p = ctx->tp_rgba[ctx->tp_cur].p; *bytes = n * 16; return MRT_OK;
+    case MRT_BUF_TEMPORAL_COUNT: if (!ctx->have_temporal) break; *p = ctx->tp_count[ctx->tp_cur].p; *bytes = n * 4; return MRT_OK;
     case MRT_BUF_HIT_T: if (!ctx->have_gbuffer || ctx->scene_kind != 2) break; *p = ctx->hit_t.p; *bytes = n * 4; return MRT_OK;
     default: return mrt_fail(ctx, MRT_ERR_INVALID, "unknown buffer id %d", id);
     }
@@ -144,6 +146,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->trans_f); dev_free(ctx->multi_f); dev_free(ctx->view_f);
     dev_free(ctx->visibility); dev_free(ctx->depth); dev_free(ctx->normal); dev_free(ctx->motion); dev_free(ctx->color16);
     dev_free(ctx->denoised); dev_free(ctx->dn_taps);
+    for (int k = 0; k < 2; k++) { dev_free(ctx->tp_rgba[k]); dev_free(ctx->tp_count[k]); dev_free(ctx->tp_vis[k]); }
     dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
     dev_free(ctx->hit0_pos); dev_free(ctx->hit0_n); dev_free(ctx->path_state);
     for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); }
@@ -200,7 +203,7 @@ int mrt_scene_set_spheres(mrt_context* ctx, const mrt_sphere* spheres, uint32_t 
     for (uint32_t i = 0; i < n; i++) ctx->spheres.s[i] = spheres[i];
     ctx->spheres.n = n;
     ctx->scene_kind = 1;
-    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;  // a new scene restarts accumulation
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = ctx->have_temporal = false;  // a new scene restarts accumulation
     return MRT_OK;
 }
 
@@ -227,7 +230,7 @@ int mrt_scene_upload_mesh(mrt_context* ctx, const float* positions, uint32_t nve
     ctx->ntris = ntris;
     ctx->scene_kind = 2;
     ctx->bvh_valid = false;
-    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;  // a new scene restarts accumulation
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = ctx->have_temporal = false;  // a new scene restarts accumulation
     return MRT_OK;
 }
 
@@ -268,7 +271,7 @@ int mrt_scene_share(mrt_context* ctx, mrt_context* owner) {
     ctx->scene_borrowed = true;
     ctx->scene_kind = 2;
     ctx->bvh_valid = true;
-    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = ctx->have_temporal = false;
     // builds and refits already queued on the owner's stream come first
     cudaEvent_t built;
     MRT_CUDA(ctx, cudaEventCreateWithFlags(&built, cudaEventDisableTiming));
@@ -318,7 +321,7 @@ int mrt_set_partition(mrt_context* ctx, uint32_t rank, uint32_t nranks, uint32_t
     MRT_ENTER(ctx);
     if (nranks == 0 || rank >= nranks || slab_rows == 0) return mrt_fail(ctx, MRT_ERR_INVALID, "bad partition %u/%u slab %u", rank, nranks, slab_rows);
     ctx->part = Partition{rank, nranks, slab_rows};
-    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;
+    ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = ctx->have_temporal = false;
     return MRT_OK;
 }
 
@@ -401,15 +404,29 @@ int mrt_denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float thr
     return s;
 }
 
+int mrt_temporal_accumulate(mrt_context* ctx, float maxHistory, uint32_t flags) {
+    MRT_ENTER(ctx);
+    if (!ctx->have_gbuffer || !ctx->have_accum) return mrt_fail(ctx, MRT_ERR_STATE, "temporal accumulation before primary + secondary rays");
+    if (ctx->part.nranks > 1) return mrt_fail(ctx, MRT_ERR_STATE, "temporal accumulation needs the whole image in one context (partition %u of %u)", ctx->part.rank, ctx->part.nranks);
+    if (!(maxHistory >= 0.0f)) return mrt_fail(ctx, MRT_ERR_INVALID, "temporal accumulation: maxHistory %g", (double)maxHistory);
+    if (flags & ~MRT_TEMPORAL_RESET) return mrt_fail(ctx, MRT_ERR_INVALID, "temporal accumulation: unknown flags 0x%x", flags);
+    cudaEventRecord(ctx->ev[10], ctx->stream);
+    int s = ctx->npix ? temporal_accumulate(ctx, maxHistory, (flags & MRT_TEMPORAL_RESET) != 0) : MRT_OK;
+    cudaEventRecord(ctx->ev[11], ctx->stream);
+    if (s == MRT_OK) ctx->have_temporal = true;
+    return s;
+}
+
 int mrt_tonemap(mrt_context* ctx, int mode, float exposure, const float* params, uint32_t nparams, int source) {
     MRT_ENTER(ctx);
     if (mode < MRT_TONEMAP_LINEAR || mode > MRT_TONEMAP_AMD) return mrt_fail(ctx, MRT_ERR_INVALID, "unknown tonemap mode %d", mode);
     static const uint32_t need[6] = {0, 1, 0, 0, 6, 5};
     if (nparams < need[mode] || (need[mode] && !params)) return mrt_fail(ctx, MRT_ERR_INVALID, "tonemap mode %d needs %u params", mode, need[mode]);
-    if (source != MRT_BUF_COLOR && source != MRT_BUF_ACCUM && source != MRT_BUF_DENOISED)
-        return mrt_fail(ctx, MRT_ERR_INVALID, "tonemap source must be COLOR, ACCUM or DENOISED");
+    if (source != MRT_BUF_COLOR && source != MRT_BUF_ACCUM && source != MRT_BUF_DENOISED && source != MRT_BUF_TEMPORAL)
+        return mrt_fail(ctx, MRT_ERR_INVALID, "tonemap source must be COLOR, ACCUM, DENOISED or TEMPORAL");
     if (!ctx->have_accum) return mrt_fail(ctx, MRT_ERR_STATE, "tonemap before secondary rays");
     if (source == MRT_BUF_DENOISED && !ctx->have_denoised) return mrt_fail(ctx, MRT_ERR_STATE, "tonemap of the denoised image before mrt_denoise_bilateral");
+    if (source == MRT_BUF_TEMPORAL && !ctx->have_temporal) return mrt_fail(ctx, MRT_ERR_STATE, "tonemap of the temporal image before mrt_temporal_accumulate");
     if (source == MRT_BUF_COLOR && !ctx->have_color) {
         void* p; size_t b;
         MRT_TRY(buffer_info(ctx, MRT_BUF_COLOR, &p, &b));
@@ -493,6 +510,7 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
     if (ctx->have_accum && cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->stats.ms_secondary = ms;
     if (ctx->have_ldr && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->stats.ms_tonemap = ms;
     if (ctx->have_denoised && cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]) == cudaSuccess) ctx->stats.ms_denoise = ms;
+    if (ctx->have_temporal && cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]) == cudaSuccess) ctx->stats.ms_temporal = ms;
     cudaGetLastError();
     if (ctx->have_accum && ctx->stats.secondary_rays == ~0ull) {
         if (ctx->scene_kind == 1) {

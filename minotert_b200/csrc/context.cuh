@@ -134,6 +134,14 @@ struct mrt_context {
     float dn_key_sigma = 0.0f, dn_key_ksigma = 0.0f;
     uint32_t dn_key_w = 0, dn_key_h = 0;
     bool have_denoised = false;
+    // temporal reprojection (temporal.cu): double-buffered history = previous output (rgb, 1), its history length and
+    // the previous frame's visibility ids
+    DevArray<float4> tp_rgba[2];
+    DevArray<float> tp_count[2];
+    DevArray<uint32_t> tp_vis[2];
+    int tp_cur = 0;
+    uint32_t tp_w = 0, tp_h = 0;
+    bool have_temporal = false;
     DevArray<uchar4> ldr_buf[2];         // double-buffered output framebuffer: an async readback of frame f
     int ldr_cur = 0;                     // overlaps the rendering of frame f+1 (the reference keeps 3 frames in flight)
     cudaStream_t copy_stream = nullptr;
@@ -154,7 +162,7 @@ struct mrt_context {
 
     // stats
     mrt_stats stats{};
-    cudaEvent_t ev[10] = {nullptr};
+    cudaEvent_t ev[12] = {nullptr};  // pairs: sky, primary, secondary, tonemap, denoise, temporal
     // The sky view of a frame is generated on a side stream so that it overlaps the primary pass
     // (Renderer::draw order: sky -> primary -> secondary); consumers join through sky_join().
     cudaStream_t aux_stream = nullptr;
@@ -213,6 +221,7 @@ int sky_gen_view(mrt_context* ctx, const float probe[3], const float sunDir[3], 
 int spheres_primary(mrt_context* ctx);
 int spheres_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags);
 int denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float threshold, float nearPlane, uint32_t frameCounter);
+int temporal_accumulate(mrt_context* ctx, float maxHistory, bool reset);
 int tonemap_run(mrt_context* ctx, int mode, float exposure, const float* params, uint32_t nparams, int source);
 int bvh_build_full(mrt_context* ctx);
 int bvh_refit(mrt_context* ctx);

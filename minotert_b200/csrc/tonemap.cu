@@ -167,6 +167,8 @@ int tonemap_run(mrt_context* ctx, int mode, float exposure, const float* params,
     if (grid == 0) grid = 1;
     if (source == MRT_BUF_ACCUM)
         k_tonemap<1><<<grid, 256, 0, ctx->stream>>>(T, ctx->accum.p, nullptr, nullptr, ldr.p, n);
+    else if (source == MRT_BUF_TEMPORAL)  // (rgb, 1): the accumulator path with a sample count of one
+        k_tonemap<1><<<grid, 256, 0, ctx->stream>>>(T, ctx->tp_rgba[ctx->tp_cur].p, nullptr, nullptr, ldr.p, n);
     else if (source == MRT_BUF_DENOISED)
         k_tonemap<2><<<grid, 256, 0, ctx->stream>>>(T, nullptr, nullptr, ctx->denoised.p, ldr.p, n);
     else

@@ -14,6 +14,7 @@ import minote.modules.sky;
 import minote.modules.pathtracer;
 import minote.modules.tonemapper;
 import minote.modules.denoiser;
+import minote.modules.reprojector;
 import minote.renderer;
 import minote.freecam;
 
@@ -157,6 +158,14 @@ int minote_app_set_denoise(void* a, int mode, float sigma, float kSigma, float t
         auto& r = *Renderer::serv;
         r.denoiseMode = static_cast<DenoiseMode>(mode);
         r.bilateralParams = BilateralParams{sigma, kSigma, threshold};
+    });
+}
+// temporal accumulation along GBuffer::motion (takes the denoiser's place in draw()); max_history <= 0 keeps the default
+int minote_app_set_temporal(void* a, int enabled, float max_history) {
+    return guarded(static_cast<App*>(a), [&] {
+        auto& r = *Renderer::serv;
+        r.temporal = enabled != 0;
+        if (max_history > 0.0f) r.reprojectorParams.maxHistory = max_history;
     });
 }
 int minote_app_resize(void* a, std::uint32_t w, std::uint32_t h) {

@@ -14,6 +14,7 @@ import minote.modules.sky;
 import minote.modules.pathtracer;
 import minote.modules.tonemapper;
 import minote.modules.denoiser;
+import minote.modules.reprojector;
 
 export enum class DenoiseMode : int { None = 0, Bilateral = 1 };  // renderer.ixx:129-132
 export enum class TonemapMode : int { Linear = 0, Reinhard = 1, Hable = 2, ACES = 3, Uchimura = 4, AMD = 5 };
@@ -52,8 +53,9 @@ public:
     }
 
     void draw(Camera const& camera) {
-        // Begin the frame: the next frame context (a progressive accumulator lives in one context, so it stays put)
-        Cuda::serv->nextFrame(!pathtracer.accumulate);
+        // Begin the frame: the next frame context (a progressive accumulator or a temporal history lives in one
+        // context, so with either the frame stays put)
+        Cuda::serv->nextFrame(!pathtracer.accumulate && !temporal);
         // Initial temporal resource values
         if (Cuda::serv->frameCount() == 1) prevCamera = camera;
 
@@ -65,7 +67,9 @@ public:
         auto skyView = sky.createView(*atmo, camera.position);
         auto gbuffer = pathtracer.primaryRays(outputSize, camera, prevCamera);
         auto pathtraced = pathtracer.secondaryRays(gbuffer, camera, *atmo, skyView, blueNoise);
-        auto filtered = denoise(pathtraced, gbuffer.depth, gbuffer.normal, camera);
+        // temporal accumulation (off by default: the reference has none) takes the denoiser's place in the chain
+        auto filtered = temporal ? reprojector.accumulate(pathtraced, gbuffer.visibility, gbuffer.motion, reprojectorParams)
+                                 : denoise(pathtraced, gbuffer.depth, gbuffer.normal, camera);
         framebuffer = tonemap(filtered);
 
         // Temporal preservation
@@ -109,6 +113,9 @@ public:
     Pathtracer pathtracer;
     Tonemapper tonemapper;
     Denoiser denoiser;
+    Reprojector reprojector;
+    bool temporal = false;  // reproject + accumulate along GBuffer::motion instead of denoising
+    ReprojectorParams reprojectorParams = ReprojectorParams::make_default();
     // ImGui statics of Renderer_impl::denoise (renderer.ixx:140-141)
     DenoiseMode denoiseMode = DenoiseMode::Bilateral;
     BilateralParams bilateralParams = BilateralParams::make_default();

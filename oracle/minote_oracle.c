@@ -1295,6 +1295,60 @@ static float uchimura1(float x, float P, float a, float m, float l, float c, flo
     return T * w0 + Lc * w1 + Sc * w2;
 }
 
+/* ---- temporal reprojection (contract in minote_oracle.h) ----
+ * Consumes the motion buffer of src/gpu/primaryRay.comp:73-75.  fp32, no contraction; the same expression order as
+ * k_temporal (minotert_b200/csrc/temporal.cu), so the two agree bit for bit. */
+void orc_temporal_accumulate(uint32_t w, uint32_t h, const float* accum, const uint32_t* vis, const uint16_t* motion16,
+                             int have_history, const float* hist_rgba, const float* hist_count, const uint32_t* hist_vis,
+                             float maxHistory, float* out_rgba, float* out_count) {
+#pragma omp parallel for schedule(static)
+    for (long long y = 0; y < (long long)h; y++)
+        for (uint32_t x = 0; x < w; x++) {
+            const size_t p = (size_t)y * w + x;
+            const float aw = accum[4 * p + 3];
+            float cur[3];
+            for (int c = 0; c < 3; c++) cur[c] = aw > 0.0f ? accum[4 * p + c] / aw : 0.0f;
+            const uint32_t id = vis[p];
+            float out[3] = {cur[0], cur[1], cur[2]}, count = 1.0f;
+            if (have_history && id != 0xFFFFFFFFu) {
+                const float mx = orc_f16_to_f32(motion16[2 * p]), my = orc_f16_to_f32(motion16[2 * p + 1]);
+                /* texel-centre coordinates of the previous position, minus the half texel of the bilinear footprint */
+                const float gx = ((float)x + 0.5f - mx * 0.5f) - 0.5f, gy = ((float)y + 0.5f + my * 0.5f) - 0.5f;
+                /* NaN / far outside (also what an inf motion gives): no history */
+                if (gx > -2.0f && gy > -2.0f && gx < (float)w + 1.0f && gy < (float)h + 1.0f) {
+                    const float fx0 = floorf(gx), fy0 = floorf(gy);
+                    const float wx = gx - fx0, wy = gy - fy0;
+                    const int x0 = (int)fx0, y0 = (int)fy0;
+                    float sum[3] = {0.0f, 0.0f, 0.0f}, nsum = 0.0f, wsum = 0.0f;
+                    for (int j = 0; j < 2; j++)
+                        for (int i = 0; i < 2; i++) {
+                            const int tx = x0 + i, ty = y0 + j;
+                            if (tx < 0 || ty < 0 || tx >= (int)w || ty >= (int)h) continue;
+                            const size_t q = (size_t)ty * w + (size_t)tx;
+                            if (hist_vis[q] != id) continue;
+                            const float wt = (i ? wx : 1.0f - wx) * (j ? wy : 1.0f - wy);
+                            for (int c = 0; c < 3; c++) sum[c] = sum[c] + wt * hist_rgba[4 * q + c];
+                            nsum = nsum + wt * hist_count[q];
+                            wsum = wsum + wt;
+                        }
+                    if (wsum > 0.00390625f) {
+                        float n = nsum / wsum;
+                        n = n < maxHistory ? n : maxHistory;
+                        const float a = 1.0f / (n + 1.0f);
+                        for (int c = 0; c < 3; c++) {
+                            const float hc = sum[c] / wsum;
+                            out[c] = hc + (cur[c] - hc) * a;
+                        }
+                        count = n + 1.0f;
+                    }
+                }
+            }
+            out_rgba[4 * p] = out[0]; out_rgba[4 * p + 1] = out[1]; out_rgba[4 * p + 2] = out[2]; out_rgba[4 * p + 3] = 1.0f;
+            out_count[p] = count;
+        }
+}
+
+
 void orc_tonemap_pixel(int mode, const float in[3], float exposure, const float* p, float out[3]) {
     v3 src = vscale(v3p(in), exposure);
     v3 mapped;

@@ -159,6 +159,22 @@ void orc_denoise_bilateral(uint32_t w, uint32_t h, const uint16_t* color16 /*RGB
                            float sigma, float kSigma, float threshold, float nearPlane,
                            uint32_t frameCounter, uint8_t* rgba8);
 
+/* ---- temporal reprojection ----
+ * No reference counterpart: the reference WRITES the motion of every primary hit between prevView and view
+ * (src/gpu/primaryRay.comp:73-75, RG16F, pathtracer.ixx:63-69) and nothing reads it (renderer.ixx:61).  This is the
+ * consumer: an exponential moving average of the frame's radiance with the history fetched at the reprojected pixel.
+ *   cur      = accum.rgb / accum.w                              (the frame's average, row n7)
+ *   miss     : visibility == 0xFFFFFFFF -> out = cur, count 1   (the sky is noise-free and carries motion 0)
+ *   prev px  : (x + 0.5 - m.x / 2, y + 0.5 + m.y / 2)           (m = motion texel; ndc.y is flipped, primaryRay.comp:46)
+ *   history  : bilinear over the 4 nearest history texels, taps outside the image or whose primitive id differs
+ *              from the pixel's are dropped and the weights renormalised; total weight <= 1/256 -> out = cur, count 1
+ *   blend    : n = min(history count, maxHistory); out = hist + (cur - hist) / (n + 1); count = n + 1
+ * accum: RGBA32F, vis: R32_UINT, motion16: RG16F; hist_rgba/hist_vis: previous outputs (have_history = 0: ignored);
+ * out_rgba: RGBA32F (rgb, 1); out_count: R32F. */
+void orc_temporal_accumulate(uint32_t w, uint32_t h, const float* accum, const uint32_t* vis, const uint16_t* motion16,
+                             int have_history, const float* hist_rgba, const float* hist_count, const uint32_t* hist_vis,
+                             float maxHistory, float* out_rgba, float* out_count);
+
 /* ---- tonemap (a14) ---- */
 /* src: RGBA32F if src_is_f16 == 0, RGBA16F if 1, RGBA8 unorm (denoiser output) if 2.  params: mode-specific push constants after exposure
  * (reinhard: hdrMax; uchimura: 6 floats; amd: 5 floats). */

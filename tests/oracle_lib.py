@@ -131,6 +131,7 @@ def lib():
         "orc_primary_rays_spheres": (None, [C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.POINTER(Sphere), C.c_uint32, u32p, u16p, u16p, u16p]),
         "orc_secondary_rays_spheres": (None, [C.c_uint32, C.c_uint32, C.POINTER(SecondaryConstants), C.POINTER(Sphere), C.c_uint32, u32p, u16p, u16p, u8p, C.c_uint32, C.c_uint32, C.POINTER(AtmosphereParams), u16p, u32p, C.c_uint32, C.c_uint32, u16p, f32p, u64p]),
         "orc_denoise_bilateral": (None, [C.c_uint32, C.c_uint32, u16p, u16p, u16p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32, u8p]),
+        "orc_temporal_accumulate": (None, [C.c_uint32, C.c_uint32, f32p, u32p, u16p, C.c_int, f32p, f32p, u32p, C.c_float, f32p, f32p]),
         "orc_tonemap": (None, [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, f32p, u8p]),
         "orc_tonemap_pixel": (None, [C.c_int, f32p, C.c_float, f32p, f32p]),
         "orc_scene_create": (C.c_void_p, [f32p, C.c_uint32, u32p, C.c_uint32, f32p]),
@@ -270,6 +271,25 @@ def denoise_bilateral(color16, depth16, normal16, params=BILATERAL_DEFAULT, near
     lib().orc_denoise_bilateral(w, h, _p(c, C.c_uint16), _p(d, C.c_uint16), _p(n, C.c_uint16), params[0], params[1],
                                 params[2], near, frame, _p(out, C.c_uint8))
     return out
+
+
+def temporal_accumulate(accum, vis, motion16, history=None, max_history=32.0):
+    """orc_temporal_accumulate: history = (rgba, count, vis) of the previous call or None.  Returns (rgba, count, vis)."""
+    h, w = vis.shape[:2]
+    a = np.ascontiguousarray(accum, np.float32)
+    v = np.ascontiguousarray(vis, np.uint32)
+    m = np.ascontiguousarray(motion16, np.uint16)
+    out = np.zeros((h, w, 4), np.float32)
+    cnt = np.zeros((h, w), np.float32)
+    if history is None:
+        hr, hc, hv = out, cnt, v
+    else:
+        hr, hc, hv = (np.ascontiguousarray(history[0], np.float32), np.ascontiguousarray(history[1], np.float32),
+                      np.ascontiguousarray(history[2], np.uint32))
+    lib().orc_temporal_accumulate(w, h, _p(a, C.c_float), _p(v, C.c_uint32), _p(m, C.c_uint16), 0 if history is None else 1,
+                                  _p(hr, C.c_float), _p(hc, C.c_float), _p(hv, C.c_uint32), float(max_history),
+                                  _p(out, C.c_float), _p(cnt, C.c_float))
+    return out, cnt, v.copy()
 
 
 class Scene:

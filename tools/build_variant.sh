@@ -8,7 +8,7 @@ NAME=$1; EXTRA=$2
 OUT=$ROOT/variants/$NAME
 mkdir -p "$OUT/obj"
 cd "$ROOT/minotert_b200/csrc"
-for f in api sky spheres tonemap denoise sort bvh_build mesh; do
+for f in api sky spheres tonemap denoise temporal sort bvh_build mesh; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false \
     -Xcompiler -fPIC -ccbin /usr/bin/g++ $EXTRA -c $f.cu -o "$OUT/obj/$f.o" &
 done
