@@ -233,6 +233,12 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             flush_buf.zero_()
 
+    # The sequential pass below runs one frame at a time on frame context 0: its traversal grids fill every SM.
+    # (With frames in flight the host modules cap them at 3 CTAs per SM so that frames co-run; restored afterwards.)
+    user_ctas = [kv for kv in args.opt if kv.startswith("trace_ctas_per_sm=")]
+    if in_flight > 1 and not user_ctas:
+        ctx.set_option("trace_ctas_per_sm", 0)
+
     # per-ray visit counts for the algorithmic-bytes figure (untimed, counted pass)
     ctx.set_option("count_visits", 1)
     frame(1)
@@ -305,6 +311,8 @@ def run_ours(args):
     # filled by the next frame's kernels.  One start event (all streams idle), one end event per stream, max taken.
     # The L2 flush of every step sits on that step's stream INSIDE the timed region.
     pipelined = None
+    if in_flight > 1 and not user_ctas:
+        ctx.set_option("trace_ctas_per_sm", 3)
     if world == 1 and in_flight > 1:
         streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c in frame_ctxs]
 

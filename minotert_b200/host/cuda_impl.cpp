@@ -18,6 +18,11 @@ Cuda_impl::Cuda_impl(int device, int framesInFlight) {
     }
     inFlight = framesInFlight;
     ctx = frameCtx[0];
+    // With several frames in flight the persistent traversal grids of different frames should co-run instead of
+    // each filling every SM: 3 of the 6 resident CTAs per SM measured best (config 2, 3 frames: 3824 -> 3958
+    // Mrays/s; 2 frames: 3757 -> 3820; profiles/r1_results.md).
+    if (inFlight > 1)
+        for (int i = 0; i < inFlight; i++) mrt_set_option(frameCtx[i], "trace_ctas_per_sm", 3);
 }
 
 void Cuda_impl::fail(int status, mrt_context* on) const {
