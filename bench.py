@@ -208,6 +208,8 @@ def run_ours(args):
     for c in frame_ctxs:
         c.sync()
     ctx.build()  # second, warm build: ms_build without the first-launch module loading
+    for c in frame_ctxs[1:]:
+        c.share_scene(ctx)  # the rebuild made the borrowing frame contexts stale
     build_stats = ctx.stats()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")

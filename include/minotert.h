@@ -172,10 +172,12 @@ int mrt_scene_build(mrt_context* ctx, int build_mode);
 /* Frames in flight.  The reference records each frame into its own arena with 3 frames in flight
  * (src/gfx/renderer.ixx:36,42-43,97) while the scene resources are shared; here one context = one frame's
  * buffers + stream, and ctx renders the mesh scene (triangles, albedo, built BVH) that `owner` holds instead
- * of its own copy.  Borrowed, not copied: `owner` must outlive ctx's use of it; after the owner rebuilds or
- * refits, wait for ctx's frames (mrt_sync) BEFORE the rebuild and call mrt_scene_share again after it (cheap;
- * it also orders ctx's stream behind the owner's queued build).  mrt_scene_update_positions / mrt_scene_build
- * on a borrowing context fail with MRT_ERR_STATE; mrt_scene_upload_mesh ends the borrowing. */
+ * of its own copy.  Borrowed, not copied.  Whenever the owner changes the scene (mrt_scene_upload_mesh,
+ * mrt_scene_update_positions, mrt_scene_build) the library first waits for the borrowers' frames in flight and marks
+ * them stale: their render calls fail with MRT_ERR_STATE until mrt_scene_share is called again (cheap; it also orders
+ * ctx's stream behind the owner's queued build).  Destroying the owner leaves its borrowers without a scene.
+ * mrt_scene_update_positions / mrt_scene_build on a borrowing context fail with MRT_ERR_STATE;
+ * mrt_scene_upload_mesh ends the borrowing.  Owner and borrowers are driven from one host thread. */
 int mrt_scene_share(mrt_context* ctx, mrt_context* owner);
 
 /* ---- sky (src/gfx/modules/sky.ixx) ---- */

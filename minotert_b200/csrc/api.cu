@@ -85,11 +85,31 @@ int buffer_info(mrt_context* ctx, int id, void** p, size_t* bytes) {
 // a context that renders another context's scene (mrt_scene_share) forgets the borrowed arrays instead of freeing them
 static void scene_unborrow(mrt_context* ctx) {
     if (!ctx->scene_borrowed) return;
+    if (ctx->scene_owner) {
+        auto& list = ctx->scene_owner->borrowers;
+        for (size_t i = 0; i < list.size(); i++)
+            if (list[i] == ctx) { list.erase(list.begin() + (long)i); break; }
+    }
+    ctx->scene_owner = nullptr;
     ctx->pos = {}; ctx->idx = {}; ctx->albedo = {}; ctx->nodes = {}; ctx->tris = {};
     ctx->nverts = ctx->ntris = ctx->num_nodes = ctx->num_leaf_tris = 0;
     ctx->scene_borrowed = false;
     ctx->bvh_valid = false;
     ctx->scene_kind = 0;
+}
+
+// Called before the owner's scene arrays are rewritten, reallocated or freed: frames of the borrowing contexts that
+// still read them are waited for, and the borrowers are marked stale (mrt_scene_share again) or, when the owner goes
+// away, left without a scene.
+static void scene_borrowers_stale(mrt_context* owner, bool owner_dies) {
+    if (owner->borrowers.empty()) return;
+    std::vector<mrt_context*> list = owner->borrowers;
+    for (mrt_context* b : list) {
+        cudaStreamSynchronize(b->stream);
+        b->bvh_valid = false;
+        b->have_gbuffer = b->have_accum = b->have_color = b->have_ldr = b->have_denoised = b->have_temporal = false;
+        if (owner_dies) scene_unborrow(b);
+    }
 }
 
 extern "C" {
@@ -131,6 +151,7 @@ void mrt_destroy(mrt_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->bn) cudaFree(ctx->bn);
+    scene_borrowers_stale(ctx, true);
     scene_unborrow(ctx);
     dev_free(ctx->pos); dev_free(ctx->idx); dev_free(ctx->albedo);
     dev_free(ctx->prim_lo); dev_free(ctx->prim_hi); dev_free(ctx->keys); dev_free(ctx->keys_alt);
@@ -215,6 +236,7 @@ int mrt_scene_upload_mesh(mrt_context* ctx, const float* positions, uint32_t nve
     for (size_t i = 0; i < 3 * (size_t)ntris; i++)
         if (indices[i] >= nverts) return mrt_fail(ctx, MRT_ERR_INVALID, "mesh: index %u out of range at %zu", indices[i], i);
     if (ctx->scene_borrowed) { cudaStreamSynchronize(ctx->stream); scene_unborrow(ctx); }
+    scene_borrowers_stale(ctx, false);
     MRT_TRY(dev_reserve(ctx, ctx->pos, 3 * (size_t)nverts));
     MRT_TRY(dev_reserve(ctx, ctx->idx, 3 * (size_t)ntris));
     MRT_TRY(dev_reserve(ctx, ctx->albedo, ntris));
@@ -239,6 +261,7 @@ int mrt_scene_update_positions(mrt_context* ctx, const float* positions, uint32_
     if (ctx->scene_kind != 2) return mrt_fail(ctx, MRT_ERR_STATE, "no mesh uploaded");
     if (ctx->scene_borrowed) return mrt_fail(ctx, MRT_ERR_STATE, "the scene is borrowed (mrt_scene_share): update it through its owner");
     if (nverts != ctx->nverts || !positions) return mrt_fail(ctx, MRT_ERR_INVALID, "vertex count mismatch (%u vs %u)", nverts, ctx->nverts);
+    scene_borrowers_stale(ctx, false);
     MRT_CUDA(ctx, cudaMemcpyAsync(ctx->pos.p, positions, sizeof(float) * 3 * (size_t)nverts, cudaMemcpyHostToDevice, ctx->stream));
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MRT_OK;
@@ -248,9 +271,9 @@ int mrt_scene_build(mrt_context* ctx, int build_mode) {
     MRT_ENTER(ctx);
     if (ctx->scene_kind != 2) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_scene_build: no mesh uploaded");
     if (ctx->scene_borrowed) return mrt_fail(ctx, MRT_ERR_STATE, "the scene is borrowed (mrt_scene_share): build it through its owner");
-    if (build_mode == MRT_BUILD_REFIT) return bvh_refit(ctx);
-    if (build_mode != MRT_BUILD_FULL) return mrt_fail(ctx, MRT_ERR_INVALID, "unknown build mode %d", build_mode);
-    return bvh_build_full(ctx);
+    if (build_mode != MRT_BUILD_REFIT && build_mode != MRT_BUILD_FULL) return mrt_fail(ctx, MRT_ERR_INVALID, "unknown build mode %d", build_mode);
+    scene_borrowers_stale(ctx, false);
+    return build_mode == MRT_BUILD_REFIT ? bvh_refit(ctx) : bvh_build_full(ctx);
 }
 
 int mrt_scene_share(mrt_context* ctx, mrt_context* owner) {
@@ -269,6 +292,8 @@ int mrt_scene_share(mrt_context* ctx, mrt_context* owner) {
     ctx->stats.bvh_bytes = owner->stats.bvh_bytes;
     ctx->stats.sah_node_cost = owner->stats.sah_node_cost; ctx->stats.sah_tri_cost = owner->stats.sah_tri_cost;
     ctx->scene_borrowed = true;
+    ctx->scene_owner = owner;
+    owner->borrowers.push_back(ctx);
     ctx->scene_kind = 2;
     ctx->bvh_valid = true;
     ctx->have_gbuffer = ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = ctx->have_temporal = false;
@@ -349,7 +374,9 @@ int mrt_primary_rays(mrt_context* ctx, uint32_t w, uint32_t h, const mrt_primary
     MRT_ENTER(ctx);
     if (!c || w == 0 || h == 0) return mrt_fail(ctx, MRT_ERR_INVALID, "primary rays: bad size %ux%u or NULL constants", w, h);
     if (ctx->scene_kind == 0) return mrt_fail(ctx, MRT_ERR_STATE, "primary rays: no scene");
-    if (ctx->scene_kind == 2 && !ctx->bvh_valid) return mrt_fail(ctx, MRT_ERR_STATE, "primary rays: mesh uploaded but not built");
+    if (ctx->scene_kind == 2 && !ctx->bvh_valid)
+        return mrt_fail(ctx, MRT_ERR_STATE, ctx->scene_borrowed ? "primary rays: the borrowed scene changed (call mrt_scene_share again)"
+                                                                 : "primary rays: mesh uploaded but not built");
     uint32_t rows = partition_local_rows(ctx->part, h);
     if (w != ctx->W || h != ctx->H || rows != ctx->local_rows) ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;
     ctx->W = w; ctx->H = h; ctx->local_rows = rows;

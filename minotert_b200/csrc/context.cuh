@@ -87,6 +87,8 @@ struct mrt_context {
     uint32_t nverts = 0, ntris = 0;
     bool bvh_valid = false;
     bool scene_borrowed = false;  // pos/idx/albedo/nodes/tris alias another context's arrays (mrt_scene_share): never freed here
+    mrt_context* scene_owner = nullptr;      // whose arrays those are
+    std::vector<mrt_context*> borrowers;     // contexts that alias THIS context's scene: made stale before it changes
 
     // LBVH build scratch + result (bvh_build.cu)
     DevArray<float4> prim_lo, prim_hi;      // per primitive AABB

@@ -576,12 +576,17 @@ def test_shared_scene_renders_the_same_frames(gpu_ctx, oracle, sky_inputs, blue_
         for call in (lambda: other.build(), lambda: other.build(capi.BUILD_REFIT), lambda: other.update_positions(pos)):
             with pytest.raises(capi.MinoteError):
                 call()
-        # owner animates + refits (borrower idle), shares again: the borrower sees the new geometry
-        other.sync()
+        # owner animates + refits while the borrower has a frame in flight: the library waits for that frame, the
+        # borrower is stale until it shares again, then it sees the new geometry
+        render(other, 6)
         pos2 = pos.copy()
         pos2[:, 1] += 0.0004 * np.sin(40.0 * pos[:, 0]).astype(np.float32)
         owner.update_positions(pos2)
         owner.build(capi.BUILD_REFIT)
+        with pytest.raises(capi.MinoteError, match="mrt_scene_share again"):
+            render(other, 7)
+        with pytest.raises(capi.MinoteError):
+            other.trace_rays(o, d)
         other.share_scene(owner)
         render(other, 5)
         render(owner, 5)
@@ -602,6 +607,37 @@ def test_shared_scene_renders_the_same_frames(gpu_ctx, oracle, sky_inputs, blue_
         other.close()  # borrower destroyed first; the owner (fixture) still works afterwards
     ids_a3, _ = owner.trace_rays(o, d)
     assert np.array_equal(ids_a3, ids_bf2)
+
+
+def test_shared_scene_owner_destroyed_first(oracle, sky_inputs, blue_noise):
+    """Destroying the owner while a borrower still exists leaves the borrower without a scene (errors, no dangling
+    device pointers); the borrower can take a scene of its own afterwards."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.cornell()
+    w, h = 64, 48
+    cam = camera_for(oracle, view, w, h)
+    pc, scn = oracle.constants(cam)
+    owner, other = capi.Context(0), capi.Context(0)
+    try:
+        owner.upload_mesh(pos, idx, alb)
+        owner.build()
+        other.upload_blue_noise(blue_noise)
+        setup_sky(other, oracle, atmo, cam.position[:])
+        other.share_scene(owner)
+        other.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+        other.secondary_rays(as_capi(scn, capi.SecondaryConstants), 1, 1)   # in flight while the owner goes away
+        owner.close()
+        with pytest.raises(capi.MinoteError):
+            other.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+        with pytest.raises(capi.MinoteError):
+            other.build()
+        other.upload_mesh(pos, idx, alb)
+        other.build()
+        other.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+        assert (other.readback(capi.BUF_VISIBILITY) != capi.MISS_ID).any()
+    finally:
+        other.close()
+        owner.close()
 
 
 def test_renderer_frames_in_flight(oracle, blue_noise):
