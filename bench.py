@@ -187,9 +187,10 @@ def run_ours(args):
     bn = np.ascontiguousarray(np.array(Image.open(os.path.join(ROOT, "assets", "blue_noise.png")).convert("RGBA"), np.uint8))
 
     # host modules: Cuda::Provider + Renderer::Provider, scene upload + BVH build (setup, untimed)
-    # frames in flight (world == 1): Renderer::draw rotates through that many frame contexts, as the reference does
-    # (renderer.ixx:36); frame context 0 owns the scene and is the one the device-timed sequential pass runs on
-    in_flight = max(1, min(3, args.frames_in_flight)) if world == 1 else 1
+    # frames in flight: Renderer::draw rotates through that many frame contexts, as the reference does
+    # (renderer.ixx:36); frame context 0 owns the scene and is the one the device-timed sequential pass runs on.
+    # N > 1: the e2e loop rotates the frame contexts by hand (NCCL reduce of each frame's accumulator in between)
+    in_flight = max(1, min(3, args.frames_in_flight))
     r = host.Renderer(w, h, bn, device=local, frames_in_flight=in_flight)
     r.set_option("builder", 1 if args.builder == "ploc" else 0)
     r.set_option("ploc_radius", args.ploc_radius)
@@ -385,20 +386,40 @@ def run_ours(args):
     torch.cuda.synchronize()
     r.stats_reset()  # zeroes the device-side running ray totals (every frame context)
     e2e_rays, t0 = 0, time.perf_counter()
+    if world > 1:  # zero-copy views of every frame context's accumulator + its stream
+        def accum_view(c):
+            ptr, _ = c.buffer(capi.BUF_ACCUM)
+
+            class W:
+                __cuda_array_interface__ = {"shape": (npix * 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+            return torch.as_tensor(W(), device=f"cuda:{local}")
+        fc_accum = [accum_view(c) for c in frame_ctxs]
+        fc_stream = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c in frame_ctxs]
+        frame0 = r.frame_count()
     for i in range(args.steps):
         if world > 1:
-            frame(r.frame_count() * world + rank + 1 + i)
+            k = i % in_flight
+            c = frame_ctxs[k]
+            pc, sc = host.camera_constants(cam, cam, (frame0 + i) * world + rank + 1)
+            c.primary_rays(w, h, pc)
+            c.secondary_rays(sc, spp, bounces, 0)
+            with torch.cuda.stream(fc_stream[k]):
+                dist.reduce(fc_accum[k], dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
-                ctx.readback_async(capi.BUF_LDR, fb_ptrs[i & 1], fb.numel())
-                ctx.readback_wait(1)
+                c.tonemap("amd", 1.0, amd, capi.BUF_ACCUM)
+                c.readback_async(capi.BUF_LDR, fb_ptrs[i % nfb], fb.numel())
+                for back in range(in_flight):  # all but the newest in_flight frames have landed in host memory
+                    frame_ctxs[(k - back) % in_flight].readback_wait(1)
         else:
             r.draw(cam)                                              # host: camera -> constants -> sky view -> primary -> secondary -> tonemap
             r.read_framebuffer_async(fb_ptrs[i % nfb], fb.numel())   # D2H of this frame on its context's copy stream
             r.wait_framebuffer(in_flight)                            # all but the newest in_flight frames have landed in host memory
     if world > 1 and rank != 0:
-        ctx.sync()
+        for c in frame_ctxs:
+            c.sync()
     elif world > 1:
-        ctx.readback_wait(0)
+        for c in frame_ctxs:
+            c.readback_wait(0)
     else:
         r.wait_framebuffer(0)
     e2e_s = time.perf_counter() - t0

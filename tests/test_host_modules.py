@@ -68,3 +68,11 @@ def test_renderer_fails_loudly_without_gpu(blue_noise):
         pytest.skip("GPU present")
     with pytest.raises(capi.MinoteError, match="no CPU fallback"):
         host.Renderer(64, 64, blue_noise)
+
+
+def test_frames_in_flight_range_is_checked(blue_noise):
+    """Cuda::Provider(device, framesInFlight): 1..3 (the reference's InflightFrames, renderer.ixx:36); anything else is
+    a logic error raised before any device is touched."""
+    for n in (0, 4, -1):
+        with pytest.raises(capi.MinoteError, match="frames in flight"):
+            host.Renderer(64, 64, blue_noise, frames_in_flight=n)
