@@ -454,10 +454,9 @@ int mrt_tonemap(mrt_context* ctx, int mode, float exposure, const float* params,
     if (!ctx->have_accum) return mrt_fail(ctx, MRT_ERR_STATE, "tonemap before secondary rays");
     if (source == MRT_BUF_DENOISED && !ctx->have_denoised) return mrt_fail(ctx, MRT_ERR_STATE, "tonemap of the denoised image before mrt_denoise_bilateral");
     if (source == MRT_BUF_TEMPORAL && !ctx->have_temporal) return mrt_fail(ctx, MRT_ERR_STATE, "tonemap of the temporal image before mrt_temporal_accumulate");
-    if (source == MRT_BUF_COLOR && !ctx->have_color) {
-        void* p; size_t b;
-        MRT_TRY(buffer_info(ctx, MRT_BUF_COLOR, &p, &b));
-    }
+    // source COLOR on the triangle path while the RGBA16F image has not been asked for: tonemap_run reads the
+    // accumulator and rounds through fp16 in registers -- same bits as resolving into MRT_BUF_COLOR first, one launch
+    // and 24 B/px less (the image is still resolved lazily when mrt_buffer / the denoiser ask for it)
     cudaEventRecord(ctx->ev[6], ctx->stream);
     int s = tonemap_run(ctx, mode, exposure, params, nparams, source);
     cudaEventRecord(ctx->ev[7], ctx->stream);

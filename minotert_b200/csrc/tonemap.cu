@@ -117,16 +117,19 @@ MRT_D uchar4 encode_ldr(float3 mapped) {
 }
 
 // SRC 1: read the fp32 accumulator and divide by its sample count (row n7); SRC 2: the denoiser's RGBA8 unorm
-// image (denoiser.ixx:56, texel = k/255); SRC 0: the reference's RGBA16F colour image (row a12).
+// image (denoiser.ixx:56, texel = k/255); SRC 0: the reference's RGBA16F colour image (row a12); SRC 3: that image
+// computed on the fly from the accumulator (average rounded to fp16 exactly as k_accum_to_color16 stores it).
 template <int SRC>
 __global__ void __launch_bounds__(256) k_tonemap(TonemapParams T, const float4* __restrict__ accum,
                                                  const uint2* __restrict__ color16, const uchar4* __restrict__ rgba8,
                                                  uchar4* __restrict__ ldr, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float3 src;
-        if (SRC == 1) {
+        if (SRC == 1 || SRC == 3) {
             float4 a = __ldcs(&accum[i]);
             src = a.w > 0.0f ? f3(a.x / a.w, a.y / a.w, a.z / a.w) : f3s(0.0f);
+            if (SRC == 3)
+                src = f3(f16_bits_to_f32(f32_to_f16_bits(src.x)), f16_bits_to_f32(f32_to_f16_bits(src.y)), f16_bits_to_f32(f32_to_f16_bits(src.z)));
         } else if (SRC == 2) {
             uchar4 c = __ldcs(&rgba8[i]);
             src = f3((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f);
@@ -171,6 +174,8 @@ int tonemap_run(mrt_context* ctx, int mode, float exposure, const float* params,
         k_tonemap<1><<<grid, 256, 0, ctx->stream>>>(T, ctx->tp_rgba[ctx->tp_cur].p, nullptr, nullptr, ldr.p, n);
     else if (source == MRT_BUF_DENOISED)
         k_tonemap<2><<<grid, 256, 0, ctx->stream>>>(T, nullptr, nullptr, ctx->denoised.p, ldr.p, n);
+    else if (!ctx->have_color)  // triangle path, RGBA16F image not materialised: same values straight from the accumulator
+        k_tonemap<3><<<grid, 256, 0, ctx->stream>>>(T, ctx->accum.p, nullptr, nullptr, ldr.p, n);
     else
         k_tonemap<0><<<grid, 256, 0, ctx->stream>>>(T, nullptr, reinterpret_cast<const uint2*>(ctx->color16.p), nullptr,
                                                     ldr.p, n);

@@ -681,3 +681,29 @@ def test_renderer_frames_in_flight(oracle, blue_noise):
         assert np.array_equal(one[f], three[f]), f"frame {f + 1}"
     assert not np.array_equal(one[0], one[1])      # different seeds
     assert not np.array_equal(one[3], one[4])      # the refit is visible
+
+
+def test_tonemap_of_color_without_materialising_it(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """Triangle path, tonemap source COLOR: while nobody has asked for the RGBA16F image the tonemapper reads the fp32
+    accumulator and rounds its average through fp16 in registers; the framebuffer is bit-identical to resolving
+    MRT_BUF_COLOR first, and to the oracle's tonemapper on that RGBA16F image within its 1-code-value bar."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h = 192, 128
+    cam = camera_for(oracle, view, w, h)
+    pc, scn = oracle.constants(cam, frame=2)
+    setup_sky(gpu_ctx, oracle, atmo, cam.position[:])
+    gpu_ctx.upload_blue_noise(blue_noise)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    gpu_ctx.build()
+    gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+    gpu_ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 2, 2)
+    launches0 = gpu_ctx.stats().kernel_launches
+    gpu_ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_COLOR)
+    assert gpu_ctx.stats().kernel_launches == launches0 + 1      # no resolve kernel
+    direct = gpu_ctx.readback(capi.BUF_LDR).copy()
+    col16 = gpu_ctx.readback(capi.BUF_COLOR)                      # materialises the RGBA16F image
+    gpu_ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_COLOR)
+    assert np.array_equal(gpu_ctx.readback(capi.BUF_LDR), direct)
+    d = np.abs(direct.astype(int) - oracle.tonemap("amd", col16).astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.01

@@ -42,7 +42,9 @@ def main():
     fb = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
     fb_ptr = C.c_void_p(fb.data_ptr())
     # pre-generate the animated vertex arrays (host-side animation is not what is measured)
-    frames = [np.ascontiguousarray(scenes.animate(pos, f / 60.0)) for f in range(8)]
+    # ... in pinned host memory, as a renderer that streams vertex data every frame would keep them
+    pinned = [torch.from_numpy(np.ascontiguousarray(scenes.animate(pos, f / 60.0))).pin_memory() for f in range(8)]
+    frames = [t.numpy() for t in pinned]
     r.draw(cam)
     r.read_framebuffer_into(fb_ptr, fb.numel())
 
