@@ -222,3 +222,20 @@ def test_golden_fixtures_reproduce(oracle, blue_noise):
     acc, cvis, crays = scn.render(64, 64, pcc, scc, blue_noise, atmo, tr2, vw2, 2, 2, use_bvh=True)
     assert np.array_equal(cvis, g["cornell_vis"]) and np.array_equal(acc, g["cornell_accum"])
     assert list(crays) == list(g["cornell_rays"])
+
+
+def test_golden_fixtures_v2_reproduce(oracle):
+    """The stages after the path tracer (bilateral denoiser, temporal reprojection): the oracle still produces, bit
+    for bit, tests/golden/oracle_v2.npz (generated by tests/golden/make_golden_v2.py, whose compute() is reused here)."""
+    import importlib.util
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_v2", os.path.join(here, "make_golden_v2.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    got = mod.compute()
+    g = np.load(os.path.join(here, "oracle_v2.npz"))
+    assert sorted(got) == sorted(g.files)
+    for k in g.files:
+        assert np.array_equal(got[k].view(np.uint8), g[k].view(np.uint8)), k
+    # the fixture exercises the history: a third of the pixels (the sphere hits) carry more than one frame
+    assert (g["temporal_count"] > 1).mean() > 0.3 and g["temporal_count"].max() > 3.0
