@@ -149,3 +149,42 @@ def test_call_order_errors(gpu_ctx, oracle):
         gpu_ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), 1, 1)
     with pytest.raises(capi.MinoteError):
         gpu_ctx.readback(capi.BUF_LDR)
+
+
+def test_minote_headless_matches_the_renderer(oracle, blue_noise, tmp_path):
+    """minote_headless (App::run without a window, host/main.cpp): the C++ executable over the host modules, with the
+    reference's 3 frames in flight and its default pipeline (8 spp x 8 bounces, bilateral denoiser, AMD tonemapper),
+    writes the same last frame as the same draw() calls made through the Python bindings with one frame in flight."""
+    import os
+    import subprocess
+    from minotert_b200 import host
+    exe = os.path.join(os.path.dirname(os.path.abspath(host.__file__)), "minote_headless")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    raw = tmp_path / "blue_noise.rgba8"
+    raw.write_bytes(np.ascontiguousarray(blue_noise, np.uint8).tobytes())
+    w, h, frames = 240, 135, 5
+    images = {}
+    for in_flight in (3, 1):
+        out = tmp_path / f"out{in_flight}.ppm"
+        p = subprocess.run([exe, str(raw), str(frames), str(w), str(h), str(out), str(in_flight)], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0, p.stderr
+        assert p.stdout.count("Frame time:") == frames
+        data = out.read_bytes()
+        header = f"P6\n{w} {h}\n255\n".encode()
+        assert data.startswith(header) and len(data) == len(header) + w * h * 3
+        images[in_flight] = np.frombuffer(data[len(header):], np.uint8).reshape(h, w, 3)
+    assert np.array_equal(images[3], images[1])
+    r = host.Renderer(w, h, blue_noise)   # the C++ defaults: nothing configured
+    try:
+        r.set_spheres(oracle.REFERENCE_SPHERES)
+        cam = host.default_camera(w, h)
+        for _ in range(frames):
+            r.draw(cam)
+        fb = r.read_framebuffer()
+    finally:
+        r.close()
+    assert np.array_equal(fb[..., :3], images[3])
+    assert fb[..., :3].std() > 10  # an image, not a constant
+    # a bad frames-in-flight count is reported, not crashed on
+    p = subprocess.run([exe, str(raw), "1", str(w), str(h), str(tmp_path / "x.ppm"), "7"], capture_output=True, text=True, timeout=60)
+    assert p.returncode != 0 and "frames in flight" in p.stderr
