@@ -10,9 +10,12 @@ A step is one frame of BASELINE.json configs[1]: the ~260k-triangle procedural s
 per-frame call order (src/gfx/renderer.ixx:56-62).  Rays are counted as the reference's structure
 implies: pixels x 1 primary + every secondary ray for which a traversal was issued.
 
-value : device-timed (CUDA events on the context's stream), scene/BVH/LUTs resident in HBM.
-e2e   : wall clock through the host modules' Renderer::draw(camera) (C++20 modules -> C ABI), camera PODs
-        coming from host memory and the RGBA8 framebuffer read back into pinned host memory every step.
+value : device-timed (CUDA events on the context's stream), scene/BVH/LUTs resident in HBM, one frame at a time
+        (the pass the per-kernel times and the traversal kernel's roofline are measured in).
+pipelined : the same steps device-timed with 3 frames in flight (frame contexts sharing one BVH).
+e2e   : wall clock through the host modules' Renderer::draw(camera) (C++20 modules -> C ABI) with the reference's
+        3 frames in flight, camera PODs coming from host memory and the RGBA8 framebuffer read back into pinned
+        host memory every step.
 N > 1 : sample-set partition with a replicated BVH: rank r renders frame (step*N + r + 1), the fp32
         accumulators are summed onto rank 0 with NCCL (reduce) and rank 0 tonemaps.  Weak scaling.
 """
