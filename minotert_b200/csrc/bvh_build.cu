@@ -876,14 +876,22 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop 
 // Quantisation grid of a wide node, per axis: 255 steps of size 2^e starting two steps below the node
 // box, sized so that 250 steps span the box.  Every child plane then lies strictly inside the grid with
 // room to spare, which lets the traversal fold the integer->float decode into its FMA (trace.cuh) at the
-// price of a plane error of at most 1/512 step; planes are rounded outward with 1/128 step of slack.
-MRT_D uint32_t grid_exponent(float ext) {
+// price of a plane error of at most 1/256 step; planes are rounded outward with 1/64 step of slack.
+// The step is never finer than 2 ulp of the largest coordinate magnitude m on the axis (nor than 2^-126): fp32
+// coordinates cannot resolve a finer grid, the grid origin nlo - 2 step would round by more than a fraction of a
+// step, and a flat node (extent 0) still gets a slab of finite thickness.  The CPU restatement of this quantiser and
+// of the traversal's slab test (oracle/minote_oracle.c orc_wide_node_*) is what tests/test_oracle_wide_node.py uses
+// to check, without a GPU, that no child box the exact ray touches is ever culled.
+MRT_D uint32_t grid_exponent(float ext, float m) {
     // biased exponent e such that 2^(e-127) * 250 >= ext
     float s = ext / 250.0f;
     uint32_t b = __float_as_uint(s);
     uint32_t e = (b >> 23) & 0xFFu;
     if (b & 0x7FFFFFu) e += 1;
     while (e < 254u && __uint_as_float(e << 23) * 250.0f < ext) e++;  // guard against rounding in the division
+    const uint32_t em = (__float_as_uint(m) >> 23) & 0xFFu;
+    const uint32_t emin = em > 23u ? em - 22u : 1u;
+    if (e < emin) e = emin;
     return e > 254u ? 254u : e;
 }
 
@@ -906,7 +914,8 @@ k_emit_nodes(BinTree T, uint32_t num_nodes, const int32_t* __restrict__ slot_nod
         nlo = f3(fminf(nlo.x, lo.x), fminf(nlo.y, lo.y), fminf(nlo.z, lo.z));
         nhi = f3(fmaxf(nhi.x, hi.x), fmaxf(nhi.y, hi.y), fmaxf(nhi.z, hi.z));
     }
-    uint32_t ex = grid_exponent(nhi.x - nlo.x), ey = grid_exponent(nhi.y - nlo.y), ez = grid_exponent(nhi.z - nlo.z);
+    uint32_t ex = grid_exponent(nhi.x - nlo.x, fmaxf(fabsf(nlo.x), fabsf(nhi.x))), ey = grid_exponent(nhi.y - nlo.y, fmaxf(fabsf(nlo.y), fabsf(nhi.y))),
+             ez = grid_exponent(nhi.z - nlo.z, fmaxf(fabsf(nlo.z), fabsf(nhi.z)));
     float sc[3] = {__uint_as_float(ex << 23), __uint_as_float(ey << 23), __uint_as_float(ez << 23)};
     float org[3] = {nlo.x - 2.0f * sc[0], nlo.y - 2.0f * sc[1], nlo.z - 2.0f * sc[2]};
     uint32_t qlo[3][2] = {{0, 0}, {0, 0}, {0, 0}}, qhi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -922,15 +931,14 @@ k_emit_nodes(BinTree T, uint32_t num_nodes, const int32_t* __restrict__ slot_nod
         float4 lo4 = T.lo[c], hi4 = T.hi[c];
         float clo[3] = {lo4.x, lo4.y, lo4.z}, chi[3] = {hi4.x, hi4.y, hi4.z};
         for (int a = 0; a < 3; a++) {
-            float ql = 0.0f, qh = 255.0f;
-            if (sc[a] > 0.0f) {
-                const float slack = sc[a] * 0.015625f;  // 1/64 step; the traversal's decode error is <= 1/256 step
-                ql = fminf(fmaxf(floorf((clo[a] - org[a]) / sc[a] - 0.02f), 0.0f), 255.0f);
-                qh = fminf(fmaxf(ceilf((chi[a] - org[a]) / sc[a] + 0.02f), 0.0f), 255.0f);
-                // outward rounding under the decode arithmetic (origin + q * scale)
-                while (ql > 0.0f && org[a] + ql * sc[a] > clo[a] - slack) ql -= 1.0f;
-                while (qh < 255.0f && org[a] + qh * sc[a] < chi[a] + slack) qh += 1.0f;
-            }
+            // outward rounding with 1/64 step of slack (the traversal's decode error is <= 1/256 step).  The plane
+            // origin + q * step is evaluated in double, i.e. exactly: that is the plane the traversal's
+            // (origin - o) / d + q * (step / d) sees, whereas an fp32 sum would round to the coordinates' ulp
+            const double o = (double)org[a], st = (double)sc[a], slack = st * 0.015625;
+            float ql = fminf(fmaxf(floorf((clo[a] - org[a]) / sc[a] - 0.02f), 0.0f), 255.0f);
+            float qh = fminf(fmaxf(ceilf((chi[a] - org[a]) / sc[a] + 0.02f), 0.0f), 255.0f);
+            while (ql > 0.0f && o + (double)ql * st > (double)clo[a] - slack) ql -= 1.0f;
+            while (qh < 255.0f && o + (double)qh * st < (double)chi[a] + slack) qh += 1.0f;
             qlo[a][s >> 2] |= (uint32_t)ql << (8 * (s & 3));
             qhi[a][s >> 2] |= (uint32_t)qh << (8 * (s & 3));
         }

@@ -1295,6 +1295,108 @@ static float uchimura1(float x, float P, float a, float m, float l, float c, flo
     return T * w0 + Lc * w1 + Sc * w2;
 }
 
+/* ---- compressed 8-wide BVH node (contract in minote_oracle.h) ---- */
+static inline float bits_f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t f_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+/* bvh_build.cu grid_exponent: biased exponent e with 2^(e-127) * 250 >= ext, and never below 2 ulp of the largest
+ * coordinate magnitude m on the axis (nor below 2^-126): a finer grid could not be resolved by fp32 coordinates, and
+ * the grid origin nlo - 2 step would round by more than a fraction of a step */
+static uint32_t wide_grid_exponent(float ext, float m) {
+    float s = ext / 250.0f;
+    uint32_t b = f_bits(s);
+    uint32_t e = (b >> 23) & 0xFFu;
+    if (b & 0x7FFFFFu) e += 1;
+    while (e < 254u && bits_f(e << 23) * 250.0f < ext) e++;
+    const uint32_t em = (f_bits(m) >> 23) & 0xFFu;
+    const uint32_t emin = em > 23u ? em - 22u : 1u;
+    if (e < emin) e = emin;
+    return e > 254u ? 254u : e;
+}
+
+/* bvh_build.cu k_emit_nodes, the quantisation part.  Plane positions origin + q * step are evaluated in double
+ * (exact for fp32 operands), because that is the plane the traversal's (origin - o) / d + q * (step / d) sees. */
+void orc_wide_node_quantize(const float lo[8][3], const float hi[8][3], uint32_t present, orc_wide_node* out) {
+    float nlo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, nhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int s = 0; s < 8; s++) {
+        if (!(present & (1u << s))) continue;
+        for (int a = 0; a < 3; a++) {
+            nlo[a] = fminf(nlo[a], lo[s][a]);
+            nhi[a] = fmaxf(nhi[a], hi[s][a]);
+        }
+    }
+    uint32_t e[3];
+    float sc[3], org[3];
+    for (int a = 0; a < 3; a++) {
+        e[a] = wide_grid_exponent(nhi[a] - nlo[a], fmaxf(fabsf(nlo[a]), fabsf(nhi[a])));
+        sc[a] = bits_f(e[a] << 23);
+        org[a] = nlo[a] - 2.0f * sc[a];
+    }
+    memset(out, 0, sizeof *out);
+    for (int a = 0; a < 3; a++) out->w[a] = f_bits(org[a]);
+    out->w[3] = e[0] | (e[1] << 8) | (e[2] << 16);
+    for (int s = 0; s < 8; s++) {
+        for (int a = 0; a < 3; a++) {
+            float ql = 255.0f, qh = 0.0f; /* empty slot: inverted box */
+            if (present & (1u << s)) {
+                const double o = (double)org[a], st = (double)sc[a], slack = st * 0.015625;
+                ql = fminf(fmaxf(floorf((lo[s][a] - org[a]) / sc[a] - 0.02f), 0.0f), 255.0f);
+                qh = fminf(fmaxf(ceilf((hi[s][a] - org[a]) / sc[a] + 0.02f), 0.0f), 255.0f);
+                while (ql > 0.0f && o + (double)ql * st > (double)lo[s][a] - slack) ql -= 1.0f;
+                while (qh < 255.0f && o + (double)qh * st < (double)hi[s][a] + slack) qh += 1.0f;
+            }
+            out->w[4 + 2 * a + (s >> 2)] |= (uint32_t)ql << (8 * (s & 3));
+            out->w[10 + 2 * a + (s >> 2)] |= (uint32_t)qh << (8 * (s & 3));
+        }
+    }
+}
+
+/* trace.cuh lane_begin + lane_node_step (TRACE_DP4A_NEAR = 1) */
+void orc_wide_node_test(const orc_wide_node* node, uint32_t n, const float* o, const float* d, const float* t_best,
+                        uint32_t* hits) {
+    const float KNEAR = 0.99999952f, KFAR = 1.00000048f, tiny = 1e-20f;
+    const uint32_t K = 0x47000000u; /* 2^15 */
+    for (uint32_t r = 0; r < n; r++) {
+        float idn[3], idf[3];
+        int pos[3];
+        for (int a = 0; a < 3; a++) {
+            float da = d[3 * r + a];
+            float dd = fabsf(da) > tiny ? da : copysignf(tiny, da);
+            float idir = 1.0f / dd;
+            idn[a] = idir * KNEAR;
+            idf[a] = idir * KFAR;
+            pos[a] = !(idir < 0.0f);
+        }
+        const float tlimit = t_best[r] >= 3.0e38f ? 3.0e38f : t_best[r] * KFAR;
+        float sn2[3], bn[3], sf[3], bf[3];
+        for (int a = 0; a < 3; a++) {
+            const float st = bits_f(((node->w[3] >> (8 * a)) & 0xFFu) << 23);
+            const float dx = bits_f(node->w[a]) - o[3 * r + a];
+            const float sn = st * idn[a];
+            sf[a] = st * idf[a];
+            bn[a] = fmaf(-65536.0f, sn, dx * idn[a]);
+            sn2[a] = sn * 2.0f;
+            bf[a] = fmaf(-32768.0f, sf[a], dx * idf[a]);
+        }
+        uint32_t mask = 0;
+        for (int s = 0; s < 8; s++) {
+            float t0[3], t1[3];
+            for (int a = 0; a < 3; a++) {
+                const uint32_t ql = (node->w[4 + 2 * a + (s >> 2)] >> (8 * (s & 3))) & 0xFFu;
+                const uint32_t qh = (node->w[10 + 2 * a + (s >> 2)] >> (8 * (s & 3))) & 0xFFu;
+                const uint32_t qn = pos[a] ? ql : qh, qf = pos[a] ? qh : ql;
+                t0[a] = fmaf(bits_f(K + 128u * qn), sn2[a], bn[a]); /* IDP.4A decode: 2^15 + q/2 */
+                t1[a] = fmaf(bits_f(K | (qf << 8)), sf[a], bf[a]);  /* PRMT decode: 2^15 + q */
+            }
+            const float tmin = fmaxf(fmaxf(t0[0], t0[1]), t0[2]);
+            const float tmax = fminf(fminf(t1[0], t1[1]), t1[2]);
+            const uint32_t neg = f_bits(tmax - tmin) | f_bits(tlimit - tmin) | f_bits(tmax);
+            if (!(neg >> 31)) mask |= 1u << s;
+        }
+        hits[r] = mask;
+    }
+}
+
 /* ---- temporal reprojection (contract in minote_oracle.h) ----
  * Consumes the motion buffer of src/gpu/primaryRay.comp:73-75.  fp32, no contraction; the same expression order as
  * k_temporal (minotert_b200/csrc/temporal.cu), so the two agree bit for bit. */

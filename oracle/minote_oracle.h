@@ -159,6 +159,24 @@ void orc_denoise_bilateral(uint32_t w, uint32_t h, const uint16_t* color16 /*RGB
                            float sigma, float kSigma, float threshold, float nearPlane,
                            uint32_t frameCounter, uint8_t* rgba8);
 
+/* ---- compressed 8-wide BVH node: quantiser + slab test (north_star row n3; no reference counterpart) ----
+ * CPU restatement of the product's node arithmetic, operation for operation, so that its central claim can be
+ * checked WITHOUT a GPU: the fp32 slab test on the quantised planes never culls a child box the exact ray touches.
+ *   orc_wide_node_quantize : minotert_b200/csrc/bvh_build.cu grid_exponent + k_emit_nodes (grid origin two steps
+ *                            below the node box, power-of-two step with 250 steps across the box, planes rounded
+ *                            outward with >= 1/64 step of slack, empty slot = (255, 0))
+ *   orc_wide_node_test     : minotert_b200/csrc/trace.cuh lane_begin + lane_node_step (1/d scaled by 1 -/+ 2^-21,
+ *                            far planes decoded as the float 2^15 + q, near planes as 2^15 + q/2, one FMA per plane,
+ *                            hit <=> no sign bit in (tmax - tmin) | (tlimit - tmin) | tmax)
+ * Node words: w[0..2] grid origin (fp32 bits), w[3] = ex | ey << 8 | ez << 16 (biased exponents of the step),
+ * w[4..9] = qlo x[0..3], x[4..7], y.., z..; w[10..15] = qhi likewise.  present: bit s = slot s holds a child. */
+typedef struct { uint32_t w[16]; } orc_wide_node;
+void orc_wide_node_quantize(const float lo[8][3], const float hi[8][3], uint32_t present, orc_wide_node* out);
+/* bit s of the result: child s passes the slab test for the ray (o, d) with the current closest hit at t_best
+ * (pass 3.0e38f for "none").  Rays are tested in batches: o, d: n x 3 floats, t_best: n floats, hits: n words. */
+void orc_wide_node_test(const orc_wide_node* node, uint32_t n, const float* o, const float* d, const float* t_best,
+                        uint32_t* hits);
+
 /* ---- temporal reprojection ----
  * No reference counterpart: the reference WRITES the motion of every primary hit between prevView and view
  * (src/gpu/primaryRay.comp:73-75, RG16F, pathtracer.ixx:63-69) and nothing reads it (renderer.ixx:61).  This is the

@@ -28,6 +28,11 @@ class Camera(C.Structure):
                 ("lookSpeed", C.c_float), ("moveSpeed", C.c_float)]
 
 
+class WideNode(C.Structure):
+    """orc_wide_node: the quantised 8-wide BVH node of the product, as the oracle restates it."""
+    _fields_ = [("w", C.c_uint32 * 16)]
+
+
 class Mat4(C.Structure):
     _fields_ = [("m", (C.c_float * 4) * 4)]
 
@@ -131,6 +136,8 @@ def lib():
         "orc_primary_rays_spheres": (None, [C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.POINTER(Sphere), C.c_uint32, u32p, u16p, u16p, u16p]),
         "orc_secondary_rays_spheres": (None, [C.c_uint32, C.c_uint32, C.POINTER(SecondaryConstants), C.POINTER(Sphere), C.c_uint32, u32p, u16p, u16p, u8p, C.c_uint32, C.c_uint32, C.POINTER(AtmosphereParams), u16p, u32p, C.c_uint32, C.c_uint32, u16p, f32p, u64p]),
         "orc_denoise_bilateral": (None, [C.c_uint32, C.c_uint32, u16p, u16p, u16p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32, u8p]),
+        "orc_wide_node_quantize": (None, [f32p, f32p, C.c_uint32, C.POINTER(WideNode)]),
+        "orc_wide_node_test": (None, [C.POINTER(WideNode), C.c_uint32, f32p, f32p, f32p, u32p]),
         "orc_temporal_accumulate": (None, [C.c_uint32, C.c_uint32, f32p, u32p, u16p, C.c_int, f32p, f32p, u32p, C.c_float, f32p, f32p]),
         "orc_tonemap": (None, [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, f32p, u8p]),
         "orc_tonemap_pixel": (None, [C.c_int, f32p, C.c_float, f32p, f32p]),
@@ -270,6 +277,26 @@ def denoise_bilateral(color16, depth16, normal16, params=BILATERAL_DEFAULT, near
     c, d, n = (np.ascontiguousarray(a, np.uint16) for a in (color16, depth16, normal16))
     lib().orc_denoise_bilateral(w, h, _p(c, C.c_uint16), _p(d, C.c_uint16), _p(n, C.c_uint16), params[0], params[1],
                                 params[2], near, frame, _p(out, C.c_uint8))
+    return out
+
+
+def wide_node_quantize(lo, hi, present=0xFF):
+    """lo, hi: (8, 3) float32 child boxes -> WideNode (bvh_build.cu k_emit_nodes restated)."""
+    lo = np.ascontiguousarray(lo, np.float32).reshape(8, 3)
+    hi = np.ascontiguousarray(hi, np.float32).reshape(8, 3)
+    node = WideNode()
+    lib().orc_wide_node_quantize(_p(lo, C.c_float), _p(hi, C.c_float), present, C.byref(node))
+    return node
+
+
+def wide_node_test(node, o, d, t_best=None):
+    """8-bit hit masks of the node's children for rays (o, d): (n, 3) float32 each (trace.cuh lane_node_step restated)."""
+    o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+    n = o.shape[0]
+    tb = np.full(n, 3.0e38, np.float32) if t_best is None else np.ascontiguousarray(t_best, np.float32)
+    out = np.zeros(n, np.uint32)
+    lib().orc_wide_node_test(C.byref(node), n, _p(o, C.c_float), _p(d, C.c_float), _p(tb, C.c_float), _p(out, C.c_uint32))
     return out
 
 

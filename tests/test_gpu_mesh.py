@@ -707,3 +707,39 @@ def test_tonemap_of_color_without_materialising_it(gpu_ctx, oracle, sky_inputs, 
     assert np.array_equal(gpu_ctx.readback(capi.BUF_LDR), direct)
     d = np.abs(direct.astype(int) - oracle.tonemap("amd", col16).astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 0.01
+
+
+@pytest.mark.parametrize("shift", [0.0, 10.0, 1000.0])
+def test_axis_aligned_walls_far_from_origin(gpu_ctx, shift):
+    """Flat leaf boxes and flat nodes (the Cornell walls are axis-aligned planes) at coordinates where one ulp is up to
+    1 % of the scene: rays that start exactly on vertices, edges and wall planes, axis-parallel rays running inside
+    a wall's plane, and random rays -- BVH closest hits == brute force, bit for bit.  (The node quantiser keeps its
+    grid step >= 2 ulp of the coordinates and evaluates planes exactly; CPU proof: tests/test_oracle_wide_node.py.)"""
+    pos, idx, alb, _ = scenes.cornell()
+    pos = (pos.astype(np.float64) + shift).astype(np.float32)
+    rng = np.random.default_rng(11)
+    for builder in (0, 1):
+        gpu_ctx.set_option("builder", builder)
+        gpu_ctx.upload_mesh(pos, idx, alb)
+        gpu_ctx.build()
+        lo, hi = pos.min(0), pos.max(0)
+        ext = (hi - lo).max()
+        o1, d1 = random_rays(6000, lo - 0.1 * ext, hi + 0.1 * ext, 5)
+        # origins exactly on mesh vertices / edge midpoints, random directions
+        verts = pos[rng.integers(0, pos.shape[0], 3000)]
+        tri = idx[rng.integers(0, idx.shape[0], 3000)]
+        mids = (0.5 * (pos[tri[:, 0]].astype(np.float64) + pos[tri[:, 1]])).astype(np.float32)
+        o2 = np.concatenate([verts, mids])
+        d2 = rng.normal(size=o2.shape)
+        d2 = (d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(np.float32)
+        # axis-parallel rays from vertices: they run inside the planes of the walls the vertex belongs to
+        o3 = np.repeat(pos[rng.integers(0, pos.shape[0], 500)], 6, axis=0)
+        d3 = np.tile(np.float32([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]]), (500, 1))
+        o = np.concatenate([o1, o2, o3]).astype(np.float32)
+        d = np.concatenate([d1, d2, d3]).astype(np.float32)
+        ids, t = gpu_ctx.trace_rays(o, d)
+        ids_bf, t_bf = gpu_ctx.trace_rays(o, d, brute_force=True)
+        assert gpu_ctx.stats().stack_overflows == 0
+        bad = np.flatnonzero((ids != ids_bf) | (t != t_bf))
+        assert bad.size == 0, f"builder {builder}, shift {shift}: {bad.size} rays differ, first {bad[:5]}: ids {ids[bad[:5]]} vs {ids_bf[bad[:5]]}, t {t[bad[:5]]} vs {t_bf[bad[:5]]}"
+        assert (ids != capi.MISS_ID).mean() > 0.3
