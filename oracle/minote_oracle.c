@@ -1295,6 +1295,15 @@ static float uchimura1(float x, float P, float a, float m, float l, float c, flo
     return T * w0 + Lc * w1 + Sc * w2;
 }
 
+void orc_ray_triangle_batch(uint32_t n, const float* o, const float* d, const float v0[3], const float v1[3],
+                            const float v2[3], uint8_t* hit, float* t) {
+    for (uint32_t i = 0; i < n; i++) {
+        float u, v;
+        t[i] = 0.0f;
+        hit[i] = (uint8_t)orc_ray_triangle(o + 3 * i, d + 3 * i, v0, v1, v2, &t[i], &u, &v);
+    }
+}
+
 /* ---- compressed 8-wide BVH node (contract in minote_oracle.h) ---- */
 static inline float bits_f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t f_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }

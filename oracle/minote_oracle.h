@@ -124,6 +124,9 @@ float orc_ray_sphere(const float o[3], const float d[3], const orc_sphere* s);
 /* returns 1 on hit; *t,*u,*v set (u,v barycentrics of v1,v2) */
 int orc_ray_triangle(const float o[3], const float d[3], const float v0[3], const float v1[3],
                      const float v2[3], float* t, float* u, float* v);
+/* the same test for n rays against one triangle (o, d: n x 3 floats); hit[i] = 0/1, t[i] valid where hit */
+void orc_ray_triangle_batch(uint32_t n, const float* o, const float* d, const float v0[3], const float v1[3],
+                            const float v2[3], uint8_t* hit, float* t);
 void orc_ray_gen(const orc_mat4* invView, const orc_mat4* invProjection, uint32_t x, uint32_t y,
                  uint32_t w, uint32_t h, float origin[3], float dir[3]);
 

@@ -136,6 +136,7 @@ def lib():
         "orc_primary_rays_spheres": (None, [C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.POINTER(Sphere), C.c_uint32, u32p, u16p, u16p, u16p]),
         "orc_secondary_rays_spheres": (None, [C.c_uint32, C.c_uint32, C.POINTER(SecondaryConstants), C.POINTER(Sphere), C.c_uint32, u32p, u16p, u16p, u8p, C.c_uint32, C.c_uint32, C.POINTER(AtmosphereParams), u16p, u32p, C.c_uint32, C.c_uint32, u16p, f32p, u64p]),
         "orc_denoise_bilateral": (None, [C.c_uint32, C.c_uint32, u16p, u16p, u16p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32, u8p]),
+        "orc_ray_triangle_batch": (None, [C.c_uint32, f32p, f32p, f32p, f32p, f32p, u8p, f32p]),
         "orc_wide_node_quantize": (None, [f32p, f32p, C.c_uint32, C.POINTER(WideNode)]),
         "orc_wide_node_test": (None, [C.POINTER(WideNode), C.c_uint32, f32p, f32p, f32p, u32p]),
         "orc_temporal_accumulate": (None, [C.c_uint32, C.c_uint32, f32p, u32p, u16p, C.c_int, f32p, f32p, u32p, C.c_float, f32p, f32p]),
@@ -278,6 +279,17 @@ def denoise_bilateral(color16, depth16, normal16, params=BILATERAL_DEFAULT, near
     lib().orc_denoise_bilateral(w, h, _p(c, C.c_uint16), _p(d, C.c_uint16), _p(n, C.c_uint16), params[0], params[1],
                                 params[2], near, frame, _p(out, C.c_uint8))
     return out
+
+
+def ray_triangle_batch(o, d, v0, v1, v2):
+    """The watertight fp32 ray/triangle test (row n4) for n rays against one triangle -> (hit bool[n], t float32[n])."""
+    o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+    n = o.shape[0]
+    hit = np.zeros(n, np.uint8)
+    t = np.zeros(n, np.float32)
+    lib().orc_ray_triangle_batch(n, _p(o, C.c_float), _p(d, C.c_float), f3(v0), f3(v1), f3(v2), _p(hit, C.c_uint8), _p(t, C.c_float))
+    return hit.astype(bool), t
 
 
 def wide_node_quantize(lo, hi, present=0xFF):

@@ -141,3 +141,59 @@ def test_known_node(oracle):
     d = np.float32([[1, 0, 0], [-1, 0, 0], [1, 0, 0], [1, 0, 0], [1, 0, 0]])
     tb = np.float32([3e38, 3e38, 3e38, 3e38, 2.5])
     assert list(oracle.wide_node_test(node, o, d, tb)) == [0b11, 0b00, 0b10, 0b00, 0b01]
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (1e-3, 0.1), (1e-2, 50.0), (1e-3, 1000.0), (1.0, 1e6)])
+def test_every_triangle_hit_passes_its_leaf_box(oracle, scale, offset):
+    """The invariant the image depends on, at the leaf level: whenever the fp32 watertight triangle test (row n4, the
+    same code the brute-force reference runs) reports a hit, the quantised slab test lets the ray into the triangle's
+    leaf box -- with no closest hit yet and with the closest hit AT this triangle (tlimit = t * (1 + 2^-21)).  Rays
+    are aimed at the triangle's interior, edges and vertices and displaced by a few ulps, from near and from far;
+    triangles include axis-aligned (flat-box) ones; siblings share the node."""
+    rng = np.random.default_rng(int(scale * 1e6) + int(offset) + 3)
+    hits_total = 0
+    for _ in range(150):
+        centre = (offset + rng.uniform(-1, 1, 3) * scale).astype(np.float32)
+        tri = (centre + rng.uniform(-1, 1, (3, 3)) * scale * 10.0 ** rng.uniform(-2, 0)).astype(np.float32)
+        if rng.random() < 0.3:                      # axis-aligned triangle: a flat leaf box
+            tri[:, int(rng.integers(3))] = tri[0, int(rng.integers(3))]
+        lo = np.zeros((8, 3), np.float32)
+        hi = np.zeros((8, 3), np.float32)
+        slot = int(rng.integers(8))
+        present = 1 << slot
+        lo[slot], hi[slot] = tri.min(0), tri.max(0)
+        for s in range(8):                          # siblings widen the node (coarser grid for this leaf)
+            if s != slot and rng.random() < 0.5:
+                c = centre + rng.uniform(-1, 1, 3) * scale * 4
+                e = scale * 10.0 ** rng.uniform(-2, 0, 3)
+                lo[s], hi[s] = (c - e).astype(np.float32), (c + e).astype(np.float32)
+                present |= 1 << s
+        node = oracle.wide_node_quantize(lo, hi, present)
+        n = 400
+        w = rng.dirichlet((1, 1, 1), n)
+        snap = rng.random(n)
+        w[snap < 0.3] = np.eye(3)[rng.integers(0, 3, (snap < 0.3).sum())]                    # vertices
+        edge = (snap >= 0.3) & (snap < 0.6)
+        w[edge, rng.integers(0, 3)] = 0.0
+        w[edge] /= np.maximum(w[edge].sum(1, keepdims=True), 1e-30)                          # edges
+        target = (w @ tri.astype(np.float64))
+        ulp = np.spacing(np.abs(target).astype(np.float32)).astype(np.float64)
+        target = (target + rng.integers(-3, 4, (n, 3)) * ulp).astype(np.float32)             # a few ulps off
+        ext = float(np.max(hi[slot] - lo[slot])) + float(np.spacing(np.float32(abs(offset) + scale)))
+        dist = 10.0 ** rng.uniform(-1, 3, (n, 1)) * ext
+        dirs = rng.normal(size=(n, 3))
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        o = (target.astype(np.float64) - dirs * dist).astype(np.float32)
+        d = (target.astype(np.float64) - o.astype(np.float64))
+        d = (d / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-300)).astype(np.float32)
+        hit, t = oracle.ray_triangle_batch(o, d, tri[0], tri[1], tri[2])
+        if not hit.any():
+            continue
+        open_mask = oracle.wide_node_test(node, o, d, None)
+        best_mask = oracle.wide_node_test(node, o, d, np.where(hit, t, np.float32(3.0e38)))
+        for name, m in (("no closest hit yet", open_mask), ("closest hit at this triangle", best_mask)):
+            lost = hit & ((m >> slot) & 1 == 0)
+            assert not lost.any(), (f"{name}: {lost.sum()} of {hit.sum()} triangle hits culled at the leaf box; first: o={o[lost][0]}, "
+                                    f"d={d[lost][0]}, t={t[lost][0]}, tri={tri.tolist()}")
+        hits_total += int(hit.sum())
+    assert hits_total > 2000
