@@ -78,8 +78,9 @@ export inline auto length(vec3 const& a) -> float { return std::sqrt(dot(a, a));
 export inline auto normalize(vec3 const& a) -> vec3 { return a / length(a); }
 export constexpr auto clamp(float v, float lo, float hi) -> float { return std::max(lo, std::min(v, hi)); }
 
-// degrees -> radians evaluated in double, then narrowed (the reference's _deg literal)
-export constexpr auto deg(double d) -> float { return static_cast<float>(d * (3.14159265358979323846 * 2.0) / 360.0); }
+// degrees -> radians as the reference's _deg literal does it: radians<double, Prec = float>(d) = float(d) * Tau_v<float> / 360.0f
+// (math.ixx:27,884-886; fp32 arithmetic -- checked against the reference's own code through oracle/_ref)
+export constexpr auto deg(double d) -> float { return static_cast<float>(d) * (3.14159265358979323846f * 2.0f) / 360.0f; }
 export constexpr float operator""_deg(long double d) { return deg(static_cast<double>(d)); }
 export constexpr float operator""_deg(unsigned long long d) { return deg(static_cast<double>(d)); }
 export constexpr float operator""_m(long double d) { return static_cast<float>(static_cast<double>(d) * 0.001); }

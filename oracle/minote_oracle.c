@@ -140,8 +140,10 @@ uint8_t orc_unorm8(float f) {
 
 /* =============================== host matrices (a1) =============================== */
 
-/* src/stx/math.ixx:27 : radians(double) then narrowed, as the _deg literals do (:884-886) */
-static float deg_lit(double deg) { return (float)(deg * (3.14159265358979323846 * 2.0) / 360.0); }
+/* src/stx/math.ixx:27 : radians<T, Prec = float>(deg) = Prec(deg) * Tau_v<Prec> / Prec(360) -- the _deg literals
+ * (:884-886) pass a double but leave Prec at float, so the arithmetic is fp32 (pinned by oracle/_ref: 22_deg and
+ * 45.5_deg differ in the last bit from the double-then-narrow value; 60, 89, 90, 360 do not) */
+static float deg_lit(double deg) { return (float)deg * (3.14159265358979323846f * 2.0f) / 360.0f; }
 
 /* src/gfx/camera.ixx:26-32 */
 void orc_camera_direction(const orc_camera* c, float out[3]) {
@@ -951,6 +953,16 @@ void orc_sky_color(const orc_atmosphere_params* p, const uint16_t* trans, const 
     sky_ctx S = sky_ctx_make(p, trans, skyView, cameraPos);
     v3 c = sky_color(&S, v3p(dir));
     out[0] = c.x; out[1] = c.y; out[2] = c.z;
+    sky_ctx_free(&S);
+}
+
+void orc_sky_color_batch(const orc_atmosphere_params* p, const uint16_t* trans, const uint32_t* skyView,
+                         const float cameraPos[3], uint32_t n, const float* dirs, float* out) {
+    sky_ctx S = sky_ctx_make(p, trans, skyView, cameraPos);
+    for (uint32_t i = 0; i < n; i++) {
+        v3 c = sky_color(&S, v3p(dirs + 3 * (size_t)i));
+        out[3 * (size_t)i] = c.x; out[3 * (size_t)i + 1] = c.y; out[3 * (size_t)i + 2] = c.z;
+    }
     sky_ctx_free(&S);
 }
 

@@ -5,11 +5,18 @@
  * __graft_entry__.py and bench.py's cpu_baseline / --impl reference legs may load it.
  * The product path (minotert_b200/csrc, libminotert.so) never links or calls it.
  *
- * PARITY UNPINNED: the reference (Tearnote/MinoteRT) ships no tests, golden vectors or
- * fixtures for this path, cannot be built outside Windows/MSVC and its GLSL cannot be
- * compiled or run here (no glslc, no Vulkan ICD).  This file is a plain-C restatement of
- * the reference's GLSL + host matrix code, each function citing the reference file:line it
- * follows.  Every implementation-defined Vulkan behaviour is fixed explicitly:
+ * PARITY PINNED (sphere path, sky, tonemap, denoiser, host matrices) against the reference's own code:
+ * the reference ships no tests or golden vectors and its renderer cannot be built or run here (Win32 +
+ * MSVC + Vulkan), but its GLSL compute shaders and its host math/camera modules DO compile as C++ --
+ * oracle/ref/ (glsl2cpp.py + glsl_shim.hpp, ixx2hpp.py) builds them from /root/reference into
+ * oracle/_ref/libminote_ref.so, and tests/test_ref_pins_oracle.py asserts that every function below that
+ * restates reference code reproduces that library BIT FOR BIT (full 960x540 8x8 frame, the three sky LUTs,
+ * six tonemappers, bilateral denoiser, 64 k-direction skyColor sweep, RNG stream, 2000 random cameras), and
+ * reproduces the golden vectors generated from it (tests/golden/ref_v1.npz).  What stays pinned only by its
+ * own contract: the triangle/BVH extensions (no reference counterpart, see the end of this comment).
+ * This file is a plain-C restatement of the reference's GLSL + host matrix code, each function citing
+ * the reference file:line it follows.  Every implementation-defined Vulkan behaviour is fixed explicitly
+ * (identically in oracle/ref/glsl_shim.hpp):
  *   fp32 -> fp16          : IEEE round-to-nearest-even, overflow -> inf
  *   fp32 -> B10G11R11     : RNE to 6/6/5-bit mantissa, negatives/NaN -> 0, saturate to max finite
  *   fp32 -> unorm8        : rint(clamp(x,0,1)*255), NaN -> 0
@@ -139,6 +146,10 @@ void orc_gen_sky_view(const orc_atmosphere_params* p, const uint16_t* trans, con
                       uint32_t* b10g11r11 /*192*108*/);
 void orc_sky_color(const orc_atmosphere_params* p, const uint16_t* trans, const uint32_t* skyView,
                    const float cameraPos[3], const float dir[3], float out[3]);
+
+/* the same for n directions (dirs, out: n x 3 floats) */
+void orc_sky_color_batch(const orc_atmosphere_params* p, const uint16_t* trans, const uint32_t* skyView,
+                         const float cameraPos[3], uint32_t n, const float* dirs, float* out);
 
 /* ---- reference sphere path, faithful mode (a2-a12) ---- */
 void orc_primary_rays_spheres(uint32_t w, uint32_t h, const orc_primary_constants* c,

@@ -133,6 +133,7 @@ def lib():
         "orc_gen_multiscattering": (None, [C.POINTER(AtmosphereParams), u16p, u16p]),
         "orc_gen_sky_view": (None, [C.POINTER(AtmosphereParams), u16p, u16p, f32p, f32p, f32p, u32p]),
         "orc_sky_color": (None, [C.POINTER(AtmosphereParams), u16p, u32p, f32p, f32p, f32p]),
+        "orc_sky_color_batch": (None, [C.POINTER(AtmosphereParams), u16p, u32p, f32p, C.c_uint32, f32p, f32p]),
         "orc_primary_rays_spheres": (None, [C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.POINTER(Sphere), C.c_uint32, u32p, u16p, u16p, u16p]),
         "orc_secondary_rays_spheres": (None, [C.c_uint32, C.c_uint32, C.POINTER(SecondaryConstants), C.POINTER(Sphere), C.c_uint32, u32p, u16p, u16p, u8p, C.c_uint32, C.c_uint32, C.POINTER(AtmosphereParams), u16p, u32p, C.c_uint32, C.c_uint32, u16p, f32p, u64p]),
         "orc_denoise_bilateral": (None, [C.c_uint32, C.c_uint32, u16p, u16p, u16p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32, u8p]),
@@ -163,8 +164,8 @@ def lib():
 
 
 def deg(d):
-    """The reference's _deg literal: radians in double, narrowed to float (src/stx/math.ixx:884)."""
-    return float(np.float32(d * (np.pi * 2.0) / 360.0))
+    """The reference's _deg literal: radians<double, Prec = float>, i.e. fp32 arithmetic (src/stx/math.ixx:27,884)."""
+    return float(np.float32(d) * (np.float32(np.pi) * np.float32(2.0)) / np.float32(360.0))
 
 
 def default_camera(w=960, h=540):
@@ -227,6 +228,15 @@ def sky_luts(atmo, probe_pos, sun_dir=SUN_DIRECTION, sun_ill=SUN_ILLUMINANCE):
     L.orc_gen_sky_view(C.byref(atmo), _p(trans, C.c_uint16), _p(multi, C.c_uint16), f3(probe_pos), f3(sun_dir),
                        f3(sun_ill), _p(view, C.c_uint32))
     return trans, multi, view
+
+
+def sky_color(atmo, trans, view, camera_pos, dirs):
+    """skyColor() of secondaryRays.comp:36-58 for an (n, 3) array of directions."""
+    d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    out = np.zeros_like(d)
+    lib().orc_sky_color_batch(C.byref(atmo), _p(trans, C.c_uint16), _p(view, C.c_uint32), f3(camera_pos), d.shape[0],
+                              _p(d, C.c_float), _p(out, C.c_float))
+    return out
 
 
 def load_blue_noise():
