@@ -107,7 +107,8 @@ typedef enum {
 
 /* mrt_secondary_rays flags */
 #define MRT_SECONDARY_ACCUMULATE 1u /* add to MRT_BUF_ACCUM instead of restarting it */
-#define MRT_SECONDARY_SORT_RAYS 2u  /* sort each bounce's ray queue by (origin cell, octant) */
+#define MRT_SECONDARY_SORT_RAYS 2u  /* reorder each bounce's ray queue before it is traced (image unchanged): stable
+                                     * binning by direction octant on top of the pixel order compaction leaves */
 
 typedef struct {
     uint64_t primary_rays;   /* rays traced by the last mrt_primary_rays */
@@ -145,8 +146,7 @@ const char* mrt_last_error(const mrt_context* ctx);
 /* Tuning / instrumentation switches (unknown names fail with MRT_ERR_INVALID):
  *   "count_visits" 0/1        count node visits and triangle tests (mrt_stats.node_visits / tri_tests)
  *   "trace_timing" 0/1        CUDA event pair around every bounce-wave traversal launch (default 1)
- *   "sort_rays" 0/1           octant sort of every bounce wave (default 0; measured slower)
- *   "persistent" 0/1          persistent-warp state machine for bounce waves (default 1)
+ *   "sort_rays" 0/1           sort every bounce wave's queue (see MRT_SECONDARY_SORT_RAYS; default 0)
  *   "fused_shade" 0/1         shade stage of a bounce wave inside its traversal launch (default 0; measured +-2 %)
  *   "persistent_primary" 0/1  ... and for primary rays (default 0: coherent per-lane loop)
  *   "trace_ctas_per_sm" n     cap the persistent traversal grid at n CTAs per SM (0 = as many as fit), for
@@ -250,6 +250,57 @@ int mrt_stream(mrt_context* ctx, void** stream_out);
 /* ---- closest-hit query (tests / tools): traces n rays through the built scene ---- */
 int mrt_trace_rays(mrt_context* ctx, const float* origins, const float* directions, uint32_t n,
                    uint32_t* prim_ids, float* t, int brute_force);
+
+/* ---- device-side unit probes (tests / tools): the per-path shading functions evaluated on the GPU ----
+ * skyColor() of src/gpu/secondaryRays.comp:36-58 for n directions (directions, rgb_out: n x 3 floats) with the LUTs of
+ * the last mrt_atmosphere / mrt_sky_view */
+int mrt_eval_sky_color(mrt_context* ctx, const float cameraPos[3], const float* directions, uint32_t n, float* rgb_out);
+/* the sample stream of one pixel (secondaryRays.comp:60-72,124-125): PCG state seeded with (frameCounter << 1) | 1,
+ * Cranley-Patterson rotation = blue-noise texel of pixel (x, y), then n consecutive Lambert bounces off
+ * (position, normal).  out9: n x 9 floats = r0, r1 (the two rotated randoms), ray origin xyz, ray direction xyz,
+ * PCG state after the bounce (bit pattern) */
+int mrt_eval_bounce_stream(mrt_context* ctx, uint32_t frameCounter, uint32_t x, uint32_t y, const float position[3],
+                           const float normal[3], uint32_t n, float* out9);
+
+/* ---- multi-GPU groups (no reference counterpart: the reference is single-GPU) ----
+ * A group = nranks contexts, each holding the whole scene (replicated BVH: upload + build through the ordinary
+ * calls on every mrt_group_context).  The render never communicates; the one exchange step is of the finished
+ * image:  tile mode   mrt_group_set_tiles + mrt_group_render + [mrt_group_tonemap] + mrt_group_gather
+ *         sample sets mrt_group_render(frame_stride != 0) + mrt_group_reduce, then tonemap on the root.
+ * Transports: MRT_GROUP_NCCL (ncclSend/ncclRecv/ncclReduce over NVLink; libnccl.so.2 is bound with dlopen when the
+ * first group is made) or MRT_GROUP_P2P (cudaMemcpyPeerAsync; one process only; several contexts may share a device).
+ * Calls on a group are made from one host thread.  Errors: mrt_group_last_error (g may be NULL: creation errors). */
+typedef struct mrt_group mrt_group;
+#define MRT_GROUP_NCCL 0
+#define MRT_GROUP_P2P 1
+/* one process drives ndev devices: creates one context per entry of devices[] (rank i = entry i); ncclCommInitAll */
+int mrt_group_create(const int* devices, uint32_t ndev, int transport, mrt_group** out);
+/* one process per GPU: rank 0 calls mrt_group_unique_id and hands the 128 bytes to the others by any means
+ * (bench.py: torch.distributed); every process then calls mrt_group_create_rank (ncclCommInitRank, collective) */
+int mrt_group_unique_id(uint8_t id_out[128]);
+int mrt_group_create_rank(int device, uint32_t rank, uint32_t nranks, const uint8_t unique_id[128], mrt_group** out);
+void mrt_group_destroy(mrt_group* g);  /* destroys the group's contexts too */
+const char* mrt_group_last_error(const mrt_group* g);
+int mrt_group_size(const mrt_group* g, uint32_t* nranks, uint32_t* nlocal);
+/* the local_index-th context this process drives (borrowed; owned by the group) and its rank */
+int mrt_group_context(mrt_group* g, uint32_t local_index, mrt_context** ctx_out, uint32_t* rank_out);
+/* tile mode: mrt_set_partition(rank, nranks, slab_rows) on every local context */
+int mrt_group_set_tiles(mrt_group* g, uint32_t slab_rows);
+/* mrt_primary_rays + mrt_secondary_rays on every local context; rank r renders frameCounter + r * frame_stride
+ * (0 in tile mode: all ranks render the same frame; N in sample-set mode: disjoint seeds) */
+int mrt_group_render(mrt_group* g, uint32_t w, uint32_t h, const mrt_primary_constants* pc, const mrt_secondary_constants* sc,
+                     uint32_t spp, uint32_t bounces, uint32_t flags, uint32_t frame_stride);
+int mrt_group_tonemap(mrt_group* g, int mode, float exposure, const float* params, uint32_t nparams, int source);
+/* tile mode: every rank's slabs of a per-pixel buffer (MRT_BUF_LDR, _ACCUM, _VISIBILITY, ...) -> the full image in
+ * row order on rank `root`.  Asynchronous (exchange streams); collective over all processes of the group. */
+int mrt_group_gather(mrt_group* g, int buffer_id, uint32_t root);
+/* sample sets: MRT_BUF_ACCUM of all ranks summed onto rank `root` in place (ncclReduce) */
+int mrt_group_reduce(mrt_group* g, uint32_t root);
+/* the image of the last gather on the root process: borrowed device pointer + the stream it is ordered on, or a
+ * blocking copy to host memory */
+int mrt_group_result(mrt_group* g, void** device_ptr, size_t* bytes, void** stream_out);
+int mrt_group_readback(mrt_group* g, void* host, size_t bytes);
+int mrt_group_sync(mrt_group* g);
 
 #ifdef __cplusplus
 }

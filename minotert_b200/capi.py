@@ -65,7 +65,12 @@ EXPORTS = [
     "mrt_secondary_rays", "mrt_tonemap", "mrt_buffer", "mrt_readback", "mrt_sync", "mrt_stats_get",
     "mrt_stats_reset", "mrt_stream", "mrt_trace_rays", "mrt_partition_rows_for", "mrt_readback_async",
     "mrt_readback_wait", "mrt_denoise_bilateral", "mrt_scene_share", "mrt_temporal_accumulate",
+    "mrt_eval_sky_color", "mrt_eval_bounce_stream",
+    "mrt_group_create", "mrt_group_unique_id", "mrt_group_create_rank", "mrt_group_destroy", "mrt_group_last_error",
+    "mrt_group_size", "mrt_group_context", "mrt_group_set_tiles", "mrt_group_render", "mrt_group_tonemap",
+    "mrt_group_gather", "mrt_group_reduce", "mrt_group_result", "mrt_group_readback", "mrt_group_sync",
 ]
+GROUP_NCCL, GROUP_P2P = 0, 1
 
 
 class MinoteError(RuntimeError):
@@ -117,9 +122,28 @@ def load():
     L.mrt_stream.argtypes = [vp, C.POINTER(vp)]
     L.mrt_trace_rays.argtypes = [vp, vp, vp, u32, vp, vp, C.c_int]
     L.mrt_partition_rows_for.argtypes = [u32, u32, u32, u32, vp, C.POINTER(u32)]
+    L.mrt_eval_sky_color.argtypes = [vp, f32p, vp, u32, vp]
+    L.mrt_eval_bounce_stream.argtypes = [vp, u32, u32, u32, f32p, f32p, u32, vp]
+    L.mrt_group_create.argtypes = [C.POINTER(C.c_int), u32, C.c_int, C.POINTER(vp)]
+    L.mrt_group_unique_id.argtypes = [vp]
+    L.mrt_group_create_rank.argtypes = [C.c_int, u32, u32, vp, C.POINTER(vp)]
+    L.mrt_group_destroy.argtypes = [vp]
+    L.mrt_group_destroy.restype = None
+    L.mrt_group_last_error.argtypes = [vp]
+    L.mrt_group_last_error.restype = C.c_char_p
+    L.mrt_group_size.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+    L.mrt_group_context.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u32)]
+    L.mrt_group_set_tiles.argtypes = [vp, u32]
+    L.mrt_group_render.argtypes = [vp, u32, u32, vp, vp, u32, u32, u32, u32]
+    L.mrt_group_tonemap.argtypes = [vp, C.c_int, C.c_float, f32p, u32, C.c_int]
+    L.mrt_group_gather.argtypes = [vp, C.c_int, u32]
+    L.mrt_group_reduce.argtypes = [vp, u32]
+    L.mrt_group_result.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
+    L.mrt_group_readback.argtypes = [vp, vp, C.c_size_t]
+    L.mrt_group_sync.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("mrt_destroy", "mrt_last_error"):
+        if name not in ("mrt_destroy", "mrt_last_error", "mrt_group_destroy", "mrt_group_last_error"):
             fn.restype = C.c_int
     _lib = L
     return L
@@ -141,18 +165,23 @@ class Context:
                BUF_LDR: (np.uint8, 4), BUF_HIT_T: (np.float32, 1), BUF_DENOISED: (np.uint8, 4),
                BUF_TEMPORAL: (np.float32, 4), BUF_TEMPORAL_COUNT: (np.float32, 1)}
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _borrowed=None):
         self.L = load()
+        self.device = device
+        self.size = (0, 0)
+        self._owned = _borrowed is None
+        if _borrowed is not None:   # a context that belongs to an mrt_group
+            self.h = C.c_void_p(_borrowed)
+            return
         self.h = C.c_void_p()
         s = self.L.mrt_create(device, C.byref(self.h))
         if s != 0:
             raise MinoteError(f"mrt_create({device}) failed ({s}): {self.L.mrt_last_error(None).decode()}")
-        self.device = device
-        self.size = (0, 0)
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.mrt_destroy(self.h)
+            if self._owned:
+                self.L.mrt_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -293,3 +322,124 @@ class Context:
         t = np.empty(o.shape[0], np.float32)
         self._ck(self.L.mrt_trace_rays(self.h, _ptr(o), _ptr(d), o.shape[0], _ptr(ids), _ptr(t), int(brute_force)))
         return ids, t
+
+    def eval_sky_color(self, camera_pos, directions):
+        """skyColor() evaluated on the GPU for an (n, 3) array of directions (mrt_eval_sky_color)."""
+        d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+        out = np.empty_like(d)
+        self._ck(self.L.mrt_eval_sky_color(self.h, _f3(camera_pos), _ptr(d), d.shape[0], _ptr(out)))
+        return out
+
+    def eval_bounce_stream(self, frame, x, y, position, normal, n):
+        """n consecutive bounces of pixel (x, y): (n, 9) = r0, r1, origin, direction, rng state bits."""
+        out = np.empty((n, 9), np.float32)
+        self._ck(self.L.mrt_eval_bounce_stream(self.h, frame, x, y, _f3(position), _f3(normal), n, _ptr(out)))
+        return out
+
+
+class Group:
+    """mrt_group: n contexts (replicated scene) + the exchange step of the finished image, all inside the library
+    (NCCL called from C++; no torch.distributed on the data path).
+
+    Group(devices=[0, 1, ...])                 one process drives the listed devices (ncclCommInitAll)
+    Group(devices=[0, 0, 0], transport="p2p")  device-to-device copies instead of NCCL; contexts may share a GPU
+    Group.rank_of(device, rank, nranks, uid)   one process per GPU, uid = Group.unique_id() made on rank 0
+    """
+
+    def __init__(self, devices=None, transport="nccl", _handle=None):
+        self.L = load()
+        self.h = C.c_void_p()
+        if _handle is not None:
+            self.h = _handle
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            s = self.L.mrt_group_create(arr, len(devices), GROUP_P2P if transport == "p2p" else GROUP_NCCL, C.byref(self.h))
+            if s != 0:
+                raise MinoteError(f"mrt_group_create failed ({s}): {self.L.mrt_group_last_error(None).decode()}")
+        n, nl = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.mrt_group_size(self.h, C.byref(n), C.byref(nl)))
+        self.nranks, self.nlocal = n.value, nl.value
+        self.contexts, self.ranks = [], []
+        for i in range(self.nlocal):
+            c, r = C.c_void_p(), C.c_uint32()
+            self._ck(self.L.mrt_group_context(self.h, i, C.byref(c), C.byref(r)))
+            self.contexts.append(Context(_borrowed=c.value))
+            self.ranks.append(r.value)
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        L = load()
+        s = L.mrt_group_unique_id(buf)
+        if s != 0:
+            raise MinoteError(f"mrt_group_unique_id failed ({s}): {L.mrt_group_last_error(None).decode()}")
+        return bytes(buf)
+
+    @classmethod
+    def rank_of(cls, device, rank, nranks, unique_id):
+        L = load()
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        s = L.mrt_group_create_rank(device, rank, nranks, buf, C.byref(h))
+        if s != 0:
+            raise MinoteError(f"mrt_group_create_rank failed ({s}): {L.mrt_group_last_error(None).decode()}")
+        return cls(_handle=h)
+
+    def _ck(self, s):
+        if s != 0:
+            raise MinoteError(f"minotert group error {s}: {self.L.mrt_group_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            for c in self.contexts:
+                c.close()
+            self.L.mrt_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tiles(self, slab_rows=8):
+        self._ck(self.L.mrt_group_set_tiles(self.h, slab_rows))
+
+    def render(self, w, h, pc, sc, spp, bounces, flags=0, frame_stride=0):
+        self._ck(self.L.mrt_group_render(self.h, w, h, C.cast(C.byref(pc), C.c_void_p), C.cast(C.byref(sc), C.c_void_p),
+                                         spp, bounces, flags, frame_stride))
+        for c in self.contexts:
+            c.size = (w, h)
+        self.size = (w, h)
+
+    def tonemap(self, mode="amd", exposure=1.0, params=(16.0, 2.0, 1.0, 0.18, 0.18), source=BUF_ACCUM):
+        par = (C.c_float * 8)(*params)
+        m = TONEMAP[mode] if isinstance(mode, str) else int(mode)
+        self._ck(self.L.mrt_group_tonemap(self.h, m, exposure, par, len(params), source))
+
+    def gather(self, buf=BUF_LDR, root=0):
+        self._ck(self.L.mrt_group_gather(self.h, buf, root))
+        self._gathered = buf
+
+    def reduce(self, root=0):
+        self._ck(self.L.mrt_group_reduce(self.h, root))
+
+    def result(self):
+        p, n, s = C.c_void_p(), C.c_size_t(), C.c_void_p()
+        self._ck(self.L.mrt_group_result(self.h, C.byref(p), C.byref(n), C.byref(s)))
+        return p.value, n.value, s.value
+
+    def readback(self, out=None):
+        """The gathered image on the root as a numpy array in image order (blocking)."""
+        dt, ch = Context._DTYPES[self._gathered]
+        w, h = self.size
+        if out is None:
+            out = np.empty((h, w, ch) if ch > 1 else (h, w), dt)
+        self._ck(self.L.mrt_group_readback(self.h, _ptr(out), out.nbytes))
+        return out
+
+    def readback_into(self, host_ptr, nbytes):
+        self._ck(self.L.mrt_group_readback(self.h, host_ptr, nbytes))
+
+    def sync(self):
+        self._ck(self.L.mrt_group_sync(self.h))

@@ -95,7 +95,7 @@ static void scene_unborrow(mrt_context* ctx) {
     ctx->nverts = ctx->ntris = ctx->num_nodes = ctx->num_leaf_tris = 0;
     ctx->scene_borrowed = false;
     ctx->bvh_valid = false;
-    ctx->scene_kind = 0;
+    if (ctx->scene_kind == 2) ctx->scene_kind = 0;  // a borrower that has since switched to a sphere scene keeps it
 }
 
 // Called before the owner's scene arrays are rewritten, reallocated or freed: frames of the borrowing contexts that
@@ -106,8 +106,10 @@ static void scene_borrowers_stale(mrt_context* owner, bool owner_dies) {
     std::vector<mrt_context*> list = owner->borrowers;
     for (mrt_context* b : list) {
         cudaStreamSynchronize(b->stream);
-        b->bvh_valid = false;
-        b->have_gbuffer = b->have_accum = b->have_color = b->have_ldr = b->have_denoised = b->have_temporal = false;
+        if (b->scene_kind == 2) {  // (a borrower rendering its own sphere scene meanwhile is not touched)
+            b->bvh_valid = false;
+            b->have_gbuffer = b->have_accum = b->have_color = b->have_ldr = b->have_denoised = b->have_temporal = false;
+        }
         if (owner_dies) scene_unborrow(b);
     }
 }
@@ -173,6 +175,7 @@ void mrt_destroy(mrt_context* ctx) {
     for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); }
     dev_free(ctx->hits); dev_free(ctx->queue_counts); dev_free(ctx->sort_keys); dev_free(ctx->sort_keys_alt);
     dev_free(ctx->sort_vals); dev_free(ctx->sort_vals_alt); dev_free(ctx->visit_counters); dev_free(ctx->total_rays);
+    dev_free(ctx->query_o); dev_free(ctx->query_d); dev_free(ctx->query_t); dev_free(ctx->query_ids);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->trace_ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -192,7 +195,6 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     if (!name) return mrt_fail(ctx, MRT_ERR_INVALID, "option name is NULL");
     if (!strcmp(name, "count_visits")) ctx->opt_count_visits = value != 0;
     else if (!strcmp(name, "sort_rays")) ctx->opt_sort_rays = value != 0;
-    else if (!strcmp(name, "persistent")) ctx->opt_persistent = value != 0;
     else if (!strcmp(name, "persistent_primary")) ctx->opt_persistent_primary = value != 0;
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;
@@ -284,7 +286,11 @@ int mrt_scene_share(mrt_context* ctx, mrt_context* owner) {
     if (owner->scene_kind != 2 || !owner->bvh_valid) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_scene_share: the owner has no built mesh scene");
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // frames of this context that still read the old scene
     if (ctx->scene_borrowed) scene_unborrow(ctx);
-    else { dev_free(ctx->pos); dev_free(ctx->idx); dev_free(ctx->albedo); dev_free(ctx->nodes); dev_free(ctx->tris); }
+    else {
+        // ctx's own arrays are about to be freed: contexts that alias them lose their scene first
+        scene_borrowers_stale(ctx, true);
+        dev_free(ctx->pos); dev_free(ctx->idx); dev_free(ctx->albedo); dev_free(ctx->nodes); dev_free(ctx->tris);
+    }
     ctx->pos = owner->pos; ctx->idx = owner->idx; ctx->albedo = owner->albedo; ctx->nodes = owner->nodes; ctx->tris = owner->tris;
     ctx->nverts = owner->nverts; ctx->ntris = owner->ntris;
     ctx->num_nodes = owner->num_nodes; ctx->num_leaf_tris = owner->num_leaf_tris;
@@ -378,7 +384,8 @@ int mrt_primary_rays(mrt_context* ctx, uint32_t w, uint32_t h, const mrt_primary
         return mrt_fail(ctx, MRT_ERR_STATE, ctx->scene_borrowed ? "primary rays: the borrowed scene changed (call mrt_scene_share again)"
                                                                  : "primary rays: mesh uploaded but not built");
     uint32_t rows = partition_local_rows(ctx->part, h);
-    if (w != ctx->W || h != ctx->H || rows != ctx->local_rows) ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = false;
+    if (w != ctx->W || h != ctx->H || rows != ctx->local_rows)
+        ctx->have_accum = ctx->have_color = ctx->have_ldr = ctx->have_denoised = ctx->have_temporal = false;
     ctx->W = w; ctx->H = h; ctx->local_rows = rows;
     ctx->npix = (size_t)w * rows;
     ctx->pc = *c;
@@ -589,6 +596,22 @@ int mrt_trace_rays(mrt_context* ctx, const float* origins, const float* directio
     if (!brute_force && !ctx->bvh_valid) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_trace_rays: BVH not built");
     if (n && (!origins || !directions || !prim_ids || !t)) return mrt_fail(ctx, MRT_ERR_INVALID, "mrt_trace_rays: NULL array");
     return mesh_trace_rays(ctx, origins, directions, n, prim_ids, t, brute_force);
+}
+
+int mrt_eval_sky_color(mrt_context* ctx, const float cameraPos[3], const float* directions, uint32_t n, float* rgb_out) {
+    MRT_ENTER(ctx);
+    if (!ctx->have_atmo || !ctx->have_view) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_eval_sky_color: sky LUTs missing (mrt_atmosphere, mrt_sky_view)");
+    if (!cameraPos || (n && (!directions || !rgb_out))) return mrt_fail(ctx, MRT_ERR_INVALID, "mrt_eval_sky_color: NULL array");
+    sky_join(ctx);
+    return probe_sky_color(ctx, cameraPos, directions, n, rgb_out);
+}
+
+int mrt_eval_bounce_stream(mrt_context* ctx, uint32_t frameCounter, uint32_t x, uint32_t y, const float position[3],
+                           const float normal[3], uint32_t n, float* out9) {
+    MRT_ENTER(ctx);
+    if (!ctx->bn) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_eval_bounce_stream: blue noise texture missing");
+    if (!position || !normal || (n && !out9)) return mrt_fail(ctx, MRT_ERR_INVALID, "mrt_eval_bounce_stream: NULL array");
+    return probe_bounce_stream(ctx, frameCounter, x, y, position, normal, n, out9);
 }
 
 }  // extern "C"

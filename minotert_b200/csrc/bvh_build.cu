@@ -1125,7 +1125,7 @@ int bvh_build_full(mrt_context* ctx) {
         ctx->bvh_valid = true;
         return MRT_OK;
     }
-    cudaEventRecord(ctx->ev[0], ctx->stream);
+    cudaEventRecord(ctx->ev[12], ctx->stream);
     MRT_TRY(dev_reserve(ctx, ctx->prim_lo, n));
     MRT_TRY(dev_reserve(ctx, ctx->prim_hi, n));
     MRT_TRY(dev_reserve(ctx, ctx->keys, n));
@@ -1236,9 +1236,9 @@ int bvh_build_full(mrt_context* ctx) {
     MRT_TRY(dev_reserve(ctx, ctx->nodes, ctx->num_nodes));
     MRT_TRY(dev_reserve(ctx, ctx->tris, 3 * (size_t)n));
     MRT_TRY(emit_nodes(ctx));
-    cudaEventRecord(ctx->ev[1], ctx->stream);
+    cudaEventRecord(ctx->ev[13], ctx->stream);
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev[12], ctx->ev[13]);
     ctx->stats.num_triangles = n;
     ctx->stats.num_wide_nodes = ctx->num_nodes;
     ctx->stats.bvh_bytes = (uint64_t)ctx->num_nodes * sizeof(WideNode) + (uint64_t)n * 48u;
@@ -1259,12 +1259,12 @@ int bvh_build_full(mrt_context* ctx) {
 
 int bvh_refit(mrt_context* ctx) {
     if (!ctx->bvh_valid || ctx->num_nodes == 0) return bvh_build_full(ctx);
-    cudaEventRecord(ctx->ev[0], ctx->stream);
+    cudaEventRecord(ctx->ev[12], ctx->stream);
     MRT_TRY(compute_boxes(ctx));
     MRT_TRY(climb_boxes(ctx));
     MRT_TRY(emit_nodes(ctx));
-    cudaEventRecord(ctx->ev[1], ctx->stream);
+    cudaEventRecord(ctx->ev[13], ctx->stream);
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev[12], ctx->ev[13]);
     return MRT_OK;
 }

@@ -65,7 +65,6 @@ struct mrt_context {
     // options
     int opt_count_visits = 0;
     int opt_sort_rays = 0;
-    int opt_persistent = 1;
     int opt_persistent_primary = 0;  // run primary rays through the persistent state machine too (A/B switch)
     int opt_trace_timing = 1;        // CUDA event pair around every bounce-wave traversal launch (mrt_stats.ms_trace)
     int opt_fused_shade = 0;         // shade stage of a bounce wave inside the traversal kernel (mesh.cu k_trace_shade); A/B: +1.5 % at 1080p 1 spp, -2 % at 4K 8 spp
@@ -159,12 +158,14 @@ struct mrt_context {
     uint32_t num_queue_counts = 0;
     DevArray<uint64_t> sort_keys, sort_keys_alt;
     DevArray<uint32_t> sort_vals, sort_vals_alt;
+    DevArray<float> query_o, query_d, query_t;    // mrt_trace_rays scratch
+    DevArray<uint32_t> query_ids;
     DevArray<unsigned long long> visit_counters;  // node visits, tri tests, stack overflows
     DevArray<unsigned long long> total_rays;      // running sum of traced rays since mrt_stats_reset
 
     // stats
     mrt_stats stats{};
-    cudaEvent_t ev[12] = {nullptr};  // pairs: sky, primary, secondary, tonemap, denoise, temporal
+    cudaEvent_t ev[14] = {nullptr};  // pairs: sky, primary, secondary, tonemap, denoise, temporal, BVH build/refit
     // The sky view of a frame is generated on a side stream so that it overlaps the primary pass
     // (Renderer::draw order: sky -> primary -> secondary); consumers join through sky_join().
     cudaStream_t aux_stream = nullptr;
@@ -229,6 +230,9 @@ int bvh_build_full(mrt_context* ctx);
 int bvh_refit(mrt_context* ctx);
 int mesh_primary(mrt_context* ctx);
 int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags);
+int probe_sky_color(mrt_context* ctx, const float cameraPos[3], const float* dirs, uint32_t n, float* out);
+int probe_bounce_stream(mrt_context* ctx, uint32_t frameCounter, uint32_t x, uint32_t y, const float pos[3], const float normal[3],
+                        uint32_t n, float* out9);
 int mesh_trace_rays(mrt_context* ctx, const float* o, const float* d, uint32_t n, uint32_t* ids, float* t, int brute);
 // device-wide primitives (sort.cu)
 int scan_exclusive_u32(mrt_context* ctx, const uint32_t* in, uint32_t* out, size_t n);

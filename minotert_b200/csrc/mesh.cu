@@ -666,12 +666,14 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
 
 int mesh_trace_rays(mrt_context* ctx, const float* o, const float* d, uint32_t n, uint32_t* ids, float* t, int brute) {
     if (n == 0) return MRT_OK;
-    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
-    uint32_t* d_ids = nullptr;
-    MRT_CUDA(ctx, cudaMalloc(&d_o, sizeof(float) * 3 * (size_t)n));
-    MRT_CUDA(ctx, cudaMalloc(&d_d, sizeof(float) * 3 * (size_t)n));
-    MRT_CUDA(ctx, cudaMalloc(&d_t, sizeof(float) * (size_t)n));
-    MRT_CUDA(ctx, cudaMalloc(&d_ids, sizeof(uint32_t) * (size_t)n));
+    // context-owned scratch (grown on demand, freed with the context): no per-call cudaMalloc, nothing to leak on an
+    // early return
+    MRT_TRY(dev_reserve(ctx, ctx->query_o, 3 * (size_t)n));
+    MRT_TRY(dev_reserve(ctx, ctx->query_d, 3 * (size_t)n));
+    MRT_TRY(dev_reserve(ctx, ctx->query_t, n));
+    MRT_TRY(dev_reserve(ctx, ctx->query_ids, n));
+    float *d_o = ctx->query_o.p, *d_d = ctx->query_d.p, *d_t = ctx->query_t.p;
+    uint32_t* d_ids = ctx->query_ids.p;
     MRT_CUDA(ctx, cudaMemcpyAsync(d_o, o, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     MRT_CUDA(ctx, cudaMemcpyAsync(d_d, d, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     MRT_TRY(reserve_visit_counters(ctx));
@@ -686,14 +688,14 @@ int mesh_trace_rays(mrt_context* ctx, const float* o, const float* d, uint32_t n
                                                                               ctx->visit_counters.p, 1);
     }
     MRT_LAUNCHED(ctx);
+    MRT_CUDA(ctx, cudaGetLastError());
     MRT_CUDA(ctx, cudaMemcpyAsync(ids, d_ids, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     MRT_CUDA(ctx, cudaMemcpyAsync(t, d_t, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     unsigned long long vc[3] = {0, 0, 0};
-    cudaMemcpy(vc, ctx->visit_counters.p, sizeof vc, cudaMemcpyDeviceToHost);
+    MRT_CUDA(ctx, cudaMemcpy(vc, ctx->visit_counters.p, sizeof vc, cudaMemcpyDeviceToHost));
     ctx->stats.node_visits = vc[0];
     ctx->stats.tri_tests = vc[1];
     ctx->stats.stack_overflows += (uint32_t)vc[2];
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_ids);
     return MRT_OK;
 }

@@ -1,0 +1,147 @@
+"""Multi-GPU groups through the C ABI only (mrt_group_*): no torch.distributed anywhere.
+
+Single-GPU box: N contexts of one device in a P2P-transport group (the N-rank tile logic, the gather and our scatter
+kernel); >= 2 GPUs: the NCCL transport (ncclSend/ncclRecv gather, ncclReduce for sample sets).
+Bar: the gathered image == the 1-context image, bit for bit (ids, fp32 accumulator, RGBA8 framebuffer)."""
+import numpy as np
+import pytest
+
+from minotert_b200 import capi, scenes
+from test_gpu_spheres import as_capi, setup_sky
+
+pytestmark = pytest.mark.gpu
+
+
+def device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def prepare(ctxs, oracle, atmo, cam, blue_noise, mesh, share=True):
+    pos, idx, alb = mesh
+    for i, c in enumerate(ctxs):
+        setup_sky(c, oracle, atmo, cam.position[:])
+        c.upload_blue_noise(blue_noise)
+        if i == 0 or not share or c.device != ctxs[0].device:
+            c.upload_mesh(pos, idx, alb)
+            c.build()
+        else:
+            c.share_scene(ctxs[0])   # contexts of one device render one copy of the triangles + BVH
+
+
+def progressive(render_frame, tonemap_gather, frames):
+    for f in range(frames):
+        render_frame(f + 1, capi.SECONDARY_ACCUMULATE if f else 0)
+        tonemap_gather()
+
+
+def single_context_image(oracle, atmo, cam, blue_noise, mesh, w, h, spp, bounces, frames):
+    ctx = capi.Context(0)
+    try:
+        prepare([ctx], oracle, atmo, cam, blue_noise, mesh)
+        for f in range(frames):
+            pc, sc = oracle.constants(cam, frame=f + 1)
+            ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+            ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), spp, bounces, capi.SECONDARY_ACCUMULATE if f else 0)
+            ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+        return ctx.readback(capi.BUF_LDR).copy(), ctx.readback(capi.BUF_ACCUM).copy(), ctx.readback(capi.BUF_VISIBILITY).copy()
+    finally:
+        ctx.close()
+
+
+def group_image(g, oracle, atmo, cam, blue_noise, mesh, w, h, spp, bounces, frames, slab):
+    prepare(g.contexts, oracle, atmo, cam, blue_noise, mesh)
+    g.set_tiles(slab)
+    for f in range(frames):
+        pc, sc = oracle.constants(cam, frame=f + 1)
+        g.render(w, h, as_capi(pc, capi.PrimaryConstants), as_capi(sc, capi.SecondaryConstants), spp, bounces,
+                 capi.SECONDARY_ACCUMULATE if f else 0)
+        g.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+        g.gather(capi.BUF_LDR, 0)          # one gather per displayed frame, asynchronous
+    ldr = g.readback().copy()
+    g.gather(capi.BUF_ACCUM, 0)
+    acc = g.readback().copy()
+    g.gather(capi.BUF_VISIBILITY, 0)
+    vis = g.readback().copy()
+    for c in g.contexts:
+        assert c.stats().stack_overflows == 0
+    return ldr, acc, vis
+
+
+@pytest.mark.parametrize("nranks,slab", [(2, 8), (3, 5), (4, 8)])
+def test_group_tiles_p2p_equals_single_context(oracle, sky_inputs, blue_noise, nranks, slab):
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h = 167, 101   # odd width: 2-byte row copies for R16F; height not a multiple of the slab
+    cam = oracle.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+    want = single_context_image(oracle, atmo, cam, blue_noise, (pos, idx, alb), w, h, 2, 2, 3)
+    g = capi.Group([0] * nranks, transport="p2p")
+    try:
+        got = group_image(g, oracle, atmo, cam, blue_noise, (pos, idx, alb), w, h, 2, 2, 3, slab)
+        g.gather(capi.BUF_DEPTH, 0)
+        depth = g.readback()
+        assert depth.shape == (h, w)
+    finally:
+        g.close()
+    for a, b, name in zip(got, want, ("LDR", "accumulator", "visibility")):
+        assert np.array_equal(a, b), f"{name}: {nranks}-rank gathered image differs from the 1-context image"
+
+
+def test_config4_4k_progressive_tiles_equals_single_context(oracle, sky_inputs, blue_noise):
+    """BASELINE config 4 at full size: 3840x2160, 8 frames x 8 spp accumulated to 64 spp, tile-partitioned over
+    N in {2, 4, 8} ranks (simulated as N contexts of this GPU sharing one BVH, P2P transport), framebuffer gathered
+    every displayed frame: final framebuffer and fp32 accumulator == the 1-context render, bit for bit."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.hall_260k()
+    w, h, spp, bounces, frames = 3840, 2160, 8, 2, 8
+    cam = oracle.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+    want = single_context_image(oracle, atmo, cam, blue_noise, (pos, idx, alb), w, h, spp, bounces, frames)
+    assert np.all(want[1][..., 3] == spp * frames)
+    for nranks in (2, 4, 8):
+        g = capi.Group([0] * nranks, transport="p2p")
+        try:
+            got = group_image(g, oracle, atmo, cam, blue_noise, (pos, idx, alb), w, h, spp, bounces, frames, 8)
+        finally:
+            g.close()
+        for a, b, name in zip(got, want, ("LDR", "accumulator", "visibility")):
+            assert np.array_equal(a, b), f"config 4, {nranks} ranks: {name} differs from the 1-context image"
+
+
+@pytest.mark.skipif(device_count() < 2, reason="needs 2 GPUs (NCCL refuses two ranks on one device)")
+def test_group_nccl_two_gpus_tiles_and_sample_sets(oracle, sky_inputs, blue_noise):
+    """Two ranks on two GPUs, driven through the C ABI alone: tile mode == 1-GPU image bit for bit; sample-set mode:
+    ncclReduce of the accumulators == the sum of the two frames rendered one after the other on one GPU."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h = 320, 180
+    cam = oracle.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+    mesh = (pos, idx, alb)
+    want = single_context_image(oracle, atmo, cam, blue_noise, mesh, w, h, 2, 2, 3)
+    g = capi.Group([0, 1], transport="nccl")
+    try:
+        got = group_image(g, oracle, atmo, cam, blue_noise, mesh, w, h, 2, 2, 3, 8)
+        for a, b, name in zip(got, want, ("LDR", "accumulator", "visibility")):
+            assert np.array_equal(a, b), f"NCCL tiles: {name} differs"
+        # sample sets: rank r renders frame 1 + r of the whole image
+        for c in g.contexts:
+            c.set_partition(0, 1, 8)
+        pc, sc = oracle.constants(cam, frame=1)
+        g.render(w, h, as_capi(pc, capi.PrimaryConstants), as_capi(sc, capi.SecondaryConstants), 2, 2, 0, frame_stride=1)
+        g.reduce(0)
+        g.sync()
+        summed = g.contexts[0].readback(capi.BUF_ACCUM).copy()
+    finally:
+        g.close()
+    ctx = capi.Context(0)
+    try:
+        prepare([ctx], oracle, atmo, cam, blue_noise, mesh)
+        parts = []
+        for f in (1, 2):
+            pc, sc = oracle.constants(cam, frame=f)
+            ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+            ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), 2, 2, 0)
+            parts.append(ctx.readback(capi.BUF_ACCUM).copy())
+    finally:
+        ctx.close()
+    assert np.array_equal(summed, parts[0] + parts[1])   # two addends: fp32 addition is commutative, the sum is exact-order-free
+    assert np.all(summed[..., 3] == 4.0)
