@@ -147,6 +147,9 @@ const char* mrt_last_error(const mrt_context* ctx);
  *   "count_visits" 0/1        count node visits and triangle tests (mrt_stats.node_visits / tri_tests)
  *   "trace_timing" 0/1        CUDA event pair around every bounce-wave traversal launch (default 1)
  *   "sort_rays" 0/1           sort every bounce wave's queue (see MRT_SECONDARY_SORT_RAYS; default 0)
+ *   "path_kernel" 0/1         triangle scenes: the whole secondary pass (all samples and bounces) as one persistent
+ *                             launch in which a lane owns a pixel (default 1), or the wavefront of trace + shade
+ *                             launches per bounce wave with compacted ray queues (0).  Same image bit for bit.
  *   "fused_shade" 0/1         shade stage of a bounce wave inside its traversal launch (default 0; measured +-2 %)
  *   "persistent_primary" 0/1  ... and for primary rays (default 0: coherent per-lane loop)
  *   "trace_ctas_per_sm" n     cap the persistent traversal grid at n CTAs per SM (0 = as many as fit), for

@@ -198,6 +198,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "persistent_primary")) ctx->opt_persistent_primary = value != 0;
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;
+    else if (!strcmp(name, "path_kernel")) ctx->opt_path_kernel = value != 0;
     else if (!strcmp(name, "trace_ctas_per_sm")) ctx->opt_trace_ctas_per_sm = (int)(value > 32 ? 32 : value);
     else if (!strcmp(name, "build_device_loop")) { ctx->opt_build_device_loop = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "builder")) { ctx->opt_builder = value != 0; ctx->bvh_valid = false; }
@@ -549,6 +550,10 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
         if (ctx->scene_kind == 1) {
             unsigned long long v = 0;
             MRT_CUDA(ctx, cudaMemcpy(&v, ctx->visit_counters.p + 4, sizeof v, cudaMemcpyDeviceToHost));
+            ctx->stats.secondary_rays = v;
+        } else if (ctx->secondary_was_path_kernel) {
+            unsigned long long v = 0;
+            MRT_CUDA(ctx, cudaMemcpy(&v, ctx->visit_counters.p + 4 + 3, sizeof v, cudaMemcpyDeviceToHost));
             ctx->stats.secondary_rays = v;
         } else {
             std::vector<uint32_t> counts(ctx->num_queue_counts);

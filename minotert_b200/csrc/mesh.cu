@@ -449,6 +449,177 @@ k_trace_shade(QueueJob job, BvhDev bvh, uint32_t* work_counter, unsigned long lo
     }
 }
 
+// ---- the whole secondary pass in ONE persistent launch (option "path_kernel") ----
+// The wavefront above pays, per bounce wave, a traversal launch whose last quarter is the drain of its longest rays
+// (~100 us, bounded by ray latency, not by work), a shade launch, and ~130 B/ray of queue / hit / path-state traffic.
+// With 4-8 spp x 2-3 bounces that is 12-24 drains per frame, and on a 1/8-image slab (tile mode on 8 GPUs) the drains
+// ARE the frame.  Here a lane owns a PIXEL for all its samples and bounces -- the reference's RNG chain forces the
+// samples of a pixel to run in sequence anyway (secondaryRays.comp:124-132) -- so the path state lives in registers /
+// shared memory, nothing is queued, and the only drain is the one at the end of the frame.  The warp-synchronous state
+// machine of trace_persistent() gains one step kind:
+//     shade : lanes whose ray has finished (or that just took a pixel) resolve the path vertex -- sky on a miss,
+//             albedo + blue-noise-rotated Lambert bounce on a hit -- and either start the next ray, the next sample,
+//             or write the pixel's accumulator and go idle; runs once PATH_SHADE_MIN lanes want it.
+// Per pixel the arithmetic and its order are exactly those of the wavefront (k_shade / shade_vertex), so the two
+// produce bit-identical images (tested).
+#ifndef PATH_SHADE_MIN
+#define PATH_SHADE_MIN 8
+#endif
+#ifndef PATH_MIN_BLOCKS
+#define PATH_MIN_BLOCKS TRACE_MIN_BLOCKS
+#endif
+enum { COLD_DX = 0, COLD_DY, COLD_DZ, COLD_TX, COLD_TY, COLD_TZ, COLD_AX, COLD_AY, COLD_AZ, COLD_AW, COLD_RX, COLD_RY, COLD_COUNT };
+
+__global__ void __launch_bounds__(TRACE_BLOCK, PATH_MIN_BLOCKS)
+k_path(ShadeArgs a, uint32_t* work_counter, unsigned long long* counters, int count_visits, unsigned long long* total_rays) {
+    __shared__ TraceShared S;
+    __shared__ float cold[COLD_COUNT][TRACE_BLOCK];  // per-lane path state that the traversal steps never touch
+    trace_shared_init(S);
+    const ShadeParams& P = a.P;
+    const BvhDev& bvh = a.bvh;
+    uint2* const sm = &S.stack[0][threadIdx.x];
+    float* const cd = &cold[0][threadIdx.x];
+#define COLD(k) cd[(k) * TRACE_BLOCK]
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t total = a.npix;
+    uint2 spill[TRACE_LOCAL_STACK];
+    TraceCounters cnt{0, 0, 0};
+    LaneState L;
+    L.ng = L.tg = L.tg2 = make_uint2(0u, 0u);
+    L.tgmask = L.tg2mask = 0u;
+    L.sp = 0;
+    L.o = f3s(0.0f);
+    L.hit.t = 0.0f; L.hit.tri = L.hit.prim = MRT_MISS_ID;
+    bool have_path = false, need_shade = false;
+    uint32_t pixel = 0, rng = 0, sv = 0;  // sv = sample << 16 | path vertex
+    unsigned nrays = 0;
+    uint32_t pool_next = 0, pool_end = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        // ---- idle lanes take the next pixels of the warp's chunk
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have_path);
+        if (idle && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= TRACE_REFILL_MIN)) {
+            if (pool_next >= pool_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work_counter, (uint32_t)TRACE_CHUNK);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                pool_next = base;
+                pool_end = min(base + (uint32_t)TRACE_CHUNK, total);
+                if (base >= total) { exhausted = true; pool_next = pool_end = 0; }
+            }
+            if (!exhausted) {
+                const uint32_t mine = pool_next + __popc(idle & lt_mask);
+                if (!have_path && mine < pool_end) {
+                    pixel = mine;
+                    have_path = need_shade = true;
+                    sv = 0;
+                    rng = P.seed;
+                    float4 acc = P.accumulate ? a.accum[pixel] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    COLD(COLD_AX) = acc.x; COLD(COLD_AY) = acc.y; COLD(COLD_AZ) = acc.z; COLD(COLD_AW) = acc.w + (float)P.spp;
+                    const uint32_t lr = pixel / P.W, x = pixel - lr * P.W;
+                    const float2 rot = blue_noise_rotation(a.bn, P.bnW, P.bnH, x, partition_local_to_y(P.part, lr));
+                    COLD(COLD_RX) = rot.x; COLD(COLD_RY) = rot.y;
+                    L.ng.y = 0u; L.tg.y = 0u; L.tg2.y = 0u; L.sp = 0;
+                }
+                pool_next = min(pool_next + (uint32_t)__popc(idle), pool_end);
+            }
+        }
+        if (exhausted && __ballot_sync(0xFFFFFFFFu, have_path) == 0u) break;
+
+        // ---- lanes whose traversal has no pending work: pop, or hand the finished ray to the shade step
+        if (have_path && !need_shade && !(L.ng.y & 0xFF000000u) && !(L.tg.y && L.tg2.y)) {
+            if (L.sp == 0) {
+                if (!(L.tg.y | L.tg2.y)) need_shade = true;
+            } else {
+                L.sp--;
+                L.ng = L.sp < TRACE_SM_STACK ? sm[L.sp * TRACE_BLOCK] : spill[L.sp - TRACE_SM_STACK];
+            }
+        }
+        const bool tracing = have_path && !need_shade;
+        const bool want_tri = tracing && (L.tg.y | L.tg2.y) != 0u;
+        const bool want_node = tracing && !(L.tg.y && L.tg2.y) && (L.ng.y & 0xFF000000u);
+        const unsigned smask = __ballot_sync(0xFFFFFFFFu, need_shade);
+        const unsigned tmask = __ballot_sync(0xFFFFFFFFu, want_tri);
+        const unsigned nmask = __ballot_sync(0xFFFFFFFFu, want_node);
+        const int tri_min = exhausted ? min(TRACE_TRI_MIN, max(1, (__popc(tmask | nmask) + TRACE_DRAIN_TRI - 1) / TRACE_DRAIN_TRI)) : TRACE_TRI_MIN;
+        const int shade_min = exhausted ? min(PATH_SHADE_MIN, max(1, (__popc(smask | tmask | nmask) + 2) / 3)) : PATH_SHADE_MIN;
+        if (smask && ((tmask | nmask) == 0u || __popc(smask) >= shade_min)) {
+            if (need_shade) {
+                float3 thr = f3(COLD(COLD_TX), COLD(COLD_TY), COLD(COLD_TZ));
+                for (;;) {
+                    const uint32_t vertex = sv & 0xFFFFu;
+                    float3 pos, n;
+                    uint32_t prim;
+                    if (vertex == 0) {  // the primary hit, carried in fp32 by the primary pass (shade_vertex<FIRST>)
+                        const float4 hp = __ldg(&a.hit0_pos[pixel]), hn = __ldg(&a.hit0_n[pixel]);
+                        pos = f3(hp.x, hp.y, hp.z);
+                        n = f3(hn.x, hn.y, hn.z);
+                        prim = __float_as_uint(hp.w);
+                        thr = f3s(1.0f);
+                    } else {
+                        const float3 d = f3(COLD(COLD_DX), COLD(COLD_DY), COLD(COLD_DZ));
+                        if (L.hit.tri != MRT_MISS_ID) {
+                            pos = L.o + d * L.hit.t;
+                            n = tri_facing_normal(bvh, L.hit.tri, d, &prim);
+                        } else {
+                            prim = MRT_MISS_ID;
+                            pos = f3s(0.0f);
+                            n = d;  // secondaryRays.comp:88
+                        }
+                    }
+                    bool sample_done;
+                    if (prim == MRT_MISS_ID) {  // secondaryRays.comp:96: the path ends in the sky
+                        const float3 c = thr * sky_color(a.A, a.luts, P.cameraPos, n);
+                        COLD(COLD_AX) += c.x; COLD(COLD_AY) += c.y; COLD(COLD_AZ) += c.z;
+                        sample_done = true;
+                    } else {
+                        const float4 al = __ldg(&a.albedo[prim]);
+                        thr = thr * f3(al.x, al.y, al.z);  // secondaryRays.comp:94
+                        sample_done = vertex >= P.bounces;  // the energy of a path that is still on a surface is dropped (:99)
+                        if (!sample_done) {
+                            float3 ro, rd;
+                            lambert_bounce(pos, n, rng, COLD(COLD_RX), COLD(COLD_RY), ro, rd);
+                            lane_begin(L, ro, rd);
+                            if (bvh.num_nodes == 0) L.ng.y = 0u;
+                            COLD(COLD_DX) = rd.x; COLD(COLD_DY) = rd.y; COLD(COLD_DZ) = rd.z;
+                            sv++;
+                            nrays++;
+                            need_shade = false;
+                            break;
+                        }
+                    }
+                    const uint32_t sample = (sv >> 16) + 1u;
+                    if (sample < P.spp) { sv = sample << 16; continue; }  // next sample: vertex 0 again, same RNG stream
+                    a.accum[pixel] = make_float4(COLD(COLD_AX), COLD(COLD_AY), COLD(COLD_AZ), COLD(COLD_AW));
+                    have_path = need_shade = false;
+                    break;
+                }
+                COLD(COLD_TX) = thr.x; COLD(COLD_TY) = thr.y; COLD(COLD_TZ) = thr.z;
+            }
+        } else if (tmask && (nmask == 0u || __popc(tmask) >= tri_min)) {
+            if (want_tri) {
+                lane_tri_step<true>(L, bvh, cnt);
+#pragma unroll 1
+                for (int k = 1; k < TRACE_TRI_PER_STEP && (L.tg.y | L.tg2.y); k++) lane_tri_step<true>(L, bvh, cnt);
+            }
+        } else if (nmask) {
+            if (want_node) lane_node_step<true>(L, bvh, S, spill, cnt);
+        }
+    }
+#undef COLD
+    flush_counters(cnt, counters, count_visits != 0);
+    // rays traced by this launch: counters[3]; running total (mrt_stats.total_rays) += primary pixels + rays
+    unsigned long long r = nrays;
+    for (int off = 16; off > 0; off >>= 1) r += __shfl_down_sync(0xFFFFFFFFu, r, off);
+    if (lane == 0 && r) {
+        atomicAdd(&counters[3], r);
+        if (total_rays) atomicAdd(total_rays, r);
+    }
+    if (total_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total_rays, (unsigned long long)a.npix);
+}
+
 // brute-force closest hit over the uploaded mesh (validation of the BVH path; mrt_trace_rays)
 __global__ void __launch_bounds__(128) k_trace_brute(const float* __restrict__ pos, const uint32_t* __restrict__ idx, uint32_t ntris,
                                                      const float* __restrict__ ro, const float* __restrict__ rdir, uint32_t n,
@@ -504,6 +675,20 @@ unsigned trace_grid(mrt_context* ctx, size_t max_rays) {
     return (unsigned)(need < want ? need : want);
 }
 
+unsigned path_grid(mrt_context* ctx, size_t pixels) {
+    static int per_sm[64] = {0};
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    int& occ = per_sm[ctx->device & 63];
+    if (occ == 0) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_path, TRACE_BLOCK, 0);
+        if (occ <= 0) occ = 4;
+    }
+    size_t want = (size_t)sms * (ctx->opt_trace_ctas_per_sm > 0 && ctx->opt_trace_ctas_per_sm < occ ? ctx->opt_trace_ctas_per_sm : occ);
+    size_t need = (pixels + 31) / 32 / (TRACE_BLOCK / 32) + 1;
+    return (unsigned)(need < want ? need : want);
+}
+
 }  // namespace
 
 int mesh_primary(mrt_context* ctx) {
@@ -545,6 +730,51 @@ int mesh_primary(mrt_context* ctx) {
 
 int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags) {
     const uint32_t npix = (uint32_t)ctx->npix;
+    const bool path_kernel = ctx->opt_path_kernel != 0 && spp < 65536u && bounces < 65535u;
+    ctx->secondary_was_path_kernel = path_kernel;
+    if (path_kernel) {
+        // one persistent launch for all samples and bounces: no queues, no hit records, no path-state buffer
+        MRT_TRY(dev_reserve(ctx, ctx->queue_counts, 4));
+        MRT_TRY(reserve_visit_counters(ctx));
+        MRT_CUDA(ctx, cudaMemsetAsync(ctx->queue_counts.p, 0, sizeof(uint32_t) * 4, ctx->stream));
+        MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        ctx->num_queue_counts = 0;
+        ShadeArgs sa{};
+        ShadeParams& P = sa.P;
+        P.cameraPos = f3(c->cameraPos[0], c->cameraPos[1], c->cameraPos[2]);
+        P.seed = (c->frameCounter << 1u) | 1u;
+        P.W = ctx->W;
+        P.spp = spp;
+        P.bnW = ctx->bnW;
+        P.bnH = ctx->bnH;
+        P.bounces = bounces;
+        P.accumulate = ((flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum) ? 1 : 0;
+        P.part = ctx->part;
+        sa.bvh = make_bvh(ctx);
+        sa.A = ctx->atmo;
+        sa.luts = SkyLuts{ctx->trans_f.p, nullptr, ctx->view_f.p};
+        sa.bn = ctx->bn;
+        sa.albedo = ctx->albedo.p;
+        sa.hit0_pos = ctx->hit0_pos.p;
+        sa.hit0_n = ctx->hit0_n.p;
+        sa.npix = npix;
+        sa.accum = ctx->accum.p;
+        const bool timed = ctx->opt_trace_timing && ctx->trace_ev_used < 4096;
+        while (timed && ctx->trace_ev.size() < 2 * (size_t)(ctx->trace_ev_used + 1)) {
+            cudaEvent_t e;
+            MRT_CUDA(ctx, cudaEventCreate(&e));
+            ctx->trace_ev.push_back(e);
+        }
+        if (timed) cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used], ctx->stream);
+        k_path<<<path_grid(ctx, npix), TRACE_BLOCK, 0, ctx->stream>>>(sa, ctx->queue_counts.p, ctx->visit_counters.p + 4, ctx->opt_count_visits,
+                                                                     ctx->total_rays.p);
+        MRT_LAUNCHED(ctx);
+        if (timed) {
+            cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used + 1], ctx->stream);
+            ctx->trace_ev_used++;
+        }
+        return mrt_check_cuda(ctx, cudaGetLastError(), "mesh_secondary (path kernel)");
+    }
     const uint32_t waves = spp * bounces;
     const bool fused = ctx->opt_fused_shade != 0;
     MRT_TRY(dev_reserve(ctx, ctx->path_state, npix));

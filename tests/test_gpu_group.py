@@ -12,6 +12,13 @@ from test_gpu_spheres import as_capi, setup_sky
 pytestmark = pytest.mark.gpu
 
 
+def same(a, b):
+    """Bit-for-bit equality that lets the reference-faithful NaN pixels through: skyViewLutParamsToUv takes
+    acos(dot(dir, up)) unclamped (skyAccess.glsl:101,109), so a bounce ray within ~1e-4 rad of the zenith whose dot
+    product rounds to 1 + 1 ulp yields NaN -- a few pixels in 10^9 rays, identical in every partition."""
+    return np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+
+
 def device_count():
     import torch
     return torch.cuda.device_count()
@@ -84,7 +91,7 @@ def test_group_tiles_p2p_equals_single_context(oracle, sky_inputs, blue_noise, n
     finally:
         g.close()
     for a, b, name in zip(got, want, ("LDR", "accumulator", "visibility")):
-        assert np.array_equal(a, b), f"{name}: {nranks}-rank gathered image differs from the 1-context image"
+        assert same(a, b), f"{name}: {nranks}-rank gathered image differs from the 1-context image"
 
 
 def test_config4_4k_progressive_tiles_equals_single_context(oracle, sky_inputs, blue_noise):
@@ -97,6 +104,7 @@ def test_config4_4k_progressive_tiles_equals_single_context(oracle, sky_inputs, 
     cam = oracle.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
     want = single_context_image(oracle, atmo, cam, blue_noise, (pos, idx, alb), w, h, spp, bounces, frames)
     assert np.all(want[1][..., 3] == spp * frames)
+    assert np.isnan(want[1]).any(-1).mean() < 1e-5
     for nranks in (2, 4, 8):
         g = capi.Group([0] * nranks, transport="p2p")
         try:
@@ -104,7 +112,7 @@ def test_config4_4k_progressive_tiles_equals_single_context(oracle, sky_inputs, 
         finally:
             g.close()
         for a, b, name in zip(got, want, ("LDR", "accumulator", "visibility")):
-            assert np.array_equal(a, b), f"config 4, {nranks} ranks: {name} differs from the 1-context image"
+            assert same(a, b), f"config 4, {nranks} ranks: {name} differs from the 1-context image"
 
 
 @pytest.mark.skipif(device_count() < 2, reason="needs 2 GPUs (NCCL refuses two ranks on one device)")
@@ -121,7 +129,7 @@ def test_group_nccl_two_gpus_tiles_and_sample_sets(oracle, sky_inputs, blue_nois
     try:
         got = group_image(g, oracle, atmo, cam, blue_noise, mesh, w, h, 2, 2, 3, 8)
         for a, b, name in zip(got, want, ("LDR", "accumulator", "visibility")):
-            assert np.array_equal(a, b), f"NCCL tiles: {name} differs"
+            assert same(a, b), f"NCCL tiles: {name} differs"
         # sample sets: rank r renders frame 1 + r of the whole image
         for c in g.contexts:
             c.set_partition(0, 1, 8)
@@ -143,5 +151,5 @@ def test_group_nccl_two_gpus_tiles_and_sample_sets(oracle, sky_inputs, blue_nois
             parts.append(ctx.readback(capi.BUF_ACCUM).copy())
     finally:
         ctx.close()
-    assert np.array_equal(summed, parts[0] + parts[1])   # two addends: fp32 addition is commutative, the sum is exact-order-free
+    assert same(summed, parts[0] + parts[1])   # two addends: fp32 addition is commutative, the sum is exact-order-free
     assert np.all(summed[..., 3] == 4.0)

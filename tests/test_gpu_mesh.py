@@ -196,6 +196,7 @@ def test_ray_sort_does_not_change_the_image(gpu_ctx, oracle, sky_inputs, blue_no
     gpu_ctx.upload_blue_noise(blue_noise)
     gpu_ctx.upload_mesh(pos, idx, alb)
     gpu_ctx.build()
+    gpu_ctx.set_option("path_kernel", 0)   # the sort stage sits between the waves of the wavefront
     out = []
     for sort in (0, 1):
         gpu_ctx.set_option("sort_rays", sort)
@@ -220,6 +221,7 @@ def test_fused_shade_does_not_change_the_image(gpu_ctx, oracle, sky_inputs, blue
     gpu_ctx.upload_blue_noise(blue_noise)
     gpu_ctx.upload_mesh(pos, idx, alb)
     gpu_ctx.build()
+    gpu_ctx.set_option("path_kernel", 0)   # fused_shade is an option of the wavefront
     try:
         for (w, h) in ((192, 128), (333, 211), (64, 48)):
             cam = camera_for(oracle, view, w, h)
@@ -238,6 +240,48 @@ def test_fused_shade_does_not_change_the_image(gpu_ctx, oracle, sky_inputs, blue
                 assert np.array_equal(acc, out["ref"][0]), f"fused={fused} flags={flags} {w}x{h}"
     finally:
         gpu_ctx.set_option("fused_shade", 0)
+
+
+def test_path_kernel_equals_wavefront(oracle, sky_inputs, blue_noise):
+    """Option path_kernel (the whole secondary pass as one persistent launch, a lane owns a pixel through all its
+    samples and bounces) against the wavefront (trace + shade launches per wave, compacted queues): accumulator,
+    ray count and framebuffer are bit-identical -- across image sizes, spp x bounces shapes incl. 0 bounces,
+    progressive accumulation, a tile partition, and when toggled between frames."""
+    atmo = sky_inputs[0]
+    for maker, sizes in (("small_terrain", ((192, 128), (333, 211), (64, 48))), ("cornell", ((160, 160),))):
+        pos, idx, alb, view = getattr(scenes, maker)()
+        ctx = capi.Context(0)
+        try:
+            ctx.upload_blue_noise(blue_noise)
+            ctx.upload_mesh(pos, idx, alb)
+            ctx.build()
+            for (w, h) in sizes:
+                cam = camera_for(oracle, view, w, h)
+                setup_sky(ctx, oracle, atmo, cam.position[:])
+                for part in ((0, 1), (1, 3)):
+                    ctx.set_partition(part[0], part[1], 8)
+                    for spp, bounces in ((1, 1), (3, 3), (8, 2), (2, 0), (1, 8)):
+                        out = []
+                        for pk in (0, 1, 0, 1):
+                            ctx.set_option("path_kernel", pk)
+                            rays = 0
+                            for frame in (3, 4):   # second frame accumulates onto the first
+                                pc, scn = oracle.constants(cam, frame=frame)
+                                ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+                                ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), spp, bounces,
+                                                   capi.SECONDARY_ACCUMULATE if frame == 4 else 0)
+                                st = ctx.stats()
+                                assert st.stack_overflows == 0
+                                rays += int(st.secondary_rays)
+                            ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+                            out.append((ctx.readback(capi.BUF_ACCUM).copy(), ctx.readback(capi.BUF_LDR).copy(), rays))
+                        for o in out[1:]:
+                            what = f"{maker} {w}x{h} part {part} {spp} spp x {bounces} bounces"
+                            assert o[2] == out[0][2], what
+                            assert np.array_equal(o[0], out[0][0], equal_nan=True) and np.array_equal(o[1], out[0][1]), what
+                        assert np.all(out[0][0][..., 3] == 2 * spp)
+        finally:
+            ctx.close()
 
 
 def test_async_readback_matches_blocking(gpu_ctx, oracle, sky_inputs, blue_noise):
