@@ -147,9 +147,13 @@ const char* mrt_last_error(const mrt_context* ctx);
  *   "count_visits" 0/1        count node visits and triangle tests (mrt_stats.node_visits / tri_tests)
  *   "trace_timing" 0/1        CUDA event pair around every bounce-wave traversal launch (default 1)
  *   "sort_rays" 0/1           sort every bounce wave's queue (see MRT_SECONDARY_SORT_RAYS; default 0)
- *   "path_kernel" 0/1         triangle scenes: the whole secondary pass (all samples and bounces) as one persistent
- *                             launch in which a lane owns a pixel (default 1), or the wavefront of trace + shade
- *                             launches per bounce wave with compacted ray queues (0).  Same image bit for bit.
+ *   "bands" 1..8              wavefront: the image's pixels are cut into that many ranges, each rendered on its own
+ *                             stream, so that the drain of one band's traversal launch overlaps another band's
+ *                             kernels.  Same image bit for bit.
+ *   "path_kernel" 0/1         triangle scenes: the whole secondary pass (all samples and bounces) as ONE persistent
+ *                             launch in which a lane owns a pixel (1), instead of the wavefront of trace + shade
+ *                             launches per bounce wave with compacted ray queues (0, default: measured faster).
+ *                             Same image bit for bit.
  *   "fused_shade" 0/1         shade stage of a bounce wave inside its traversal launch (default 0; measured +-2 %)
  *   "persistent_primary" 0/1  ... and for primary rays (default 0: coherent per-lane loop)
  *   "trace_ctas_per_sm" n     cap the persistent traversal grid at n CTAs per SM (0 = as many as fit), for

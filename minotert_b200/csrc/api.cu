@@ -180,6 +180,11 @@ void mrt_destroy(mrt_context* ctx) {
     for (auto& ev : ctx->trace_ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    for (int b = 0; b < MRT_MAX_BANDS; b++) {
+        if (ctx->band_stream[b]) { cudaStreamSynchronize(ctx->band_stream[b]); cudaStreamDestroy(ctx->band_stream[b]); }
+        if (ctx->band_done[b]) cudaEventDestroy(ctx->band_done[b]);
+    }
+    if (ctx->band_fork) cudaEventDestroy(ctx->band_fork);
     if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
     if (ctx->sky_ready) cudaEventDestroy(ctx->sky_ready);
     if (ctx->ldr_ready) cudaEventDestroy(ctx->ldr_ready);
@@ -199,6 +204,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;
     else if (!strcmp(name, "path_kernel")) ctx->opt_path_kernel = value != 0;
+    else if (!strcmp(name, "bands")) ctx->opt_bands = (int)(value < 1 ? 1 : (value > MRT_MAX_BANDS ? MRT_MAX_BANDS : value));
     else if (!strcmp(name, "trace_ctas_per_sm")) ctx->opt_trace_ctas_per_sm = (int)(value > 32 ? 32 : value);
     else if (!strcmp(name, "build_device_loop")) { ctx->opt_build_device_loop = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "builder")) { ctx->opt_builder = value != 0; ctx->bvh_valid = false; }

@@ -25,6 +25,7 @@ static_assert(sizeof(WideNode) == 80, "wide node is 80 bytes");
 #define MRT_MAX_LEAF_TRIS 2  // triangles per leaf slot (the node format allows 3): 2 measured best of 1, 2, 3
 #endif
 #define MRT_MAX_SPHERES 16
+#define MRT_MAX_BANDS 8
 
 struct BvhDev {
     const WideNode* nodes;  // [num_nodes]
@@ -67,7 +68,10 @@ struct mrt_context {
     int opt_sort_rays = 0;
     int opt_persistent_primary = 0;  // run primary rays through the persistent state machine too (A/B switch)
     int opt_trace_timing = 1;        // CUDA event pair around every bounce-wave traversal launch (mrt_stats.ms_trace)
-    int opt_path_kernel = 1;         // the secondary pass of a triangle scene as ONE persistent launch (mesh.cu k_path); 0: wavefront (trace + shade launches per bounce wave)
+    int opt_bands = 1;               // wavefront: pixel bands rendered on their own streams so that one band's traversal drain overlaps another band's kernels
+    cudaStream_t band_stream[8] = {nullptr};
+    cudaEvent_t band_done[8] = {nullptr}, band_fork = nullptr;
+    int opt_path_kernel = 0;         // the secondary pass of a triangle scene as ONE persistent launch (mesh.cu k_path); 0: wavefront (trace + shade launches per bounce wave)
     bool secondary_was_path_kernel = false;
     int opt_fused_shade = 0;         // shade stage of a bounce wave inside the traversal kernel (mesh.cu k_trace_shade); A/B: +1.5 % at 1080p 1 spp, -2 % at 4K 8 spp
     int opt_trace_ctas_per_sm = 0;   // 0: as many as fit; n: persistent traversal grids use n CTAs per SM (co-running contexts)

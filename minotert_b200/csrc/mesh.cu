@@ -266,6 +266,7 @@ struct ShadeParams {
     int first_sample;    // sample 0 of this frame: seed the PCG state, start/continue the accumulator
     int accumulate;
     Partition part;
+    uint32_t pixel_base; // FIRST: vertex k of this launch is pixel pixel_base + k (bands of the image, see mesh_secondary)
 };
 
 // Everything the shade stage reads and writes (passed by value to the kernels).
@@ -307,17 +308,17 @@ MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
         float3 pos, n, thr;
         uint32_t prim, rng;
         if (FIRST) {
-            pixel = k;
-            float4 hp = __ldg(&a.hit0_pos[k]), hn = __ldg(&a.hit0_n[k]);
+            pixel = P.pixel_base + k;
+            float4 hp = __ldg(&a.hit0_pos[pixel]), hn = __ldg(&a.hit0_n[pixel]);
             pos = f3(hp.x, hp.y, hp.z);
             n = f3(hn.x, hn.y, hn.z);
             prim = __float_as_uint(hp.w);
             thr = f3s(1.0f);
-            rng = P.first_sample ? P.seed : __float_as_uint(a.path_state[k].w);
+            rng = P.first_sample ? P.seed : __float_as_uint(a.path_state[pixel].w);
             if (P.first_sample) {
-                float4 acc = P.accumulate ? a.accum[k] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                float4 acc = P.accumulate ? a.accum[pixel] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 acc.w += (float)P.spp;
-                a.accum[k] = acc;
+                a.accum[pixel] = acc;
             }
         } else {
             unsigned long long rec;
@@ -777,6 +778,15 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     }
     const uint32_t waves = spp * bounces;
     const bool fused = ctx->opt_fused_shade != 0;
+    const bool sort = ctx->opt_sort_rays || (flags & MRT_SECONDARY_SORT_RAYS);
+    // Bands: the image's pixels are cut into contiguous ranges, each with its own queues, counters and STREAM.  The last
+    // quarter of every persistent traversal launch is the drain of its longest rays (latency-bound, ~100 us whatever the
+    // wave's size); with several bands in flight the drain of one band's launch is filled by another band's kernels --
+    // the frames-in-flight overlap brought inside a frame.  Pixels are independent, so the image does
+    // not depend on the number of bands (tested).  fused_shade and the sort stage keep one band (shared scratch).
+    uint32_t bands = (fused || sort || ctx->opt_bands < 1) ? 1u : (uint32_t)ctx->opt_bands;
+    if (bands > MRT_MAX_BANDS) bands = MRT_MAX_BANDS;
+    while (bands > 1 && npix / bands < 32768u) bands--;  // a band must still fill the GPU
     MRT_TRY(dev_reserve(ctx, ctx->path_state, npix));
     for (int q = 0; q < 2; q++) {
         MRT_TRY(dev_reserve(ctx, ctx->ray_o[q], npix));
@@ -788,14 +798,26 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         MRT_CUDA(ctx, cudaMemsetAsync(ctx->hits.p, 0xFE, sizeof(unsigned long long) * ctx->hits.cap, ctx->stream));
         ctx->hits_dirty = false;
     }
-    // [0, waves]: queue sizes; then per wave: work counter of the persistent launch, chunk counter of its shade stage
-    MRT_TRY(dev_reserve(ctx, ctx->queue_counts, 3 * (size_t)waves + 3));
+    // counters: [band][0..waves] queue sizes; then [band][wave] work counters of the persistent launches; then
+    // [band][wave] chunk counters of their (fused) shade stages
+    const size_t ncount = (size_t)bands * (3 * (size_t)waves + 3);
+    MRT_TRY(dev_reserve(ctx, ctx->queue_counts, ncount));
     MRT_TRY(reserve_visit_counters(ctx));
-    MRT_CUDA(ctx, cudaMemsetAsync(ctx->queue_counts.p, 0, sizeof(uint32_t) * (3 * (size_t)waves + 3), ctx->stream));
+    MRT_CUDA(ctx, cudaMemsetAsync(ctx->queue_counts.p, 0, sizeof(uint32_t) * ncount, ctx->stream));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    ctx->num_queue_counts = waves + 1;
+    ctx->num_queue_counts = bands * (waves + 1);
+    if (bands > 1) {
+        for (uint32_t b = 0; b < bands; b++) {
+            if (!ctx->band_stream[b]) {
+                MRT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->band_stream[b], cudaStreamNonBlocking));
+                MRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->band_done[b], cudaEventDisableTiming));
+            }
+        }
+        if (!ctx->band_fork) MRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->band_fork, cudaEventDisableTiming));
+        MRT_CUDA(ctx, cudaEventRecord(ctx->band_fork, ctx->stream));
+    }
 
-    ShadeArgs sa;
+    ShadeArgs sa{};
     ShadeParams& P = sa.P;
     P.cameraPos = f3(c->cameraPos[0], c->cameraPos[1], c->cameraPos[2]);
     P.seed = (c->frameCounter << 1u) | 1u;
@@ -813,78 +835,92 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     sa.albedo = ctx->albedo.p;
     sa.hit0_pos = ctx->hit0_pos.p;
     sa.hit0_n = ctx->hit0_n.p;
-    sa.hits = ctx->hits.p;
-    sa.npix = npix;
     sa.path_state = ctx->path_state.p;
     sa.accum = ctx->accum.p;
     sa.overflow = ctx->visit_counters.p + 4 + 2;
-    const unsigned shade_grid = div_up(npix, 256), tgrid = trace_grid(ctx, npix);
-    uint32_t* const work_counters = ctx->queue_counts.p + waves + 1;
-    uint32_t* const shade_counters = ctx->queue_counts.p + 2 * (size_t)waves + 2;
-
-    uint32_t wave = 0;
     constexpr uint32_t kMaxTimedLaunches = 4096;  // event pairs kept since mrt_stats_reset
-    for (uint32_t s = 0; s < spp; s++) {
-        P.first_sample = s == 0;
-        P.vertex = 0;
-        int q = 0;
-        sa.in_o = sa.in_d = nullptr;
-        sa.out_o = ctx->ray_o[q].p;
-        sa.out_d = ctx->ray_d[q].p;
-        sa.out_count = ctx->queue_counts.p + wave;
-        k_shade<true><<<shade_grid, 256, 0, ctx->stream>>>(sa, nullptr);
-        MRT_LAUNCHED(ctx);
-        for (uint32_t b = 1; b <= bounces; b++) {
-            const uint32_t* in_count = ctx->queue_counts.p + wave;
-            const bool timed = ctx->opt_trace_timing && ctx->trace_ev_used < kMaxTimedLaunches;
-            while (timed && ctx->trace_ev.size() < 2 * (size_t)(ctx->trace_ev_used + 1)) {
-                cudaEvent_t e;
-                MRT_CUDA(ctx, cudaEventCreate(&e));
-                ctx->trace_ev.push_back(e);
+
+    for (uint32_t band = 0; band < bands; band++) {
+        // pixel range of the band: multiples of 256 so that the shade CTAs of different bands never share a pixel
+        const uint32_t p0 = (uint32_t)(((uint64_t)npix * band / bands) & ~255ull);
+        const uint32_t p1 = band + 1 == bands ? npix : (uint32_t)(((uint64_t)npix * (band + 1) / bands) & ~255ull);
+        const uint32_t bpix = p1 - p0;
+        if (bpix == 0) continue;
+        cudaStream_t st = bands > 1 ? ctx->band_stream[band] : ctx->stream;
+        if (bands > 1) MRT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->band_fork, 0));
+        uint32_t* const qcounts = ctx->queue_counts.p + (size_t)band * (waves + 1);
+        uint32_t* const work_counters = ctx->queue_counts.p + (size_t)bands * (waves + 1) + (size_t)band * waves;
+        uint32_t* const shade_counters = ctx->queue_counts.p + (size_t)bands * (2 * (size_t)waves + 1) + (size_t)band * waves;
+        float4* const ray_o[2] = {ctx->ray_o[0].p + p0, ctx->ray_o[1].p + p0};
+        float4* const ray_d[2] = {ctx->ray_d[0].p + p0, ctx->ray_d[1].p + p0};
+        sa.hits = ctx->hits.p + p0;
+        sa.npix = bpix;
+        P.pixel_base = p0;
+        const unsigned shade_grid = div_up(bpix, 256), tgrid = trace_grid(ctx, bpix);
+        uint32_t wave = 0;
+        for (uint32_t s = 0; s < spp; s++) {
+            P.first_sample = s == 0;
+            P.vertex = 0;
+            int q = 0;
+            sa.in_o = sa.in_d = nullptr;
+            sa.out_o = ray_o[q];
+            sa.out_d = ray_d[q];
+            sa.out_count = qcounts + wave;
+            k_shade<true><<<shade_grid, 256, 0, st>>>(sa, nullptr);
+            MRT_LAUNCHED(ctx);
+            for (uint32_t b = 1; b <= bounces; b++) {
+                const uint32_t* in_count = qcounts + wave;
+                const bool timed = ctx->opt_trace_timing && ctx->trace_ev_used < kMaxTimedLaunches;
+                while (timed && ctx->trace_ev.size() < 2 * (size_t)(ctx->trace_ev_used + 1)) {
+                    cudaEvent_t e;
+                    MRT_CUDA(ctx, cudaEventCreate(&e));
+                    ctx->trace_ev.push_back(e);
+                }
+                if (timed) cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used], st);
+                if (sort) {
+                    const uint32_t tiles = div_up(npix, OB_TILE);
+                    MRT_TRY(dev_reserve(ctx, ctx->sort_vals, npix));
+                    MRT_TRY(dev_reserve(ctx, ctx->sort_vals_alt, 8 * (size_t)tiles));
+                    k_oct_hist<<<tiles, OB_THREADS, 0, st>>>(ray_d[q], in_count, ctx->sort_vals_alt.p, tiles);
+                    MRT_LAUNCHED(ctx);
+                    MRT_TRY(scan_exclusive_u32(ctx, ctx->sort_vals_alt.p, ctx->sort_vals_alt.p, 8 * (size_t)tiles));
+                    k_oct_scatter<<<tiles, OB_THREADS, 0, st>>>(ray_d[q], in_count, ctx->sort_vals_alt.p, tiles, ctx->sort_vals.p);
+                    MRT_LAUNCHED(ctx);
+                }
+                QueueJob J{ray_o[q], ray_d[q], in_count, sa.hits, sort ? ctx->sort_vals.p : nullptr};
+                const unsigned long long extra = wave == 0 ? (unsigned long long)bpix : 0ull;
+                // the shade stage of this wave: vertex b of the paths; the last vertex emits nothing (its counter slot stays 0)
+                P.vertex = b;
+                sa.in_o = ray_o[q];
+                sa.in_d = ray_d[q];
+                sa.out_o = ray_o[q ^ 1];
+                sa.out_d = ray_d[q ^ 1];
+                sa.out_count = qcounts + (wave + 1 < waves ? wave + 1 : waves);
+                if (fused) {
+                    k_trace_shade<<<tgrid, TRACE_BLOCK, 0, st>>>(J, sa.bvh, work_counters + wave, ctx->visit_counters.p + 4,
+                                                                 ctx->opt_count_visits, ctx->total_rays.p, extra, sa, shade_counters + wave);
+                    MRT_LAUNCHED(ctx);
+                } else {
+                    k_trace<QueueJob><<<tgrid, TRACE_BLOCK, 0, st>>>(J, sa.bvh, work_counters + wave, ctx->visit_counters.p + 4,
+                                                                     ctx->opt_count_visits, ctx->total_rays.p, extra);
+                    MRT_LAUNCHED(ctx);
+                    ctx->hits_dirty = true;
+                }
+                if (timed) {
+                    cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used + 1], st);
+                    ctx->trace_ev_used++;
+                }
+                if (!fused) {
+                    k_shade<false><<<shade_grid, 256, 0, st>>>(sa, in_count);
+                    MRT_LAUNCHED(ctx);
+                }
+                wave++;
+                q ^= 1;
             }
-            if (timed) cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used], ctx->stream);
-            const bool sort = ctx->opt_sort_rays || (flags & MRT_SECONDARY_SORT_RAYS);
-            if (sort) {
-                const uint32_t tiles = div_up(npix, OB_TILE);
-                MRT_TRY(dev_reserve(ctx, ctx->sort_vals, npix));
-                MRT_TRY(dev_reserve(ctx, ctx->sort_vals_alt, 8 * (size_t)tiles));
-                k_oct_hist<<<tiles, OB_THREADS, 0, ctx->stream>>>(ctx->ray_d[q].p, in_count, ctx->sort_vals_alt.p, tiles);
-                MRT_LAUNCHED(ctx);
-                MRT_TRY(scan_exclusive_u32(ctx, ctx->sort_vals_alt.p, ctx->sort_vals_alt.p, 8 * (size_t)tiles));
-                k_oct_scatter<<<tiles, OB_THREADS, 0, ctx->stream>>>(ctx->ray_d[q].p, in_count, ctx->sort_vals_alt.p, tiles,
-                                                                    ctx->sort_vals.p);
-                MRT_LAUNCHED(ctx);
-            }
-            QueueJob J{ctx->ray_o[q].p, ctx->ray_d[q].p, in_count, ctx->hits.p, sort ? ctx->sort_vals.p : nullptr};
-            const unsigned long long extra = wave == 0 ? (unsigned long long)npix : 0ull;
-            // the shade stage of this wave: vertex b of the paths; the last vertex emits nothing (its counter slot stays 0)
-            P.vertex = b;
-            sa.in_o = ctx->ray_o[q].p;
-            sa.in_d = ctx->ray_d[q].p;
-            sa.out_o = ctx->ray_o[q ^ 1].p;
-            sa.out_d = ctx->ray_d[q ^ 1].p;
-            sa.out_count = ctx->queue_counts.p + (wave + 1 < waves ? wave + 1 : waves);
-            if (fused) {
-                k_trace_shade<<<tgrid, TRACE_BLOCK, 0, ctx->stream>>>(J, sa.bvh, work_counters + wave, ctx->visit_counters.p + 4,
-                                                                     ctx->opt_count_visits, ctx->total_rays.p, extra, sa,
-                                                                     shade_counters + wave);
-                MRT_LAUNCHED(ctx);
-            } else {
-                k_trace<QueueJob><<<tgrid, TRACE_BLOCK, 0, ctx->stream>>>(J, sa.bvh, work_counters + wave, ctx->visit_counters.p + 4,
-                                                                          ctx->opt_count_visits, ctx->total_rays.p, extra);
-                MRT_LAUNCHED(ctx);
-                ctx->hits_dirty = true;
-            }
-            if (timed) {
-                cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used + 1], ctx->stream);
-                ctx->trace_ev_used++;
-            }
-            if (!fused) {
-                k_shade<false><<<shade_grid, 256, 0, ctx->stream>>>(sa, in_count);
-                MRT_LAUNCHED(ctx);
-            }
-            wave++;
-            q ^= 1;
+        }
+        if (bands > 1) {
+            MRT_CUDA(ctx, cudaEventRecord(ctx->band_done[band], st));
+            MRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->band_done[band], 0));
         }
     }
     if (ctx->total_rays.p && waves == 0) {

@@ -284,6 +284,41 @@ def test_path_kernel_equals_wavefront(oracle, sky_inputs, blue_noise):
             ctx.close()
 
 
+def test_bands_do_not_change_the_image(oracle, sky_inputs, blue_noise):
+    """Option bands (pixel ranges rendered on their own streams so that one band's traversal drain overlaps another
+    band's kernels): accumulator, ray count and framebuffer equal the one-band render bit for bit, also with
+    progressive accumulation and under a tile partition."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    ctx = capi.Context(0)
+    try:
+        ctx.upload_blue_noise(blue_noise)
+        ctx.upload_mesh(pos, idx, alb)
+        ctx.build()
+        for (w, h), part in (((640, 411), (0, 1)), ((1001, 517), (1, 2))):
+            cam = camera_for(oracle, view, w, h)
+            setup_sky(ctx, oracle, atmo, cam.position[:])
+            ctx.set_partition(part[0], part[1], 8)
+            out = []
+            for bands in (1, 2, 3, 4, 8, 1):
+                ctx.set_option("bands", bands)
+                rays = 0
+                for frame in (5, 6):
+                    pc, scn = oracle.constants(cam, frame=frame)
+                    ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+                    ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 3, 2, capi.SECONDARY_ACCUMULATE if frame == 6 else 0)
+                    st = ctx.stats()
+                    assert st.stack_overflows == 0
+                    rays += int(st.secondary_rays)
+                ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+                out.append((ctx.readback(capi.BUF_ACCUM).copy(), ctx.readback(capi.BUF_LDR).copy(), rays))
+            for o in out[1:]:
+                assert o[2] == out[0][2]
+                assert np.array_equal(o[0], out[0][0], equal_nan=True) and np.array_equal(o[1], out[0][1])
+    finally:
+        ctx.close()
+
+
 def test_async_readback_matches_blocking(gpu_ctx, oracle, sky_inputs, blue_noise):
     """Pipelined framebuffer readback (double-buffered LDR): frame f's async copy equals its blocking readback even
     when frame f+1 has been issued in between."""

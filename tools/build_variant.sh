@@ -8,12 +8,12 @@ NAME=$1; EXTRA=$2
 OUT=$ROOT/variants/$NAME
 mkdir -p "$OUT/obj"
 cd "$ROOT/minotert_b200/csrc"
-for f in api sky spheres tonemap denoise temporal sort bvh_build mesh; do
+for f in api sky spheres tonemap denoise temporal sort bvh_build mesh group probe; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false \
     -Xcompiler -fPIC -ccbin /usr/bin/g++ $EXTRA -c $f.cu -o "$OUT/obj/$f.o" &
 done
 wait
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libminotert.so" "$OUT"/obj/*.o -ccbin /usr/bin/g++
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libminotert.so" "$OUT"/obj/*.o -ccbin /usr/bin/g++ -ldl
 cp "$ROOT/minotert_b200/libminote_host.so" "$OUT/"
 rm -rf "$OUT/obj"
 echo "built $OUT"
