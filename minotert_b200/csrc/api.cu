@@ -203,6 +203,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "persistent_primary")) ctx->opt_persistent_primary = value != 0;
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;
+    else if (!strcmp(name, "primary_entry")) ctx->opt_primary_entry = value != 0;
     else if (!strcmp(name, "path_kernel")) ctx->opt_path_kernel = value != 0;
     else if (!strcmp(name, "bands")) ctx->opt_bands = (int)(value < 1 ? 1 : (value > MRT_MAX_BANDS ? MRT_MAX_BANDS : value));
     else if (!strcmp(name, "trace_ctas_per_sm")) ctx->opt_trace_ctas_per_sm = (int)(value > 32 ? 32 : value);

@@ -319,6 +319,51 @@ def test_bands_do_not_change_the_image(oracle, sky_inputs, blue_noise):
         ctx.close()
 
 
+def test_primary_entry_list_does_not_change_the_gbuffer(gpu_ctx, oracle):
+    """Option primary_entry (the top of the BVH walked once per 8x4 tile against the tile's frustum, rays start from
+    the entry list): visibility ids, hit distances and the fp16 G-buffer are bit-identical to the walk from the root --
+    for cameras outside and inside the geometry, looking along the axes (tiles that straddle an octant boundary fall
+    back), with prime image sizes (padding lanes), far from the origin (widened entry boxes), and ids/t equal the
+    brute force over all triangles on sampled pixels."""
+    rng = np.random.default_rng(12)
+    cases = []
+    for maker in ("cornell", "small_terrain", "hall_260k"):
+        pos, idx, alb, view = getattr(scenes, maker)()
+        cams = [(view["position"], view["yaw_deg"], view["pitch_deg"]), (view["position"], 90.0, 0.0),
+                (tuple(np.asarray(pos.mean(0)) + [0.0, 0.0, 0.0005]), 37.0, -25.0), (view["position"], 180.0, 89.0)]
+        cases.append((pos, idx, alb, cams))
+    pos, idx, alb, view = scenes.small_terrain()
+    shift = np.array([1000.0, -2000.0, 500.0], np.float32)   # far from the origin: coordinates' ulp ~ the ray offset
+    cases.append((pos + shift, idx, alb, [(tuple(np.asarray(view["position"]) + shift), view["yaw_deg"], view["pitch_deg"])]))
+    for pos, idx, alb, cams in cases:
+        gpu_ctx.upload_mesh(pos, idx, alb)
+        gpu_ctx.build()
+        for (cpos, yaw, pitch) in cams:
+            for (w, h) in ((331, 197), (1280, 720)):
+                cam = oracle.make_camera(w, h, cpos, yaw, pitch)
+                pc, _ = oracle.constants(cam, frame=1)
+                out = []
+                for entry in (0, 1):
+                    gpu_ctx.set_option("primary_entry", entry)
+                    gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+                    assert gpu_ctx.stats().stack_overflows == 0
+                    out.append([gpu_ctx.readback(b).copy() for b in (capi.BUF_VISIBILITY, capi.BUF_HIT_T, capi.BUF_DEPTH,
+                                                                      capi.BUF_NORMAL, capi.BUF_MOTION)])
+                for a, b in zip(*out):
+                    assert np.array_equal(a, b), f"primary_entry changes the G-buffer ({w}x{h}, yaw {yaw}, pitch {pitch})"
+                # sampled pixels vs brute force
+                xs, ys = rng.integers(0, w, 400), rng.integers(0, h, 400)
+                o = np.zeros((400, 3), np.float32)
+                d = np.zeros((400, 3), np.float32)
+                oo, dd = (C.c_float * 3)(), (C.c_float * 3)()
+                for k in range(400):
+                    oracle.lib().orc_ray_gen(C.byref(pc.invView), C.byref(pc.invProjection), int(xs[k]), int(ys[k]), w, h, oo, dd)
+                    o[k], d[k] = oo[:], dd[:]
+                ids_bf, t_bf = gpu_ctx.trace_rays(o, d, brute_force=True)
+                assert np.array_equal(out[1][0][ys, xs], ids_bf) and np.array_equal(out[1][1][ys, xs], t_bf)
+    gpu_ctx.set_option("primary_entry", 1)
+
+
 def test_async_readback_matches_blocking(gpu_ctx, oracle, sky_inputs, blue_noise):
     """Pipelined framebuffer readback (double-buffered LDR): frame f's async copy equals its blocking readback even
     when frame f+1 has been issued in between."""
