@@ -71,6 +71,8 @@ def load():
     L.minote_app_stats.argtypes = [vp, C.POINTER(capi.Stats)]
     L.minote_app_read_framebuffer_async.argtypes = [vp, vp, C.c_size_t]
     L.minote_app_wait_framebuffer.argtypes = [vp, C.c_int]
+    L.minote_app_frame_time.argtypes = [vp]
+    L.minote_app_frame_time.restype = C.c_float
     L.minote_app_frame_count.argtypes = [vp]
     L.minote_app_frame_count.restype = u32
     _lib = L
@@ -198,6 +200,10 @@ class Renderer:
         s = capi.Stats()
         self._ck(self.L.minote_app_stats(self.h, C.byref(s)))
         return s
+
+    def frame_time(self):
+        """Renderer_impl::frameTime(): moving average over 0.25 s of the time between draw() calls, in seconds."""
+        return float(self.L.minote_app_frame_time(self.h))
 
     def frame_count(self):
         return self.L.minote_app_frame_count(self.h)

@@ -187,6 +187,7 @@ int minote_app_wait_framebuffer(void* a, int frames_in_flight) {
 int minote_app_stats(void* a, mrt_stats* out) {
     return guarded(static_cast<App*>(a), [&] { *out = Renderer::serv->stats(); });
 }
+float minote_app_frame_time(void* a) { (void)a; return Renderer::serv ? Renderer::serv->frameTime() : 0.0f; }
 std::uint32_t minote_app_frame_count(void* a) { (void)a; return Cuda::serv ? Cuda::serv->frameCount() : 0; }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 // replaced by an RGBA8 framebuffer the caller reads back.
 module;
 #include <cstdint>
+#include <ctime>
 
 #include "../../include/minotert.h"
 export module minote.renderer;
@@ -53,6 +54,7 @@ public:
     }
 
     void draw(Camera const& camera) {
+        updateFrameTime();
         // Begin the frame: the next frame context (a progressive accumulator or a temporal history lives in one
         // context, so with either the frame stays put)
         Cuda::serv->nextFrame(!pathtracer.accumulate && !temporal);
@@ -75,6 +77,10 @@ public:
         // Temporal preservation
         prevCamera = camera;
     }
+
+    // moving-average frame time in seconds, refreshed every 0.25 s (renderer.ixx:37,70-71,113-125); the reference shows it
+    // in its ImGui overlay, here the caller prints it
+    [[nodiscard]] auto frameTime() const -> float { return m_frameTime; }
 
     // host copy of the output framebuffer (RGBA8); blocks until the frame is done
     void readFramebuffer(void* host, std::size_t bytes) const { framebuffer.readback(host, bytes); }
@@ -163,6 +169,27 @@ private:
         default: Cuda::serv->raise("Unknown tonemap mode");
         }
     }
+
+    // renderer.ixx:113-125 (Window::getTime -> the monotonic clock)
+    static constexpr double FrameTimeUpdate = 0.25;
+    static auto now() -> double {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return double(ts.tv_sec) + 1e-9 * double(ts.tv_nsec);
+    }
+    void updateFrameTime() {
+        framesSinceLastCheck += 1;
+        auto const currentTime = now();
+        auto const timeElapsed = currentTime - lastFrameTimeCheck;
+        if (timeElapsed >= FrameTimeUpdate) {
+            m_frameTime = float(timeElapsed / double(framesSinceLastCheck));
+            lastFrameTimeCheck = currentTime;
+            framesSinceLastCheck = 0;
+        }
+    }
+    float m_frameTime = 0.0f;
+    double lastFrameTimeCheck = now();
+    unsigned framesSinceLastCheck = 0;
 
     Camera prevCamera{};
     DeviceImage blueNoise;
