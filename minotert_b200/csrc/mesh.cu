@@ -85,6 +85,9 @@ struct PrimaryJob {
     MRT_D void store_with_ray(uint32_t i, const TraceHit& h, float3 o, float3 d) const {
         uint32_t x, lr;
         pixel(i, x, lr);
+        store_xy(x, lr, h, o, d);
+    }
+    MRT_D void store_xy(uint32_t x, uint32_t lr, const TraceHit& h, float3 o, float3 d) const {
         const size_t p = (size_t)lr * F.gen.W + x;
         float dep = 0.0f;
         float2 mo = make_float2(0.0f, 0.0f);
@@ -102,226 +105,274 @@ struct PrimaryJob {
 };
 
 // ---- tile-frustum entry (primary rays) ----
-// The 32 rays of an 8x4-pixel tile share their origin and differ by a fraction of a degree, yet each of them used to
-// repeat the child tests of the upper BVH levels for itself (ncu r1: 268 M warp instructions for 2 M rays).  Now the
-// warp walks the top of the tree ONCE against the tile's frustum -- 8 lanes test the 8 children of a node, four nodes
-// per round -- down to the nodes that are no larger than the tile's footprint at their distance, and leaves the
-// result in shared memory as an ENTRY LIST: node entries (node index + fp32 box) and leaf entries (the triangles of a
-// leaf slot of a descended node + its box), sorted near to far.  Every ray then tests itself against the entry boxes
-// (12 instructions each, no divergence), tests the triangles of the leaf entries it touches, pushes the node entries it
-// touches onto its own stack, far to near, and continues with the ordinary per-ray walk.
-// Exactness: the frustum test and the entry-box test only ever REJECT boxes that no ray of the tile / the ray cannot
-// touch (planes through the four corner rays, slack for rounding; boxes decoded from the quantised planes and widened
-// by 2 ulp), so the set of triangles a ray tests still contains its closest hit, and closest hit = lexicographic
+// The rays of a screen tile share their origin and differ by a fraction of a degree, yet each of them used to repeat
+// the child tests of the upper BVH levels for itself (ncu r1: 268 M warp instructions for 2 M rays).  Now a CTA owns a
+// 32x16-pixel tile and
+//   A. walks the top of the tree ONCE against the tile's frustum, all 128 threads together (8 threads test the 8
+//      children of a node, 16 nodes per round), down to the nodes that are no larger than the footprint of an 8x4 SUB-tile
+//      at their distance; the result is an ENTRY LIST in shared memory -- node entries (node index + fp32 box relative to
+//      the camera) and leaf entries (the triangles of a leaf slot of a descended node + its box) -- sorted near to far;
+//   B. each warp then takes four of the tile's sixteen 8x4 sub-tiles in turn: it culls the list against the sub-tile's own
+//      frustum (one entry per lane, a ballot per 32 entries), and every ray tests itself against the surviving boxes
+//      (12 instructions each, no divergence), tests the triangles of the leaf entries it touches, pushes the node
+//      entries it touches onto its own stack, far to near, and continues with the ordinary per-ray walk.
+// A first version that built the list per warp (8x4 tile) removed 70 % of the primary node steps and gained nothing:
+// the descent and the sort cost every lane as much as the steps they saved.  Amortised over 512 rays they cost ~3 %.
+// Exactness: the frustum tests and the entry-box test only ever REJECT boxes that no ray of the tile / the ray cannot
+// touch (planes through the corner rays of the tile, slack for rounding; boxes decoded from the quantised planes and
+// widened by 2 ulp), so the set of triangles a ray tests still contains its closest hit, and closest hit = lexicographic
 // minimum of (t, primitive id) does not depend on the order: ids and t stay bit-identical to brute force (tested).
-// Tiles whose rays do not share one direction octant (they straddle an axis plane through the camera) and trees of a
-// single node fall back to the walk from the root.
+// Tiles whose corner rays do not share one direction octant (they straddle an axis plane through the camera), trees of
+// a single node and tiles whose list would overflow fall back to the walk from the root.
 #ifndef PRIMARY_ENTRY
 #define PRIMARY_ENTRY 1
 #endif
 #ifndef ENTRY_MAX
-#define ENTRY_MAX 64       // entries per tile
+#define ENTRY_MAX 256      // entries per 32x16 tile (a power of two: bitonic sort)
 #endif
 #ifndef ENTRY_WORK
-#define ENTRY_WORK 64      // nodes per level of the frustum walk
+#define ENTRY_WORK 256     // nodes per level of the frustum walk
+#endif
+#ifndef ENTRY_SUB
+#define ENTRY_SUB 96       // entries a sub-tile may keep after culling
 #endif
 #ifndef ENTRY_K
-#define ENTRY_K 1.0f       // descend while a node's diagonal exceeds ENTRY_K x the tile's footprint at its distance
+#define ENTRY_K 1.0f       // descend while a node's diagonal exceeds ENTRY_K x the sub-tile's footprint at its distance
 #endif
 #define ENTRY_NODE 0xFFFFFFFFu
+#define BIG_W 32
+#define BIG_H 16
 
-struct EntryTile {                   // per warp
+struct EntryTile {                   // per CTA
     float rn[3][ENTRY_MAX];          // entry planes relative to the camera: the ones the tile's octant enters through ...
     float rf[3][ENTRY_MAX];          // ... and leaves through
-    float dist[ENTRY_MAX];           // lower bound of the distance along the tile axis (sort key)
     uint32_t a[ENTRY_MAX];           // node entry: node index; leaf entry: tri_base of the node
     uint32_t b[ENTRY_MAX];           // node entry: ENTRY_NODE; leaf entry: the slot's triangle bits
     uint32_t c[ENTRY_MAX];           // leaf entry: leafmask24 of the node
+    unsigned long long key[ENTRY_MAX];  // sort key: ordered distance bits << 32 | entry index
     uint32_t work[2][ENTRY_WORK];
+    unsigned char sub[TRACE_BLOCK / 32][ENTRY_SUB];  // per warp: the entries that survive its sub-tile's frustum
+    int nwork, nnext, nent, overflow;
 };
 
-// Builds the tile's entry list; returns the number of entries, or -1 for "walk from the root".  All 32 lanes call it
-// with their ray (padding lanes included: their rays exist even if their pixels do not).
-MRT_D int build_entry_list(const BvhDev& bvh, float3 o, float3 d, unsigned oct_inv, EntryTile& E, TraceCounters& cnt) {
-    const unsigned lane = threadIdx.x & 31, full = 0xFFFFFFFFu;
-    if (bvh.num_nodes < 2) return -1;
-    if (!__all_sync(full, oct_inv == __shfl_sync(full, oct_inv, 0))) return -1;
-    // corner rays of the 8x4 tile: lanes 0, 7, 24, 31
-    float3 c00 = f3(__shfl_sync(full, d.x, 0), __shfl_sync(full, d.y, 0), __shfl_sync(full, d.z, 0));
-    float3 c10 = f3(__shfl_sync(full, d.x, 7), __shfl_sync(full, d.y, 7), __shfl_sync(full, d.z, 7));
-    float3 c01 = f3(__shfl_sync(full, d.x, 24), __shfl_sync(full, d.y, 24), __shfl_sync(full, d.z, 24));
-    float3 c11 = f3(__shfl_sync(full, d.x, 31), __shfl_sync(full, d.y, 31), __shfl_sync(full, d.z, 31));
-    const float3 axis = normalize3(c00 + c10 + c01 + c11);
-    // inward normals of the four side planes (through the camera and two neighbouring corner rays)
-    float3 pn[4] = {cross3(c00, c10), cross3(c10, c11), cross3(c11, c01), cross3(c01, c00)};
+struct Frustum { float3 pn[4]; float3 axis; float angle; };
+
+// frustum through four corner directions (any order around the tile)
+MRT_D Frustum make_frustum(float3 c00, float3 c10, float3 c01, float3 c11) {
+    Frustum F;
+    F.axis = normalize3(c00 + c10 + c01 + c11);
+    F.pn[0] = cross3(c00, c10); F.pn[1] = cross3(c10, c11); F.pn[2] = cross3(c11, c01); F.pn[3] = cross3(c01, c00);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        if (dot3(pn[k], axis) < 0.0f) pn[k] = -pn[k];
-        pn[k] = normalize3(pn[k]);
+        if (dot3(F.pn[k], F.axis) < 0.0f) F.pn[k] = -F.pn[k];
+        F.pn[k] = normalize3(F.pn[k]);
     }
-    const float tile_angle = length3(c11 - c00);  // angular size of the tile's diagonal (unit vectors)
-    if (!(tile_angle > 0.0f) || !(tile_angle < 0.5f)) return -1;
-    const bool px = oct_inv & 1u, py = oct_inv & 2u, pz = oct_inv & 4u;
-
-    int nentries = 0, nwork = 1, cur = 0;
-    bool overflow = false;
-    if (lane == 0) E.work[0][0] = 0u;
-    __syncwarp();
-    while (nwork > 0 && !overflow) {
-        int nnext = 0;
-        for (int base = 0; base < nwork && !overflow; base += 4) {
-            const int wi = base + (int)(lane >> 3);
-            const unsigned j = lane & 7u;
-            bool is_node = false, is_leaf = false, descend = false;
-            uint32_t child = 0, tri_base = 0, leafbits = 0, leafmask = 0;
-            float3 lo = f3s(0.0f), hi = f3s(0.0f);
-            float dmin = 0.0f;
-            if (wi < nwork) {
-                const uint32_t node = E.work[cur][wi];
-                const uint4* np = reinterpret_cast<const uint4*>(bvh.nodes + node);
-                const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-                if (j == 0) cnt.nodes++;
-                const float stx = __uint_as_float((n0.w & 0xFFu) << 23), sty = __uint_as_float((n0.w & 0xFF00u) << 15),
-                            stz = __uint_as_float((n0.w & 0xFF0000u) << 7);
-                const unsigned sh = 8u * (j & 3u);
-                const bool hi4 = j >= 4u;
-                const float qlx = (float)(((hi4 ? n2.y : n2.x) >> sh) & 0xFFu), qly = (float)(((hi4 ? n2.w : n2.z) >> sh) & 0xFFu),
-                            qlz = (float)(((hi4 ? n3.y : n3.x) >> sh) & 0xFFu);
-                const float qhx = (float)(((hi4 ? n3.w : n3.z) >> sh) & 0xFFu), qhy = (float)(((hi4 ? n4.y : n4.x) >> sh) & 0xFFu),
-                            qhz = (float)(((hi4 ? n4.w : n4.z) >> sh) & 0xFFu);
-                if (qlx <= qhx && qly <= qhy && qlz <= qhz) {  // (empty slots carry the inverted box)
-                    const float ox = __uint_as_float(n0.x), oy = __uint_as_float(n0.y), oz = __uint_as_float(n0.z);
-                    lo = f3(fmaf(qlx, stx, ox), fmaf(qly, sty, oy), fmaf(qlz, stz, oz));
-                    hi = f3(fmaf(qhx, stx, ox), fmaf(qhy, sty, oy), fmaf(qhz, stz, oz));
-                    // the planes the traversal sees are origin + q * step evaluated exactly: widen the fp32 values by 2 ulp of
-                    // the largest magnitude involved, then move to camera-relative coordinates
-                    const float ex = 2.4e-7f * fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fabsf(o.x)),
-                                ey = 2.4e-7f * fmaxf(fmaxf(fabsf(lo.y), fabsf(hi.y)), fabsf(o.y)),
-                                ez = 2.4e-7f * fmaxf(fmaxf(fabsf(lo.z), fabsf(hi.z)), fabsf(o.z));
-                    lo = f3(lo.x - ex, lo.y - ey, lo.z - ez) - o;
-                    hi = f3(hi.x + ex, hi.y + ey, hi.z + ez) - o;
-                    // frustum test: outside if the box corner furthest along a plane's inward normal is still behind it
-                    const float mag = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
-                    const float slack = 1e-5f * mag;
-                    bool inside = true;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const float s = pn[k].x * (pn[k].x > 0.0f ? hi.x : lo.x) + pn[k].y * (pn[k].y > 0.0f ? hi.y : lo.y) +
-                                        pn[k].z * (pn[k].z > 0.0f ? hi.z : lo.z);
-                        inside = inside && s >= -slack;
-                    }
-                    const float dmax = axis.x * (axis.x > 0.0f ? hi.x : lo.x) + axis.y * (axis.y > 0.0f ? hi.y : lo.y) +
-                                       axis.z * (axis.z > 0.0f ? hi.z : lo.z);
-                    dmin = axis.x * (axis.x > 0.0f ? lo.x : hi.x) + axis.y * (axis.y > 0.0f ? lo.y : hi.y) +
-                           axis.z * (axis.z > 0.0f ? lo.z : hi.z);
-                    inside = inside && dmax >= -slack;  // not entirely behind the camera
-                    if (inside) {
-                        const unsigned imask = n0.w >> 24;
-                        if (imask & (1u << j)) {
-                            is_node = true;
-                            child = n1.x + __popc(imask & ((1u << j) - 1u));
-                            const float diag = length3(hi - lo);
-                            descend = !(dmin > 0.0f) || diag > ENTRY_K * tile_angle * dmin;
-                        } else {
-                            leafbits = n1.z & (7u << (3u * j));
-                            is_leaf = leafbits != 0u;
-                            tri_base = n1.y;
-                            leafmask = n1.z;
-                        }
-                    }
-                }
-            }
-            // inner children that are still large go to the next level, everything else becomes an entry
-            const unsigned dm = __ballot_sync(full, is_node && descend);
-            const bool room = nnext + __popc(dm) <= ENTRY_WORK;
-            const unsigned em = __ballot_sync(full, (is_node && !(descend && room)) || is_leaf);
-            if (room && (is_node && descend)) E.work[cur ^ 1][nnext + __popc(dm & ((1u << lane) - 1u))] = child;
-            if (room) nnext += __popc(dm);
-            if (nentries + __popc(em) > ENTRY_MAX) { overflow = true; break; }
-            if ((is_node && !(descend && room)) || is_leaf) {
-                const int e = nentries + __popc(em & ((1u << lane) - 1u));
-                E.rn[0][e] = px ? lo.x : hi.x; E.rf[0][e] = px ? hi.x : lo.x;
-                E.rn[1][e] = py ? lo.y : hi.y; E.rf[1][e] = py ? hi.y : lo.y;
-                E.rn[2][e] = pz ? lo.z : hi.z; E.rf[2][e] = pz ? hi.z : lo.z;
-                E.dist[e] = dmin;
-                E.a[e] = is_node ? child : tri_base;
-                E.b[e] = is_node ? ENTRY_NODE : leafbits;
-                E.c[e] = leafmask;
-            }
-            nentries += __popc(em);
-        }
-        __syncwarp();
-        cur ^= 1;
-        nwork = nnext;
-    }
-    if (overflow) return -1;
-    // sort near to far: rank of each entry by (dist, index), then a permutation through registers
-    __syncwarp();
-    float v[2][8];
-    int rank[2];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int e = (int)lane + 32 * h;
-        rank[h] = -1;
-        if (e < nentries) {
-            const float key = E.dist[e];
-            int r = 0;
-            for (int k = 0; k < nentries; k++) {
-                const float kk = E.dist[k];
-                r += (kk < key || (kk == key && k < e)) ? 1 : 0;
-            }
-            rank[h] = r;
-            v[h][0] = E.rn[0][e]; v[h][1] = E.rn[1][e]; v[h][2] = E.rn[2][e];
-            v[h][3] = E.rf[0][e]; v[h][4] = E.rf[1][e]; v[h][5] = E.rf[2][e];
-            v[h][6] = __uint_as_float(E.a[e]); v[h][7] = __uint_as_float(E.b[e]);
-        }
-    }
-    uint32_t cc[2] = {(int)lane < nentries ? E.c[lane] : 0u, (int)lane + 32 < nentries ? E.c[lane + 32] : 0u};
-    float dd[2] = {(int)lane < nentries ? E.dist[lane] : 0.0f, (int)lane + 32 < nentries ? E.dist[lane + 32] : 0.0f};
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-        if (rank[h] >= 0) {
-            const int r = rank[h];
-            E.rn[0][r] = v[h][0]; E.rn[1][r] = v[h][1]; E.rn[2][r] = v[h][2];
-            E.rf[0][r] = v[h][3]; E.rf[1][r] = v[h][4]; E.rf[2][r] = v[h][5];
-            E.a[r] = __float_as_uint(v[h][6]); E.b[r] = __float_as_uint(v[h][7]);
-            E.c[r] = cc[h]; E.dist[r] = dd[h];
-        }
-    __syncwarp();
-    return nentries;
+    F.angle = length3(c11 - c00);
+    return F;
 }
 
-// closest hit of one ray of the tile, starting from the tile's entry list
-MRT_D TraceHit trace_from_entries(const BvhDev& bvh, float3 o, float3 d, const EntryTile& E, int nentries, TraceShared& S,
+// false: no point of the camera-relative box [lo, hi] lies inside the frustum (conservative: slack for rounding)
+MRT_D bool frustum_touches(const Frustum& F, float3 lo, float3 hi, float& dmin) {
+    const float mag = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
+    const float slack = 1e-5f * mag;
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float3 n = F.pn[k];
+        const float s = n.x * (n.x > 0.0f ? hi.x : lo.x) + n.y * (n.y > 0.0f ? hi.y : lo.y) + n.z * (n.z > 0.0f ? hi.z : lo.z);
+        inside = inside && s >= -slack;
+    }
+    const float3 a = F.axis;
+    const float dmax = a.x * (a.x > 0.0f ? hi.x : lo.x) + a.y * (a.y > 0.0f ? hi.y : lo.y) + a.z * (a.z > 0.0f ? hi.z : lo.z);
+    dmin = a.x * (a.x > 0.0f ? lo.x : hi.x) + a.y * (a.y > 0.0f ? lo.y : hi.y) + a.z * (a.z > 0.0f ? lo.z : hi.z);
+    return inside && dmax >= -slack;  // (not entirely behind the camera)
+}
+
+MRT_D unsigned long long entry_key(float dist, int e) {
+    unsigned u = __float_as_uint(dist);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving map of the float
+    return ((unsigned long long)u << 32) | (unsigned)e;
+}
+
+// Stage A, all threads of the CTA: entry list of the tile with frustum F (camera at o).  Returns the number of entries
+// (sorted near to far), or -1 for "walk from the root".  sub_angle: angular size of an 8x4 sub-tile.
+MRT_D int build_entry_list(const BvhDev& bvh, float3 o, const Frustum& F, float sub_angle, unsigned oct_inv, EntryTile& E,
+                           TraceCounters& cnt) {
+    const bool px = oct_inv & 1u, py = oct_inv & 2u, pz = oct_inv & 4u;
+    if (threadIdx.x == 0) { E.work[0][0] = 0u; E.nwork = 1; E.nnext = 0; E.nent = 0; E.overflow = 0; }
+    __syncthreads();
+    int cur = 0;
+    for (;;) {
+        const int nwork = E.nwork;
+        if (nwork == 0 || E.overflow) break;
+        for (int base = 0; base < nwork; base += TRACE_BLOCK / 8) {
+            const int wi = base + (int)(threadIdx.x >> 3);
+            const unsigned j = threadIdx.x & 7u;
+            if (wi >= nwork) continue;
+            const uint32_t node = E.work[cur][wi];
+            const uint4* np = reinterpret_cast<const uint4*>(bvh.nodes + node);
+            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            if (j == 0) cnt.nodes++;
+            const float stx = __uint_as_float((n0.w & 0xFFu) << 23), sty = __uint_as_float((n0.w & 0xFF00u) << 15),
+                        stz = __uint_as_float((n0.w & 0xFF0000u) << 7);
+            const unsigned sh = 8u * (j & 3u);
+            const bool hi4 = j >= 4u;
+            const float qlx = (float)(((hi4 ? n2.y : n2.x) >> sh) & 0xFFu), qly = (float)(((hi4 ? n2.w : n2.z) >> sh) & 0xFFu),
+                        qlz = (float)(((hi4 ? n3.y : n3.x) >> sh) & 0xFFu);
+            const float qhx = (float)(((hi4 ? n3.w : n3.z) >> sh) & 0xFFu), qhy = (float)(((hi4 ? n4.y : n4.x) >> sh) & 0xFFu),
+                        qhz = (float)(((hi4 ? n4.w : n4.z) >> sh) & 0xFFu);
+            if (!(qlx <= qhx && qly <= qhy && qlz <= qhz)) continue;  // (empty slots carry the inverted box)
+            const float ox = __uint_as_float(n0.x), oy = __uint_as_float(n0.y), oz = __uint_as_float(n0.z);
+            float3 lo = f3(fmaf(qlx, stx, ox), fmaf(qly, sty, oy), fmaf(qlz, stz, oz));
+            float3 hi = f3(fmaf(qhx, stx, ox), fmaf(qhy, sty, oy), fmaf(qhz, stz, oz));
+            // the planes the traversal sees are origin + q * step evaluated exactly: widen the fp32 values by 2 ulp of the
+            // largest magnitude involved, then move to camera-relative coordinates
+            const float ex = 2.4e-7f * fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fabsf(o.x)),
+                        ey = 2.4e-7f * fmaxf(fmaxf(fabsf(lo.y), fabsf(hi.y)), fabsf(o.y)),
+                        ez = 2.4e-7f * fmaxf(fmaxf(fabsf(lo.z), fabsf(hi.z)), fabsf(o.z));
+            lo = f3(lo.x - ex, lo.y - ey, lo.z - ez) - o;
+            hi = f3(hi.x + ex, hi.y + ey, hi.z + ez) - o;
+            float dmin;
+            if (!frustum_touches(F, lo, hi, dmin)) continue;
+            const unsigned imask = n0.w >> 24;
+            const bool is_node = (imask >> j) & 1u;
+            const uint32_t leafbits = n1.z & (7u << (3u * j));
+            uint32_t ea = n1.y, eb = leafbits, ec = n1.z;
+            bool as_entry = !is_node && leafbits != 0u;
+            if (is_node) {
+                const uint32_t child = n1.x + __popc(imask & ((1u << j) - 1u));
+                as_entry = true;
+                ea = child; eb = ENTRY_NODE; ec = 0u;
+                if (!(dmin > 0.0f) || length3(hi - lo) > ENTRY_K * sub_angle * dmin) {  // still large: next level
+                    const int p = atomicAdd(&E.nnext, 1);
+                    if (p < ENTRY_WORK) { E.work[cur ^ 1][p] = child; as_entry = false; }
+                }
+            }
+            if (as_entry) {
+                const int e = atomicAdd(&E.nent, 1);
+                if (e < ENTRY_MAX) {
+                    E.rn[0][e] = px ? lo.x : hi.x; E.rf[0][e] = px ? hi.x : lo.x;
+                    E.rn[1][e] = py ? lo.y : hi.y; E.rf[1][e] = py ? hi.y : lo.y;
+                    E.rn[2][e] = pz ? lo.z : hi.z; E.rf[2][e] = pz ? hi.z : lo.z;
+                    E.a[e] = ea; E.b[e] = eb; E.c[e] = ec;
+                    E.key[e] = entry_key(dmin, e);
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            E.nwork = min(E.nnext, ENTRY_WORK);
+            E.nnext = 0;
+            if (E.nent > ENTRY_MAX) E.overflow = 1;
+        }
+        cur ^= 1;
+        __syncthreads();
+    }
+    const int n = E.nent;
+    if (E.overflow || n > ENTRY_MAX) return -1;
+    // ---- sort near to far: bitonic sort of (distance, index) keys, then the permutation through registers
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int e = n + (int)threadIdx.x; e < m; e += TRACE_BLOCK) E.key[e] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int t = threadIdx.x; t < m; t += TRACE_BLOCK) {
+                const int p = t ^ jj;
+                if (p > t) {
+                    const unsigned long long x = E.key[t], y = E.key[p];
+                    const bool up = (t & k) == 0;
+                    if ((x > y) == up) { E.key[t] = y; E.key[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    float v[2][6];
+    uint32_t w[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int r = (int)threadIdx.x + TRACE_BLOCK * h;
+        if (r < n) {
+            const int e = (int)(unsigned)E.key[r];
+            v[h][0] = E.rn[0][e]; v[h][1] = E.rn[1][e]; v[h][2] = E.rn[2][e];
+            v[h][3] = E.rf[0][e]; v[h][4] = E.rf[1][e]; v[h][5] = E.rf[2][e];
+            w[h][0] = E.a[e]; w[h][1] = E.b[e]; w[h][2] = E.c[e];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int r = (int)threadIdx.x + TRACE_BLOCK * h;
+        if (r < n) {
+            E.rn[0][r] = v[h][0]; E.rn[1][r] = v[h][1]; E.rn[2][r] = v[h][2];
+            E.rf[0][r] = v[h][3]; E.rf[1][r] = v[h][4]; E.rf[2][r] = v[h][5];
+            E.a[r] = w[h][0]; E.b[r] = w[h][1]; E.c[r] = w[h][2];
+        }
+    }
+    __syncthreads();
+    return n;
+}
+
+// Stage B, one warp: the entries of the tile's list that the sub-tile's frustum touches -> E.sub[warp][0..count).
+// Returns the count, or -1 when more than ENTRY_SUB survive (the sub-tile then walks from the root).
+MRT_D int cull_entries(const Frustum& F, unsigned oct_inv, EntryTile& E, int n) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool px = oct_inv & 1u, py = oct_inv & 2u, pz = oct_inv & 4u;
+    int count = 0;
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+        const int e = base + (int)lane;
+        bool keep = false;
+        if (e < n) {
+            const float nx = E.rn[0][e], fx = E.rf[0][e], ny = E.rn[1][e], fy = E.rf[1][e], nz = E.rn[2][e], fz = E.rf[2][e];
+            float dmin;
+            keep = frustum_touches(F, f3(px ? nx : fx, py ? ny : fy, pz ? nz : fz), f3(px ? fx : nx, py ? fy : ny, pz ? fz : nz), dmin);
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+        if (count + __popc(m) > ENTRY_SUB) return -1;
+        if (keep) E.sub[warp][count + __popc(m & ((1u << lane) - 1u))] = (unsigned char)e;
+        count += __popc(m);
+    }
+    __syncwarp();
+    return count;
+}
+
+// closest hit of one ray of a sub-tile, starting from the sub-tile's entries
+MRT_D TraceHit trace_from_entries(const BvhDev& bvh, float3 o, float3 d, const EntryTile& E, int count, TraceShared& S,
                                   TraceCounters& cnt) {
     uint2* const sm = &S.stack[0][threadIdx.x];
+    const unsigned char* const sub = E.sub[threadIdx.x >> 5];
     uint2 spill[TRACE_LOCAL_STACK];
     LaneState L;
     lane_begin(L, o, d);
     L.ng.y = 0u;
-    unsigned long long nodehits = 0ull;
-    for (int e = 0; e < nentries; e++) {
+    // node entries the ray touches, as a bit list over the sub-tile's entries (ENTRY_SUB <= 96 bits)
+    unsigned h0 = 0u, h1 = 0u, h2 = 0u;
+    for (int k = 0; k < count; k++) {
+        const int e = sub[k];
         const float t0x = E.rn[0][e] * L.idn.x, t0y = E.rn[1][e] * L.idn.y, t0z = E.rn[2][e] * L.idn.z;
         const float t1x = E.rf[0][e] * L.idf.x, t1y = E.rf[1][e] * L.idf.y, t1z = E.rf[2][e] * L.idf.z;
         const float tmin = fmaxf(fmaxf(t0x, t0y), t0z), tmax = fminf(fminf(t1x, t1y), t1z);
         const bool hit = tmin <= tmax && tmin <= L.tlimit && tmax >= 0.0f;
         const uint32_t kind = E.b[e];
         if (kind == ENTRY_NODE) {
-            nodehits |= (unsigned long long)(hit ? 1u : 0u) << e;
+            const unsigned bit = hit ? 1u << (k & 31) : 0u;
+            if (k < 32) h0 |= bit; else if (k < 64) h1 |= bit; else h2 |= bit;
         } else if (hit) {
             L.tg = make_uint2(E.a[e], kind);
             L.tgmask = E.c[e];
             while (L.tg.y) lane_tri_step<false>(L, bvh, cnt);
         }
     }
-    // node entries the ray touches: onto the stack far to near; the nearest becomes the pending group
+    // onto the stack far to near; the nearest becomes the pending group
     const unsigned one = (1u << (24u + L.oct_inv)) | 1u;  // "group" of the single node a: slot 0, see lane_node_step
-    while (nodehits) {
-        const int e = 63 - __clzll((long long)nodehits);
-        nodehits &= ~(1ull << e);
-        const uint2 g = make_uint2(E.a[e], one);
-        if (nodehits == 0ull) { L.ng = g; break; }
+    while (h0 | h1 | h2) {
+        int k;
+        if (h2) { k = 31 - __clz(h2); h2 &= ~(1u << k); k += 64; }
+        else if (h1) { k = 31 - __clz(h1); h1 &= ~(1u << k); k += 32; }
+        else { k = 31 - __clz(h0); h0 &= ~(1u << k); }
+        const uint2 g = make_uint2(E.a[sub[k]], one);
+        if (!(h0 | h1 | h2)) { L.ng = g; break; }
         if (L.sp < TRACE_SM_STACK) sm[L.sp * TRACE_BLOCK] = g;
         else if (L.sp < TRACE_SM_STACK + TRACE_LOCAL_STACK) spill[L.sp - TRACE_SM_STACK] = g;
         else cnt.overflow++;
@@ -345,38 +396,68 @@ MRT_D TraceHit trace_from_entries(const BvhDev& bvh, float3 o, float3 d, const E
 #define PRIMARY_MIN_BLOCKS 6  // register cap 85 (ptxas picks 80 instead of 72): measured best of 1, 4, 5, 6, 8, 9
 #endif
 __global__ void __launch_bounds__(TRACE_BLOCK, PRIMARY_MIN_BLOCKS)
-k_mesh_primary(PrimaryJob J, unsigned long long* counters, int count_visits, int use_entry) {
+k_mesh_primary(PrimaryJob J, unsigned long long* counters, int count_visits) {
     __shared__ TraceShared S;
     trace_shared_init(S);
     // CTA = 4 warps = four 8x4 tiles side by side; ray index as in PrimaryJob::pixel
     const uint32_t i = blockIdx.x * TRACE_BLOCK + threadIdx.x;
     TraceCounters cnt{0, 0, 0};
     float3 o, d;
-#if PRIMARY_ENTRY
-    __shared__ EntryTile ET[TRACE_BLOCK / 32];
-    if (use_entry) {
-        // every lane of the warp has a ray (padding pixels too: the frustum needs the tile's corners)
-        uint32_t x, lr;
-        const bool valid = i < J.count() && J.pixel(i, x, lr);
-        J.pixel(i, x, lr);
-        ray_gen(J.F.gen, x, partition_local_to_y(J.F.part, lr), o, d);
-        const unsigned oct_inv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
-        EntryTile& E = ET[threadIdx.x >> 5];
-        const int n = build_entry_list(J.bvh, o, d, oct_inv, E, cnt);
-        if (valid) {
-            TraceHit h = n >= 0 ? trace_from_entries(J.bvh, o, d, E, n, S, cnt) : trace_coherent(J.bvh, o, d, S, cnt);
-            J.store_with_ray(i, h, o, d);
-        }
-        flush_counters(cnt, counters, count_visits != 0);
-        return;
-    }
-#endif
     if (i < J.count() && J.load(i, o, d)) {
         TraceHit h = trace_coherent(J.bvh, o, d, S, cnt);
         J.store_with_ray(i, h, o, d);
     }
     flush_counters(cnt, counters, count_visits != 0);
 }
+
+#if PRIMARY_ENTRY
+// Primary pass with the tile-frustum entry list: CTA = one 32x16-pixel tile (grid = tiles_x32 x tiles_y16).
+__global__ void __launch_bounds__(TRACE_BLOCK, PRIMARY_MIN_BLOCKS)
+k_mesh_primary_entry(PrimaryJob J, uint32_t big_x, unsigned long long* counters, int count_visits) {
+    __shared__ TraceShared S;
+    __shared__ EntryTile E;
+    trace_shared_init(S);
+    TraceCounters cnt{0, 0, 0};
+    const uint32_t bx = blockIdx.x % big_x, by = blockIdx.x / big_x;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, full = 0xFFFFFFFFu;
+    const uint32_t x0 = bx * BIG_W, r0 = by * BIG_H;
+    // the tile's corner rays (pixels outside the image still have rays); local rows map monotonically to image rows
+    float3 o, c00, c10, c01, c11;
+    ray_gen(J.F.gen, x0, partition_local_to_y(J.F.part, r0), o, c00);
+    ray_gen(J.F.gen, x0 + BIG_W - 1, partition_local_to_y(J.F.part, r0), o, c10);
+    ray_gen(J.F.gen, x0, partition_local_to_y(J.F.part, r0 + BIG_H - 1), o, c01);
+    ray_gen(J.F.gen, x0 + BIG_W - 1, partition_local_to_y(J.F.part, r0 + BIG_H - 1), o, c11);
+    auto octant = [](float3 d) { return 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u)); };
+    const unsigned oct_inv = octant(c00);
+    int n = -1;
+    const Frustum FB = make_frustum(c00, c10, c01, c11);
+    // one octant for the whole tile (the interior rays are convex combinations of the corners), a sane frustum, a real tree
+    const bool usable = J.bvh.num_nodes >= 2 && octant(c10) == oct_inv && octant(c01) == oct_inv && octant(c11) == oct_inv &&
+                        FB.angle > 0.0f && FB.angle < 0.5f;
+    if (usable) n = build_entry_list(J.bvh, o, FB, FB.angle * 0.25f, oct_inv, E, cnt);
+    for (int it = 0; it < (BIG_W / 8) * (BIG_H / 4) / (TRACE_BLOCK / 32); it++) {
+        const unsigned sidx = it * (TRACE_BLOCK / 32) + warp;        // sub-tile of this warp: 4 x 4 grid of 8x4 tiles
+        const uint32_t x = x0 + (sidx & 3u) * 8u + (lane & 7u), lr = r0 + (sidx >> 2) * 4u + (lane >> 3);
+        const bool valid = x < J.F.gen.W && lr < J.F.local_rows;
+        float3 d;
+        ray_gen(J.F.gen, x, partition_local_to_y(J.F.part, lr), o, d);
+        int count = -1;
+        if (n >= 0) {
+            const Frustum FS = make_frustum(f3(__shfl_sync(full, d.x, 0), __shfl_sync(full, d.y, 0), __shfl_sync(full, d.z, 0)),
+                                            f3(__shfl_sync(full, d.x, 7), __shfl_sync(full, d.y, 7), __shfl_sync(full, d.z, 7)),
+                                            f3(__shfl_sync(full, d.x, 24), __shfl_sync(full, d.y, 24), __shfl_sync(full, d.z, 24)),
+                                            f3(__shfl_sync(full, d.x, 31), __shfl_sync(full, d.y, 31), __shfl_sync(full, d.z, 31)));
+            count = cull_entries(FS, oct_inv, E, n);
+        }
+        if (valid) {
+            const TraceHit h = count >= 0 ? trace_from_entries(J.bvh, o, d, E, count, S, cnt) : trace_coherent(J.bvh, o, d, S, cnt);
+            J.store_xy(x, lr, h, o, d);
+        }
+        __syncwarp();
+    }
+    flush_counters(cnt, counters, count_visits != 0);
+}
+#endif
 
 // ---- one wave of the wavefront: queue entry k -> hit record k ----
 struct QueueJob {
@@ -978,9 +1059,15 @@ int mesh_primary(mrt_context* ctx) {
     if (ctx->opt_persistent_primary)
         k_trace<PrimaryJob><<<trace_grid(ctx, (size_t)J.tiles * 32), TRACE_BLOCK, 0, ctx->stream>>>(
             J, J.bvh, ctx->counters.p + 8, ctx->visit_counters.p, ctx->opt_count_visits);
+#if PRIMARY_ENTRY
+    else if (ctx->opt_primary_entry) {
+        const uint32_t big_x = div_up(ctx->W, BIG_W), big_y = div_up(ctx->local_rows, BIG_H);
+        k_mesh_primary_entry<<<big_x * big_y, TRACE_BLOCK, 0, ctx->stream>>>(J, big_x, ctx->visit_counters.p, ctx->opt_count_visits);
+    }
+#endif
     else
         k_mesh_primary<<<div_up((size_t)J.tiles * 32, TRACE_BLOCK), TRACE_BLOCK, 0, ctx->stream>>>(J, ctx->visit_counters.p,
-                                                                                                  ctx->opt_count_visits, ctx->opt_primary_entry);
+                                                                                                  ctx->opt_count_visits);
     MRT_LAUNCHED(ctx);
     ctx->stats.primary_rays = ctx->npix;
     return mrt_check_cuda(ctx, cudaGetLastError(), "mesh_primary");
