@@ -261,6 +261,12 @@ int mrt_stream(mrt_context* ctx, void** stream_out);
 int mrt_trace_rays(mrt_context* ctx, const float* origins, const float* directions, uint32_t n,
                    uint32_t* prim_ids, float* t, int brute_force);
 
+/* ---- checkpoint / resume of a progressive render: the only cross-frame state of the path is the fp32
+ * accumulator (xyz radiance sums, w samples).  Dump it with mrt_readback(MRT_BUF_ACCUM); restore it here -- after an
+ * mrt_primary_rays at the same size and partition -- and continue with MRT_SECONDARY_ACCUMULATE and the next frame
+ * counter: the result is bit-identical to the uninterrupted render. */
+int mrt_accum_restore(mrt_context* ctx, const float* rgba32f, size_t bytes);
+
 /* ---- device-side unit probes (tests / tools): the per-path shading functions evaluated on the GPU ----
  * skyColor() of src/gpu/secondaryRays.comp:36-58 for n directions (directions, rgb_out: n x 3 floats) with the LUTs of
  * the last mrt_atmosphere / mrt_sky_view */

@@ -65,7 +65,7 @@ EXPORTS = [
     "mrt_secondary_rays", "mrt_tonemap", "mrt_buffer", "mrt_readback", "mrt_sync", "mrt_stats_get",
     "mrt_stats_reset", "mrt_stream", "mrt_trace_rays", "mrt_partition_rows_for", "mrt_readback_async",
     "mrt_readback_wait", "mrt_denoise_bilateral", "mrt_scene_share", "mrt_temporal_accumulate",
-    "mrt_eval_sky_color", "mrt_eval_bounce_stream",
+    "mrt_eval_sky_color", "mrt_eval_bounce_stream", "mrt_accum_restore",
     "mrt_group_create", "mrt_group_unique_id", "mrt_group_create_rank", "mrt_group_destroy", "mrt_group_last_error",
     "mrt_group_size", "mrt_group_context", "mrt_group_set_tiles", "mrt_group_render", "mrt_group_tonemap",
     "mrt_group_gather", "mrt_group_reduce", "mrt_group_result", "mrt_group_readback", "mrt_group_sync",
@@ -122,6 +122,7 @@ def load():
     L.mrt_stream.argtypes = [vp, C.POINTER(vp)]
     L.mrt_trace_rays.argtypes = [vp, vp, vp, u32, vp, vp, C.c_int]
     L.mrt_partition_rows_for.argtypes = [u32, u32, u32, u32, vp, C.POINTER(u32)]
+    L.mrt_accum_restore.argtypes = [vp, vp, C.c_size_t]
     L.mrt_eval_sky_color.argtypes = [vp, f32p, vp, u32, vp]
     L.mrt_eval_bounce_stream.argtypes = [vp, u32, u32, u32, f32p, f32p, u32, vp]
     L.mrt_group_create.argtypes = [C.POINTER(C.c_int), u32, C.c_int, C.POINTER(vp)]
@@ -322,6 +323,11 @@ class Context:
         t = np.empty(o.shape[0], np.float32)
         self._ck(self.L.mrt_trace_rays(self.h, _ptr(o), _ptr(d), o.shape[0], _ptr(ids), _ptr(t), int(brute_force)))
         return ids, t
+
+    def accum_restore(self, accum):
+        """mrt_accum_restore: resume a progressive render from a dumped accumulator (readback(BUF_ACCUM))."""
+        a = np.ascontiguousarray(accum, np.float32)
+        self._ck(self.L.mrt_accum_restore(self.h, _ptr(a), a.nbytes))
 
     def eval_sky_color(self, camera_pos, directions):
         """skyColor() evaluated on the GPU for an (n, 3) array of directions (mrt_eval_sky_color)."""

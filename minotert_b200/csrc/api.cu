@@ -610,6 +610,18 @@ int mrt_trace_rays(mrt_context* ctx, const float* origins, const float* directio
     return mesh_trace_rays(ctx, origins, directions, n, prim_ids, t, brute_force);
 }
 
+int mrt_accum_restore(mrt_context* ctx, const float* rgba32f, size_t bytes) {
+    MRT_ENTER(ctx);
+    if (!ctx->have_gbuffer) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_accum_restore before mrt_primary_rays (the image size is not known yet)");
+    if (!rgba32f || bytes != ctx->npix * sizeof(float4))
+        return mrt_fail(ctx, MRT_ERR_INVALID, "mrt_accum_restore: %zu bytes for a %zu-byte accumulator", bytes, ctx->npix * sizeof(float4));
+    MRT_CUDA(ctx, cudaMemcpyAsync(ctx->accum.p, rgba32f, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffer is consumed before the call returns
+    ctx->have_accum = true;
+    ctx->have_color = false;
+    return MRT_OK;
+}
+
 int mrt_eval_sky_color(mrt_context* ctx, const float cameraPos[3], const float* directions, uint32_t n, float* rgb_out) {
     MRT_ENTER(ctx);
     if (!ctx->have_atmo || !ctx->have_view) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_eval_sky_color: sky LUTs missing (mrt_atmosphere, mrt_sky_view)");

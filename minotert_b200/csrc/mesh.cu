@@ -196,7 +196,7 @@ MRT_D unsigned long long entry_key(float dist, int e) {
 
 // Stage A, all threads of the CTA: entry list of the tile with frustum F (camera at o).  Returns the number of entries
 // (sorted near to far), or -1 for "walk from the root".  sub_angle: angular size of an 8x4 sub-tile.
-MRT_D int build_entry_list(const BvhDev& bvh, float3 o, const Frustum& F, float sub_angle, unsigned oct_inv, EntryTile& E,
+MRT_D int build_entry_list(const BvhDev& bvh, float3 o, const Frustum& F, float sub_angle, float t_far, unsigned oct_inv, EntryTile& E,
                            TraceCounters& cnt) {
     const bool px = oct_inv & 1u, py = oct_inv & 2u, pz = oct_inv & 4u;
     if (threadIdx.x == 0) { E.work[0][0] = 0u; E.nwork = 1; E.nnext = 0; E.nent = 0; E.overflow = 0; }
@@ -243,7 +243,9 @@ MRT_D int build_entry_list(const BvhDev& bvh, float3 o, const Frustum& F, float 
                 const uint32_t child = n1.x + __popc(imask & ((1u << j) - 1u));
                 as_entry = true;
                 ea = child; eb = ENTRY_NODE; ec = 0u;
-                if (!(dmin > 0.0f) || length3(hi - lo) > ENTRY_K * sub_angle * dmin) {  // still large: next level
+                // still large, and not beyond everything the probe rays hit (occluded parts of the frustum stay coarse:
+                // a ray that does get there walks them the ordinary way)
+                if (dmin <= t_far && (!(dmin > 0.0f) || length3(hi - lo) > ENTRY_K * sub_angle * dmin)) {
                     const int p = atomicAdd(&E.nnext, 1);
                     if (p < ENTRY_WORK) { E.work[cur ^ 1][p] = child; as_entry = false; }
                 }
@@ -431,17 +433,23 @@ k_mesh_primary_entry(PrimaryJob J, uint32_t big_x, unsigned long long* counters,
     const unsigned oct_inv = octant(c00);
     int n = -1;
     const Frustum FB = make_frustum(c00, c10, c01, c11);
+    __shared__ float probe_far[TRACE_BLOCK / 32];
     // one octant for the whole tile (the interior rays are convex combinations of the corners), a sane frustum, a real tree
     const bool usable = J.bvh.num_nodes >= 2 && octant(c10) == oct_inv && octant(c01) == oct_inv && octant(c11) == oct_inv &&
                         FB.angle > 0.0f && FB.angle < 0.5f;
-    if (usable) n = build_entry_list(J.bvh, o, FB, FB.angle * 0.25f, oct_inv, E, cnt);
     for (int it = 0; it < (BIG_W / 8) * (BIG_H / 4) / (TRACE_BLOCK / 32); it++) {
-        const unsigned sidx = it * (TRACE_BLOCK / 32) + warp;        // sub-tile of this warp: 4 x 4 grid of 8x4 tiles
+        // sub-tile of this warp: 4 x 4 grid of 8x4 tiles; the first round takes the diagonal (spread over the tile) and walks
+        // from the root: its hit distances bound how deep into the frustum the entry list needs to be fine
+        const unsigned sidx = ((warp + (unsigned)it) & 3u) * 4u + warp;  // column = warp, row = (warp + it) mod 4
         const uint32_t x = x0 + (sidx & 3u) * 8u + (lane & 7u), lr = r0 + (sidx >> 2) * 4u + (lane >> 3);
         const bool valid = x < J.F.gen.W && lr < J.F.local_rows;
         float3 d;
         ray_gen(J.F.gen, x, partition_local_to_y(J.F.part, lr), o, d);
         int count = -1;
+        if (it == 1) {  // (uniform across the CTA)
+            float t_far = fmaxf(fmaxf(probe_far[0], probe_far[1]), fmaxf(probe_far[2], probe_far[3]));
+            if (usable) n = build_entry_list(J.bvh, o, FB, FB.angle * 0.25f, t_far, oct_inv, E, cnt);
+        }
         if (n >= 0) {
             const Frustum FS = make_frustum(f3(__shfl_sync(full, d.x, 0), __shfl_sync(full, d.y, 0), __shfl_sync(full, d.z, 0)),
                                             f3(__shfl_sync(full, d.x, 7), __shfl_sync(full, d.y, 7), __shfl_sync(full, d.z, 7)),
@@ -449,10 +457,21 @@ k_mesh_primary_entry(PrimaryJob J, uint32_t big_x, unsigned long long* counters,
                                             f3(__shfl_sync(full, d.x, 31), __shfl_sync(full, d.y, 31), __shfl_sync(full, d.z, 31)));
             count = cull_entries(FS, oct_inv, E, n);
         }
+        TraceHit h;
+        h.t = 0.0f; h.prim = h.tri = MRT_MISS_ID;
         if (valid) {
-            const TraceHit h = count >= 0 ? trace_from_entries(J.bvh, o, d, E, count, S, cnt) : trace_coherent(J.bvh, o, d, S, cnt);
+            h = count >= 0 ? trace_from_entries(J.bvh, o, d, E, count, S, cnt) : trace_coherent(J.bvh, o, d, S, cnt);
             J.store_xy(x, lr, h, o, d);
         }
+        if (it == 0) {  // farthest hit of the warp's probe sub-tile; a miss (or a pixel off the image) means "no bound"
+            float far = (valid && h.prim != MRT_MISS_ID) ? h.t * 1.001f : 3.0e38f;
+            for (int off = 16; off > 0; off >>= 1) far = fmaxf(far, __shfl_xor_sync(full, far, off));
+            if (lane == 0) probe_far[warp] = far;
+            __syncthreads();
+        }
+#ifdef ENTRY_DEBUG
+        if (it > 0 && lane == 0 && blockIdx.x % 397 == 0) printf("tile %u sub %u: n %d count %d\n", blockIdx.x, sidx, n, count);
+#endif
         __syncwarp();
     }
     flush_counters(cnt, counters, count_visits != 0);

@@ -364,6 +364,53 @@ def test_primary_entry_list_does_not_change_the_gbuffer(gpu_ctx, oracle):
     gpu_ctx.set_option("primary_entry", 1)
 
 
+def test_checkpoint_resume_of_a_progressive_render(oracle, sky_inputs, blue_noise):
+    """SURVEY 5 checkpoint/resume: dump the fp32 accumulator after 2 frames, restore it in a fresh context, render
+    frames 3-4 on top: bit-identical to the uninterrupted 4-frame accumulation."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h = 200, 120
+    cam = camera_for(oracle, view, w, h)
+
+    def fresh():
+        c = capi.Context(0)
+        setup_sky(c, oracle, atmo, cam.position[:])
+        c.upload_blue_noise(blue_noise)
+        c.upload_mesh(pos, idx, alb)
+        c.build()
+        return c
+
+    def frame(c, f, accumulate):
+        pc, scn = oracle.constants(cam, frame=f)
+        c.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+        c.secondary_rays(as_capi(scn, capi.SecondaryConstants), 2, 2, capi.SECONDARY_ACCUMULATE if accumulate else 0)
+
+    a = fresh()
+    try:
+        for f in (1, 2, 3, 4):
+            frame(a, f, f > 1)
+            if f == 2:
+                dump = a.readback(capi.BUF_ACCUM).copy()
+        want = a.readback(capi.BUF_ACCUM).copy()
+    finally:
+        a.close()
+    b = fresh()
+    try:
+        with pytest.raises(capi.MinoteError):
+            b.accum_restore(dump)                      # size unknown before the first primary pass
+        pc, _ = oracle.constants(cam, frame=3)
+        b.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+        with pytest.raises(capi.MinoteError):
+            b.accum_restore(dump[:10])                 # wrong size
+        b.accum_restore(dump)
+        for f in (3, 4):
+            frame(b, f, True)
+        got = b.readback(capi.BUF_ACCUM)
+        assert np.array_equal(got, want, equal_nan=True) and np.all(got[..., 3] == 8.0)
+    finally:
+        b.close()
+
+
 def test_async_readback_matches_blocking(gpu_ctx, oracle, sky_inputs, blue_noise):
     """Pipelined framebuffer readback (double-buffered LDR): frame f's async copy equals its blocking readback even
     when frame f+1 has been issued in between."""
