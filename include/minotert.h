@@ -147,9 +147,9 @@ const char* mrt_last_error(const mrt_context* ctx);
  *   "count_visits" 0/1        count node visits and triangle tests (mrt_stats.node_visits / tri_tests)
  *   "trace_timing" 0/1        CUDA event pair around every bounce-wave traversal launch (default 1)
  *   "sort_rays" 0/1           sort every bounce wave's queue (see MRT_SECONDARY_SORT_RAYS; default 0)
- *   "primary_entry" 0/1       primary pass: the top of the BVH is walked once per 8x4-pixel tile against the tile's
- *                             frustum and every ray starts from the resulting entry list (default 1); 0: every ray
- *                             walks from the root.  Same G-buffer bit for bit.
+ *   "primary_entry" 0/1       primary pass: the top of the BVH is walked once per 32x16-pixel tile against the tile's
+ *                             frustum and every ray starts from the resulting entry list (1); default 0: every ray
+ *                             walks from the root (measured faster).  Same G-buffer bit for bit.
  *   "bands" 1..8              wavefront: the image's pixels are cut into that many ranges, each rendered on its own
  *                             stream, so that the drain of one band's traversal launch overlaps another band's
  *                             kernels.  Same image bit for bit.

@@ -35,7 +35,9 @@
 #pragma once
 #include "context.cuh"
 
-#define TRACE_BLOCK 128
+#ifndef TRACE_BLOCK
+#define TRACE_BLOCK 128  // threads per traversal CTA
+#endif
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 6   // resident CTAs per SM the register budget is capped for (80 regs/thread)
 #endif

@@ -361,7 +361,7 @@ def test_primary_entry_list_does_not_change_the_gbuffer(gpu_ctx, oracle):
                     o[k], d[k] = oo[:], dd[:]
                 ids_bf, t_bf = gpu_ctx.trace_rays(o, d, brute_force=True)
                 assert np.array_equal(out[1][0][ys, xs], ids_bf) and np.array_equal(out[1][1][ys, xs], t_bf)
-    gpu_ctx.set_option("primary_entry", 1)
+    gpu_ctx.set_option("primary_entry", 0)
 
 
 def test_checkpoint_resume_of_a_progressive_render(oracle, sky_inputs, blue_noise):
