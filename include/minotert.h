@@ -107,8 +107,8 @@ typedef enum {
 
 /* mrt_secondary_rays flags */
 #define MRT_SECONDARY_ACCUMULATE 1u /* add to MRT_BUF_ACCUM instead of restarting it */
-#define MRT_SECONDARY_SORT_RAYS 2u  /* reorder each bounce's ray queue before it is traced (image unchanged): stable
-                                     * binning by direction octant on top of the pixel order compaction leaves */
+#define MRT_SECONDARY_SORT_RAYS 2u  /* reorder each bounce's ray queue before it is traced (image unchanged) with the
+                                     * mode of option "sort_rays" (octant binning if that is 0) */
 
 typedef struct {
     uint64_t primary_rays;   /* rays traced by the last mrt_primary_rays */
@@ -146,7 +146,9 @@ const char* mrt_last_error(const mrt_context* ctx);
 /* Tuning / instrumentation switches (unknown names fail with MRT_ERR_INVALID):
  *   "count_visits" 0/1        count node visits and triangle tests (mrt_stats.node_visits / tri_tests)
  *   "trace_timing" 0/1        CUDA event pair around every bounce-wave traversal launch (default 1)
- *   "sort_rays" 0/1           sort every bounce wave's queue (see MRT_SECONDARY_SORT_RAYS; default 0)
+ *   "sort_rays" 0/1/2         reorder every bounce wave's queue before it is traced: 1 stable binning by direction
+ *                             octant, 2 radix sort by (Morton cell of the ray origin in a 128^3 grid, direction octant);
+ *                             default 0 (both measured slower than the pixel order compaction leaves).  Same image.
  *   "primary_entry" 0/1       primary pass: the top of the BVH is walked once per 32x16-pixel tile against the tile's
  *                             frustum and every ray starts from the resulting entry list (1); default 0: every ray
  *                             walks from the root (measured faster).  Same G-buffer bit for bit.

@@ -199,7 +199,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     MRT_ENTER(ctx);
     if (!name) return mrt_fail(ctx, MRT_ERR_INVALID, "option name is NULL");
     if (!strcmp(name, "count_visits")) ctx->opt_count_visits = value != 0;
-    else if (!strcmp(name, "sort_rays")) ctx->opt_sort_rays = value != 0;
+    else if (!strcmp(name, "sort_rays")) ctx->opt_sort_rays = (int)(value < 0 ? 0 : (value > 2 ? 2 : value));
     else if (!strcmp(name, "persistent_primary")) ctx->opt_persistent_primary = value != 0;
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;

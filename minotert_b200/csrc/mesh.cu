@@ -580,6 +580,40 @@ __global__ void __launch_bounds__(OB_THREADS) k_oct_scatter(const float4* __rest
     }
 }
 
+// ---- ray sort by (origin cell, direction octant) (row n5, sort mode 2) ----
+// key = 21-bit Morton code of the ray origin in a 128^3 grid over the root node's box, then the 3-bit direction octant:
+// rays of one cell stay together (the locality the octant-only binning destroys) and, inside a cell, rays that share the
+// near/far plane selection and the child visiting order.  Sorted with the 8-bit LSD radix sort of sort.cu (3 passes over
+// 24 bits); entries beyond the queue's size get the key ~0 and end up last.  Only the 4-byte permutation moves.
+MRT_D uint32_t spread7(uint32_t v) {  // 7 bits -> every third bit
+    v &= 0x7Fu;
+    v = (v | (v << 8)) & 0x0000700Fu;
+    v = (v | (v << 4)) & 0x000430C3u;
+    v = (v | (v << 2)) & 0x00049249u;
+    return v;
+}
+__global__ void __launch_bounds__(256) k_ray_keys(const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                  const uint32_t* __restrict__ count_ptr, BvhDev bvh, uint32_t n,
+                                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint64_t key = ~0ull;
+    if (k < *count_ptr && bvh.num_nodes) {
+        const uint4 n0 = __ldg(reinterpret_cast<const uint4*>(bvh.nodes));  // root: grid origin + per-axis step exponents
+        const float3 lo = f3(__uint_as_float(n0.x), __uint_as_float(n0.y), __uint_as_float(n0.z));
+        const float3 ext = f3(255.0f * __uint_as_float((n0.w & 0xFFu) << 23), 255.0f * __uint_as_float((n0.w & 0xFF00u) << 15),
+                              255.0f * __uint_as_float((n0.w & 0xFF0000u) << 7));
+        const float4 o = __ldg(&ray_o[k]);
+        const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - lo.x) / ext.x * 128.0f, 0.0f), 127.0f),
+                       cy = (uint32_t)fminf(fmaxf((o.y - lo.y) / ext.y * 128.0f, 0.0f), 127.0f),
+                       cz = (uint32_t)fminf(fmaxf((o.z - lo.z) / ext.z * 128.0f, 0.0f), 127.0f);
+        const uint32_t cell = spread7(cx) | (spread7(cy) << 1) | (spread7(cz) << 2);
+        key = ((uint64_t)cell << 3) | ray_octant(__ldg(&ray_d[k]));
+    }
+    keys[k] = key;
+    vals[k] = k;
+}
+
 // ---- closest-hit query for mrt_trace_rays ----
 struct QueryJob {
     const float* ro;
@@ -1141,7 +1175,10 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     }
     const uint32_t waves = spp * bounces;
     const bool fused = ctx->opt_fused_shade != 0;
-    const bool sort = ctx->opt_sort_rays || (flags & MRT_SECONDARY_SORT_RAYS);
+    // sort mode: 0 none, 1 direction octant (binning), 2 (origin cell, octant) (radix sort); the flag asks for the configured
+    // mode, or the octant binning when none is configured
+    const int sort_mode = ctx->opt_sort_rays ? ctx->opt_sort_rays : ((flags & MRT_SECONDARY_SORT_RAYS) ? 1 : 0);
+    const bool sort = sort_mode != 0;
     // Bands: the image's pixels are cut into contiguous ranges, each with its own queues, counters and STREAM.  The last
     // quarter of every persistent traversal launch is the drain of its longest rays (latency-bound, ~100 us whatever the
     // wave's size); with several bands in flight the drain of one band's launch is filled by another band's kernels --
@@ -1240,7 +1277,18 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
                     ctx->trace_ev.push_back(e);
                 }
                 if (timed) cudaEventRecord(ctx->trace_ev[2 * ctx->trace_ev_used], st);
-                if (sort) {
+                const uint32_t* order = nullptr;
+                if (sort_mode == 2) {
+                    MRT_TRY(dev_reserve(ctx, ctx->sort_keys, bpix));
+                    MRT_TRY(dev_reserve(ctx, ctx->sort_keys_alt, bpix));
+                    MRT_TRY(dev_reserve(ctx, ctx->sort_vals, bpix));
+                    MRT_TRY(dev_reserve(ctx, ctx->sort_vals_alt, bpix));
+                    k_ray_keys<<<div_up(bpix, 256), 256, 0, st>>>(ray_o[q], ray_d[q], in_count, sa.bvh, bpix, ctx->sort_keys.p, ctx->sort_vals.p);
+                    MRT_LAUNCHED(ctx);
+                    bool in_alt = false;
+                    MRT_TRY(radix_sort_pairs_u64(ctx, ctx->sort_keys.p, ctx->sort_keys_alt.p, ctx->sort_vals.p, ctx->sort_vals_alt.p, bpix, 0, 24, &in_alt));
+                    order = in_alt ? ctx->sort_vals_alt.p : ctx->sort_vals.p;
+                } else if (sort) {
                     const uint32_t tiles = div_up(npix, OB_TILE);
                     MRT_TRY(dev_reserve(ctx, ctx->sort_vals, npix));
                     MRT_TRY(dev_reserve(ctx, ctx->sort_vals_alt, 8 * (size_t)tiles));
@@ -1249,8 +1297,9 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
                     MRT_TRY(scan_exclusive_u32(ctx, ctx->sort_vals_alt.p, ctx->sort_vals_alt.p, 8 * (size_t)tiles));
                     k_oct_scatter<<<tiles, OB_THREADS, 0, st>>>(ray_d[q], in_count, ctx->sort_vals_alt.p, tiles, ctx->sort_vals.p);
                     MRT_LAUNCHED(ctx);
+                    order = ctx->sort_vals.p;
                 }
-                QueueJob J{ray_o[q], ray_d[q], in_count, sa.hits, sort ? ctx->sort_vals.p : nullptr};
+                QueueJob J{ray_o[q], ray_d[q], in_count, sa.hits, order};
                 const unsigned long long extra = wave == 0 ? (unsigned long long)bpix : 0ull;
                 // the shade stage of this wave: vertex b of the paths; the last vertex emits nothing (its counter slot stays 0)
                 P.vertex = b;

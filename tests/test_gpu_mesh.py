@@ -185,8 +185,9 @@ def test_render_260k_config2_reduced_resolution(gpu_ctx, oracle, sky_inputs, blu
 
 
 def test_ray_sort_does_not_change_the_image(gpu_ctx, oracle, sky_inputs, blue_noise):
-    """Row n5: binning the bounce queues by direction octant reorders work only; every pixel owns its path, so the
-    accumulator must be bit-identical with and without the sort stage."""
+    """Row n5: reordering the bounce queues -- mode 1 binning by direction octant, mode 2 radix sort by (Morton cell of
+    the ray origin, direction octant) -- reorders work only; every pixel owns its path, so the accumulator must be
+    bit-identical with and without the sort stage."""
     atmo = sky_inputs[0]
     pos, idx, alb, view = scenes.small_terrain()
     w, h = 192, 128
@@ -198,13 +199,13 @@ def test_ray_sort_does_not_change_the_image(gpu_ctx, oracle, sky_inputs, blue_no
     gpu_ctx.build()
     gpu_ctx.set_option("path_kernel", 0)   # the sort stage sits between the waves of the wavefront
     out = []
-    for sort in (0, 1):
+    for sort in (0, 1, 2):
         gpu_ctx.set_option("sort_rays", sort)
         gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
         gpu_ctx.secondary_rays(as_capi(scn, capi.SecondaryConstants), 3, 3)
         out.append((gpu_ctx.readback(capi.BUF_ACCUM).copy(), int(gpu_ctx.stats().secondary_rays)))
-    assert out[0][1] == out[1][1] and out[0][1] > 0
-    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1] == out[1][1] == out[2][1] and out[0][1] > 0
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][0], out[2][0])
     # the flag on the call does the same as the option
     gpu_ctx.set_option("sort_rays", 0)
     gpu_ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
