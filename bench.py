@@ -47,7 +47,7 @@ WORKLOADS = {
     "tiles_4k_progressive": ("scene_10m", 3840, 2160, 8, 3), # configs[3]: one displayed frame of the 64-spp accumulation
     "spheres_960x540": (None, 960, 540, 8, 8),               # the reference's own frame (scene.glsl, main.cpp:24)
 }
-EXTRA_CONFIGS = ["scene_1m_1080p", "scene_10m_4k", "cornell_512", "spheres_960x540", "tiles_4k_progressive"]
+EXTRA_CONFIGS = ["scene_1m_1080p", "scene_10m_4k", "tiles_4k_progressive", "cornell_512", "spheres_960x540"]
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 AMD = (16.0, 2.0, 1.0, 0.18, 0.18)
 METRIC = "Mrays/s (primary+secondary)"
