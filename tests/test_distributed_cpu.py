@@ -74,3 +74,51 @@ def test_partition_rows_cover_image():
         assert np.array_equal(np.sort(rows), np.arange(2160))
     with pytest.raises(ValueError):
         D.partition_rows(3, 2, 8, 64)
+
+
+def _uid_worker(rank, world, port, q):
+    """The plumbing bench.py --gpus N uses around mrt_group_create_rank: rank 0 makes the ncclUniqueId through the
+    C ABI, the bytes travel by torch.distributed (gloo here, NCCL on the GPU box), every rank ends up with the same
+    128 bytes and with complementary row tables.  (mrt_group_create_rank itself needs a GPU per rank.)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from minotert_b200 import capi
+        from minotert_b200 import distributed as D
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.Group.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        rows = D.partition_rows(rank, world, 8, 2160)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (bytes(uid.numpy().tobytes()), rows.tolist()))
+        ok = all(g[0] == gathered[0][0] for g in gathered) and any(b != 0 for b in gathered[0][0])
+        allrows = np.sort(np.concatenate([np.array(g[1]) for g in gathered]))
+        ok &= bool(np.array_equal(allrows, np.arange(2160)))
+        # without a CUDA device the group cannot be made: it must fail loudly, not fall back
+        try:
+            capi.Group.rank_of(0, rank, world, gathered[0][0])
+            ok &= torch.cuda.is_available()
+        except capi.MinoteError as e:
+            ok &= "no CPU fallback" in str(e) or "CUDA" in str(e)
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_group_unique_id_plumbing_gloo():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_group.py")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_uid_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in results), results
