@@ -845,33 +845,39 @@ k_trace_shade(QueueJob job, BvhDev bvh, uint32_t* work_counter, unsigned long lo
 // The wavefront above pays, per bounce wave, a traversal launch whose last quarter is the drain of its longest rays
 // (~100 us, bounded by ray latency, not by work), a shade launch, and ~130 B/ray of queue / hit / path-state traffic.
 // With 4-8 spp x 2-3 bounces that is 12-24 drains per frame, and on a 1/8-image slab (tile mode on 8 GPUs) the drains
-// ARE the frame.  Here a lane owns a PIXEL for all its samples and bounces -- the reference's RNG chain forces the
-// samples of a pixel to run in sequence anyway (secondaryRays.comp:124-132) -- so the path state lives in registers /
-// shared memory, nothing is queued, and the only drain is the one at the end of the frame.  The warp-synchronous state
-// machine of trace_persistent() gains one step kind:
-//     shade : lanes whose ray has finished (or that just took a pixel) resolve the path vertex -- sky on a miss,
-//             albedo + blue-noise-rotated Lambert bounce on a hit -- and either start the next ray, the next sample,
-//             or write the pixel's accumulator and go idle; runs once PATH_SHADE_MIN lanes want it.
+// ARE the frame (tools/bench_slab.py: 62 % render efficiency at 1/8).  Here a lane owns PIXELS for all their samples and
+// bounces -- the reference's RNG chain forces the samples of a pixel to run in sequence anyway
+// (secondaryRays.comp:124-132) -- nothing is queued in global memory and the only drain is the one at the end of the frame.
+// A first version gave each lane one pixel: a lane whose ray had finished waited for a shade step, shade steps ran with
+// 8-16 of 32 lanes and both branches (sky / bounce), and the kernel was 25 % slower than the wavefront.  Now each lane
+// owns TWO path slots in shared memory; while one path waits to be shaded the lane traverses the other's ray, so
+// shade steps can wait until 3/4 of the warp wants one.  The warp-synchronous state machine of trace_persistent() has two
+// more step kinds:
+//     refill : idle lanes start the ray a shaded slot holds ready; lanes with an empty slot take the next pixel;
+//     shade  : lanes with a slot whose ray has finished (or that just took a pixel) resolve the path vertex -- sky on a
+//              miss, albedo + blue-noise-rotated Lambert bounce on a hit -- and leave the next ray in the slot, start the
+//              next sample, or finish the pixel.
 // Per pixel the arithmetic and its order are exactly those of the wavefront (k_shade / shade_vertex), so the two
 // produce bit-identical images (tested).
 #ifndef PATH_SHADE_MIN
-#define PATH_SHADE_MIN 8
+#define PATH_SHADE_MIN 24
 #endif
 #ifndef PATH_MIN_BLOCKS
 #define PATH_MIN_BLOCKS TRACE_MIN_BLOCKS
 #endif
-enum { COLD_DX = 0, COLD_DY, COLD_DZ, COLD_TX, COLD_TY, COLD_TZ, COLD_AX, COLD_AY, COLD_AZ, COLD_AW, COLD_RX, COLD_RY, COLD_COUNT };
+enum { SL_PX = 0, SL_PY, SL_PZ, SL_DX, SL_DY, SL_DZ, SL_TX, SL_TY, SL_TZ, SL_TRI, SL_PIXEL, SL_RNG, SL_SV, SL_STATE, SL_COUNT };
+enum { SLOT_EMPTY = 0, SLOT_SHADE = 1, SLOT_READY = 2, SLOT_ACTIVE = 3 };
 
 __global__ void __launch_bounds__(TRACE_BLOCK, PATH_MIN_BLOCKS)
 k_path(ShadeArgs a, uint32_t* work_counter, unsigned long long* counters, int count_visits, unsigned long long* total_rays) {
     __shared__ TraceShared S;
-    __shared__ float cold[COLD_COUNT][TRACE_BLOCK];  // per-lane path state that the traversal steps never touch
+    __shared__ uint32_t slots[2][SL_COUNT][TRACE_BLOCK];  // two path slots per lane, column layout (conflict-free)
     trace_shared_init(S);
     const ShadeParams& P = a.P;
     const BvhDev& bvh = a.bvh;
     uint2* const sm = &S.stack[0][threadIdx.x];
-    float* const cd = &cold[0][threadIdx.x];
-#define COLD(k) cd[(k) * TRACE_BLOCK]
+#define SLU(s, k) slots[s][k][threadIdx.x]
+#define SLF(s, k) (reinterpret_cast<float(*)[SL_COUNT][TRACE_BLOCK]>(slots))[s][k][threadIdx.x]
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t total = a.npix;
@@ -883,63 +889,94 @@ k_path(ShadeArgs a, uint32_t* work_counter, unsigned long long* counters, int co
     L.sp = 0;
     L.o = f3s(0.0f);
     L.hit.t = 0.0f; L.hit.tri = L.hit.prim = MRT_MISS_ID;
-    bool have_path = false, need_shade = false;
-    uint32_t pixel = 0, rng = 0, sv = 0;  // sv = sample << 16 | path vertex
+    SLU(0, SL_STATE) = SLOT_EMPTY;
+    SLU(1, SL_STATE) = SLOT_EMPTY;
+    int cur = -1;  // slot whose ray this lane is traversing
     unsigned nrays = 0;
     uint32_t pool_next = 0, pool_end = 0;
     bool exhausted = false;
 
     for (;;) {
-        // ---- idle lanes take the next pixels of the warp's chunk
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have_path);
-        if (idle && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= TRACE_REFILL_MIN)) {
-            if (pool_next >= pool_end) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(work_counter, (uint32_t)TRACE_CHUNK);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                pool_next = base;
-                pool_end = min(base + (uint32_t)TRACE_CHUNK, total);
-                if (base >= total) { exhausted = true; pool_next = pool_end = 0; }
-            }
-            if (!exhausted) {
-                const uint32_t mine = pool_next + __popc(idle & lt_mask);
-                if (!have_path && mine < pool_end) {
-                    pixel = mine;
-                    have_path = need_shade = true;
-                    sv = 0;
-                    rng = P.seed;
-                    float4 acc = P.accumulate ? a.accum[pixel] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    COLD(COLD_AX) = acc.x; COLD(COLD_AY) = acc.y; COLD(COLD_AZ) = acc.z; COLD(COLD_AW) = acc.w + (float)P.spp;
-                    const uint32_t lr = pixel / P.W, x = pixel - lr * P.W;
-                    const float2 rot = blue_noise_rotation(a.bn, P.bnW, P.bnH, x, partition_local_to_y(P.part, lr));
-                    COLD(COLD_RX) = rot.x; COLD(COLD_RY) = rot.y;
-                    L.ng.y = 0u; L.tg.y = 0u; L.tg2.y = 0u; L.sp = 0;
-                }
-                pool_next = min(pool_next + (uint32_t)__popc(idle), pool_end);
-            }
-        }
-        if (exhausted && __ballot_sync(0xFFFFFFFFu, have_path) == 0u) break;
-
-        // ---- lanes whose traversal has no pending work: pop, or hand the finished ray to the shade step
-        if (have_path && !need_shade && !(L.ng.y & 0xFF000000u) && !(L.tg.y && L.tg2.y)) {
+        // ---- traversal bookkeeping: pop, or park the finished ray in its slot for the shade step
+        if (cur >= 0 && !(L.ng.y & 0xFF000000u) && !(L.tg.y && L.tg2.y)) {
             if (L.sp == 0) {
-                if (!(L.tg.y | L.tg2.y)) need_shade = true;
+                if (!(L.tg.y | L.tg2.y)) {
+                    if (L.hit.tri != MRT_MISS_ID) {
+                        const float3 d = f3(SLF(cur, SL_DX), SLF(cur, SL_DY), SLF(cur, SL_DZ));
+                        const float3 pos = L.o + d * L.hit.t;
+                        SLF(cur, SL_PX) = pos.x; SLF(cur, SL_PY) = pos.y; SLF(cur, SL_PZ) = pos.z;
+                    }
+                    SLU(cur, SL_TRI) = L.hit.tri;
+                    SLU(cur, SL_STATE) = SLOT_SHADE;
+                    cur = -1;
+                }
             } else {
                 L.sp--;
                 L.ng = L.sp < TRACE_SM_STACK ? sm[L.sp * TRACE_BLOCK] : spill[L.sp - TRACE_SM_STACK];
             }
         }
-        const bool tracing = have_path && !need_shade;
+        const uint32_t st0 = SLU(0, SL_STATE), st1 = SLU(1, SL_STATE);
+        const bool has_ready = st0 == SLOT_READY || st1 == SLOT_READY;
+        const bool has_empty = st0 == SLOT_EMPTY || st1 == SLOT_EMPTY;
+        const bool has_shade = st0 == SLOT_SHADE || st1 == SLOT_SHADE;
+        const bool tracing = cur >= 0;
         const bool want_tri = tracing && (L.tg.y | L.tg2.y) != 0u;
         const bool want_node = tracing && !(L.tg.y && L.tg2.y) && (L.ng.y & 0xFF000000u);
-        const unsigned smask = __ballot_sync(0xFFFFFFFFu, need_shade);
         const unsigned tmask = __ballot_sync(0xFFFFFFFFu, want_tri);
         const unsigned nmask = __ballot_sync(0xFFFFFFFFu, want_node);
+        const unsigned smask = __ballot_sync(0xFFFFFFFFu, has_shade);
+        const unsigned amask = __ballot_sync(0xFFFFFFFFu, !tracing && has_ready);                 // lanes that could start a ray
+        const unsigned pmask = __ballot_sync(0xFFFFFFFFu, has_empty && !exhausted);               // lanes that could take a pixel
+        const unsigned busy = __ballot_sync(0xFFFFFFFFu, tracing || st0 != SLOT_EMPTY || st1 != SLOT_EMPTY);
+        if (exhausted && busy == 0u) break;
+        const bool no_trace_work = (tmask | nmask) == 0u;
+        const unsigned idle_fillable = amask | (pmask & __ballot_sync(0xFFFFFFFFu, !tracing));
         const int tri_min = exhausted ? min(TRACE_TRI_MIN, max(1, (__popc(tmask | nmask) + TRACE_DRAIN_TRI - 1) / TRACE_DRAIN_TRI)) : TRACE_TRI_MIN;
-        const int shade_min = exhausted ? min(PATH_SHADE_MIN, max(1, (__popc(smask | tmask | nmask) + 2) / 3)) : PATH_SHADE_MIN;
-        if (smask && ((tmask | nmask) == 0u || __popc(smask) >= shade_min)) {
-            if (need_shade) {
-                float3 thr = f3(COLD(COLD_TX), COLD(COLD_TY), COLD(COLD_TZ));
+        const int shade_min = exhausted ? min(PATH_SHADE_MIN, max(1, (__popc(busy) * 3 + 3) / 4)) : PATH_SHADE_MIN;
+
+        if (idle_fillable && (__popc(idle_fillable) >= TRACE_REFILL_MIN || no_trace_work)) {
+            // ---- refill step: new pixels into empty slots (every lane that has one), then idle lanes start a ready ray
+            if (pmask) {
+                if (pool_next >= pool_end) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(work_counter, (uint32_t)TRACE_CHUNK);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    pool_next = base;
+                    pool_end = min(base + (uint32_t)TRACE_CHUNK, total);
+                    if (base >= total) { exhausted = true; pool_next = pool_end = 0; }
+                }
+                if (!exhausted) {
+                    const uint32_t mine = pool_next + __popc(pmask & lt_mask);
+                    if ((pmask >> lane) & 1u) {
+                        if (mine < pool_end) {
+                            const int s = st0 == SLOT_EMPTY ? 0 : 1;
+                            SLU(s, SL_PIXEL) = mine;
+                            SLU(s, SL_RNG) = P.seed;
+                            SLU(s, SL_SV) = 0u;
+                            SLU(s, SL_STATE) = SLOT_SHADE;
+                            float4 acc = P.accumulate ? a.accum[mine] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            acc.w += (float)P.spp;
+                            a.accum[mine] = acc;
+                        }
+                    }
+                    pool_next = min(pool_next + (uint32_t)__popc(pmask), pool_end);
+                }
+            }
+            if (!tracing && has_ready) {
+                const int s = st0 == SLOT_READY ? 0 : 1;
+                lane_begin(L, f3(SLF(s, SL_PX), SLF(s, SL_PY), SLF(s, SL_PZ)), f3(SLF(s, SL_DX), SLF(s, SL_DY), SLF(s, SL_DZ)));
+                if (bvh.num_nodes == 0) L.ng.y = 0u;
+                SLU(s, SL_STATE) = SLOT_ACTIVE;
+                cur = s;
+                nrays++;
+            }
+        } else if (smask && (__popc(smask) >= shade_min || no_trace_work)) {
+            // ---- shade step: one slot per lane
+            if (has_shade) {
+                const int s = st0 == SLOT_SHADE ? 0 : 1;
+                const uint32_t pixel = SLU(s, SL_PIXEL);
+                uint32_t rng = SLU(s, SL_RNG), sv = SLU(s, SL_SV);
+                float3 thr = f3(SLF(s, SL_TX), SLF(s, SL_TY), SLF(s, SL_TZ));
                 for (;;) {
                     const uint32_t vertex = sv & 0xFFFFu;
                     float3 pos, n;
@@ -951,10 +988,11 @@ k_path(ShadeArgs a, uint32_t* work_counter, unsigned long long* counters, int co
                         prim = __float_as_uint(hp.w);
                         thr = f3s(1.0f);
                     } else {
-                        const float3 d = f3(COLD(COLD_DX), COLD(COLD_DY), COLD(COLD_DZ));
-                        if (L.hit.tri != MRT_MISS_ID) {
-                            pos = L.o + d * L.hit.t;
-                            n = tri_facing_normal(bvh, L.hit.tri, d, &prim);
+                        const float3 d = f3(SLF(s, SL_DX), SLF(s, SL_DY), SLF(s, SL_DZ));
+                        const uint32_t tri = SLU(s, SL_TRI);
+                        if (tri != MRT_MISS_ID) {
+                            pos = f3(SLF(s, SL_PX), SLF(s, SL_PY), SLF(s, SL_PZ));
+                            n = tri_facing_normal(bvh, tri, d, &prim);
                         } else {
                             prim = MRT_MISS_ID;
                             pos = f3s(0.0f);
@@ -964,31 +1002,33 @@ k_path(ShadeArgs a, uint32_t* work_counter, unsigned long long* counters, int co
                     bool sample_done;
                     if (prim == MRT_MISS_ID) {  // secondaryRays.comp:96: the path ends in the sky
                         const float3 c = thr * sky_color(a.A, a.luts, P.cameraPos, n);
-                        COLD(COLD_AX) += c.x; COLD(COLD_AY) += c.y; COLD(COLD_AZ) += c.z;
+                        const float4 acc = a.accum[pixel];
+                        a.accum[pixel] = make_float4(acc.x + c.x, acc.y + c.y, acc.z + c.z, acc.w);
                         sample_done = true;
                     } else {
                         const float4 al = __ldg(&a.albedo[prim]);
                         thr = thr * f3(al.x, al.y, al.z);  // secondaryRays.comp:94
                         sample_done = vertex >= P.bounces;  // the energy of a path that is still on a surface is dropped (:99)
                         if (!sample_done) {
+                            const uint32_t lr = pixel / P.W, x = pixel - lr * P.W;
+                            const float2 rot = blue_noise_rotation(a.bn, P.bnW, P.bnH, x, partition_local_to_y(P.part, lr));
                             float3 ro, rd;
-                            lambert_bounce(pos, n, rng, COLD(COLD_RX), COLD(COLD_RY), ro, rd);
-                            lane_begin(L, ro, rd);
-                            if (bvh.num_nodes == 0) L.ng.y = 0u;
-                            COLD(COLD_DX) = rd.x; COLD(COLD_DY) = rd.y; COLD(COLD_DZ) = rd.z;
+                            lambert_bounce(pos, n, rng, rot.x, rot.y, ro, rd);
+                            SLF(s, SL_PX) = ro.x; SLF(s, SL_PY) = ro.y; SLF(s, SL_PZ) = ro.z;
+                            SLF(s, SL_DX) = rd.x; SLF(s, SL_DY) = rd.y; SLF(s, SL_DZ) = rd.z;
                             sv++;
-                            nrays++;
-                            need_shade = false;
+                            SLU(s, SL_STATE) = SLOT_READY;
                             break;
                         }
                     }
                     const uint32_t sample = (sv >> 16) + 1u;
                     if (sample < P.spp) { sv = sample << 16; continue; }  // next sample: vertex 0 again, same RNG stream
-                    a.accum[pixel] = make_float4(COLD(COLD_AX), COLD(COLD_AY), COLD(COLD_AZ), COLD(COLD_AW));
-                    have_path = need_shade = false;
+                    SLU(s, SL_STATE) = SLOT_EMPTY;
                     break;
                 }
-                COLD(COLD_TX) = thr.x; COLD(COLD_TY) = thr.y; COLD(COLD_TZ) = thr.z;
+                SLU(s, SL_RNG) = rng;
+                SLU(s, SL_SV) = sv;
+                SLF(s, SL_TX) = thr.x; SLF(s, SL_TY) = thr.y; SLF(s, SL_TZ) = thr.z;
             }
         } else if (tmask && (nmask == 0u || __popc(tmask) >= tri_min)) {
             if (want_tri) {
@@ -1000,7 +1040,8 @@ k_path(ShadeArgs a, uint32_t* work_counter, unsigned long long* counters, int co
             if (want_node) lane_node_step<true>(L, bvh, S, spill, cnt);
         }
     }
-#undef COLD
+#undef SLU
+#undef SLF
     flush_counters(cnt, counters, count_visits != 0);
     // rays traced by this launch: counters[3]; running total (mrt_stats.total_rays) += primary pixels + rays
     unsigned long long r = nrays;

@@ -1,2 +1,5 @@
-for v in blk32 blk64; do for b in 1 2 4; do MINOTERT_LIB_DIR=variants/$v tools/ab.sh hall_${v}_b$b --no-extra-configs --opt bands=$b; done; MINOTERT_LIB_DIR=variants/$v tools/ab.sh hall_${v}_c0 --no-extra-configs --opt trace_ctas_per_sm=0; MINOTERT_LIB_DIR=variants/$v tools/ab.sh 1m_${v} --workload scene_1m_1080p; done
-python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "checkpoint or primary_entry" 2>&1 | tail -3
+timeout 300 python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "path_kernel or ray_sort" 2>&1 | tail -4
+for w in "hall" "1m --workload scene_1m_1080p" "10m --workload scene_10m_4k --steps 5"; do set -- $w; t=$1; shift; tools/ab.sh ${t}_pk1 --no-extra-configs "$@" --opt path_kernel=1; done
+for v in 16 28; do MINOTERT_LIB_DIR=variants/shade$v tools/ab.sh hall_pk1_s$v --no-extra-configs --opt path_kernel=1; done
+tools/ab.sh hall_sort2 --no-extra-configs --opt sort_rays=2
+timeout 600 python tools/bench_slab.py scene_10m 2>/dev/null
