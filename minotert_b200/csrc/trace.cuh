@@ -185,6 +185,29 @@ MRT_D float q_plane(unsigned w, unsigned K, unsigned sel) { return __uint_as_flo
 // planes with PRMT so that neither pipe carries all 48 decodes (ncu: ALU pipe 65 % busy, FMA 22 %).
 MRT_D float q_plane_half(unsigned w, unsigned K, unsigned sel) { return __uint_as_float(__dp4a(w, 128u << (8 * sel), K)); }
 
+#ifndef TRACE_FFMA2
+#define TRACE_FFMA2 1  // slab planes of two children per FFMA2 / FADD2 (packed fp32, sm_100)
+#endif
+MRT_D unsigned long long pack2(float x, float y) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+MRT_D float2 fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    float2 o;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+}
+MRT_D float2 add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    float2 o;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+}
+
 // Per-CTA shared memory of the traversal kernels: the lanes' stack columns and two bit-shuffle tables.
 struct TraceShared {
     uint2 stack[TRACE_SM_STACK][TRACE_BLOCK];
@@ -267,6 +290,39 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2
 
     const unsigned K = bvh.prmt_k;  // 0x47000000 from the kernel parameters (a constant-bank operand of PRMT)
     unsigned miss = 0u;  // after the loop: bit j set <=> child j missed
+#if TRACE_FFMA2
+    // Two children per instruction: Blackwell's packed fp32 pipe (FFMA2 / FADD2, PTX fma.rn.f32x2) evaluates the slab
+    // planes of children j and j-1 in one issue slot each -- the kernel is issue-bound (ncu: 70 % of the issue slots, FMA
+    // pipe 25 %), so halving the FMA and FADD instruction count of the node step is worth the register pairing.  Every
+    // component is the same IEEE fused multiply-add as the scalar code: results are bit-identical.
+    // near planes are evaluated NEGATED (slope and offset negated: fma(q, -s, -b) = -fma(q, s, b) exactly), so that
+    // -tmin = min of the three and the hit test's subtractions become packed additions
+    const unsigned long long sn2x = pack2(-snx2, -snx2), sn2y = pack2(-sny2, -sny2), sn2z = pack2(-snz2, -snz2);
+    const unsigned long long bn2x = pack2(-bnx, -bnx), bn2y = pack2(-bny, -bny), bn2z = pack2(-bnz, -bnz);
+    const unsigned long long sf2x = pack2(sfx, sfx), sf2y = pack2(sfy, sfy), sf2z = pack2(sfz, sfz);
+    const unsigned long long bf2x = pack2(bfx, bfx), bf2y = pack2(bfy, bfy), bf2z = pack2(bfz, bfz);
+    const unsigned long long tl2 = pack2(tlimit, tlimit);
+#pragma unroll
+    for (int j = 7; j >= 1; j -= 2) {
+        const unsigned wnx = j < 4 ? nx0 : nx1, wny = j < 4 ? ny0 : ny1, wnz = j < 4 ? nz0 : nz1;
+        const unsigned wfx = j < 4 ? fx0 : fx1, wfy = j < 4 ? fy0 : fy1, wfz = j < 4 ? fz0 : fz1;
+        const int a = j & 3, b = (j - 1) & 3;  // child j in the high half... (x = child j, y = child j-1)
+        float2 t0x = fma2(pack2(q_plane_half(wnx, K, a), q_plane_half(wnx, K, b)), sn2x, bn2x);
+        float2 t0y = fma2(pack2(q_plane_half(wny, K, a), q_plane_half(wny, K, b)), sn2y, bn2y);
+        float2 t0z = fma2(pack2(q_plane_half(wnz, K, a), q_plane_half(wnz, K, b)), sn2z, bn2z);
+        float2 t1x = fma2(pack2(q_plane(wfx, K, a), q_plane(wfx, K, b)), sf2x, bf2x);
+        float2 t1y = fma2(pack2(q_plane(wfy, K, a), q_plane(wfy, K, b)), sf2y, bf2y);
+        float2 t1z = fma2(pack2(q_plane(wfz, K, a), q_plane(wfz, K, b)), sf2z, bf2z);
+        const float ntminA = fminf(fminf(t0x.x, t0y.x), t0z.x), tmaxA = fminf(fminf(t1x.x, t1y.x), t1z.x);  // -tmin, tmax
+        const float ntminB = fminf(fminf(t0x.y, t0y.y), t0z.y), tmaxB = fminf(fminf(t1x.y, t1y.y), t1z.y);
+        const unsigned long long tmin2 = pack2(ntminA, ntminB);
+        const float2 d1 = add2(pack2(tmaxA, tmaxB), tmin2), d2 = add2(tl2, tmin2);  // tmax - tmin, tlimit - tmin
+        const unsigned negA = __float_as_uint(d1.x) | __float_as_uint(d2.x) | __float_as_uint(tmaxA);
+        const unsigned negB = __float_as_uint(d1.y) | __float_as_uint(d2.y) | __float_as_uint(tmaxB);
+        miss = __funnelshift_l(negA, miss, 1);
+        miss = __funnelshift_l(negB, miss, 1);
+    }
+#else
 #pragma unroll
     for (int j = 7; j >= 0; j--) {
         const unsigned wnx = j < 4 ? nx0 : nx1, wny = j < 4 ? ny0 : ny1, wnz = j < 4 ? nz0 : nz1;
@@ -287,6 +343,7 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2
         const unsigned neg = __float_as_uint(tmax - tmin) | __float_as_uint(tlimit - tmin) | __float_as_uint(tmax);
         miss = __funnelshift_l(neg, miss, 1);  // (miss << 1) | any sign set
     }
+#endif
     const unsigned imask = n0.w >> 24;
     const unsigned hit8 = ~miss & 0xFFu;
     // inner hits -> bit (slot ^ oct_inv); leaf hits -> 3 bits per slot, masked by the triangles that exist.
