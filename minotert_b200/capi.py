@@ -352,11 +352,12 @@ class Group:
     Group.rank_of(device, rank, nranks, uid)   one process per GPU, uid = Group.unique_id() made on rank 0
     """
 
-    def __init__(self, devices=None, transport="nccl", _handle=None):
+    def __init__(self, devices=None, transport="nccl", _handle=None, _device=None):
         self.L = load()
         self.h = C.c_void_p()
         if _handle is not None:
             self.h = _handle
+            devices = [_device]
         else:
             arr = (C.c_int * len(devices))(*devices)
             s = self.L.mrt_group_create(arr, len(devices), GROUP_P2P if transport == "p2p" else GROUP_NCCL, C.byref(self.h))
@@ -369,7 +370,7 @@ class Group:
         for i in range(self.nlocal):
             c, r = C.c_void_p(), C.c_uint32()
             self._ck(self.L.mrt_group_context(self.h, i, C.byref(c), C.byref(r)))
-            self.contexts.append(Context(_borrowed=c.value))
+            self.contexts.append(Context(device=devices[i], _borrowed=c.value))
             self.ranks.append(r.value)
 
     @staticmethod
@@ -389,7 +390,7 @@ class Group:
         s = L.mrt_group_create_rank(device, rank, nranks, buf, C.byref(h))
         if s != 0:
             raise MinoteError(f"mrt_group_create_rank failed ({s}): {L.mrt_group_last_error(None).decode()}")
-        return cls(_handle=h)
+        return cls(_handle=h, _device=device)
 
     def _ck(self, s):
         if s != 0:
