@@ -62,6 +62,9 @@
 #ifndef TRACE_PREFETCH
 #define TRACE_PREFETCH 0     // prefetch the next child node to L1 at the end of a node step (A/B measured)
 #endif
+#ifndef TRACE_DRAIN_PREFETCH
+#define TRACE_DRAIN_PREFETCH 0  // prefetch the next child node in the drain phase only (A/B measured: -1.5 %, off)
+#endif
 #ifndef TRACE_DRAIN_TRI
 #define TRACE_DRAIN_TRI 3    // drain phase: a triangle step runs once 1/n of the working lanes want one (measured 2..32: flat)
 #endif
@@ -247,7 +250,7 @@ MRT_D void trace_shared_init(TraceShared& S) {
 // One node step: take the nearest pending child of L.ng, fetch it, test its 8 children.
 // POSTPONE: the lane may arrive with untested triangles in L.tg; they move to the (free) postponed slot.
 template <bool POSTPONE>
-MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2* spill, TraceCounters& cnt) {
+MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2* spill, TraceCounters& cnt, bool prefetch = false) {
     uint2* const sm = &S.stack[0][threadIdx.x];
     if (POSTPONE && L.tg.y) { L.tg2 = L.tg; L.tg2mask = L.tgmask; }
     const unsigned bit = 31u - __clz(L.ng.y);
@@ -353,10 +356,11 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2
     L.ng = make_uint2(n1.x, (inner << 24) | imask);
     L.tg = make_uint2(n1.y, leaf & n1.z);
     L.tgmask = n1.z;
-#if TRACE_PREFETCH
-    // The child this lane visits next is already known: pull its 80 bytes towards L1 while the warp does its
-    // triangle step / loop bookkeeping (ncu: long_scoreboard is the top stall of the bounce waves).
-    if (inner) {
+    // The child this lane visits next is already known: pull its 80 bytes towards L1 while the warp does its triangle
+    // step / loop bookkeeping.  In the body of a launch this costs more issue slots than it hides latency (+5 %, the
+    // kernel is issue-bound there); in the DRAIN phase (queue exhausted, a few thin warps per SM, every step waits out
+    // the full L2 latency) it is the latency that counts: TRACE_DRAIN_PREFETCH passes prefetch = true then.
+    if ((TRACE_PREFETCH || prefetch) && inner) {
         const unsigned nbit = 31u - __clz(inner << 24);
         const unsigned nslot = (nbit - 24u) ^ L.oct_inv;
         const unsigned nrel = __popc(imask & ~(0xFFFFFFFFu << nslot));
@@ -364,7 +368,6 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 64));
     }
-#endif
 }
 
 // One triangle of the lane's pending group (POSTPONE: of the older group first).
@@ -485,7 +488,7 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
 #endif
             }
         } else if (nmask) {
-            if (want_node) lane_node_step<TRACE_POSTPONE != 0>(L, bvh, S, spill, cnt);
+            if (want_node) lane_node_step<TRACE_POSTPONE != 0>(L, bvh, S, spill, cnt, TRACE_DRAIN_PREFETCH && exhausted);
         }
     }
 }

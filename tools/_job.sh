@@ -1,2 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_mesh.py tests/test_gpu_sizes.py -m gpu -q -x -k "not 10m" 2>&1 | tail -4
-for w in "hall" "1m --workload scene_1m_1080p" "10m --workload scene_10m_4k --steps 5"; do set -- $w; t=$1; shift; tools/ab.sh ${t}_ffma2 --no-extra-configs "$@"; MINOTERT_LIB_DIR=variants/noffma2 tools/ab.sh ${t}_scalar --no-extra-configs "$@"; done
+set +e
+tools/profile.sh kernel lines_trace_hall "k_trace" 12 1
+tools/profile.sh kernel lines_primary_hall "k_mesh_primary" 3 1
+ls -la gpurun_out/*.ncu-rep

@@ -1,6 +1,5 @@
 N=$1
-nvidia-smi -L | head -8
-if [ "$N" = "2" ]; then timeout 600 python -m pytest tests/test_gpu_group.py -m gpu -q -x 2>&1 | tail -4; fi
+if [ "$N" = "2" ]; then timeout 600 python -m pytest tests/test_gpu_group.py -m gpu -q -x 2>&1 | tail -25; fi
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 16 --warmup 3 > gpurun_out/r2_scale_$N.json 2> gpurun_out/r2_scale_$N.err || tail -20 gpurun_out/r2_scale_$N.err
 python - $N <<'PY'
 import json, sys
