@@ -280,7 +280,9 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- GPU arm, one GPU: frames of a workload
 
-def roofline_block(wl, trace_rays, trace_ms, trace_launches, nodes_per_ray, tris_per_ray, step_ms, bvh_bytes, kernel):
+def roofline_block(wl, trace_rays, trace_ms, trace_launches, nodes_per_ray, tris_per_ray, step_ms, bvh_bytes, kernel, all_rays_visits=None):
+    """nodes_per_ray / tris_per_ray: visit counts of the rays THIS kernel traces (bounce rays; primary rays, traced by
+    k_mesh_primary, visit fewer nodes -- the average over all rays of a frame is reported beside it as *_all_rays)."""
     peak, peak_src = measured_peak()
     bytes_per_ray = 32 + 16 + 80.0 * nodes_per_ray + 48.0 * tris_per_ray
     achieved = (trace_rays * bytes_per_ray) / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
@@ -289,7 +291,8 @@ def roofline_block(wl, trace_rays, trace_ms, trace_launches, nodes_per_ray, tris
     avg_ms = trace_ms / max(1, trace_launches)
     out = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
            "traffic": traffic, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
-           "tris_per_ray": tris_per_ray, "launches": trace_launches, "avg_launch_ms": avg_ms,
+           "tris_per_ray": tris_per_ray, "nodes_per_ray_all_rays": (all_rays_visits or (None, None))[0],
+           "tris_per_ray_all_rays": (all_rays_visits or (None, None))[1], "launches": trace_launches, "avg_launch_ms": avg_ms,
            "share_of_step": trace_ms / max(step_ms, 1e-9),
            # what the kernel really moves through DRAM (ncu, cold caches, per launch) over its live launch time: the honest
            # memory-utilisation figure; and the issue-side counters that bound it on L2-resident scenes
@@ -362,12 +365,15 @@ def measure_frames(args, wl, steps, warmup, local, detail):
             ctx.set_option("trace_ctas_per_sm", 0)
 
         nodes_per_ray = tris_per_ray = 0.0
+        bounce_visits = (0.0, 0.0)
         if not spheres:  # per-ray visit counts for the algorithmic-bytes figure (untimed, counted pass)
             ctx.set_option("count_visits", 1)
             frame(ctx, 1)
             st = ctx.stats()
             nodes_per_ray = st.node_visits / max(1, st.primary_rays + st.secondary_rays)
             tris_per_ray = st.tri_tests / max(1, st.primary_rays + st.secondary_rays)
+            # the bounce-wave kernel's own rays (what its roofline is quoted on); primary rays visit fewer nodes
+            bounce_visits = (st.secondary_node_visits / max(1, st.secondary_rays), st.secondary_tri_tests / max(1, st.secondary_rays))
             ctx.set_option("count_visits", 0)
         for i in range(warmup):
             frame(ctx, i + 1)
@@ -496,8 +502,8 @@ def measure_frames(args, wl, steps, warmup, local, detail):
                                "traffic": ncu.get("dram_bytes_per_launch"), "issue_frac": ncu.get("issue_slot_utilisation"),
                                "note": "ALU/SFU-bound kernel: 8 samples x <= 9 vertices x 5 sphere tests in registers per pixel"}
         else:
-            out["roofline"] = roofline_block(wl, trace_rays, trace_ms, trace_launches, nodes_per_ray, tris_per_ray, dev_ms, build_stats.bvh_bytes,
-                                             "k_trace (secondary-ray BVH traversal, persistent warps)")
+            out["roofline"] = roofline_block(wl, trace_rays, trace_ms, trace_launches, bounce_visits[0], bounce_visits[1], dev_ms, build_stats.bvh_bytes,
+                                             "k_trace (secondary-ray BVH traversal, persistent warps)", (nodes_per_ray, tris_per_ray))
         return out
     finally:
         r.close()
@@ -554,6 +560,7 @@ def measure_tiles(args, steps, warmup, world, rank, local):
         st = ctx.stats()
         nodes_per_ray = st.node_visits / max(1, st.primary_rays + st.secondary_rays)
         tris_per_ray = st.tri_tests / max(1, st.primary_rays + st.secondary_rays)
+        bounce_visits = (st.secondary_node_visits / max(1, st.secondary_rays), st.secondary_tri_tests / max(1, st.secondary_rays))
         ctx.set_option("count_visits", 0)
         for i in range(warmup):
             frame(i, i == 0)
@@ -624,8 +631,9 @@ def measure_tiles(args, steps, warmup, world, rank, local):
                        "d2h_bytes_per_step": w * h * 4, "ms_per_step": e2e_ms / steps},
                "gpu_launches": int(launches_all), "clocks": clocks,
                "kernels": {"primary_ms_per_step": st.ms_primary, "secondary_ms_per_step": st.ms_secondary, "trace_ms_per_step": trace_ms / steps},
-               "roofline": roofline_block(wl, rays - npix_local * steps, trace_ms, trace_launches, nodes_per_ray, tris_per_ray, dev_ms,
-                                          build_stats.bvh_bytes, "k_trace (secondary-ray BVH traversal, persistent warps), rank 0's launches")}
+               "roofline": roofline_block(wl, rays - npix_local * steps, trace_ms, trace_launches, bounce_visits[0], bounce_visits[1], dev_ms,
+                                          build_stats.bvh_bytes, "k_trace (secondary-ray BVH traversal, persistent warps), rank 0's launches",
+                                          (nodes_per_ray, tris_per_ray))}
         return out
     finally:
         g.close()

@@ -133,6 +133,8 @@ typedef struct {
     float sah_tri_cost;       /* ... and triangle tests of a random ray that hits the root box */
     float ms_denoise;         /* device time of the last mrt_denoise_bilateral */
     float ms_temporal;        /* device time of the last mrt_temporal_accumulate */
+    uint64_t secondary_node_visits; /* the share of node_visits / tri_tests spent by the last mrt_secondary_rays   */
+    uint64_t secondary_tri_tests;   /*   (bounce rays only: what the roofline of the bounce-wave kernel is quoted on) */
 } mrt_stats;
 
 /* ---- lifetime ---- */

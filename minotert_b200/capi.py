@@ -55,7 +55,8 @@ class Stats(C.Structure):
                 ("stack_overflows", C.c_uint32), ("num_triangles", C.c_uint32), ("num_wide_nodes", C.c_uint32),
                 ("bvh_bytes", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
                 ("trace_launches", C.c_uint32), ("_reserved", C.c_uint32), ("total_rays", C.c_uint64), ("sah_node_cost", C.c_float), ("sah_tri_cost", C.c_float),
-                ("ms_denoise", C.c_float), ("ms_temporal", C.c_float)]
+                ("ms_denoise", C.c_float), ("ms_temporal", C.c_float),
+                ("secondary_node_visits", C.c_uint64), ("secondary_tri_tests", C.c_uint64)]
 
 
 EXPORTS = [

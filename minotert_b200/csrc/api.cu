@@ -201,6 +201,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "count_visits")) ctx->opt_count_visits = value != 0;
     else if (!strcmp(name, "sort_rays")) ctx->opt_sort_rays = (int)(value < 0 ? 0 : (value > 2 ? 2 : value));
     else if (!strcmp(name, "persistent_primary")) ctx->opt_persistent_primary = value != 0;
+    else if (!strcmp(name, "primary_batched")) ctx->opt_primary_batched = value != 0;
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;
     else if (!strcmp(name, "primary_entry")) ctx->opt_primary_entry = value != 0;
@@ -581,6 +582,8 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
         MRT_CUDA(ctx, cudaMemcpy(vc, ctx->visit_counters.p, sizeof vc, cudaMemcpyDeviceToHost));
         ctx->stats.node_visits = vc[0] + vc[4];
         ctx->stats.tri_tests = vc[1] + vc[5];
+        ctx->stats.secondary_node_visits = vc[4];
+        ctx->stats.secondary_tri_tests = vc[5];
         ctx->stats.stack_overflows = (uint32_t)(vc[2] + vc[6]);
     }
     if (ctx->total_rays.p) {

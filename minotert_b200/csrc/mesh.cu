@@ -397,6 +397,7 @@ MRT_D TraceHit trace_from_entries(const BvhDev& bvh, float3 o, float3 d, const E
 #ifndef PRIMARY_MIN_BLOCKS
 #define PRIMARY_MIN_BLOCKS 6  // register cap 85 (ptxas picks 80 instead of 72): measured best of 1, 4, 5, 6, 8, 9
 #endif
+template <bool BATCHED>
 __global__ void __launch_bounds__(TRACE_BLOCK, PRIMARY_MIN_BLOCKS)
 k_mesh_primary(PrimaryJob J, unsigned long long* counters, int count_visits) {
     __shared__ TraceShared S;
@@ -404,8 +405,12 @@ k_mesh_primary(PrimaryJob J, unsigned long long* counters, int count_visits) {
     // CTA = 4 warps = four 8x4 tiles side by side; ray index as in PrimaryJob::pixel
     const uint32_t i = blockIdx.x * TRACE_BLOCK + threadIdx.x;
     TraceCounters cnt{0, 0, 0};
-    float3 o, d;
-    if (i < J.count() && J.load(i, o, d)) {
+    float3 o = f3s(0.0f), d = f3(1.0f, 0.0f, 0.0f);
+    if (BATCHED) {  // option "primary_batched": warp-voted triangle steps (trace_coherent_batched)
+        const bool active = i < J.count() && J.load(i, o, d);
+        TraceHit h = trace_coherent_batched(J.bvh, active, o, d, S, cnt);
+        if (active) J.store_with_ray(i, h, o, d);
+    } else if (i < J.count() && J.load(i, o, d)) {
         TraceHit h = trace_coherent(J.bvh, o, d, S, cnt);
         J.store_with_ray(i, h, o, d);
     }
@@ -1159,9 +1164,12 @@ int mesh_primary(mrt_context* ctx) {
         k_mesh_primary_entry<<<big_x * big_y, TRACE_BLOCK, 0, ctx->stream>>>(J, big_x, ctx->visit_counters.p, ctx->opt_count_visits);
     }
 #endif
+    else if (ctx->opt_primary_batched)
+        k_mesh_primary<true><<<div_up((size_t)J.tiles * 32, TRACE_BLOCK), TRACE_BLOCK, 0, ctx->stream>>>(J, ctx->visit_counters.p,
+                                                                                                        ctx->opt_count_visits);
     else
-        k_mesh_primary<<<div_up((size_t)J.tiles * 32, TRACE_BLOCK), TRACE_BLOCK, 0, ctx->stream>>>(J, ctx->visit_counters.p,
-                                                                                                  ctx->opt_count_visits);
+        k_mesh_primary<false><<<div_up((size_t)J.tiles * 32, TRACE_BLOCK), TRACE_BLOCK, 0, ctx->stream>>>(J, ctx->visit_counters.p,
+                                                                                                         ctx->opt_count_visits);
     MRT_LAUNCHED(ctx);
     ctx->stats.primary_rays = ctx->npix;
     return mrt_check_cuda(ctx, cudaGetLastError(), "mesh_primary");

@@ -514,6 +514,48 @@ MRT_D TraceHit trace_coherent(const BvhDev& bvh, float3 o, float3 d, TraceShared
     return L.hit;
 }
 
+// Coherent rays through the warp-synchronous step machine, WITHOUT refill: the 32 rays of a tile stay together (that is
+// what makes them coherent), but a lane keeps its leaf triangles pending (one postponed group, as in trace_persistent)
+// until a share of the working lanes wants a triangle step.  In the per-lane loop above the triangle tests run right
+// after the node step that found them -- with ~10 of 32 lanes (ncu: 27 % of the primary pass' issue slots).
+// Must be called by all 32 lanes of the warp; `active` = this lane has a ray.
+#ifndef COHERENT_TRI_DIV
+#define COHERENT_TRI_DIV 2   // a triangle step runs once 1/n of the lanes still working want one
+#endif
+MRT_D TraceHit trace_coherent_batched(const BvhDev& bvh, bool active, float3 o, float3 d, TraceShared& S, TraceCounters& cnt) {
+    uint2* const sm = &S.stack[0][threadIdx.x];
+    uint2 spill[TRACE_LOCAL_STACK];
+    LaneState L;
+    lane_begin(L, o, d);
+    bool have_ray = active && bvh.num_nodes != 0;
+    for (;;) {
+        if (have_ray && !(L.ng.y & 0xFF000000u) && !(L.tg.y && L.tg2.y)) {
+            if (L.sp == 0) {
+                if (!(L.tg.y | L.tg2.y)) have_ray = false;
+            } else {
+                L.sp--;
+                L.ng = L.sp < TRACE_SM_STACK ? sm[L.sp * TRACE_BLOCK] : spill[L.sp - TRACE_SM_STACK];
+            }
+        }
+        const bool want_tri = have_ray && (L.tg.y | L.tg2.y) != 0u;
+        const bool want_node = have_ray && !(L.tg.y && L.tg2.y) && (L.ng.y & 0xFF000000u);
+        const unsigned tmask = __ballot_sync(0xFFFFFFFFu, want_tri);
+        const unsigned nmask = __ballot_sync(0xFFFFFFFFu, want_node);
+        if (!(tmask | nmask)) break;
+        const int tri_min = max(1, (__popc(tmask | nmask) + COHERENT_TRI_DIV - 1) / COHERENT_TRI_DIV);
+        if (tmask && (nmask == 0u || __popc(tmask) >= tri_min)) {
+            if (want_tri) {
+                lane_tri_step<true>(L, bvh, cnt);
+#pragma unroll 1
+                for (int k = 1; k < TRACE_TRI_PER_STEP && (L.tg.y | L.tg2.y); k++) lane_tri_step<true>(L, bvh, cnt);
+            }
+        } else {
+            if (want_node) lane_node_step<true>(L, bvh, S, spill, cnt);
+        }
+    }
+    return L.hit;
+}
+
 // geometric normal of a hit triangle, flipped to face the incoming ray (two-sided surfaces)
 MRT_D float3 tri_facing_normal(const BvhDev& bvh, uint32_t tri, float3 d, uint32_t* prim_out) {
     const float4* tp = bvh.tris + 3 * (size_t)tri;
