@@ -109,6 +109,11 @@ typedef enum {
 #define MRT_SECONDARY_ACCUMULATE 1u /* add to MRT_BUF_ACCUM instead of restarting it */
 #define MRT_SECONDARY_SORT_RAYS 2u  /* reorder each bounce's ray queue before it is traced (image unchanged) with the
                                      * mode of option "sort_rays" (octant binning if that is 0) */
+#define MRT_SECONDARY_FRAME_SUM 4u  /* triangle scenes: this call's samples are summed into the context's own per-frame
+                                     * buffer, starting from zero, and MRT_BUF_ACCUM is left alone; mrt_accum_commit
+                                     * then adds the frame to an accumulator.  Frames rendered by different contexts
+                                     * (frames in flight) and committed in frame order give the same bits as one
+                                     * context rendering them one after the other in this mode. */
 
 typedef struct {
     uint64_t primary_rays;   /* rays traced by the last mrt_primary_rays */
@@ -270,6 +275,12 @@ int mrt_trace_rays(mrt_context* ctx, const float* origins, const float* directio
  * mrt_primary_rays at the same size and partition -- and continue with MRT_SECONDARY_ACCUMULATE and the next frame
  * counter: the result is bit-identical to the uninterrupted render. */
 int mrt_accum_restore(mrt_context* ctx, const float* rgba32f, size_t bytes);
+/* Progressive accumulation with frames in flight: dst.MRT_BUF_ACCUM (+)= the frame src rendered with
+ * MRT_SECONDARY_FRAME_SUM (flags & MRT_SECONDARY_ACCUMULATE: add to dst's accumulator, else restart it with this
+ * frame).  dst may be src; otherwise both live on one device, dst takes src's image size and partition, the add runs on
+ * dst's stream behind src's render, and src's next render waits for it.  After the call dst can be tonemapped
+ * (source MRT_BUF_ACCUM) / read back / gathered like a context that rendered the frames itself. */
+int mrt_accum_commit(mrt_context* dst, mrt_context* src, uint32_t flags);
 
 /* ---- device-side unit probes (tests / tools): the per-path shading functions evaluated on the GPU ----
  * skyColor() of src/gpu/secondaryRays.comp:36-58 for n directions (directions, rgb_out: n x 3 floats) with the LUTs of
@@ -310,6 +321,15 @@ int mrt_group_set_tiles(mrt_group* g, uint32_t slab_rows);
  * (0 in tile mode: all ranks render the same frame; N in sample-set mode: disjoint seeds) */
 int mrt_group_render(mrt_group* g, uint32_t w, uint32_t h, const mrt_primary_constants* pc, const mrt_secondary_constants* sc,
                      uint32_t spp, uint32_t bounces, uint32_t flags, uint32_t frame_stride);
+/* Frames in flight for progressive tile mode (the reference keeps 3 frames in flight, renderer.ixx:36): every local
+ * rank gets `frames` (1..3) frame contexts on its device; mrt_group_render calls that carry MRT_SECONDARY_FRAME_SUM go
+ * round-robin over them and are committed (mrt_accum_commit) to the rank's context in call order, so consecutive
+ * frames overlap on the GPU -- the drain of one frame's traversal launches is filled by the next frame's kernels -- and
+ * the accumulated image is bit-identical for every `frames` and every number of ranks.  The caller prepares each
+ * frame context like the rank's own (blue noise, mrt_scene_share from the rank's context, atmosphere, sky view);
+ * partitions and traversal grid sizes are set by the group.  frames = 1 (default): the rank's context renders. */
+int mrt_group_set_frames_in_flight(mrt_group* g, uint32_t frames);
+int mrt_group_frame_context(mrt_group* g, uint32_t local_index, uint32_t slot, mrt_context** ctx_out);
 int mrt_group_tonemap(mrt_group* g, int mode, float exposure, const float* params, uint32_t nparams, int source);
 /* tile mode: every rank's slabs of a per-pixel buffer (MRT_BUF_LDR, _ACCUM, _VISIBILITY, ...) -> the full image in
  * row order on rank `root`.  Asynchronous (exchange streams); collective over all processes of the group. */
@@ -320,6 +340,10 @@ int mrt_group_reduce(mrt_group* g, uint32_t root);
  * blocking copy to host memory */
 int mrt_group_result(mrt_group* g, void** device_ptr, size_t* bytes, void** stream_out);
 int mrt_group_readback(mrt_group* g, void* host, size_t bytes);
+/* non-blocking variant for frames in flight: the copy into (pinned) host memory is queued behind the last gather;
+ * mrt_group_readback_wait returns once at most keep_in_flight queued copies are outstanding (0: all landed) */
+int mrt_group_readback_async(mrt_group* g, void* host, size_t bytes);
+int mrt_group_readback_wait(mrt_group* g, uint32_t keep_in_flight);
 int mrt_group_sync(mrt_group* g);
 
 #ifdef __cplusplus

@@ -19,7 +19,7 @@ MISS_ID = 0xFFFFFFFF
  BUF_MULTISCATTERING, BUF_SKY_VIEW, BUF_HIT_T, BUF_DENOISED, BUF_BVH_NODES, BUF_BVH_TRIS, BUF_TEMPORAL,
  BUF_TEMPORAL_COUNT) = range(16)
 BUILD_FULL, BUILD_REFIT = 0, 1
-SECONDARY_ACCUMULATE, SECONDARY_SORT_RAYS = 1, 2
+SECONDARY_ACCUMULATE, SECONDARY_SORT_RAYS, SECONDARY_FRAME_SUM = 1, 2, 4
 TEMPORAL_RESET = 1
 TONEMAP = {"linear": 0, "reinhard": 1, "hable": 2, "aces": 3, "uchimura": 4, "amd": 5}
 DENOISE = {"none": 0, "bilateral": 1}   # Renderer_impl::denoise modes (src/gfx/renderer.ixx:129-132)
@@ -66,7 +66,8 @@ EXPORTS = [
     "mrt_secondary_rays", "mrt_tonemap", "mrt_buffer", "mrt_readback", "mrt_sync", "mrt_stats_get",
     "mrt_stats_reset", "mrt_stream", "mrt_trace_rays", "mrt_partition_rows_for", "mrt_readback_async",
     "mrt_readback_wait", "mrt_denoise_bilateral", "mrt_scene_share", "mrt_temporal_accumulate",
-    "mrt_eval_sky_color", "mrt_eval_bounce_stream", "mrt_accum_restore",
+    "mrt_eval_sky_color", "mrt_eval_bounce_stream", "mrt_accum_restore", "mrt_accum_commit",
+    "mrt_group_set_frames_in_flight", "mrt_group_frame_context", "mrt_group_readback_async", "mrt_group_readback_wait",
     "mrt_group_create", "mrt_group_unique_id", "mrt_group_create_rank", "mrt_group_destroy", "mrt_group_last_error",
     "mrt_group_size", "mrt_group_context", "mrt_group_set_tiles", "mrt_group_render", "mrt_group_tonemap",
     "mrt_group_gather", "mrt_group_reduce", "mrt_group_result", "mrt_group_readback", "mrt_group_sync",
@@ -124,6 +125,11 @@ def load():
     L.mrt_trace_rays.argtypes = [vp, vp, vp, u32, vp, vp, C.c_int]
     L.mrt_partition_rows_for.argtypes = [u32, u32, u32, u32, vp, C.POINTER(u32)]
     L.mrt_accum_restore.argtypes = [vp, vp, C.c_size_t]
+    L.mrt_accum_commit.argtypes = [vp, vp, u32]
+    L.mrt_group_set_frames_in_flight.argtypes = [vp, u32]
+    L.mrt_group_frame_context.argtypes = [vp, u32, u32, C.POINTER(vp)]
+    L.mrt_group_readback_async.argtypes = [vp, vp, C.c_size_t]
+    L.mrt_group_readback_wait.argtypes = [vp, u32]
     L.mrt_eval_sky_color.argtypes = [vp, f32p, vp, u32, vp]
     L.mrt_eval_bounce_stream.argtypes = [vp, u32, u32, u32, f32p, f32p, u32, vp]
     L.mrt_group_create.argtypes = [C.POINTER(C.c_int), u32, C.c_int, C.POINTER(vp)]
@@ -325,6 +331,12 @@ class Context:
         self._ck(self.L.mrt_trace_rays(self.h, _ptr(o), _ptr(d), o.shape[0], _ptr(ids), _ptr(t), int(brute_force)))
         return ids, t
 
+    def accum_commit(self, src=None, flags=0):
+        """mrt_accum_commit: MRT_BUF_ACCUM (+)= the frame `src` (default: this context) rendered with SECONDARY_FRAME_SUM."""
+        self._ck(self.L.mrt_accum_commit(self.h, (src or self).h, flags))
+        if src is not None:
+            self.size = src.size
+
     def accum_restore(self, accum):
         """mrt_accum_restore: resume a progressive render from a dumped accumulator (readback(BUF_ACCUM))."""
         a = np.ascontiguousarray(accum, np.float32)
@@ -413,6 +425,21 @@ class Group:
     def set_tiles(self, slab_rows=8):
         self._ck(self.L.mrt_group_set_tiles(self.h, slab_rows))
 
+    def set_frames_in_flight(self, frames):
+        """mrt_group_set_frames_in_flight: renders that carry SECONDARY_FRAME_SUM go round-robin over `frames` frame
+        contexts per rank.  Returns them as [local rank][slot] (borrowed Context objects): the caller prepares each like the
+        rank's own context -- upload_blue_noise, share_scene(rank's context), atmosphere, sky_view."""
+        self._ck(self.L.mrt_group_set_frames_in_flight(self.h, frames))
+        self.frame_contexts = []
+        for i in range(self.nlocal):
+            slots = []
+            for k in range(frames):
+                c = C.c_void_p()
+                self._ck(self.L.mrt_group_frame_context(self.h, i, k, C.byref(c)))
+                slots.append(self.contexts[i] if frames == 1 else Context(device=self.contexts[i].device, _borrowed=c.value))
+            self.frame_contexts.append(slots)
+        return self.frame_contexts
+
     def render(self, w, h, pc, sc, spp, bounces, flags=0, frame_stride=0):
         self._ck(self.L.mrt_group_render(self.h, w, h, C.cast(C.byref(pc), C.c_void_p), C.cast(C.byref(sc), C.c_void_p),
                                          spp, bounces, flags, frame_stride))
@@ -448,6 +475,12 @@ class Group:
 
     def readback_into(self, host_ptr, nbytes):
         self._ck(self.L.mrt_group_readback(self.h, host_ptr, nbytes))
+
+    def readback_async(self, host_ptr, nbytes):
+        self._ck(self.L.mrt_group_readback_async(self.h, host_ptr, nbytes))
+
+    def readback_wait(self, keep_in_flight=0):
+        self._ck(self.L.mrt_group_readback_wait(self.h, keep_in_flight))
 
     def sync(self):
         self._ck(self.L.mrt_group_sync(self.h))

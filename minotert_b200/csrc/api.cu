@@ -170,7 +170,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->visibility); dev_free(ctx->depth); dev_free(ctx->normal); dev_free(ctx->motion); dev_free(ctx->color16);
     dev_free(ctx->denoised); dev_free(ctx->dn_taps);
     for (int k = 0; k < 2; k++) { dev_free(ctx->tp_rgba[k]); dev_free(ctx->tp_count[k]); dev_free(ctx->tp_vis[k]); }
-    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
+    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->frame_sum); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
     dev_free(ctx->hit0_pos); dev_free(ctx->hit0_n); dev_free(ctx->path_state);
     for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); }
     dev_free(ctx->hits); dev_free(ctx->queue_counts); dev_free(ctx->sort_keys); dev_free(ctx->sort_keys_alt);
@@ -188,6 +188,7 @@ void mrt_destroy(mrt_context* ctx) {
     if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
     if (ctx->sky_ready) cudaEventDestroy(ctx->sky_ready);
     if (ctx->ldr_ready) cudaEventDestroy(ctx->ldr_ready);
+    for (auto& ev : ctx->commit_ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->copy_done) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -418,18 +419,77 @@ int mrt_secondary_rays(mrt_context* ctx, const mrt_secondary_constants* c, uint3
     if (!ctx->have_gbuffer) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays before primary rays");
     if (!ctx->have_atmo || !ctx->have_view) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: sky LUTs missing (mrt_atmosphere, mrt_sky_view)");
     if (!ctx->bn) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: blue noise texture missing");
+    if ((flags & MRT_SECONDARY_FRAME_SUM) && ctx->scene_kind != 2)
+        return mrt_fail(ctx, MRT_ERR_INVALID, "secondary rays: MRT_SECONDARY_FRAME_SUM is for triangle scenes");
     sky_join(ctx);
     cudaEventRecord(ctx->ev[4], ctx->stream);
     int s = MRT_OK;
     if (ctx->npix) s = ctx->scene_kind == 1 ? spheres_secondary(ctx, c, spp, bounces, flags) : mesh_secondary(ctx, c, spp, bounces, flags);
     cudaEventRecord(ctx->ev[5], ctx->stream);
     if (s == MRT_OK) {
-        ctx->have_accum = true;
-        ctx->have_color = ctx->scene_kind == 1;
-        ctx->have_denoised = false;
+        if (flags & MRT_SECONDARY_FRAME_SUM) {
+            ctx->have_frame_sum = true;  // MRT_BUF_ACCUM is untouched until mrt_accum_commit
+        } else {
+            ctx->have_accum = true;
+            ctx->have_color = ctx->scene_kind == 1;
+            ctx->have_denoised = false;
+        }
+        ctx->secondary_done = true;
         ctx->stats.secondary_rays = ~0ull;  // resolved lazily in mrt_stats_get
     }
     return s;
+}
+
+namespace {
+// dst (+)= src, both float4 (xyz radiance sums, w samples); plain fp32 adds in a fixed order: frames committed in frame
+// order give the same bits whichever context rendered them
+__global__ void __launch_bounds__(256) k_accum_commit(float4* __restrict__ dst, const float4* __restrict__ src, size_t n, int accumulate) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 f = src[i];
+        float4 a = accumulate ? dst[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        dst[i] = make_float4(a.x + f.x, a.y + f.y, a.z + f.z, a.w + f.w);
+    }
+}
+}  // namespace
+
+int mrt_accum_commit(mrt_context* dst, mrt_context* src, uint32_t flags) {
+    MRT_ENTER(dst);
+    if (!src) return mrt_fail(dst, MRT_ERR_INVALID, "mrt_accum_commit: src is NULL");
+    if (src->poisoned) return mrt_fail(dst, MRT_ERR_CUDA, "mrt_accum_commit: the source context is poisoned: %s", src->err);
+    if (!src->have_frame_sum) return mrt_fail(dst, MRT_ERR_STATE, "mrt_accum_commit: the source holds no frame (render it with MRT_SECONDARY_FRAME_SUM)");
+    if (src->device != dst->device) return mrt_fail(dst, MRT_ERR_INVALID, "mrt_accum_commit: contexts of different devices (%d, %d)", dst->device, src->device);
+    if (flags & ~MRT_SECONDARY_ACCUMULATE) return mrt_fail(dst, MRT_ERR_INVALID, "mrt_accum_commit: unknown flags 0x%x", flags);
+    if (dst != src && (dst->W != src->W || dst->H != src->H || dst->local_rows != src->local_rows || dst->npix != src->npix ||
+                       dst->part.rank != src->part.rank || dst->part.nranks != src->part.nranks || dst->part.slab_rows != src->part.slab_rows)) {
+        // dst becomes a display context of src's image: same size and partition, nothing rendered yet
+        dst->part = src->part;
+        dst->W = src->W; dst->H = src->H; dst->local_rows = src->local_rows; dst->npix = src->npix;
+        dst->have_gbuffer = dst->have_accum = dst->have_color = dst->have_ldr = dst->have_denoised = dst->have_temporal = false;
+    }
+    const size_t n = src->npix;
+    MRT_TRY(dev_reserve(dst, dst->accum, n));
+    const int accumulate = ((flags & MRT_SECONDARY_ACCUMULATE) && dst->have_accum) ? 1 : 0;
+    if (dst != src) {
+        for (mrt_context* c : {dst, src})
+            for (int k = 0; k < 2; k++)
+                if (!c->commit_ev[k]) MRT_CUDA(dst, cudaEventCreateWithFlags(&c->commit_ev[k], cudaEventDisableTiming));
+        MRT_CUDA(dst, cudaEventRecord(src->commit_ev[0], src->stream));
+        MRT_CUDA(dst, cudaStreamWaitEvent(dst->stream, src->commit_ev[0], 0));
+    }
+    if (n) {
+        k_accum_commit<<<(unsigned)std::min<size_t>(div_up(n, 256), 148 * 16), 256, 0, dst->stream>>>(dst->accum.p, src->frame_sum.p, n, accumulate);
+        MRT_LAUNCHED(dst);
+        MRT_CUDA(dst, cudaGetLastError());
+    }
+    if (dst != src) {  // src may overwrite its frame buffer only after the add has read it
+        MRT_CUDA(dst, cudaEventRecord(src->commit_ev[1], dst->stream));
+        MRT_CUDA(dst, cudaStreamWaitEvent(src->stream, src->commit_ev[1], 0));
+    }
+    src->have_frame_sum = false;
+    dst->have_accum = true;
+    dst->have_color = false;
+    dst->have_denoised = false;
+    return MRT_OK;
 }
 
 int mrt_denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float threshold, float nearPlane, uint32_t frameCounter) {
@@ -549,12 +609,12 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
     float ms;
     if (ctx->have_atmo && cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->stats.ms_sky = ms;
     if (ctx->have_gbuffer && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.ms_primary = ms;
-    if (ctx->have_accum && cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->stats.ms_secondary = ms;
+    if (ctx->secondary_done && cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->stats.ms_secondary = ms;
     if (ctx->have_ldr && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->stats.ms_tonemap = ms;
     if (ctx->have_denoised && cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]) == cudaSuccess) ctx->stats.ms_denoise = ms;
     if (ctx->have_temporal && cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]) == cudaSuccess) ctx->stats.ms_temporal = ms;
     cudaGetLastError();
-    if (ctx->have_accum && ctx->stats.secondary_rays == ~0ull) {
+    if (ctx->secondary_done && ctx->stats.secondary_rays == ~0ull) {
         if (ctx->scene_kind == 1) {
             unsigned long long v = 0;
             MRT_CUDA(ctx, cudaMemcpy(&v, ctx->visit_counters.p + 4, sizeof v, cudaMemcpyDeviceToHost));
@@ -573,7 +633,7 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
     }
     ctx->stats.ms_trace = 0.0f;
     ctx->stats.trace_launches = ctx->scene_kind == 2 ? ctx->trace_ev_used : 0;
-    if (ctx->scene_kind == 2 && ctx->have_accum)
+    if (ctx->scene_kind == 2 && ctx->secondary_done)
         for (uint32_t i = 0; i < ctx->trace_ev_used; i++)
             if (cudaEventElapsedTime(&ms, ctx->trace_ev[2 * i], ctx->trace_ev[2 * i + 1]) == cudaSuccess) ctx->stats.ms_trace += ms;
     cudaGetLastError();

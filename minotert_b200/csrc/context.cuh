@@ -131,11 +131,15 @@ struct mrt_context {
     uint32_t W = 0, H = 0, local_rows = 0;
     size_t npix = 0;  // local pixels
     bool have_gbuffer = false, have_color = false, have_accum = false, have_ldr = false;
+    bool secondary_done = false;   // a secondary pass has run (its events and queue counters can be read)
+    bool have_frame_sum = false;   // a frame rendered with MRT_SECONDARY_FRAME_SUM waits in frame_sum (mrt_accum_commit)
     mrt_primary_constants pc{};
     DevArray<uint32_t> visibility;
     DevArray<uint16_t> depth, normal, motion, color16;
     DevArray<float> hit_t;
     DevArray<float4> accum;
+    DevArray<float4> frame_sum;    // MRT_SECONDARY_FRAME_SUM: this frame's radiance sums (xyz) and samples (w)
+    cudaEvent_t commit_ev[2] = {nullptr, nullptr};  // mrt_accum_commit: src rendered / dst consumed
     // bilateral denoiser (denoise.cu): RGBA8 output, tap list cached per (sigma, kSigma, image size)
     DevArray<uchar4> denoised;
     DevArray<float4> dn_taps;

@@ -90,6 +90,12 @@ struct mrt_group {
     std::vector<ncclComm_t> comm;        // one per local context (NCCL transport)
     std::vector<cudaStream_t> comm_stream;  // exchange stream of each local context (ordered by events)
     std::vector<cudaEvent_t> ready, done;
+    // frames in flight (mrt_group_set_frames_in_flight): frame contexts of each local rank, used round-robin by renders
+    // that carry MRT_SECONDARY_FRAME_SUM and committed to ctx[i] in call order; empty: ctx[i] renders itself
+    std::vector<std::vector<mrt_context*>> fctx;
+    uint32_t frames_in_flight = 1;
+    uint64_t frame_index = 0;
+    std::vector<cudaEvent_t> copies;     // outstanding mrt_group_readback_async copies, oldest first
     uint32_t slab_rows = 0;              // 0: no tile partition set
     // root side (allocated on the root's device on first use)
     int root_local = -1;                 // index into ctx of the root of the last gather, -1 if the root is remote
@@ -259,6 +265,11 @@ void mrt_group_destroy(mrt_group* g) {
         if (i < g->comm_stream.size()) { cudaStreamSynchronize(g->comm_stream[i]); }
         cudaStreamSynchronize(g->ctx[i]->stream);
     }
+    for (auto& slots : g->fctx)  // the frame contexts borrow the scenes of the ranks' contexts: they go first
+        for (mrt_context* c : slots) mrt_destroy(c);
+    g->fctx.clear();
+    for (cudaEvent_t e : g->copies) cudaEventDestroy(e);
+    g->copies.clear();
     for (ncclComm_t c : g->comm) g_nccl.CommDestroy(c);
     if (g->root_local >= 0 || g->staging.p || g->full.p || g->row_table.p) {
         // root-side buffers live on the device of the context that was root
@@ -292,22 +303,77 @@ int mrt_group_context(mrt_group* g, uint32_t local_index, mrt_context** ctx_out,
 int mrt_group_set_tiles(mrt_group* g, uint32_t slab_rows) {
     if (!g) return MRT_ERR_INVALID;
     if (slab_rows == 0) return group_fail(g, MRT_ERR_INVALID, "slab_rows = 0");
-    for (size_t i = 0; i < g->ctx.size(); i++) GRP_CTX(g, i, mrt_set_partition(g->ctx[i], g->rank[i], g->nranks, slab_rows));
+    for (size_t i = 0; i < g->ctx.size(); i++) {
+        GRP_CTX(g, i, mrt_set_partition(g->ctx[i], g->rank[i], g->nranks, slab_rows));
+        if (i < g->fctx.size())
+            for (mrt_context* c : g->fctx[i])
+                if (mrt_set_partition(c, g->rank[i], g->nranks, slab_rows) != MRT_OK)
+                    return group_fail(g, MRT_ERR_INVALID, "rank %u frame context: %s", g->rank[i], mrt_last_error(c));
+    }
     g->slab_rows = slab_rows;
+    return MRT_OK;
+}
+
+int mrt_group_set_frames_in_flight(mrt_group* g, uint32_t frames) {
+    if (!g) return MRT_ERR_INVALID;
+    if (frames < 1 || frames > 3) return group_fail(g, MRT_ERR_INVALID, "frames in flight: %u (1..3)", frames);
+    if (int s0 = mrt_group_sync(g)) return s0;
+    if (frames == 1) {
+        for (auto& slots : g->fctx)
+            for (mrt_context* c : slots) mrt_destroy(c);
+        g->fctx.clear();
+        for (size_t i = 0; i < g->ctx.size(); i++) GRP_CTX(g, i, mrt_set_option(g->ctx[i], "trace_ctas_per_sm", 0));
+    } else {
+        g->fctx.resize(g->ctx.size());
+        for (size_t i = 0; i < g->ctx.size(); i++) {
+            while (g->fctx[i].size() > frames) { mrt_destroy(g->fctx[i].back()); g->fctx[i].pop_back(); }
+            while (g->fctx[i].size() < frames) {
+                mrt_context* c = nullptr;
+                int s = mrt_create(g->ctx[i]->device, &c);
+                if (s != MRT_OK) return group_fail(g, s, "frame context on device %d: %s", g->ctx[i]->device, mrt_last_error(nullptr));
+                g->fctx[i].push_back(c);
+            }
+            for (mrt_context* c : g->fctx[i]) {
+                // co-running frames share the SMs: cap each frame's persistent traversal grid (6 resident CTAs per SM in all)
+                mrt_set_option(c, "trace_ctas_per_sm", (int)((6 + frames - 1) / frames));
+                if (g->slab_rows) mrt_set_partition(c, g->rank[i], g->nranks, g->slab_rows);
+            }
+        }
+    }
+    g->frames_in_flight = frames;
+    g->frame_index = 0;
+    return MRT_OK;
+}
+
+int mrt_group_frame_context(mrt_group* g, uint32_t local_index, uint32_t slot, mrt_context** ctx_out) {
+    if (!g || !ctx_out || local_index >= g->ctx.size()) return MRT_ERR_INVALID;
+    if (g->frames_in_flight == 1) {
+        if (slot != 0) return group_fail(g, MRT_ERR_INVALID, "frame context %u of 1", slot);
+        *ctx_out = g->ctx[local_index];
+        return MRT_OK;
+    }
+    if (slot >= g->fctx[local_index].size()) return group_fail(g, MRT_ERR_INVALID, "frame context %u of %zu", slot, g->fctx[local_index].size());
+    *ctx_out = g->fctx[local_index][slot];
     return MRT_OK;
 }
 
 int mrt_group_render(mrt_group* g, uint32_t w, uint32_t h, const mrt_primary_constants* pc, const mrt_secondary_constants* sc,
                      uint32_t spp, uint32_t bounces, uint32_t flags, uint32_t frame_stride) {
     if (!g || !pc || !sc) return MRT_ERR_INVALID;
+    const bool frame_sum = (flags & MRT_SECONDARY_FRAME_SUM) != 0;
     for (size_t i = 0; i < g->ctx.size(); i++) {
         mrt_primary_constants p = *pc;
         mrt_secondary_constants s = *sc;
         p.frameCounter += g->rank[i] * frame_stride;  // sample sets: rank r renders its own frame counters
         s.frameCounter += g->rank[i] * frame_stride;
-        GRP_CTX(g, i, mrt_primary_rays(g->ctx[i], w, h, &p));
-        GRP_CTX(g, i, mrt_secondary_rays(g->ctx[i], &s, spp, bounces, flags));
+        // frames in flight: this frame renders on the next frame context (its previous frame has been committed; the
+        // commit below is stream-ordered behind the render and behind the commit of the frame before)
+        mrt_context* c = (frame_sum && g->frames_in_flight > 1) ? g->fctx[i][g->frame_index % g->frames_in_flight] : g->ctx[i];
+        if (mrt_primary_rays(c, w, h, &p) != MRT_OK || mrt_secondary_rays(c, &s, spp, bounces, flags) != MRT_OK)
+            return group_fail(g, MRT_ERR_STATE, "rank %u: %s", g->rank[i], mrt_last_error(c));
+        if (frame_sum) GRP_CTX(g, i, mrt_accum_commit(g->ctx[i], c, flags & MRT_SECONDARY_ACCUMULATE));
     }
+    if (frame_sum) g->frame_index++;
     return MRT_OK;
 }
 
@@ -348,7 +414,9 @@ int mrt_group_gather(mrt_group* g, int buffer_id, uint32_t root) {
         g->root_local = root_local;
         MRT_TRY(group_tables(g, rc, W, H));
         GRP_CUDA(g, cudaSetDevice(rc->device));
-        if (g->gather_pending) GRP_CUDA(g, cudaStreamSynchronize(g->comm_stream[root_local]));  // staging is reused
+        // staging and the full image are reused by every gather: with NCCL all their readers and writers (recv, scatter,
+        // readback copies) are on the root's exchange stream, in order; with P2P the peers' copies are made to wait for the
+        // root's previous scatter below.  Nothing blocks the host: frames in flight stay in flight.
         if (dev_reserve(rc, g->staging, row_bytes * H) != MRT_OK || dev_reserve(rc, g->full, row_bytes * H) != MRT_OK)
             return group_fail(g, MRT_ERR_OOM, "%s", rc->err);
         g->full_bytes = row_bytes * H;
@@ -384,6 +452,7 @@ int mrt_group_gather(mrt_group* g, int buffer_id, uint32_t root) {
         for (size_t i = 0; i < nloc; i++) {
             if ((int)i == root_local || !src_bytes[i]) continue;
             GRP_CUDA(g, cudaSetDevice(g->ctx[i]->device));
+            if (g->gather_pending) GRP_CUDA(g, cudaStreamWaitEvent(g->comm_stream[i], g->done[root_local], 0));  // previous scatter has read staging
             GRP_CUDA(g, cudaMemcpyPeerAsync(g->staging.p + (size_t)g->rank_first[g->rank[i]] * row_bytes, rc->device, src[i],
                                             g->ctx[i]->device, src_bytes[i], g->comm_stream[i]));
             GRP_CUDA(g, cudaEventRecord(g->done[i], g->comm_stream[i]));
@@ -411,6 +480,14 @@ int mrt_group_gather(mrt_group* g, int buffer_id, uint32_t root) {
         GRP_CUDA(g, cudaSetDevice(g->ctx[i]->device));
         GRP_CUDA(g, cudaEventRecord(g->done[i], g->comm_stream[i]));
         if (buffer_id != MRT_BUF_LDR) GRP_CUDA(g, cudaStreamWaitEvent(g->ctx[i]->stream, g->done[i], 0));
+        else {
+            // the LDR framebuffer is double-buffered and gathers do not block the host: the tonemap after next, which
+            // overwrites this half, waits for this gather (the context's own async-readback guard, tonemap.cu)
+            mrt_context* c = g->ctx[i];
+            if (!c->copy_done[c->ldr_cur]) GRP_CUDA(g, cudaEventCreateWithFlags(&c->copy_done[c->ldr_cur], cudaEventDisableTiming));
+            GRP_CUDA(g, cudaEventRecord(c->copy_done[c->ldr_cur], g->comm_stream[i]));
+            c->copy_pending[c->ldr_cur] = true;
+        }
     }
     return MRT_OK;
 }
@@ -453,14 +530,46 @@ int mrt_group_readback(mrt_group* g, void* host, size_t bytes) {
     return MRT_OK;
 }
 
+// Asynchronous readback of the gathered image: the copy is queued on the root's exchange stream behind the gather (and
+// ahead of the next one, which reuses the image), so the host can go on issuing frames; mrt_group_readback_wait blocks
+// until at most `keep_in_flight` of the queued copies are still outstanding (0: all have landed).
+int mrt_group_readback_async(mrt_group* g, void* host, size_t bytes) {
+    if (!g || !host) return MRT_ERR_INVALID;
+    if (g->root_local < 0 || !g->full.p) return group_fail(g, MRT_ERR_STATE, "no gathered image in this process (remote root, or no gather yet)");
+    if (bytes > g->full_bytes) return group_fail(g, MRT_ERR_INVALID, "readback of %zu bytes from a %zu-byte image", bytes, g->full_bytes);
+    GRP_CUDA(g, cudaSetDevice(g->ctx[g->root_local]->device));
+    cudaStream_t cs = g->comm_stream[g->root_local];
+    GRP_CUDA(g, cudaMemcpyAsync(host, g->full.p, bytes, cudaMemcpyDeviceToHost, cs));
+    cudaEvent_t e;
+    GRP_CUDA(g, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    GRP_CUDA(g, cudaEventRecord(e, cs));
+    g->copies.push_back(e);
+    return MRT_OK;
+}
+
+int mrt_group_readback_wait(mrt_group* g, uint32_t keep_in_flight) {
+    if (!g) return MRT_ERR_INVALID;
+    while (g->copies.size() > keep_in_flight) {
+        cudaEvent_t e = g->copies.front();
+        g->copies.erase(g->copies.begin());
+        cudaError_t r = cudaEventSynchronize(e);
+        cudaEventDestroy(e);
+        if (r != cudaSuccess) return group_fail(g, MRT_ERR_CUDA, "readback wait: %s", cudaGetErrorString(r));
+    }
+    return MRT_OK;
+}
+
 int mrt_group_sync(mrt_group* g) {
     if (!g) return MRT_ERR_INVALID;
     for (size_t i = 0; i < g->ctx.size(); i++) {
+        if (i < g->fctx.size())
+            for (mrt_context* c : g->fctx[i])
+                if (mrt_sync(c) != MRT_OK) return group_fail(g, MRT_ERR_CUDA, "rank %u frame context: %s", g->rank[i], mrt_last_error(c));
         GRP_CTX(g, i, mrt_sync(g->ctx[i]));
         GRP_CUDA(g, cudaStreamSynchronize(g->comm_stream[i]));
     }
     g->gather_pending = false;
-    return MRT_OK;
+    return mrt_group_readback_wait(g, 0);
 }
 
 }  // extern "C"

@@ -1177,6 +1177,8 @@ int mesh_primary(mrt_context* ctx) {
 
 int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags) {
     const uint32_t npix = (uint32_t)ctx->npix;
+    const bool frame_sum = (flags & MRT_SECONDARY_FRAME_SUM) != 0;  // samples go to the per-frame buffer (mrt_accum_commit)
+    if (frame_sum) MRT_TRY(dev_reserve(ctx, ctx->frame_sum, npix));
     const bool path_kernel = ctx->opt_path_kernel != 0 && spp < 65536u && bounces < 65535u;
     ctx->secondary_was_path_kernel = path_kernel;
     if (path_kernel) {
@@ -1195,7 +1197,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         P.bnW = ctx->bnW;
         P.bnH = ctx->bnH;
         P.bounces = bounces;
-        P.accumulate = ((flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum) ? 1 : 0;
+        P.accumulate = ((flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum && !frame_sum) ? 1 : 0;
         P.part = ctx->part;
         sa.bvh = make_bvh(ctx);
         sa.A = ctx->atmo;
@@ -1205,7 +1207,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         sa.hit0_pos = ctx->hit0_pos.p;
         sa.hit0_n = ctx->hit0_n.p;
         sa.npix = npix;
-        sa.accum = ctx->accum.p;
+        sa.accum = frame_sum ? ctx->frame_sum.p : ctx->accum.p;
         const bool timed = ctx->opt_trace_timing && ctx->trace_ev_used < 4096;
         while (timed && ctx->trace_ev.size() < 2 * (size_t)(ctx->trace_ev_used + 1)) {
             cudaEvent_t e;
@@ -1275,7 +1277,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     P.bnW = ctx->bnW;
     P.bnH = ctx->bnH;
     P.bounces = bounces;
-    P.accumulate = ((flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum) ? 1 : 0;
+    P.accumulate = ((flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum && !frame_sum) ? 1 : 0;
     P.part = ctx->part;
     sa.bvh = make_bvh(ctx);
     sa.A = ctx->atmo;
@@ -1285,7 +1287,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     sa.hit0_pos = ctx->hit0_pos.p;
     sa.hit0_n = ctx->hit0_n.p;
     sa.path_state = ctx->path_state.p;
-    sa.accum = ctx->accum.p;
+    sa.accum = frame_sum ? ctx->frame_sum.p : ctx->accum.p;
     sa.overflow = ctx->visit_counters.p + 4 + 2;
     constexpr uint32_t kMaxTimedLaunches = 4096;  // event pairs kept since mrt_stats_reset
 

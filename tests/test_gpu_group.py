@@ -153,3 +153,106 @@ def test_group_nccl_two_gpus_tiles_and_sample_sets(oracle, sky_inputs, blue_nois
         ctx.close()
     assert same(summed, parts[0] + parts[1])   # two addends: fp32 addition is commutative, the sum is exact-order-free
     assert np.all(summed[..., 3] == 4.0)
+
+
+# ---- frames in flight for progressive tile mode (MRT_SECONDARY_FRAME_SUM + mrt_accum_commit) ----
+
+def frame_sum_single_context(oracle, atmo, cam, blue_noise, mesh, w, h, spp, bounces, frames):
+    """One context, one frame at a time, in the frame-sum semantic: every frame's samples are summed from zero into the
+    per-frame buffer and the frame is then added to the accumulator -- the expected bits for every N and every K."""
+    ctx = capi.Context(0)
+    try:
+        prepare([ctx], oracle, atmo, cam, blue_noise, mesh)
+        for f in range(frames):
+            pc, sc = oracle.constants(cam, frame=f + 1)
+            ctx.primary_rays(w, h, as_capi(pc, capi.PrimaryConstants))
+            ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), spp, bounces, capi.SECONDARY_FRAME_SUM)
+            ctx.accum_commit(None, capi.SECONDARY_ACCUMULATE if f else 0)
+            ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+        return ctx.readback(capi.BUF_LDR).copy(), ctx.readback(capi.BUF_ACCUM).copy()
+    finally:
+        ctx.close()
+
+
+def group_frames_in_flight_image(nranks, k, oracle, atmo, cam, blue_noise, mesh, w, h, spp, bounces, frames, slab):
+    g = capi.Group([0] * nranks, transport="p2p")
+    try:
+        prepare(g.contexts, oracle, atmo, cam, blue_noise, mesh)
+        g.set_tiles(slab)
+        slots = g.set_frames_in_flight(k)
+        for i, fcs in enumerate(slots):
+            for fc in fcs:
+                if fc is g.contexts[i]:
+                    continue
+                setup_sky(fc, oracle, atmo, cam.position[:])
+                fc.upload_blue_noise(blue_noise)
+                fc.share_scene(g.contexts[0])
+        for f in range(frames):
+            pc, sc = oracle.constants(cam, frame=f + 1)
+            g.render(w, h, as_capi(pc, capi.PrimaryConstants), as_capi(sc, capi.SecondaryConstants), spp, bounces,
+                     capi.SECONDARY_FRAME_SUM | (capi.SECONDARY_ACCUMULATE if f else 0))
+            g.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+            g.gather(capi.BUF_LDR, 0)
+        ldr = g.readback().copy()
+        g.gather(capi.BUF_ACCUM, 0)
+        acc = g.readback().copy()
+        for fcs in slots:
+            for fc in fcs:
+                assert fc.stats().stack_overflows == 0
+        return ldr, acc
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("nranks,k,slab", [(1, 1, 8), (1, 3, 8), (2, 2, 8), (3, 3, 5), (4, 2, 8)])
+def test_frames_in_flight_tiles_equal_the_sequential_frame_sum_render(oracle, sky_inputs, blue_noise, nranks, k, slab):
+    """Progressive tile mode with K frame contexts per rank (frames overlap on the GPU) == one context rendering the
+    frames one after the other, bit for bit, for every number of ranks and every K."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h, spp, bounces, frames = 167, 101, 2, 2, 7
+    cam = oracle.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+    mesh = (pos, idx, alb)
+    want = frame_sum_single_context(oracle, atmo, cam, blue_noise, mesh, w, h, spp, bounces, frames)
+    got = group_frames_in_flight_image(nranks, k, oracle, atmo, cam, blue_noise, mesh, w, h, spp, bounces, frames, slab)
+    for a, b, name in zip(got, want, ("LDR", "accumulator")):
+        assert same(a, b), f"{nranks} ranks x {k} frames in flight: {name} differs from the sequential frame-sum render"
+    assert np.all(got[1][..., 3] == spp * frames)
+
+
+def test_frame_sum_semantic_is_the_plain_accumulation_up_to_rounding(oracle, sky_inputs, blue_noise):
+    """The frame-sum accumulator adds the same samples as the plain progressive accumulator, grouped per frame: equal up
+    to fp32 summation order (a few ulp of the sum), identical sample counts, framebuffers within one code value."""
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h, spp, bounces, frames = 160, 90, 4, 2, 4
+    cam = oracle.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+    mesh = (pos, idx, alb)
+    ldr_a, acc_a, _ = single_context_image(oracle, atmo, cam, blue_noise, mesh, w, h, spp, bounces, frames)
+    ldr_b, acc_b = frame_sum_single_context(oracle, atmo, cam, blue_noise, mesh, w, h, spp, bounces, frames)
+    assert np.array_equal(acc_a[..., 3], acc_b[..., 3])
+    ok = np.isfinite(acc_a).all(-1) & np.isfinite(acc_b).all(-1)
+    assert np.allclose(acc_a[ok], acc_b[ok], rtol=1e-5, atol=1e-6)
+    assert (np.abs(ldr_a.astype(int) - ldr_b.astype(int)).max(-1) <= 1).all()
+
+
+def test_frame_sum_call_order_errors(oracle, sky_inputs, blue_noise):
+    atmo = sky_inputs[0]
+    pos, idx, alb, view = scenes.small_terrain()
+    cam = oracle.make_camera(64, 36, view["position"], view["yaw_deg"], view["pitch_deg"])
+    ctx = capi.Context(0)
+    try:
+        prepare([ctx], oracle, atmo, cam, blue_noise, (pos, idx, alb))
+        with pytest.raises(capi.MinoteError):   # nothing rendered with FRAME_SUM yet
+            ctx.accum_commit(None, 0)
+        pc, sc = oracle.constants(cam, frame=1)
+        ctx.primary_rays(64, 36, as_capi(pc, capi.PrimaryConstants))
+        ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), 1, 1, capi.SECONDARY_FRAME_SUM)
+        with pytest.raises(capi.MinoteError):   # the accumulator does not exist until the frame is committed
+            ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+        ctx.accum_commit(None, 0)
+        ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+        with pytest.raises(capi.MinoteError):   # a frame is committed once
+            ctx.accum_commit(None, 0)
+    finally:
+        ctx.close()

@@ -1,10 +1,11 @@
-set +e
-python tools/check_option.py hall_260k 1920 1080 1 2 primary_batched=1 2>&1 | tail -7
-tools/ab.sh hall_base --no-extra-configs
-tools/ab.sh hall_pb --no-extra-configs --opt primary_batched=1
-tools/ab.sh 1m_base --no-extra-configs --workload scene_1m_1080p
-tools/ab.sh 1m_pb --no-extra-configs --workload scene_1m_1080p --opt primary_batched=1
-tools/ab.sh hall_b2c3 --no-extra-configs --opt bands=2 --opt trace_ctas_per_sm=3
-tools/ab.sh hall_b3c2 --no-extra-configs --opt bands=3 --opt trace_ctas_per_sm=2
-tools/ab.sh 10m_base --no-extra-configs --workload scene_10m_4k --steps 5
-tools/ab.sh 10m_b2c3 --no-extra-configs --workload scene_10m_4k --steps 5 --opt bands=2 --opt trace_ctas_per_sm=3
+timeout 900 python -m pytest tests/test_gpu_group.py -m gpu -q -x -k "frame or tiles_p2p" 2>&1 | tail -15
+python bench.py --workload tiles_4k_progressive --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/tiles1_fif3.json 2> gpurun_out/tiles1_fif3.err || tail -20 gpurun_out/tiles1_fif3.err
+python bench.py --workload tiles_4k_progressive --steps 8 --warmup 3 --no-cpu-baseline --frames-in-flight 1 > gpurun_out/tiles1_fif1.json 2> gpurun_out/tiles1_fif1.err || tail -20 gpurun_out/tiles1_fif1.err
+python - <<'PY'
+import json
+for t in ("fif3","fif1"):
+    try:
+        d=json.loads([l for l in open(f"gpurun_out/tiles1_{t}.json") if l.startswith("{")][-1])
+        print(t, round(d["value"],1), "ms", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"],1), d["details"]["framebuffer_sha256_16"], "roof", round(d["roofline"]["frac"],3), d["kernels"])
+    except Exception as e: print(t,"FAILED",e)
+PY
