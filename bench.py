@@ -548,7 +548,7 @@ def measure_tiles(args, steps, warmup, world, rank, local):
         # Frames in flight (the reference keeps 3, renderer.ixx:36): consecutive progressive frames render on their own
         # frame contexts (shared BVH) and are added to the rank's accumulator in frame order (MRT_SECONDARY_FRAME_SUM +
         # mrt_accum_commit inside mrt_group_render), so one frame's traversal drains are filled by the next frame's kernels.
-        in_flight = max(1, min(3, args.frames_in_flight))
+        in_flight = max(1, min(8, args.tile_frames_in_flight))
         fcs = g.set_frames_in_flight(in_flight)[0]
         for fc in fcs:
             if fc is ctx:
@@ -625,7 +625,7 @@ def measure_tiles(args, steps, warmup, world, rank, local):
         kc.sync()
         st = kc.stats()
         trace_ms, trace_launches, trace_rays = st.ms_trace, st.trace_launches, int(st.total_rays) - w * local_rows * ksteps
-        kc.set_option("trace_ctas_per_sm", 0 if in_flight == 1 else (6 + in_flight - 1) // in_flight)
+        kc.set_option("trace_ctas_per_sm", 0 if in_flight == 1 else (8 + in_flight - 1) // in_flight)
         frame(0, True)  # restart the accumulation for the e2e loop below
 
         # ---- e2e: camera constants from the host in, rank 0 reads the gathered framebuffer back every step; wall clock
@@ -758,6 +758,7 @@ def main():
     ap.add_argument("--no-trace-timing", action="store_true", help="A/B: drop the per-launch CUDA events (roofline fields become 0)")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="extra mrt_set_option switches (A/B experiments)")
     ap.add_argument("--frames-in-flight", type=int, default=3, help="frame contexts of the e2e / pipelined measurements at N = 1 (reference: 3)")
+    ap.add_argument("--tile-frames-in-flight", type=int, default=6, help="frame contexts per rank of the tile-partitioned progressive workload (config 4)")
     ap.add_argument("--builder", default="ploc", choices=["ploc", "lbvh"], help="binary hierarchy under the 8-wide BVH")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -322,12 +322,13 @@ int mrt_group_set_tiles(mrt_group* g, uint32_t slab_rows);
 int mrt_group_render(mrt_group* g, uint32_t w, uint32_t h, const mrt_primary_constants* pc, const mrt_secondary_constants* sc,
                      uint32_t spp, uint32_t bounces, uint32_t flags, uint32_t frame_stride);
 /* Frames in flight for progressive tile mode (the reference keeps 3 frames in flight, renderer.ixx:36): every local
- * rank gets `frames` (1..3) frame contexts on its device; mrt_group_render calls that carry MRT_SECONDARY_FRAME_SUM go
+ * rank gets `frames` (1..MRT_GROUP_MAX_FRAMES) frame contexts on its device; mrt_group_render calls that carry MRT_SECONDARY_FRAME_SUM go
  * round-robin over them and are committed (mrt_accum_commit) to the rank's context in call order, so consecutive
  * frames overlap on the GPU -- the drain of one frame's traversal launches is filled by the next frame's kernels -- and
  * the accumulated image is bit-identical for every `frames` and every number of ranks.  The caller prepares each
  * frame context like the rank's own (blue noise, mrt_scene_share from the rank's context, atmosphere, sky view);
  * partitions and traversal grid sizes are set by the group.  frames = 1 (default): the rank's context renders. */
+#define MRT_GROUP_MAX_FRAMES 8
 int mrt_group_set_frames_in_flight(mrt_group* g, uint32_t frames);
 int mrt_group_frame_context(mrt_group* g, uint32_t local_index, uint32_t slot, mrt_context** ctx_out);
 int mrt_group_tonemap(mrt_group* g, int mode, float exposure, const float* params, uint32_t nparams, int source);

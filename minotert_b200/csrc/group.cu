@@ -316,7 +316,7 @@ int mrt_group_set_tiles(mrt_group* g, uint32_t slab_rows) {
 
 int mrt_group_set_frames_in_flight(mrt_group* g, uint32_t frames) {
     if (!g) return MRT_ERR_INVALID;
-    if (frames < 1 || frames > 3) return group_fail(g, MRT_ERR_INVALID, "frames in flight: %u (1..3)", frames);
+    if (frames < 1 || frames > MRT_GROUP_MAX_FRAMES) return group_fail(g, MRT_ERR_INVALID, "frames in flight: %u (1..%d)", frames, MRT_GROUP_MAX_FRAMES);
     if (int s0 = mrt_group_sync(g)) return s0;
     if (frames == 1) {
         for (auto& slots : g->fctx)
@@ -334,8 +334,9 @@ int mrt_group_set_frames_in_flight(mrt_group* g, uint32_t frames) {
                 g->fctx[i].push_back(c);
             }
             for (mrt_context* c : g->fctx[i]) {
-                // co-running frames share the SMs: cap each frame's persistent traversal grid (6 resident CTAs per SM in all)
-                mrt_set_option(c, "trace_ctas_per_sm", (int)((6 + frames - 1) / frames));
+                // co-running frames share the SMs: cap each frame's persistent traversal grid so that ~8 CTAs per SM are
+                // offered in all (6 are resident; measured on 1/8-image slabs, tools/bench_slab_inflight.py)
+                mrt_set_option(c, "trace_ctas_per_sm", (int)((8 + frames - 1) / frames));
                 if (g->slab_rows) mrt_set_partition(c, g->rank[i], g->nranks, g->slab_rows);
             }
         }

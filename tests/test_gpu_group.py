@@ -204,7 +204,7 @@ def group_frames_in_flight_image(nranks, k, oracle, atmo, cam, blue_noise, mesh,
         g.close()
 
 
-@pytest.mark.parametrize("nranks,k,slab", [(1, 1, 8), (1, 3, 8), (2, 2, 8), (3, 3, 5), (4, 2, 8)])
+@pytest.mark.parametrize("nranks,k,slab", [(1, 1, 8), (1, 3, 8), (2, 2, 8), (3, 3, 5), (4, 2, 8), (2, 6, 8)])
 def test_frames_in_flight_tiles_equal_the_sequential_frame_sum_render(oracle, sky_inputs, blue_noise, nranks, k, slab):
     """Progressive tile mode with K frame contexts per rank (frames overlap on the GPU) == one context rendering the
     frames one after the other, bit for bit, for every number of ranks and every K."""

@@ -16,7 +16,8 @@ pos, idx, alb, view = getattr(scenes, scene)()
 bn = np.ascontiguousarray(np.array(Image.open(os.path.join(ROOT, "assets", "blue_noise.png")).convert("RGBA"), np.uint8))
 cam = host.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
 ctxs = []
-for k in range(3):
+KMAX = 6
+for k in range(KMAX):
     c = capi.Context(0)
     c.upload_blue_noise(bn)
     if k == 0:
@@ -27,10 +28,11 @@ for k in range(3):
     c.sky_view(cam.position[:], (-0.435286462, 0.818654716, 0.374606609), (8.0, 8.0, 8.0))
     ctxs.append(c)
 out = {}
-for n in (8, 1):
+for n, pk in ((8, 0), (8, 1)):
     for c in ctxs: c.set_partition(0, n, 8)
-    for K in (1, 2, 3):
-        for cap in (0, (6 + K - 1) // K):
+    for c in ctxs: c.set_option("path_kernel", pk)
+    for K, cap in ((1, 0), (2, 3), (3, 2), (3, 3), (4, 2), (4, 1), (6, 1), (6, 2)):
+        if True:
             if K == 1 and cap: continue
             for c in ctxs: c.set_option("trace_ctas_per_sm", cap)
             def frame(i):
@@ -45,6 +47,6 @@ for n in (8, 1):
             t0 = time.perf_counter()
             for i in range(steps): frame(i)
             for c in ctxs: c.sync()
-            out[f"N{n}_K{K}_cap{cap}"] = round(1e3 * (time.perf_counter() - t0) / steps, 3)
-            print(f"N{n}_K{K}_cap{cap}", out[f"N{n}_K{K}_cap{cap}"], flush=True)
+            out[f"N{n}_pk{pk}_K{K}_cap{cap}"] = round(1e3 * (time.perf_counter() - t0) / steps, 3)
+            print(f"N{n}_pk{pk}_K{K}_cap{cap}", out[f"N{n}_pk{pk}_K{K}_cap{cap}"], flush=True)
 print(json.dumps(out))
