@@ -109,6 +109,14 @@ typedef enum {
 #define MRT_SECONDARY_ACCUMULATE 1u /* add to MRT_BUF_ACCUM instead of restarting it */
 #define MRT_SECONDARY_SORT_RAYS 2u  /* reorder each bounce's ray queue before it is traced (image unchanged) with the
                                      * mode of option "sort_rays" (octant binning if that is 0) */
+#define MRT_SECONDARY_NEE_SUN 8u    /* triangle scenes: the sun is a sampled light -- every hit vertex that
+                                     * bounces sends a shadow ray into the sun's disc (two more rotated random numbers,
+                                     * drawn before the bounce's; any-hit traversal) and adds throughput * E_sun * n.l *
+                                     * limb * Omega / pi when it is free; escaping bounce rays then add the sky-view term
+                                     * only.  Same expectation as the reference's estimator, without waiting for a bounce
+                                     * ray to hit a 0.5 degree disc.  Shadow rays count as secondary rays. */
+#define MRT_SECONDARY_SKY_AT_HIT 16u /* the sky is evaluated at the origin of the escaping ray (the shaded point), not at
+                                     * the camera position as secondaryRays.comp:37 does for every vertex */
 #define MRT_SECONDARY_FRAME_SUM 4u  /* triangle scenes: this call's samples are summed into the context's own per-frame
                                      * buffer, starting from zero, and MRT_BUF_ACCUM is left alone; mrt_accum_commit
                                      * then adds the frame to an accumulator.  Frames rendered by different contexts

@@ -19,7 +19,7 @@ MISS_ID = 0xFFFFFFFF
  BUF_MULTISCATTERING, BUF_SKY_VIEW, BUF_HIT_T, BUF_DENOISED, BUF_BVH_NODES, BUF_BVH_TRIS, BUF_TEMPORAL,
  BUF_TEMPORAL_COUNT) = range(16)
 BUILD_FULL, BUILD_REFIT = 0, 1
-SECONDARY_ACCUMULATE, SECONDARY_SORT_RAYS, SECONDARY_FRAME_SUM = 1, 2, 4
+SECONDARY_ACCUMULATE, SECONDARY_SORT_RAYS, SECONDARY_FRAME_SUM, SECONDARY_NEE_SUN, SECONDARY_SKY_AT_HIT = 1, 2, 4, 8, 16
 TEMPORAL_RESET = 1
 TONEMAP = {"linear": 0, "reinhard": 1, "hable": 2, "aces": 3, "uchimura": 4, "amd": 5}
 DENOISE = {"none": 0, "bilateral": 1}   # Renderer_impl::denoise modes (src/gfx/renderer.ixx:129-132)

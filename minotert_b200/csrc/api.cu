@@ -170,7 +170,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->visibility); dev_free(ctx->depth); dev_free(ctx->normal); dev_free(ctx->motion); dev_free(ctx->color16);
     dev_free(ctx->denoised); dev_free(ctx->dn_taps);
     for (int k = 0; k < 2; k++) { dev_free(ctx->tp_rgba[k]); dev_free(ctx->tp_count[k]); dev_free(ctx->tp_vis[k]); }
-    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->frame_sum); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
+    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->frame_sum); for (auto& q : ctx->shadow_q) dev_free(q); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
     dev_free(ctx->hit0_pos); dev_free(ctx->hit0_n); dev_free(ctx->path_state);
     for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); }
     dev_free(ctx->hits); dev_free(ctx->queue_counts); dev_free(ctx->sort_keys); dev_free(ctx->sort_keys_alt);
@@ -419,8 +419,8 @@ int mrt_secondary_rays(mrt_context* ctx, const mrt_secondary_constants* c, uint3
     if (!ctx->have_gbuffer) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays before primary rays");
     if (!ctx->have_atmo || !ctx->have_view) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: sky LUTs missing (mrt_atmosphere, mrt_sky_view)");
     if (!ctx->bn) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: blue noise texture missing");
-    if ((flags & MRT_SECONDARY_FRAME_SUM) && ctx->scene_kind != 2)
-        return mrt_fail(ctx, MRT_ERR_INVALID, "secondary rays: MRT_SECONDARY_FRAME_SUM is for triangle scenes");
+    if ((flags & (MRT_SECONDARY_FRAME_SUM | MRT_SECONDARY_NEE_SUN | MRT_SECONDARY_SKY_AT_HIT)) && ctx->scene_kind != 2)
+        return mrt_fail(ctx, MRT_ERR_INVALID, "secondary rays: flags 0x%x are for triangle scenes", flags);
     sky_join(ctx);
     cudaEventRecord(ctx->ev[4], ctx->stream);
     int s = MRT_OK;
@@ -628,6 +628,11 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
             MRT_CUDA(ctx, cudaMemcpy(counts.data(), ctx->queue_counts.p, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost));
             uint64_t total = 0;
             for (uint32_t v : counts) total += v;
+            if (ctx->num_shadow_counts) {  // MRT_SECONDARY_NEE_SUN: shadow rays are traced rays too
+                counts.resize(ctx->num_shadow_counts);
+                MRT_CUDA(ctx, cudaMemcpy(counts.data(), ctx->queue_counts.p + ctx->shadow_counts_at, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost));
+                for (uint32_t v : counts) total += v;
+            }
             ctx->stats.secondary_rays = total;
         }
     }

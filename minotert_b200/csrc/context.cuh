@@ -138,6 +138,8 @@ struct mrt_context {
     DevArray<uint16_t> depth, normal, motion, color16;
     DevArray<float> hit_t;
     DevArray<float4> accum;
+    DevArray<float4> shadow_q[3];  // MRT_SECONDARY_NEE_SUN: shadow-ray queue (origin|pixel, direction, contribution)
+    uint32_t shadow_counts_at = 0, num_shadow_counts = 0;  // where the shadow-queue sizes sit in queue_counts
     DevArray<float4> frame_sum;    // MRT_SECONDARY_FRAME_SUM: this frame's radiance sums (xyz) and samples (w)
     cudaEvent_t commit_ev[2] = {nullptr, nullptr};  // mrt_accum_commit: src rendered / dst consumed
     // bilateral denoiser (denoise.cu): RGBA8 output, tap list cached per (sigma, kSigma, image size)

@@ -54,6 +54,7 @@ MRT_D void flush_counters(const TraceCounters& c, unsigned long long* counters, 
 // Ray index r -> 8x4-pixel tile r/32 (row-major tile grid), pixel r%32 inside it, so the 32 rays a fresh
 // warp takes are one compact tile (coherent) and padding pixels are skipped by load().
 struct PrimaryJob {
+    static constexpr bool ANY_HIT = false;
     MeshFrame F;
     BvhDev bvh;
     uint32_t tiles_x, tiles;
@@ -485,6 +486,7 @@ k_mesh_primary_entry(PrimaryJob J, uint32_t big_x, unsigned long long* counters,
 
 // ---- one wave of the wavefront: queue entry k -> hit record k ----
 struct QueueJob {
+    static constexpr bool ANY_HIT = false;
     const float4* ray_o;
     const float4* ray_d;
     const uint32_t* count_ptr;
@@ -621,6 +623,7 @@ __global__ void __launch_bounds__(256) k_ray_keys(const float4* __restrict__ ray
 
 // ---- closest-hit query for mrt_trace_rays ----
 struct QueryJob {
+    static constexpr bool ANY_HIT = false;
     const float* ro;
     const float* rd;
     uint32_t n;
@@ -635,6 +638,32 @@ struct QueryJob {
     MRT_D void store(uint32_t i, const TraceHit& h) const {
         ids[i] = h.prim;
         ts[i] = h.prim != MRT_MISS_ID ? h.t : 0.0f;
+    }
+};
+
+// Shadow rays of MRT_SECONDARY_NEE_SUN: occlusion queries towards the sun's disc.  A free ray adds the contribution the
+// shade stage computed for it to its pixel; a pixel has at most one shadow ray per wave and no other kernel runs on the
+// context's stream meanwhile, so the add needs no atomic and the image does not depend on the queue order.
+struct ShadowJob {
+    static constexpr bool ANY_HIT = true;
+    const float4* ray_o;   // origin, pixel
+    const float4* ray_d;   // direction
+    const float4* contrib; // throughput * E_sun * n.l * limb * Omega / pi
+    const uint32_t* count_ptr;
+    float4* accum;
+    MRT_D uint32_t count() const { return *count_ptr; }
+    MRT_D bool load(uint32_t i, float3& o, float3& d) const {
+        float4 o4 = __ldg(&ray_o[i]), d4 = __ldg(&ray_d[i]);
+        o = f3(o4.x, o4.y, o4.z);
+        d = f3(d4.x, d4.y, d4.z);
+        return true;
+    }
+    MRT_D void store(uint32_t i, const TraceHit& h) const {
+        if (h.prim != MRT_MISS_ID) return;
+        const uint32_t pixel = __float_as_uint(__ldg(&ray_o[i]).w);
+        const float4 c = __ldg(&contrib[i]);
+        float4 a = accum[pixel];
+        accum[pixel] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w);
     }
 };
 
@@ -663,6 +692,7 @@ struct ShadeParams {
     int accumulate;
     Partition part;
     uint32_t pixel_base; // FIRST: vertex k of this launch is pixel pixel_base + k (bands of the image, see mesh_secondary)
+    uint32_t ext;        // MRT_SECONDARY_NEE_SUN | MRT_SECONDARY_SKY_AT_HIT
 };
 
 // Everything the shade stage reads and writes (passed by value to the kernels).
@@ -685,6 +715,10 @@ struct ShadeArgs {
     float4* out_d;
     uint32_t* out_count;
     unsigned long long* overflow; // error counter (mrt_stats.stack_overflows) for a fused worker that gave up waiting
+    float4* sh_o;                 // MRT_SECONDARY_NEE_SUN: shadow-ray queue of this vertex (origin|pixel, direction, contribution)
+    float4* sh_d;
+    float4* sh_c;
+    uint32_t* sh_count;
 };
 
 // hit record of a ray that has not been traced yet (byte pattern of cudaMemset(0xFE)): tri index 0xFEFEFEFE
@@ -697,11 +731,12 @@ struct ShadeArgs {
 template <bool FIRST, bool FUSED>
 MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
     const ShadeParams& P = a.P;
-    bool emit = false;
-    float3 ro = f3s(0.0f), rd = f3s(0.0f);
+    bool emit = false, emit_shadow = false;
+    float3 ro = f3s(0.0f), rd = f3s(0.0f), sl = f3s(0.0f), sc = f3s(0.0f);
     uint32_t pixel = 0;
     if (k < count) {
         float3 pos, n, thr;
+        float3 sky_pos = P.cameraPos;  // MRT_SECONDARY_SKY_AT_HIT: the origin of the ray that escaped
         uint32_t prim, rng;
         if (FIRST) {
             pixel = P.pixel_base + k;
@@ -748,11 +783,12 @@ MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
                 prim = MRT_MISS_ID;
                 pos = f3s(0.0f);
                 n = d;  // secondaryRays.comp:88
+                if (P.ext & MRT_SECONDARY_SKY_AT_HIT) sky_pos = o;
             }
         }
         if (prim == MRT_MISS_ID) {
-            // secondaryRays.comp:96: the path ends in the sky
-            float3 c = thr * sky_color(a.A, a.luts, P.cameraPos, n);
+            // secondaryRays.comp:96: the path ends in the sky (a bounce ray of an NEE path adds the sky-view term only)
+            float3 c = thr * sky_color(a.A, a.luts, sky_pos, n, FIRST || !(P.ext & MRT_SECONDARY_NEE_SUN));
             float4 acc = a.accum[pixel];
             a.accum[pixel] = make_float4(acc.x + c.x, acc.y + c.y, acc.z + c.z, acc.w);
             if (FIRST) a.path_state[pixel] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
@@ -762,6 +798,21 @@ MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
             if (P.vertex < P.bounces) {
                 uint32_t lr = pixel / P.W, x = pixel - lr * P.W;
                 float2 rot = blue_noise_rotation(a.bn, P.bnW, P.bnH, x, partition_local_to_y(P.part, lr));
+                if (P.ext & MRT_SECONDARY_NEE_SUN) {  // contract: oracle orc_render_tris_ext; drawn BEFORE the bounce's numbers
+                    const float u0 = rotated_random(rng, rot.x);
+                    const float u1 = rotated_random(rng, rot.y);
+                    float wgt;
+                    sky_nee_sun_sample(u0, u1, sl, wgt);
+                    const float ndotl = dot3(n, sl);
+                    if (ndotl > 0.0f) {
+                        const float3 so = pos + n * RAY_OFFSET;
+                        const float3 E = sky_sun_centre_radiance(a.A, a.luts, (P.ext & MRT_SECONDARY_SKY_AT_HIT) ? so : P.cameraPos);
+                        if (E.x > 0.0f || E.y > 0.0f || E.z > 0.0f) {
+                            sc = (thr * E) * (ndotl * wgt);
+                            emit_shadow = true;
+                        }
+                    }
+                }
                 lambert_bounce(pos, n, rng, rot.x, rot.y, ro, rd);
                 emit = true;
             }
@@ -779,6 +830,21 @@ MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
             uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
             a.out_o[slot] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(pixel));
             a.out_d[slot] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+        }
+    }
+    if (P.ext & MRT_SECONDARY_NEE_SUN) {  // shadow rays: same compaction into their own queue (origin = the bounce's)
+        const unsigned sb = __ballot_sync(0xFFFFFFFFu, emit_shadow);
+        if (sb) {
+            const unsigned lane = threadIdx.x & 31;
+            uint32_t base = 0;
+            if (lane == (unsigned)(__ffs(sb) - 1)) base = atomicAdd(a.sh_count, (uint32_t)__popc(sb));
+            base = __shfl_sync(0xFFFFFFFFu, base, __ffs(sb) - 1);
+            if (emit_shadow) {
+                uint32_t slot = base + __popc(sb & ((1u << lane) - 1u));
+                a.sh_o[slot] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(pixel));
+                a.sh_d[slot] = make_float4(sl.x, sl.y, sl.z, 0.0f);
+                a.sh_c[slot] = make_float4(sc.x, sc.y, sc.z, 0.0f);
+            }
         }
     }
 }
@@ -1179,7 +1245,10 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     const uint32_t npix = (uint32_t)ctx->npix;
     const bool frame_sum = (flags & MRT_SECONDARY_FRAME_SUM) != 0;  // samples go to the per-frame buffer (mrt_accum_commit)
     if (frame_sum) MRT_TRY(dev_reserve(ctx, ctx->frame_sum, npix));
-    const bool path_kernel = ctx->opt_path_kernel != 0 && spp < 65536u && bounces < 65535u;
+    const uint32_t ext = flags & (MRT_SECONDARY_NEE_SUN | MRT_SECONDARY_SKY_AT_HIT);
+    const bool nee = (ext & MRT_SECONDARY_NEE_SUN) != 0;
+    // the sky extensions live in the wavefront's shade stage only
+    const bool path_kernel = ctx->opt_path_kernel != 0 && spp < 65536u && bounces < 65535u && ext == 0;
     ctx->secondary_was_path_kernel = path_kernel;
     if (path_kernel) {
         // one persistent launch for all samples and bounces: no queues, no hit records, no path-state buffer
@@ -1188,6 +1257,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         MRT_CUDA(ctx, cudaMemsetAsync(ctx->queue_counts.p, 0, sizeof(uint32_t) * 4, ctx->stream));
         MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
         ctx->num_queue_counts = 0;
+        ctx->num_shadow_counts = 0;
         ShadeArgs sa{};
         ShadeParams& P = sa.P;
         P.cameraPos = f3(c->cameraPos[0], c->cameraPos[1], c->cameraPos[2]);
@@ -1225,7 +1295,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         return mrt_check_cuda(ctx, cudaGetLastError(), "mesh_secondary (path kernel)");
     }
     const uint32_t waves = spp * bounces;
-    const bool fused = ctx->opt_fused_shade != 0;
+    const bool fused = ctx->opt_fused_shade != 0 && !nee;
     // sort mode: 0 none, 1 direction octant (binning), 2 (origin cell, octant) (radix sort); the flag asks for the configured
     // mode, or the octant binning when none is configured
     const int sort_mode = ctx->opt_sort_rays ? ctx->opt_sort_rays : ((flags & MRT_SECONDARY_SORT_RAYS) ? 1 : 0);
@@ -1251,12 +1321,17 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     }
     // counters: [band][0..waves] queue sizes; then [band][wave] work counters of the persistent launches; then
     // [band][wave] chunk counters of their (fused) shade stages
-    const size_t ncount = (size_t)bands * (3 * (size_t)waves + 3);
+    // ... then, with MRT_SECONDARY_NEE_SUN, [band][wave] shadow-queue sizes and [band][wave] their work counters
+    const size_t ncount = (size_t)bands * (3 * (size_t)waves + 3) + (nee ? 2 * (size_t)bands * waves : 0);
+    if (nee)
+        for (int q = 0; q < 3; q++) MRT_TRY(dev_reserve(ctx, ctx->shadow_q[q], npix));
     MRT_TRY(dev_reserve(ctx, ctx->queue_counts, ncount));
     MRT_TRY(reserve_visit_counters(ctx));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->queue_counts.p, 0, sizeof(uint32_t) * ncount, ctx->stream));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
     ctx->num_queue_counts = bands * (waves + 1);
+    ctx->shadow_counts_at = nee ? (uint32_t)(bands * (3 * (size_t)waves + 3)) : 0u;  // mrt_stats: shadow rays are secondary rays
+    ctx->num_shadow_counts = nee ? bands * waves : 0u;
     if (bands > 1) {
         for (uint32_t b = 0; b < bands; b++) {
             if (!ctx->band_stream[b]) {
@@ -1279,6 +1354,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     P.bounces = bounces;
     P.accumulate = ((flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum && !frame_sum) ? 1 : 0;
     P.part = ctx->part;
+    P.ext = ext;
     sa.bvh = make_bvh(ctx);
     sa.A = ctx->atmo;
     sa.luts = SkyLuts{ctx->trans_f.p, nullptr, ctx->view_f.p};
@@ -1308,6 +1384,13 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         sa.npix = bpix;
         P.pixel_base = p0;
         const unsigned shade_grid = div_up(bpix, 256), tgrid = trace_grid(ctx, bpix);
+        uint32_t* const sh_counts = nee ? ctx->queue_counts.p + ctx->shadow_counts_at + (size_t)band * waves : nullptr;
+        uint32_t* const sh_work = nee ? ctx->queue_counts.p + ctx->shadow_counts_at + (size_t)bands * waves + (size_t)band * waves : nullptr;
+        if (nee) {
+            sa.sh_o = ctx->shadow_q[0].p + p0;
+            sa.sh_d = ctx->shadow_q[1].p + p0;
+            sa.sh_c = ctx->shadow_q[2].p + p0;
+        }
         uint32_t wave = 0;
         for (uint32_t s = 0; s < spp; s++) {
             P.first_sample = s == 0;
@@ -1317,10 +1400,19 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
             sa.out_o = ray_o[q];
             sa.out_d = ray_d[q];
             sa.out_count = qcounts + wave;
+            sa.sh_count = nee ? sh_counts + wave : nullptr;
             k_shade<true><<<shade_grid, 256, 0, st>>>(sa, nullptr);
             MRT_LAUNCHED(ctx);
             for (uint32_t b = 1; b <= bounces; b++) {
                 const uint32_t* in_count = qcounts + wave;
+                if (nee) {
+                    // the shadow rays of the vertex just shaded: any-hit traversal, free rays add their sun light to the
+                    // accumulator; on the same stream, i.e. before the shade stage below touches the same pixels
+                    ShadowJob SJ{sa.sh_o, sa.sh_d, sa.sh_c, sh_counts + wave, sa.accum};
+                    k_trace<ShadowJob><<<tgrid, TRACE_BLOCK, 0, st>>>(SJ, sa.bvh, sh_work + wave, ctx->visit_counters.p + 4,
+                                                                      ctx->opt_count_visits, ctx->total_rays.p, 0ull);
+                    MRT_LAUNCHED(ctx);
+                }
                 const bool timed = ctx->opt_trace_timing && ctx->trace_ev_used < kMaxTimedLaunches;
                 while (timed && ctx->trace_ev.size() < 2 * (size_t)(ctx->trace_ev_used + 1)) {
                     cudaEvent_t e;
@@ -1359,6 +1451,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
                 sa.out_o = ray_o[q ^ 1];
                 sa.out_d = ray_d[q ^ 1];
                 sa.out_count = qcounts + (wave + 1 < waves ? wave + 1 : waves);
+                sa.sh_count = nee ? sh_counts + (wave + 1 < waves ? wave + 1 : 0) : nullptr;  // the last vertex emits none
                 if (fused) {
                     k_trace_shade<<<tgrid, TRACE_BLOCK, 0, st>>>(J, sa.bvh, work_counters + wave, ctx->visit_counters.p + 4,
                                                                  ctx->opt_count_visits, ctx->total_rays.p, extra, sa, shade_counters + wave);

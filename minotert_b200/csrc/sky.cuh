@@ -76,8 +76,9 @@ MRT_D float3 sky_sun_luminance(const mrt_atmosphere_params& A, const SkyLuts& L,
     return f3s(0.0f);
 }
 
-// secondaryRays.comp:36-58 (+ skyAccess.glsl:87-117 inlined)
-MRT_D float3 sky_color(const mrt_atmosphere_params& A, const SkyLuts& L, float3 cameraPos, float3 dir) {
+// secondaryRays.comp:36-58 (+ skyAccess.glsl:87-117 inlined).  with_sun = false: the sky-view term only (bounce rays of
+// a path whose sun light comes from shadow rays, MRT_SECONDARY_NEE_SUN)
+MRT_D float3 sky_color(const mrt_atmosphere_params& A, const SkyLuts& L, float3 cameraPos, float3 dir, bool with_sun = true) {
     float3 worldPos = cameraPos + f3(0.0f, 0.0f, A.bottomRadius);
     float3 up = normalize3(worldPos);
     float cosZen = dot3(dir, up);
@@ -110,6 +111,39 @@ MRT_D float3 sky_color(const mrt_atmosphere_params& A, const SkyLuts& L, float3 
     u = sky_unit_to_sub_uv(u, (float)MRT_VIEW_W);
     v = sky_unit_to_sub_uv(v, (float)MRT_VIEW_H);
     float3 skyView = lut_bilinear(L.view, MRT_VIEW_W, MRT_VIEW_H, u, v, true);
+    if (!with_sun) return skyView;
     float3 sun = sky_sun_luminance(A, L, worldPos, dir, sunDir, sunIll) * (f3s(120000.0f) / sunIll);
     return skyView + sun;
+}
+
+// ---- the sun as a sampled light (contract: oracle/minote_oracle.c sun_centre_radiance, nee_sun_sample) ----
+// radiance of the sun's centre seen from pos: sky_sun_luminance without the disc test and the limb factor, times the
+// 120000 / illuminance scale of sky_color; zero when the centre direction meets the ground sphere
+MRT_D float3 sky_sun_centre_radiance(const mrt_atmosphere_params& A, const SkyLuts& L, float3 pos) {
+    const float3 sunDir = f3(-0.435286462f, 0.818654716f, 0.374606609f);
+    const float3 sunIll = f3s(8.0f);
+    float3 worldPos = pos + f3(0.0f, 0.0f, A.bottomRadius);
+    if (sky_ray_sphere_nearest(worldPos, sunDir, f3s(0.0f), A.bottomRadius) >= 0.0f) return f3s(0.0f);
+    float2 uvUp = sky_trans_params_to_uv(A.bottomRadius, 1.0f, A.bottomRadius, A.topRadius);
+    float pHeight = length3(worldPos);
+    float3 up = worldPos / pHeight;
+    float sunZen = dot3(sunDir, up);
+    float2 uvSun = sky_trans_params_to_uv(pHeight, sunZen, A.bottomRadius, A.topRadius);
+    float3 inSpace = sunIll / lut_bilinear(L.trans, MRT_TRANS_W, MRT_TRANS_H, uvUp.x, uvUp.y, false);
+    return (inSpace * lut_bilinear(L.trans, MRT_TRANS_W, MRT_TRANS_H, uvSun.x, uvSun.y, false)) * (f3s(120000.0f) / sunIll);
+}
+// one sun sample: direction uniform in solid angle inside the disc, weight = limb darkening * Omega / pi
+MRT_D void sky_nee_sun_sample(float u0, float u1, float3& l, float& weight) {
+    const float3 sun = f3(-0.435286462f, 0.818654716f, 0.374606609f);
+    const float SunRadius = 0.5f * 0.505f * 3.14159f / 180.0f;
+    const float oneMinusCos = 1.0f - cosf(SunRadius);
+    float cosT = 1.0f - u0 * oneMinusCos;
+    float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
+    float phi = (u1 * 2.0f) * SKY_PI;
+    float3 t = normalize3(cross3(f3(0.0f, 0.0f, 1.0f), sun));
+    float3 b = cross3(sun, t);
+    float sn, cs;
+    sincosf(phi, &sn, &cs);
+    l = normalize3((t * (cs * sinT) + b * (sn * sinT)) + sun * cosT);
+    weight = sqrtf(clampf(1.0f - u0, 0.0001f, 1.0f)) * (2.0f * oneMinusCos);
 }

@@ -68,6 +68,9 @@
 #ifndef TRACE_DRAIN_TRI
 #define TRACE_DRAIN_TRI 3    // drain phase: a triangle step runs once 1/n of the working lanes want one (measured 2..32: flat)
 #endif
+#ifndef TRACE_NODE_REPEAT
+#define TRACE_NODE_REPEAT 1  // node steps per trip round the persistent loop (A/B: 2)
+#endif
 #ifndef TRACE_POSTPONE
 #define TRACE_POSTPONE 1     // 1: a lane of the persistent loop may hold one postponed triangle group and keep taking node steps
 #endif
@@ -400,6 +403,7 @@ MRT_D void lane_tri_step(LaneState& L, const BvhDev& bvh, TraceCounters& cnt) {
 //   uint32_t Job::count() const;                          rays in this wave
 //   bool     Job::load(uint32_t i, float3& o, float3& d); false => ray i does not exist (padding)
 //   void     Job::store(uint32_t i, const TraceHit& h);
+//   static constexpr bool Job::ANY_HIT;                   true: occlusion query, the ray ends at its first hit
 // work_counter: global counter of handed-out rays (zeroed before the launch).
 template <class Job>
 MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter, TraceShared& S, TraceCounters& cnt) {
@@ -486,9 +490,31 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
 #pragma unroll 1
                 for (int k = 1; k < TRACE_TRI_PER_STEP && (L.tg.y | (PP ? L.tg2.y : 0u)); k++) lane_tri_step<PP>(L, bvh, cnt);
 #endif
+                if (Job::ANY_HIT && L.hit.prim != MRT_MISS_ID) {  // shadow rays: the first hit ends the ray
+                    L.ng.y = 0u; L.tg.y = 0u; L.tg2.y = 0u; L.sp = 0;
+                }
             }
         } else if (nmask) {
+#if TRACE_NODE_REPEAT > 1 && TRACE_POSTPONE
+            // several node steps per trip round the loop: the refill check, the two ballots and the step choice (~35 warp
+            // instructions with all 32 lanes) are paid once per TRACE_NODE_REPEAT node steps; a lane takes the next step
+            // (popping its stack if the group is used up) as long as it has a free triangle slot
+            if (want_node) {
+                lane_node_step<true>(L, bvh, S, spill, cnt, TRACE_DRAIN_PREFETCH && exhausted);
+#pragma unroll 1
+                for (int rep = 1; rep < TRACE_NODE_REPEAT; rep++) {
+                    if (L.tg.y && L.tg2.y) break;
+                    if (!(L.ng.y & 0xFF000000u)) {
+                        if (L.sp == 0) break;
+                        L.sp--;
+                        L.ng = L.sp < TRACE_SM_STACK ? sm[L.sp * TRACE_BLOCK] : spill[L.sp - TRACE_SM_STACK];
+                    }
+                    lane_node_step<true>(L, bvh, S, spill, cnt, TRACE_DRAIN_PREFETCH && exhausted);
+                }
+            }
+#else
             if (want_node) lane_node_step<TRACE_POSTPONE != 0>(L, bvh, S, spill, cnt, TRACE_DRAIN_PREFETCH && exhausted);
+#endif
         }
     }
 }

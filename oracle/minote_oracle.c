@@ -912,10 +912,11 @@ static v3 getSunLuminance(const sky_ctx* S, v3 worldPos, v3 worldDir, v3 sunDire
     return V(0, 0, 0);
 }
 
-/* src/gpu/secondaryRays.comp:36-58 */
-static v3 sky_color(const sky_ctx* S, v3 dir) {
+/* src/gpu/secondaryRays.comp:36-58; `pos` is C.cameraPos there (the SKY_AT_HIT extension passes the ray origin),
+ * parts: bit 0 the sky-view LUT term, bit 1 the sun disc */
+static v3 sky_color_at(const sky_ctx* S, v3 pos, v3 dir, int parts) {
     const orc_atmosphere_params* A = S->A;
-    v3 worldPos = vadd(S->cameraPos, V(0.0f, 0.0f, A->bottomRadius));
+    v3 worldPos = vadd(pos, V(0.0f, 0.0f, A->bottomRadius));
     v3 upVector = vnorm(worldPos);
     float viewZenithCosAngle = vdot(dir, upVector);
     float viewHeight = vlen(worldPos);
@@ -932,10 +933,52 @@ static v3 sky_color(const sky_ctx* S, v3 dir) {
     skyViewLutParamsToUv(intersectGround, viewZenithCosAngle, lightViewCosAngle, (float)S->view.w,
                          (float)S->view.h, viewHeight, &u, &v, A->bottomRadius);
     v3 skyView = tex_bilinear(&S->view, u, v, 1);
+    if (parts == 1) return skyView;
     v3 sun = vmul(getSunLuminance(S, worldPos, dir, sunDirection, sunIlluminance),
                   vdiv(vsplat(120000.0f), sunIlluminance));
     return vadd(skyView, sun);
 }
+static v3 sky_color(const sky_ctx* S, v3 dir) { return sky_color_at(S, S->cameraPos, dir, 3); }
+
+/* ---- SURVEY 8f-4 extension (no reference counterpart; contract written here): the sun as a sampled light ----
+ * Radiance of the sun's centre seen from `pos` through the atmosphere: getSunLuminance's expression without the disc
+ * test and the limb factor, times the 120000 / illuminance scale of skyColor (secondaryRays.comp:54-55).  Zero when the
+ * sun's centre direction meets the ground sphere. */
+static v3 sun_centre_radiance(const sky_ctx* S, v3 pos) {
+    const orc_atmosphere_params* A = S->A;
+    const v3 sunDirection = V(-0.435286462f, 0.818654716f, 0.374606609f);
+    const v3 sunIlluminance = V(8.0f, 8.0f, 8.0f);
+    v3 worldPos = vadd(pos, V(0.0f, 0.0f, A->bottomRadius));
+    if (raySphereIntersectNearest(worldPos, sunDirection, V(0, 0, 0), A->bottomRadius) >= 0.0f) return V(0, 0, 0);
+    float uUp, vUp, uSun, vSun;
+    lutTransmittanceParamsToUv(A->bottomRadius, 1.0f, &uUp, &vUp, A->bottomRadius, A->topRadius);
+    float pHeight = vlen(worldPos);
+    v3 upVector = vdivs(worldPos, pHeight);
+    float sunZenithCosAngle = vdot(sunDirection, upVector);
+    lutTransmittanceParamsToUv(pHeight, sunZenithCosAngle, &uSun, &vSun, A->bottomRadius, A->topRadius);
+    v3 inSpace = vdiv(sunIlluminance, tex_bilinear(&S->trans, uUp, vUp, 0));
+    return vmul(vmul(inSpace, tex_bilinear(&S->trans, uSun, vSun, 0)), vdiv(vsplat(120000.0f), sunIlluminance));
+}
+
+/* One sun sample from two uniform numbers: direction l uniform in solid angle inside the sun's cone (half-angle
+ * 0.5 * 0.505 deg, the disc of getSunLuminance), and the scalar weight  limb(u0) * Omega / pi  that multiplies
+ * throughput * sun_centre_radiance * max(0, n.l):  limb darkening sqrt(clamp(1 - r^2, 1e-4, 1)) with r^2 = u0 (the
+ * squared radius ratio of a cone sample with cos(theta) = 1 - u0 (1 - cos R), to O(R^2)), Omega = 2 pi (1 - cos R). */
+static void nee_sun_sample(float u0, float u1, v3* l, float* weight) {
+    const v3 sun = V(-0.435286462f, 0.818654716f, 0.374606609f);
+    const float SunRadius = 0.5f * 0.505f * 3.14159f / 180.0f;
+    const float oneMinusCos = 1.0f - cosf(SunRadius);
+    float cosT = 1.0f - u0 * oneMinusCos;
+    float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
+    float phi = (u1 * 2.0f) * 3.14159274101257324f;
+    v3 t = vnorm(vcross(V(0.0f, 0.0f, 1.0f), sun)); /* the sun is never vertical: |sun.z| = 0.37 */
+    v3 b = vcross(sun, t);
+    v3 dir = vadd(vadd(vscale(t, cosf(phi) * sinT), vscale(b, sinf(phi) * sinT)), vscale(sun, cosT));
+    *l = vnorm(dir);
+    float limb = sqrtf(clampf(1.0f - u0, 0.0001f, 1.0f));
+    *weight = limb * ((2.0f * oneMinusCos)); /* Omega / pi = 2 (1 - cos R) */
+}
+
 
 static sky_ctx sky_ctx_make(const orc_atmosphere_params* A, const uint16_t* trans, const uint32_t* skyView,
                             const float cameraPos[3]) {
@@ -947,6 +990,19 @@ static sky_ctx sky_ctx_make(const orc_atmosphere_params* A, const uint16_t* tran
     return S;
 }
 static void sky_ctx_free(sky_ctx* S) { tex_free(&S->trans); tex_free(&S->view); }
+
+void orc_nee_sun_sample(float u0, float u1, float l[3], float* weight) {
+    v3 d;
+    nee_sun_sample(u0, u1, &d, weight);
+    l[0] = d.x; l[1] = d.y; l[2] = d.z;
+}
+void orc_sun_centre_radiance(const orc_atmosphere_params* p, const uint16_t* trans, const uint32_t* skyView, const float pos[3],
+                             float out[3]) {
+    sky_ctx S = sky_ctx_make(p, trans, skyView, pos);
+    v3 e = sun_centre_radiance(&S, v3p(pos));
+    out[0] = e.x; out[1] = e.y; out[2] = e.z;
+    sky_ctx_free(&S);
+}
 
 void orc_sky_color(const orc_atmosphere_params* p, const uint16_t* trans, const uint32_t* skyView,
                    const float cameraPos[3], const float dir[3], float out[3]) {
@@ -1715,7 +1771,28 @@ void orc_render_tris(const orc_scene* s, uint32_t w, uint32_t h, const orc_prima
                      const orc_atmosphere_params* atmo, const uint16_t* trans, const uint32_t* skyView,
                      uint32_t spp, uint32_t bounces, int use_bvh, uint32_t y0, uint32_t y1, float* accum,
                      uint32_t* visibility, uint64_t* rays_out) {
+    orc_render_tris_ext(s, w, h, pc, sc, blueNoise, bnW, bnH, atmo, trans, skyView, spp, bounces, use_bvh, y0, y1, accum,
+                        visibility, rays_out, 0u);
+}
+
+/* The native path tracer with the SURVEY 8f-4 extensions (ext = 0: exactly secondaryRays.comp:64-135 per pixel).
+ *  ORC_EXT_NEE_SUN    at every hit vertex i < bounces, BEFORE the bounce's two random numbers, two more rotated random
+ *                     numbers (u0 with the pixel's x rotation, u1 with its y rotation) pick a direction l inside the sun's
+ *                     disc (nee_sun_sample); if n.l > 0 a shadow ray from the bounce origin (pos + n * 1e-6) is tested for
+ *                     ANY hit with t >= 0, and if there is none  throughput(after this vertex' albedo) * E * (n.l * weight)
+ *                     is added to the pixel, E = sun_centre_radiance at the sky position.  Bounce rays that escape then add
+ *                     the sky-view term only (the disc they would otherwise hit by chance is what the shadow rays
+ *                     integrate); a PRIMARY ray that escapes still sees the disc.  Shadow rays count as secondary rays.
+ *  ORC_EXT_SKY_AT_HIT the sky is evaluated at the origin of the escaping ray (and E at the shaded point) instead of at the
+ *                     camera (secondaryRays.comp:37 uses C.cameraPos for every vertex). */
+void orc_render_tris_ext(const orc_scene* s, uint32_t w, uint32_t h, const orc_primary_constants* pc,
+                         const orc_secondary_constants* sc, const uint8_t* blueNoise, uint32_t bnW, uint32_t bnH,
+                         const orc_atmosphere_params* atmo, const uint16_t* trans, const uint32_t* skyView,
+                         uint32_t spp, uint32_t bounces, int use_bvh, uint32_t y0, uint32_t y1, float* accum,
+                         uint32_t* visibility, uint64_t* rays_out, uint32_t ext) {
+    const int nee = (ext & ORC_EXT_NEE_SUN) != 0, at_hit = (ext & ORC_EXT_SKY_AT_HIT) != 0;
     sky_ctx S = sky_ctx_make(atmo, trans, skyView, sc->cameraPos);
+    const v3 E_cam = sun_centre_radiance(&S, S.cameraPos);
     uint64_t prim = 0, sec = 0;
 #pragma omp parallel for schedule(dynamic, 2) reduction(+ : prim, sec)
     for (int y = (int)y0; y < (int)y1; y++)
@@ -1739,9 +1816,11 @@ void orc_render_tris(const orc_scene* s, uint32_t w, uint32_t h, const orc_prima
                 v3 thr = V(1, 1, 1);
                 uint32_t hid = h0.id;
                 v3 hpos = p0, hn = n0;
+                v3 sky_pos = S.cameraPos;  /* where the sky is evaluated for the ray that escapes next */
                 for (uint32_t i = 0; i < bounces + 1u; i++) {
                     if (i > 0) {
                         v3 ro = vadd(hpos, vscale(hn, 0.000001f));
+                        if (at_hit) sky_pos = ro;
                         float r0 = rotated_random(&seed, rotx);
                         float r1 = rotated_random(&seed, roty);
                         v3 rd = vnorm(vadd(hn, random_sphere_point(r0 * 2.0f - 1.0f, r1 * 2.0f - 1.0f)));
@@ -1757,8 +1836,25 @@ void orc_render_tris(const orc_scene* s, uint32_t w, uint32_t h, const orc_prima
                     }
                     if (hid != NONE_ID) {
                         thr = vmul(thr, v3p(&s->albedo[3 * (size_t)hid]));
+                        if (nee && i < bounces) {
+                            float u0 = rotated_random(&seed, rotx);
+                            float u1 = rotated_random(&seed, roty);
+                            v3 l;
+                            float wgt;
+                            nee_sun_sample(u0, u1, &l, &wgt);
+                            float ndotl = vdot(hn, l);
+                            if (ndotl > 0.0f) {
+                                v3 so = vadd(hpos, vscale(hn, 0.000001f));
+                                v3 E = at_hit ? sun_centre_radiance(&S, so) : E_cam;
+                                if (E.x > 0.0f || E.y > 0.0f || E.z > 0.0f) {
+                                    sec++;
+                                    hit_t sh = closest_hit(s, so, l, use_bvh); /* any hit <=> a closest hit exists */
+                                    if (sh.id == NONE_ID) color = vadd(color, vscale(vmul(thr, E), ndotl * wgt));
+                                }
+                            }
+                        }
                     } else {
-                        color = vadd(color, vmul(thr, sky_color(&S, hn)));
+                        color = vadd(color, vmul(thr, sky_color_at(&S, sky_pos, hn, (nee && i > 0) ? 1 : 3)));
                         break;
                     }
                 }

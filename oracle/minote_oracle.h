@@ -236,6 +236,19 @@ void orc_render_tris(const orc_scene* s, uint32_t w, uint32_t h, const orc_prima
                      const uint32_t* skyView, uint32_t spp, uint32_t bounces, int use_bvh,
                      uint32_t y0, uint32_t y1, float* accum, uint32_t* visibility,
                      uint64_t* rays_out);
+/* SURVEY 8f-4 extensions of the native path tracer (contract in minote_oracle.c at orc_render_tris_ext) */
+#define ORC_EXT_NEE_SUN 1u
+#define ORC_EXT_SKY_AT_HIT 2u
+void orc_render_tris_ext(const orc_scene* s, uint32_t w, uint32_t h, const orc_primary_constants* pc,
+                         const orc_secondary_constants* sc, const uint8_t* blueNoise, uint32_t bnW,
+                         uint32_t bnH, const orc_atmosphere_params* atmo, const uint16_t* trans,
+                         const uint32_t* skyView, uint32_t spp, uint32_t bounces, int use_bvh,
+                         uint32_t y0, uint32_t y1, float* accum, uint32_t* visibility,
+                         uint64_t* rays_out, uint32_t ext);
+/* one sun sample: direction inside the disc and the weight limb * Omega / pi; the sun centre's radiance seen from pos */
+void orc_nee_sun_sample(float u0, float u1, float l[3], float* weight);
+void orc_sun_centre_radiance(const orc_atmosphere_params* p, const uint16_t* trans, const uint32_t* skyView,
+                             const float pos[3], float out[3]);
 /* accum (RGBA32F sums, w = spp) -> RGBA32F average */
 void orc_resolve(uint32_t npixels, const float* accum, float* color32);
 

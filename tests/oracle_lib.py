@@ -148,6 +148,9 @@ def lib():
         "orc_scene_closest_hit": (C.c_uint32, [C.c_void_p, f32p, f32p, C.c_int, f32p, f32p, f32p]),
         "orc_primary_rays_tris": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.c_int, C.c_uint32, C.c_uint32, u32p, u16p, u16p, u16p, f32p]),
         "orc_render_tris": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.POINTER(SecondaryConstants), u8p, C.c_uint32, C.c_uint32, C.POINTER(AtmosphereParams), u16p, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, f32p, u32p, u64p]),
+        "orc_render_tris_ext": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.POINTER(SecondaryConstants), u8p, C.c_uint32, C.c_uint32, C.POINTER(AtmosphereParams), u16p, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, f32p, u32p, u64p, C.c_uint32]),
+        "orc_nee_sun_sample": (None, [C.c_float, C.c_float, f32p, f32p]),
+        "orc_sun_centre_radiance": (None, [C.POINTER(AtmosphereParams), u16p, u32p, f32p, f32p]),
         "orc_resolve": (None, [C.c_uint32, f32p, f32p]),
         "orc_num_threads": (C.c_int, []),
         "orc_set_num_threads": (None, [C.c_int]),
@@ -372,16 +375,32 @@ class Scene:
                                     _p(t, C.c_float))
         return vis, depth, normal, motion, t
 
-    def render(self, w, h, pc, sc, bn, atmo, trans, view, spp, bounces, use_bvh=True, rows=None, accum=None):
+    def render(self, w, h, pc, sc, bn, atmo, trans, view, spp, bounces, use_bvh=True, rows=None, accum=None, ext=0):
         y0, y1 = rows if rows else (0, h)
         if accum is None:
             accum = np.zeros((h, w, 4), np.float32)
         vis = np.full((h, w), NONE_ID, np.uint32)
         rays = (C.c_uint64 * 2)()
-        lib().orc_render_tris(self.h, w, h, C.byref(pc), C.byref(sc), _p(bn, C.c_uint8), bn.shape[1], bn.shape[0],
-                              C.byref(atmo), _p(trans, C.c_uint16), _p(view, C.c_uint32), spp, bounces, int(use_bvh),
-                              y0, y1, _p(accum, C.c_float), _p(vis, C.c_uint32), rays)
+        lib().orc_render_tris_ext(self.h, w, h, C.byref(pc), C.byref(sc), _p(bn, C.c_uint8), bn.shape[1], bn.shape[0],
+                                  C.byref(atmo), _p(trans, C.c_uint16), _p(view, C.c_uint32), spp, bounces, int(use_bvh),
+                                  y0, y1, _p(accum, C.c_float), _p(vis, C.c_uint32), rays, ext)
         return accum, vis, (rays[0], rays[1])
+
+
+EXT_NEE_SUN, EXT_SKY_AT_HIT = 1, 2
+
+
+def nee_sun_sample(u0, u1):
+    l = np.zeros(3, np.float32)
+    w = C.c_float()
+    lib().orc_nee_sun_sample(float(u0), float(u1), _p(l, C.c_float), C.byref(w))
+    return l, w.value
+
+
+def sun_centre_radiance(atmo, trans, view, pos):
+    out = np.zeros(3, np.float32)
+    lib().orc_sun_centre_radiance(C.byref(atmo), _p(trans, C.c_uint16), _p(view, C.c_uint32), f3(pos), _p(out, C.c_float))
+    return out
 
 
 def resolve(accum):
