@@ -97,6 +97,7 @@ typedef enum {
     MRT_BUF_BVH_TRIS = 13,       /* ... and its triangles in leaf order, 3 x float4 each (v0.w = primitive id) */
     MRT_BUF_TEMPORAL = 14,       /* RGBA32F 16 B/px (rgb, 1): output of mrt_temporal_accumulate = next frame's history */
     MRT_BUF_TEMPORAL_COUNT = 15, /* R32F 4 B/px: history length of each pixel after mrt_temporal_accumulate (1 = reset) */
+    MRT_BUF_AERIAL = 16,         /* RGBA16F 32 x 32 x 32 (x fastest): aerial-perspective volume of mrt_sky_aerial_perspective */
     MRT_BUF_COUNT_
 } mrt_buffer_id;
 
@@ -117,6 +118,9 @@ typedef enum {
                                      * ray to hit a 0.5 degree disc.  Shadow rays count as secondary rays. */
 #define MRT_SECONDARY_SKY_AT_HIT 16u /* the sky is evaluated at the origin of the escaping ray (the shaded point), not at
                                      * the camera position as secondaryRays.comp:37 does for every vertex */
+#define MRT_SECONDARY_AERIAL 32u    /* aerial perspective between the camera and the primary hit from the volume of
+                                     * mrt_sky_aerial_perspective: each sample's throughput starts at 1 - AP.a and AP.rgb
+                                     * is added once per sample (pixels whose primary ray escapes are left alone) */
 #define MRT_SECONDARY_FRAME_SUM 4u  /* triangle scenes: this call's samples are summed into the context's own per-frame
                                      * buffer, starting from zero, and MRT_BUF_ACCUM is left alone; mrt_accum_commit
                                      * then adds the frame to an accumulator.  Frames rendered by different contexts
@@ -213,6 +217,13 @@ int mrt_atmosphere(mrt_context* ctx, const mrt_atmosphere_params* params);
 /* Sky::createView(atmo, probePos) with the push constants of sky.ixx:239-250 */
 int mrt_sky_view(mrt_context* ctx, const float probePos[3], const float sunDirection[3],
                  const float sunIlluminance[3]);
+/* Aerial-perspective camera volume (the reference declares it -- Sky::AerialPerspectiveFormat / Size, sky.ixx:190-191,
+ * AP_KM_PER_SLICE and the depth<->slice maps, skyAccess.glsl:9,119-125 -- and never builds it).  32^3
+ * froxels over the view of the camera whose primary constants are given: luminance scattered towards the camera and
+ * 1 - transmittance up to depth ((z + 0.5) / 32)^2 * 128 km, RGBA16F.  Needs mrt_atmosphere.  Applied by
+ * mrt_secondary_rays(MRT_SECONDARY_AERIAL); readable as MRT_BUF_AERIAL. */
+int mrt_sky_aerial_perspective(mrt_context* ctx, const mrt_primary_constants* c, const float cameraPos[3],
+                               const float sunDirection[3], const float sunIlluminance[3]);
 
 /* ---- partition (multi-GPU tile mode; default rank 0 of 1) ----
  * Image rows are grouped into slabs of slab_rows rows; slab j belongs to rank j % nranks.

@@ -18,8 +18,10 @@ MISS_ID = 0xFFFFFFFF
 (BUF_VISIBILITY, BUF_DEPTH, BUF_NORMAL, BUF_MOTION, BUF_COLOR, BUF_ACCUM, BUF_LDR, BUF_TRANSMITTANCE,
  BUF_MULTISCATTERING, BUF_SKY_VIEW, BUF_HIT_T, BUF_DENOISED, BUF_BVH_NODES, BUF_BVH_TRIS, BUF_TEMPORAL,
  BUF_TEMPORAL_COUNT) = range(16)
+BUF_AERIAL = 16
 BUILD_FULL, BUILD_REFIT = 0, 1
 SECONDARY_ACCUMULATE, SECONDARY_SORT_RAYS, SECONDARY_FRAME_SUM, SECONDARY_NEE_SUN, SECONDARY_SKY_AT_HIT = 1, 2, 4, 8, 16
+SECONDARY_AERIAL = 32
 TEMPORAL_RESET = 1
 TONEMAP = {"linear": 0, "reinhard": 1, "hable": 2, "aces": 3, "uchimura": 4, "amd": 5}
 DENOISE = {"none": 0, "bilateral": 1}   # Renderer_impl::denoise modes (src/gfx/renderer.ixx:129-132)
@@ -62,7 +64,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "mrt_abi_version", "mrt_create", "mrt_destroy", "mrt_last_error", "mrt_set_option", "mrt_upload_blue_noise",
     "mrt_scene_set_spheres", "mrt_scene_upload_mesh", "mrt_scene_update_positions", "mrt_scene_build",
-    "mrt_atmosphere", "mrt_sky_view", "mrt_set_partition", "mrt_partition_rows", "mrt_primary_rays",
+    "mrt_atmosphere", "mrt_sky_view", "mrt_sky_aerial_perspective", "mrt_set_partition", "mrt_partition_rows", "mrt_primary_rays",
     "mrt_secondary_rays", "mrt_tonemap", "mrt_buffer", "mrt_readback", "mrt_sync", "mrt_stats_get",
     "mrt_stats_reset", "mrt_stream", "mrt_trace_rays", "mrt_partition_rows_for", "mrt_readback_async",
     "mrt_readback_wait", "mrt_denoise_bilateral", "mrt_scene_share", "mrt_temporal_accumulate",
@@ -108,6 +110,7 @@ def load():
     L.mrt_temporal_accumulate.argtypes = [vp, C.c_float, u32]
     L.mrt_atmosphere.argtypes = [vp, vp]
     L.mrt_sky_view.argtypes = [vp, f32p, f32p, f32p]
+    L.mrt_sky_aerial_perspective.argtypes = [vp, vp, f32p, f32p, f32p]
     L.mrt_set_partition.argtypes = [vp, u32, u32, u32]
     L.mrt_partition_rows.argtypes = [vp, u32, vp, C.POINTER(u32)]
     L.mrt_primary_rays.argtypes = [vp, u32, u32, vp]
@@ -242,6 +245,10 @@ class Context:
     def sky_view(self, probe_pos, sun_dir, sun_ill):
         self._ck(self.L.mrt_sky_view(self.h, _f3(probe_pos), _f3(sun_dir), _f3(sun_ill)))
 
+    def sky_aerial_perspective(self, pc, camera_pos, sun_dir=(-0.435286462, 0.818654716, 0.374606609), sun_ill=(8.0, 8.0, 8.0)):
+        """mrt_sky_aerial_perspective: the 32^3 camera volume for the camera of the primary constants pc."""
+        self._ck(self.L.mrt_sky_aerial_perspective(self.h, C.cast(C.byref(pc), C.c_void_p), _f3(camera_pos), _f3(sun_dir), _f3(sun_ill)))
+
     def set_partition(self, rank, nranks, slab_rows=8):
         self._ck(self.L.mrt_set_partition(self.h, rank, nranks, slab_rows))
 
@@ -294,6 +301,8 @@ class Context:
             dt, shape = np.uint32, (108, 192)
         elif buf == BUF_TRANSMITTANCE:
             dt, shape = np.uint16, (64, 256, 4)
+        elif buf == BUF_AERIAL:
+            dt, shape = np.uint16, (32, 32, 32, 4)
         else:
             dt, shape = np.uint16, (32, 32, 4)
         if out is None:

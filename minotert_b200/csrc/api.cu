@@ -62,6 +62,7 @@ int buffer_info(mrt_context* ctx, int id, void** p, size_t* bytes) {
     case MRT_BUF_LDR: if (!ctx->have_ldr) break; *p = ctx->ldr_buf[ctx->ldr_cur].p; *bytes = n * 4; return MRT_OK;
     case MRT_BUF_TRANSMITTANCE: if (!ctx->have_atmo) break; *p = ctx->trans16.p; *bytes = (size_t)MRT_TRANS_W * MRT_TRANS_H * 8; return MRT_OK;
     case MRT_BUF_MULTISCATTERING: if (!ctx->have_atmo) break; *p = ctx->multi16.p; *bytes = (size_t)MRT_MULTI_W * MRT_MULTI_H * 8; return MRT_OK;
+    case MRT_BUF_AERIAL: if (!ctx->have_aerial) break; *p = ctx->aerial16.p; *bytes = (size_t)MRT_AERIAL_SIZE * MRT_AERIAL_SIZE * MRT_AERIAL_SIZE * 8; return MRT_OK;
     case MRT_BUF_SKY_VIEW:
         if (!ctx->have_view) break;
         if (ctx->sky_pending) {  // still being generated on the side stream: order the main stream after it
@@ -170,7 +171,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->visibility); dev_free(ctx->depth); dev_free(ctx->normal); dev_free(ctx->motion); dev_free(ctx->color16);
     dev_free(ctx->denoised); dev_free(ctx->dn_taps);
     for (int k = 0; k < 2; k++) { dev_free(ctx->tp_rgba[k]); dev_free(ctx->tp_count[k]); dev_free(ctx->tp_vis[k]); }
-    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->frame_sum); for (auto& q : ctx->shadow_q) dev_free(q); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
+    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->frame_sum); dev_free(ctx->aerial16); dev_free(ctx->aerial_f); for (auto& q : ctx->shadow_q) dev_free(q); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
     dev_free(ctx->hit0_pos); dev_free(ctx->hit0_n); dev_free(ctx->path_state);
     for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); }
     dev_free(ctx->hits); dev_free(ctx->queue_counts); dev_free(ctx->sort_keys); dev_free(ctx->sort_keys_alt);
@@ -358,6 +359,16 @@ int mrt_sky_view(mrt_context* ctx, const float probePos[3], const float sunDirec
     return MRT_OK;
 }
 
+int mrt_sky_aerial_perspective(mrt_context* ctx, const mrt_primary_constants* c, const float cameraPos[3],
+                               const float sunDirection[3], const float sunIlluminance[3]) {
+    MRT_ENTER(ctx);
+    if (!ctx->have_atmo) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_sky_aerial_perspective before mrt_atmosphere");
+    if (!c || !cameraPos || !sunDirection || !sunIlluminance) return mrt_fail(ctx, MRT_ERR_INVALID, "aerial perspective: NULL argument");
+    MRT_TRY(sky_gen_aerial(ctx, c, cameraPos, sunDirection, sunIlluminance));
+    ctx->have_aerial = true;
+    return MRT_OK;
+}
+
 int mrt_set_partition(mrt_context* ctx, uint32_t rank, uint32_t nranks, uint32_t slab_rows) {
     MRT_ENTER(ctx);
     if (nranks == 0 || rank >= nranks || slab_rows == 0) return mrt_fail(ctx, MRT_ERR_INVALID, "bad partition %u/%u slab %u", rank, nranks, slab_rows);
@@ -419,7 +430,9 @@ int mrt_secondary_rays(mrt_context* ctx, const mrt_secondary_constants* c, uint3
     if (!ctx->have_gbuffer) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays before primary rays");
     if (!ctx->have_atmo || !ctx->have_view) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: sky LUTs missing (mrt_atmosphere, mrt_sky_view)");
     if (!ctx->bn) return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: blue noise texture missing");
-    if ((flags & (MRT_SECONDARY_FRAME_SUM | MRT_SECONDARY_NEE_SUN | MRT_SECONDARY_SKY_AT_HIT)) && ctx->scene_kind != 2)
+    if ((flags & MRT_SECONDARY_AERIAL) && !ctx->have_aerial)
+        return mrt_fail(ctx, MRT_ERR_STATE, "secondary rays: MRT_SECONDARY_AERIAL before mrt_sky_aerial_perspective");
+    if ((flags & (MRT_SECONDARY_FRAME_SUM | MRT_SECONDARY_NEE_SUN | MRT_SECONDARY_SKY_AT_HIT | MRT_SECONDARY_AERIAL)) && ctx->scene_kind != 2)
         return mrt_fail(ctx, MRT_ERR_INVALID, "secondary rays: flags 0x%x are for triangle scenes", flags);
     sky_join(ctx);
     cudaEventRecord(ctx->ev[4], ctx->stream);

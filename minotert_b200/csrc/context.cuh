@@ -125,6 +125,9 @@ struct mrt_context {
     DevArray<uint16_t> trans16, multi16;
     DevArray<uint32_t> view_packed;
     DevArray<float4> trans_f, multi_f, view_f;
+    DevArray<uint16_t> aerial16;   // aerial-perspective camera volume, 32^3 RGBA16F (mrt_sky_aerial_perspective)
+    DevArray<float4> aerial_f;     // ... decoded for the trilinear taps
+    bool have_aerial = false;
 
     // frame
     Partition part{0, 1, 8};
@@ -239,6 +242,7 @@ int spheres_primary(mrt_context* ctx);
 int spheres_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags);
 int denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float threshold, float nearPlane, uint32_t frameCounter);
 int temporal_accumulate(mrt_context* ctx, float maxHistory, bool reset);
+int sky_gen_aerial(mrt_context* ctx, const mrt_primary_constants* c, const float cameraPos[3], const float sunDir[3], const float sunIll[3]);
 int tonemap_run(mrt_context* ctx, int mode, float exposure, const float* params, uint32_t nparams, int source);
 int bvh_build_full(mrt_context* ctx);
 int bvh_refit(mrt_context* ctx);

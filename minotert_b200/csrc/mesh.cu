@@ -692,7 +692,8 @@ struct ShadeParams {
     int accumulate;
     Partition part;
     uint32_t pixel_base; // FIRST: vertex k of this launch is pixel pixel_base + k (bands of the image, see mesh_secondary)
-    uint32_t ext;        // MRT_SECONDARY_NEE_SUN | MRT_SECONDARY_SKY_AT_HIT
+    uint32_t ext;        // MRT_SECONDARY_NEE_SUN | MRT_SECONDARY_SKY_AT_HIT | MRT_SECONDARY_AERIAL
+    uint32_t H;          // image height (aerial-perspective lookup)
 };
 
 // Everything the shade stage reads and writes (passed by value to the kernels).
@@ -715,6 +716,8 @@ struct ShadeArgs {
     float4* out_d;
     uint32_t* out_count;
     unsigned long long* overflow; // error counter (mrt_stats.stack_overflows) for a fused worker that gave up waiting
+    const float4* aerial;         // MRT_SECONDARY_AERIAL: decoded camera volume; hit_t = distance of the primary hit
+    const float* hit_t;
     float4* sh_o;                 // MRT_SECONDARY_NEE_SUN: shadow-ray queue of this vertex (origin|pixel, direction, contribution)
     float4* sh_d;
     float4* sh_c;
@@ -746,9 +749,17 @@ MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
             prim = __float_as_uint(hp.w);
             thr = f3s(1.0f);
             rng = P.first_sample ? P.seed : __float_as_uint(a.path_state[pixel].w);
-            if (P.first_sample) {
-                float4 acc = P.accumulate ? a.accum[pixel] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                acc.w += (float)P.spp;
+            const bool ap_on = (P.ext & MRT_SECONDARY_AERIAL) && prim != MRT_MISS_ID;
+            if (P.first_sample || ap_on) {
+                float4 acc = (!P.first_sample || P.accumulate) ? a.accum[pixel] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (P.first_sample) acc.w += (float)P.spp;
+                if (ap_on) {  // contract: oracle ORC_EXT_AERIAL -- the sample starts behind the air between camera and hit
+                    const uint32_t lr = pixel / P.W, x = pixel - lr * P.W;
+                    const float4 ap = sky_aerial_lookup(a.aerial, ((float)x + 0.5f) / (float)P.W,
+                                                        ((float)partition_local_to_y(P.part, lr) + 0.5f) / (float)P.H, __ldg(&a.hit_t[pixel]));
+                    thr = f3s(1.0f - ap.w);
+                    acc = make_float4(acc.x + ap.x, acc.y + ap.y, acc.z + ap.z, acc.w);
+                }
                 a.accum[pixel] = acc;
             }
         } else {
@@ -1245,7 +1256,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     const uint32_t npix = (uint32_t)ctx->npix;
     const bool frame_sum = (flags & MRT_SECONDARY_FRAME_SUM) != 0;  // samples go to the per-frame buffer (mrt_accum_commit)
     if (frame_sum) MRT_TRY(dev_reserve(ctx, ctx->frame_sum, npix));
-    const uint32_t ext = flags & (MRT_SECONDARY_NEE_SUN | MRT_SECONDARY_SKY_AT_HIT);
+    const uint32_t ext = flags & (MRT_SECONDARY_NEE_SUN | MRT_SECONDARY_SKY_AT_HIT | MRT_SECONDARY_AERIAL);
     const bool nee = (ext & MRT_SECONDARY_NEE_SUN) != 0;
     // the sky extensions live in the wavefront's shade stage only
     const bool path_kernel = ctx->opt_path_kernel != 0 && spp < 65536u && bounces < 65535u && ext == 0;
@@ -1355,6 +1366,9 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     P.accumulate = ((flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum && !frame_sum) ? 1 : 0;
     P.part = ctx->part;
     P.ext = ext;
+    P.H = ctx->H;
+    sa.aerial = ctx->aerial_f.p;
+    sa.hit_t = ctx->hit_t.p;
     sa.bvh = make_bvh(ctx);
     sa.A = ctx->atmo;
     sa.luts = SkyLuts{ctx->trans_f.p, nullptr, ctx->view_f.p};

@@ -3,6 +3,7 @@
 // and integrateScatteredLuminance (src/gpu/sky/sky.glsl:176-343); host side mirrors
 // Atmosphere::Atmosphere / Sky::createView (src/gfx/modules/sky.ixx:91-176,199-262).
 #include "context.cuh"
+#include "shading.cuh"
 
 namespace {
 
@@ -40,7 +41,7 @@ MRT_D float rayleigh_phase(float cosTheta) {
     return factor * (1.0f + cosTheta * cosTheta);
 }
 
-struct Scatter { float3 L, opticalDepth, multiScatAs1; };
+struct Scatter { float3 L, opticalDepth, transmittance, multiScatAs1; };
 
 // sky.glsl:176-343.  HAS_TRANS / HAS_MULTI stand for the S_TRANSMITTANCE / S_MULTISCATTERING macros.
 template <bool HAS_TRANS, bool HAS_MULTI>
@@ -48,7 +49,7 @@ MRT_D Scatter integrate_scattered(const mrt_atmosphere_params& A, const SkyLuts&
                                   float3 sunDir, bool ground, float sampleCountIni, bool variableSampleCount,
                                   bool mieRayPhase, float tMaxMax, float3 sunIll) {
     Scatter result;
-    result.L = result.opticalDepth = result.multiScatAs1 = f3s(0.0f);
+    result.L = result.opticalDepth = result.transmittance = result.multiScatAs1 = f3s(0.0f);
     float3 earthO = f3s(0.0f);
     float tBottom = sky_ray_sphere_nearest(worldPos, worldDir, earthO, A.bottomRadius);
     float tTop = sky_ray_sphere_nearest(worldPos, worldDir, earthO, A.topRadius);
@@ -152,6 +153,7 @@ MRT_D Scatter integrate_scattered(const mrt_atmosphere_params& A, const SkyLuts&
     }
     result.L = L;
     result.opticalDepth = opticalDepth;
+    result.transmittance = throughput;
     return result;
 }
 
@@ -285,7 +287,79 @@ __global__ void k_gen_view(mrt_atmosphere_params A, SkyLuts luts, float3 probePo
     outf[y * MRT_VIEW_W + x] = make_float4(d.x, d.y, d.z, 1.0f);
 }
 
+// Aerial-perspective camera volume (the reference declares it -- sky.ixx:190-191, skyAccess.glsl:9,119-125 --
+// and never builds it).  Contract and derivation: oracle/minote_oracle.c orc_gen_aerial_perspective.  One thread per
+// froxel; RGBA16F (scattered luminance, 1 - mean transmittance) + a decoded float4 copy for the trilinear taps.
+__global__ void __launch_bounds__(256) k_gen_aerial(mrt_atmosphere_params A, SkyLuts luts, RayGen gen, float3 cameraPos, float3 sunDirection,
+                                                    float3 sunIll, uint16_t* out16, float4* outf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= MRT_AERIAL_SIZE * MRT_AERIAL_SIZE * MRT_AERIAL_SIZE) return;
+    const int x = i % MRT_AERIAL_SIZE, y = (i / MRT_AERIAL_SIZE) % MRT_AERIAL_SIZE, z = i / (MRT_AERIAL_SIZE * MRT_AERIAL_SIZE);
+    float3 o, worldDir;
+    ray_gen(gen, (uint32_t)x, (uint32_t)y, o, worldDir);
+    const float3 camPos = cameraPos + f3(0.0f, 0.0f, A.bottomRadius);
+    float slice = ((float)z + 0.5f) / (float)MRT_AERIAL_SIZE;
+    slice *= slice;
+    slice *= (float)MRT_AERIAL_SIZE;
+    float3 worldPos = camPos;
+    float tMax = slice * MRT_AERIAL_KM_PER_SLICE;
+    float3 newWorldPos = worldPos + worldDir * tMax;
+    float viewHeight = length3(newWorldPos);
+    if (viewHeight <= A.bottomRadius + SKY_PLANET_RADIUS_OFFSET) {
+        newWorldPos = normalize3(newWorldPos) * (A.bottomRadius + SKY_PLANET_RADIUS_OFFSET + 0.001f);
+        worldDir = normalize3(newWorldPos - camPos);
+        tMax = length3(newWorldPos - camPos);
+    }
+    float tMaxMax = tMax;
+    float4 rgba = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    bool inside = true;
+    viewHeight = length3(worldPos);
+    if (viewHeight >= A.topRadius) {
+        const float3 prev = worldPos;
+        if (viewHeight > A.topRadius) {  // sky.glsl:79-94 moveToTopAtmosphere
+            float tTop = sky_ray_sphere_nearest(worldPos, worldDir, f3s(0.0f), A.topRadius);
+            if (tTop >= 0.0f) {
+                float3 upv = worldPos / viewHeight;
+                worldPos = (worldPos + worldDir * tTop) + upv * -SKY_PLANET_RADIUS_OFFSET;
+            } else {
+                inside = false;
+            }
+        }
+        if (inside) {
+            float lengthToAtmosphere = length3(prev - worldPos);
+            if (tMaxMax < lengthToAtmosphere) inside = false;
+            tMaxMax = fmaxf(0.0f, tMaxMax - lengthToAtmosphere);
+        }
+    }
+    if (inside) {
+        const float sampleCountIni = fmaxf(1.0f, ((float)z + 1.0f) * 2.0f);
+        Scatter ss = integrate_scattered<true, true>(A, luts, worldPos, worldDir, sunDirection, false, sampleCountIni, false, true,
+                                                     tMaxMax, sunIll);
+        const float T = (ss.transmittance.x + ss.transmittance.y + ss.transmittance.z) * (1.0f / 3.0f);
+        rgba = make_float4(ss.L.x, ss.L.y, ss.L.z, 1.0f - T);
+    }
+    const uint16_t h[4] = {f32_to_f16_bits(rgba.x), f32_to_f16_bits(rgba.y), f32_to_f16_bits(rgba.z), f32_to_f16_bits(rgba.w)};
+    for (int c = 0; c < 4; c++) out16[4 * (size_t)i + c] = h[c];
+    outf[i] = make_float4(f16_bits_to_f32(h[0]), f16_bits_to_f32(h[1]), f16_bits_to_f32(h[2]), f16_bits_to_f32(h[3]));
+}
+
 }  // namespace
+
+int sky_gen_aerial(mrt_context* ctx, const mrt_primary_constants* c, const float cameraPos[3], const float sunDir[3], const float sunIll[3]) {
+    const size_t n = (size_t)MRT_AERIAL_SIZE * MRT_AERIAL_SIZE * MRT_AERIAL_SIZE;
+    MRT_TRY(dev_reserve(ctx, ctx->aerial16, 4 * n));
+    MRT_TRY(dev_reserve(ctx, ctx->aerial_f, n));
+    RayGen gen;
+    memcpy(&gen.invView, &c->invView, sizeof(Mat4));
+    memcpy(&gen.invProj, &c->invProjection, sizeof(Mat4));
+    gen.W = gen.H = MRT_AERIAL_SIZE;
+    SkyLuts luts{ctx->trans_f.p, ctx->multi_f.p, nullptr};
+    k_gen_aerial<<<div_up(n, 256), 256, 0, ctx->stream>>>(ctx->atmo, luts, gen, f3(cameraPos[0], cameraPos[1], cameraPos[2]),
+                                                          f3(sunDir[0], sunDir[1], sunDir[2]), f3(sunIll[0], sunIll[1], sunIll[2]),
+                                                          ctx->aerial16.p, ctx->aerial_f.p);
+    MRT_LAUNCHED(ctx);
+    return mrt_check_cuda(ctx, cudaGetLastError(), "sky_gen_aerial");
+}
 
 int sky_gen_atmosphere(mrt_context* ctx) {
     MRT_TRY(dev_reserve(ctx, ctx->trans16, (size_t)MRT_TRANS_W * MRT_TRANS_H * 4));

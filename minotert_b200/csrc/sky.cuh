@@ -11,6 +11,8 @@
 #define MRT_MULTI_H 32
 #define MRT_VIEW_W 192
 #define MRT_VIEW_H 108
+#define MRT_AERIAL_SIZE 32              // Sky::AerialPerspectiveSize, sky.ixx:191
+#define MRT_AERIAL_KM_PER_SLICE 4.0f    // AP_KM_PER_SLICE, skyAccess.glsl:9
 
 #define SKY_PI 3.14159274101257324f          // constants.glsl:4 rounded to fp32
 #define SKY_PLANET_RADIUS_OFFSET 0.01f       // sky.glsl:13
@@ -146,4 +148,39 @@ MRT_D void sky_nee_sun_sample(float u0, float u1, float3& l, float& weight) {
     sincosf(phi, &sn, &cs);
     l = normalize3((t * (cs * sinT) + b * (sn * sinT)) + sun * cosT);
     weight = sqrtf(clampf(1.0f - u0, 0.0001f, 1.0f)) * (2.0f * oneMinusCos);
+}
+
+// aerial perspective of a surface at distance t (km) seen through image position (u, v): weight * trilinear(volume) at
+// (u, v, sqrt(slice / 32)), clamp to edge; .xyz luminance scattered towards the camera, .w = 1 - transmittance
+MRT_D float4 sky_aerial_lookup(const float4* __restrict__ vol, float u, float v, float t) {
+    float slice = t * (1.0f / MRT_AERIAL_KM_PER_SLICE);  // aerialPerspectiveDepthToSlice, skyAccess.glsl:119-121
+    float weight = 1.0f;
+    if (slice < 0.5f) {
+        weight = clampf(slice * 2.0f, 0.0f, 1.0f);
+        slice = 0.5f;
+    }
+    const float w = sqrtf(slice / (float)MRT_AERIAL_SIZE);
+    const float c[3] = {u * (float)MRT_AERIAL_SIZE - 0.5f, v * (float)MRT_AERIAL_SIZE - 0.5f, w * (float)MRT_AERIAL_SIZE - 0.5f};
+    int i0[3];
+    float f[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float fl = floorf(c[a]);
+        i0[a] = (int)fl;
+        f[a] = c[a] - fl;
+    }
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                const int x = min(max(i0[0] + dx, 0), MRT_AERIAL_SIZE - 1), y = min(max(i0[1] + dy, 0), MRT_AERIAL_SIZE - 1),
+                          z = min(max(i0[2] + dz, 0), MRT_AERIAL_SIZE - 1);
+                const float4 tx = __ldg(&vol[((size_t)z * MRT_AERIAL_SIZE + y) * MRT_AERIAL_SIZE + x]);
+                const float wt = ((dx ? f[0] : 1.0f - f[0]) * (dy ? f[1] : 1.0f - f[1])) * (dz ? f[2] : 1.0f - f[2]);
+                acc = make_float4(acc.x + tx.x * wt, acc.y + tx.y * wt, acc.z + tx.z * wt, acc.w + tx.w * wt);
+            }
+    return make_float4(acc.x * weight, acc.y * weight, acc.z * weight, acc.w * weight);
 }

@@ -65,6 +65,7 @@ def load():
     L.minote_app_configure.argtypes = [vp, u32, u32, C.c_int, C.c_int, C.c_float]
     L.minote_app_set_denoise.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float]
     L.minote_app_set_temporal.argtypes = [vp, C.c_int, C.c_float]
+    L.minote_app_set_sky_extensions.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.minote_app_resize.argtypes = [vp, u32, u32]
     L.minote_app_draw.argtypes = [vp, cam]
     L.minote_app_read_framebuffer.argtypes = [vp, vp, C.c_size_t]
@@ -172,6 +173,10 @@ class Renderer:
         so that the ray-throughput measurements and the path-trace parity tests see the path tracer's image."""
         self._ck(self.L.minote_app_configure(self.h, samples, bounces, int(accumulate), capi.TONEMAP[tonemap], exposure))
         self._ck(self.L.minote_app_set_denoise(self.h, capi.DENOISE[denoise], *[float(x) for x in bilateral]))
+
+    def set_sky_extensions(self, sun_sampling=False, sky_at_hit=False, aerial_perspective=False):
+        """Pathtracer::sunSampling / skyAtHit / aerialPerspective (SURVEY 8f-4; triangle scenes)."""
+        self._ck(self.L.minote_app_set_sky_extensions(self.h, int(sun_sampling), int(sky_at_hit), int(aerial_perspective)))
 
     def set_temporal(self, enabled, max_history=32.0):
         """Temporal accumulation along GBuffer::motion (Reprojector::accumulate) instead of the denoiser."""

@@ -152,6 +152,14 @@ int minote_app_configure(void* a, std::uint32_t samples, std::uint32_t bounces, 
         r.exposure = exposure;
     });
 }
+// sky extensions of the path tracer: sun as a sampled light, sky evaluated at the shaded point
+int minote_app_set_sky_extensions(void* a, int sun_sampling, int sky_at_hit, int aerial_perspective) {
+    return guarded(static_cast<App*>(a), [&] {
+        Renderer::serv->pathtracer.sunSampling = sun_sampling != 0;
+        Renderer::serv->pathtracer.skyAtHit = sky_at_hit != 0;
+        Renderer::serv->pathtracer.aerialPerspective = aerial_perspective != 0;
+    });
+}
 // Renderer_impl::denoise controls (renderer.ixx:140-152): mode 0 None, 1 Bilateral
 int minote_app_set_denoise(void* a, int mode, float sigma, float kSigma, float threshold) {
     return guarded(static_cast<App*>(a), [&] {

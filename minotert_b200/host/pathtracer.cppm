@@ -26,6 +26,10 @@ public:
     u32 samples = 8;
     u32 bounces = 8;
     bool accumulate = false;  // progressive accumulation across draw() calls (row n7)
+    // Sky extensions the reference stubs out (sky.ixx:190-191, secondaryRays.comp:37; SURVEY 8f-4), triangle scenes:
+    bool sunSampling = false; // the sun as a sampled light: a shadow ray into its disc at every hit that bounces
+    bool skyAtHit = false;    // sky evaluated at the shaded point instead of at the camera
+    bool aerialPerspective = false;  // camera volume (Sky::createAerialPerspective) applied between camera and primary hit
 
     struct PrimaryConstants {
         mat4 view, projection, invView, invProjection, prevView;
@@ -64,7 +68,9 @@ public:
         auto const constants = secondaryConstants(camera, Cuda::serv->frameCount());
         mrt_secondary_constants raw;
         std::memcpy(&raw, &constants, sizeof raw);
-        Cuda::serv->check(mrt_secondary_rays(Cuda::serv->ctx, &raw, samples, bounces, accumulate ? MRT_SECONDARY_ACCUMULATE : 0u));
+        u32 const flags = (accumulate ? MRT_SECONDARY_ACCUMULATE : 0u) | (sunSampling ? MRT_SECONDARY_NEE_SUN : 0u) |
+                                    (skyAtHit ? MRT_SECONDARY_SKY_AT_HIT : 0u) | (aerialPerspective ? MRT_SECONDARY_AERIAL : 0u);
+        Cuda::serv->check(mrt_secondary_rays(Cuda::serv->ctx, &raw, samples, bounces, flags));
         return DeviceImage{accumulate ? MRT_BUF_ACCUM : MRT_BUF_COLOR};
     }
 };

@@ -4,6 +4,7 @@
 // replaced by an RGBA8 framebuffer the caller reads back.
 module;
 #include <cstdint>
+#include <cstring>
 #include <ctime>
 
 #include "../../include/minotert.h"
@@ -67,6 +68,12 @@ public:
         if (!atmo) atmo = new Atmosphere(Atmosphere::Params::earth());
         auto sky = Sky();
         auto skyView = sky.createView(*atmo, camera.position);
+        if (pathtracer.aerialPerspective) {  // camera-dependent: rebuilt with the view (32^3 froxels, ~20 us)
+            auto const constants = Pathtracer::primaryConstants(camera, prevCamera, Cuda::serv->frameCount());
+            mrt_primary_constants raw;
+            std::memcpy(&raw, &constants, sizeof raw);
+            sky.createAerialPerspective(*atmo, raw, camera.position);
+        }
         auto gbuffer = pathtracer.primaryRays(outputSize, camera, prevCamera);
         auto pathtraced = pathtracer.secondaryRays(gbuffer, camera, *atmo, skyView, blueNoise);
         // temporal accumulation (off by default: the reference has none) takes the denoiser's place in the chain

@@ -85,4 +85,14 @@ public:
         Cuda::serv->check(mrt_sky_view(Cuda::serv->ctx, probePos.v.data(), sunDirection.v.data(), sunIlluminance.v.data()));
         return DeviceImage{MRT_BUF_SKY_VIEW};
     }
+
+    // The camera volume the reference declares and never builds (AerialPerspectiveFormat / AerialPerspectiveSize,
+    // sky.ixx:190-191): luminance scattered towards the camera + 1 - transmittance in 32^3 froxels of the view whose
+    // inverse matrices are given (the Pathtracer's primary constants); SURVEY 8f-4
+    static constexpr unsigned AerialPerspectiveSize = 32;
+    auto createAerialPerspective(Atmosphere const&, mrt_primary_constants const& constants, vec3 cameraPos) -> DeviceImage {
+        Cuda::serv->check(mrt_sky_aerial_perspective(Cuda::serv->ctx, &constants, cameraPos.v.data(), sunDirection.v.data(),
+                                                     sunIlluminance.v.data()));
+        return DeviceImage{MRT_BUF_AERIAL};
+    }
 };

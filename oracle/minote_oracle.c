@@ -1772,8 +1772,112 @@ void orc_render_tris(const orc_scene* s, uint32_t w, uint32_t h, const orc_prima
                      uint32_t spp, uint32_t bounces, int use_bvh, uint32_t y0, uint32_t y1, float* accum,
                      uint32_t* visibility, uint64_t* rays_out) {
     orc_render_tris_ext(s, w, h, pc, sc, blueNoise, bnW, bnH, atmo, trans, skyView, spp, bounces, use_bvh, y0, y1, accum,
-                        visibility, rays_out, 0u);
+                        visibility, rays_out, 0u, NULL);
 }
+
+/* ---- aerial-perspective volume ----
+ * The reference declares the volume (Sky::AerialPerspectiveFormat RGBA16F, AerialPerspectiveSize 32^3, sky.ixx:190-191;
+ * AP_KM_PER_SLICE 4.0 and the depth<->slice maps, skyAccess.glsl:9,119-125) and never builds it.  The contract here is the
+ * camera-volume pass of the technique its sky code comes from (Hillaire 2020, "A Scalable and Production Ready Sky and
+ * Atmosphere Rendering Technique", sec. 5.3), written with the reference's own integrateScatteredLuminance:
+ *   froxel (x, y, z): view ray of the centre of cell (x, y) of a 32 x 32 image through ray_gen (primaryRay.comp:40-56),
+ *   slice s = ((z + 0.5) / 32)^2 * 32, depth tMax = s * 4 km along that ray from the camera; a froxel below the ground
+ *   is pulled onto it; luminance scattered towards the camera and transmittance over [0, tMax] by the ray march with
+ *   max(1, 2 (z + 1)) fixed steps, Mie + Rayleigh phase, no ground term  ->  RGBA16F (L.rgb, 1 - mean transmittance).
+ * Lookup for a surface seen at distance t through pixel (px, py) of a w x h image: s = t / 4; weight = 1, and for
+ * s < 0.5: weight = clamp(2 s, 0, 1), s = 0.5 (fades to nothing at the camera); trilinear, clamp to edge, at
+ * ((px + 0.5) / w, (py + 0.5) / h, sqrt(s / 32)); result * weight.  ORC_EXT_AERIAL applies it to every sample of a pixel
+ * whose primary ray hit: the path's throughput starts at 1 - AP.a and AP.rgb is added once per sample. */
+#define AP_SIZE 32
+#define AP_KM_PER_SLICE 4.0f
+void orc_gen_aerial_perspective(const orc_atmosphere_params* A, const uint16_t* trans16, const uint16_t* multi16,
+                                const orc_mat4* invView, const orc_mat4* invProjection, const float cameraPos[3],
+                                const float sunDirection[3], const float sunIlluminance[3], uint16_t* out) {
+    tex3 trans = tex_from_rgba16f(trans16, ORC_TRANS_W, ORC_TRANS_H);
+    tex3 multi = tex_from_rgba16f(multi16, ORC_MULTI_W, ORC_MULTI_H);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int z = 0; z < AP_SIZE; z++)
+        for (int y = 0; y < AP_SIZE; y++)
+            for (int x = 0; x < AP_SIZE; x++) {
+                v3 o, worldDir;
+                ray_gen(invView, invProjection, (uint32_t)x, (uint32_t)y, AP_SIZE, AP_SIZE, &o, &worldDir);
+                v3 camPos = vadd(v3p(cameraPos), V(0.0f, 0.0f, A->bottomRadius));
+                float slice = ((float)z + 0.5f) / (float)AP_SIZE;
+                slice *= slice;
+                slice *= (float)AP_SIZE;
+                v3 worldPos = camPos;
+                float tMax = slice * AP_KM_PER_SLICE; /* aerialPerspectiveSliceToDepth */
+                v3 newWorldPos = vadd(worldPos, vscale(worldDir, tMax));
+                float viewHeight = vlen(newWorldPos);
+                if (viewHeight <= A->bottomRadius + PLANET_RADIUS_OFFSET) {
+                    newWorldPos = vscale(vnorm(newWorldPos), A->bottomRadius + PLANET_RADIUS_OFFSET + 0.001f);
+                    worldDir = vnorm(vsub(newWorldPos, camPos));
+                    tMax = vlen(vsub(newWorldPos, camPos));
+                }
+                float tMaxMax = tMax;
+                float rgba[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+                int inside = 1;
+                viewHeight = vlen(worldPos);
+                if (viewHeight >= A->topRadius) {
+                    v3 prev = worldPos;
+                    if (!moveToTopAtmosphere(&worldPos, worldDir, A->topRadius)) inside = 0;
+                    else {
+                        float lengthToAtmosphere = vlen(vsub(prev, worldPos));
+                        if (tMaxMax < lengthToAtmosphere) inside = 0;
+                        tMaxMax = fmaxf(0.0f, tMaxMax - lengthToAtmosphere);
+                    }
+                }
+                if (inside) {
+                    float sampleCountIni = fmaxf(1.0f, ((float)z + 1.0f) * 2.0f);
+                    scatter_result ss = integrateScatteredLuminance(A, &trans, &multi, worldPos, worldDir, v3p(sunDirection), 0,
+                                                                    sampleCountIni, 0, 1, tMaxMax, v3p(sunIlluminance));
+                    float T = (ss.transmittance.x + ss.transmittance.y + ss.transmittance.z) * (1.0f / 3.0f);
+                    rgba[0] = ss.L.x; rgba[1] = ss.L.y; rgba[2] = ss.L.z; rgba[3] = 1.0f - T;
+                }
+                uint16_t* px = &out[4 * (((size_t)z * AP_SIZE + y) * AP_SIZE + x)];
+                for (int c = 0; c < 4; c++) px[c] = orc_f32_to_f16(rgba[c]);
+            }
+    tex_free(&trans);
+    tex_free(&multi);
+}
+
+static void ap_texel(const uint16_t* vol, int x, int y, int z, float out[4]) {
+    x = x < 0 ? 0 : (x > AP_SIZE - 1 ? AP_SIZE - 1 : x);
+    y = y < 0 ? 0 : (y > AP_SIZE - 1 ? AP_SIZE - 1 : y);
+    z = z < 0 ? 0 : (z > AP_SIZE - 1 ? AP_SIZE - 1 : z);
+    const uint16_t* p = &vol[4 * (((size_t)z * AP_SIZE + y) * AP_SIZE + x)];
+    for (int c = 0; c < 4; c++) out[c] = orc_f16_to_f32(p[c]);
+}
+/* weight * trilinear(vol, u, v, sqrt(slice / 32)) for a surface at distance t (km) */
+static void ap_lookup(const uint16_t* vol, float u, float v, float t, float out[4]) {
+    float slice = t * (1.0f / AP_KM_PER_SLICE); /* aerialPerspectiveDepthToSlice */
+    float weight = 1.0f;
+    if (slice < 0.5f) {
+        weight = clampf(slice * 2.0f, 0.0f, 1.0f);
+        slice = 0.5f;
+    }
+    float w = sqrtf(slice / (float)AP_SIZE);
+    float c[3] = {u * (float)AP_SIZE - 0.5f, v * (float)AP_SIZE - 0.5f, w * (float)AP_SIZE - 0.5f};
+    int i0[3];
+    float f[3];
+    for (int a = 0; a < 3; a++) {
+        float fl = floorf(c[a]);
+        i0[a] = (int)fl;
+        f[a] = c[a] - fl;
+    }
+    float acc[4] = {0, 0, 0, 0};
+    for (int dz = 0; dz < 2; dz++)
+        for (int dy = 0; dy < 2; dy++)
+            for (int dx = 0; dx < 2; dx++) {
+                float tx[4];
+                ap_texel(vol, i0[0] + dx, i0[1] + dy, i0[2] + dz, tx);
+                float wx = dx ? f[0] : 1.0f - f[0], wy = dy ? f[1] : 1.0f - f[1], wz = dz ? f[2] : 1.0f - f[2];
+                float wt = (wx * wy) * wz;
+                for (int k = 0; k < 4; k++) acc[k] += tx[k] * wt;
+            }
+    for (int k = 0; k < 4; k++) out[k] = acc[k] * weight;
+}
+void orc_aerial_perspective_lookup(const uint16_t* vol, float u, float v, float t, float out[4]) { ap_lookup(vol, u, v, t, out); }
 
 /* The native path tracer with the SURVEY 8f-4 extensions (ext = 0: exactly secondaryRays.comp:64-135 per pixel).
  *  ORC_EXT_NEE_SUN    at every hit vertex i < bounces, BEFORE the bounce's two random numbers, two more rotated random
@@ -1784,13 +1888,16 @@ void orc_render_tris(const orc_scene* s, uint32_t w, uint32_t h, const orc_prima
  *                     the sky-view term only (the disc they would otherwise hit by chance is what the shadow rays
  *                     integrate); a PRIMARY ray that escapes still sees the disc.  Shadow rays count as secondary rays.
  *  ORC_EXT_SKY_AT_HIT the sky is evaluated at the origin of the escaping ray (and E at the shaded point) instead of at the
- *                     camera (secondaryRays.comp:37 uses C.cameraPos for every vertex). */
+ *                     camera (secondaryRays.comp:37 uses C.cameraPos for every vertex).
+ *  ORC_EXT_AERIAL     aerial perspective between the camera and the primary hit from the volume `aerial`
+ *                     (orc_gen_aerial_perspective; contract above). */
 void orc_render_tris_ext(const orc_scene* s, uint32_t w, uint32_t h, const orc_primary_constants* pc,
                          const orc_secondary_constants* sc, const uint8_t* blueNoise, uint32_t bnW, uint32_t bnH,
                          const orc_atmosphere_params* atmo, const uint16_t* trans, const uint32_t* skyView,
                          uint32_t spp, uint32_t bounces, int use_bvh, uint32_t y0, uint32_t y1, float* accum,
-                         uint32_t* visibility, uint64_t* rays_out, uint32_t ext) {
+                         uint32_t* visibility, uint64_t* rays_out, uint32_t ext, const uint16_t* aerial) {
     const int nee = (ext & ORC_EXT_NEE_SUN) != 0, at_hit = (ext & ORC_EXT_SKY_AT_HIT) != 0;
+    const int ap_on = (ext & ORC_EXT_AERIAL) != 0 && aerial != NULL;
     sky_ctx S = sky_ctx_make(atmo, trans, skyView, sc->cameraPos);
     const v3 E_cam = sun_centre_radiance(&S, S.cameraPos);
     uint64_t prim = 0, sec = 0;
@@ -1812,8 +1919,15 @@ void orc_render_tris_ext(const orc_scene* s, uint32_t w, uint32_t h, const orc_p
             const uint8_t* bn = &blueNoise[4 * ((size_t)((uint32_t)y % bnH) * bnW + (x % bnW))];
             float rotx = (float)bn[0] / 255.0f, roty = (float)bn[1] / 255.0f;
             v3 color = V(0, 0, 0);
+            float ap[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (ap_on && h0.id != NONE_ID)
+                ap_lookup(aerial, ((float)x + 0.5f) / (float)w, ((float)y + 0.5f) / (float)h, h0.t, ap);
             for (uint32_t smp = 0; smp < spp; smp++) {
                 v3 thr = V(1, 1, 1);
+                if (ap_on && h0.id != NONE_ID) {
+                    thr = vsplat(1.0f - ap[3]);
+                    color = vadd(color, V(ap[0], ap[1], ap[2]));
+                }
                 uint32_t hid = h0.id;
                 v3 hpos = p0, hn = n0;
                 v3 sky_pos = S.cameraPos;  /* where the sky is evaluated for the ray that escapes next */

@@ -239,12 +239,19 @@ void orc_render_tris(const orc_scene* s, uint32_t w, uint32_t h, const orc_prima
 /* SURVEY 8f-4 extensions of the native path tracer (contract in minote_oracle.c at orc_render_tris_ext) */
 #define ORC_EXT_NEE_SUN 1u
 #define ORC_EXT_SKY_AT_HIT 2u
+#define ORC_EXT_AERIAL 4u
 void orc_render_tris_ext(const orc_scene* s, uint32_t w, uint32_t h, const orc_primary_constants* pc,
                          const orc_secondary_constants* sc, const uint8_t* blueNoise, uint32_t bnW,
                          uint32_t bnH, const orc_atmosphere_params* atmo, const uint16_t* trans,
                          const uint32_t* skyView, uint32_t spp, uint32_t bounces, int use_bvh,
                          uint32_t y0, uint32_t y1, float* accum, uint32_t* visibility,
-                         uint64_t* rays_out, uint32_t ext);
+                         uint64_t* rays_out, uint32_t ext, const uint16_t* aerial /* 32^3 RGBA16F or NULL */);
+/* aerial-perspective volume (32 x 32 x 32 RGBA16F, x fastest) for a camera, and its lookup for a surface at distance t
+ * (km) seen through image position (u, v) in [0,1]^2 (v down) */
+void orc_gen_aerial_perspective(const orc_atmosphere_params* p, const uint16_t* trans, const uint16_t* multi,
+                                const orc_mat4* invView, const orc_mat4* invProjection, const float cameraPos[3],
+                                const float sunDirection[3], const float sunIlluminance[3], uint16_t* out);
+void orc_aerial_perspective_lookup(const uint16_t* vol, float u, float v, float t, float out[4]);
 /* one sun sample: direction inside the disc and the weight limb * Omega / pi; the sun centre's radiance seen from pos */
 void orc_nee_sun_sample(float u0, float u1, float l[3], float* weight);
 void orc_sun_centre_radiance(const orc_atmosphere_params* p, const uint16_t* trans, const uint32_t* skyView,

@@ -148,7 +148,9 @@ def lib():
         "orc_scene_closest_hit": (C.c_uint32, [C.c_void_p, f32p, f32p, C.c_int, f32p, f32p, f32p]),
         "orc_primary_rays_tris": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.c_int, C.c_uint32, C.c_uint32, u32p, u16p, u16p, u16p, f32p]),
         "orc_render_tris": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.POINTER(SecondaryConstants), u8p, C.c_uint32, C.c_uint32, C.POINTER(AtmosphereParams), u16p, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, f32p, u32p, u64p]),
-        "orc_render_tris_ext": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.POINTER(SecondaryConstants), u8p, C.c_uint32, C.c_uint32, C.POINTER(AtmosphereParams), u16p, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, f32p, u32p, u64p, C.c_uint32]),
+        "orc_render_tris_ext": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(PrimaryConstants), C.POINTER(SecondaryConstants), u8p, C.c_uint32, C.c_uint32, C.POINTER(AtmosphereParams), u16p, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, f32p, u32p, u64p, C.c_uint32, u16p]),
+        "orc_gen_aerial_perspective": (None, [C.POINTER(AtmosphereParams), u16p, u16p, C.c_void_p, C.c_void_p, f32p, f32p, f32p, u16p]),
+        "orc_aerial_perspective_lookup": (None, [u16p, C.c_float, C.c_float, C.c_float, f32p]),
         "orc_nee_sun_sample": (None, [C.c_float, C.c_float, f32p, f32p]),
         "orc_sun_centre_radiance": (None, [C.POINTER(AtmosphereParams), u16p, u32p, f32p, f32p]),
         "orc_resolve": (None, [C.c_uint32, f32p, f32p]),
@@ -375,7 +377,7 @@ class Scene:
                                     _p(t, C.c_float))
         return vis, depth, normal, motion, t
 
-    def render(self, w, h, pc, sc, bn, atmo, trans, view, spp, bounces, use_bvh=True, rows=None, accum=None, ext=0):
+    def render(self, w, h, pc, sc, bn, atmo, trans, view, spp, bounces, use_bvh=True, rows=None, accum=None, ext=0, aerial=None):
         y0, y1 = rows if rows else (0, h)
         if accum is None:
             accum = np.zeros((h, w, 4), np.float32)
@@ -383,11 +385,35 @@ class Scene:
         rays = (C.c_uint64 * 2)()
         lib().orc_render_tris_ext(self.h, w, h, C.byref(pc), C.byref(sc), _p(bn, C.c_uint8), bn.shape[1], bn.shape[0],
                                   C.byref(atmo), _p(trans, C.c_uint16), _p(view, C.c_uint32), spp, bounces, int(use_bvh),
-                                  y0, y1, _p(accum, C.c_float), _p(vis, C.c_uint32), rays, ext)
+                                  y0, y1, _p(accum, C.c_float), _p(vis, C.c_uint32), rays, ext,
+                                  _p(aerial, C.c_uint16) if aerial is not None else None)
         return accum, vis, (rays[0], rays[1])
 
 
-EXT_NEE_SUN, EXT_SKY_AT_HIT = 1, 2
+EXT_NEE_SUN, EXT_SKY_AT_HIT, EXT_AERIAL = 1, 2, 4
+SUN_DIRECTION = (-0.435286462, 0.818654716, 0.374606609)
+SUN_ILLUMINANCE = (8.0, 8.0, 8.0)
+
+
+def aerial_perspective(atmo, trans, multi, pc, camera_pos, sun_dir=SUN_DIRECTION, sun_ill=SUN_ILLUMINANCE):
+    """orc_gen_aerial_perspective: the 32^3 RGBA16F camera volume (z, y, x, 4) for the camera of the constants pc."""
+    out = np.zeros((32, 32, 32, 4), np.uint16)
+    lib().orc_gen_aerial_perspective(C.byref(atmo), _p(trans, C.c_uint16), _p(multi, C.c_uint16), C.byref(pc.invView),
+                                     C.byref(pc.invProjection), f3(camera_pos), f3(sun_dir), f3(sun_ill), _p(out, C.c_uint16))
+    return out
+
+
+def ray_gen(pc, x, y, w, h):
+    """primaryRay.comp:40-56 for pixel (x, y): origin and direction (float32 arrays)."""
+    o, d = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    lib().orc_ray_gen(C.byref(pc.invView), C.byref(pc.invProjection), int(x), int(y), w, h, _p(o, C.c_float), _p(d, C.c_float))
+    return o, d
+
+
+def aerial_lookup(vol, u, v, t):
+    out = np.zeros(4, np.float32)
+    lib().orc_aerial_perspective_lookup(_p(vol, C.c_uint16), float(u), float(v), float(t), _p(out, C.c_float))
+    return out
 
 
 def nee_sun_sample(u0, u1):

@@ -112,3 +112,75 @@ def test_sky_extension_flags_are_for_triangle_scenes(gpu_ctx, oracle, sky_inputs
     gpu_ctx.primary_rays(64, 36, as_capi(pc, capi.PrimaryConstants))
     with pytest.raises(capi.MinoteError):
         gpu_ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), 1, 1, capi.SECONDARY_NEE_SUN)
+
+
+def test_renderer_sky_extensions_reach_the_context(oracle, blue_noise):
+    """Pathtracer::sunSampling / skyAtHit through Renderer::draw == the same flags on a bare context (RGBA8 framebuffer)."""
+    from minotert_b200 import host
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h = 192, 108
+    cam = host.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+    r = host.Renderer(w, h, blue_noise, device=0, frames_in_flight=1)
+    try:
+        r.set_mesh(pos, idx, alb)
+        r.configure(samples=2, bounces=2, accumulate=True)
+        r.set_sky_extensions(sun_sampling=True, sky_at_hit=True)
+        r.draw(cam)
+        fb = r.read_framebuffer().copy()
+        r.set_sky_extensions(False, False)
+        r.configure(samples=2, bounces=2, accumulate=False)
+        r.draw(cam)
+        plain = r.read_framebuffer().copy()
+    finally:
+        r.close()
+    assert fb.astype(int).sum() > 1.1 * plain.astype(int).sum()      # the sun lights the terrain
+    ctx = capi.Context(0)
+    try:
+        ctx.upload_blue_noise(blue_noise)
+        ctx.upload_mesh(pos, idx, alb)
+        ctx.build()
+        ctx.atmosphere(host.atmosphere_earth())
+        ctx.sky_view(cam.position[:], (-0.435286462, 0.818654716, 0.374606609), (8.0, 8.0, 8.0))
+        pc, sc = host.camera_constants(cam, cam, 1)
+        ctx.primary_rays(w, h, pc)
+        ctx.secondary_rays(sc, 2, 2, capi.SECONDARY_NEE_SUN | capi.SECONDARY_SKY_AT_HIT)
+        ctx.tonemap("amd", 1.0, oracle.AMD_DEFAULT, capi.BUF_ACCUM)
+        want = ctx.readback(capi.BUF_LDR)
+        assert np.array_equal(fb, want)
+    finally:
+        ctx.close()
+
+
+def test_aerial_perspective_volume_and_render_match_the_oracle(gpu_ctx, oracle, sky_inputs, blue_noise):
+    """mrt_sky_aerial_perspective vs orc_gen_aerial_perspective (<= 2 fp16 steps on every froxel channel: libdevice vs
+    glibc exp/sqrt inside a 2..64-step ray march), and a frame with MRT_SECONDARY_AERIAL on a wall 30 km away vs the
+    oracle's ORC_EXT_AERIAL (PSNR >= 50 dB; the plain frame differs from it by far more)."""
+    from test_oracle_nee import far_wall_scene
+    atmo = sky_inputs[0]
+    w, h, spp = 96, 54, 2
+    pos, idx, alb = far_wall_scene()
+    cam = oracle.make_camera(w, h, (0.0, 0.0, 0.1), 90.0, 0.0, vfov_deg=30.0)
+    pc, sc = oracle.constants(cam, frame=1)
+    trans, multi, view = oracle.sky_luts(atmo, cam.position[:])
+    vol = oracle.aerial_perspective(atmo, trans, multi, pc, cam.position[:])
+    prepare(gpu_ctx, oracle, atmo, cam, blue_noise, (pos, idx, alb))
+    gpc = as_capi(pc, capi.PrimaryConstants)
+    with pytest.raises(capi.MinoteError):    # the flag needs the volume
+        gpu_ctx.primary_rays(w, h, gpc)
+        gpu_ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), spp, 1, capi.SECONDARY_AERIAL)
+    gpu_ctx.sky_aerial_perspective(gpc, cam.position[:])
+    gvol = gpu_ctx.readback(capi.BUF_AERIAL)
+    assert gvol.shape == vol.shape
+    a, b = oracle.f16_to_f32(gvol).astype(np.float64), oracle.f16_to_f32(vol).astype(np.float64)
+    step = np.maximum(np.abs(b), 6.1e-5) * 2.0 ** -10     # one fp16 step at the value (normal range)
+    assert (np.abs(a - b) <= 2.0 * step + 1e-7).mean() >= 0.999, float((np.abs(a - b) / step).max())
+    osc = oracle.Scene(pos, idx, alb)
+    hazy, vis, _ = osc.render(w, h, pc, sc, blue_noise, atmo, trans, view, spp, 1, use_bvh=False, ext=oracle.EXT_AERIAL, aerial=vol)
+    plain, _, _ = osc.render(w, h, pc, sc, blue_noise, atmo, trans, view, spp, 1, use_bvh=False)
+    gpu_ctx.primary_rays(w, h, gpc)
+    gpu_ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), spp, 1, capi.SECONDARY_AERIAL)
+    gacc = gpu_ctx.readback(capi.BUF_ACCUM)
+    assert np.array_equal(gpu_ctx.readback(capi.BUF_VISIBILITY), vis)
+    p = oracle.psnr(oracle.resolve(gacc)[..., :3], oracle.resolve(hazy)[..., :3], 16.0)
+    assert p >= 50.0, f"PSNR {p:.1f} dB"
+    assert oracle.psnr(oracle.resolve(gacc)[..., :3], oracle.resolve(plain)[..., :3], 16.0) < 40.0

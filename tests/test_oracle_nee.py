@@ -122,3 +122,64 @@ def test_sky_at_hit_moves_the_sky_position_by_metres_only(oracle, sky_inputs, bl
     assert ra == rb
     assert not np.array_equal(a, b)                       # 6 m lower: the sky-view parameterisation moves in the last digits
     assert np.allclose(a[..., :3], b[..., :3], rtol=5e-2, atol=1e-2)
+
+
+# ---- aerial-perspective volume (ORC_EXT_AERIAL) ----
+
+def far_wall_scene(distance_km=30.0):
+    """A 40 km wall facing the camera `distance_km` away along +y (the default camera's view axis), plus the ground plane
+    of plane_scene so that near pixels exist too."""
+    z = 0.0985
+    d, s = distance_km, 20.0
+    pos = np.array([[-s, d, z - 12.0], [s, d, z - 12.0], [s, d, z + 12.0], [-s, d, z + 12.0]], np.float32)
+    idx = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    alb = np.tile(np.array([[0.5, 0.5, 0.5]], np.float32), (2, 1))
+    return pos, idx, alb
+
+
+def test_aerial_volume_and_lookup(oracle, sky_inputs):
+    atmo = sky_inputs[0]
+    cam = oracle.make_camera(64, 36, (0.0, 0.0, 0.1), 90.0, 20.0)   # looking up: no froxel of the centre column is below ground
+    pc, sc = oracle.constants(cam, frame=1)
+    trans, multi, view = oracle.sky_luts(atmo, cam.position[:])
+    vol = oracle.aerial_perspective(atmo, trans, multi, pc, cam.position[:])
+    v = oracle.f16_to_f32(vol)
+    assert np.isfinite(v).all() and (v >= 0).all() and (v[..., 3] <= 1.0).all()
+    col = v[:, 16, 16]
+    assert np.all(np.diff(col[:, 3]) >= -1e-3)          # opacity grows with depth along a ray that leaves the atmosphere
+    assert col[-1, 3] > 0.05 and col[0, 3] < 2e-3
+    assert np.all(np.diff(col[:, :3].sum(-1)) >= -1e-3)  # so does the in-scattered luminance
+    # lookup: texel centres reproduce the texel; t -> 0 fades to nothing; clamp to edge beyond the last slice
+    z = 10
+    t_centre = ((z + 0.5) / 32.0) ** 2 * 32.0 * 4.0
+    got = oracle.aerial_lookup(vol, (16 + 0.5) / 32, (16 + 0.5) / 32, t_centre)
+    assert np.allclose(got, v[z, 16, 16], rtol=2e-3, atol=1e-6)
+    assert np.all(oracle.aerial_lookup(vol, 0.5, 0.5, 0.0) == 0.0)
+    near = oracle.aerial_lookup(vol, 0.5, 0.5, 0.01)
+    assert 0.0 < near[3] < 1e-3
+    assert np.allclose(oracle.aerial_lookup(vol, 0.5, 0.5, 500.0), oracle.aerial_lookup(vol, 0.5, 0.5, 127.9), rtol=0.05)
+
+
+def test_aerial_perspective_dims_a_far_wall_and_adds_inscatter(oracle, sky_inputs, blue_noise):
+    atmo = sky_inputs[0]
+    w, h, spp = 48, 27, 4
+    pos, idx, alb = far_wall_scene()
+    cam = oracle.make_camera(w, h, (0.0, 0.0, 0.1), 90.0, 0.0, vfov_deg=30.0)
+    pc, sc = oracle.constants(cam, frame=1)
+    trans, multi, view = oracle.sky_luts(atmo, cam.position[:])
+    vol = oracle.aerial_perspective(atmo, trans, multi, pc, cam.position[:])
+    osc = oracle.Scene(pos, idx, alb)
+    plain, vis, _ = osc.render(w, h, pc, sc, blue_noise, atmo, trans, view, spp, 1, use_bvh=False)
+    hazy, vis2, _ = osc.render(w, h, pc, sc, blue_noise, atmo, trans, view, spp, 1, use_bvh=False, ext=oracle.EXT_AERIAL, aerial=vol)
+    assert np.array_equal(vis, vis2) and (vis != oracle.NONE_ID).mean() > 0.9
+    hit = vis != oracle.NONE_ID
+    ys, xs = np.nonzero(hit)
+    for y, x in list(zip(ys, xs))[::97]:
+        # same RNG stream: per pixel hazy = plain * (1 - a) + spp * inscatter, with the pixel's own lookup
+        o, d = oracle.ray_gen(pc, x, y, w, h)
+        t = (30.0 - o[1]) / d[1]
+        ap = oracle.aerial_lookup(vol, (x + 0.5) / w, (y + 0.5) / h, t)
+        want = plain[y, x, :3] * (1.0 - ap[3]) + spp * ap[:3]
+        assert np.allclose(hazy[y, x, :3], want, rtol=2e-4, atol=1e-5), (x, y)
+        assert 0.2 < ap[3] < 0.6                     # 30 km of air: a third of the light is gone
+    assert np.array_equal(hazy[~hit], plain[~hit])   # escaping primary rays are left alone
