@@ -3,6 +3,8 @@
 // last framebuffer as a PPM.  Like the reference (InflightFrames = 3, src/gfx/renderer.ixx:36) it keeps up to 3
 // frames in flight: draw() rotates the frame contexts and the framebuffer of frame i is copied out while frames
 // i+1, i+2 render.  Usage: minote_headless <blue_noise.rgba8> [frames] [width height] [out.ppm] [frames in flight]
+// With `--script events.txt` as the first arguments the frames are driven by the scripted front end (minote.frontend: the
+// events of the reference's window + ImGui panels):  minote_headless --script events.txt <blue_noise.rgba8> [w h]
 // With `--gpus N` as the first arguments the same frames are rendered tile-partitioned over N GPUs through the
 // C ABI's mrt_group_* (replicated scene, NCCL gather of the RGBA8 framebuffer every frame):
 //        minote_headless --gpus N <blue_noise.rgba8> [frames] [width height] [out.ppm]
@@ -20,6 +22,7 @@ import minote.renderer;
 import minote.freecam;
 import minote.modules.pathtracer;
 import minote.modules.sky;
+import minote.frontend;
 
 // Tile-partitioned multi-GPU loop: one process, N devices, everything behind the C ABI.
 static int run_group(int ngpus, std::uint8_t const* bn, int frames, u32 w, u32 h, char const* out) {
@@ -82,6 +85,62 @@ int main(int argc, char** argv) try {
         ngpus = std::atoi(argv[2]);
         argc -= 2;
         argv += 2;
+    }
+    char const* script = nullptr;
+    if (argc > 2 && argv[1][0] == '-' && argv[1][1] == '-' && argv[1][2] == 's') {  // --script file
+        script = argv[2];
+        argc -= 2;
+        argv += 2;
+    }
+    if (script) {
+        if (argc < 2) {
+            std::fprintf(stderr, "usage: minote_headless --script events.txt <blue_noise.rgba8> [width height]\n");
+            return EXIT_FAILURE;
+        }
+        u32 const w = argc > 3 ? std::atoi(argv[2]) : 960, h = argc > 3 ? std::atoi(argv[3]) : 540;
+        std::size_t const bnBytes = 256 * 256 * 4;
+        auto* bn = static_cast<std::uint8_t*>(std::malloc(bnBytes));
+        FILE* bf = std::fopen(argv[1], "rb");
+        if (!bf || std::fread(bn, 1, bnBytes, bf) != bnBytes) {
+            std::fprintf(stderr, "cannot read 256x256 RGBA8 blue noise from %s\n", argv[1]);
+            return EXIT_FAILURE;
+        }
+        std::fclose(bf);
+        Cuda::Provider cuda(0, 1);  // every frame is shown before the next one is drawn: one frame in flight
+        Renderer::Provider renderer(uvec2{w, h}, bn, uvec2{256u, 256u});
+        mrt_sphere const spheres[5] = {{{0.0000f, 0.0017f, 0.10000f}, 0.00050f, {0.2f, 0.7f, 0.0f}},
+                                       {{-0.0008f, 0.0012f, 0.09983f}, 0.00033f, {0.0f, 0.2f, 0.7f}},
+                                       {{0.0008f, 0.0012f, 0.09983f}, 0.00033f, {0.7f, 0.0f, 0.2f}},
+                                       {{0.0000f, 0.0008f, 0.09975f}, 0.00025f, {1.0f, 1.0f, 1.0f}},
+                                       {{0.0000f, 0.0010f, -0.00050f}, 0.10000f, {0.5f, 0.5f, 0.5f}}};
+        Renderer::serv->setSpheres(spheres, 5);
+        auto camera = Camera{{w, h}, 60_deg, 0.001f, {0.0f, -0.001f, 0.1f}, 90_deg, 0.0f, 1.0f / 256.0f, 8.0f};  // src/app.ixx:20-32
+        Frontend ui(script);
+        std::size_t const fbBytes = std::size_t(w) * h * 4;
+        auto* fb = static_cast<std::uint8_t*>(std::malloc(fbBytes));
+        float frameTime = 1.0f / 60.0f;
+        auto now = [] {
+            timespec ts;
+            clock_gettime(CLOCK_MONOTONIC, &ts);
+            return double(ts.tv_sec) + 1e-9 * double(ts.tv_nsec);
+        };
+        for (int i = 0;; i++) {
+            double const t0 = now();
+            bool const more = ui.beginFrame(i, *Renderer::serv);          // Window::poll + ImGui widgets
+            ui.freecam.updateCamera(camera, ui.fixedFrameTime > 0.0f ? ui.fixedFrameTime : frameTime);
+            Renderer::serv->draw(camera);
+            if (ui.wantsPresent()) {
+                Renderer::serv->readFramebuffer(fb, fbBytes);
+                ui.presentAll(fb, w, h);
+            }
+            frameTime = float(now() - t0);
+            std::printf("frame %d  Frame time: %.2f ms  camera %.8f %.8f %.8f yaw %.6f pitch %.6f\n", i, frameTime * 1000.0f,
+                        camera.position.x(), camera.position.y(), camera.position.z(), camera.yaw, camera.pitch);
+            if (!more) break;
+        }
+        std::free(fb);
+        std::free(bn);
+        return EXIT_SUCCESS;
     }
     if (argc < 2) {
         std::fprintf(stderr, "usage: %s <blue_noise.rgba8 (256x256 raw)> [frames] [width height] [out.ppm] [frames in flight 1..3]\n", argv[0]);

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_nee.py -m gpu -q -x 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_frontend.py -m gpu -q -x 2>&1 | tail -25
