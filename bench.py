@@ -697,14 +697,29 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         blk = measure_tiles(args, args.steps, args.warmup, world, rank, local)
+        # the single-GPU base of this strong-scaling point, measured in the same job: rank 0 renders the same workload
+        # alone (same steps, same frames in flight) while the other ranks wait
+        base = None
+        if rank == 0 and not args.no_single_gpu_base:
+            try:
+                b1 = measure_tiles(args, args.steps, args.warmup, 1, 0, local)
+                base = {"n_gpus": 1, "value": b1["value"], "ms_per_step": b1["ms_per_step"], "e2e": b1["e2e"]["value"],
+                        "framebuffer_sha256_16": b1["details"]["framebuffer_sha256_16"],
+                        "speedup": b1["ms_per_step"] / blk["ms_per_step"],
+                        "same_framebuffer": b1["details"]["framebuffer_sha256_16"] == blk["details"]["framebuffer_sha256_16"]}
+            except Exception as e:
+                base = {"error": str(e)[:300]}
+        dist.barrier()
         if rank == 0:
             line = {"metric": METRIC, "value": blk["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                     "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                     "data": "synthetic"}
             line.update({k: blk[k] for k in ("config", "details", "clocks", "e2e", "gpu_launches", "roofline", "kernels", "ms_per_displayed_frame")})
             line["cpu_baseline"] = None
+            line["single_gpu_base"] = base
             line["note"] = ("strong scaling of BASELINE config 4 (fixed 4K / 8 spp per displayed frame); its single-GPU base is "
-                            "configs[tiles_4k_progressive] of the N = 1 line, not that line's `value` (config 2)")
+                            "`single_gpu_base` (the same workload on rank 0's GPU alone, measured in this job; also "
+                            "configs[tiles_4k_progressive] of the N = 1 line), not the N = 1 line's `value` (config 2)")
             print(json.dumps(line), flush=True)
         dist.destroy_process_group()
         return
@@ -758,6 +773,7 @@ def main():
     ap.add_argument("--no-trace-timing", action="store_true", help="A/B: drop the per-launch CUDA events (roofline fields become 0)")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="extra mrt_set_option switches (A/B experiments)")
     ap.add_argument("--frames-in-flight", type=int, default=3, help="frame contexts of the e2e / pipelined measurements at N = 1 (reference: 3)")
+    ap.add_argument("--no-single-gpu-base", action="store_true", help="N > 1: skip rank 0's single-GPU run of the same workload")
     ap.add_argument("--tile-frames-in-flight", type=int, default=6, help="frame contexts per rank of the tile-partitioned progressive workload (config 4)")
     ap.add_argument("--builder", default="ploc", choices=["ploc", "lbvh"], help="binary hierarchy under the 8-wide BVH")
     args = ap.parse_args()
