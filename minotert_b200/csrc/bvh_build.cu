@@ -292,6 +292,22 @@ __global__ void __launch_bounds__(256) k_leaf_boxes(const float4* __restrict__ p
 #define PLOC_TAIL LOOP_THREADS  // clusters at which CTA 0 takes over (one position per thread)
 #endif
 
+// Search radius of a round with m clusters left.  PLOC_TOP_RADIUS > 0: the rounds that build the TOP of the tree (few
+// clusters left, each a large region) look further than the configured radius -- nearest-neighbour quality matters most
+// where boxes are biggest, and a round over a few thousand clusters costs the same whatever the radius.
+#ifndef PLOC_TOP_RADIUS
+#define PLOC_TOP_RADIUS 0
+#endif
+#ifndef PLOC_TOP_CLUSTERS
+#define PLOC_TOP_CLUSTERS 16384
+#endif
+MRT_D int ploc_radius_for(int radius, uint32_t m) {
+#if PLOC_TOP_RADIUS > 0
+    if (m <= (uint32_t)PLOC_TOP_CLUSTERS) return max(radius, PLOC_TOP_RADIUS);
+#endif
+    return radius;
+}
+
 struct PlocLoop {
     uint32_t n;
     int radius;
@@ -386,7 +402,7 @@ MRT_D uint2 ploc_round(const PlocLoop& A, uint32_t m, int cur, uint32_t next_nod
     // phase 1: nearest neighbour of every position.  A CTA takes LOOP_THREADS consecutive positions at a time and stages
     // the boxes of that window (+- radius) in shared memory: one gather per position instead of one per pair.
     {
-        const int radius = A.radius;
+        const int radius = ploc_radius_for(A.radius, m);
         for (uint32_t t0 = b * LOOP_THREADS; t0 < m; t0 += nb * LOOP_THREADS) {
             const int w0 = (int)t0 - radius;                       // window = positions [w0, w0 + LOOP_THREADS + 2 radius)
             for (int q = threadIdx.x; q < LOOP_THREADS + 2 * radius; q += LOOP_THREADS) {
