@@ -215,7 +215,13 @@ MRT_D float2 add2(unsigned long long a, unsigned long long b) {
 }
 
 // Per-CTA shared memory of the traversal kernels: the lanes' stack columns and two bit-shuffle tables.
+#ifndef TRACE_COOP_TRI
+#define TRACE_COOP_TRI 0     // triangle steps of the persistent loop: pending (ray, triangle) pairs spread over ALL lanes of the warp
+#endif
 struct TraceShared {
+#if TRACE_COOP_TRI
+    uint2 pairs[TRACE_BLOCK / 32][64];   // per warp: (triangle, owner lane) of the pairs of one triangle step
+#endif
     uint2 stack[TRACE_SM_STACK][TRACE_BLOCK];
     uint32_t expand3[256];        // bit j -> bits 3j..3j+2
     unsigned char perm[8][256];   // perm[c][x]: bit (s ^ c) = bit s of x
@@ -399,6 +405,73 @@ MRT_D void lane_tri_step(LaneState& L, const BvhDev& bvh, TraceCounters& cnt) {
     }
 }
 
+#if TRACE_COOP_TRI
+// Cooperative triangle step (all 32 lanes call it).  ncu: triangle steps are 22 % of the bounce kernel's issue slots and run
+// with ~11 of 32 lanes -- the lanes that hold pending triangles test up to two of them one after the other while the rest of
+// the warp waits.  Here every lane with pending triangles contributes up to two (ray, triangle) PAIRS; the pairs are numbered
+// with two ballots, published through shared memory, and lane w tests pair w: it fetches the owner's ray (origin, shear) with
+// shuffles, runs the same watertight test, and the owner reads the results of its pairs back with shuffles and merges them
+// with hit_consider -- closest hit is the lexicographic minimum of (t, primitive id), so who tested what does not matter.
+// ~20 pairs from ~12 lanes become ONE test round with ~20 lanes instead of two rounds with 12 and 9.
+MRT_D void warp_tri_step_coop(LaneState& L, const BvhDev& bvh, TraceCounters& cnt, bool want_tri, uint2* pairs) {
+    const unsigned FULL = 0xFFFFFFFFu, lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    uint32_t mine[2] = {0u, 0u};
+    unsigned n = 0;
+    if (want_tri) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (k == 1 && !(L.tg.y | L.tg2.y)) break;
+            const bool old = L.tg2.y != 0u;
+            const unsigned bits = old ? L.tg2.y : L.tg.y;
+            const unsigned bit = __ffs(bits) - 1;
+            mine[k] = (old ? L.tg2.x : L.tg.x) + __popc((old ? L.tg2mask : L.tgmask) & ((1u << bit) - 1u));
+            if (old) L.tg2.y = bits & (bits - 1);
+            else L.tg.y = bits & (bits - 1);
+            n = k + 1;
+        }
+    }
+    const unsigned b1 = __ballot_sync(FULL, n >= 1), b2 = __ballot_sync(FULL, n == 2);
+    const unsigned pre = __popc(b1 & lt) + __popc(b2 & lt);
+    const unsigned P = __popc(b1) + __popc(b2);
+    if (n >= 1) pairs[pre] = make_uint2(mine[0], lane);
+    if (n == 2) pairs[pre + 1] = make_uint2(mine[1], lane);
+    __syncwarp();
+    const int kpack = L.rs.kx | (L.rs.ky << 2) | (L.rs.kz << 4);
+#pragma unroll 1
+    for (unsigned base = 0; base < P; base += 32) {  // one round unless more than 32 pairs are pending
+        const unsigned w = base + lane;
+        const bool work = w < P;
+        uint2 pr = make_uint2(0u, lane);
+        if (work) pr = pairs[w];
+        const float3 o = f3(__shfl_sync(FULL, L.o.x, pr.y), __shfl_sync(FULL, L.o.y, pr.y), __shfl_sync(FULL, L.o.z, pr.y));
+        RayShear rs;
+        rs.Sx = __shfl_sync(FULL, L.rs.Sx, pr.y);
+        rs.Sy = __shfl_sync(FULL, L.rs.Sy, pr.y);
+        rs.Sz = __shfl_sync(FULL, L.rs.Sz, pr.y);
+        const int kp = __shfl_sync(FULL, kpack, pr.y);
+        rs.kx = kp & 3; rs.ky = (kp >> 2) & 3; rs.kz = kp >> 4;
+        float t = 0.0f;
+        uint32_t prim = MRT_MISS_ID;
+        if (work) {
+            const float4* tp = bvh.tris + 3 * (size_t)pr.x;
+            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+            cnt.tris++;
+            if (tri_test(o, rs, f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), t)) prim = __float_as_uint(v0.w);
+        }
+        // results travel back to the owners (slots pre, pre + 1 if they fall into this round)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const unsigned slot = pre + k - base;
+            const float tk = __shfl_sync(FULL, t, slot & 31u);
+            const uint32_t pk = __shfl_sync(FULL, prim, slot & 31u);
+            if ((unsigned)k < n && slot < 32u && pk != MRT_MISS_ID) hit_consider(L.hit, tk, mine[k], pk);
+        }
+    }
+    __syncwarp();  // the pair list is rewritten by the next triangle step
+    if (L.hit.prim != MRT_MISS_ID) L.tlimit = L.hit.t * TRACE_KFAR;
+}
+#endif
+
 // Persistent warp loop.  Job supplies the rays and consumes the hits:
 //   uint32_t Job::count() const;                          rays in this wave
 //   bool     Job::load(uint32_t i, float3& o, float3& d); false => ray i does not exist (padding)
@@ -483,6 +556,12 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
         // for every node lane, so a triangle step runs once a third of the lanes still working want one
         const int tri_min = exhausted ? min(TRACE_TRI_MIN, max(1, (__popc(tmask | nmask) + TRACE_DRAIN_TRI - 1) / TRACE_DRAIN_TRI)) : TRACE_TRI_MIN;
         if (tmask && (nmask == 0u || __popc(tmask) >= tri_min)) {
+#if TRACE_COOP_TRI && TRACE_POSTPONE
+            warp_tri_step_coop(L, bvh, cnt, want_tri, S.pairs[threadIdx.x >> 5]);
+            if (Job::ANY_HIT && L.hit.prim != MRT_MISS_ID) {  // shadow rays: the first hit ends the ray
+                L.ng.y = 0u; L.tg.y = 0u; L.tg2.y = 0u; L.sp = 0;
+            }
+#else
             if (want_tri) {
                 constexpr bool PP = TRACE_POSTPONE != 0;
                 lane_tri_step<PP>(L, bvh, cnt);
@@ -494,6 +573,7 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
                     L.ng.y = 0u; L.tg.y = 0u; L.tg2.y = 0u; L.sp = 0;
                 }
             }
+#endif
         } else if (nmask) {
 #if TRACE_NODE_REPEAT > 1 && TRACE_POSTPONE
             // several node steps per trip round the loop: the refill check, the two ballots and the step choice (~35 warp

@@ -42,6 +42,12 @@ def render(scene, w, h, spp, bounces, opts):
 def main():
     scene, w, h, spp, bounces = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
     opts = [(kv.split("=")[0], int(kv.split("=")[1])) for kv in sys.argv[6:]]
+    if not opts:  # no option given: print the hashes of the buffers (compare two library variants, MINOTERT_LIB_DIR)
+        import hashlib
+        a = render(scene, w, h, spp, bounces, [])
+        print("HASHES", " ".join(f"{k}:{hashlib.sha256(np.ascontiguousarray(v).tobytes()).hexdigest()[:12]}" for k, v in a.items() if k != "overflows"),
+              "overflows", a["overflows"])
+        return
     a = render(scene, w, h, spp, bounces, [])
     b = render(scene, w, h, spp, bounces, opts)
     ok = True
