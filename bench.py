@@ -336,6 +336,8 @@ def measure_frames(args, wl, steps, warmup, local, detail):
             cam = host.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
             ntris = int(idx.shape[0])
         r.configure(samples=spp, bounces=bounces, accumulate=False, tonemap="amd", exposure=1.0)
+        if args.secondary_flags and not spheres:  # A/B of the sky extensions: the same flags through Renderer::draw
+            r.set_sky_extensions(bool(args.secondary_flags & capi.SECONDARY_NEE_SUN), bool(args.secondary_flags & capi.SECONDARY_SKY_AT_HIT))
         ctx = r.context()
         frame_ctxs = [r.context(i) if i else ctx for i in range(in_flight)]
         for _ in range(in_flight):
@@ -355,7 +357,7 @@ def measure_frames(args, wl, steps, warmup, local, detail):
         def frame(c, frame_no):
             pc, sc = host.camera_constants(cam, cam, frame_no)
             c.primary_rays(w, h, pc)
-            c.secondary_rays(sc, spp, bounces, 0)
+            c.secondary_rays(sc, spp, bounces, args.secondary_flags)
             c.tonemap("amd", 1.0, AMD, src)
 
         # The sequential pass runs one frame at a time on frame context 0: its traversal grids fill every SM.
@@ -487,7 +489,7 @@ def measure_frames(args, wl, steps, warmup, local, detail):
                "details": {"bvh_bytes": int(build_stats.bvh_bytes), "wide_nodes": int(build_stats.num_wide_nodes),
                            "bvh_build_ms": build_stats.ms_build, "builder": args.builder, "stack_overflows": int(ctx.stats().stack_overflows),
                            "sah_node_cost": build_stats.sah_node_cost, "sah_tri_cost": build_stats.sah_tri_cost,
-                           "frames_in_flight_e2e": in_flight, "options": args.opt},
+                           "frames_in_flight_e2e": in_flight, "options": args.opt, "secondary_flags": args.secondary_flags},
                "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 44 + 324 + 272 + 36,
                        "d2h_bytes_per_step": int(nbytes), "ms_per_step": 1e3 * e2e_s / e2e_steps, "frames_in_flight": in_flight},
                "gpu_launches": int(launches),
@@ -773,6 +775,7 @@ def main():
     ap.add_argument("--no-trace-timing", action="store_true", help="A/B: drop the per-launch CUDA events (roofline fields become 0)")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="extra mrt_set_option switches (A/B experiments)")
     ap.add_argument("--frames-in-flight", type=int, default=3, help="frame contexts of the e2e / pipelined measurements at N = 1 (reference: 3)")
+    ap.add_argument("--secondary-flags", type=int, default=0, help="extra mrt_secondary_rays flags for A/B runs (8: sun sampling, 16: sky at hit); the headline uses 0")
     ap.add_argument("--no-single-gpu-base", action="store_true", help="N > 1: skip rank 0's single-GPU run of the same workload")
     ap.add_argument("--tile-frames-in-flight", type=int, default=6, help="frame contexts per rank of the tile-partitioned progressive workload (config 4)")
     ap.add_argument("--builder", default="ploc", choices=["ploc", "lbvh"], help="binary hierarchy under the 8-wide BVH")
