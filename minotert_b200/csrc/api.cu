@@ -171,7 +171,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->visibility); dev_free(ctx->depth); dev_free(ctx->normal); dev_free(ctx->motion); dev_free(ctx->color16);
     dev_free(ctx->denoised); dev_free(ctx->dn_taps);
     for (int k = 0; k < 2; k++) { dev_free(ctx->tp_rgba[k]); dev_free(ctx->tp_count[k]); dev_free(ctx->tp_vis[k]); }
-    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->frame_sum); dev_free(ctx->aerial16); dev_free(ctx->aerial_f); for (auto& q : ctx->shadow_q) dev_free(q); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
+    dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->frame_sum); dev_free(ctx->sun_e); dev_free(ctx->aerial16); dev_free(ctx->aerial_f); for (auto& q : ctx->shadow_q) dev_free(q); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
     dev_free(ctx->hit0_pos); dev_free(ctx->hit0_n); dev_free(ctx->path_state);
     for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); }
     dev_free(ctx->hits); dev_free(ctx->queue_counts); dev_free(ctx->sort_keys); dev_free(ctx->sort_keys_alt);

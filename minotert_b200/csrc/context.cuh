@@ -141,6 +141,7 @@ struct mrt_context {
     DevArray<uint16_t> depth, normal, motion, color16;
     DevArray<float> hit_t;
     DevArray<float4> accum;
+    DevArray<float4> sun_e;        // MRT_SECONDARY_NEE_SUN: sun-centre radiance at the camera, one value per frame
     DevArray<float4> shadow_q[3];  // MRT_SECONDARY_NEE_SUN: shadow-ray queue (origin|pixel, direction, contribution)
     uint32_t shadow_counts_at = 0, num_shadow_counts = 0;  // where the shadow-queue sizes sit in queue_counts
     DevArray<float4> frame_sum;    // MRT_SECONDARY_FRAME_SUM: this frame's radiance sums (xyz) and samples (w)

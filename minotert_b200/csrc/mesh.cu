@@ -718,6 +718,7 @@ struct ShadeArgs {
     unsigned long long* overflow; // error counter (mrt_stats.stack_overflows) for a fused worker that gave up waiting
     const float4* aerial;         // MRT_SECONDARY_AERIAL: decoded camera volume; hit_t = distance of the primary hit
     const float* hit_t;
+    const float4* sun_e;          // MRT_SECONDARY_NEE_SUN: the sun centre's radiance seen from the camera (k_sun_centre)
     float4* sh_o;                 // MRT_SECONDARY_NEE_SUN: shadow-ray queue of this vertex (origin|pixel, direction, contribution)
     float4* sh_d;
     float4* sh_c;
@@ -817,7 +818,14 @@ MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
                     const float ndotl = dot3(n, sl);
                     if (ndotl > 0.0f) {
                         const float3 so = pos + n * RAY_OFFSET;
-                        const float3 E = sky_sun_centre_radiance(a.A, a.luts, (P.ext & MRT_SECONDARY_SKY_AT_HIT) ? so : P.cameraPos);
+                        // at the camera position E is one value per frame: k_sun_centre evaluated it once (same function, same bits)
+                        float3 E;
+                        if (P.ext & MRT_SECONDARY_SKY_AT_HIT) {
+                            E = sky_sun_centre_radiance(a.A, a.luts, so);
+                        } else {
+                            const float4 e4 = __ldg(a.sun_e);
+                            E = f3(e4.x, e4.y, e4.z);
+                        }
                         if (E.x > 0.0f || E.y > 0.0f || E.z > 0.0f) {
                             sc = (thr * E) * (ndotl * wgt);
                             emit_shadow = true;
@@ -863,6 +871,11 @@ MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
 #ifndef SHADE_REGROUP
 #define SHADE_REGROUP 1  // bounce waves: order the CTA's 256 vertices hits-first so that warps do not run both branches
 #endif
+
+__global__ void k_sun_centre(mrt_atmosphere_params A, SkyLuts luts, float3 cameraPos, float4* out) {
+    const float3 e = sky_sun_centre_radiance(A, luts, cameraPos);
+    out[0] = make_float4(e.x, e.y, e.z, 0.0f);
+}
 
 // Shade stage as its own kernel: one thread per path vertex.
 template <bool FIRST>
@@ -1372,6 +1385,12 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     sa.bvh = make_bvh(ctx);
     sa.A = ctx->atmo;
     sa.luts = SkyLuts{ctx->trans_f.p, nullptr, ctx->view_f.p};
+    if (nee) {
+        MRT_TRY(dev_reserve(ctx, ctx->sun_e, 1));
+        k_sun_centre<<<1, 1, 0, ctx->stream>>>(sa.A, sa.luts, P.cameraPos, ctx->sun_e.p);
+        MRT_LAUNCHED(ctx);
+        sa.sun_e = ctx->sun_e.p;
+    }
     sa.bn = ctx->bn;
     sa.albedo = ctx->albedo.p;
     sa.hit0_pos = ctx->hit0_pos.p;
