@@ -53,6 +53,9 @@ MRT_D void flush_counters(const TraceCounters& c, unsigned long long* counters, 
 // ---- primary pass: primaryRay.comp:38-76 with the 5-sphere loop replaced by BVH traversal ----
 // Ray index r -> 8x4-pixel tile r/32 (row-major tile grid), pixel r%32 inside it, so the 32 rays a fresh
 // warp takes are one compact tile (coherent) and padding pixels are skipped by load().
+#ifndef PRIMARY_TILE_W
+#define PRIMARY_TILE_W 8u   // pixels per tile row of a warp's 32-pixel tile (8 x 4; A/B: 4 x 8, 16 x 2, 32 x 1)
+#endif
 struct PrimaryJob {
     static constexpr bool ANY_HIT = false;
     MeshFrame F;
@@ -66,8 +69,8 @@ struct PrimaryJob {
     MRT_D uint32_t count() const { return tiles * 32u; }
     MRT_D bool pixel(uint32_t i, uint32_t& x, uint32_t& lr) const {
         uint32_t tile = i >> 5, in = i & 31u;
-        x = (tile % tiles_x) * 8u + (in & 7u);
-        lr = (tile / tiles_x) * 4u + (in >> 3);
+        x = (tile % tiles_x) * PRIMARY_TILE_W + (in % PRIMARY_TILE_W);
+        lr = (tile / tiles_x) * (32u / PRIMARY_TILE_W) + (in / PRIMARY_TILE_W);
         return x < F.gen.W && lr < F.local_rows;
     }
     MRT_D bool load(uint32_t i, float3& o, float3& d) const {
@@ -1241,8 +1244,8 @@ int mesh_primary(mrt_context* ctx) {
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     MRT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p + 8, 0, sizeof(uint32_t), ctx->stream));
     J.bvh = make_bvh(ctx);
-    J.tiles_x = div_up(ctx->W, 8);
-    J.tiles = J.tiles_x * div_up(ctx->local_rows, 4);
+    J.tiles_x = div_up(ctx->W, PRIMARY_TILE_W);
+    J.tiles = J.tiles_x * div_up(ctx->local_rows, 32u / PRIMARY_TILE_W);
     J.vis = ctx->visibility.p; J.depth = ctx->depth.p; J.normal = ctx->normal.p; J.motion = ctx->motion.p;
     J.hit_t = ctx->hit_t.p; J.hit0_pos = ctx->hit0_pos.p; J.hit0_n = ctx->hit0_n.p;
     if (ctx->opt_persistent_primary)
