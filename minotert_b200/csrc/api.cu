@@ -204,6 +204,8 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "sort_rays")) ctx->opt_sort_rays = (int)(value < 0 ? 0 : (value > 2 ? 2 : value));
     else if (!strcmp(name, "persistent_primary")) ctx->opt_persistent_primary = value != 0;
     else if (!strcmp(name, "primary_batched")) ctx->opt_primary_batched = value != 0;
+    else if (!strcmp(name, "shadow_coherent")) ctx->opt_shadow_coherent = value != 0;
+    else if (!strcmp(name, "trace_carveout")) ctx->opt_trace_carveout = (int)value;
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;
     else if (!strcmp(name, "primary_entry")) ctx->opt_primary_entry = value != 0;

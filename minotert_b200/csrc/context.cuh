@@ -67,6 +67,8 @@ struct mrt_context {
     int opt_count_visits = 0;
     int opt_sort_rays = 0;
     int opt_persistent_primary = 0;  // run primary rays through the persistent state machine too (A/B switch)
+    int opt_trace_carveout = -1;     // cudaFuncAttributePreferredSharedMemoryCarveout of the traversal kernels (-1: driver default)
+    int opt_shadow_coherent = 0;     // MRT_SECONDARY_NEE_SUN: shadow rays through the per-lane loop of the primary pass (A/B)
     int opt_primary_batched = 0;     // primary rays: warp-voted triangle steps (trace_coherent_batched) instead of the per-lane loop
     int opt_trace_timing = 1;        // CUDA event pair around every bounce-wave traversal launch (mrt_stats.ms_trace)
     int opt_primary_entry = 0;       // primary pass: walk the top of the BVH once per 32x16 tile against its frustum (entry list), then per ray; measured slower

@@ -670,6 +670,25 @@ struct ShadowJob {
     }
 };
 
+// Shadow rays with the per-lane loop of the primary pass (option "shadow_coherent"): all of them point into the sun's
+// 0.5-degree disc -- one direction octant, parallel within half a degree -- and the queue of the first vertex is in pixel
+// order, so neighbouring lanes walk the same nodes.
+__global__ void __launch_bounds__(TRACE_BLOCK, PRIMARY_MIN_BLOCKS)
+k_shadow_coherent(ShadowJob job, BvhDev bvh, unsigned long long* counters, int count_visits, unsigned long long* total_rays) {
+    __shared__ TraceShared S;
+    trace_shared_init(S);
+    const uint32_t n = job.count();
+    if (total_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total_rays, (unsigned long long)n);
+    TraceCounters cnt{0, 0, 0};
+    for (uint32_t i = blockIdx.x * TRACE_BLOCK + threadIdx.x; i < n; i += gridDim.x * TRACE_BLOCK) {
+        float3 o, d;
+        job.load(i, o, d);
+        const TraceHit h = trace_coherent<true>(bvh, o, d, S, cnt);
+        job.store(i, h);
+    }
+    flush_counters(cnt, counters, count_visits != 0);
+}
+
 template <class Job>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
 k_trace(Job job, BvhDev bvh, uint32_t* work_counter, unsigned long long* counters, int count_visits,
@@ -1323,6 +1342,17 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     }
     const uint32_t waves = spp * bounces;
     const bool fused = ctx->opt_fused_shade != 0 && !nee;
+    {   // L1 / shared-memory split of the traversal kernels (option "trace_carveout": percent of the 228 KB that is shared
+        // memory; -1 = the driver's choice).  6 CTAs x 13.3 KB need 86 KB; what is not shared memory is L1 for the BVH.
+        static int applied[64] = {0};
+        int& a = applied[ctx->device & 63];
+        if (a != ctx->opt_trace_carveout + 2) {
+            cudaFuncSetAttribute(k_trace<QueueJob>, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->opt_trace_carveout);
+            cudaFuncSetAttribute(k_trace<ShadowJob>, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->opt_trace_carveout);
+            cudaFuncSetAttribute(k_mesh_primary<false>, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->opt_trace_carveout);
+            a = ctx->opt_trace_carveout + 2;
+        }
+    }
     // sort mode: 0 none, 1 direction octant (binning), 2 (origin cell, octant) (radix sort); the flag asks for the configured
     // mode, or the octant binning when none is configured
     const int sort_mode = ctx->opt_sort_rays ? ctx->opt_sort_rays : ((flags & MRT_SECONDARY_SORT_RAYS) ? 1 : 0);
@@ -1445,8 +1475,12 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
                     // the shadow rays of the vertex just shaded: any-hit traversal, free rays add their sun light to the
                     // accumulator; on the same stream, i.e. before the shade stage below touches the same pixels
                     ShadowJob SJ{sa.sh_o, sa.sh_d, sa.sh_c, sh_counts + wave, sa.accum};
-                    k_trace<ShadowJob><<<tgrid, TRACE_BLOCK, 0, st>>>(SJ, sa.bvh, sh_work + wave, ctx->visit_counters.p + 4,
-                                                                      ctx->opt_count_visits, ctx->total_rays.p, 0ull);
+                    if (ctx->opt_shadow_coherent)
+                        k_shadow_coherent<<<div_up(bpix, TRACE_BLOCK), TRACE_BLOCK, 0, st>>>(SJ, sa.bvh, ctx->visit_counters.p + 4, ctx->opt_count_visits,
+                                                                                             ctx->total_rays.p);
+                    else
+                        k_trace<ShadowJob><<<tgrid, TRACE_BLOCK, 0, st>>>(SJ, sa.bvh, sh_work + wave, ctx->visit_counters.p + 4,
+                                                                          ctx->opt_count_visits, ctx->total_rays.p, 0ull);
                     MRT_LAUNCHED(ctx);
                 }
                 const bool timed = ctx->opt_trace_timing && ctx->trace_ev_used < kMaxTimedLaunches;

@@ -602,6 +602,7 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
 // Per-lane loop for COHERENT rays (the primary pass): one node, then its triangles, per iteration.
 // Rays of an 8x4 pixel tile walk the same nodes and reach leaves together, so the warp stays
 // converged without the state machine, and testing triangles at once tightens t early.
+template <bool ANY_HIT = false>
 MRT_D TraceHit trace_coherent(const BvhDev& bvh, float3 o, float3 d, TraceShared& S, TraceCounters& cnt) {
     uint2* const sm = &S.stack[0][threadIdx.x];
     uint2 spill[TRACE_LOCAL_STACK];
@@ -610,7 +611,10 @@ MRT_D TraceHit trace_coherent(const BvhDev& bvh, float3 o, float3 d, TraceShared
     if (bvh.num_nodes == 0) return L.hit;
     for (;;) {
         if (L.ng.y & 0xFF000000u) lane_node_step<false>(L, bvh, S, spill, cnt);
-        while (L.tg.y) lane_tri_step<false>(L, bvh, cnt);
+        while (L.tg.y) {
+            lane_tri_step<false>(L, bvh, cnt);
+            if (ANY_HIT && L.hit.prim != MRT_MISS_ID) return L.hit;  // occlusion query: the first hit ends the ray
+        }
         if (!(L.ng.y & 0xFF000000u)) {
             if (L.sp == 0) break;
             L.sp--;

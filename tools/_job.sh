@@ -1,6 +1,6 @@
-for v in tile4 tile16 tile32 ""; do
-  if [ -z "$v" ]; then unset MINOTERT_LIB_DIR; t=base; else export MINOTERT_LIB_DIR=variants/$v; t=$v; fi
-  python tools/check_option.py hall_260k 1920 1080 1 1 2>&1 | tail -1
-  tools/ab.sh hall_$t --no-extra-configs; tools/ab.sh 1m_$t --no-extra-configs --workload scene_1m_1080p
-  tools/ab.sh 10m_$t --no-extra-configs --workload scene_10m_4k --steps 4
+for c in -1 38 44 58 30 100; do
+  tools/ab.sh hall_c$c --no-extra-configs --opt trace_carveout=$c; tools/ab.sh 1m_c$c --no-extra-configs --workload scene_1m_1080p --opt trace_carveout=$c
 done
+tools/ab.sh 10m_c-1 --no-extra-configs --workload scene_10m_4k --steps 4 --opt trace_carveout=-1
+tools/ab.sh 10m_c38 --no-extra-configs --workload scene_10m_4k --steps 4 --opt trace_carveout=38
+tools/ab.sh 10m_c44 --no-extra-configs --workload scene_10m_4k --steps 4 --opt trace_carveout=44

@@ -28,7 +28,7 @@ def render(scene, w, h, spp, bounces, opts):
         c.atmosphere(host.atmosphere_earth())
         c.sky_view(cam.position[:], (-0.435286462, 0.818654716, 0.374606609), (8.0, 8.0, 8.0))
         c.primary_rays(w, h, pc)
-        c.secondary_rays(sc, spp, bounces, 0)
+        c.secondary_rays(sc, spp, bounces, int(os.environ.get("CHECK_FLAGS", "0")))  # CHECK_FLAGS=8: sun sampling
         c.tonemap("amd", 1.0, (16.0, 2.0, 1.0, 0.18, 0.18), capi.BUF_ACCUM)
         out = {n: c.readback(b) for n, b in (("vis", capi.BUF_VISIBILITY), ("accum", capi.BUF_ACCUM), ("ldr", capi.BUF_LDR),
                                               ("depth", capi.BUF_DEPTH), ("normal", capi.BUF_NORMAL))}
