@@ -206,6 +206,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "primary_batched")) ctx->opt_primary_batched = value != 0;
     else if (!strcmp(name, "shadow_coherent")) ctx->opt_shadow_coherent = value != 0;
     else if (!strcmp(name, "trace_carveout")) ctx->opt_trace_carveout = (int)value;
+    else if (!strcmp(name, "ray_split")) ctx->opt_ray_split = (int)value;
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;
     else if (!strcmp(name, "primary_entry")) ctx->opt_primary_entry = value != 0;
@@ -643,6 +644,11 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
             MRT_CUDA(ctx, cudaMemcpy(counts.data(), ctx->queue_counts.p, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost));
             uint64_t total = 0;
             for (uint32_t v : counts) total += v;
+            if (ctx->num_back_counts) {    // option ray_split: the queues' back ends
+                counts.resize(ctx->num_back_counts);
+                MRT_CUDA(ctx, cudaMemcpy(counts.data(), ctx->queue_counts.p + ctx->back_counts_at, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost));
+                for (uint32_t v : counts) total += v;
+            }
             if (ctx->num_shadow_counts) {  // MRT_SECONDARY_NEE_SUN: shadow rays are traced rays too
                 counts.resize(ctx->num_shadow_counts);
                 MRT_CUDA(ctx, cudaMemcpy(counts.data(), ctx->queue_counts.p + ctx->shadow_counts_at, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost));

@@ -67,6 +67,7 @@ struct mrt_context {
     int opt_count_visits = 0;
     int opt_sort_rays = 0;
     int opt_persistent_primary = 0;  // run primary rays through the persistent state machine too (A/B switch)
+    int opt_ray_split = 0;           // bounce queues filled from both ends: rays with n.d < value/100 (expected long) are traced first (0: off)
     int opt_trace_carveout = -1;     // cudaFuncAttributePreferredSharedMemoryCarveout of the traversal kernels (-1: driver default)
     int opt_shadow_coherent = 0;     // MRT_SECONDARY_NEE_SUN: shadow rays through the per-lane loop of the primary pass (A/B)
     int opt_primary_batched = 0;     // primary rays: warp-voted triangle steps (trace_coherent_batched) instead of the per-lane loop
@@ -145,6 +146,7 @@ struct mrt_context {
     DevArray<float4> accum;
     DevArray<float4> sun_e;        // MRT_SECONDARY_NEE_SUN: sun-centre radiance at the camera, one value per frame
     DevArray<float4> shadow_q[3];  // MRT_SECONDARY_NEE_SUN: shadow-ray queue (origin|pixel, direction, contribution)
+    uint32_t back_counts_at = 0, num_back_counts = 0;      // option ray_split: sizes of the queues' back ends
     uint32_t shadow_counts_at = 0, num_shadow_counts = 0;  // where the shadow-queue sizes sit in queue_counts
     DevArray<float4> frame_sum;    // MRT_SECONDARY_FRAME_SUM: this frame's radiance sums (xyz) and samples (w)
     cudaEvent_t commit_ev[2] = {nullptr, nullptr};  // mrt_accum_commit: src rendered / dst consumed

@@ -495,15 +495,27 @@ struct QueueJob {
     const uint32_t* count_ptr;
     unsigned long long* hits;  // t bits | tri << 32; MRT_HIT_PENDING until the ray has been traced
     const uint32_t* order;  // optional: ray k of the sorted order is queue entry order[k] (row n5 sort stage)
-    MRT_D uint32_t count() const { return *count_ptr; }
-    MRT_D bool load(uint32_t i, float3& o, float3& d) const {
+    // option "ray_split": the shade stage fills the queue from both ends -- rays it expects to be LONG (leaving their
+    // surface at a grazing angle) from the front, the others from the back (slot cap - 1 - j) -- and the persistent launch
+    // hands the front out first, so that the long rays start early and the launch ends with short ones
+    const uint32_t* back_ptr;  // number of back entries, or nullptr
+    uint32_t cap;
+    MRT_D uint32_t count() const { return *count_ptr + (back_ptr ? *back_ptr : 0u); }
+    MRT_D uint32_t slot(uint32_t i) const {
+        if (!back_ptr) return i;
+        const uint32_t nf = *count_ptr;
+        return i < nf ? i : cap - 1u - (i - nf);
+    }
+    MRT_D bool load(uint32_t i0, float3& o, float3& d) const {
+        const uint32_t i = slot(i0);
         const uint32_t k = order ? __ldg(&order[i]) : i;
         float4 o4 = __ldg(&ray_o[k]), d4 = __ldg(&ray_d[k]);
         o = f3(o4.x, o4.y, o4.z);
         d = f3(d4.x, d4.y, d4.z);
         return true;
     }
-    MRT_D void store(uint32_t i, const TraceHit& h) const {
+    MRT_D void store(uint32_t i0, const TraceHit& h) const {
+        const uint32_t i = slot(i0);
         const uint32_t k = order ? __ldg(&order[i]) : i;  // hit records stay in queue order for the shade kernel
         // one 64-bit relaxed store: the record doubles as the "ray k is done" flag of the fused shade stage
         const unsigned long long rec = (unsigned long long)__float_as_uint(h.t) | ((unsigned long long)h.tri << 32);
@@ -737,6 +749,11 @@ struct ShadeArgs {
     float4* out_o;                // next bounce's queue
     float4* out_d;
     uint32_t* out_count;
+    uint32_t* out_back;           // option "ray_split": entries taken from the back of the next queue (nullptr: off) ...
+    uint32_t out_cap;             // ... whose capacity this is
+    const uint32_t* in_back;      // ... and the same for the traced queue this stage reads
+    uint32_t in_cap;
+    float split_cos;              // a bounce ray with n.d below this is expected to be long
     unsigned long long* overflow; // error counter (mrt_stats.stack_overflows) for a fused worker that gave up waiting
     const float4* aerial;         // MRT_SECONDARY_AERIAL: decoded camera volume; hit_t = distance of the primary hit
     const float* hit_t;
@@ -755,12 +772,13 @@ struct ShadeArgs {
 // traced wave.  FUSED: called from the traversal kernel while other warps still trace -- the lane waits for
 // its hit record and hands the sentinel back for the next wave.
 template <bool FIRST, bool FUSED>
-MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
+MRT_D void shade_vertex(uint32_t k, bool valid, const ShadeArgs& a) {
     const ShadeParams& P = a.P;
     bool emit = false, emit_shadow = false;
     float3 ro = f3s(0.0f), rd = f3s(0.0f), sl = f3s(0.0f), sc = f3s(0.0f);
     uint32_t pixel = 0;
-    if (k < count) {
+    bool long_ray = true;
+    if (valid) {
         float3 pos, n, thr;
         float3 sky_pos = P.cameraPos;  // MRT_SECONDARY_SKY_AT_HIT: the origin of the ray that escaped
         uint32_t prim, rng;
@@ -856,21 +874,38 @@ MRT_D void shade_vertex(uint32_t k, uint32_t count, const ShadeArgs& a) {
                 }
                 lambert_bounce(pos, n, rng, rot.x, rot.y, ro, rd);
                 emit = true;
+                long_ray = dot3(rd, n) < a.split_cos;
             }
             a.path_state[pixel] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
         }
     }
-    // compaction: one atomic per warp, lanes take consecutive queue slots
-    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, emit);
+    // compaction: one atomic per warp, lanes take consecutive queue slots (ray_split: a second one for the back end)
+    const bool to_front = emit && (long_ray || !a.out_back);
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, to_front);
     if (ballot) {
         const unsigned lane = threadIdx.x & 31;
         uint32_t base = 0;
         if (lane == (unsigned)(__ffs(ballot) - 1)) base = atomicAdd(a.out_count, (uint32_t)__popc(ballot));
         base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ballot) - 1);
-        if (emit) {
+        if (to_front) {
             uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
             a.out_o[slot] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(pixel));
             a.out_d[slot] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+        }
+    }
+    if (a.out_back) {
+        const bool to_back = emit && !to_front;
+        const unsigned bb = __ballot_sync(0xFFFFFFFFu, to_back);
+        if (bb) {
+            const unsigned lane = threadIdx.x & 31;
+            uint32_t base = 0;
+            if (lane == (unsigned)(__ffs(bb) - 1)) base = atomicAdd(a.out_back, (uint32_t)__popc(bb));
+            base = __shfl_sync(0xFFFFFFFFu, base, __ffs(bb) - 1);
+            if (to_back) {
+                uint32_t slot = a.out_cap - 1u - (base + __popc(bb & ((1u << lane) - 1u)));
+                a.out_o[slot] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(pixel));
+                a.out_d[slot] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+            }
         }
     }
     if (P.ext & MRT_SECONDARY_NEE_SUN) {  // shadow rays: same compaction into their own queue (origin = the bounce's)
@@ -903,8 +938,11 @@ __global__ void k_sun_centre(mrt_atmosphere_params A, SkyLuts luts, float3 camer
 template <bool FIRST>
 __global__ void __launch_bounds__(256) k_shade(ShadeArgs a, const uint32_t* __restrict__ in_count_ptr) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t count = FIRST ? a.npix : *in_count_ptr;
+    const uint32_t nfront = FIRST ? a.npix : *in_count_ptr;
+    const uint32_t count = nfront + ((!FIRST && a.in_back) ? *a.in_back : 0u);
     if (blockIdx.x * blockDim.x >= count) return;
+    bool valid = k < count;
+    if (!FIRST && a.in_back && valid && k >= nfront) k = a.in_cap - 1u - (k - nfront);  // ray_split: entry k sits at the back
 #if SHADE_REGROUP
     if (!FIRST) {
         // A hit runs the bounce (triangle fetch, sincos), a miss the sky evaluation; mixed warps execute both, one
@@ -912,7 +950,6 @@ __global__ void __launch_bounds__(256) k_shade(ShadeArgs a, const uint32_t* __re
         __shared__ uint32_t perm[256];
         __shared__ uint32_t warp_hits[8];
         const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        const bool valid = k < count;
         const bool is_hit = valid && (uint32_t)(a.hits[k] >> 32) != MRT_MISS_ID;
         const unsigned hb = __ballot_sync(0xFFFFFFFFu, is_hit);
         if (lane == 0) warp_hits[wid] = __popc(hb);
@@ -926,12 +963,13 @@ __global__ void __launch_bounds__(256) k_shade(ShadeArgs a, const uint32_t* __re
         }
         const uint32_t hit_rank = hits_before + __popc(hb & ((1u << lane) - 1u));
         const uint32_t miss_rank = (wid * 32u - hits_before) + __popc(~hb & ((1u << lane) - 1u));
-        perm[is_hit ? hit_rank : hits_total + miss_rank] = k;  // invalid lanes count as misses and stay last
+        perm[is_hit ? hit_rank : hits_total + miss_rank] = valid ? k : 0xFFFFFFFFu;  // invalid lanes count as misses and stay last
         __syncthreads();
         k = perm[threadIdx.x];
+        valid = k != 0xFFFFFFFFu;
     }
 #endif
-    shade_vertex<FIRST, false>(k, count, a);
+    shade_vertex<FIRST, false>(k, valid, a);
 }
 
 // One bounce wave, traversal + shading in one persistent launch.  A warp leaves trace_persistent() when the
@@ -954,7 +992,7 @@ k_trace_shade(QueueJob job, BvhDev bvh, uint32_t* work_counter, unsigned long lo
         if (lane == 0) c = atomicAdd(shade_counter, 32u);
         c = __shfl_sync(0xFFFFFFFFu, c, 0);
         if (c >= count) break;
-        shade_vertex<false, true>(c + lane, count, sa);
+        shade_vertex<false, true>(c + lane, c + lane < count, sa);
     }
 }
 
@@ -1304,6 +1342,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         MRT_CUDA(ctx, cudaMemsetAsync(ctx->visit_counters.p + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
         ctx->num_queue_counts = 0;
         ctx->num_shadow_counts = 0;
+        ctx->num_back_counts = 0;
         ShadeArgs sa{};
         ShadeParams& P = sa.P;
         P.cameraPos = f3(c->cameraPos[0], c->cameraPos[1], c->cameraPos[2]);
@@ -1379,7 +1418,10 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     // counters: [band][0..waves] queue sizes; then [band][wave] work counters of the persistent launches; then
     // [band][wave] chunk counters of their (fused) shade stages
     // ... then, with MRT_SECONDARY_NEE_SUN, [band][wave] shadow-queue sizes and [band][wave] their work counters
-    const size_t ncount = (size_t)bands * (3 * (size_t)waves + 3) + (nee ? 2 * (size_t)bands * waves : 0);
+    // ... then, with option ray_split, [band][0..waves] sizes of the queues' back ends
+    const bool split = ctx->opt_ray_split != 0 && !fused && !sort;
+    const size_t split_at = (size_t)bands * (3 * (size_t)waves + 3) + (nee ? 2 * (size_t)bands * waves : 0);
+    const size_t ncount = split_at + (split ? (size_t)bands * (waves + 1) : 0);
     if (nee)
         for (int q = 0; q < 3; q++) MRT_TRY(dev_reserve(ctx, ctx->shadow_q[q], npix));
     MRT_TRY(dev_reserve(ctx, ctx->queue_counts, ncount));
@@ -1389,6 +1431,8 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     ctx->num_queue_counts = bands * (waves + 1);
     ctx->shadow_counts_at = nee ? (uint32_t)(bands * (3 * (size_t)waves + 3)) : 0u;  // mrt_stats: shadow rays are secondary rays
     ctx->num_shadow_counts = nee ? bands * waves : 0u;
+    ctx->back_counts_at = split ? (uint32_t)split_at : 0u;
+    ctx->num_back_counts = split ? bands * (waves + 1) : 0u;
     if (bands > 1) {
         for (uint32_t b = 0; b < bands; b++) {
             if (!ctx->band_stream[b]) {
@@ -1457,6 +1501,9 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
             sa.sh_d = ctx->shadow_q[1].p + p0;
             sa.sh_c = ctx->shadow_q[2].p + p0;
         }
+        uint32_t* const bcounts = split ? ctx->queue_counts.p + split_at + (size_t)band * (waves + 1) : nullptr;
+        sa.out_cap = sa.in_cap = bpix;
+        sa.split_cos = 0.01f * (float)ctx->opt_ray_split;  // option value = 100 * the cosine below which a ray counts as long
         uint32_t wave = 0;
         for (uint32_t s = 0; s < spp; s++) {
             P.first_sample = s == 0;
@@ -1466,6 +1513,8 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
             sa.out_o = ray_o[q];
             sa.out_d = ray_d[q];
             sa.out_count = qcounts + wave;
+            sa.out_back = split ? bcounts + wave : nullptr;
+            sa.in_back = nullptr;
             sa.sh_count = nee ? sh_counts + wave : nullptr;
             k_shade<true><<<shade_grid, 256, 0, st>>>(sa, nullptr);
             MRT_LAUNCHED(ctx);
@@ -1512,7 +1561,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
                     MRT_LAUNCHED(ctx);
                     order = ctx->sort_vals.p;
                 }
-                QueueJob J{ray_o[q], ray_d[q], in_count, sa.hits, order};
+                QueueJob J{ray_o[q], ray_d[q], in_count, sa.hits, order, split ? bcounts + wave : nullptr, bpix};
                 const unsigned long long extra = wave == 0 ? (unsigned long long)bpix : 0ull;
                 // the shade stage of this wave: vertex b of the paths; the last vertex emits nothing (its counter slot stays 0)
                 P.vertex = b;
@@ -1521,6 +1570,8 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
                 sa.out_o = ray_o[q ^ 1];
                 sa.out_d = ray_d[q ^ 1];
                 sa.out_count = qcounts + (wave + 1 < waves ? wave + 1 : waves);
+                sa.in_back = split ? bcounts + wave : nullptr;
+                sa.out_back = split ? bcounts + (wave + 1 < waves ? wave + 1 : waves) : nullptr;
                 sa.sh_count = nee ? sh_counts + (wave + 1 < waves ? wave + 1 : 0) : nullptr;  // the last vertex emits none
                 if (fused) {
                     k_trace_shade<<<tgrid, TRACE_BLOCK, 0, st>>>(J, sa.bvh, work_counters + wave, ctx->visit_counters.p + 4,
