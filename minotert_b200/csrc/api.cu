@@ -207,6 +207,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "shadow_coherent")) ctx->opt_shadow_coherent = value != 0;
     else if (!strcmp(name, "trace_carveout")) ctx->opt_trace_carveout = (int)value;
     else if (!strcmp(name, "ray_split")) ctx->opt_ray_split = (int)value;
+    else if (!strcmp(name, "shade_tiles")) ctx->opt_shade_tiles = value != 0;
     else if (!strcmp(name, "trace_timing")) ctx->opt_trace_timing = value != 0;
     else if (!strcmp(name, "fused_shade")) ctx->opt_fused_shade = value != 0;
     else if (!strcmp(name, "primary_entry")) ctx->opt_primary_entry = value != 0;

@@ -67,6 +67,7 @@ struct mrt_context {
     int opt_count_visits = 0;
     int opt_sort_rays = 0;
     int opt_persistent_primary = 0;  // run primary rays through the persistent state machine too (A/B switch)
+    int opt_shade_tiles = 0;         // (A/B: no gain, off) vertex 0 shaded in 8x4-pixel tile order: the bounce queues hold compact patches, not row strips
     int opt_ray_split = 0;           // bounce queues filled from both ends: rays with n.d < value/100 (expected long) are traced first (0: off)
     int opt_trace_carveout = -1;     // cudaFuncAttributePreferredSharedMemoryCarveout of the traversal kernels (-1: driver default)
     int opt_shadow_coherent = 0;     // MRT_SECONDARY_NEE_SUN: shadow rays through the per-lane loop of the primary pass (A/B)

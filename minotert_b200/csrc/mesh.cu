@@ -728,6 +728,7 @@ struct ShadeParams {
     uint32_t pixel_base; // FIRST: vertex k of this launch is pixel pixel_base + k (bands of the image, see mesh_secondary)
     uint32_t ext;        // MRT_SECONDARY_NEE_SUN | MRT_SECONDARY_SKY_AT_HIT | MRT_SECONDARY_AERIAL
     uint32_t H;          // image height (aerial-perspective lookup)
+    uint32_t first_tiles_x, first_count, first_rows;  // shade_tiles: tile columns, threads (tiles * 32) and rows of vertex 0; 0: row order
 };
 
 // Everything the shade stage reads and writes (passed by value to the kernels).
@@ -771,6 +772,19 @@ struct ShadeArgs {
 // compaction).  FIRST: vertex 0, k = pixel, inputs from the primary pass.  Otherwise k = queue entry of the
 // traced wave.  FUSED: called from the traversal kernel while other warps still trace -- the lane waits for
 // its hit record and hands the sentinel back for the next wave.
+// Option "shade_tiles" (default off: measured neutral, profiles/r2_results.md): vertex 0 is shaded in the order of the primary pass' 8x4-pixel tiles, not row by row,
+// so that 32 consecutive entries of the first bounce queue -- one warp of the traversal kernel -- leave from a compact
+// 8x4 patch of the image instead of a 32x1 strip; later queues inherit the order through the compaction.  The image does not
+// depend on the order (one live path per pixel).  k -> tile k / 32 (row-major tile grid), pixel k % 32 inside it.
+MRT_D bool first_tile_valid(const ShadeParams& P, uint32_t k, uint32_t rows) {
+    const uint32_t tile = k >> 5, in = k & 31u;
+    return (tile % P.first_tiles_x) * 8u + (in & 7u) < P.W && (tile / P.first_tiles_x) * 4u + (in >> 3) < rows;
+}
+MRT_D uint32_t first_tile_pixel(const ShadeParams& P, uint32_t k) {
+    const uint32_t tile = k >> 5, in = k & 31u;
+    return ((tile / P.first_tiles_x) * 4u + (in >> 3)) * P.W + (tile % P.first_tiles_x) * 8u + (in & 7u);
+}
+
 template <bool FIRST, bool FUSED>
 MRT_D void shade_vertex(uint32_t k, bool valid, const ShadeArgs& a) {
     const ShadeParams& P = a.P;
@@ -783,7 +797,7 @@ MRT_D void shade_vertex(uint32_t k, bool valid, const ShadeArgs& a) {
         float3 sky_pos = P.cameraPos;  // MRT_SECONDARY_SKY_AT_HIT: the origin of the ray that escaped
         uint32_t prim, rng;
         if (FIRST) {
-            pixel = P.pixel_base + k;
+            pixel = P.first_tiles_x ? first_tile_pixel(P, k) : P.pixel_base + k;
             float4 hp = __ldg(&a.hit0_pos[pixel]), hn = __ldg(&a.hit0_n[pixel]);
             pos = f3(hp.x, hp.y, hp.z);
             n = f3(hn.x, hn.y, hn.z);
@@ -938,10 +952,11 @@ __global__ void k_sun_centre(mrt_atmosphere_params A, SkyLuts luts, float3 camer
 template <bool FIRST>
 __global__ void __launch_bounds__(256) k_shade(ShadeArgs a, const uint32_t* __restrict__ in_count_ptr) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t nfront = FIRST ? a.npix : *in_count_ptr;
+    const uint32_t nfront = FIRST ? (a.P.first_tiles_x ? a.P.first_count : a.npix) : *in_count_ptr;
     const uint32_t count = nfront + ((!FIRST && a.in_back) ? *a.in_back : 0u);
     if (blockIdx.x * blockDim.x >= count) return;
     bool valid = k < count;
+    if (FIRST && a.P.first_tiles_x) valid = valid && first_tile_valid(a.P, k, a.P.first_rows);
     if (!FIRST && a.in_back && valid && k >= nfront) k = a.in_cap - 1u - (k - nfront);  // ray_split: entry k sits at the back
 #if SHADE_REGROUP
     if (!FIRST) {
@@ -1494,6 +1509,12 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         sa.npix = bpix;
         P.pixel_base = p0;
         const unsigned shade_grid = div_up(bpix, 256), tgrid = trace_grid(ctx, bpix);
+        // vertex 0 in tile order (one band only: bands are pixel ranges in row order)
+        const bool tiles = ctx->opt_shade_tiles != 0 && bands == 1;
+        P.first_tiles_x = tiles ? div_up(ctx->W, 8u) : 0u;
+        P.first_rows = ctx->local_rows;
+        P.first_count = tiles ? P.first_tiles_x * div_up(ctx->local_rows, 4u) * 32u : bpix;
+        const unsigned first_grid = div_up(P.first_count, 256);
         uint32_t* const sh_counts = nee ? ctx->queue_counts.p + ctx->shadow_counts_at + (size_t)band * waves : nullptr;
         uint32_t* const sh_work = nee ? ctx->queue_counts.p + ctx->shadow_counts_at + (size_t)bands * waves + (size_t)band * waves : nullptr;
         if (nee) {
@@ -1516,7 +1537,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
             sa.out_back = split ? bcounts + wave : nullptr;
             sa.in_back = nullptr;
             sa.sh_count = nee ? sh_counts + wave : nullptr;
-            k_shade<true><<<shade_grid, 256, 0, st>>>(sa, nullptr);
+            k_shade<true><<<first_grid, 256, 0, st>>>(sa, nullptr);
             MRT_LAUNCHED(ctx);
             for (uint32_t b = 1; b <= bounces; b++) {
                 const uint32_t* in_count = qcounts + wave;
