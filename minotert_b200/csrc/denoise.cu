@@ -9,17 +9,22 @@
 // exp and 5 multiply-adds -- an issue-bound stencil (about 25 000 instructions per pixel), not a bandwidth-bound
 // one: the 18 B/px of input are read once per CTA tile into shared memory.
 //
-// Kernel: one thread per pixel, 32x8-pixel CTA, shared tile with a halo of radius+1 texels holding
-// {r, g, b, depth, nx, ny, nz} as the stored halfs (one LDS.128 per texel); image-edge clamping is applied when
-// the tile is filled, so the tap loop needs none.  The tap list (which taps exist, d.y/size.y, the spatial
-// Gaussian, the tile offset of d.x) depends only on the push constants and the image size: it is evaluated once on
-// the host with the shader's own fp32 loops and read through uniform loads.  Taps are visited in the shader's order.
+// Kernel: one thread per pixel, 32x8-pixel CTA (a warp = one image row of the tile), shared tile with a halo of
+// radius+1 texels holding {r, g, b, depth} and {nx, ny, nz} as fp32 (converted ONCE per CTA when the tile is filled; two
+// conflict-free LDS.128 per texel); image-edge clamping is applied when the tile is filled, so the tap loop needs none.
+// Everything about a tap that does not depend on the pixel's column is evaluated once on the host, with the shader's own
+// fp32 operations, into a table of one 16-byte record per (image row, tap): which taps exist, the spatial Gaussian, and --
+// the part the first version of this kernel recomputed per pixel and per tap, a third of its instructions -- the row the
+// LinearClamp sampler reads and its k/256 weight.  The records of a row are the same for all its pixels: a warp reads them
+// with one broadcast load per tap.  Taps are visited in the shader's order (same sums, bit for bit, as that first version).
 // Sampler rule (the oracle's, oracle/minote_oracle.c:texn_bilinear): bilinear weights carry 8 fractional bits and
 // zero-weight texels are not read.  d.x is integral, so in x every tap is the texel centre px + d.x (the fp32
 // residue of uv + d/size is < 2^-10 texel for images up to 4096 wide and rounds to weight 0): one column, no
-// x-lerp, no per-tap x arithmetic; the same holds for the taps whose d.y is integral.  For the others the row
-// position and its k/256 weight are computed per pixel with the oracle's operations, so both sides pick the same
-// weight.  Deliberate deviations, all at the 1e-6 relative level and absorbed by the bar in
+// x-lerp.  In y the tap reads rows floor(y) and floor(y) + 1 with weights (1 - k/256, k/256); k = 0 and k = 256 (and every
+// tap whose d.y is integral) are single texels.  Consecutive taps of a column step down one row, so the lower texel of
+// one tap is the upper texel of the next: the table flags that, and the loop keeps the texel in registers (two register
+// sets that swap roles every tap) -- one shared-memory texel per tap instead of two.
+// Deliberate deviations, all at the 1e-6 relative level and absorbed by the bar in
 // tests/test_gpu_denoise.py (RGBA8: <= 1 code value on >= 99.9 % of pixels; measured: 8e-6 of the pixels differ,
 // by 1): exp and the depth division run on the SFU (ex2.approx, rcp.approx), as GLSL exp() and '/' do on the
 // reference's GPU path, and the row lerp and the accumulation are contracted to FMAs (this file is built with
@@ -36,14 +41,10 @@ namespace {
 #ifndef DN_ROWS
 #define DN_ROWS 8     // CTA = 32 x DN_ROWS pixels
 #endif
-#ifndef DN_UNROLL
-#define DN_UNROLL 4   // taps per loop trip (1: 1.37 ms, 2: 1.34, 4: 1.29 at 1080p)
-#endif
-constexpr int DN_BX = 32, DN_BY = DN_ROWS, DN_UNROLL_N = DN_UNROLL;
+constexpr int DN_BX = 32, DN_BY = DN_ROWS;
 
 struct DenoiseArgs {
     uint32_t W, H;
-    float sizeX, sizeY;
     float invThresholdSqx2Log2e, invThresholdSqrt2PI;
     float nearPlane;
     uint32_t frameCounter;
@@ -51,15 +52,9 @@ struct DenoiseArgs {
     int ntaps;
 };
 
-struct Texel { float r, g, b, z, nx, ny, nz; };
-
-MRT_D Texel unpack_texel(uint4 t) {
-    float2 rg = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
-    float2 bz = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
-    float2 nxy = __half22float2(*reinterpret_cast<const __half2*>(&t.z));
-    float2 nzw = __half22float2(*reinterpret_cast<const __half2*>(&t.w));
-    return Texel{rg.x, rg.y, bz.x, bz.y, nxy.x, nxy.y, nzw.x};
-}
+// record of one (image row, tap): .x = (tile offset of the upper texel relative to the pixel) * 16 | flags, .w = spatial Gaussian
+enum : int { DN_LERP = 1,    // the tap interpolates rows (.y = weight of the lower row, .z = 1 - .y); else a single texel
+             DN_REUSE = 2 }; // the upper texel is the previous tap's lower texel (still in registers)
 
 // single-instruction SFU forms (MUFU.RCP / MUFU.EX2): arguments here are never fp32-denormal (depth comes from
 // fp16, the exponent is >= 0), so the flush-to-zero variants lose nothing
@@ -74,74 +69,105 @@ MRT_D float ex2_approx(float x) {
     return r;
 }
 
+struct DnSums { float z, r, g, b; };
+struct DnConsts { float centreDist, cnx, cny, cnz, nearPlane, k1, k2; };
+
+MRT_D float4 lds4(uint32_t addr) {  // 32-bit shared-memory address
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// the weight of one tap and its accumulation (bilateral.comp:52-61)
+MRT_D void dn_accumulate(DnSums& sum, const DnConsts& K, float blur, float r, float g, float b, float z, float nx, float ny, float nz) {
+    float dZ = K.nearPlane * rcp_approx(z) - K.centreDist;
+    dZ *= 100.0f;
+    const float dN = fmaf(nz, K.cnz, fmaf(ny, K.cny, nx * K.cnx));
+    // exp(c * invThresholdSqx2) = 2^(c * invThresholdSqx2 * log2 e)
+    const float deltaFactor = ex2_approx(clampf(dN - dZ * dZ, 0.0f, 1.0f) * K.k1) * K.k2 * blur;
+    sum.z += deltaFactor;
+    sum.r = fmaf(deltaFactor, r, sum.r);
+    sum.g = fmaf(deltaFactor, g, sum.g);
+    sum.b = fmaf(deltaFactor, b, sum.b);
+}
+
+// One tap (bilateral.comp:49-62).  P = register set of the upper texel, Q = of the lower one.  Both branches are uniform
+// across the warp (the record belongs to the image row) and each carries its own copy of the accumulation, so that
+// neither pays register moves to meet the other.
+#define DN_TAP(P, Q, RC)                                                                                               \
+    {                                                                                                                  \
+        const float4 rc = RC;                                                                                          \
+        const int code = __float_as_int(rc.x);                                                                         \
+        const uint32_t at = centre_addr + (uint32_t)(code & ~3);                                                       \
+        if (!(code & DN_REUSE)) { P##c = lds4(at); P##n = lds4(at + normal_off); }                                     \
+        if (code & DN_LERP) {                                                                                          \
+            Q##c = lds4(at + row_bytes); Q##n = lds4(at + row_bytes + normal_off);                                     \
+            const float fy = rc.y, gy = rc.z;                                                                          \
+            dn_accumulate(sum, K, rc.w, fmaf(Q##c.x, fy, P##c.x * gy), fmaf(Q##c.y, fy, P##c.y * gy),                  \
+                          fmaf(Q##c.z, fy, P##c.z * gy), fmaf(Q##c.w, fy, P##c.w * gy), fmaf(Q##n.x, fy, P##n.x * gy), \
+                          fmaf(Q##n.y, fy, P##n.y * gy), fmaf(Q##n.z, fy, P##n.z * gy));                               \
+        } else {                                                                                                       \
+            dn_accumulate(sum, K, rc.w, P##c.x, P##c.y, P##c.z, P##c.w, P##n.x, P##n.y, P##n.z);                       \
+        }                                                                                                              \
+    }
+
 // bilateral.comp:23-76
 __global__ void __launch_bounds__(DN_BX* DN_BY)
     k_denoise_bilateral(DenoiseArgs A, const uint2* __restrict__ color16, const uint16_t* __restrict__ depth16,
-                        const uint2* __restrict__ normal16, const float4* __restrict__ taps, uchar4* __restrict__ out) {
-    extern __shared__ uint4 tile[];
+                        const uint2* __restrict__ normal16, const float4* __restrict__ recs, uchar4* __restrict__ out) {
+    extern __shared__ float4 tile[];
     const int TW = DN_BX + 2 * A.halo, TH = DN_BY + 2 * A.halo;
+    float4* const tileC = tile;            // r, g, b, depth
+    float4* const tileN = tile + TW * TH;  // nx, ny, nz, -
     const int x0 = (int)blockIdx.x * DN_BX - A.halo, y0 = (int)blockIdx.y * DN_BY - A.halo;
     const int tid = threadIdx.y * DN_BX + threadIdx.x;
     for (int i = tid; i < TW * TH; i += DN_BX * DN_BY) {
         int ty = i / TW, tx = i - ty * TW;
         int gx = min(max(x0 + tx, 0), (int)A.W - 1), gy = min(max(y0 + ty, 0), (int)A.H - 1);  // ClampToEdge
         size_t g = (size_t)gy * A.W + gx;
-        uint2 c = __ldg(&color16[g]);
-        uint2 n = __ldg(&normal16[g]);
-        uint32_t d = __ldg(&depth16[g]);
-        tile[i] = make_uint4(c.x, (c.y & 0xFFFFu) | (d << 16), n.x, n.y);
+        const uint2 c = __ldg(&color16[g]);
+        const uint2 n = __ldg(&normal16[g]);
+        const float2 rg = __half22float2(*reinterpret_cast<const __half2*>(&c.x));
+        const float2 ba = __half22float2(*reinterpret_cast<const __half2*>(&c.y));
+        const float2 nxy = __half22float2(*reinterpret_cast<const __half2*>(&n.x));
+        const float2 nzw = __half22float2(*reinterpret_cast<const __half2*>(&n.y));
+        tileC[i] = make_float4(rg.x, rg.y, ba.x, __half2float(__ushort_as_half(__ldg(&depth16[g]))));
+        tileN[i] = make_float4(nxy.x, nxy.y, nzw.x, 0.0f);
     }
     __syncthreads();
     const uint32_t px = blockIdx.x * DN_BX + threadIdx.x, py = blockIdx.y * DN_BY + threadIdx.y;
     if (px >= A.W || py >= A.H) return;
 
-    const float uvy = ((float)py + 0.5f) / A.sizeY;
-    const int tix = (int)px - x0, tiy = (int)py - y0;
-    const int centre_idx = tiy * TW + tix;
-    const Texel centre = unpack_texel(tile[centre_idx]);
+    const int centre_idx = ((int)py - y0) * TW + ((int)px - x0);
+    const float4 cc = tileC[centre_idx], cn = tileN[centre_idx];
     float3 filtered;
-    if (centre.z < 0.0f) {  // bilateral.comp:36
-        filtered = f3(centre.r, centre.g, centre.b);
+    if (cc.w < 0.0f) {  // bilateral.comp:36
+        filtered = f3(cc.x, cc.y, cc.z);
     } else {
-        const float centreDist = A.nearPlane * rcp_approx(centre.z);
-        float zBuff = 0.0f;
-        float3 aBuff = f3s(0.0f);
-#pragma unroll DN_UNROLL_N
-        for (int i = 0; i < A.ntaps; i++) {
-            const float4 tp = __ldg(&taps[i]);  // d.y/size.y, blurFactor, tile offset (int), d.y integral? (int)
-            const int off = __float_as_int(tp.z);
-            Texel w;
-            if (__float_as_int(tp.w) != 0) {  // d.x and d.y integral (uniform across the CTA): a texel centre
-                w = unpack_texel(tile[centre_idx + off]);
-            } else {
-                // row position and its k/256 weight exactly as the oracle's sampler computes them
-                const float y = (uvy + tp.x) * A.sizeY - 0.5f;
-                const float fy0 = floorf(y);
-                const float fy = rintf((y - fy0) * 256.0f) * (1.0f / 256.0f), gy = 1.0f - fy;
-                const int idx = ((int)fy0 - y0) * TW + tix + off;
-                const Texel a = unpack_texel(tile[idx]);
-                const Texel b = unpack_texel(tile[idx + TW]);
-                // zero-weight texels are not read: only the colour can hold inf (sun disc), depth and normal are finite
-                const bool only_a = fy == 0.0f, only_b = gy == 0.0f;
-                w.r = only_a ? a.r : (only_b ? b.r : fmaf(b.r, fy, a.r * gy));
-                w.g = only_a ? a.g : (only_b ? b.g : fmaf(b.g, fy, a.g * gy));
-                w.b = only_a ? a.b : (only_b ? b.b : fmaf(b.b, fy, a.b * gy));
-                w.z = fmaf(b.z, fy, a.z * gy);
-                w.nx = fmaf(b.nx, fy, a.nx * gy);
-                w.ny = fmaf(b.ny, fy, a.ny * gy);
-                w.nz = fmaf(b.nz, fy, a.nz * gy);
-            }
-            float dZ = A.nearPlane * rcp_approx(w.z) - centreDist;
-            dZ *= 100.0f;
-            const float dN = fmaf(w.nz, centre.nz, fmaf(w.ny, centre.ny, w.nx * centre.nx));
-            // exp(c * invThresholdSqx2) = 2^(c * invThresholdSqx2 * log2 e)
-            const float deltaFactor = ex2_approx(clampf(dN - dZ * dZ, 0.0f, 1.0f) * A.invThresholdSqx2Log2e) * A.invThresholdSqrt2PI * tp.y;
-            zBuff += deltaFactor;
-            aBuff.x = fmaf(deltaFactor, w.r, aBuff.x);
-            aBuff.y = fmaf(deltaFactor, w.g, aBuff.y);
-            aBuff.z = fmaf(deltaFactor, w.b, aBuff.z);
+        DnConsts K;
+        K.centreDist = A.nearPlane * rcp_approx(cc.w);
+        K.cnx = cn.x; K.cny = cn.y; K.cnz = cn.z;
+        K.nearPlane = A.nearPlane; K.k1 = A.invThresholdSqx2Log2e; K.k2 = A.invThresholdSqrt2PI;
+        asm volatile("" : "+f"(K.nearPlane), "+f"(K.k1), "+f"(K.k2));  // keep the kernel parameters in registers
+        DnSums sum = {0.0f, 0.0f, 0.0f, 0.0f};
+        // byte addresses: record offsets are tile offsets * 16, flags in the two low bits
+        const uint32_t centre_addr = (uint32_t)__cvta_generic_to_shared(tileC + centre_idx);
+        const uint32_t normal_off = (uint32_t)(TW * TH) * 16u, row_bytes = (uint32_t)TW * 16u;
+        const float4* rp = recs + (size_t)py * A.ntaps;
+        float4 Xc = cc, Xn = cn, Yc = cc, Yn = cn;
+        // the records of the next two taps are fetched while this pair is evaluated (one broadcast load per tap and warp)
+        const int last = A.ntaps - 1;
+        float4 r0 = __ldg(rp), r1 = __ldg(rp + min(1, last));
+        int i = 0;
+#pragma unroll 2
+        for (; i + 1 < A.ntaps; i += 2) {
+            const float4 n0 = __ldg(rp + min(i + 2, last)), n1 = __ldg(rp + min(i + 3, last));
+            DN_TAP(X, Y, r0)
+            DN_TAP(Y, X, r1)
+            r0 = n0; r1 = n1;
         }
-        filtered = f3(aBuff.x / zBuff, aBuff.y / zBuff, aBuff.z / zBuff);
+        if (i < A.ntaps) DN_TAP(X, Y, r0)
+        filtered = f3(sum.r / sum.z, sum.g / sum.z, sum.b / sum.z);
     }
     // bilateral.comp:71-73: one PCG draw per pixel, the same value on r, g and b
     uint32_t seed = px * 709u + py * 1153u + A.frameCounter * 1361u;
@@ -153,33 +179,62 @@ __global__ void __launch_bounds__(DN_BX* DN_BY)
 
 }  // namespace
 
-// The loops of smartDeNoise (bilateral.comp:43-47) in the shader's own fp32 arithmetic: which taps exist, their
-// d/size offsets and the spatial Gaussian depend only on (sigma, kSigma, image size).
-static void build_taps(float sigma, float kSigma, float sizeY, int tileW, std::vector<float4>& taps) {
+// The loops of smartDeNoise (bilateral.comp:43-47) in the shader's own fp32 arithmetic, once per image row: which taps
+// exist, the spatial Gaussian, and where the sampler reads -- all of it depends only on (sigma, kSigma, image height, row).
+// recs[row * ntaps + tap]; returns ntaps.
+static int build_tap_records(float sigma, float kSigma, uint32_t H, int tileW, std::vector<float4>& recs) {
     const float INV_PI = 0.31830988618379067153776752674503f;
     const float radius = roundf(kSigma * sigma);
     const float radQ = radius * radius;
     const float invSigmaQx2 = .5f / (sigma * sigma);
     const float invSigmaQx2PI = INV_PI * invSigmaQx2;
-    taps.clear();
+    const float sizeY = (float)H;
+    struct Tap { float dx, dy, blur; bool whole; };
+    std::vector<Tap> taps;
     for (float dx = -radius; dx <= radius; dx++) {
         const float pt = sqrtf(radQ - dx * dx);
-        for (float dy = -pt; dy <= pt; dy++) {
-            const float blurFactor = expf(-(dx * dx + dy * dy) * invSigmaQx2) * invSigmaQx2PI;
+        for (float dy = -pt; dy <= pt; dy++)
+            taps.push_back(Tap{dx, dy, expf(-(dx * dx + dy * dy) * invSigmaQx2) * invSigmaQx2PI, dy == rintf(dy)});
+    }
+    const int ntaps = (int)taps.size();
+    recs.resize((size_t)H * ntaps);
+    for (uint32_t py = 0; py < H; py++) {
+        const float uvy = ((float)py + 0.5f) / sizeY;
+        bool prev_lerp = false;
+        int prev_lower = 0;  // tile offset of the previous tap's lower texel
+        for (int k = 0; k < ntaps; k++) {
+            const Tap& t = taps[k];
             // In x the tap is the texel centre px + d.x: (uv.x + d.x/W) * W - 0.5 differs from it by the fp32 rounding of
             // uv.x and d.x/W, at most 2^-23 * W * 2 < 2^-10 texel for W <= 4096, which the 8-bit weight rounds to 0.
-            // The same holds in y when d.y is integral; otherwise the kernel evaluates the row position per pixel.
-            const bool whole = dy == rintf(dy);
-            const int off = whole ? (int)dy * tileW + (int)dx : (int)dx;
-            float4 t;
-            t.x = dy / sizeY;
-            t.y = blurFactor;
-            memcpy(&t.z, &off, 4);
-            const int flag = whole ? 1 : 0;
-            memcpy(&t.w, &flag, 4);
-            taps.push_back(t);
+            // The same holds in y when d.y is integral; otherwise the row position and its k/256 weight are evaluated
+            // exactly as the oracle's sampler computes them.
+            int row;
+            float fy = 0.0f;
+            if (t.whole) {
+                row = (int)t.dy;
+            } else {
+                const float y = (uvy + t.dy / sizeY) * sizeY - 0.5f;
+                const float fy0 = floorf(y);
+                fy = rintf((y - fy0) * 256.0f) * (1.0f / 256.0f);
+                row = (int)fy0 - (int)py;
+                if (1.0f - fy == 0.0f) { row += 1; fy = 0.0f; }  // weight 256/256: the lower texel alone
+            }
+            const int off = row * tileW + (int)t.dx;
+            int flags = 0;
+            if (fy != 0.0f) flags |= DN_LERP;
+            if (prev_lerp && prev_lower == off) flags |= DN_REUSE;
+            prev_lerp = fy != 0.0f;
+            prev_lower = off + tileW;
+            const int code = off * 16 + flags;  // byte offset in the tile of 16-byte texels; flags in the low bits
+            float4 r;
+            memcpy(&r.x, &code, 4);
+            r.y = fy;
+            r.z = 1.0f - fy;
+            r.w = t.blur;
+            recs[(size_t)py * ntaps + k] = r;
         }
     }
+    return ntaps;
 }
 
 int denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float threshold, float nearPlane, uint32_t frameCounter) {
@@ -195,26 +250,25 @@ int denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float thresho
     if (n == 0) return MRT_OK;
 
     if (ctx->dn_key_sigma != sigma || ctx->dn_key_ksigma != kSigma || ctx->dn_key_w != W || ctx->dn_key_h != H) {
-        std::vector<float4> taps;
-        build_taps(sigma, kSigma, (float)H, DN_BX + 2 * ((int)radius + 1), taps);
-        MRT_TRY(dev_reserve(ctx, ctx->dn_taps, taps.size()));
+        std::vector<float4> recs;
+        const int ntaps = build_tap_records(sigma, kSigma, H, DN_BX + 2 * ((int)radius + 1), recs);
+        MRT_TRY(dev_reserve(ctx, ctx->dn_taps, recs.size()));
         // pageable source: the copy is staged before the call returns
-        MRT_CUDA(ctx, cudaMemcpyAsync(ctx->dn_taps.p, taps.data(), taps.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        MRT_CUDA(ctx, cudaMemcpyAsync(ctx->dn_taps.p, recs.data(), recs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
         MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->dn_ntaps = (int)taps.size();
+        ctx->dn_ntaps = ntaps;
         ctx->dn_key_sigma = sigma; ctx->dn_key_ksigma = kSigma; ctx->dn_key_w = W; ctx->dn_key_h = H;
     }
 
     DenoiseArgs A;
     A.W = W; A.H = H;
-    A.sizeX = (float)W; A.sizeY = (float)H;
     A.invThresholdSqx2Log2e = .5f / (threshold * threshold) * 1.4426950408889634f;
     A.invThresholdSqrt2PI = 0.39894228040143267793994605993439f / threshold;
     A.nearPlane = nearPlane;
     A.frameCounter = frameCounter;
     A.halo = (int)radius + 1;
     A.ntaps = ctx->dn_ntaps;
-    const size_t smem = (size_t)(DN_BX + 2 * A.halo) * (DN_BY + 2 * A.halo) * sizeof(uint4);
+    const size_t smem = (size_t)(DN_BX + 2 * A.halo) * (DN_BY + 2 * A.halo) * 2 * sizeof(float4);
     if (smem > 48 * 1024)
         MRT_CUDA(ctx, cudaFuncSetAttribute(k_denoise_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(div_up(W, DN_BX), div_up(H, DN_BY)), block(DN_BX, DN_BY);
