@@ -184,6 +184,9 @@ const char* mrt_last_error(const mrt_context* ctx);
  *                             contexts that share a GPU
  *   "build_device_loop" 0/1   PLOC rounds and collapse levels looped inside two cooperative kernels (default 1) or
  *                             driven from the host with a readback per round (0); same tree either way; invalidates the BVH
+ *   "wide_refit" 0/1          final node emission and MRT_BUILD_REFIT level by level on the wide tree, 8 lanes per node
+ *                             (default 1), or through the binary tree's boxes with one thread per node (0); same nodes
+ *                             and leaf triangles bit for bit
  *   "builder" 0/1             hierarchy builder: 0 Karras LBVH, 1 PLOC (default); invalidates the BVH
  *   "ploc_radius" 1..32       PLOC search radius (default 6); invalidates the BVH */
 int mrt_set_option(mrt_context* ctx, const char* name, int64_t value);

@@ -165,6 +165,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->bin_lo); dev_free(ctx->bin_hi); dev_free(ctx->bin_flag);
     dev_free(ctx->scene_bounds); dev_free(ctx->work_a); dev_free(ctx->work_b); dev_free(ctx->slot_node);
     dev_free(ctx->node_nchild); dev_free(ctx->node_ntri); dev_free(ctx->node_child_base); dev_free(ctx->node_tri_base);
+    dev_free(ctx->node_lo); dev_free(ctx->node_hi); dev_free(ctx->level_starts_dev);
     dev_free(ctx->nodes); dev_free(ctx->tris); dev_free(ctx->counters); dev_free(ctx->loop_sums);
     dev_free(ctx->trans16); dev_free(ctx->multi16); dev_free(ctx->view_packed);
     dev_free(ctx->trans_f); dev_free(ctx->multi_f); dev_free(ctx->view_f);
@@ -214,6 +215,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "path_kernel")) ctx->opt_path_kernel = value != 0;
     else if (!strcmp(name, "bands")) ctx->opt_bands = (int)(value < 1 ? 1 : (value > MRT_MAX_BANDS ? MRT_MAX_BANDS : value));
     else if (!strcmp(name, "trace_ctas_per_sm")) ctx->opt_trace_ctas_per_sm = (int)(value > 32 ? 32 : value);
+    else if (!strcmp(name, "wide_refit")) ctx->opt_wide_refit = value != 0;
     else if (!strcmp(name, "build_device_loop")) { ctx->opt_build_device_loop = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "builder")) { ctx->opt_builder = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "ploc_radius")) { ctx->opt_ploc_radius = (int)(value < 1 ? 1 : (value > 32 ? 32 : value)); ctx->bvh_valid = false; }

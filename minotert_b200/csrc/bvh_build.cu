@@ -798,8 +798,10 @@ struct CollapseLoop {
     uint32_t *node_nchild, *node_ntri, *node_child_base, *node_tri_base;
     uint32_t* block_sums;     // [gridDim.x]
     uint32_t* result;         // [0] wide nodes, [1] status (0 ok, 1 node budget exceeded), [2] levels
+    uint32_t* level_starts;   // [MAX_WIDE_LEVELS + 1]: first node of each level, then the node count
     uint32_t n;               // primitives = node budget
 };
+#define MAX_WIDE_LEVELS 1023u
 
 
 // exclusive scan of in[first .. first+count) across the grid; calls emit(index, exclusive prefix) for every element
@@ -845,6 +847,7 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop 
     grid.sync();
     while (level_count > 0) {
         if ((size_t)level_start + level_count > A.n) { status = 1; break; }
+        if (gtid == 0 && levels < MAX_WIDE_LEVELS) A.level_starts[levels] = level_start;
         const uint2* items = A.items[cur];
         uint2* next_items = A.items[cur ^ 1];
         for (uint32_t k0 = (gtid >> 5) * 4u; k0 < level_count; k0 += (gsize >> 5) * 4u) {  // a warp takes 4 nodes, 8 lanes each
@@ -886,6 +889,7 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop 
         A.result[0] = num_nodes;
         A.result[1] = status;
         A.result[2] = levels;
+        if (levels <= MAX_WIDE_LEVELS) A.level_starts[levels] = num_nodes;
     }
 }
 
@@ -984,6 +988,162 @@ k_emit_nodes(BinTree T, uint32_t num_nodes, const int32_t* __restrict__ slot_nod
     N.w[3] = make_uint4(qlo[2][0], qlo[2][1], qhi[0][0], qhi[0][1]);
     N.w[4] = make_uint4(qhi[1][0], qhi[1][1], qhi[2][0], qhi[2][1]);
     nodes[w] = N;
+}
+
+// ---- emission and refit on the WIDE tree, level by level, eight lanes per node (option "wide_refit", default) ----
+// k_emit_nodes above walks a node's eight slots in one thread: 8 x (two gathers of binary boxes, 6 quantisations with
+// a double-precision outward check, up to 3 triangles copied through 12 dependent loads) -- ~100 us per million
+// triangles with 1/8 of the lanes a node could use, and MRT_BUILD_REFIT pays it after a bottom-up climb of the BINARY
+// tree (k_bin_boxes: one atomic + fence + dependent loads per level of a ~40-level tree, 176 us per million triangles).
+// The wide tree is stored level by level (children behind their parents, each level contiguous), and a slot's box is
+// the exact union -- fmin / fmax, no rounding -- of the triangles below it whichever tree it is accumulated on.  So:
+//   full build:  k_emit_topology writes what the collapse decided (imask, child_base, tri_base, leafmask; the primitive id
+//                of every leaf triangle), then the refit below fills in everything that depends on coordinates;
+//   refit:       for each level from the deepest up, k_wide_refit -- lane s of a group of 8 owns slot s: a leaf slot
+//                re-reads its <= 3 triangles from the (new) vertex positions and rewrites them, an inner slot takes the
+//                box its child node stored one launch earlier; the node box, the grid exponents and the packed plane
+//                words come out of 8-lane shuffles; the quantiser is k_emit_nodes' own, expression for expression.
+// Nodes and leaf triangles are bit-identical to the round-1 path (tests/test_gpu_mesh.py::test_wide_refit_*).
+struct WideRefit {
+    WideNode* nodes;
+    float4* tris;
+    const float* pos;
+    const uint32_t* idx;
+    float4 *node_lo, *node_hi;
+    uint32_t first, count;  // this level: nodes [first, first + count)
+};
+
+__global__ void __launch_bounds__(256) k_wide_refit(WideRefit A) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool active = g < A.count;
+    const uint32_t w = A.first + (active ? g : A.count - 1u);  // idle groups shadow the last node (shuffles need all lanes)
+    const int s = threadIdx.x & 7;
+    const uint32_t n0w = A.nodes[w].w[0].w;
+    const uint4 n1 = A.nodes[w].w[1];
+    const uint32_t imask = active ? n0w >> 24 : 0u, leafmask = active ? n1.z : 0u;  // idle groups touch nothing else
+    float3 lo = f3s(3.0e38f), hi = f3s(-3.0e38f);
+    bool present = false;
+    if ((imask >> s) & 1u) {
+        const uint32_t child = n1.x + __popc(imask & ((1u << s) - 1u));
+        const float4 clo = A.node_lo[child], chi = A.node_hi[child];
+        lo = f3(clo.x, clo.y, clo.z);
+        hi = f3(chi.x, chi.y, chi.z);
+        present = true;
+    } else {
+        const uint32_t bits = (leafmask >> (3 * s)) & 7u;
+        if (bits) {
+            const uint32_t cnt = __popc(bits), first = n1.y + __popc(leafmask & ((1u << (3 * s)) - 1u));
+            for (uint32_t t = 0; t < cnt; t++) {
+                const size_t o = 3 * (size_t)(first + t);
+                const uint32_t prim = __float_as_uint(A.tris[o].w);
+                const uint32_t i0 = A.idx[3 * (size_t)prim], i1 = A.idx[3 * (size_t)prim + 1], i2 = A.idx[3 * (size_t)prim + 2];
+                const float3 a = f3(A.pos[3 * (size_t)i0], A.pos[3 * (size_t)i0 + 1], A.pos[3 * (size_t)i0 + 2]);
+                const float3 b = f3(A.pos[3 * (size_t)i1], A.pos[3 * (size_t)i1 + 1], A.pos[3 * (size_t)i1 + 2]);
+                const float3 c = f3(A.pos[3 * (size_t)i2], A.pos[3 * (size_t)i2 + 1], A.pos[3 * (size_t)i2 + 2]);
+                A.tris[o + 0] = make_float4(a.x, a.y, a.z, __uint_as_float(prim));
+                A.tris[o + 1] = make_float4(b.x, b.y, b.z, 0.0f);
+                A.tris[o + 2] = make_float4(c.x, c.y, c.z, 0.0f);
+                lo = f3(fminf(lo.x, fminf(a.x, fminf(b.x, c.x))), fminf(lo.y, fminf(a.y, fminf(b.y, c.y))), fminf(lo.z, fminf(a.z, fminf(b.z, c.z))));
+                hi = f3(fmaxf(hi.x, fmaxf(a.x, fmaxf(b.x, c.x))), fmaxf(hi.y, fmaxf(a.y, fmaxf(b.y, c.y))), fmaxf(hi.z, fmaxf(a.z, fmaxf(b.z, c.z))));
+            }
+            present = true;
+        }
+    }
+    // node box over the 8 slots
+    float3 nlo = lo, nhi = hi;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        nlo.x = fminf(nlo.x, __shfl_xor_sync(FULL, nlo.x, d, 8)); nlo.y = fminf(nlo.y, __shfl_xor_sync(FULL, nlo.y, d, 8));
+        nlo.z = fminf(nlo.z, __shfl_xor_sync(FULL, nlo.z, d, 8));
+        nhi.x = fmaxf(nhi.x, __shfl_xor_sync(FULL, nhi.x, d, 8)); nhi.y = fmaxf(nhi.y, __shfl_xor_sync(FULL, nhi.y, d, 8));
+        nhi.z = fmaxf(nhi.z, __shfl_xor_sync(FULL, nhi.z, d, 8));
+    }
+    const uint32_t ex = grid_exponent(nhi.x - nlo.x, fmaxf(fabsf(nlo.x), fabsf(nhi.x))), ey = grid_exponent(nhi.y - nlo.y, fmaxf(fabsf(nlo.y), fabsf(nhi.y))),
+                   ez = grid_exponent(nhi.z - nlo.z, fmaxf(fabsf(nlo.z), fabsf(nhi.z)));
+    const float sc[3] = {__uint_as_float(ex << 23), __uint_as_float(ey << 23), __uint_as_float(ez << 23)};
+    const float org[3] = {nlo.x - 2.0f * sc[0], nlo.y - 2.0f * sc[1], nlo.z - 2.0f * sc[2]};
+    // this slot's planes (k_emit_nodes' quantiser), shifted to its byte of the packed words
+    uint32_t vlo[3] = {255u, 255u, 255u}, vhi[3] = {0u, 0u, 0u};
+    if (present) {
+        const float clo[3] = {lo.x, lo.y, lo.z}, chi[3] = {hi.x, hi.y, hi.z};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const double o = (double)org[a], st = (double)sc[a], slack = st * 0.015625;
+            float ql = fminf(fmaxf(floorf((clo[a] - org[a]) / sc[a] - 0.02f), 0.0f), 255.0f);
+            float qh = fminf(fmaxf(ceilf((chi[a] - org[a]) / sc[a] + 0.02f), 0.0f), 255.0f);
+            while (ql > 0.0f && o + (double)ql * st > (double)clo[a] - slack) ql -= 1.0f;
+            while (qh < 255.0f && o + (double)qh * st < (double)chi[a] + slack) qh += 1.0f;
+            vlo[a] = (uint32_t)ql;
+            vhi[a] = (uint32_t)qh;
+        }
+    }
+    uint32_t own_lo[3], own_hi[3], oth_lo[3], oth_hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        uint32_t l = vlo[a] << (8 * (s & 3)), h = vhi[a] << (8 * (s & 3));
+        l |= __shfl_xor_sync(FULL, l, 1, 8); h |= __shfl_xor_sync(FULL, h, 1, 8);
+        l |= __shfl_xor_sync(FULL, l, 2, 8); h |= __shfl_xor_sync(FULL, h, 2, 8);
+        own_lo[a] = l; own_hi[a] = h;
+        oth_lo[a] = __shfl_xor_sync(FULL, l, 4, 8); oth_hi[a] = __shfl_xor_sync(FULL, h, 4, 8);
+    }
+    if (!active) return;
+    const bool low = s < 4;  // this lane's own words are those of slots 0..3
+#define QLO(a, h) ((h == 0) == low ? own_lo[a] : oth_lo[a])
+#define QHI(a, h) ((h == 0) == low ? own_hi[a] : oth_hi[a])
+    uint4* const out = A.nodes[w].w;
+    if (s == 0) {
+        out[0] = make_uint4(__float_as_uint(org[0]), __float_as_uint(org[1]), __float_as_uint(org[2]), ex | (ey << 8) | (ez << 16) | (imask << 24));
+        A.node_lo[w] = make_float4(nlo.x, nlo.y, nlo.z, 0.0f);
+        A.node_hi[w] = make_float4(nhi.x, nhi.y, nhi.z, 0.0f);
+    } else if (s == 1) {
+        out[2] = make_uint4(QLO(0, 0), QLO(0, 1), QLO(1, 0), QLO(1, 1));
+    } else if (s == 2) {
+        out[3] = make_uint4(QLO(2, 0), QLO(2, 1), QHI(0, 0), QHI(0, 1));
+    } else if (s == 3) {
+        out[4] = make_uint4(QHI(1, 0), QHI(1, 1), QHI(2, 0), QHI(2, 1));
+    }
+#undef QLO
+#undef QHI
+}
+
+// What the collapse decided, per wide node (8 lanes, lane s = slot s): imask, child_base, tri_base, leafmask, and the
+// primitive id of every leaf triangle in leaf order.  Coordinates follow from k_wide_refit.
+__global__ void __launch_bounds__(256)
+k_emit_topology(BinTree T, uint32_t num_nodes, const int32_t* __restrict__ slot_node, const uint32_t* __restrict__ node_child_base,
+                const uint32_t* __restrict__ node_tri_base, const uint32_t* __restrict__ order, WideNode* __restrict__ nodes,
+                float4* __restrict__ tris) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool active = g < num_nodes;
+    const uint32_t w = active ? g : num_nodes - 1u;
+    const int s = threadIdx.x & 7;
+    const int c = slot_node[(size_t)w * 8 + s];
+    const uint32_t cnt = c < 0 ? 0u : bin_count(T, c);
+    const bool inner = cnt > MRT_MAX_LEAF_TRIS;
+    uint32_t imask = inner ? 1u << s : 0u;
+    uint32_t leafmask = (!inner && cnt) ? ((1u << cnt) - 1u) << (3 * s) : 0u;
+    const uint32_t ntri = inner ? 0u : cnt;
+    uint32_t inc = ntri;  // inclusive prefix of the leaf triangles over the slots
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        imask |= __shfl_xor_sync(FULL, imask, d, 8);
+        leafmask |= __shfl_xor_sync(FULL, leafmask, d, 8);
+        const uint32_t t = __shfl_up_sync(FULL, inc, d, 8);
+        if (s >= d) inc += t;
+    }
+    if (!active) return;
+    const uint32_t tri_base = node_tri_base[w];
+    if (ntri) {
+        uint32_t where[3];
+        bin_gather(T, c, where);
+        for (uint32_t t = 0; t < ntri; t++)
+            tris[3 * (size_t)(tri_base + inc - ntri + t)] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(order[where[t]]));
+    }
+    if (s == 0) {
+        nodes[w].w[0] = make_uint4(0u, 0u, 0u, imask << 24);
+        nodes[w].w[1] = make_uint4(node_child_base[w], tri_base, leafmask, 0u);
+    }
 }
 
 // SAH cost of the wide tree (quality metric reported in mrt_stats.sah_cost): sum over wide nodes of
@@ -1121,7 +1281,31 @@ int build_ploc(mrt_context* ctx) {
     return MRT_OK;
 }
 
+// boxes, planes and leaf triangles of every level, deepest first (the topology words are in place)
+int wide_refit_levels(mrt_context* ctx) {
+    MRT_TRY(dev_reserve(ctx, ctx->node_lo, ctx->num_nodes));
+    MRT_TRY(dev_reserve(ctx, ctx->node_hi, ctx->num_nodes));
+    WideRefit A;
+    A.nodes = ctx->nodes.p; A.tris = ctx->tris.p; A.pos = ctx->pos.p; A.idx = ctx->idx.p;
+    A.node_lo = ctx->node_lo.p; A.node_hi = ctx->node_hi.p;
+    for (size_t l = ctx->level_starts.size() - 1; l-- > 0;) {
+        A.first = ctx->level_starts[l];
+        A.count = ctx->level_starts[l + 1] - A.first;
+        if (A.count == 0) continue;
+        k_wide_refit<<<div_up(A.count, 256 / 8), 256, 0, ctx->stream>>>(A);
+        MRT_LAUNCHED(ctx);
+    }
+    return mrt_check_cuda(ctx, cudaGetLastError(), "wide_refit");
+}
+
 int emit_nodes(mrt_context* ctx) {
+    if (ctx->opt_wide_refit && ctx->level_starts.size() >= 2 && ctx->level_starts.back() == ctx->num_nodes) {
+        k_emit_topology<<<div_up(ctx->num_nodes, 256 / 8), 256, 0, ctx->stream>>>(make_tree(ctx), ctx->num_nodes, ctx->slot_node.p,
+                                                                                  ctx->node_child_base.p, ctx->node_tri_base.p,
+                                                                                  ctx->order.p, ctx->nodes.p, ctx->tris.p);
+        MRT_LAUNCHED(ctx);
+        return wide_refit_levels(ctx);
+    }
     k_emit_nodes<<<div_up(ctx->num_nodes, 128), 128, 0, ctx->stream>>>(make_tree(ctx), ctx->num_nodes, ctx->slot_node.p,
                                                                        ctx->node_child_base.p, ctx->node_tri_base.p,
                                                                        ctx->order.p, ctx->pos.p, ctx->idx.p, ctx->nodes.p,
@@ -1204,23 +1388,32 @@ int bvh_build_full(mrt_context* ctx) {
         A.slot_node = ctx->slot_node.p; A.node_nchild = ctx->node_nchild.p; A.node_ntri = ctx->node_ntri.p;
         A.node_child_base = ctx->node_child_base.p; A.node_tri_base = ctx->node_tri_base.p;
         A.block_sums = reinterpret_cast<uint32_t*>(ctx->loop_sums.p); A.result = ctx->counters.p; A.n = n;
+        MRT_TRY(dev_reserve(ctx, ctx->level_starts_dev, MAX_WIDE_LEVELS + 1));
+        A.level_starts = ctx->level_starts_dev.p;
         void* args[] = {&A};
         MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_collapse_loop, dim3(grid), dim3(LOOP_THREADS), args, 0, ctx->stream));
         MRT_LAUNCHED(ctx);
         uint32_t res[3] = {0, 0, 0};
+        ctx->level_starts.assign(MAX_WIDE_LEVELS + 1, 0u);
         MRT_CUDA(ctx, cudaMemcpyAsync(res, ctx->counters.p, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
+        MRT_CUDA(ctx, cudaMemcpyAsync(ctx->level_starts.data(), ctx->level_starts_dev.p, sizeof(uint32_t) * (MAX_WIDE_LEVELS + 1),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
         MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (res[1] != 0) return mrt_fail(ctx, MRT_ERR_INVALID, "wide BVH node budget exceeded");
         ctx->num_nodes = res[0];
         ctx->num_leaf_tris = n;
+        if (res[2] <= MAX_WIDE_LEVELS) ctx->level_starts.resize(res[2] + 1);
+        else ctx->level_starts.clear();  // deeper than the table: emission falls back to one thread per node
     } else {
     uint2 root = make_uint2((uint32_t)ctx->bin_root /* n == 1: the single leaf is binary node n-1 = 0 */, 0u);
     MRT_CUDA(ctx, cudaMemcpyAsync(ctx->work_a.p, &root, sizeof root, cudaMemcpyHostToDevice, ctx->stream));
     uint32_t level_start = 0, level_count = 1;
     DevArray<uint2>* cur = &ctx->work_a;
     DevArray<uint2>* nxt = &ctx->work_b;
+    ctx->level_starts.clear();
     while (level_count > 0) {
         if ((size_t)level_start + level_count > n) return mrt_fail(ctx, MRT_ERR_INVALID, "wide BVH node budget exceeded");
+        ctx->level_starts.push_back(level_start);
         k_collapse_expand<<<div_up(level_count, 128), 128, 0, ctx->stream>>>(T, cur->p, level_count, ctx->slot_node.p,
                                                                              ctx->node_nchild.p, ctx->node_ntri.p);
         MRT_LAUNCHED(ctx);
@@ -1245,6 +1438,7 @@ int bvh_build_full(mrt_context* ctx) {
     }
     ctx->num_nodes = level_start;
     ctx->num_leaf_tris = n;
+    ctx->level_starts.push_back(level_start);
     MRT_TRY(scan_exclusive_u32(ctx, ctx->node_ntri.p, ctx->node_tri_base.p, ctx->num_nodes));
     }
 
@@ -1276,9 +1470,13 @@ int bvh_build_full(mrt_context* ctx) {
 int bvh_refit(mrt_context* ctx) {
     if (!ctx->bvh_valid || ctx->num_nodes == 0) return bvh_build_full(ctx);
     cudaEventRecord(ctx->ev[12], ctx->stream);
-    MRT_TRY(compute_boxes(ctx));
-    MRT_TRY(climb_boxes(ctx));
-    MRT_TRY(emit_nodes(ctx));
+    if (ctx->opt_wide_refit && ctx->level_starts.size() >= 2 && ctx->level_starts.back() == ctx->num_nodes) {
+        MRT_TRY(wide_refit_levels(ctx));  // the topology words and the triangles' primitive ids are in place
+    } else {
+        MRT_TRY(compute_boxes(ctx));
+        MRT_TRY(climb_boxes(ctx));
+        MRT_TRY(emit_nodes(ctx));
+    }
     cudaEventRecord(ctx->ev[13], ctx->stream);
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev[12], ctx->ev[13]);

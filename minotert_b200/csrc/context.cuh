@@ -82,6 +82,7 @@ struct mrt_context {
     int opt_fused_shade = 0;         // shade stage of a bounce wave inside the traversal kernel (mesh.cu k_trace_shade); A/B: +1.5 % at 1080p 1 spp, -2 % at 4K 8 spp
     int opt_trace_ctas_per_sm = 0;   // 0: as many as fit; n: persistent traversal grids use n CTAs per SM (co-running contexts)
     int opt_builder = 1;             // 0: Karras LBVH hierarchy, 1: PLOC (locally-ordered clustering) hierarchy
+    int opt_wide_refit = 1;          // boxes, planes and leaf triangles level by level on the wide tree, 8 lanes per node (0: round 1's binary climb + one thread per node)
     int opt_build_device_loop = 1;   // PLOC rounds and collapse levels looped inside cooperative kernels (0: host-driven loops with a readback per round)
     int opt_ploc_radius = 6;         // +-positions searched for the nearest cluster (measured best of 2..32 on config 2)
 
@@ -119,6 +120,9 @@ struct mrt_context {
     DevArray<uint32_t> node_nchild, node_ntri, node_child_base, node_tri_base;
     DevArray<WideNode> nodes;
     DevArray<float4> tris;
+    DevArray<float4> node_lo, node_hi;                    // boxes of the wide nodes (scratch of the level-wise emission / refit)
+    DevArray<uint32_t> level_starts_dev;                  // first wide node of each level (+ the node count), written by k_collapse_loop
+    std::vector<uint32_t> level_starts;                   // host copy: level L = nodes [level_starts[L], level_starts[L + 1])
     DevArray<uint2> loop_sums;                            // per-CTA counts of the device-side build loops
     DevArray<uint32_t> counters;                          // misc device counters
     uint32_t num_nodes = 0, num_leaf_tris = 0;

@@ -503,6 +503,60 @@ def test_tile_partition_equals_single_context(oracle, sky_inputs, blue_noise):
         assert np.array_equal(vis, vis1) and np.array_equal(acc, acc1) and np.array_equal(ldr, ldr1)
 
 
+@pytest.mark.parametrize("builder", [0, 1])
+@pytest.mark.parametrize("maker", ["tiny", "soup", "small_terrain", "hall_260k"])
+def test_wide_refit_gives_the_same_nodes(gpu_ctx, maker, builder):
+    """Option wide_refit (default): node emission and MRT_BUILD_REFIT level by level on the wide tree with 8 lanes per
+    node, vs round 1's path (binary boxes climbed with atomics, one thread per wide node): a slot's box is the exact
+    union of its triangles either way and the quantiser is the same code, so nodes and leaf triangles are
+    bit-identical -- after a full build, after a refit of animated vertices, and when a wide refit follows a build
+    emitted the old way."""
+    if maker == "tiny":
+        pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.5], [2, 0, 1], [2, 2, 1]], np.float32)
+        idx = np.array([[0, 1, 2], [1, 3, 2], [3, 4, 5]], np.uint32)
+        alb = np.full((3, 3), 0.5, np.float32)
+    elif maker == "soup":  # sizes over six decades, far from the origin
+        rng = np.random.default_rng(13)
+        n = 20000
+        c = np.array([1.0e4, -2.0e4, 5.0e3], np.float32) + rng.uniform(-50, 50, (n, 3)).astype(np.float32)
+        size = (10.0 ** rng.uniform(-4, 2, (n, 1))).astype(np.float32)
+        pos = (c[:, None, :] + size[:, None, :] * rng.normal(size=(n, 3, 3)).astype(np.float32)).reshape(-1, 3).astype(np.float32)
+        idx = np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)
+        alb = np.full((n, 3), 0.5, np.float32)
+    else:
+        pos, idx, alb, _ = getattr(scenes, maker)()
+    rng = np.random.default_rng(5)
+    pos2 = (pos + rng.normal(scale=0.01 * float(np.abs(pos).max() + 1e-3), size=pos.shape)).astype(np.float32)
+    gpu_ctx.set_option("builder", builder)
+    gpu_ctx.upload_mesh(pos, idx, alb)
+
+    def tree():
+        return gpu_ctx.readback(capi.BUF_BVH_NODES).copy(), gpu_ctx.readback(capi.BUF_BVH_TRIS).copy()
+
+    got = {}
+    for wide in (0, 1):
+        gpu_ctx.set_option("wide_refit", wide)
+        gpu_ctx.update_positions(pos)
+        gpu_ctx.build()
+        got[wide, "full"] = tree()
+        gpu_ctx.update_positions(pos2)
+        gpu_ctx.build(capi.BUILD_REFIT)
+        got[wide, "refit"] = tree()
+    # a wide refit on top of a build emitted by the one-thread-per-node kernel
+    gpu_ctx.set_option("wide_refit", 0)
+    gpu_ctx.update_positions(pos)
+    gpu_ctx.build()
+    gpu_ctx.set_option("wide_refit", 1)
+    gpu_ctx.update_positions(pos2)
+    gpu_ctx.build(capi.BUILD_REFIT)
+    got["mixed", "refit"] = tree()
+    for what in ("full", "refit"):
+        assert np.array_equal(got[1, what][0], got[0, what][0]), f"{what}: nodes differ"
+        assert np.array_equal(got[1, what][1], got[0, what][1]), f"{what}: leaf triangles differ"
+    assert np.array_equal(got["mixed", "refit"][0], got[0, "refit"][0]) and np.array_equal(got["mixed", "refit"][1], got[0, "refit"][1])
+    assert not np.array_equal(got[0, "full"][0], got[0, "refit"][0])  # the animation is visible in the nodes
+
+
 def test_refit_matches_full_rebuild(gpu_ctx, oracle):
     """BASELINE config 5 mechanics: animate vertices, REFIT; closest hits equal a fresh FULL build and brute force."""
     pos, idx, alb, _ = scenes.small_terrain()
