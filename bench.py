@@ -17,7 +17,8 @@ secondary ray for which a traversal was issued.
   configs   the same {value, ms_per_step, e2e, roofline} block for the other configurations the targets are stated on:
             the 1 M-triangle target scene (primary + 1 bounce, 1080p), BASELINE config 3 (10.4 M triangles, 4K,
             4 spp x 3 bounces), config 1 (Cornell-class, 512^2), the reference's own sphere frame (960x540, 8x8; CPU
-            side = oracle/_ref, the reference's shaders compiled as C++), and config 4 at N = 1 (the strong-scaling base)
+            side = oracle/_ref, the reference's shaders compiled as C++), config 4 at N = 1 (the strong-scaling base), and
+            config 5 (1 M animated triangles: upload + refit every frame, rebuild every 10th; end to end only)
 N > 1.  BASELINE config 4: progressive 4K accumulation, tile-partitioned over the N GPUs (interleaved 8-row slabs,
 replicated BVH), the RGBA8 framebuffer gathered onto rank 0 with NCCL every displayed frame -- all through the C ABI's
 mrt_group_* (NCCL is called from libminotert.so; torch.distributed only hands round the ncclUniqueId and the timings).
@@ -47,7 +48,7 @@ WORKLOADS = {
     "tiles_4k_progressive": ("scene_10m", 3840, 2160, 8, 3), # configs[3]: one displayed frame of the 64-spp accumulation
     "spheres_960x540": (None, 960, 540, 8, 8),               # the reference's own frame (scene.glsl, main.cpp:24)
 }
-EXTRA_CONFIGS = ["scene_1m_1080p", "scene_10m_4k", "tiles_4k_progressive", "cornell_512", "spheres_960x540"]
+EXTRA_CONFIGS = ["scene_1m_1080p", "scene_10m_4k", "tiles_4k_progressive", "cornell_512", "spheres_960x540", "animated_1m_1080p"]
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 AMD = (16.0, 2.0, 1.0, 0.18, 0.18)
 METRIC = "Mrays/s (primary+secondary)"
@@ -686,6 +687,20 @@ def measure_tiles(args, steps, warmup, world, rank, local):
         torch.cuda.empty_cache()
 
 
+def measure_animated():
+    """BASELINE.json configs[4]: ~1 M animated triangles, a new vertex array every frame (H2D from pinned memory), BVH refit
+    per frame and a full rebuild every 10th, 1080p, 1 spp, one bounce, scripted freecam, framebuffer read back every frame --
+    end to end through Renderer::updateMesh + draw (tools/bench_animated.py).  3 frames in flight, option async_update."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_animated
+    d = bench_animated.run_animated(frames=120, rebuild_every=10, frames_in_flight=3, async_update=1)
+    return {"workload": "animated_1m_1080p", "value": d["Mrays_per_s_e2e"], "ms_per_step": d["ms_per_frame"], "steps": d["frames"],
+            "config": {"workload": d["workload"], "mode": d["mode"], "rebuild_every": d["rebuild_every"], "fps": d["fps"]},
+            "e2e": {"value": d["Mrays_per_s_e2e"], "unit": METRIC, "h2d_bytes_per_step": d["h2d_bytes_per_frame"],
+                    "d2h_bytes_per_step": d["d2h_bytes_per_frame"]},
+            "note": "timed on the host around the whole loop (uploads, refits / rebuilds, frames, readbacks): value == e2e"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -743,7 +758,9 @@ def run_ours(args):
         line["configs"] = []
         for extra in EXTRA_CONFIGS:
             try:
-                if extra == "tiles_4k_progressive":
+                if extra == "animated_1m_1080p":
+                    b = measure_animated()
+                elif extra == "tiles_4k_progressive":
                     b = measure_tiles(args, 8, 3, 1, 0, local)
                 else:
                     b = measure_frames(args, extra, 10 if extra != "scene_10m_4k" else 5, 3, local, detail=False)

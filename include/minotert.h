@@ -187,6 +187,13 @@ const char* mrt_last_error(const mrt_context* ctx);
  *   "wide_refit" 0/1          final node emission and MRT_BUILD_REFIT level by level on the wide tree, 8 lanes per node
  *                             (default 1), or through the binary tree's boxes with one thread per node (0); same nodes
  *                             and leaf triangles bit for bit
+ *   "async_update" 0/1        animated scenes without host stalls (default 0).  With 1, mrt_scene_update_positions queues the
+ *                             copy on an upload stream of its own and returns at once -- `positions` must be page-locked
+ *                             and stay untouched until mrt_sync, a readback or mrt_stats_get of this context returns --
+ *                             and mrt_scene_build(MRT_BUILD_REFIT) queues the refit without waiting for it: frames in
+ *                             flight of contexts that borrow the scene (mrt_scene_share) are waited for on the GPU, the
+ *                             borrowers stay valid (a refit rewrites nodes and triangles in place) and the frames they
+ *                             record next wait for the refit.  MRT_BUILD_FULL stays synchronous.
  *   "builder" 0/1             hierarchy builder: 0 Karras LBVH, 1 PLOC (default); invalidates the BVH
  *   "ploc_radius" 1..32       PLOC search radius (default 6); invalidates the BVH */
 int mrt_set_option(mrt_context* ctx, const char* name, int64_t value);

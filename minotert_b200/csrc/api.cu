@@ -152,7 +152,11 @@ int mrt_create(int device, mrt_context** out) {
 void mrt_destroy(mrt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->upload_stream) { cudaStreamSynchronize(ctx->upload_stream); cudaStreamDestroy(ctx->upload_stream); }
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_pos_ready) cudaEventDestroy(ctx->ev_pos_ready);
+    if (ctx->ev_refit_done) cudaEventDestroy(ctx->ev_refit_done);
+    if (ctx->ev_frames_done) cudaEventDestroy(ctx->ev_frames_done);
     if (ctx->bn) cudaFree(ctx->bn);
     scene_borrowers_stale(ctx, true);
     scene_unborrow(ctx);
@@ -166,6 +170,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->scene_bounds); dev_free(ctx->work_a); dev_free(ctx->work_b); dev_free(ctx->slot_node);
     dev_free(ctx->node_nchild); dev_free(ctx->node_ntri); dev_free(ctx->node_child_base); dev_free(ctx->node_tri_base);
     dev_free(ctx->node_lo); dev_free(ctx->node_hi); dev_free(ctx->level_starts_dev);
+    if (!ctx->scene_borrowed) { dev_free(ctx->nodes_alt); dev_free(ctx->tris_alt); }
     dev_free(ctx->nodes); dev_free(ctx->tris); dev_free(ctx->counters); dev_free(ctx->loop_sums);
     dev_free(ctx->trans16); dev_free(ctx->multi16); dev_free(ctx->view_packed);
     dev_free(ctx->trans_f); dev_free(ctx->multi_f); dev_free(ctx->view_f);
@@ -216,6 +221,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "bands")) ctx->opt_bands = (int)(value < 1 ? 1 : (value > MRT_MAX_BANDS ? MRT_MAX_BANDS : value));
     else if (!strcmp(name, "trace_ctas_per_sm")) ctx->opt_trace_ctas_per_sm = (int)(value > 32 ? 32 : value);
     else if (!strcmp(name, "wide_refit")) ctx->opt_wide_refit = value != 0;
+    else if (!strcmp(name, "async_update")) ctx->opt_async_update = value != 0;
     else if (!strcmp(name, "build_device_loop")) { ctx->opt_build_device_loop = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "builder")) { ctx->opt_builder = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "ploc_radius")) { ctx->opt_ploc_radius = (int)(value < 1 ? 1 : (value > 32 ? 32 : value)); ctx->bvh_valid = false; }
@@ -275,12 +281,33 @@ int mrt_scene_upload_mesh(mrt_context* ctx, const float* positions, uint32_t nve
     return MRT_OK;
 }
 
+// lazily created: a context that never updates asynchronously pays nothing
+static int scene_async_objects(mrt_context* ctx) {
+    if (!ctx->upload_stream) MRT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+    if (!ctx->ev_pos_ready) MRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_pos_ready, cudaEventDisableTiming));
+    if (!ctx->ev_refit_done) MRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_refit_done, cudaEventDisableTiming));
+    return MRT_OK;
+}
+
 int mrt_scene_update_positions(mrt_context* ctx, const float* positions, uint32_t nverts) {
     MRT_ENTER(ctx);
     if (ctx->scene_kind != 2) return mrt_fail(ctx, MRT_ERR_STATE, "no mesh uploaded");
     if (ctx->scene_borrowed) return mrt_fail(ctx, MRT_ERR_STATE, "the scene is borrowed (mrt_scene_share): update it through its owner");
     if (nverts != ctx->nverts || !positions) return mrt_fail(ctx, MRT_ERR_INVALID, "vertex count mismatch (%u vs %u)", nverts, ctx->nverts);
+    if (ctx->opt_async_update) {
+        // The vertex array is read by builds and refits only (rendering reads the leaf triangles), so the copy runs on
+        // the scene-update stream beside the frames in flight, behind the refit that may still read the old positions.
+        MRT_TRY(scene_async_objects(ctx));
+        MRT_CUDA(ctx, cudaMemcpyAsync(ctx->pos.p, positions, sizeof(float) * 3 * (size_t)nverts, cudaMemcpyHostToDevice, ctx->upload_stream));
+        MRT_CUDA(ctx, cudaEventRecord(ctx->ev_pos_ready, ctx->upload_stream));
+        ctx->pos_upload_pending = true;
+        return MRT_OK;
+    }
     scene_borrowers_stale(ctx, false);
+    if (ctx->pos_upload_pending) {  // an asynchronous upload queued before the option was switched off
+        MRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pos_ready, 0));
+        ctx->pos_upload_pending = false;
+    }
     MRT_CUDA(ctx, cudaMemcpyAsync(ctx->pos.p, positions, sizeof(float) * 3 * (size_t)nverts, cudaMemcpyHostToDevice, ctx->stream));
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MRT_OK;
@@ -291,8 +318,51 @@ int mrt_scene_build(mrt_context* ctx, int build_mode) {
     if (ctx->scene_kind != 2) return mrt_fail(ctx, MRT_ERR_STATE, "mrt_scene_build: no mesh uploaded");
     if (ctx->scene_borrowed) return mrt_fail(ctx, MRT_ERR_STATE, "the scene is borrowed (mrt_scene_share): build it through its owner");
     if (build_mode != MRT_BUILD_REFIT && build_mode != MRT_BUILD_FULL) return mrt_fail(ctx, MRT_ERR_INVALID, "unknown build mode %d", build_mode);
+    if (build_mode == MRT_BUILD_REFIT && ctx->opt_async_update && bvh_refit_can_be_async(ctx)) {
+        // The host never blocks, and neither do the frames in flight: the tree exists twice, the refit runs on the
+        // scene-update stream (behind the upload) into the copy nobody reads, and the copies swap roles.  Two event
+        // edges order it against rendering:
+        //   * the copy being rewritten was current until the PREVIOUS asynchronous refit: its last readers are the
+        //     frames recorded before that call, marked by the events recorded then (and re-recorded now);
+        //   * frames recorded from now on wait for this refit and read the new copy (the contexts that borrow the
+        //     scene stay valid: same topology, same sizes -- only their two pointers move).
+        MRT_TRY(scene_async_objects(ctx));
+        cudaStream_t ss = ctx->upload_stream;
+        std::vector<mrt_context*> all = ctx->borrowers;
+        all.push_back(ctx);
+        for (mrt_context* c : all) {
+            if (!c->ev_frames_done) MRT_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_frames_done, cudaEventDisableTiming));
+            if (c->frames_marked) MRT_CUDA(ctx, cudaStreamWaitEvent(ss, c->ev_frames_done, 0));
+            MRT_CUDA(ctx, cudaEventRecord(c->ev_frames_done, c->stream));
+            c->frames_marked = true;
+        }
+        if (!ctx->alt_valid) {  // first refit after a full build: the second copy takes over the topology
+            MRT_TRY(dev_reserve(ctx, ctx->nodes_alt, ctx->num_nodes));
+            MRT_TRY(dev_reserve(ctx, ctx->tris_alt, 3 * (size_t)ctx->ntris));
+            MRT_CUDA(ctx, cudaMemcpyAsync(ctx->nodes_alt.p, ctx->nodes.p, sizeof(WideNode) * (size_t)ctx->num_nodes, cudaMemcpyDeviceToDevice, ss));
+            MRT_CUDA(ctx, cudaMemcpyAsync(ctx->tris_alt.p, ctx->tris.p, sizeof(float4) * 3 * (size_t)ctx->ntris, cudaMemcpyDeviceToDevice, ss));
+            ctx->alt_valid = true;
+        }
+        std::swap(ctx->nodes, ctx->nodes_alt);
+        std::swap(ctx->tris, ctx->tris_alt);
+        ctx->pos_upload_pending = false;  // same stream: the upload comes first
+        MRT_TRY(bvh_refit(ctx, false, ss));
+        MRT_CUDA(ctx, cudaEventRecord(ctx->ev_refit_done, ss));
+        ctx->refit_recorded = true;
+        for (mrt_context* c : all) {
+            MRT_CUDA(ctx, cudaStreamWaitEvent(c->stream, ctx->ev_refit_done, 0));
+            if (c != ctx) { c->nodes = ctx->nodes; c->tris = ctx->tris; }
+        }
+        return MRT_OK;
+    }
     scene_borrowers_stale(ctx, false);
-    return build_mode == MRT_BUILD_REFIT ? bvh_refit(ctx) : bvh_build_full(ctx);
+    if (ctx->pos_upload_pending) {  // positions uploaded asynchronously: the build reads them on the main stream
+        MRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pos_ready, 0));
+        ctx->pos_upload_pending = false;
+    }
+    // (an asynchronous refit still running has every main stream waiting for it already; builds are synchronous, so a
+    // later asynchronous upload cannot overtake this one)
+    return build_mode == MRT_BUILD_REFIT ? bvh_refit(ctx, true) : bvh_build_full(ctx);
 }
 
 int mrt_scene_share(mrt_context* ctx, mrt_context* owner) {
@@ -610,6 +680,7 @@ int mrt_readback_wait(mrt_context* ctx, int frames_in_flight) {
 int mrt_sync(mrt_context* ctx) {
     MRT_ENTER(ctx);
     sky_join(ctx);
+    if (ctx->upload_stream) MRT_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));  // option async_update: the caller's vertex array is free again
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MRT_OK;
 }
@@ -632,6 +703,7 @@ int mrt_stats_get(mrt_context* ctx, mrt_stats* out) {
     if (ctx->have_ldr && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->stats.ms_tonemap = ms;
     if (ctx->have_denoised && cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]) == cudaSuccess) ctx->stats.ms_denoise = ms;
     if (ctx->have_temporal && cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]) == cudaSuccess) ctx->stats.ms_temporal = ms;
+    if (ctx->build_time_pending && cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]) == cudaSuccess) { ctx->stats.ms_build = ms; ctx->build_time_pending = false; }
     cudaGetLastError();
     if (ctx->secondary_done && ctx->stats.secondary_rays == ~0ull) {
         if (ctx->scene_kind == 1) {

@@ -1282,7 +1282,7 @@ int build_ploc(mrt_context* ctx) {
 }
 
 // boxes, planes and leaf triangles of every level, deepest first (the topology words are in place)
-int wide_refit_levels(mrt_context* ctx) {
+int wide_refit_levels(mrt_context* ctx, cudaStream_t stream) {
     MRT_TRY(dev_reserve(ctx, ctx->node_lo, ctx->num_nodes));
     MRT_TRY(dev_reserve(ctx, ctx->node_hi, ctx->num_nodes));
     WideRefit A;
@@ -1292,7 +1292,7 @@ int wide_refit_levels(mrt_context* ctx) {
         A.first = ctx->level_starts[l];
         A.count = ctx->level_starts[l + 1] - A.first;
         if (A.count == 0) continue;
-        k_wide_refit<<<div_up(A.count, 256 / 8), 256, 0, ctx->stream>>>(A);
+        k_wide_refit<<<div_up(A.count, 256 / 8), 256, 0, stream>>>(A);
         MRT_LAUNCHED(ctx);
     }
     return mrt_check_cuda(ctx, cudaGetLastError(), "wide_refit");
@@ -1304,7 +1304,7 @@ int emit_nodes(mrt_context* ctx) {
                                                                                   ctx->node_child_base.p, ctx->node_tri_base.p,
                                                                                   ctx->order.p, ctx->nodes.p, ctx->tris.p);
         MRT_LAUNCHED(ctx);
-        return wide_refit_levels(ctx);
+        return wide_refit_levels(ctx, ctx->stream);
     }
     k_emit_nodes<<<div_up(ctx->num_nodes, 128), 128, 0, ctx->stream>>>(make_tree(ctx), ctx->num_nodes, ctx->slot_node.p,
                                                                        ctx->node_child_base.p, ctx->node_tri_base.p,
@@ -1319,6 +1319,7 @@ int emit_nodes(mrt_context* ctx) {
 int bvh_build_full(mrt_context* ctx) {
     const uint32_t n = ctx->ntris;
     ctx->bvh_valid = false;
+    ctx->alt_valid = false;  // option async_update: the second copy of the tree holds another topology now
     ctx->num_nodes = 0;
     ctx->num_leaf_tris = 0;
     if (n == 0) {
@@ -1449,6 +1450,7 @@ int bvh_build_full(mrt_context* ctx) {
     cudaEventRecord(ctx->ev[13], ctx->stream);
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev[12], ctx->ev[13]);
+    ctx->build_time_pending = false;
     ctx->stats.num_triangles = n;
     ctx->stats.num_wide_nodes = ctx->num_nodes;
     ctx->stats.bvh_bytes = (uint64_t)ctx->num_nodes * sizeof(WideNode) + (uint64_t)n * 48u;
@@ -1467,11 +1469,23 @@ int bvh_build_full(mrt_context* ctx) {
     return MRT_OK;
 }
 
-int bvh_refit(mrt_context* ctx) {
+// the refit that needs no host round trip: topology in place, level table known
+bool bvh_refit_can_be_async(const mrt_context* ctx) {
+    return ctx->bvh_valid && ctx->num_nodes != 0 && ctx->opt_wide_refit && ctx->level_starts.size() >= 2 && ctx->level_starts.back() == ctx->num_nodes;
+}
+
+int bvh_refit(mrt_context* ctx, bool wait, cudaStream_t side) {
     if (!ctx->bvh_valid || ctx->num_nodes == 0) return bvh_build_full(ctx);
+    if (!wait) {  // asynchronous (bvh_refit_can_be_async): queued on the caller's scene-update stream; mrt_stats_get reads the time later
+        cudaEventRecord(ctx->ev[12], side);
+        MRT_TRY(wide_refit_levels(ctx, side));
+        cudaEventRecord(ctx->ev[13], side);
+        ctx->build_time_pending = true;
+        return MRT_OK;
+    }
     cudaEventRecord(ctx->ev[12], ctx->stream);
     if (ctx->opt_wide_refit && ctx->level_starts.size() >= 2 && ctx->level_starts.back() == ctx->num_nodes) {
-        MRT_TRY(wide_refit_levels(ctx));  // the topology words and the triangles' primitive ids are in place
+        MRT_TRY(wide_refit_levels(ctx, ctx->stream));  // the topology words and the triangles' primitive ids are in place
     } else {
         MRT_TRY(compute_boxes(ctx));
         MRT_TRY(climb_boxes(ctx));
@@ -1480,5 +1494,6 @@ int bvh_refit(mrt_context* ctx) {
     cudaEventRecord(ctx->ev[13], ctx->stream);
     MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev[12], ctx->ev[13]);
+    ctx->build_time_pending = false;
     return MRT_OK;
 }

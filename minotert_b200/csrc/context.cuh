@@ -82,6 +82,7 @@ struct mrt_context {
     int opt_fused_shade = 0;         // shade stage of a bounce wave inside the traversal kernel (mesh.cu k_trace_shade); A/B: +1.5 % at 1080p 1 spp, -2 % at 4K 8 spp
     int opt_trace_ctas_per_sm = 0;   // 0: as many as fit; n: persistent traversal grids use n CTAs per SM (co-running contexts)
     int opt_builder = 1;             // 0: Karras LBVH hierarchy, 1: PLOC (locally-ordered clustering) hierarchy
+    int opt_async_update = 0;        // mrt_scene_update_positions + MRT_BUILD_REFIT return without waiting for the GPU (see minotert.h)
     int opt_wide_refit = 1;          // boxes, planes and leaf triangles level by level on the wide tree, 8 lanes per node (0: round 1's binary climb + one thread per node)
     int opt_build_device_loop = 1;   // PLOC rounds and collapse levels looped inside cooperative kernels (0: host-driven loops with a readback per round)
     int opt_ploc_radius = 6;         // +-positions searched for the nearest cluster (measured best of 2..32 on config 2)
@@ -120,6 +121,13 @@ struct mrt_context {
     DevArray<uint32_t> node_nchild, node_ntri, node_child_base, node_tri_base;
     DevArray<WideNode> nodes;
     DevArray<float4> tris;
+    // option async_update: vertex uploads on their own stream, ordered against refits and the borrowers' frames by events
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t ev_pos_ready = nullptr, ev_refit_done = nullptr, ev_frames_done = nullptr;
+    bool pos_upload_pending = false, refit_recorded = false, build_time_pending = false, frames_marked = false;
+    DevArray<WideNode> nodes_alt;                         // second copy of the tree: an asynchronous refit writes the copy no
+    DevArray<float4> tris_alt;                            // frame in flight reads, then the copies swap roles
+    bool alt_valid = false;                               // nodes_alt / tris_alt hold the current topology
     DevArray<float4> node_lo, node_hi;                    // boxes of the wide nodes (scratch of the level-wise emission / refit)
     DevArray<uint32_t> level_starts_dev;                  // first wide node of each level (+ the node count), written by k_collapse_loop
     std::vector<uint32_t> level_starts;                   // host copy: level L = nodes [level_starts[L], level_starts[L + 1])
@@ -255,7 +263,8 @@ int temporal_accumulate(mrt_context* ctx, float maxHistory, bool reset);
 int sky_gen_aerial(mrt_context* ctx, const mrt_primary_constants* c, const float cameraPos[3], const float sunDir[3], const float sunIll[3]);
 int tonemap_run(mrt_context* ctx, int mode, float exposure, const float* params, uint32_t nparams, int source);
 int bvh_build_full(mrt_context* ctx);
-int bvh_refit(mrt_context* ctx);
+int bvh_refit(mrt_context* ctx, bool wait = true, cudaStream_t side = nullptr);  // wait = false: queued on `side` only (mrt_stats_get reads ms_build later)
+bool bvh_refit_can_be_async(const mrt_context* ctx);
 int mesh_primary(mrt_context* ctx);
 int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t spp, uint32_t bounces, uint32_t flags);
 int probe_sky_color(mrt_context* ctx, const float cameraPos[3], const float* dirs, uint32_t n, float* out);

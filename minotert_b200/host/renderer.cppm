@@ -48,6 +48,13 @@ public:
     }
     void updateMesh(float const* positions, u32 nverts, bool refit) {
         auto* const owner = Cuda::serv->owner();
+        if (refit && asyncUpdate) {
+            // option async_update: the library orders upload, refit and the frames in flight on the GPU (events); the
+            // borrowed scenes stay valid and this call returns at once (positions: page-locked, left alone meanwhile)
+            Cuda::serv->checkOn(owner, mrt_scene_update_positions(owner, positions, nverts));
+            Cuda::serv->checkOn(owner, mrt_scene_build(owner, MRT_BUILD_REFIT));
+            return;
+        }
         waitBorrowers();  // frames in flight still read the nodes a refit rewrites in place
         Cuda::serv->checkOn(owner, mrt_scene_update_positions(owner, positions, nverts));
         Cuda::serv->checkOn(owner, mrt_scene_build(owner, refit ? MRT_BUILD_REFIT : MRT_BUILD_FULL));
@@ -118,8 +125,9 @@ public:
     void resetStats() const {
         forEachFrame([](mrt_context* c) { return mrt_stats_reset(c); });
     }
-    void setOption(char const* name, std::int64_t value) const {
+    void setOption(char const* name, std::int64_t value) {
         forEachFrame([&](mrt_context* c) { return mrt_set_option(c, name, value); });
+        if (std::strcmp(name, "async_update") == 0) asyncUpdate = value != 0;
     }
 
     uvec2 outputSize;
@@ -127,6 +135,7 @@ public:
     Tonemapper tonemapper;
     Denoiser denoiser;
     Reprojector reprojector;
+    bool asyncUpdate = false;  // updateMesh(refit) without host stalls (mrt_set_option "async_update")
     bool temporal = false;  // reproject + accumulate along GBuffer::motion instead of denoising
     ReprojectorParams reprojectorParams = ReprojectorParams::make_default();
     // ImGui statics of Renderer_impl::denoise (renderer.ixx:140-141)

@@ -909,6 +909,45 @@ def test_renderer_frames_in_flight(oracle, blue_noise):
     assert not np.array_equal(one[3], one[4])      # the refit is visible
 
 
+def test_renderer_async_mesh_updates(oracle, blue_noise):
+    """Option async_update (animated scenes, BASELINE config 5): Renderer::updateMesh(refit) returns without waiting for
+    the GPU -- the vertex upload runs on its own stream, the refit is ordered behind the frames in flight and before the
+    next ones with events, the borrowed scenes stay valid.  A new vertex array EVERY frame, 1 and 3 frames in flight,
+    with a synchronous full rebuild in the middle: every framebuffer equals the synchronous renderer's."""
+    import torch
+    from minotert_b200 import host
+    pos, idx, alb, view = scenes.small_terrain()
+    w, h = 160, 96
+    cam = host.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
+    nframes = 9
+    anim = [torch.from_numpy(np.ascontiguousarray(scenes.animate(pos, f / 10.0, amplitude=0.002))).pin_memory() for f in range(nframes)]
+
+    def run(in_flight, async_update):
+        r = host.Renderer(w, h, blue_noise, frames_in_flight=in_flight)
+        try:
+            r.set_mesh(pos, idx, alb)
+            r.configure(samples=2, bounces=2, accumulate=False, tonemap="amd", exposure=1.0)
+            r.set_option("async_update", async_update)
+            bufs = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(nframes)]
+            for f in range(nframes):
+                r.update_mesh(anim[f].numpy(), refit=(f != 5))
+                r.draw(cam)
+                r.read_framebuffer_async(C.c_void_p(bufs[f].data_ptr()), bufs[f].numel())
+                r.wait_framebuffer(in_flight - 1)
+            r.wait_framebuffer(0)
+            assert r.stats().ms_build > 0.0
+            return [b.numpy().copy() for b in bufs]
+        finally:
+            r.close()
+
+    want = run(1, 0)
+    assert not np.array_equal(want[0], want[1])
+    for in_flight in (1, 3):
+        got = run(in_flight, 1)
+        for f in range(nframes):
+            assert np.array_equal(got[f], want[f]), f"{in_flight} frame(s) in flight, frame {f + 1}"
+
+
 def test_tonemap_of_color_without_materialising_it(gpu_ctx, oracle, sky_inputs, blue_noise):
     """Triangle path, tonemap source COLOR: while nobody has asked for the RGBA16F image the tonemapper reads the fp32
     accumulator and rounds its average through fp16 in registers; the framebuffer is bit-identical to resolving

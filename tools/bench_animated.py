@@ -18,6 +18,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def run_animated(frames=120, rebuild_every=10, frames_in_flight=3, async_update=1, scene="scene_1m", spp=1, bounces=1):
+    """The measurement as a function (bench.py's `configs` entry animated_1m_1080p): returns the JSON line as a dict."""
+    args = argparse.Namespace(frames=frames, rebuild_every=rebuild_every, frames_in_flight=frames_in_flight,
+                              async_update=async_update, scene=scene, spp=spp, bounces=bounces)
+    return measure(args)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=40)
@@ -25,8 +32,13 @@ def main():
     ap.add_argument("--scene", default="scene_1m")
     ap.add_argument("--spp", type=int, default=1)
     ap.add_argument("--bounces", type=int, default=1)
+    ap.add_argument("--frames-in-flight", type=int, default=1, help="> 1 or --async-update: pipelined loop (async readbacks)")
+    ap.add_argument("--async-update", type=int, default=0, help="mrt_set_option async_update: upload + refit without host stalls")
     args = ap.parse_args()
+    print(json.dumps(measure(args)))
 
+
+def measure(args):
     import torch
     from PIL import Image
     from minotert_b200 import host, scenes
@@ -35,9 +47,10 @@ def main():
     w, h = 1920, 1080
     pos, idx, alb, view = getattr(scenes, args.scene)()
     bn = np.ascontiguousarray(np.array(Image.open(os.path.join(ROOT, "assets", "blue_noise.png")).convert("RGBA"), np.uint8))
-    r = host.Renderer(w, h, bn)
+    r = host.Renderer(w, h, bn, frames_in_flight=args.frames_in_flight)
     r.set_mesh(pos, idx, alb)
     r.configure(samples=args.spp, bounces=args.bounces)
+    r.set_option("async_update", args.async_update)
     cam = host.make_camera(w, h, view["position"], view["yaw_deg"], view["pitch_deg"])
     fb = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
     fb_ptr = C.c_void_p(fb.data_ptr())
@@ -47,6 +60,9 @@ def main():
     frames = [t.numpy() for t in pinned]
     r.draw(cam)
     r.read_framebuffer_into(fb_ptr, fb.numel())
+
+    if args.frames_in_flight > 1 or args.async_update:
+        return pipelined(args, r, cam, frames, idx, w, h)
 
     t_update = t_rebuild = t_render = 0.0
     n_refit = n_rebuild = 0
@@ -75,14 +91,52 @@ def main():
         frame_time = t2 - t0
     total = time.perf_counter() - t_all
     st = r.stats()
-    print(json.dumps({
+    out = ({
         "workload": f"animated {args.scene} ({idx.shape[0]} triangles), {w}x{h}, {args.spp} spp, {args.bounces} bounce(s), freecam",
+        "mode": "synchronous: upload, refit / rebuild, draw and readback one after the other",
         "frames": args.frames, "ms_per_frame": 1e3 * total / args.frames, "fps": args.frames / total,
         "ms_upload_plus_refit": 1e3 * t_update / max(1, n_refit), "ms_upload_plus_rebuild": 1e3 * t_rebuild / max(1, n_rebuild),
         "ms_render_plus_readback": 1e3 * t_render / args.frames, "rebuild_every": args.rebuild_every,
         "Mrays_per_s_e2e": rays / total / 1e6, "h2d_bytes_per_frame": int(frames[0].nbytes) + 676,
-        "d2h_bytes_per_frame": int(fb.numel()), "wide_nodes": int(st.num_wide_nodes), "stack_overflows": int(st.stack_overflows)}))
+        "d2h_bytes_per_frame": int(fb.numel()), "wide_nodes": int(st.num_wide_nodes), "stack_overflows": int(st.stack_overflows)})
     r.close()
+    return out
+
+
+def pipelined(args, r, cam, frames, idx, w, h):
+    """The same frames with the host running ahead: asynchronous readbacks into a ring of pinned framebuffers, up to
+    frames_in_flight - 1 of them pending; with --async-update the vertex upload and the refit do not stall either."""
+    import torch
+    from minotert_b200 import host
+    K = args.frames_in_flight
+    fbs = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(K)]
+    for warm in range(2 * K):
+        r.update_mesh(frames[warm % len(frames)], refit=True)
+        r.draw(cam)
+        r.read_framebuffer_async(C.c_void_p(fbs[warm % K].data_ptr()), fbs[warm % K].numel())
+        r.wait_framebuffer(K - 1)
+    r.wait_framebuffer(0)
+    r.stats_reset()
+    t_all = time.perf_counter()
+    for f in range(args.frames):
+        host.freecam_update(cam, 1.0 / 60.0, up=True, moving=True, cursor=(2.0, 0.0))
+        full = args.rebuild_every > 0 and f % args.rebuild_every == args.rebuild_every - 1
+        r.update_mesh(frames[f % len(frames)], refit=not full)
+        r.draw(cam)
+        r.read_framebuffer_async(C.c_void_p(fbs[f % K].data_ptr()), fbs[f % K].numel())
+        r.wait_framebuffer(K - 1)
+    r.wait_framebuffer(0)
+    total = time.perf_counter() - t_all
+    st = r.stats()
+    out = ({
+        "workload": f"animated {args.scene} ({idx.shape[0]} triangles), {w}x{h}, {args.spp} spp, {args.bounces} bounce(s), freecam",
+        "mode": f"pipelined: {K} frame(s) in flight, async_update {args.async_update}",
+        "frames": args.frames, "ms_per_frame": 1e3 * total / args.frames, "fps": args.frames / total,
+        "rebuild_every": args.rebuild_every, "Mrays_per_s_e2e": st.total_rays / total / 1e6,
+        "h2d_bytes_per_frame": int(frames[0].nbytes) + 676, "d2h_bytes_per_frame": int(fbs[0].numel()),
+        "wide_nodes": int(st.num_wide_nodes), "stack_overflows": int(st.stack_overflows)})
+    r.close()
+    return out
 
 
 if __name__ == "__main__":
