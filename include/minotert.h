@@ -193,7 +193,8 @@ const char* mrt_last_error(const mrt_context* ctx);
  *                             and mrt_scene_build(MRT_BUILD_REFIT) queues the refit without waiting for it: frames in
  *                             flight of contexts that borrow the scene (mrt_scene_share) are waited for on the GPU, the
  *                             borrowers stay valid (a refit rewrites nodes and triangles in place) and the frames they
- *                             record next wait for the refit.  MRT_BUILD_FULL stays synchronous.
+ *                             record next wait for the refit.  MRT_BUILD_FULL still returns when the build is done, but
+ *                             runs beside the frames in flight (into the second copy of the tree) instead of draining them.
  *   "builder" 0/1             hierarchy builder: 0 Karras LBVH, 1 PLOC (default); invalidates the BVH
  *   "ploc_radius" 1..32       PLOC search radius (default 6); invalidates the BVH */
 int mrt_set_option(mrt_context* ctx, const char* name, int64_t value);

@@ -355,6 +355,42 @@ int mrt_scene_build(mrt_context* ctx, int build_mode) {
         }
         return MRT_OK;
     }
+    if (build_mode == MRT_BUILD_FULL && ctx->opt_async_update && ctx->bvh_valid && ctx->num_nodes != 0 && ctx->opt_sort_rays == 0) {
+        // A rebuild with frames in flight: it needs the host (two counters are read back), but not the GPU's
+        // attention -- it runs on the scene-update stream into the copy of the tree nobody reads, while the frames
+        // already recorded keep rendering the current copy; the host blocks on the scene-update stream only.  The same two
+        // event edges as for the refit above; afterwards the copies swap roles and the borrowers take over the new sizes.
+        // (Not with the ray sort on: it shares the radix-sort scratch with the builder.)
+        MRT_TRY(scene_async_objects(ctx));
+        cudaStream_t ss = ctx->upload_stream;
+        std::vector<mrt_context*> all = ctx->borrowers;
+        all.push_back(ctx);
+        for (mrt_context* c : all) {
+            if (!c->ev_frames_done) MRT_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_frames_done, cudaEventDisableTiming));
+            if (c->frames_marked) MRT_CUDA(ctx, cudaStreamWaitEvent(ss, c->ev_frames_done, 0));
+            MRT_CUDA(ctx, cudaEventRecord(c->ev_frames_done, c->stream));
+            c->frames_marked = true;
+        }
+        std::swap(ctx->nodes, ctx->nodes_alt);
+        std::swap(ctx->tris, ctx->tris_alt);
+        ctx->pos_upload_pending = false;  // same stream: the upload comes first
+        cudaStream_t main_stream = ctx->stream;
+        ctx->stream = ss;
+        const int s = bvh_build_full(ctx);  // leaves alt_valid false: the other copy holds the old topology
+        ctx->stream = main_stream;
+        if (s != MRT_OK) return s;
+        MRT_CUDA(ctx, cudaEventRecord(ctx->ev_refit_done, ss));
+        ctx->refit_recorded = true;
+        for (mrt_context* c : all) {
+            MRT_CUDA(ctx, cudaStreamWaitEvent(c->stream, ctx->ev_refit_done, 0));
+            if (c == ctx) continue;
+            c->nodes = ctx->nodes; c->tris = ctx->tris;
+            c->num_nodes = ctx->num_nodes; c->num_leaf_tris = ctx->num_leaf_tris;
+            c->stats.num_wide_nodes = ctx->stats.num_wide_nodes; c->stats.bvh_bytes = ctx->stats.bvh_bytes;
+            c->stats.sah_node_cost = ctx->stats.sah_node_cost; c->stats.sah_tri_cost = ctx->stats.sah_tri_cost;
+        }
+        return MRT_OK;
+    }
     scene_borrowers_stale(ctx, false);
     if (ctx->pos_upload_pending) {  // positions uploaded asynchronously: the build reads them on the main stream
         MRT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pos_ready, 0));

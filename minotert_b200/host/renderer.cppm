@@ -48,11 +48,12 @@ public:
     }
     void updateMesh(float const* positions, u32 nverts, bool refit) {
         auto* const owner = Cuda::serv->owner();
-        if (refit && asyncUpdate) {
-            // option async_update: the library orders upload, refit and the frames in flight on the GPU (events); the
-            // borrowed scenes stay valid and this call returns at once (positions: page-locked, left alone meanwhile)
+        if (asyncUpdate) {
+            // option async_update: the library orders upload, refit / rebuild and the frames in flight on the GPU
+            // (events); the borrowed scenes stay valid.  A refit returns at once, a rebuild when its own stream is done --
+            // the frames already recorded keep rendering meanwhile (positions: page-locked, left alone until then)
             Cuda::serv->checkOn(owner, mrt_scene_update_positions(owner, positions, nverts));
-            Cuda::serv->checkOn(owner, mrt_scene_build(owner, MRT_BUILD_REFIT));
+            Cuda::serv->checkOn(owner, mrt_scene_build(owner, refit ? MRT_BUILD_REFIT : MRT_BUILD_FULL));
             return;
         }
         waitBorrowers();  // frames in flight still read the nodes a refit rewrites in place
