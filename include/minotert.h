@@ -184,6 +184,9 @@ const char* mrt_last_error(const mrt_context* ctx);
  *                             contexts that share a GPU
  *   "build_device_loop" 0/1   PLOC rounds and collapse levels looped inside two cooperative kernels (default 1) or
  *                             driven from the host with a readback per round (0); same tree either way; invalidates the BVH
+ *   "fused_sort" 0/1          Morton / ray radix sort: all 8-bit passes in one cooperative launch when every tile's CTA is
+ *                             resident at once (<= 1.2 M keys; default 1), or 5 launches per pass (0); same permutation;
+ *                             invalidates the BVH
  *   "wide_refit" 0/1          final node emission and MRT_BUILD_REFIT level by level on the wide tree, 8 lanes per node
  *                             (default 1), or through the binary tree's boxes with one thread per node (0); same nodes
  *                             and leaf triangles bit for bit

@@ -557,6 +557,33 @@ def test_wide_refit_gives_the_same_nodes(gpu_ctx, maker, builder):
     assert not np.array_equal(got[0, "full"][0], got[0, "refit"][0])  # the animation is visible in the nodes
 
 
+@pytest.mark.parametrize("maker", ["tiny", "soup", "hall_260k", "scene_1m"])
+def test_fused_sort_gives_the_same_tree(gpu_ctx, maker):
+    """Option fused_sort (default): the Morton sort's eight passes inside one cooperative launch (one CTA per tile of 8192
+    keys, grid barriers between the phases) vs five launches per pass: the same stable permutation, hence the same nodes
+    and leaf triangles bit for bit.  scene_1m (128 of at most 148 tiles) is close to the co-residency limit of the fused kernel."""
+    if maker == "tiny":
+        pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.5], [2, 0, 1], [2, 2, 1]], np.float32)
+        idx = np.array([[0, 1, 2], [1, 3, 2], [3, 4, 5]], np.uint32)
+        alb = np.full((3, 3), 0.5, np.float32)
+    elif maker == "soup":  # many equal keys: duplicates exercise the stability of the ranking
+        rng = np.random.default_rng(14)
+        n = 30000
+        c = rng.integers(0, 40, (n, 3)).astype(np.float32)
+        pos = (c[:, None, :] + 0.25 * rng.integers(0, 3, (n, 3, 3)).astype(np.float32)).reshape(-1, 3).astype(np.float32)
+        idx = np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)
+        alb = np.full((n, 3), 0.5, np.float32)
+    else:
+        pos, idx, alb, _ = getattr(scenes, maker)()
+    gpu_ctx.upload_mesh(pos, idx, alb)
+    trees = []
+    for fused in (0, 1):
+        gpu_ctx.set_option("fused_sort", fused)
+        gpu_ctx.build()
+        trees.append((gpu_ctx.readback(capi.BUF_BVH_NODES).copy(), gpu_ctx.readback(capi.BUF_BVH_TRIS).copy()))
+    assert np.array_equal(trees[0][0], trees[1][0]) and np.array_equal(trees[0][1], trees[1][1])
+
+
 def test_refit_matches_full_rebuild(gpu_ctx, oracle):
     """BASELINE config 5 mechanics: animate vertices, REFIT; closest hits equal a fresh FULL build and brute force."""
     pos, idx, alb, _ = scenes.small_terrain()
