@@ -329,12 +329,18 @@ constexpr unsigned LOOP_WARPS = LOOP_THREADS / 32;
 
 // -DBUILD_PROFILE: thread 0 of CTA 0 prints the time between phase boundaries of the cooperative loops
 #ifdef BUILD_PROFILE
+// phase boundaries are time-stamped into a global table and printed when the kernel ends (a printf per phase costs ~30 us)
 MRT_D unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define PROF_DECL unsigned long long prof_t = gtimer();
-#define PROF(label, a, b) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long n_ = gtimer(); printf("%s %u %u: %llu ns\n", label, (unsigned)(a), (unsigned)(b), n_ - prof_t); prof_t = n_; } } while (0)
+struct ProfRec { const char* label; unsigned a, b; unsigned long long dt; };
+__device__ ProfRec g_prof[512];
+__device__ unsigned g_prof_n;
+#define PROF_DECL unsigned long long prof_t = gtimer(); if (blockIdx.x == 0 && threadIdx.x == 0) g_prof_n = 0;
+#define PROF(label_, a_, b_) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long n_ = gtimer(); if (g_prof_n < 512) { g_prof[g_prof_n].label = label_; g_prof[g_prof_n].a = (unsigned)(a_); g_prof[g_prof_n].b = (unsigned)(b_); g_prof[g_prof_n].dt = n_ - prof_t; g_prof_n++; } prof_t = gtimer(); } } while (0)
+#define PROF_DUMP() do { if (blockIdx.x == 0 && threadIdx.x == 0) for (unsigned k_ = 0; k_ < g_prof_n; k_++) printf("%s %u %u: %llu ns\n", g_prof[k_].label, g_prof[k_].a, g_prof[k_].b, g_prof[k_].dt); } while (0)
 #else
 #define PROF_DECL
 #define PROF(label, a, b) do {} while (0)
+#define PROF_DUMP() do {} while (0)
 #endif
 
 // exclusive scan of one 32-bit value per thread (packed counters: two 16-bit fields); *total = CTA sum
@@ -497,8 +503,94 @@ MRT_D uint2 ploc_round(const PlocLoop& A, uint32_t m, int cur, uint32_t next_nod
     return total;
 }
 
+// The last rounds (<= LOOP_THREADS clusters, CTA 0 alone) with the cluster list in SHARED memory: ids, boxes and primitive
+// counts are loaded once, a round is a neighbour search, a mutual-pair test and an in-place compaction between CTA
+// barriers, and the only global traffic left is the record of each new node going out (nothing waits for it).  The
+// generic round above costs ~5.5 us here (about ten dependent round trips to L2 per round, ~22 rounds at one million
+// triangles); this one ~1 us.  Same pairs, same node ids, same boxes: one thread per position, the scan of ploc_round.
+#ifndef PLOC_SMEM_TAIL
+#define PLOC_SMEM_TAIL 1
+#endif
+MRT_D void ploc_tail_shared(const PlocLoop& A, uint32_t& m, uint32_t& next_node, uint32_t& rounds, uint32_t& status, int cur,
+                            float4* slo, float4* shi, uint32_t* scid, uint32_t* scnt, uint32_t* snn) {
+    const uint32_t i = threadIdx.x;
+    const int nprims = (int)A.n;
+    if (i < m) {
+        const uint32_t c = A.clusters[cur][i];
+        scid[i] = c;
+        slo[i] = A.lo[c];
+        shi[i] = A.hi[c];
+        scnt[i] = (int)c >= nprims - 1 ? 1u : A.count[c];
+    }
+    __syncthreads();
+    while (status == 0 && m > 1) {
+        const int radius = ploc_radius_for(A.radius, m);
+        if (i < m) {
+            const float4 ilo = slo[i], ihi = shi[i];
+            const int j0 = max((int)i - radius, 0), j1 = min((int)i + radius, (int)m - 1);
+            float best = 3.0e38f;
+            uint32_t bj = i, bkey = 0xFFFFFFFFu;
+            for (int j = j0; j <= j1; j++) {  // same pair order and tie-break as ploc_round
+                if (j == (int)i) continue;
+                const float a = merged_area(ilo, ihi, slo[j], shi[j]);
+                const uint32_t dist = (uint32_t)abs(j - (int)i);
+                const uint32_t lowpos = (uint32_t)min(j, (int)i);
+                const uint32_t key = (dist << 26) | ((lowpos & 1u) << 25) | (lowpos & 0x1FFFFFFu);
+                if (a < best || (a == best && key < bkey)) { best = a; bj = (uint32_t)j; bkey = key; }
+            }
+            snn[i] = bj;
+        }
+        __syncthreads();
+        bool keep = false, create = false;
+        uint32_t c = 0, cj = 0, cnt = 0;
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        if (i < m) {
+            const uint32_t j = snn[i];
+            const bool mutual = j != i && snn[j] == i;
+            keep = !(mutual && i > j);
+            create = mutual && i < j;
+            c = scid[i]; lo = slo[i]; hi = shi[i]; cnt = scnt[i];
+            if (create) {
+                cj = scid[j];
+                const float4 blo = slo[j], bhi = shi[j];
+                lo = make_float4(fminf(lo.x, blo.x), fminf(lo.y, blo.y), fminf(lo.z, blo.z), 0.0f);
+                hi = make_float4(fmaxf(hi.x, bhi.x), fmaxf(hi.y, bhi.y), fmaxf(hi.z, bhi.z), 0.0f);
+                cnt += scnt[j];
+            }
+        }
+        uint32_t tile_total;
+        const uint32_t ex = cta_scan((keep ? 1u : 0u) | (create ? 0x10000u : 0u), &tile_total);  // its barriers separate the reads above from the writes below
+        if (keep) {
+            if (create) {
+                const uint32_t id = next_node + (ex >> 16);
+                A.left[id] = (int32_t)c;
+                A.right[id] = (int32_t)cj;
+                A.parent[c] = (int32_t)id;
+                A.parent[cj] = (int32_t)id;
+                A.parent[id] = -1;
+                A.count[id] = cnt;
+                A.lo[id] = lo;
+                A.hi[id] = hi;
+                c = id;
+            }
+            const uint32_t pos = ex & 0xFFFFu;
+            scid[pos] = c; slo[pos] = lo; shi[pos] = hi; scnt[pos] = cnt;
+        }
+        __syncthreads();
+        const uint32_t kept = tile_total & 0xFFFFu, created = tile_total >> 16;
+        rounds++;
+        if (created == 0 || kept >= m) { status = 1; break; }
+        next_node += created;
+        m = kept;
+    }
+}
+
 __global__ void __launch_bounds__(LOOP_THREADS, 1) k_ploc_loop(PlocLoop A) {
     __shared__ float4 wlo[LOOP_THREADS + 2 * PLOC_MAX_RADIUS], whi[LOOP_THREADS + 2 * PLOC_MAX_RADIUS];
+#if PLOC_SMEM_TAIL
+    __shared__ uint32_t tail_cid[LOOP_THREADS], tail_cnt[LOOP_THREADS], tail_nn[LOOP_THREADS];
+    static_assert(PLOC_TAIL <= LOOP_THREADS, "the shared-memory tail keeps one cluster per thread");
+#endif
     cg::grid_group grid = cg::this_grid();
     const uint32_t nb = gridDim.x, b = blockIdx.x;
     for (uint32_t i = b * LOOP_THREADS + threadIdx.x; i < A.n; i += nb * LOOP_THREADS) {  // k_ploc_init
@@ -520,6 +612,9 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_ploc_loop(PlocLoop A) {
     }
     if (b != 0) return;
     PROF("ploc grid done round/m", rounds, m);
+#if PLOC_SMEM_TAIL
+    ploc_tail_shared(A, m, next_node, rounds, status, cur, wlo, whi, tail_cid, tail_cnt, tail_nn);
+#endif
     while (status == 0 && m > 1) {
         const uint2 t = ploc_round(A, m, cur, next_node, 0u, 1u, wlo, whi, [] { __syncthreads(); });
         rounds++;
@@ -529,6 +624,7 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_ploc_loop(PlocLoop A) {
         cur ^= 1;
     }
     PROF("ploc tail done round/m", rounds, m);
+    PROF_DUMP();
     if (threadIdx.x == 0) {
         A.result[0] = next_node;
         A.result[1] = status;
@@ -799,6 +895,7 @@ struct CollapseLoop {
     uint32_t* block_sums;     // [gridDim.x]
     uint32_t* result;         // [0] wide nodes, [1] status (0 ok, 1 node budget exceeded), [2] levels
     uint32_t* level_starts;   // [MAX_WIDE_LEVELS + 1]: first node of each level, then the node count
+    const uint32_t* ploc_result;  // k_ploc_loop's result words when it built the hierarchy just before (else null)
     uint32_t n;               // primitives = node budget
 };
 #define MAX_WIDE_LEVELS 1023u
@@ -844,6 +941,8 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop 
     int cur = 0;
     PROF_DECL
     if (gtid == 0) A.items[0][0] = make_uint2((uint32_t)A.T.root, 0u);
+    // the host has not looked at k_ploc_loop's result yet: an incomplete hierarchy is not walked (status 2, every thread alike)
+    if (A.ploc_result && A.n > 1 && (A.ploc_result[1] != 0u || A.ploc_result[0] != A.n - 1u)) { status = 2; level_count = 0; }
     grid.sync();
     while (level_count > 0) {
         if ((size_t)level_start + level_count > A.n) { status = 1; break; }
@@ -885,6 +984,8 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop 
     uint32_t num_nodes = level_start;
     if (status == 0)
         grid_scan(grid, A.node_ntri, 0u, num_nodes, A.block_sums, [&](uint32_t w, uint32_t off) { A.node_tri_base[w] = off; });
+    PROF("collapse tri scan levels/nodes", levels, num_nodes);
+    PROF_DUMP();
     if (gtid == 0) {
         A.result[0] = num_nodes;
         A.result[1] = status;
@@ -1239,15 +1340,14 @@ int build_ploc(mrt_context* ctx) {
         A.n = n; A.radius = ctx->opt_ploc_radius;
         A.clusters[0] = ctx->ploc_c[0].p; A.clusters[1] = ctx->ploc_c[1].p; A.nn = ctx->ploc_nn.p;
         A.left = ctx->bin_left.p; A.right = ctx->bin_right.p; A.parent = ctx->bin_parent.p; A.count = ctx->bin_count.p;
-        A.lo = ctx->bin_lo.p; A.hi = ctx->bin_hi.p; A.block_sums = ctx->loop_sums.p; A.result = ctx->counters.p;
+        A.lo = ctx->bin_lo.p; A.hi = ctx->bin_hi.p; A.block_sums = ctx->loop_sums.p; A.result = ctx->counters.p + 4;
         void* args[] = {&A};
         MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_ploc_loop, dim3(grid), dim3(LOOP_THREADS), args, 0, ctx->stream));
         MRT_LAUNCHED(ctx);
-        uint32_t res[3] = {0, 0, 0};
-        MRT_CUDA(ctx, cudaMemcpyAsync(res, ctx->counters.p, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
-        MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (res[1] != 0) return mrt_fail(ctx, MRT_ERR_INVALID, "PLOC made no progress (round %u)", res[2]);
-        next_node = res[0];
+        // No readback here: the result words (counters[4..6]) are checked by k_collapse_loop on the device -- it refuses a
+        // hierarchy that is not complete -- and by the host together with the collapse's own result: one round trip less
+        ctx->bin_root = (int)n - 2;
+        return MRT_OK;
     } else {
     k_ploc_init<<<div_up(n, 256), 256, 0, ctx->stream>>>(n, ctx->ploc_c[0].p, ctx->bin_parent.p);
     MRT_LAUNCHED(ctx);
@@ -1389,17 +1489,20 @@ int bvh_build_full(mrt_context* ctx) {
         A.slot_node = ctx->slot_node.p; A.node_nchild = ctx->node_nchild.p; A.node_ntri = ctx->node_ntri.p;
         A.node_child_base = ctx->node_child_base.p; A.node_tri_base = ctx->node_tri_base.p;
         A.block_sums = reinterpret_cast<uint32_t*>(ctx->loop_sums.p); A.result = ctx->counters.p; A.n = n;
+        A.ploc_result = (n > 1 && ctx->opt_builder == 1) ? ctx->counters.p + 4 : nullptr;
         MRT_TRY(dev_reserve(ctx, ctx->level_starts_dev, MAX_WIDE_LEVELS + 1));
         A.level_starts = ctx->level_starts_dev.p;
         void* args[] = {&A};
         MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_collapse_loop, dim3(grid), dim3(LOOP_THREADS), args, 0, ctx->stream));
         MRT_LAUNCHED(ctx);
-        uint32_t res[3] = {0, 0, 0};
+        uint32_t res[7] = {0, 0, 0, 0, 0, 0, 0};
         ctx->level_starts.assign(MAX_WIDE_LEVELS + 1, 0u);
         MRT_CUDA(ctx, cudaMemcpyAsync(res, ctx->counters.p, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
         MRT_CUDA(ctx, cudaMemcpyAsync(ctx->level_starts.data(), ctx->level_starts_dev.p, sizeof(uint32_t) * (MAX_WIDE_LEVELS + 1),
                                       cudaMemcpyDeviceToHost, ctx->stream));
         MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (A.ploc_result && res[5] != 0) return mrt_fail(ctx, MRT_ERR_INVALID, "PLOC made no progress (round %u)", res[6]);
+        if (A.ploc_result && res[4] != n - 1) return mrt_fail(ctx, MRT_ERR_INVALID, "PLOC produced %u internal nodes for %u primitives", res[4], n);
         if (res[1] != 0) return mrt_fail(ctx, MRT_ERR_INVALID, "wide BVH node budget exceeded");
         ctx->num_nodes = res[0];
         ctx->num_leaf_tris = n;
