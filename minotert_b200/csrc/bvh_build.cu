@@ -1448,7 +1448,10 @@ int bvh_build_full(mrt_context* ctx) {
     MRT_TRY(dev_reserve(ctx, ctx->node_ntri, (size_t)n + 1));
     MRT_TRY(dev_reserve(ctx, ctx->node_child_base, (size_t)n + 1));
     MRT_TRY(dev_reserve(ctx, ctx->node_tri_base, (size_t)n + 1));
-    MRT_TRY(dev_reserve(ctx, ctx->counters, 16));
+    if (ctx->counters.p == nullptr) {  // first use: not every word is written by every builder, all are read back
+        MRT_TRY(dev_reserve(ctx, ctx->counters, 16));
+        MRT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(uint32_t), ctx->stream));
+    }
 
     // 1-3: boxes, Morton keys, sort
     MRT_TRY(compute_boxes(ctx));
@@ -1490,7 +1493,10 @@ int bvh_build_full(mrt_context* ctx) {
         A.node_child_base = ctx->node_child_base.p; A.node_tri_base = ctx->node_tri_base.p;
         A.block_sums = reinterpret_cast<uint32_t*>(ctx->loop_sums.p); A.result = ctx->counters.p; A.n = n;
         A.ploc_result = (n > 1 && ctx->opt_builder == 1) ? ctx->counters.p + 4 : nullptr;
-        MRT_TRY(dev_reserve(ctx, ctx->level_starts_dev, MAX_WIDE_LEVELS + 1));
+        if (ctx->level_starts_dev.p == nullptr) {  // first use: the tail of the table beyond the tree's depth is copied to the host too
+            MRT_TRY(dev_reserve(ctx, ctx->level_starts_dev, MAX_WIDE_LEVELS + 1));
+            MRT_CUDA(ctx, cudaMemsetAsync(ctx->level_starts_dev.p, 0, sizeof(uint32_t) * (MAX_WIDE_LEVELS + 1), ctx->stream));
+        }
         A.level_starts = ctx->level_starts_dev.p;
         void* args[] = {&A};
         MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_collapse_loop, dim3(grid), dim3(LOOP_THREADS), args, 0, ctx->stream));

@@ -1,6 +1,12 @@
-python tools/check_option.py hall_260k 1921 1079 2 3 shade_tiles=0 2>&1 | tail -2
-CHECK_FLAGS=24 python tools/check_option.py hall_260k 1280 720 2 2 shade_tiles=0 2>&1 | tail -1
-for c in 1 0; do
-  tools/ab.sh hall_t$c --no-extra-configs --opt shade_tiles=$c; tools/ab.sh 1m_t$c --no-extra-configs --workload scene_1m_1080p --opt shade_tiles=$c
-  tools/ab.sh 10m_t$c --no-extra-configs --workload scene_10m_4k --steps 4 --opt shade_tiles=$c
-done
+out=gpurun_out/sanitizer_r2b.txt
+echo "compute-sanitizer $(compute-sanitizer --version | tail -1) on $(nvidia-smi -L | head -1)" > $out
+run() { echo "== $1" >> $out; shift; timeout 1200 "$@" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|hazard|Invalid|Uninit|error" | head -20 >> $out; }
+K1='(wide_refit or fused_sort or device_side) and (tiny or soup or small_terrain)'
+run memcheck_build compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "$K1"
+run racecheck_build compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "$K1"
+run initcheck_build compute-sanitizer --tool initcheck python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "$K1"
+run synccheck_build compute-sanitizer --tool synccheck python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "$K1"
+run memcheck_async compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "async_mesh_updates or frames_in_flight"
+run memcheck_denoise compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_denoise.py -m gpu -q -x
+run racecheck_denoise compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_denoise.py -m gpu -q -x -k "default_params"
+cat $out
