@@ -168,7 +168,7 @@ struct mrt_context {
     // bilateral denoiser (denoise.cu): RGBA8 output, tap list cached per (sigma, kSigma, image size)
     DevArray<uchar4> denoised;
     DevArray<float4> dn_taps;
-    int dn_ntaps = 0;
+    int dn_ntaps = 0, dn_ncols = 0;
     float dn_key_sigma = 0.0f, dn_key_ksigma = 0.0f;
     uint32_t dn_key_w = 0, dn_key_h = 0;
     bool have_denoised = false;

@@ -9,7 +9,7 @@
 // exp and 5 multiply-adds -- an issue-bound stencil (about 25 000 instructions per pixel), not a bandwidth-bound
 // one: the 18 B/px of input are read once per CTA tile into shared memory.
 //
-// Kernel: one thread per pixel, 32x8-pixel CTA (a warp = one image row of the tile), shared tile with a halo of
+// Kernel (the column descriptors of DN_COL_* below came after this text: DESIGN.md 5.7): one thread per pixel, 32x8-pixel CTA (a warp = one image row of the tile), shared tile with a halo of
 // radius+1 texels holding {r, g, b, depth} and {nx, ny, nz} as fp32 (converted ONCE per CTA when the tile is filled; two
 // conflict-free LDS.128 per texel); image-edge clamping is applied when the tile is filled, so the tap loop needs none.
 // Everything about a tap that does not depend on the pixel's column is evaluated once on the host, with the shader's own
@@ -50,9 +50,15 @@ struct DenoiseArgs {
     uint32_t frameCounter;
     int halo;   // radius + 1
     int ntaps;
+    int ncols;  // tap columns (2 radius + 1)
 };
 
 // record of one (image row, tap): .x = (tile offset of the upper texel relative to the pixel) * 16 | flags, .w = spatial Gaussian
+// descriptor of one (image row, tap column): .x = (tile offset of the column's first texel) * 16 | class, .y = taps in the column;
+// class DN_COL_LERP: .z / .w = the two row weights shared by all its taps; DN_COL_GENERIC: .z = index of its first tap record
+enum : int { DN_COL_GENERIC = 0,  // walk the per-tap records (rows whose rounding breaks the pattern)
+             DN_COL_LERP = 1,     // every tap interpolates rows r, r + 1 with the same weights, r stepping down by one
+             DN_COL_SINGLE = 2 }; // every tap is a single texel (d.y integral), rows stepping down by one
 enum : int { DN_LERP = 1,    // the tap interpolates rows (.y = weight of the lower row, .z = 1 - .y); else a single texel
              DN_REUSE = 2 }; // the upper texel is the previous tap's lower texel (still in registers)
 
@@ -72,6 +78,11 @@ MRT_D float ex2_approx(float x) {
 struct DnSums { float z, r, g, b; };
 struct DnConsts { float centreDist, cnx, cny, cnz, nearPlane, k1, k2; };
 
+MRT_D float lds1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 MRT_D float4 lds4(uint32_t addr) {  // 32-bit shared-memory address
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -111,16 +122,22 @@ MRT_D void dn_accumulate(DnSums& sum, const DnConsts& K, float blur, float r, fl
         }                                                                                                              \
     }
 
-// bilateral.comp:23-76
+// bilateral.comp:23-76.  BLUR_SMEM: the per-tap spatial Gaussian is staged in shared memory (always, except for the largest
+// radii, whose tile leaves no room for it).
+template <bool BLUR_SMEM>
 __global__ void __launch_bounds__(DN_BX* DN_BY)
     k_denoise_bilateral(DenoiseArgs A, const uint2* __restrict__ color16, const uint16_t* __restrict__ depth16,
-                        const uint2* __restrict__ normal16, const float4* __restrict__ recs, uchar4* __restrict__ out) {
+                        const uint2* __restrict__ normal16, const float4* __restrict__ recs, const float4* __restrict__ cols,
+                        const float* __restrict__ blur, uchar4* __restrict__ out) {
     extern __shared__ float4 tile[];
     const int TW = DN_BX + 2 * A.halo, TH = DN_BY + 2 * A.halo;
     float4* const tileC = tile;            // r, g, b, depth
     float4* const tileN = tile + TW * TH;  // nx, ny, nz, -
+    float* const sblur = reinterpret_cast<float*>(tile + 2 * TW * TH);  // the spatial Gaussian of every tap
     const int x0 = (int)blockIdx.x * DN_BX - A.halo, y0 = (int)blockIdx.y * DN_BY - A.halo;
     const int tid = threadIdx.y * DN_BX + threadIdx.x;
+    if (BLUR_SMEM)
+        for (int i = tid; i < A.ntaps; i += DN_BX * DN_BY) sblur[i] = __ldg(&blur[i]);
     for (int i = tid; i < TW * TH; i += DN_BX * DN_BY) {
         int ty = i / TW, tx = i - ty * TW;
         int gx = min(max(x0 + tx, 0), (int)A.W - 1), gy = min(max(y0 + ty, 0), (int)A.H - 1);  // ClampToEdge
@@ -154,19 +171,60 @@ __global__ void __launch_bounds__(DN_BX* DN_BY)
         const uint32_t centre_addr = (uint32_t)__cvta_generic_to_shared(tileC + centre_idx);
         const uint32_t normal_off = (uint32_t)(TW * TH) * 16u, row_bytes = (uint32_t)TW * 16u;
         const float4* rp = recs + (size_t)py * A.ntaps;
+        const float4* cp = cols + (size_t)py * A.ncols;
+        const uint32_t blur_base = (uint32_t)__cvta_generic_to_shared(sblur);
+        uint32_t blur_addr = blur_base;  // of the current column's first tap
+#define DN_BLUR(ba) (BLUR_SMEM ? lds1(ba) : __ldg(blur + (((ba) - blur_base) >> 2)))
         float4 Xc = cc, Xn = cn, Yc = cc, Yn = cn;
-        // the records of the next two taps are fetched while this pair is evaluated (one broadcast load per tap and warp)
-        const int last = A.ntaps - 1;
-        float4 r0 = __ldg(rp), r1 = __ldg(rp + min(1, last));
-        int i = 0;
+        float4 cd = __ldg(cp);
+        for (int col = 0; col < A.ncols; col++) {
+            const int code = __float_as_int(cd.x), n = __float_as_int(cd.y);
+            const float fy = cd.z, gy = cd.w;
+            const int first_rec = __float_as_int(cd.z);
+            if (col + 1 < A.ncols) cd = __ldg(cp + col + 1);  // the next column's descriptor travels while this one is summed
+            uint32_t at = centre_addr + (uint32_t)(code & ~3);
+            uint32_t ba = blur_addr;
+            blur_addr += 4u * (uint32_t)n;
+            const int cls = code & 3;
+            if (cls == DN_COL_LERP) {
+                // rows r, r + 1, ... : the lower texel of one tap is the upper texel of the next (X and Y swap roles)
+                Xc = lds4(at); Xn = lds4(at + normal_off);
+                int i = 0;
+#define DN_LERP_TAP(P, Q)                                                                                              \
+    {                                                                                                                  \
+        at += row_bytes;                                                                                               \
+        Q##c = lds4(at); Q##n = lds4(at + normal_off);                                                                 \
+        dn_accumulate(sum, K, DN_BLUR(ba), fmaf(Q##c.x, fy, P##c.x * gy), fmaf(Q##c.y, fy, P##c.y * gy),                  \
+                      fmaf(Q##c.z, fy, P##c.z * gy), fmaf(Q##c.w, fy, P##c.w * gy), fmaf(Q##n.x, fy, P##n.x * gy),     \
+                      fmaf(Q##n.y, fy, P##n.y * gy), fmaf(Q##n.z, fy, P##n.z * gy));                                   \
+        ba += 4u;                                                                                                      \
+    }
 #pragma unroll 2
-        for (; i + 1 < A.ntaps; i += 2) {
-            const float4 n0 = __ldg(rp + min(i + 2, last)), n1 = __ldg(rp + min(i + 3, last));
-            DN_TAP(X, Y, r0)
-            DN_TAP(Y, X, r1)
-            r0 = n0; r1 = n1;
+                for (; i + 1 < n; i += 2) {
+                    DN_LERP_TAP(X, Y)
+                    DN_LERP_TAP(Y, X)
+                }
+                if (i < n) DN_LERP_TAP(X, Y)
+#undef DN_LERP_TAP
+            } else if (cls == DN_COL_SINGLE) {
+#pragma unroll 2
+                for (int i = 0; i < n; i++) {
+                    const float4 tc = lds4(at), tn = lds4(at + normal_off);
+                    dn_accumulate(sum, K, DN_BLUR(ba), tc.x, tc.y, tc.z, tc.w, tn.x, tn.y, tn.z);
+                    at += row_bytes;
+                    ba += 4u;
+                }
+            } else {
+                // per-tap records: the sampler's row / weight of this image row do not follow the column's pattern
+                const float4* r = rp + first_rec;
+                int i = 0;
+                for (; i + 1 < n; i += 2) {
+                    DN_TAP(X, Y, __ldg(r + i))
+                    DN_TAP(Y, X, __ldg(r + i + 1))
+                }
+                if (i < n) DN_TAP(X, Y, __ldg(r + i))
+            }
         }
-        if (i < A.ntaps) DN_TAP(X, Y, r0)
         filtered = f3(sum.r / sum.z, sum.g / sum.z, sum.b / sum.z);
     }
     // bilateral.comp:71-73: one PCG draw per pixel, the same value on r, g and b
@@ -181,8 +239,10 @@ __global__ void __launch_bounds__(DN_BX* DN_BY)
 
 // The loops of smartDeNoise (bilateral.comp:43-47) in the shader's own fp32 arithmetic, once per image row: which taps
 // exist, the spatial Gaussian, and where the sampler reads -- all of it depends only on (sigma, kSigma, image height, row).
-// recs[row * ntaps + tap]; returns ntaps.
-static int build_tap_records(float sigma, float kSigma, uint32_t H, int tileW, std::vector<float4>& recs) {
+// recs[row * ntaps + tap]: one record per tap; cols[row * ncols + column]: one descriptor per tap column (the taps of one
+// d.x); blur[tap].  Returns ntaps.
+static int build_tap_records(float sigma, float kSigma, uint32_t H, int tileW, std::vector<float4>& recs, std::vector<float4>& cols,
+                             std::vector<float>& blur, int* ncols_out) {
     const float INV_PI = 0.31830988618379067153776752674503f;
     const float radius = roundf(kSigma * sigma);
     const float radQ = radius * radius;
@@ -191,13 +251,21 @@ static int build_tap_records(float sigma, float kSigma, uint32_t H, int tileW, s
     const float sizeY = (float)H;
     struct Tap { float dx, dy, blur; bool whole; };
     std::vector<Tap> taps;
+    std::vector<int> col_first;  // first tap of each column, then ntaps
     for (float dx = -radius; dx <= radius; dx++) {
         const float pt = sqrtf(radQ - dx * dx);
+        col_first.push_back((int)taps.size());
         for (float dy = -pt; dy <= pt; dy++)
             taps.push_back(Tap{dx, dy, expf(-(dx * dx + dy * dy) * invSigmaQx2) * invSigmaQx2PI, dy == rintf(dy)});
     }
-    const int ntaps = (int)taps.size();
+    const int ntaps = (int)taps.size(), ncols = (int)col_first.size();
+    col_first.push_back(ntaps);
+    blur.resize(ntaps);
+    for (int k = 0; k < ntaps; k++) blur[k] = taps[k].blur;
     recs.resize((size_t)H * ntaps);
+    cols.resize((size_t)H * ncols);
+    std::vector<int> offs(ntaps);
+    std::vector<float> fys(ntaps);
     for (uint32_t py = 0; py < H; py++) {
         const float uvy = ((float)py + 0.5f) / sizeY;
         bool prev_lerp = false;
@@ -220,6 +288,8 @@ static int build_tap_records(float sigma, float kSigma, uint32_t H, int tileW, s
                 if (1.0f - fy == 0.0f) { row += 1; fy = 0.0f; }  // weight 256/256: the lower texel alone
             }
             const int off = row * tileW + (int)t.dx;
+            offs[k] = off;
+            fys[k] = fy;
             int flags = 0;
             if (fy != 0.0f) flags |= DN_LERP;
             if (prev_lerp && prev_lower == off) flags |= DN_REUSE;
@@ -233,7 +303,28 @@ static int build_tap_records(float sigma, float kSigma, uint32_t H, int tileW, s
             r.w = t.blur;
             recs[(size_t)py * ntaps + k] = r;
         }
+        // Column descriptors.  In exact arithmetic the taps of a column share the fractional part of d.y and step down one
+        // row at a time; the sampler's fp32 evaluation agrees with that on all but a handful of (row, column) pairs, which
+        // fall back to the per-tap records.
+        for (int c = 0; c < ncols; c++) {
+            const int k0 = col_first[c], n = col_first[c + 1] - k0;
+            bool steps = true, lerp = fys[k0] != 0.0f, same = true;
+            for (int k = k0 + 1; k < k0 + n; k++) {
+                steps = steps && offs[k] == offs[k - 1] + tileW;
+                same = same && fys[k] == fys[k0];
+            }
+            int cls = DN_COL_GENERIC;
+            if (steps && same) cls = lerp ? DN_COL_LERP : DN_COL_SINGLE;
+            const int code = cls == DN_COL_GENERIC ? 0 : offs[k0] * 16 + cls;
+            float4 d;
+            memcpy(&d.x, &code, 4);
+            memcpy(&d.y, &n, 4);
+            if (cls == DN_COL_GENERIC) { memcpy(&d.z, &k0, 4); d.w = 0.0f; }
+            else { d.z = fys[k0]; d.w = 1.0f - fys[k0]; }
+            cols[(size_t)py * ncols + c] = d;
+        }
     }
+    *ncols_out = ncols;
     return ntaps;
 }
 
@@ -250,12 +341,19 @@ int denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float thresho
     if (n == 0) return MRT_OK;
 
     if (ctx->dn_key_sigma != sigma || ctx->dn_key_ksigma != kSigma || ctx->dn_key_w != W || ctx->dn_key_h != H) {
-        std::vector<float4> recs;
-        const int ntaps = build_tap_records(sigma, kSigma, H, DN_BX + 2 * ((int)radius + 1), recs);
-        MRT_TRY(dev_reserve(ctx, ctx->dn_taps, recs.size()));
-        // pageable source: the copy is staged before the call returns
+        std::vector<float4> recs, cols;
+        std::vector<float> blur;
+        int ncols = 0;
+        const int ntaps = build_tap_records(sigma, kSigma, H, DN_BX + 2 * ((int)radius + 1), recs, cols, blur, &ncols);
+        // one allocation: [records | column descriptors | blur]
+        const size_t total = recs.size() + cols.size() + (blur.size() + 3) / 4;
+        MRT_TRY(dev_reserve(ctx, ctx->dn_taps, total));
+        // pageable sources: the copies are staged before the calls return
         MRT_CUDA(ctx, cudaMemcpyAsync(ctx->dn_taps.p, recs.data(), recs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        MRT_CUDA(ctx, cudaMemcpyAsync(ctx->dn_taps.p + recs.size(), cols.data(), cols.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        MRT_CUDA(ctx, cudaMemcpyAsync(ctx->dn_taps.p + recs.size() + cols.size(), blur.data(), blur.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->dn_ncols = ncols;
         ctx->dn_ntaps = ntaps;
         ctx->dn_key_sigma = sigma; ctx->dn_key_ksigma = kSigma; ctx->dn_key_w = W; ctx->dn_key_h = H;
     }
@@ -268,13 +366,18 @@ int denoise_bilateral(mrt_context* ctx, float sigma, float kSigma, float thresho
     A.frameCounter = frameCounter;
     A.halo = (int)radius + 1;
     A.ntaps = ctx->dn_ntaps;
-    const size_t smem = (size_t)(DN_BX + 2 * A.halo) * (DN_BY + 2 * A.halo) * 2 * sizeof(float4);
-    if (smem > 48 * 1024)
-        MRT_CUDA(ctx, cudaFuncSetAttribute(k_denoise_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    A.ncols = ctx->dn_ncols;
+    const float4* const recs = ctx->dn_taps.p;
+    const float4* const cols = recs + (size_t)H * A.ntaps;
+    const float* const blur = reinterpret_cast<const float*>(cols + (size_t)H * A.ncols);
+    const size_t tile_bytes = (size_t)(DN_BX + 2 * A.halo) * (DN_BY + 2 * A.halo) * 2 * sizeof(float4);
+    const bool blur_smem = tile_bytes + (size_t)A.ntaps * sizeof(float) <= 227u * 1024u;
+    const size_t smem = tile_bytes + (blur_smem ? (size_t)A.ntaps * sizeof(float) : 0u);
+    auto* const kernel = blur_smem ? k_denoise_bilateral<true> : k_denoise_bilateral<false>;
+    if (smem > 48 * 1024) MRT_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(div_up(W, DN_BX), div_up(H, DN_BY)), block(DN_BX, DN_BY);
-    k_denoise_bilateral<<<grid, block, smem, ctx->stream>>>(A, reinterpret_cast<const uint2*>(ctx->color16.p), ctx->depth.p,
-                                                            reinterpret_cast<const uint2*>(ctx->normal.p), ctx->dn_taps.p,
-                                                            ctx->denoised.p);
+    kernel<<<grid, block, smem, ctx->stream>>>(A, reinterpret_cast<const uint2*>(ctx->color16.p), ctx->depth.p,
+                                               reinterpret_cast<const uint2*>(ctx->normal.p), recs, cols, blur, ctx->denoised.p);
     MRT_LAUNCHED(ctx);
     return mrt_check_cuda(ctx, cudaGetLastError(), "denoise_bilateral");
 }

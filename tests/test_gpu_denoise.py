@@ -65,6 +65,7 @@ def test_reference_scene_default_params(gpu_ctx, oracle, sky_inputs, blue_noise)
 @pytest.mark.parametrize("size,params", [((67, 35), (5.0, 2.0, 0.12)),      # ragged, smaller than one CTA tile row
                                           ((200, 113), (3.3, 1.7, 0.3)),     # radius round(5.61) = 6
                                           ((97, 61), (10.0, 3.0, 0.1)),      # radius 30: 2 821 taps, > 48 KB of shared memory
+                                          ((70, 40), (16.0, 2.0, 0.2)),      # radius 32, the largest: the tile leaves no room for the tap weights
                                           ((33, 9), (1.0, 1.0, 1.0)),        # radius 1
                                           ((64, 64), (1.0, 0.4, 0.5))])      # radius 0: a single tap
 def test_sizes_and_parameters(gpu_ctx, oracle, sky_inputs, blue_noise, size, params):
