@@ -9,21 +9,24 @@
 // exp and 5 multiply-adds -- an issue-bound stencil (about 25 000 instructions per pixel), not a bandwidth-bound
 // one: the 18 B/px of input are read once per CTA tile into shared memory.
 //
-// Kernel (the column descriptors of DN_COL_* below came after this text: DESIGN.md 5.7): one thread per pixel, 32x8-pixel CTA (a warp = one image row of the tile), shared tile with a halo of
+// Kernel: one thread per pixel, 32x8-pixel CTA (a warp = one image row of the tile), shared tile with a halo of
 // radius+1 texels holding {r, g, b, depth} and {nx, ny, nz} as fp32 (converted ONCE per CTA when the tile is filled; two
 // conflict-free LDS.128 per texel); image-edge clamping is applied when the tile is filled, so the tap loop needs none.
 // Everything about a tap that does not depend on the pixel's column is evaluated once on the host, with the shader's own
-// fp32 operations, into a table of one 16-byte record per (image row, tap): which taps exist, the spatial Gaussian, and --
-// the part the first version of this kernel recomputed per pixel and per tap, a third of its instructions -- the row the
-// LinearClamp sampler reads and its k/256 weight.  The records of a row are the same for all its pixels: a warp reads them
-// with one broadcast load per tap.  Taps are visited in the shader's order (same sums, bit for bit, as that first version).
+// fp32 operations: which taps exist, the spatial Gaussian, and -- the part the first version of this kernel recomputed per
+// pixel and per tap, a third of its instructions -- the row the LinearClamp sampler reads and its k/256 weight.  The taps
+// of one d.x (a "column") share the fractional part of d.y and step down one row at a time; the sampler's fp32
+// evaluation agrees with that on all but a handful of (image row, column) pairs.  So the table holds one 16-byte descriptor
+// per (image row, column) -- first texel, tap count, the two row weights, a class (DN_COL_*) -- which a warp reads with one
+// broadcast load per column, plus one 16-byte record per (image row, tap) for the columns whose pattern breaks on that
+// row.  Taps are visited in the shader's order (same sums, bit for bit, as the first version).
 // Sampler rule (the oracle's, oracle/minote_oracle.c:texn_bilinear): bilinear weights carry 8 fractional bits and
 // zero-weight texels are not read.  d.x is integral, so in x every tap is the texel centre px + d.x (the fp32
 // residue of uv + d/size is < 2^-10 texel for images up to 4096 wide and rounds to weight 0): one column, no
 // x-lerp.  In y the tap reads rows floor(y) and floor(y) + 1 with weights (1 - k/256, k/256); k = 0 and k = 256 (and every
 // tap whose d.y is integral) are single texels.  Consecutive taps of a column step down one row, so the lower texel of
-// one tap is the upper texel of the next: the table flags that, and the loop keeps the texel in registers (two register
-// sets that swap roles every tap) -- one shared-memory texel per tap instead of two.
+// one tap is the upper texel of the next: the loop keeps the texel in registers (two register sets that swap roles every
+// tap) -- one shared-memory texel per tap instead of two.
 // Deliberate deviations, all at the 1e-6 relative level and absorbed by the bar in
 // tests/test_gpu_denoise.py (RGBA8: <= 1 code value on >= 99.9 % of pixels; measured: 8e-6 of the pixels differ,
 // by 1): exp and the depth division run on the SFU (ex2.approx, rcp.approx), as GLSL exp() and '/' do on the
