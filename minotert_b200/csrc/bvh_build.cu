@@ -503,6 +503,95 @@ MRT_D uint2 ploc_round(const PlocLoop& A, uint32_t m, int cur, uint32_t next_nod
     return total;
 }
 
+// A round in which every CTA's range of positions, with a halo of 2 radius on either side, fits one window of
+// LOOP_THREADS positions (<= ~130 k clusters): the window's ids, boxes and counts are read once into shared memory;
+// nearest neighbours are computed for the range plus a halo of one radius, so that the mutual-pair test of the range
+// needs no other CTA's result -- one grid barrier (and four dependent trips to L2) less than ploc_round; the merges
+// take their boxes and counts from shared memory.  Same pairs, ids and boxes as ploc_round (ids come from a scan over
+// positions, whatever the chunking).
+#ifndef PLOC_FUSED_ROUNDS
+#define PLOC_FUSED_ROUNDS 1
+#endif
+template <class Sync>
+MRT_D uint2 ploc_round_fused(const PlocLoop& A, uint32_t m, int cur, uint32_t next_node, uint32_t b, uint32_t nb, float4* wlo,
+                              float4* whi, uint32_t* wid, uint32_t* wcnt, uint32_t* wnn, Sync sync) {
+    const uint32_t* C = A.clusters[cur];
+    uint32_t* Cout = A.clusters[cur ^ 1];
+    const int radius = ploc_radius_for(A.radius, m);
+    const uint32_t chunk = (m + nb - 1) / nb;  // the caller checked chunk + 4 radius <= LOOP_THREADS
+    const uint32_t r0 = min(m, b * chunk), r1 = min(m, r0 + chunk);
+    const int w0 = (int)r0 - 2 * radius;       // window = positions [w0, w0 + LOOP_THREADS)
+    const int q = (int)threadIdx.x, pos = w0 + q;
+    const int nprims = (int)A.n;
+    if (pos >= 0 && pos < (int)min(m, r1 + 2u * (uint32_t)radius)) {
+        const uint32_t c = C[pos];
+        wid[q] = c;
+        wlo[q] = A.lo[c];
+        whi[q] = A.hi[c];
+        wcnt[q] = (int)c >= nprims - 1 ? 1u : A.count[c];
+    }
+    __syncthreads();
+    if (pos >= max(0, (int)r0 - radius) && pos < (int)min(m, r1 + (uint32_t)radius)) {
+        const int i = pos;
+        const float4 ilo = wlo[q], ihi = whi[q];
+        const int j0 = max(i - radius, 0), j1 = min(i + radius, (int)m - 1);
+        float best = 3.0e38f;
+        uint32_t bj = (uint32_t)i, bkey = 0xFFFFFFFFu;
+        for (int j = j0; j <= j1; j++) {  // same pair order and tie-break as ploc_round
+            if (j == i) continue;
+            const float a = merged_area(ilo, ihi, wlo[j - w0], whi[j - w0]);
+            const uint32_t dist = (uint32_t)abs(j - i);
+            const uint32_t lowpos = (uint32_t)min(j, i);
+            const uint32_t key = (dist << 26) | ((lowpos & 1u) << 25) | (lowpos & 0x1FFFFFFu);
+            if (a < best || (a == best && key < bkey)) { best = a; bj = (uint32_t)j; bkey = key; }
+        }
+        wnn[q] = bj;
+    }
+    __syncthreads();
+    bool keep = false, create = false;
+    uint32_t j = 0;
+    if (pos >= (int)r0 && pos < (int)r1) {
+        const uint32_t i = (uint32_t)pos;
+        j = wnn[q];
+        const bool mutual = j != i && wnn[(int)j - w0] == i;
+        keep = !(mutual && i > j);
+        create = mutual && i < j;
+    }
+    const uint2 mine = cta_sum2(keep ? 1u : 0u, create ? 1u : 0u);
+    if (threadIdx.x == 0) A.block_sums[b] = mine;
+    sync();
+    uint32_t kb = 0, cb = 0, kt = 0, ct = 0;
+    for (uint32_t k = threadIdx.x; k < nb; k += LOOP_THREADS) {
+        const uint2 sq = A.block_sums[k];
+        kt += sq.x; ct += sq.y;
+        if (k < b) { kb += sq.x; cb += sq.y; }
+    }
+    const uint2 before = cta_sum2(kb, cb), total = cta_sum2(kt, ct);
+    uint32_t tile_total;
+    const uint32_t ex = cta_scan((keep ? 1u : 0u) | (create ? 0x10000u : 0u), &tile_total);
+    if (keep) {
+        uint32_t c = wid[q];
+        if (create) {
+            const int qj = (int)j - w0;
+            const uint32_t cj = wid[qj];
+            const uint32_t id = next_node + before.y + (ex >> 16);
+            const float4 alo = wlo[q], ahi = whi[q], blo = wlo[qj], bhi = whi[qj];
+            A.left[id] = (int32_t)c;
+            A.right[id] = (int32_t)cj;
+            A.parent[c] = (int32_t)id;
+            A.parent[cj] = (int32_t)id;
+            A.parent[id] = -1;
+            A.count[id] = wcnt[q] + wcnt[qj];
+            A.lo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+            A.hi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+            c = id;
+        }
+        Cout[before.x + (ex & 0xFFFFu)] = c;
+    }
+    sync();
+    return total;
+}
+
 // The last rounds (<= LOOP_THREADS clusters, CTA 0 alone) with the cluster list in SHARED memory: ids, boxes and primitive
 // counts are loaded once, a round is a neighbour search, a mutual-pair test and an in-place compaction between CTA
 // barriers, and the only global traffic left is the record of each new node going out (nothing waits for it).  The
@@ -603,7 +692,13 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_ploc_loop(PlocLoop A) {
     PROF_DECL
     while (m > (uint32_t)PLOC_TAIL) {
         PROF("ploc grid round/m", rounds, m);
+#if PLOC_FUSED_ROUNDS && PLOC_SMEM_TAIL
+        const bool fused = (m + nb - 1) / nb + 4u * (uint32_t)ploc_radius_for(A.radius, m) <= (uint32_t)LOOP_THREADS;
+        const uint2 t = fused ? ploc_round_fused(A, m, cur, next_node, b, nb, wlo, whi, tail_cid, tail_cnt, tail_nn, [&] { grid.sync(); })
+                              : ploc_round(A, m, cur, next_node, b, nb, wlo, whi, [&] { grid.sync(); });
+#else
         const uint2 t = ploc_round(A, m, cur, next_node, b, nb, wlo, whi, [&] { grid.sync(); });
+#endif
         rounds++;
         if (t.y == 0 || t.x >= m) { status = 1; break; }  // every CTA sees the same totals
         next_node += t.y;
