@@ -154,6 +154,7 @@ void mrt_destroy(mrt_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->upload_stream) { cudaStreamSynchronize(ctx->upload_stream); cudaStreamDestroy(ctx->upload_stream); }
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->build_results_host) cudaFreeHost(ctx->build_results_host);
     if (ctx->ev_pos_ready) cudaEventDestroy(ctx->ev_pos_ready);
     if (ctx->ev_refit_done) cudaEventDestroy(ctx->ev_refit_done);
     if (ctx->ev_frames_done) cudaEventDestroy(ctx->ev_frames_done);
@@ -169,7 +170,7 @@ void mrt_destroy(mrt_context* ctx) {
     dev_free(ctx->bin_lo); dev_free(ctx->bin_hi); dev_free(ctx->bin_flag);
     dev_free(ctx->scene_bounds); dev_free(ctx->work_a); dev_free(ctx->work_b); dev_free(ctx->slot_node);
     dev_free(ctx->node_nchild); dev_free(ctx->node_ntri); dev_free(ctx->node_child_base); dev_free(ctx->node_tri_base);
-    dev_free(ctx->node_lo); dev_free(ctx->node_hi); dev_free(ctx->level_starts_dev);
+    dev_free(ctx->node_lo); dev_free(ctx->node_hi); dev_free(ctx->level_starts_dev); dev_free(ctx->bin_rec);
     if (!ctx->scene_borrowed) { dev_free(ctx->nodes_alt); dev_free(ctx->tris_alt); }
     dev_free(ctx->nodes); dev_free(ctx->tris); dev_free(ctx->counters); dev_free(ctx->loop_sums);
     dev_free(ctx->trans16); dev_free(ctx->multi16); dev_free(ctx->view_packed);

@@ -843,19 +843,16 @@ MRT_D void collapse_expand_one(const BinTree& T, int b, uint32_t w, int32_t* slo
 // reproduces the serial scan order -- largest area / cost first, ties to the lowest slot, then the lowest child --
 // so both versions build the same node bit for bit (tested through build_device_loop 0 vs 1).
 // All 32 lanes of the warp call this together; groups without a node pass active = false.
-MRT_D void collapse_expand_group(const BinTree& T, bool active, int b, uint32_t w, int32_t* slot_node, uint32_t* node_nchild,
-                                 uint32_t* node_ntri) {
+// rec (k_collapse_loop only): one 16-byte record per internal binary node -- (left | big << 31, right | big << 31, area of left,
+// area of right), big = more than MRT_MAX_LEAF_TRIS primitives below -- so that opening a slot is ONE dependent load
+// instead of the child index followed by its count and box (the expansion is a chain of such loads, ~17 round trips
+// to L2 per node without the records, ~10 with them).  Same decisions: the areas are bin_area's own values.
+MRT_D void collapse_expand_group(const BinTree& T, const uint4* rec, bool active, int b, uint32_t w, int32_t* slot_node,
+                                 uint32_t* node_nchild, uint32_t* node_ntri) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int s = threadIdx.x & 7;
     int slot = -1;      // binary node in slot s
     int ns = 1;
-    if (bin_is_leaf(T, b)) {
-        if (s == 0) slot = b;
-    } else {
-        if (s == 0) slot = T.left[b];
-        if (s == 1) slot = T.right[b];
-        ns = 2;
-    }
     // cached per lane: can this slot be opened, is it "big", its area
     bool inner = false, big = false;
     float area = 0.0f;
@@ -864,7 +861,27 @@ MRT_D void collapse_expand_group(const BinTree& T, bool active, int b, uint32_t 
         big = inner && T.count[slot] > MRT_MAX_LEAF_TRIS;
         area = inner ? bin_area(T, slot) : 0.0f;
     };
-    refresh();
+    auto take = [&](const uint4& r, bool right) {  // this lane's slot becomes a child of the record's node
+        const uint32_t v = right ? r.y : r.x;
+        slot = (int)(v & 0x7FFFFFFFu);
+        inner = !bin_is_leaf(T, slot);
+        big = inner && (v >> 31) != 0u;
+        area = inner ? __uint_as_float(right ? r.w : r.z) : 0.0f;
+    };
+    if (bin_is_leaf(T, b)) {
+        if (s == 0) slot = b;
+        refresh();
+    } else if (rec) {
+        const uint4 r = rec[b];
+        if (s == 0) take(r, false);
+        if (s == 1) take(r, true);
+        ns = 2;
+    } else {
+        if (s == 0) slot = T.left[b];
+        if (s == 1) slot = T.right[b];
+        ns = 2;
+        refresh();
+    }
     // phase 0: open the largest subtree that is too big to be a leaf; phase 1: spend spare slots on small leaves
 #pragma unroll 1
     for (int phase = 0; phase < 2; phase++) {
@@ -884,8 +901,12 @@ MRT_D void collapse_expand_group(const BinTree& T, bool active, int b, uint32_t 
             // the chosen slot takes its left child, slot ns its right child
             const int chosen = __shfl_sync(FULL, slot, who, 8);
             if (open) {
-                if (s == who) { slot = T.left[chosen]; refresh(); }
-                else if (s == ns) { slot = T.right[chosen]; refresh(); }
+                if (rec) {
+                    if (s == who || s == ns) take(rec[chosen], s != who);
+                } else {
+                    if (s == who) { slot = T.left[chosen]; refresh(); }
+                    else if (s == ns) { slot = T.right[chosen]; refresh(); }
+                }
                 ns++;
             }
         }
@@ -991,6 +1012,7 @@ struct CollapseLoop {
     uint32_t* result;         // [0] wide nodes, [1] status (0 ok, 1 node budget exceeded), [2] levels
     uint32_t* level_starts;   // [MAX_WIDE_LEVELS + 1]: first node of each level, then the node count
     const uint32_t* ploc_result;  // k_ploc_loop's result words when it built the hierarchy just before (else null)
+    uint4* rec;                   // [n - 1] child records of the internal binary nodes (collapse_expand_group), filled here
     uint32_t n;               // primitives = node budget
 };
 #define MAX_WIDE_LEVELS 1023u
@@ -1038,6 +1060,13 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop 
     if (gtid == 0) A.items[0][0] = make_uint2((uint32_t)A.T.root, 0u);
     // the host has not looked at k_ploc_loop's result yet: an incomplete hierarchy is not walked (status 2, every thread alike)
     if (A.ploc_result && A.n > 1 && (A.ploc_result[1] != 0u || A.ploc_result[0] != A.n - 1u)) { status = 2; level_count = 0; }
+    if (status == 0 && A.rec) {
+        for (uint32_t i = gtid; i + 1 < A.n; i += gsize) {
+            const int l = A.T.left[i], r = A.T.right[i];
+            const uint32_t bl = bin_count(A.T, l) > MRT_MAX_LEAF_TRIS ? 0x80000000u : 0u, br = bin_count(A.T, r) > MRT_MAX_LEAF_TRIS ? 0x80000000u : 0u;
+            A.rec[i] = make_uint4((uint32_t)l | bl, (uint32_t)r | br, __float_as_uint(bin_area(A.T, l)), __float_as_uint(bin_area(A.T, r)));
+        }
+    }
     grid.sync();
     while (level_count > 0) {
         if ((size_t)level_start + level_count > A.n) { status = 1; break; }
@@ -1048,7 +1077,7 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop 
             const uint32_t k = k0 + ((threadIdx.x & 31) >> 3);
             const bool active = k < level_count;
             const uint2 item = active ? items[k] : make_uint2((uint32_t)A.T.root, 0u);
-            collapse_expand_group(A.T, active, (int)item.x, item.y, A.slot_node, A.node_nchild, A.node_ntri);
+            collapse_expand_group(A.T, A.rec, active, (int)item.x, item.y, A.slot_node, A.node_nchild, A.node_ntri);
         }
         PROF("collapse expand(cta0) level/count", levels, level_count);
         grid.sync();
@@ -1588,6 +1617,8 @@ int bvh_build_full(mrt_context* ctx) {
         A.node_child_base = ctx->node_child_base.p; A.node_tri_base = ctx->node_tri_base.p;
         A.block_sums = reinterpret_cast<uint32_t*>(ctx->loop_sums.p); A.result = ctx->counters.p; A.n = n;
         A.ploc_result = (n > 1 && ctx->opt_builder == 1) ? ctx->counters.p + 4 : nullptr;
+        MRT_TRY(dev_reserve(ctx, ctx->bin_rec, n));
+        A.rec = ctx->bin_rec.p;
         if (ctx->level_starts_dev.p == nullptr) {  // first use: the tail of the table beyond the tree's depth is copied to the host too
             MRT_TRY(dev_reserve(ctx, ctx->level_starts_dev, MAX_WIDE_LEVELS + 1));
             MRT_CUDA(ctx, cudaMemsetAsync(ctx->level_starts_dev.p, 0, sizeof(uint32_t) * (MAX_WIDE_LEVELS + 1), ctx->stream));
@@ -1596,12 +1627,13 @@ int bvh_build_full(mrt_context* ctx) {
         void* args[] = {&A};
         MRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_collapse_loop, dim3(grid), dim3(LOOP_THREADS), args, 0, ctx->stream));
         MRT_LAUNCHED(ctx);
-        uint32_t res[7] = {0, 0, 0, 0, 0, 0, 0};
-        ctx->level_starts.assign(MAX_WIDE_LEVELS + 1, 0u);
-        MRT_CUDA(ctx, cudaMemcpyAsync(res, ctx->counters.p, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
-        MRT_CUDA(ctx, cudaMemcpyAsync(ctx->level_starts.data(), ctx->level_starts_dev.p, sizeof(uint32_t) * (MAX_WIDE_LEVELS + 1),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
+        // results and level table land in page-locked memory: a pageable destination is staged by the driver (~15 us more)
+        if (!ctx->build_results_host) MRT_CUDA(ctx, cudaHostAlloc(&ctx->build_results_host, sizeof(uint32_t) * (8 + MAX_WIDE_LEVELS + 1), cudaHostAllocDefault));
+        uint32_t* const res = ctx->build_results_host;
+        MRT_CUDA(ctx, cudaMemcpyAsync(res, ctx->counters.p, sizeof(uint32_t) * 7, cudaMemcpyDeviceToHost, ctx->stream));
+        MRT_CUDA(ctx, cudaMemcpyAsync(res + 8, ctx->level_starts_dev.p, sizeof(uint32_t) * (MAX_WIDE_LEVELS + 1), cudaMemcpyDeviceToHost, ctx->stream));
         MRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->level_starts.assign(res + 8, res + 8 + MAX_WIDE_LEVELS + 1);
         if (A.ploc_result && res[5] != 0) return mrt_fail(ctx, MRT_ERR_INVALID, "PLOC made no progress (round %u)", res[6]);
         if (A.ploc_result && res[4] != n - 1) return mrt_fail(ctx, MRT_ERR_INVALID, "PLOC produced %u internal nodes for %u primitives", res[4], n);
         if (res[1] != 0) return mrt_fail(ctx, MRT_ERR_INVALID, "wide BVH node budget exceeded");

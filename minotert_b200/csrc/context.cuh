@@ -117,6 +117,7 @@ struct mrt_context {
     DevArray<uint32_t> ploc_c[2], ploc_nn, ploc_flag[2], ploc_scan[2];  // PLOC cluster lists and scratch
     DevArray<float4> bin_lo, bin_hi;                      // boxes of all 2N-1 binary nodes
     DevArray<uint32_t> bin_flag;
+    DevArray<uint4> bin_rec;                              // child records of the internal binary nodes (k_collapse_loop)
     DevArray<uint32_t> scene_bounds;                      // 6 ordered-int floats
     DevArray<uint2> work_a, work_b;                       // collapse work items (binary node, wide node)
     DevArray<int32_t> slot_node;                          // [num_nodes][8] binary node behind each slot
@@ -132,6 +133,7 @@ struct mrt_context {
     bool alt_valid = false;                               // nodes_alt / tris_alt hold the current topology
     DevArray<float4> node_lo, node_hi;                    // boxes of the wide nodes (scratch of the level-wise emission / refit)
     DevArray<uint32_t> level_starts_dev;                  // first wide node of each level (+ the node count), written by k_collapse_loop
+    uint32_t* build_results_host = nullptr;               // page-locked landing area of the build's result words + level table
     std::vector<uint32_t> level_starts;                   // host copy: level L = nodes [level_starts[L], level_starts[L + 1])
     DevArray<uint2> loop_sums;                            // per-CTA counts of the device-side build loops
     DevArray<uint32_t> counters;                          // misc device counters
