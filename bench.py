@@ -693,7 +693,7 @@ def measure_animated():
     end to end through Renderer::updateMesh + draw (tools/bench_animated.py).  3 frames in flight, option async_update."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import bench_animated
-    d = bench_animated.run_animated(frames=120, rebuild_every=10, frames_in_flight=3, async_update=1)
+    d = bench_animated.run_animated(frames=200, rebuild_every=10, frames_in_flight=3, async_update=1)
     return {"workload": "animated_1m_1080p", "value": d["Mrays_per_s_e2e"], "ms_per_step": d["ms_per_frame"], "steps": d["frames"],
             "config": {"workload": d["workload"], "mode": d["mode"], "rebuild_every": d["rebuild_every"], "fps": d["fps"]},
             "e2e": {"value": d["Mrays_per_s_e2e"], "unit": METRIC, "h2d_bytes_per_step": d["h2d_bytes_per_frame"],

@@ -18,22 +18,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run_animated(frames=120, rebuild_every=10, frames_in_flight=3, async_update=1, scene="scene_1m", spp=1, bounces=1):
+def run_animated(frames=200, rebuild_every=10, frames_in_flight=3, async_update=1, scene="scene_1m", spp=1, bounces=1):
     """The measurement as a function (bench.py's `configs` entry animated_1m_1080p): returns the JSON line as a dict."""
     args = argparse.Namespace(frames=frames, rebuild_every=rebuild_every, frames_in_flight=frames_in_flight,
-                              async_update=async_update, scene=scene, spp=spp, bounces=bounces)
+                              async_update=async_update, scene=scene, spp=spp, bounces=bounces, opt=[])
     return measure(args)
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=40)
+    ap.add_argument("--frames", type=int, default=200, help="the camera flies on: compare runs of the SAME length only")
     ap.add_argument("--rebuild-every", type=int, default=10)
     ap.add_argument("--scene", default="scene_1m")
     ap.add_argument("--spp", type=int, default=1)
     ap.add_argument("--bounces", type=int, default=1)
     ap.add_argument("--frames-in-flight", type=int, default=1, help="> 1 or --async-update: pipelined loop (async readbacks)")
     ap.add_argument("--async-update", type=int, default=0, help="mrt_set_option async_update: upload + refit without host stalls")
+    ap.add_argument("--opt", action="append", default=[], help="name=value for mrt_set_option (A/B of build paths), repeatable")
     args = ap.parse_args()
     print(json.dumps(measure(args)))
 
@@ -48,6 +49,9 @@ def measure(args):
     pos, idx, alb, view = getattr(scenes, args.scene)()
     bn = np.ascontiguousarray(np.array(Image.open(os.path.join(ROOT, "assets", "blue_noise.png")).convert("RGBA"), np.uint8))
     r = host.Renderer(w, h, bn, frames_in_flight=args.frames_in_flight)
+    for o in getattr(args, "opt", []) or []:  # before the build: some of these invalidate the BVH
+        name, value = o.split("=")
+        r.set_option(name, int(value))
     r.set_mesh(pos, idx, alb)
     r.configure(samples=args.spp, bounces=args.bounces)
     r.set_option("async_update", args.async_update)
@@ -110,8 +114,9 @@ def pipelined(args, r, cam, frames, idx, w, h):
     from minotert_b200 import host
     K = args.frames_in_flight
     fbs = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(K)]
-    for warm in range(2 * K):
-        r.update_mesh(frames[warm % len(frames)], refit=True)
+    nwarm = 2 * K + max(0, args.rebuild_every)  # includes one rebuild: the second copy of the tree is allocated on first use
+    for warm in range(nwarm):
+        r.update_mesh(frames[warm % len(frames)], refit=not (args.rebuild_every > 0 and warm == nwarm - K - 1))
         r.draw(cam)
         r.read_framebuffer_async(C.c_void_p(fbs[warm % K].data_ptr()), fbs[warm % K].numel())
         r.wait_framebuffer(K - 1)
