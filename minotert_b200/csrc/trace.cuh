@@ -74,6 +74,9 @@
 #ifndef TRACE_POSTPONE
 #define TRACE_POSTPONE 1     // 1: a lane of the persistent loop may hold one postponed triangle group and keep taking node steps
 #endif
+#ifndef TRACE_DEFER_STORE
+#define TRACE_DEFER_STORE 0  // 1: a finished ray's hit record is written when its lane takes the next ray (A/B measured: neutral)
+#endif
 #ifndef TRACE_DP4A_NEAR
 #define TRACE_DP4A_NEAR 1    // decode near planes with IDP.4A (FMA-heavy pipe), far planes with PRMT (ALU pipe)
 #endif
@@ -492,6 +495,9 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
     uint32_t ray_index = 0;
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform chunk of ray indices
     bool exhausted = false;
+#if TRACE_DEFER_STORE
+    bool store_pending = false;
+#endif
 
     for (;;) {
         // ---- refill idle lanes from the warp's chunk
@@ -509,6 +515,9 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
                 const uint32_t mine = pool_next + __popc(idle & lt_mask);
                 if (!have_ray && mine < pool_end) {
                     float3 o, d;
+#if TRACE_DEFER_STORE
+                    if (store_pending) { job.store(ray_index, L.hit); store_pending = false; }  // the lane's previous ray
+#endif
                     ray_index = mine;
                     if (job.load(mine, o, d)) {
                         lane_begin(L, o, d);
@@ -527,7 +536,12 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
         if (have_ray && !(L.ng.y & 0xFF000000u) && !(L.tg.y && L.tg2.y)) {
             if (L.sp == 0) {
                 if (!(L.tg.y | L.tg2.y)) {
+#if TRACE_DEFER_STORE
+                    store_pending = true;  // written when the lane takes its next ray (or after the loop): rays end one or
+                                           // two lanes at a time, refills come ~7 lanes at a time
+#else
                     job.store(ray_index, L.hit);
+#endif
                     have_ray = false;
                 }
             } else {
@@ -540,7 +554,11 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
 #else
         if (have_ray && !(L.ng.y & 0xFF000000u) && L.tg.y == 0u) {
             if (L.sp == 0) {
+#if TRACE_DEFER_STORE
+                store_pending = true;
+#else
                 job.store(ray_index, L.hit);
+#endif
                 have_ray = false;
             } else {
                 L.sp--;
@@ -597,6 +615,9 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
 #endif
         }
     }
+#if TRACE_DEFER_STORE
+    if (store_pending) job.store(ray_index, L.hit);
+#endif
 }
 
 // Per-lane loop for COHERENT rays (the primary pass): one node, then its triangles, per iteration.
