@@ -74,6 +74,9 @@
 #ifndef TRACE_POSTPONE
 #define TRACE_POSTPONE 1     // 1: a lane of the persistent loop may hold one postponed triangle group and keep taking node steps
 #endif
+#ifndef TRACE_NEAREST_FIRST
+#define TRACE_NEAREST_FIRST 0  // 1: of a node's hit inner children the one whose box the ray enters first is visited first, the rest in octant order (A/B)
+#endif
 #ifndef TRACE_DEFER_STORE
 #define TRACE_DEFER_STORE 0  // 1: a finished ray's hit record is written when its lane takes the next ray (A/B measured: neutral)
 #endif
@@ -265,8 +268,15 @@ template <bool POSTPONE>
 MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2* spill, TraceCounters& cnt, bool prefetch = false) {
     uint2* const sm = &S.stack[0][threadIdx.x];
     if (POSTPONE && L.tg.y) { L.tg2 = L.tg; L.tg2mask = L.tgmask; }
+#if TRACE_NEAREST_FIRST
+    // bits 8..11 of ng.y: octant-order position + 1 of the child whose box the ray enters first (set by the step that made the group)
+    const unsigned first = (L.ng.y >> 8) & 15u;
+    const unsigned bit = first ? 23u + first : 31u - __clz(L.ng.y);
+    L.ng.y &= ~((1u << bit) | 0xF00u);
+#else
     const unsigned bit = 31u - __clz(L.ng.y);
     L.ng.y &= ~(1u << bit);
+#endif
     if (L.ng.y & 0xFF000000u) {  // siblings remain: keep the group for later
         if (L.sp < TRACE_SM_STACK) sm[L.sp * TRACE_BLOCK] = L.ng;
         else if (L.sp < TRACE_SM_STACK + TRACE_LOCAL_STACK) spill[L.sp - TRACE_SM_STACK] = L.ng;
@@ -305,6 +315,9 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2
 
     const unsigned K = bvh.prmt_k;  // 0x47000000 from the kernel parameters (a constant-bank operand of PRMT)
     unsigned miss = 0u;  // after the loop: bit j set <=> child j missed
+#if defined(TRACE_COUNT_EMPTY) && TRACE_COUNT_EMPTY == 2
+    unsigned miss_nolimit = 0u;
+#endif
 #if TRACE_FFMA2
     // Two children per instruction: Blackwell's packed fp32 pipe (FFMA2 / FADD2, PTX fma.rn.f32x2) evaluates the slab
     // planes of children j and j-1 in one issue slot each -- the kernel is issue-bound (ncu: 70 % of the issue slots, FMA
@@ -317,6 +330,10 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2
     const unsigned long long sf2x = pack2(sfx, sfx), sf2y = pack2(sfy, sfy), sf2z = pack2(sfz, sfz);
     const unsigned long long bf2x = pack2(bfx, bfx), bf2y = pack2(bfy, bfy), bf2z = pack2(bfz, bfz);
     const unsigned long long tl2 = pack2(tlimit, tlimit);
+#if TRACE_NEAREST_FIRST
+    float nearest_key = -3.4e38f;
+    const unsigned imask_early = n0.w >> 24;
+#endif
 #pragma unroll
     for (int j = 7; j >= 1; j -= 2) {
         const unsigned wnx = j < 4 ? nx0 : nx1, wny = j < 4 ? ny0 : ny1, wnz = j < 4 ? nz0 : nz1;
@@ -336,6 +353,18 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2
         const unsigned negB = __float_as_uint(d1.y) | __float_as_uint(d2.y) | __float_as_uint(tmaxB);
         miss = __funnelshift_l(negA, miss, 1);
         miss = __funnelshift_l(negB, miss, 1);
+#if defined(TRACE_COUNT_EMPTY) && TRACE_COUNT_EMPTY == 2  // diagnostic: the same test without the closest-hit limit
+        miss_nolimit = __funnelshift_l(__float_as_uint(d1.x) | __float_as_uint(tmaxA), miss_nolimit, 1);
+        miss_nolimit = __funnelshift_l(__float_as_uint(d1.y) | __float_as_uint(tmaxB), miss_nolimit, 1);
+#endif
+#if TRACE_NEAREST_FIRST
+        {   // largest -tmin among the inner children that are hit; the slot rides in the three low mantissa bits
+            const float kA = __uint_as_float((__float_as_uint(ntminA) & ~7u) | (unsigned)j);
+            const float kB = __uint_as_float((__float_as_uint(ntminB) & ~7u) | (unsigned)(j - 1));
+            const bool okA = !(negA >> 31) && ((imask_early >> j) & 1u), okB = !(negB >> 31) && ((imask_early >> (j - 1)) & 1u);
+            nearest_key = fmaxf(nearest_key, fmaxf(okA ? kA : -3.4e38f, okB ? kB : -3.4e38f));
+        }
+#endif
     }
 #else
 #pragma unroll
@@ -361,11 +390,25 @@ MRT_D void lane_node_step(LaneState& L, const BvhDev& bvh, TraceShared& S, uint2
 #endif
     const unsigned imask = n0.w >> 24;
     const unsigned hit8 = ~miss & 0xFFu;
+#ifdef TRACE_COUNT_EMPTY  // diagnostic build: node steps that hit no child are counted as "stack overflows" (tools/count_empty.py)
+#if TRACE_COUNT_EMPTY == 2    // ... only those that would have hit a child without the closest-hit limit: stale stack entries
+    if (hit8 == 0u && (~miss_nolimit & 0xFFu) != 0u) cnt.overflow++;
+#else
+    if (hit8 == 0u) cnt.overflow++;
+#endif
+#endif
     // inner hits -> bit (slot ^ oct_inv); leaf hits -> 3 bits per slot, masked by the triangles that exist.
     // Both are 256-entry shared-memory tables (the LSU is idle here, the ALU pipe is the bottleneck).
     const unsigned inner = S.perm[L.oct_inv][hit8 & imask];
     const unsigned leaf = S.expand3[hit8 & ~imask];
+#if TRACE_NEAREST_FIRST && TRACE_FFMA2
+    {
+        const unsigned pos = ((__float_as_uint(nearest_key) & 7u) ^ L.oct_inv) + 1u;  // octant-order position of the nearest child
+        L.ng = make_uint2(n1.x, (inner << 24) | imask | (nearest_key > -3.0e38f ? pos << 8 : 0u));
+    }
+#else
     L.ng = make_uint2(n1.x, (inner << 24) | imask);
+#endif
     L.tg = make_uint2(n1.y, leaf & n1.z);
     L.tgmask = n1.z;
     // The child this lane visits next is already known: pull its 80 bytes towards L1 while the warp does its triangle

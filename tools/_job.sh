@@ -1,12 +1,8 @@
-out=gpurun_out/sanitizer_r2b.txt
-echo "compute-sanitizer $(compute-sanitizer --version | tail -1) on $(nvidia-smi -L | head -1)" > $out
-run() { echo "== $1" >> $out; shift; timeout 1200 "$@" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|hazard|Invalid|Uninit|error" | head -20 >> $out; }
-K1='(wide_refit or fused_sort or device_side) and (tiny or soup or small_terrain)'
-run memcheck_build compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "$K1"
-run racecheck_build compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "$K1"
-run initcheck_build compute-sanitizer --tool initcheck python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "$K1"
-run synccheck_build compute-sanitizer --tool synccheck python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "$K1"
-run memcheck_async compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_mesh.py -m gpu -q -x -k "async_mesh_updates or frames_in_flight"
-run memcheck_denoise compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_denoise.py -m gpu -q -x
-run racecheck_denoise compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_denoise.py -m gpu -q -x -k "default_params"
-cat $out
+MINOTERT_LIB_DIR=variants/empty python tools/count_empty.py 2>&1 | tail -3
+MINOTERT_LIB_DIR=variants/nearest timeout 600 python -m pytest tests/test_gpu_mesh.py -x -q -m gpu -k "brute_force or watertight or axis_parallel or render" 2>&1 | tail -2
+for w in hall_260k_1080p scene_1m_1080p; do
+  tools/ab.sh base_$w --no-extra-configs --workload $w --opt count_visits=1
+  MINOTERT_LIB_DIR=variants/nearest tools/ab.sh nearest_$w --no-extra-configs --workload $w --opt count_visits=1
+  tools/ab.sh base2_$w --no-extra-configs --workload $w
+  MINOTERT_LIB_DIR=variants/nearest tools/ab.sh nearest2_$w --no-extra-configs --workload $w
+done
