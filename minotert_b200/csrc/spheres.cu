@@ -41,7 +41,22 @@ struct SecondaryParams {
     uint32_t bnW, bnH;
 };
 
-// secondaryRays.comp:64-135 with Samples/Bounces as parameters
+// secondaryRays.comp:64-135 with Samples/Bounces as parameters.
+// BATCHED = false: the shader's loops as they stand -- for each sample, for each bounce -- one pixel per lane.  Paths end
+// at very different bounces, and a lane whose path has ended waits for the warp's longest one, sample after sample
+// (ncu: 16.8 of 32 lanes active); and the sky colour of a path that escapes (~300 instructions of LUT arithmetic) is
+// evaluated inside the bounce loop, i.e. in almost every iteration for the few lanes that escaped in it.
+// BATCHED = true (default, option "spheres_batched"): the same arithmetic per lane in the same order -- samples one after the
+// other, bounces one after the other, the running sum added to in sample order, the RNG state handed on -- but the warp
+// steps a small state machine instead of the nested loops: a lane whose path ends starts its NEXT sample at once, so lanes
+// only idle at the very end of the pixel (the sum of 8 path lengths varies far less than one of them); and a lane whose
+// path escaped waits with (throughput, direction) until SKY_MIN lanes want the sky colour (or no lane can bounce), so that
+// the LUT code runs with a dozen lanes instead of two; and a pixel that shows the sky evaluates its colour once, not once per
+// sample (same direction, same value).  Bit-identical image and ray count (test).
+#ifndef SPHERES_SKY_MIN
+#define SPHERES_SKY_MIN 12
+#endif
+template <bool BATCHED>
 __global__ void __launch_bounds__(128)
 k_spheres_secondary(SecondaryParams P, Spheres sp, Partition part, mrt_atmosphere_params A, SkyLuts luts,
                     const uchar4* __restrict__ bn, const uint32_t* __restrict__ vis, const uint16_t* __restrict__ depth,
@@ -49,6 +64,8 @@ k_spheres_secondary(SecondaryParams P, Spheres sp, Partition part, mrt_atmospher
                     int accumulate, unsigned long long* __restrict__ ray_counter) {
     uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, lr = blockIdx.y * blockDim.y + threadIdx.y;
     unsigned long long rays = 0;
+    // the lanes of this warp that own a pixel: the votes of the BATCHED state machine are taken among them
+    const unsigned warp_mask = __ballot_sync(0xFFFFFFFFu, x < P.W && lr < P.local_rows);
     if (x < P.W && lr < P.local_rows) {
         uint32_t y = partition_local_to_y(part, lr);
         size_t p = (size_t)lr * P.W + x;
@@ -70,6 +87,71 @@ k_spheres_secondary(SecondaryParams P, Spheres sp, Partition part, mrt_atmospher
         float2 rot = blue_noise_rotation(bn, P.bnW, P.bnH, x, y);
 
         float3 color = f3s(0.0f);
+        if (BATCHED) {
+            // per-lane path state; sky_wait: the path escaped along hn with throughput thr, its sky colour is still to be added
+            uint32_t s = 0, i = 0, hid = pid;
+            float3 thr = f3s(1.0f), hpos = ppos, hn = pn;
+            bool sky_wait = false;
+            // A pixel that shows the sky asks for the same sky colour (direction pn, throughput 1) once per sample: the
+            // first answer is kept and the others add it again -- same value, same sum
+            bool sky_known = false;
+            float3 sky_pn = f3s(0.0f);
+            // vertex 0 of sample s is the primary hit from the G-buffer: no ray, no random numbers
+            auto begin_samples = [&]() {
+                while (s < P.spp) {
+                    hid = pid; hpos = ppos; hn = pn;
+                    thr = f3s(1.0f);
+                    if (hid == MRT_MISS_ID) {
+                        if (sky_known) { color = color + thr * sky_pn; s++; continue; }
+                        sky_wait = true;
+                        return;
+                    }
+                    thr = thr * f3(sp.s[hid].albedo[0], sp.s[hid].albedo[1], sp.s[hid].albedo[2]);
+                    i = 1;
+                    if (i < P.bounces + 1u) return;
+                    s++;  // no bounces asked for: the sample adds nothing
+                }
+            };
+            begin_samples();
+            for (;;) {
+                const bool want_sky = s < P.spp && sky_wait, want_bounce = s < P.spp && !sky_wait;
+                const unsigned sky_mask = __ballot_sync(warp_mask, want_sky), bounce_mask = __ballot_sync(warp_mask, want_bounce);
+                if (!(sky_mask | bounce_mask)) break;
+                if (sky_mask && (bounce_mask == 0u || __popc(sky_mask) >= SPHERES_SKY_MIN)) {
+                    if (want_sky) {
+                        const float3 sky = sky_color(A, luts, P.cameraPos, hn);
+                        if (pid == MRT_MISS_ID) { sky_pn = sky; sky_known = true; }
+                        color = color + thr * sky;
+                        sky_wait = false;
+                        s++;
+                        begin_samples();
+                    }
+                } else if (want_bounce) {
+                    float3 ro, rd;
+                    lambert_bounce(hpos, hn, rng, rot.x, rot.y, ro, rd);
+                    rays++;
+                    hid = MRT_MISS_ID;
+                    float ht = -1.0f;
+                    for (uint32_t k = 0; k < sp.n; k++) {
+                        float t = ray_sphere(ro, rd, sp.s[k]);
+                        if (t >= 0.0f && (t < ht || ht < 0.0f)) { hid = k; ht = t; }
+                    }
+                    if (hid != MRT_MISS_ID) {
+                        hpos = ro + rd * ht;
+                        hn = normalize3(hpos - f3(sp.s[hid].center[0], sp.s[hid].center[1], sp.s[hid].center[2]));
+                        thr = thr * f3(sp.s[hid].albedo[0], sp.s[hid].albedo[1], sp.s[hid].albedo[2]);
+                        i++;
+                        if (i == P.bounces + 1u) {  // the last bounce hit a sphere: the sample adds nothing (contrib = 0)
+                            s++;
+                            begin_samples();
+                        }
+                    } else {
+                        hn = rd;
+                        sky_wait = true;
+                    }
+                }
+            }
+        } else
         for (uint32_t s = 0; s < P.spp; s++) {
             float3 thr = f3s(1.0f);
             uint32_t hid = pid;
@@ -151,9 +233,10 @@ int spheres_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32
     // 16x8 tiles: warps cover 16x2 pixel footprints, which keeps the divergent bounce loops of
     // neighbouring pixels (same sphere, similar path length) in one warp.
     dim3 b(16, 8), grid(div_up(ctx->W, 16), div_up(ctx->local_rows, 8));
-    k_spheres_secondary<<<grid, b, 0, ctx->stream>>>(P, ctx->spheres, ctx->part, ctx->atmo, luts, ctx->bn, ctx->visibility.p,
-                                                     ctx->depth.p, ctx->normal.p, ctx->color16.p, ctx->accum.p,
-                                                     (flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum ? 1 : 0, ctx->visit_counters.p + 4);
+    auto* const kernel = ctx->opt_spheres_batched ? k_spheres_secondary<true> : k_spheres_secondary<false>;
+    kernel<<<grid, b, 0, ctx->stream>>>(P, ctx->spheres, ctx->part, ctx->atmo, luts, ctx->bn, ctx->visibility.p, ctx->depth.p,
+                                        ctx->normal.p, ctx->color16.p, ctx->accum.p,
+                                        (flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum ? 1 : 0, ctx->visit_counters.p + 4);
     MRT_LAUNCHED(ctx);
     return mrt_check_cuda(ctx, cudaGetLastError(), "spheres_secondary");
 }
