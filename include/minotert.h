@@ -184,9 +184,10 @@ const char* mrt_last_error(const mrt_context* ctx);
  *                             contexts that share a GPU
  *   "build_device_loop" 0/1   PLOC rounds and collapse levels looped inside two cooperative kernels (default 1) or
  *                             driven from the host with a readback per round (0); same tree either way; invalidates the BVH
- *   "spheres_batched" 0/1     sphere path: every lane runs its samples and bounces back to back through a warp-synchronous
- *                             state machine and escaped paths wait for a batched sky evaluation (default 1), or the
- *                             shader's nested loops (0); same image and ray count bit for bit
+ *   "spheres_batched" 0/1/2   sphere path: the shader's nested loops (0); every lane runs its samples and bounces back to back
+ *                             through a warp-synchronous state machine and escaped paths wait for a batched sky
+ *                             evaluation (1, default); ... and a lane that has finished its pixel takes the next one,
+ *                             persistent grid (2: measured slower); same image and ray count bit for bit
  *   "fused_sort" 0/1          Morton / ray radix sort: all 8-bit passes in one cooperative launch when every tile's CTA is
  *                             resident at once (<= 1.2 M keys; default 1), or 5 launches per pass (0); same permutation;
  *                             invalidates the BVH

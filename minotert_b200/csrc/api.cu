@@ -222,7 +222,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "bands")) ctx->opt_bands = (int)(value < 1 ? 1 : (value > MRT_MAX_BANDS ? MRT_MAX_BANDS : value));
     else if (!strcmp(name, "trace_ctas_per_sm")) ctx->opt_trace_ctas_per_sm = (int)(value > 32 ? 32 : value);
     else if (!strcmp(name, "wide_refit")) ctx->opt_wide_refit = value != 0;
-    else if (!strcmp(name, "spheres_batched")) ctx->opt_spheres_batched = value != 0;
+    else if (!strcmp(name, "spheres_batched")) ctx->opt_spheres_batched = value < 0 ? 0 : value > 2 ? 2 : (int)value;
     else if (!strcmp(name, "fused_sort")) { ctx->opt_fused_sort = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "async_update")) ctx->opt_async_update = value != 0;
     else if (!strcmp(name, "build_device_loop")) { ctx->opt_build_device_loop = value != 0; ctx->bvh_valid = false; }

@@ -82,7 +82,8 @@ struct mrt_context {
     int opt_fused_shade = 0;         // shade stage of a bounce wave inside the traversal kernel (mesh.cu k_trace_shade); A/B: +1.5 % at 1080p 1 spp, -2 % at 4K 8 spp
     int opt_trace_ctas_per_sm = 0;   // 0: as many as fit; n: persistent traversal grids use n CTAs per SM (co-running contexts)
     int opt_builder = 1;             // 0: Karras LBVH hierarchy, 1: PLOC (locally-ordered clustering) hierarchy
-    int opt_spheres_batched = 1;     // sphere path: samples and bounces through a warp-synchronous state machine (0: the shader's nested loops)
+    int opt_spheres_batched = 1;     // sphere path: 0 the shader's nested loops, 1 warp-synchronous state machine over samples and bounces (default), 2 ... with per-lane pixel refill (persistent grid; measured slower)
+    int spheres_grid = 0;            // resident CTAs of k_spheres_secondary_persistent (queried once)
     int opt_fused_sort = 1;          // radix sort: all passes in one cooperative launch when the tiles are co-resident (0: 5 launches per pass)
     int fused_sort_capacity = -1;    // co-resident CTAs of k_rs_fused (queried once)
     int opt_async_update = 0;        // mrt_scene_update_positions + MRT_BUILD_REFIT return without waiting for the GPU (see minotert.h)

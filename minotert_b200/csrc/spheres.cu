@@ -198,6 +198,144 @@ k_spheres_secondary(SecondaryParams P, Spheres sp, Partition part, mrt_atmospher
     if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0 && rays) atomicAdd(ray_counter, rays);
 }
 
+// option "spheres_batched" 2 (A/B: 0.396 vs 0.271 ms per frame -- 80 registers, and every pixel pays a thin refill: kept as an
+// option, off): the state machine of BATCHED above, plus the traversal kernel's refill -- a
+// persistent grid whose lanes take the NEXT PIXEL (in 16x2-tile order, one global atomic per tile) as soon as six of a
+// warp's lanes have finished theirs.  What BATCHED leaves idle is the end of a pixel: the sum of eight path lengths still
+// varies by +-17 % across a warp, and warps over the sky / ground boundary mix cheap and expensive pixels.  Same per-pixel
+// arithmetic in the same order; pixels are independent, so the image does not depend on which lane renders which.
+#ifndef SPHERES_REFILL_MIN
+#define SPHERES_REFILL_MIN 6
+#endif
+__global__ void __launch_bounds__(128)
+k_spheres_secondary_persistent(SecondaryParams P, Spheres sp, Partition part, mrt_atmosphere_params A, SkyLuts luts,
+                               const uchar4* __restrict__ bn, const uint32_t* __restrict__ vis, const uint16_t* __restrict__ depth,
+                               const uint16_t* __restrict__ normal, uint16_t* __restrict__ color16, float4* __restrict__ accum,
+                               int accumulate, unsigned long long* __restrict__ ray_counter, uint32_t* __restrict__ work_counter) {
+    const unsigned FULL = 0xFFFFFFFFu, lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+    const uint32_t tiles_x = (P.W + 15u) / 16u, tiles_y = (P.local_rows + 1u) / 2u, total = tiles_x * tiles_y * 32u;
+    const float pitchx = 1.0f / (float)P.W, pitchy = 1.0f / (float)P.H;
+    unsigned long long rays = 0;
+    // the pixel this lane renders and its path state (see k_spheres_secondary<true>)
+    bool have_pixel = false, sky_wait = false, sky_known = false;
+    size_t p = 0;
+    uint32_t pid = MRT_MISS_ID, rng = 0, s = 0, i = 0, hid = MRT_MISS_ID;
+    float3 pn = f3s(0.0f), ppos = f3s(0.0f), color = f3s(0.0f), thr = f3s(1.0f), hpos = f3s(0.0f), hn = f3s(0.0f), sky_pn = f3s(0.0f);
+    float2 rot = make_float2(0.0f, 0.0f);
+    auto begin_samples = [&]() {
+        while (s < P.spp) {
+            hid = pid; hpos = ppos; hn = pn;
+            thr = f3s(1.0f);
+            if (hid == MRT_MISS_ID) {
+                if (sky_known) { color = color + thr * sky_pn; s++; continue; }
+                sky_wait = true;
+                return;
+            }
+            thr = thr * f3(sp.s[hid].albedo[0], sp.s[hid].albedo[1], sp.s[hid].albedo[2]);
+            i = 1;
+            if (i < P.bounces + 1u) return;
+            s++;
+        }
+    };
+    uint32_t pool_next = 0, pool_end = 0;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !have_pixel);
+        if (idle && !exhausted && (idle == FULL || __popc(idle) >= SPHERES_REFILL_MIN)) {
+            if (pool_next >= pool_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work_counter, 32u);
+                base = __shfl_sync(FULL, base, 0);
+                pool_next = base;
+                pool_end = min(base + 32u, total);
+                if (base >= total) { exhausted = true; pool_next = pool_end = 0; }
+            }
+            if (!exhausted) {
+                const uint32_t mine = pool_next + __popc(idle & lt_mask);
+                if (!have_pixel && mine < pool_end) {
+                    const uint32_t tile = mine >> 5, j = mine & 31u;
+                    const uint32_t x = (tile % tiles_x) * 16u + (j & 15u), lr = (tile / tiles_x) * 2u + (j >> 4);
+                    if (x < P.W && lr < P.local_rows) {
+                        const uint32_t y = partition_local_to_y(part, lr);
+                        p = (size_t)lr * P.W + x;
+                        float u = ((float)x + 0.5f) * pitchx;
+                        float v = ((float)y + 0.5f) * pitchy;
+                        v = 1.0f - v;
+                        // reconstruct the primary hit from the fp16 G-buffer (:114-123)
+                        pid = vis[p];
+                        const uint2 npk = reinterpret_cast<const uint2*>(normal)[p];
+                        pn = f3(f16_bits_to_f32((uint16_t)(npk.x & 0xFFFF)), f16_bits_to_f32((uint16_t)(npk.x >> 16)),
+                                f16_bits_to_f32((uint16_t)(npk.y & 0xFFFF)));
+                        const float dep = f16_bits_to_f32(depth[p]);
+                        float4 vp = mat_vec(P.invProj, u * 2.0f - 1.0f, v * 2.0f - 1.0f, dep, 1.0f);
+                        vp.x /= vp.w; vp.y /= vp.w; vp.z /= vp.w;
+                        const float4 wp = mat_vec(P.invView, vp.x, vp.y, vp.z, 1.0f);
+                        ppos = f3(wp.x, wp.y, wp.z);
+                        rng = (P.frameCounter << 1u) | 1u;
+                        rot = blue_noise_rotation(bn, P.bnW, P.bnH, x, y);
+                        color = f3s(0.0f);
+                        s = 0;
+                        sky_wait = false;
+                        sky_known = false;
+                        have_pixel = true;
+                        begin_samples();
+                    }
+                }
+                pool_next = min(pool_next + (uint32_t)__popc(idle), pool_end);
+            }
+        }
+        if (exhausted && __ballot_sync(FULL, have_pixel) == 0u) break;
+        if (have_pixel && s >= P.spp) {
+            // progressive sum (row n7) before the reference's own average (:133)
+            const float4 a = accumulate ? accum[p] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            accum[p] = make_float4(a.x + color.x, a.y + color.y, a.z + color.z, a.w + (float)P.spp);
+            const float3 avg = color / (float)P.spp;
+            uint2 pk;
+            pk.x = (uint32_t)f32_to_f16_bits(avg.x) | ((uint32_t)f32_to_f16_bits(avg.y) << 16);
+            pk.y = (uint32_t)f32_to_f16_bits(avg.z) | (0x3C00u << 16);
+            reinterpret_cast<uint2*>(color16)[p] = pk;
+            have_pixel = false;
+        }
+        const bool want_sky = have_pixel && sky_wait, want_bounce = have_pixel && !sky_wait;
+        const unsigned sky_mask = __ballot_sync(FULL, want_sky), bounce_mask = __ballot_sync(FULL, want_bounce);
+        if (sky_mask && (bounce_mask == 0u || __popc(sky_mask) >= SPHERES_SKY_MIN)) {
+            if (want_sky) {
+                const float3 sky = sky_color(A, luts, P.cameraPos, hn);
+                if (pid == MRT_MISS_ID) { sky_pn = sky; sky_known = true; }
+                color = color + thr * sky;
+                sky_wait = false;
+                s++;
+                begin_samples();
+            }
+        } else if (want_bounce) {
+            float3 ro, rd;
+            lambert_bounce(hpos, hn, rng, rot.x, rot.y, ro, rd);
+            rays++;
+            hid = MRT_MISS_ID;
+            float ht = -1.0f;
+            for (uint32_t k = 0; k < sp.n; k++) {
+                float t = ray_sphere(ro, rd, sp.s[k]);
+                if (t >= 0.0f && (t < ht || ht < 0.0f)) { hid = k; ht = t; }
+            }
+            if (hid != MRT_MISS_ID) {
+                hpos = ro + rd * ht;
+                hn = normalize3(hpos - f3(sp.s[hid].center[0], sp.s[hid].center[1], sp.s[hid].center[2]));
+                thr = thr * f3(sp.s[hid].albedo[0], sp.s[hid].albedo[1], sp.s[hid].albedo[2]);
+                i++;
+                if (i == P.bounces + 1u) {  // the last bounce hit a sphere: the sample adds nothing (contrib = 0)
+                    s++;
+                    begin_samples();
+                }
+            } else {
+                hn = rd;
+                sky_wait = true;
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(FULL, rays, off);
+    if (lane == 0 && rays) atomicAdd(ray_counter, rays);
+}
+
 }  // namespace
 
 int spheres_primary(mrt_context* ctx) {
@@ -233,10 +371,27 @@ int spheres_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32
     // 16x8 tiles: warps cover 16x2 pixel footprints, which keeps the divergent bounce loops of
     // neighbouring pixels (same sphere, similar path length) in one warp.
     dim3 b(16, 8), grid(div_up(ctx->W, 16), div_up(ctx->local_rows, 8));
+    const int acc = (flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum ? 1 : 0;
+    if (ctx->opt_spheres_batched >= 2) {
+        // persistent grid: as many CTAs as are resident at once (or fewer when the image is small)
+        if (ctx->spheres_grid <= 0) {
+            int sms = 148, per_sm = 4;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spheres_secondary_persistent, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+            ctx->spheres_grid = sms * per_sm;
+        }
+        const unsigned warps = div_up(ctx->W, 16u) * div_up(ctx->local_rows, 2u);
+        const unsigned grid1 = max(1u, min((unsigned)ctx->spheres_grid, div_up(warps, 4u)));
+        k_spheres_secondary_persistent<<<grid1, 128, 0, ctx->stream>>>(P, ctx->spheres, ctx->part, ctx->atmo, luts, ctx->bn, ctx->visibility.p,
+                                                                       ctx->depth.p, ctx->normal.p, ctx->color16.p, ctx->accum.p, acc,
+                                                                       ctx->visit_counters.p + 4,
+                                                                       reinterpret_cast<uint32_t*>(ctx->visit_counters.p + 5));
+        MRT_LAUNCHED(ctx);
+        return mrt_check_cuda(ctx, cudaGetLastError(), "spheres_secondary");
+    }
     auto* const kernel = ctx->opt_spheres_batched ? k_spheres_secondary<true> : k_spheres_secondary<false>;
     kernel<<<grid, b, 0, ctx->stream>>>(P, ctx->spheres, ctx->part, ctx->atmo, luts, ctx->bn, ctx->visibility.p, ctx->depth.p,
-                                        ctx->normal.p, ctx->color16.p, ctx->accum.p,
-                                        (flags & MRT_SECONDARY_ACCUMULATE) && ctx->have_accum ? 1 : 0, ctx->visit_counters.p + 4);
+                                        ctx->normal.p, ctx->color16.p, ctx->accum.p, acc, ctx->visit_counters.p + 4);
     MRT_LAUNCHED(ctx);
     return mrt_check_cuda(ctx, cudaGetLastError(), "spheres_secondary");
 }

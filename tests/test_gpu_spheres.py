@@ -124,7 +124,7 @@ def test_spheres_batched_equals_the_nested_loops(gpu_ctx, oracle, sky_inputs, bl
     gpu_ctx.upload_blue_noise(blue_noise)
     gpu_ctx.set_spheres(oracle.REFERENCE_SPHERES)
     got = []
-    for batched in (0, 1):
+    for batched in (0, 1, 2):
         gpu_ctx.set_option("spheres_batched", batched)
         frames = []
         for frame in (1, 2):
@@ -134,10 +134,10 @@ def test_spheres_batched_equals_the_nested_loops(gpu_ctx, oracle, sky_inputs, bl
             gpu_ctx.secondary_rays(as_capi(sc, capi.SecondaryConstants), spp, bounces, capi.SECONDARY_ACCUMULATE if frame > 1 else 0)
             frames.append((gpu_ctx.readback(capi.BUF_COLOR).copy(), gpu_ctx.readback(capi.BUF_ACCUM).copy(), int(gpu_ctx.stats().secondary_rays)))
         got.append(frames)
-    gpu_ctx.set_option("spheres_batched", 1)
-    for a, b in zip(got[0], got[1]):
-        assert a[2] == b[2], "ray counts differ"
-        assert np.array_equal(a[0].view(np.uint16), b[0].view(np.uint16)) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    for other in got[1:]:
+        for a, b in zip(got[0], other):
+            assert a[2] == b[2], "ray counts differ"
+            assert np.array_equal(a[0].view(np.uint16), b[0].view(np.uint16)) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
 
 
 @pytest.mark.parametrize("mode,params", [("linear", ()), ("reinhard", (8.0,)), ("hable", ()), ("aces", ()),
