@@ -184,6 +184,9 @@ const char* mrt_last_error(const mrt_context* ctx);
  *                             contexts that share a GPU
  *   "build_device_loop" 0/1   PLOC rounds and collapse levels looped inside two cooperative kernels (default 1) or
  *                             driven from the host with a readback per round (0); same tree either way; invalidates the BVH
+ *   "prepared_rays" 0/1       bounce rays are queued with 1/d, the shear constants of the triangle test and the octant, computed
+ *                             by the shade stage (default 1), or the traversal kernel derives them when a lane takes
+ *                             the ray (0); same image bit for bit
  *   "spheres_batched" 0/1/2   sphere path: the shader's nested loops (0); every lane runs its samples and bounces back to back
  *                             through a warp-synchronous state machine and escaped paths wait for a batched sky
  *                             evaluation (1, default); ... and a lane that has finished its pixel takes the next one,

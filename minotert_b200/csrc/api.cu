@@ -180,7 +180,7 @@ void mrt_destroy(mrt_context* ctx) {
     for (int k = 0; k < 2; k++) { dev_free(ctx->tp_rgba[k]); dev_free(ctx->tp_count[k]); dev_free(ctx->tp_vis[k]); }
     dev_free(ctx->hit_t); dev_free(ctx->accum); dev_free(ctx->frame_sum); dev_free(ctx->sun_e); dev_free(ctx->aerial16); dev_free(ctx->aerial_f); for (auto& q : ctx->shadow_q) dev_free(q); dev_free(ctx->ldr_buf[0]); dev_free(ctx->ldr_buf[1]);
     dev_free(ctx->hit0_pos); dev_free(ctx->hit0_n); dev_free(ctx->path_state);
-    for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); }
+    for (int q = 0; q < 2; q++) { dev_free(ctx->ray_o[q]); dev_free(ctx->ray_d[q]); dev_free(ctx->ray_p[q]); dev_free(ctx->ray_s[q]); }
     dev_free(ctx->hits); dev_free(ctx->queue_counts); dev_free(ctx->sort_keys); dev_free(ctx->sort_keys_alt);
     dev_free(ctx->sort_vals); dev_free(ctx->sort_vals_alt); dev_free(ctx->visit_counters); dev_free(ctx->total_rays);
     dev_free(ctx->query_o); dev_free(ctx->query_d); dev_free(ctx->query_t); dev_free(ctx->query_ids);
@@ -222,6 +222,7 @@ int mrt_set_option(mrt_context* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "bands")) ctx->opt_bands = (int)(value < 1 ? 1 : (value > MRT_MAX_BANDS ? MRT_MAX_BANDS : value));
     else if (!strcmp(name, "trace_ctas_per_sm")) ctx->opt_trace_ctas_per_sm = (int)(value > 32 ? 32 : value);
     else if (!strcmp(name, "wide_refit")) ctx->opt_wide_refit = value != 0;
+    else if (!strcmp(name, "prepared_rays")) ctx->opt_prepared_rays = value != 0;
     else if (!strcmp(name, "spheres_batched")) ctx->opt_spheres_batched = value < 0 ? 0 : value > 2 ? 2 : (int)value;
     else if (!strcmp(name, "fused_sort")) { ctx->opt_fused_sort = value != 0; ctx->bvh_valid = false; }
     else if (!strcmp(name, "async_update")) ctx->opt_async_update = value != 0;

@@ -82,6 +82,7 @@ struct mrt_context {
     int opt_fused_shade = 0;         // shade stage of a bounce wave inside the traversal kernel (mesh.cu k_trace_shade); A/B: +1.5 % at 1080p 1 spp, -2 % at 4K 8 spp
     int opt_trace_ctas_per_sm = 0;   // 0: as many as fit; n: persistent traversal grids use n CTAs per SM (co-running contexts)
     int opt_builder = 1;             // 0: Karras LBVH hierarchy, 1: PLOC (locally-ordered clustering) hierarchy
+    int opt_prepared_rays = 1;       // the shade stage stores 1/d, the shear constants and the octant with the rays it queues (0: the traversal kernel derives them at refill)
     int opt_spheres_batched = 1;     // sphere path: 0 the shader's nested loops, 1 warp-synchronous state machine over samples and bounces (default), 2 ... with per-lane pixel refill (persistent grid; measured slower)
     int spheres_grid = 0;            // resident CTAs of k_spheres_secondary_persistent (queried once)
     int opt_fused_sort = 1;          // radix sort: all passes in one cooperative launch when the tiles are co-resident (0: 5 launches per pass)
@@ -193,6 +194,7 @@ struct mrt_context {
     DevArray<float4> hit0_pos, hit0_n;   // primary hit position|prim id, normal|valid
     DevArray<float4> path_state;         // throughput rgb | rng state
     DevArray<float4> ray_o[2], ray_d[2]; // queues: origin|pixel, direction|tmax
+    DevArray<float4> ray_p[2], ray_s[2]; // option prepared_rays: (1/d, Sx), (Sy, Sz, axes | octant) of the queued rays
     DevArray<unsigned long long> hits;   // t bits | tri slot << 32 (MRT_HIT_PENDING_TRI: not traced yet)
     bool hits_dirty = true;              // records are not all "pending": reset before the next fused wave
     DevArray<uint32_t> queue_counts;     // one counter per wave, then one work counter per trace launch

@@ -79,6 +79,7 @@ struct PrimaryJob {
         ray_gen(F.gen, x, partition_local_to_y(F.part, lr), o, d);
         return true;
     }
+    MRT_D bool load_prepared(uint32_t, float3&, RayPre&) const { return false; }  // rays are set up by the traversal kernel
     MRT_D void store(uint32_t i, const TraceHit& h) const {
         uint32_t x, lr;
         pixel(i, x, lr);
@@ -514,6 +515,17 @@ struct QueueJob {
         d = f3(d4.x, d4.y, d4.z);
         return true;
     }
+    const float4* ray_p;  // option "prepared_rays": (1/d, Sx) and (Sy, Sz, axes | octant) written by the shade stage, or nullptr
+    const float4* ray_s;
+    MRT_D bool load_prepared(uint32_t i0, float3& o, RayPre& pre) const {
+        if (!ray_p) return false;
+        const uint32_t i = slot(i0);
+        const uint32_t k = order ? __ldg(&order[i]) : i;
+        const float4 o4 = __ldg(&ray_o[k]);
+        o = f3(o4.x, o4.y, o4.z);
+        pre = ray_pre_unpack(__ldg(&ray_p[k]), __ldg(&ray_s[k]));
+        return true;
+    }
     MRT_D void store(uint32_t i0, const TraceHit& h) const {
         const uint32_t i = slot(i0);
         const uint32_t k = order ? __ldg(&order[i]) : i;  // hit records stay in queue order for the shade kernel
@@ -650,6 +662,7 @@ struct QueryJob {
         d = f3(rd[3 * (size_t)i], rd[3 * (size_t)i + 1], rd[3 * (size_t)i + 2]);
         return true;
     }
+    MRT_D bool load_prepared(uint32_t, float3&, RayPre&) const { return false; }  // rays are set up by the traversal kernel
     MRT_D void store(uint32_t i, const TraceHit& h) const {
         ids[i] = h.prim;
         ts[i] = h.prim != MRT_MISS_ID ? h.t : 0.0f;
@@ -673,6 +686,7 @@ struct ShadowJob {
         d = f3(d4.x, d4.y, d4.z);
         return true;
     }
+    MRT_D bool load_prepared(uint32_t, float3&, RayPre&) const { return false; }  // rays are set up by the traversal kernel
     MRT_D void store(uint32_t i, const TraceHit& h) const {
         if (h.prim != MRT_MISS_ID) return;
         const uint32_t pixel = __float_as_uint(__ldg(&ray_o[i]).w);
@@ -749,6 +763,8 @@ struct ShadeArgs {
     float4* accum;
     float4* out_o;                // next bounce's queue
     float4* out_d;
+    float4* out_p;                // option "prepared_rays": ray_prepare(direction) of the next queue's rays (nullptr: off)
+    float4* out_s;
     uint32_t* out_count;
     uint32_t* out_back;           // option "ray_split": entries taken from the back of the next queue (nullptr: off) ...
     uint32_t out_cap;             // ... whose capacity this is
@@ -905,6 +921,12 @@ MRT_D void shade_vertex(uint32_t k, bool valid, const ShadeArgs& a) {
             uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
             a.out_o[slot] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(pixel));
             a.out_d[slot] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+            if (a.out_p) {
+                float4 pa, pb;
+                ray_pre_pack(ray_prepare(rd), pa, pb);
+                a.out_p[slot] = pa;
+                a.out_s[slot] = pb;
+            }
         }
     }
     if (a.out_back) {
@@ -919,6 +941,12 @@ MRT_D void shade_vertex(uint32_t k, bool valid, const ShadeArgs& a) {
                 uint32_t slot = a.out_cap - 1u - (base + __popc(bb & ((1u << lane) - 1u)));
                 a.out_o[slot] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(pixel));
                 a.out_d[slot] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+                if (a.out_p) {
+                    float4 pa, pb;
+                    ray_pre_pack(ray_prepare(rd), pa, pb);
+                    a.out_p[slot] = pa;
+                    a.out_s[slot] = pb;
+                }
             }
         }
     }
@@ -1420,9 +1448,14 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
     if (bands > MRT_MAX_BANDS) bands = MRT_MAX_BANDS;
     while (bands > 1 && npix / bands < 32768u) bands--;  // a band must still fill the GPU
     MRT_TRY(dev_reserve(ctx, ctx->path_state, npix));
+    const bool prepared = ctx->opt_prepared_rays != 0;
     for (int q = 0; q < 2; q++) {
         MRT_TRY(dev_reserve(ctx, ctx->ray_o[q], npix));
         MRT_TRY(dev_reserve(ctx, ctx->ray_d[q], npix));
+        if (prepared) {
+            MRT_TRY(dev_reserve(ctx, ctx->ray_p[q], npix));
+            MRT_TRY(dev_reserve(ctx, ctx->ray_s[q], npix));
+        }
     }
     if (npix > ctx->hits.cap || !ctx->hits.p) ctx->hits_dirty = true;
     MRT_TRY(dev_reserve(ctx, ctx->hits, npix));
@@ -1505,6 +1538,8 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
         uint32_t* const shade_counters = ctx->queue_counts.p + (size_t)bands * (2 * (size_t)waves + 1) + (size_t)band * waves;
         float4* const ray_o[2] = {ctx->ray_o[0].p + p0, ctx->ray_o[1].p + p0};
         float4* const ray_d[2] = {ctx->ray_d[0].p + p0, ctx->ray_d[1].p + p0};
+        float4* const ray_p[2] = {prepared ? ctx->ray_p[0].p + p0 : nullptr, prepared ? ctx->ray_p[1].p + p0 : nullptr};
+        float4* const ray_s[2] = {prepared ? ctx->ray_s[0].p + p0 : nullptr, prepared ? ctx->ray_s[1].p + p0 : nullptr};
         sa.hits = ctx->hits.p + p0;
         sa.npix = bpix;
         P.pixel_base = p0;
@@ -1533,6 +1568,8 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
             sa.in_o = sa.in_d = nullptr;
             sa.out_o = ray_o[q];
             sa.out_d = ray_d[q];
+            sa.out_p = ray_p[q];
+            sa.out_s = ray_s[q];
             sa.out_count = qcounts + wave;
             sa.out_back = split ? bcounts + wave : nullptr;
             sa.in_back = nullptr;
@@ -1582,7 +1619,7 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
                     MRT_LAUNCHED(ctx);
                     order = ctx->sort_vals.p;
                 }
-                QueueJob J{ray_o[q], ray_d[q], in_count, sa.hits, order, split ? bcounts + wave : nullptr, bpix};
+                QueueJob J{ray_o[q], ray_d[q], in_count, sa.hits, order, split ? bcounts + wave : nullptr, bpix, ray_p[q], ray_s[q]};
                 const unsigned long long extra = wave == 0 ? (unsigned long long)bpix : 0ull;
                 // the shade stage of this wave: vertex b of the paths; the last vertex emits nothing (its counter slot stays 0)
                 P.vertex = b;
@@ -1590,6 +1627,8 @@ int mesh_secondary(mrt_context* ctx, const mrt_secondary_constants* c, uint32_t 
                 sa.in_d = ray_d[q];
                 sa.out_o = ray_o[q ^ 1];
                 sa.out_d = ray_d[q ^ 1];
+                sa.out_p = ray_p[q ^ 1];
+                sa.out_s = ray_s[q ^ 1];
                 sa.out_count = qcounts + (wave + 1 < waves ? wave + 1 : waves);
                 sa.in_back = split ? bcounts + wave : nullptr;
                 sa.out_back = split ? bcounts + (wave + 1 < waves ? wave + 1 : waves) : nullptr;

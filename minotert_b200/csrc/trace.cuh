@@ -169,16 +169,45 @@ struct LaneState {
 #define TRACE_KNEAR 0.99999952f
 #define TRACE_KFAR 1.00000048f
 
-MRT_D void lane_begin(LaneState& L, float3 o, float3 d) {
+// What lane_begin derives from a ray's direction alone: six IEEE divisions (1/d per axis, the shear) and the octant.  Rays
+// the shade stage generates can carry it (option "prepared_rays": computed there by full warps, read back here as two
+// 16-byte loads) instead of having it recomputed by the ~7 lanes of a refill.
+struct RayPre {
+    float3 idir;
+    RayShear rs;
+    unsigned oct_inv;
+};
+MRT_D RayPre ray_prepare(float3 d) {
     const float tiny = 1e-20f;
     float3 dd = f3(fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x), fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y),
                    fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-    float3 idir = f3(1.0f / dd.x, 1.0f / dd.y, 1.0f / dd.z);
+    RayPre r;
+    r.idir = f3(1.0f / dd.x, 1.0f / dd.y, 1.0f / dd.z);
+    r.oct_inv = 7u - ((r.idir.x < 0.0f ? 1u : 0u) | (r.idir.y < 0.0f ? 2u : 0u) | (r.idir.z < 0.0f ? 4u : 0u));
+    r.rs = make_shear(d);
+    return r;
+}
+// the two queue words next to origin and direction: (1/d, Sx) and (Sy, Sz, kx | ky << 2 | kz << 4 | oct_inv << 8, -)
+MRT_D void ray_pre_pack(const RayPre& r, float4& a, float4& b) {
+    a = make_float4(r.idir.x, r.idir.y, r.idir.z, r.rs.Sx);
+    b = make_float4(r.rs.Sy, r.rs.Sz, __uint_as_float((unsigned)r.rs.kx | ((unsigned)r.rs.ky << 2) | ((unsigned)r.rs.kz << 4) | (r.oct_inv << 8)), 0.0f);
+}
+MRT_D RayPre ray_pre_unpack(float4 a, float4 b) {
+    RayPre r;
+    r.idir = f3(a.x, a.y, a.z);
+    const unsigned k = __float_as_uint(b.z);
+    r.rs.kx = (int)(k & 3u); r.rs.ky = (int)((k >> 2) & 3u); r.rs.kz = (int)((k >> 4) & 3u);
+    r.rs.Sx = a.w; r.rs.Sy = b.x; r.rs.Sz = b.y;
+    r.oct_inv = k >> 8;
+    return r;
+}
+
+MRT_D void lane_begin_prepared(LaneState& L, float3 o, const RayPre& pre) {
     L.o = o;
-    L.idn = idir * TRACE_KNEAR;
-    L.idf = idir * TRACE_KFAR;
-    L.oct_inv = 7u - ((idir.x < 0.0f ? 1u : 0u) | (idir.y < 0.0f ? 2u : 0u) | (idir.z < 0.0f ? 4u : 0u));
-    L.rs = make_shear(d);
+    L.idn = pre.idir * TRACE_KNEAR;
+    L.idf = pre.idir * TRACE_KFAR;
+    L.oct_inv = pre.oct_inv;
+    L.rs = pre.rs;
     L.ng = make_uint2(0u, 0x80000000u);  // root "group": node 0, one pending inner hit
     L.tg = make_uint2(0u, 0u);
     L.tgmask = 0u;
@@ -188,6 +217,7 @@ MRT_D void lane_begin(LaneState& L, float3 o, float3 d) {
     L.hit.t = 3.0e38f; L.hit.tri = MRT_MISS_ID; L.hit.prim = MRT_MISS_ID;
     L.tlimit = 3.0e38f;
 }
+MRT_D void lane_begin(LaneState& L, float3 o, float3 d) { lane_begin_prepared(L, o, ray_prepare(d)); }
 
 // float 2^15 + (byte `sel` of w).  K = 0x47000000 is passed in a register so that the selector can be the
 // immediate operand of PRMT (otherwise ptxas keeps four selectors in uniform registers and copies them).
@@ -521,6 +551,7 @@ MRT_D void warp_tri_step_coop(LaneState& L, const BvhDev& bvh, TraceCounters& cn
 // Persistent warp loop.  Job supplies the rays and consumes the hits:
 //   uint32_t Job::count() const;                          rays in this wave
 //   bool     Job::load(uint32_t i, float3& o, float3& d); false => ray i does not exist (padding)
+//   bool     Job::load_prepared(uint32_t i, float3& o, RayPre& pre);  true => the queue carries ray_prepare's results for ray i
 //   void     Job::store(uint32_t i, const TraceHit& h);
 //   static constexpr bool Job::ANY_HIT;                   true: occlusion query, the ray ends at its first hit
 // work_counter: global counter of handed-out rays (zeroed before the launch).
@@ -562,7 +593,12 @@ MRT_D void trace_persistent(const BvhDev& bvh, Job& job, uint32_t* work_counter,
                     if (store_pending) { job.store(ray_index, L.hit); store_pending = false; }  // the lane's previous ray
 #endif
                     ray_index = mine;
-                    if (job.load(mine, o, d)) {
+                    RayPre pre;
+                    if (job.load_prepared(mine, o, pre)) {  // (a job without prepared rays returns false here, at compile time)
+                        lane_begin_prepared(L, o, pre);
+                        if (bvh.num_nodes == 0) L.ng.y = 0u;
+                        have_ray = true;
+                    } else if (job.load(mine, o, d)) {
                         lane_begin(L, o, d);
                         if (bvh.num_nodes == 0) L.ng.y = 0u;  // empty scene: finishes as a miss below
                         have_ray = true;
