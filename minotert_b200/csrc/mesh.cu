@@ -978,7 +978,7 @@ __global__ void k_sun_centre(mrt_atmosphere_params A, SkyLuts luts, float3 camer
 
 // Shade stage as its own kernel: one thread per path vertex.
 template <bool FIRST>
-__global__ void __launch_bounds__(256) k_shade(ShadeArgs a, const uint32_t* __restrict__ in_count_ptr) {
+__global__ void __launch_bounds__(256, 6) k_shade(ShadeArgs a, const uint32_t* __restrict__ in_count_ptr) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nfront = FIRST ? (a.P.first_tiles_x ? a.P.first_count : a.npix) : *in_count_ptr;
     const uint32_t count = nfront + ((!FIRST && a.in_back) ? *a.in_back : 0u);
