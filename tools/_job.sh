@@ -1,5 +1,9 @@
-timeout 900 python -m pytest tests/test_gpu_mesh.py tests/test_gpu_nee.py tests/test_gpu_sizes.py -x -q -m gpu 2>&1 | tail -2
-python tools/check_option.py hall_260k 1921 1079 2 3 prepared_rays=0 2>&1 | tail -2
-for w in hall_260k_1080p scene_1m_1080p; do for v in 1 0 1 0; do tools/ab.sh prep${v}_$w --no-extra-configs --workload $w --opt prepared_rays=$v; done; done
-tools/ab.sh prep1_10m --no-extra-configs --workload scene_10m_4k --steps 4 --opt prepared_rays=1
-tools/ab.sh prep0_10m --no-extra-configs --workload scene_10m_4k --steps 4 --opt prepared_rays=0
+set +e
+tools/profile.sh launches r2_hall
+tools/profile.sh kernel r2_trace_hall "k_trace" 12 2
+tools/profile.sh kernel r2_shade_hall "k_shade" 10 3
+tools/profile.sh kernel r2_trace_1m "k_trace" 6 1 --workload scene_1m_1080p
+tools/profile.sh kernel r2_trace_10m "k_trace" 24 3 --workload scene_10m_4k --steps 1
+python tools/agg_launches.py gpurun_out/launches_r2_hall.csv > gpurun_out/launches_r2_hall_summary.txt; tail -30 gpurun_out/launches_r2_hall_summary.txt
+rm -f gpurun_out/ncu_r2_trace_*.ncu-rep gpurun_out/ncu_r2_shade_hall.ncu-rep
+python tools/bench_build.py --scenes hall_260k scene_1m > gpurun_out/r2_build.jsonl 2>/dev/null; grep -c . gpurun_out/r2_build.jsonl
