@@ -1016,6 +1016,9 @@ struct CollapseLoop {
     uint32_t n;               // primitives = node budget
 };
 #define MAX_WIDE_LEVELS 1023u
+#ifndef COLLAPSE_TOP_IN_ONE_CTA
+#define COLLAPSE_TOP_IN_ONE_CTA 0  // A/B (1 M / 260 k triangles): 1.257 vs 1.265 ms, 0.763 vs 0.748 ms -- no gain, off
+#endif
 
 
 // exclusive scan of in[first .. first+count) across the grid; calls emit(index, exclusive prefix) for every element
@@ -1068,6 +1071,60 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop 
         }
     }
     grid.sync();
+#if COLLAPSE_TOP_IN_ONE_CTA
+    // The top of the wide tree (levels of <= 128 nodes: the first three of a large scene, all of a small one) inside CTA 0,
+    // with CTA barriers and a CTA-wide scan: a level costs its expansion chain and ~1 us instead of three grid barriers and
+    // a grid-wide scan (~15 us less per level).  Same nodes in the same order.  The other CTAs wait for the state at one barrier.
+    {
+        uint32_t* const state = A.level_starts + MAX_WIDE_LEVELS + 1;  // level_start, level_count, levels, cur | status << 8
+        if (blockIdx.x == 0) {
+            while (status == 0 && level_count > 0 && level_count <= LOOP_THREADS / 8u) {
+                if ((size_t)level_start + level_count > A.n) { status = 1; break; }
+                if (threadIdx.x == 0 && levels < MAX_WIDE_LEVELS) A.level_starts[levels] = level_start;
+                const uint2* items = A.items[cur];
+                uint2* next_items = A.items[cur ^ 1];
+                {
+                    const uint32_t k = threadIdx.x >> 3;
+                    const bool active = k < level_count;
+                    const uint2 item = active ? items[k] : make_uint2((uint32_t)A.T.root, 0u);
+                    collapse_expand_group(A.T, A.rec, active, (int)item.x, item.y, A.slot_node, A.node_nchild, A.node_ntri);
+                }
+                __syncthreads();
+                const uint32_t next_start = level_start + level_count;
+                const bool mine = threadIdx.x < level_count;
+                const uint32_t w = level_start + threadIdx.x;
+                uint32_t next_count;
+                const uint32_t child_off = cta_scan(mine ? A.node_nchild[w] : 0u, &next_count);
+                if (mine) {
+                    const uint32_t base = next_start + child_off;
+                    A.node_child_base[w] = base;
+                    uint32_t rel = 0;
+                    for (int s = 0; s < 8; s++) {
+                        const int c = A.slot_node[(size_t)w * 8 + s];
+                        if (c < 0) continue;
+                        if (bin_count(A.T, c) > MRT_MAX_LEAF_TRIS) {
+                            next_items[base - next_start + rel] = make_uint2((uint32_t)c, base + rel);
+                            rel++;
+                        }
+                    }
+                }
+                __syncthreads();
+                if ((size_t)next_start + next_count > A.n) { status = 1; break; }
+                level_start = next_start;
+                level_count = next_count;
+                cur ^= 1;
+                levels++;
+            }
+            if (threadIdx.x == 0) {
+                state[0] = level_start; state[1] = level_count; state[2] = levels; state[3] = (uint32_t)cur | (status << 8);
+            }
+        }
+        grid.sync();
+        level_start = state[0]; level_count = state[1]; levels = state[2];
+        cur = (int)(state[3] & 0xFFu); status = state[3] >> 8;
+        if (status != 0) level_count = 0;
+    }
+#endif
     while (level_count > 0) {
         if ((size_t)level_start + level_count > A.n) { status = 1; break; }
         if (gtid == 0 && levels < MAX_WIDE_LEVELS) A.level_starts[levels] = level_start;
@@ -1620,8 +1677,8 @@ int bvh_build_full(mrt_context* ctx) {
         MRT_TRY(dev_reserve(ctx, ctx->bin_rec, n));
         A.rec = ctx->bin_rec.p;
         if (ctx->level_starts_dev.p == nullptr) {  // first use: the tail of the table beyond the tree's depth is copied to the host too
-            MRT_TRY(dev_reserve(ctx, ctx->level_starts_dev, MAX_WIDE_LEVELS + 1));
-            MRT_CUDA(ctx, cudaMemsetAsync(ctx->level_starts_dev.p, 0, sizeof(uint32_t) * (MAX_WIDE_LEVELS + 1), ctx->stream));
+            MRT_TRY(dev_reserve(ctx, ctx->level_starts_dev, MAX_WIDE_LEVELS + 1 + 8));  // + the state CTA 0 hands to the grid
+            MRT_CUDA(ctx, cudaMemsetAsync(ctx->level_starts_dev.p, 0, sizeof(uint32_t) * (MAX_WIDE_LEVELS + 1 + 8), ctx->stream));
         }
         A.level_starts = ctx->level_starts_dev.p;
         void* args[] = {&A};
