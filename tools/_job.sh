@@ -1,9 +1,2 @@
-out=gpurun_out/sanitizer_r2c_spheres.txt
-: > $out
-run() { echo "== $1" >> $out; shift; timeout 1200 "$@" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|hazard|Invalid|Uninit|error" | head -12 >> $out; }
-KS='batched and not size0'
-run memcheck_spheres compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_spheres.py -m gpu -q -x -k "$KS"
-run racecheck_spheres compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_spheres.py -m gpu -q -x -k "$KS"
-run synccheck_spheres compute-sanitizer --tool synccheck python -m pytest tests/test_gpu_spheres.py -m gpu -q -x -k "$KS"
-run initcheck_spheres compute-sanitizer --tool initcheck python -m pytest tests/test_gpu_spheres.py -m gpu -q -x -k "$KS"
-cat $out
+for v in variants/rf3 variants/rf4 variants/rf8; do for w in hall_260k_1080p scene_1m_1080p; do MINOTERT_LIB_DIR=$v tools/ab.sh $(basename $v)_$w --no-extra-configs --workload $w; done; done
+for w in hall_260k_1080p scene_1m_1080p; do tools/ab.sh base_$w --no-extra-configs --workload $w; done
