@@ -119,15 +119,17 @@ __global__ void __launch_bounds__(RS_THREADS)
 k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
              uint32_t* __restrict__ vals_out, size_t n, int shift, const uint32_t* __restrict__ offsets, uint32_t num_tiles) {
     __shared__ uint32_t wc[RS_WARPS][256];
-    __shared__ uint32_t gbase[256];
+    __shared__ uint32_t gbase[256], texcl[256];
+    __shared__ uint64_t skeys[RS_TILE];  // the tile in digit order: a warp's stores then walk runs of equal digits
+    __shared__ uint32_t svals[RS_TILE];  // (8 keys on average at 2048 keys per tile) instead of 32 different sectors
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wc[0][0])[i] = 0;
-    gbase[threadIdx.x] = offsets[(size_t)threadIdx.x * num_tiles + blockIdx.x];
     __syncthreads();
 
     uint64_t key[RS_ITEMS];
     uint32_t val[RS_ITEMS], loc[RS_ITEMS];
-    const size_t wbase = (size_t)blockIdx.x * RS_TILE + (size_t)warp * RS_WARP_SPAN;
+    const size_t tbase = (size_t)blockIdx.x * RS_TILE, wbase = tbase + (size_t)warp * RS_WARP_SPAN;
+    const uint32_t nvalid = (uint32_t)min((size_t)RS_TILE, n - min(n, tbase));
     const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
@@ -148,9 +150,9 @@ k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ 
         __syncwarp();
     }
     __syncthreads();
+    uint32_t run = 0;
     {
         // exclusive prefix over the tile's warps for digit = threadIdx.x
-        uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
             uint32_t c = wc[w][threadIdx.x];
@@ -158,15 +160,33 @@ k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ 
             run += c;
         }
     }
+    {
+        uint32_t all;
+        const uint32_t ex = block_exclusive_scan<RS_THREADS>(run, &all);  // where digit threadIdx.x starts inside the tile
+        texcl[threadIdx.x] = ex;
+        // global position of the tile's entry i of this digit: gbase + i (modulo 2^32)
+        gbase[threadIdx.x] = offsets[(size_t)threadIdx.x * num_tiles + blockIdx.x] - ex;
+    }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
         size_t i = wbase + (size_t)j * 32 + lane;
         if (i < n) {
             unsigned d = (unsigned)(key[j] >> shift) & 255u;
-            size_t pos = (size_t)gbase[d] + wc[warp][d] + loc[j];
-            keys_out[pos] = key[j];
-            vals_out[pos] = val[j];
+            const uint32_t lp = texcl[d] + wc[warp][d] + loc[j];
+            skeys[lp] = key[j];
+            svals[lp] = val[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        const uint32_t i = (uint32_t)j * RS_THREADS + threadIdx.x;
+        if (i < nvalid) {
+            const uint64_t k = skeys[i];
+            const size_t pos = (size_t)(uint32_t)(gbase[(unsigned)(k >> shift) & 255u] + i);
+            keys_out[pos] = k;
+            vals_out[pos] = svals[i];
         }
     }
 }
