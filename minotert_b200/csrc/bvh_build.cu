@@ -592,6 +592,108 @@ MRT_D uint2 ploc_round_fused(const PlocLoop& A, uint32_t m, int cur, uint32_t ne
     return total;
 }
 
+// The same idea for the LARGE rounds (a CTA's range spans several windows): per window, nearest neighbours for the window's
+// own positions plus one radius of halo, the mutual-pair test from shared memory, and one packed word per own position
+// -- keep, create, partner offset -- written where ploc_round keeps its neighbour index.  The counting pass of ploc_round
+// (its phase 2: two dependent loads per position, a grid barrier) is gone, and the merge phase reads one word instead of
+// chasing nn[i] and nn[nn[i]].  Same pairs, ids and boxes.
+template <class Sync>
+MRT_D uint2 ploc_round_windows(const PlocLoop& A, uint32_t m, int cur, uint32_t next_node, uint32_t b, uint32_t nb, float4* wlo,
+                                float4* whi, uint32_t* wnn, Sync sync) {
+    const uint32_t* C = A.clusters[cur];
+    uint32_t* Cout = A.clusters[cur ^ 1];
+    const int radius = ploc_radius_for(A.radius, m);
+    const uint32_t chunk = (m + nb - 1) / nb;
+    const uint32_t r0 = min(m, b * chunk), r1 = min(m, r0 + chunk);
+    const uint32_t own = (uint32_t)LOOP_THREADS - 4u * (uint32_t)radius;  // own positions per window
+    const int q = (int)threadIdx.x;
+    uint32_t keepc = 0, createc = 0;
+    for (uint32_t a = r0; a < r1; a += own) {
+        const uint32_t e = min(a + own, r1);
+        const int w0 = (int)a - 2 * radius, pos = w0 + q;
+        if (pos >= 0 && pos < (int)min(m, e + 2u * (uint32_t)radius)) {
+            const uint32_t c = C[pos];
+            wlo[q] = A.lo[c];
+            whi[q] = A.hi[c];
+        }
+        __syncthreads();
+        if (pos >= max(0, (int)a - radius) && pos < (int)min(m, e + (uint32_t)radius)) {
+            const int i = pos;
+            const float4 ilo = wlo[q], ihi = whi[q];
+            const int j0 = max(i - radius, 0), j1 = min(i + radius, (int)m - 1);
+            float best = 3.0e38f;
+            uint32_t bj = (uint32_t)i, bkey = 0xFFFFFFFFu;
+            for (int j = j0; j <= j1; j++) {  // same pair order and tie-break as ploc_round
+                if (j == i) continue;
+                const float ar = merged_area(ilo, ihi, wlo[j - w0], whi[j - w0]);
+                const uint32_t dist = (uint32_t)abs(j - i);
+                const uint32_t lowpos = (uint32_t)min(j, i);
+                const uint32_t key = (dist << 26) | ((lowpos & 1u) << 25) | (lowpos & 0x1FFFFFFu);
+                if (ar < best || (ar == best && key < bkey)) { best = ar; bj = (uint32_t)j; bkey = key; }
+            }
+            wnn[q] = bj;
+        }
+        __syncthreads();
+        if (pos >= (int)a && pos < (int)e) {
+            const uint32_t i = (uint32_t)pos, j = wnn[q];
+            const bool mutual = j != i && wnn[(int)j - w0] == i;
+            const bool keep = !(mutual && i > j), create = mutual && i < j;
+            keepc += keep ? 1u : 0u;
+            createc += create ? 1u : 0u;
+            A.nn[i] = (keep ? 1u : 0u) | (create ? 2u : 0u) | ((uint32_t)((int)j - (int)i + 64) << 2);  // |j - i| <= radius <= 32
+        }
+        __syncthreads();  // the window is refilled
+    }
+    const uint2 mine = cta_sum2(keepc, createc);
+    if (threadIdx.x == 0) A.block_sums[b] = mine;
+    sync();
+    uint32_t kb = 0, cb = 0, kt = 0, ct = 0;
+    for (uint32_t k = threadIdx.x; k < nb; k += LOOP_THREADS) {
+        const uint2 sq = A.block_sums[k];
+        kt += sq.x; ct += sq.y;
+        if (k < b) { kb += sq.x; cb += sq.y; }
+    }
+    const uint2 before = cta_sum2(kb, cb), total = cta_sum2(kt, ct);
+    uint32_t keep_base = before.x, create_base = before.y;
+    const int nprims = (int)A.n;
+    for (uint32_t base = r0; base < r1; base += LOOP_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        bool keep = false, create = false;
+        uint32_t j = 0;
+        if (i < r1) {
+            const uint32_t f = A.nn[i];  // written by this CTA (this thread's CTA owns [r0, r1)) before the barrier
+            keep = (f & 1u) != 0u;
+            create = (f & 2u) != 0u;
+            j = (uint32_t)((int)i + (int)(f >> 2) - 64);
+        }
+        uint32_t tile_total;
+        const uint32_t ex = cta_scan((keep ? 1u : 0u) | (create ? 0x10000u : 0u), &tile_total);
+        if (keep) {
+            uint32_t c = C[i];
+            if (create) {
+                const uint32_t cj = C[j];
+                const uint32_t id = next_node + create_base + (ex >> 16);
+                const float4 alo = A.lo[c], ahi = A.hi[c], blo = A.lo[cj], bhi = A.hi[cj];
+                A.left[id] = (int32_t)c;
+                A.right[id] = (int32_t)cj;
+                A.parent[c] = (int32_t)id;
+                A.parent[cj] = (int32_t)id;
+                A.parent[id] = -1;
+                const uint32_t na = (int)c >= nprims - 1 ? 1u : A.count[c], nbb = (int)cj >= nprims - 1 ? 1u : A.count[cj];
+                A.count[id] = na + nbb;
+                A.lo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+                A.hi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+                c = id;
+            }
+            Cout[keep_base + (ex & 0xFFFFu)] = c;
+        }
+        keep_base += tile_total & 0xFFFFu;
+        create_base += tile_total >> 16;
+    }
+    sync();
+    return total;
+}
+
 // The last rounds (<= LOOP_THREADS clusters, CTA 0 alone) with the cluster list in SHARED memory: ids, boxes and primitive
 // counts are loaded once, a round is a neighbour search, a mutual-pair test and an in-place compaction between CTA
 // barriers, and the only global traffic left is the record of each new node going out (nothing waits for it).  The
@@ -695,7 +797,7 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_ploc_loop(PlocLoop A) {
 #if PLOC_FUSED_ROUNDS && PLOC_SMEM_TAIL
         const bool fused = (m + nb - 1) / nb + 4u * (uint32_t)ploc_radius_for(A.radius, m) <= (uint32_t)LOOP_THREADS;
         const uint2 t = fused ? ploc_round_fused(A, m, cur, next_node, b, nb, wlo, whi, tail_cid, tail_cnt, tail_nn, [&] { grid.sync(); })
-                              : ploc_round(A, m, cur, next_node, b, nb, wlo, whi, [&] { grid.sync(); });
+                              : ploc_round_windows(A, m, cur, next_node, b, nb, wlo, whi, tail_nn, [&] { grid.sync(); });
 #else
         const uint2 t = ploc_round(A, m, cur, next_node, b, nb, wlo, whi, [&] { grid.sync(); });
 #endif
