@@ -949,8 +949,8 @@ MRT_D void collapse_expand_one(const BinTree& T, int b, uint32_t w, int32_t* slo
 // area of right), big = more than MRT_MAX_LEAF_TRIS primitives below -- so that opening a slot is ONE dependent load
 // instead of the child index followed by its count and box (the expansion is a chain of such loads, ~17 round trips
 // to L2 per node without the records, ~10 with them).  Same decisions: the areas are bin_area's own values.
-MRT_D void collapse_expand_group(const BinTree& T, const uint4* rec, bool active, int b, uint32_t w, int32_t* slot_node,
-                                 uint32_t* node_nchild, uint32_t* node_ntri) {
+MRT_D uint32_t collapse_expand_group(const BinTree& T, const uint4* rec, bool active, int b, uint32_t w, int32_t* slot_node,
+                                     uint32_t* node_nchild, uint32_t* node_ntri) {  // returns the node's child count (0 if !active)
     const unsigned FULL = 0xFFFFFFFFu;
     const int s = threadIdx.x & 7;
     int slot = -1;      // binary node in slot s
@@ -1061,13 +1061,14 @@ MRT_D void collapse_expand_group(const BinTree& T, const uint4* rec, bool active
         nchild += __shfl_xor_sync(FULL, nchild, d, 8);
         ntri += __shfl_xor_sync(FULL, ntri, d, 8);
     }
-    if (!active) return;
+    if (!active) return 0u;
     if (slot >= 0 && my_slot >= 0) slot_node[(size_t)w * 8 + my_slot] = slot;
     if (!(slot_done & (1u << s))) slot_node[(size_t)w * 8 + s] = -1;
     if (s == 0) {
         node_nchild[w] = nchild;
         node_ntri[w] = ntri;
     }
+    return nchild;
 }
 
 // One thread per wide node of the current level.
@@ -1118,6 +1119,9 @@ struct CollapseLoop {
     uint32_t n;               // primitives = node budget
 };
 #define MAX_WIDE_LEVELS 1023u
+#ifndef COLLAPSE_CHUNKED
+#define COLLAPSE_CHUNKED 0  // A/B (1 M / 260 k / 10.4 M triangles): 1.282 vs 1.202, 0.778 vs 0.719, 8.15 vs 7.92 ms -- one barrier less per level, yet slower: off
+#endif
 #ifndef COLLAPSE_TOP_IN_ONE_CTA
 #define COLLAPSE_TOP_IN_ONE_CTA 0  // A/B (1 M / 260 k triangles): 1.257 vs 1.265 ms, 0.763 vs 0.748 ms -- no gain, off
 #endif
@@ -1232,6 +1236,62 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop 
         if (gtid == 0 && levels < MAX_WIDE_LEVELS) A.level_starts[levels] = level_start;
         const uint2* items = A.items[cur];
         uint2* next_items = A.items[cur ^ 1];
+#if COLLAPSE_CHUNKED
+        // Every CTA expands a contiguous range of the level -- the range whose child counts it scans afterwards -- so its
+        // partial sum is known without reading the counts back: one grid barrier and one global round trip per level less
+        // than expand | barrier | grid_scan (sum, barrier, scan).
+        const uint32_t nbk = gridDim.x, bk = blockIdx.x;
+        const uint32_t chunk = (level_count + nbk - 1) / nbk;
+        const uint32_t r0 = min(level_count, bk * chunk), r1 = min(level_count, r0 + chunk);
+        uint32_t local = 0;
+        for (uint32_t k0 = r0; k0 < r1; k0 += LOOP_THREADS / 8u) {  // 8 lanes per node
+            const uint32_t k = k0 + (threadIdx.x >> 3);
+            const bool active = k < r1;
+            const uint2 item = active ? items[k] : make_uint2((uint32_t)A.T.root, 0u);
+            const uint32_t nc = collapse_expand_group(A.T, A.rec, active, (int)item.x, item.y, A.slot_node, A.node_nchild, A.node_ntri);
+            if ((threadIdx.x & 7u) == 0u) local += nc;
+        }
+        const uint32_t mine = cta_sum2(local, 0u).x;
+        if (threadIdx.x == 0) A.block_sums[bk] = mine;
+        PROF("collapse expand(cta0) level/count", levels, level_count);
+        grid.sync();
+        PROF("collapse expand-wait level/count", levels, level_count);
+        const uint32_t next_start = level_start + level_count;
+        uint32_t next_count;
+        {
+            uint32_t before = 0, all = 0;
+            for (uint32_t q = threadIdx.x; q < nbk; q += LOOP_THREADS) {
+                const uint32_t sq = A.block_sums[q];
+                all += sq;
+                if (q < bk) before += sq;
+            }
+            const uint2 sums = cta_sum2(before, all);
+            uint32_t base_off = sums.x;
+            next_count = sums.y;
+            for (uint32_t t0 = r0; t0 < r1; t0 += LOOP_THREADS) {
+                const uint32_t k = t0 + threadIdx.x;
+                const uint32_t w = level_start + k;
+                const uint32_t v = k < r1 ? A.node_nchild[w] : 0u;  // written by this CTA, before the barrier
+                uint32_t tile_total;
+                const uint32_t ex = cta_scan(v, &tile_total);
+                if (k < r1) {
+                    const uint32_t base = next_start + base_off + ex;
+                    A.node_child_base[w] = base;
+                    uint32_t rel = 0;
+                    for (int sl = 0; sl < 8; sl++) {
+                        const int c = A.slot_node[(size_t)w * 8 + sl];
+                        if (c < 0) continue;
+                        if (bin_count(A.T, c) > MRT_MAX_LEAF_TRIS) {
+                            next_items[base - next_start + rel] = make_uint2((uint32_t)c, base + rel);
+                            rel++;
+                        }
+                    }
+                }
+                base_off += tile_total;
+            }
+            grid.sync();
+        }
+#else
         for (uint32_t k0 = (gtid >> 5) * 4u; k0 < level_count; k0 += (gsize >> 5) * 4u) {  // a warp takes 4 nodes, 8 lanes each
             const uint32_t k = k0 + ((threadIdx.x & 31) >> 3);
             const bool active = k < level_count;
@@ -1257,6 +1317,7 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_collapse_loop(CollapseLoop 
                     }
                 }
             });
+#endif
         PROF("collapse scan+emit level/next", levels, next_count);
         if ((size_t)next_start + next_count > A.n) { status = 1; break; }
         level_start = next_start;
