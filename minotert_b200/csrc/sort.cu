@@ -365,7 +365,10 @@ int radix_sort_pairs_u64(mrt_context* ctx, uint64_t* keys, uint64_t* keys_alt, u
         // (8192 keys) up to 1.2 M keys on a B200; beyond that the launch-by-launch passes below
         if (ctx->fused_sort_capacity < 0) cudaDeviceGetAttribute(&ctx->fused_sort_capacity, cudaDevAttrMultiProcessorCount, ctx->device);
         const unsigned small = div_up(n, (size_t)256 * RS_ITEMS), large = div_up(n, (size_t)1024 * RS_ITEMS);
-        const unsigned ftiles = (int)small <= ctx->fused_sort_capacity ? small : large;
+#ifndef FUSED_SORT_SMALL_MAX
+#define FUSED_SORT_SMALL_MAX 1000000  // tiles of 2048 keys above which the 8192-key variant is used even though the small one would fit (A/B knob)
+#endif
+        const unsigned ftiles = ((int)small <= ctx->fused_sort_capacity && small <= (unsigned)FUSED_SORT_SMALL_MAX) ? small : large;
         if ((int)ftiles <= ctx->fused_sort_capacity) {
             const unsigned ngroups = div_up(ftiles, 32u);
             MRT_TRY(dev_reserve(ctx, ctx->hist, (size_t)256 * (ftiles + ngroups)));
